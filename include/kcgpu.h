@@ -1,0 +1,120 @@
+/* libkcgpu — C ABI of the B200-native `kmercamel compute` hot path.
+ *
+ * The reference (OndrejSladky/kmercamel) has no FFI boundary: its compute path is a chain of C++ templates inside
+ * one translation unit, src/main.cpp:122-212 kmercamel<kmer_t, kh_wrapper_t>():
+ *
+ *     ReadKMers / ReadKMersFiltered        src/parser.h:107,123        -> kc_count_kmers   (stage 1 alone)
+ *     get_simplitigs | simplitigs_from_fasta  src/simplitigs.h:192,89  \
+ *     Global / GlobalSparse                src/global.h:218, src/global_sparse.h:211  -> kc_compute (all stages)
+ *     OverlapHamiltonianPath[Sparse]       src/global.h:43, src/global_sparse.h:42     -> kc_overlap_path
+ *     kseq_read loop                       src/kseq.h:182-224, src/parser.h:106-118    -> kc_frame_fasta (host only)
+ *
+ * Conventions: plain C types only; every function returns 0 (KC_OK) or a negative KC_ERR_* code and never throws;
+ * one context per process and GPU; calls are synchronous and not thread-safe per context.  There is no CPU
+ * fallback: without a CUDA device kc_init fails with KC_ERR_NO_DEVICE.
+ *
+ * k-mer words cross the boundary as `limbs` little-endian uint64 limbs per k-mer, limbs = 1 (k < 32), 2 (k < 64),
+ * 4 (k < 128) — the reference's word widths (src/main.cpp:309-315); base i (0 = leftmost) sits at bits
+ * 2(k-1-i)+1..2(k-1-i), A=0 C=1 G=2 T=3 (src/kmers.h:15-32), so integer order is lexicographic order.
+ */
+#ifndef KCGPU_H
+#define KCGPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KC_OK 0
+#define KC_ERR_CUDA (-1)
+#define KC_ERR_ARG (-2)       /* bad parameter (k outside 1..127, min_frequency outside 1..255, -z with -S, ...) */
+#define KC_ERR_OOM (-3)
+#define KC_ERR_EMPTY (-4)     /* no k-mer in the input (reference src/main.cpp:155-158) / empty node list (src/global.h:219-221) */
+#define KC_ERR_BAD_SEQ (-5)   /* -S record with a non-ACGT byte (reference src/simplitigs.h:82 asserts) or shorter than k */
+#define KC_ERR_TOO_LARGE (-6) /* more than 2^32-2 virtual nodes or sequence bytes on one GPU */
+#define KC_ERR_INTERNAL (-7)
+#define KC_ERR_NO_DEVICE (-8)
+
+typedef struct kc_ctx kc_ctx;
+
+/* Flags of `kmercamel compute` (reference src/main.cpp:214-316). */
+typedef struct kc_params {
+    int k;                 /* -k, 1..127 */
+    int complements;       /* 1 = bidirectional (default), 0 = -u */
+    int min_frequency;     /* -z, 1..255; k-mers with fewer occurrences are dropped (src/khash_utils.h:143-151) */
+    int assume_simplitigs; /* -S: every record is one node, in input order (src/simplitigs.h:89-103) */
+    int want_maxone;       /* -M: also produce the max-one mask (src/global.h:185-195) */
+} kc_params;
+
+/* Framed input: the record sequences of the FASTA/FASTQ file (what kseq_read yields, src/kseq.h:182-224)
+ * concatenated in `seq`, each followed by exactly one '\n'.  rec_off[r] / rec_len[r] delimit record r.
+ * kc_frame_fasta produces this from raw file bytes.  For kc_compute the pointers are host pointers, for
+ * kc_compute_device they are device pointers (rec_off / rec_len are only read with assume_simplitigs). */
+typedef struct kc_input {
+    const uint8_t *seq;
+    uint64_t n_bytes;
+    const uint64_t *rec_off;
+    const uint64_t *rec_len;
+    uint64_t n_recs;
+} kc_input;
+
+typedef struct kc_stage_times { /* device time per stage in milliseconds (CUDA events on the context stream) */
+    float extract_ms;           /* bytes -> canonical k-mer occurrences */
+    float count_ms;             /* radix sort + dedup + count + -z filter */
+    float path_ms;              /* all overlap levels d = k-1..0 */
+    float emit_ms;              /* list ranking + character emission (+ max-one) */
+    float total_ms;
+} kc_stage_times;
+
+typedef struct kc_output {
+    uint8_t *ms;           /* the masked superstring, `length` bytes, no newline.  Upper case = mask 1. */
+    uint8_t *ms_maxone;    /* same characters with the max-one mask, or NULL without want_maxone */
+    uint64_t length;       /* "l=" of the reference log (src/global.h:225) */
+    uint64_t n_kmers;      /* distinct (canonical) k-mers kept after -z; 0 with assume_simplitigs unless want_maxone */
+    uint64_t n_occurrences;/* k-mer windows seen (M) */
+    uint64_t n_nodes;      /* nodes handed to the overlap stage (k-mers, or records with -S) */
+    uint64_t n_launches;   /* CUDA kernels launched by this call */
+    kc_stage_times t;
+} kc_output;
+
+/* device = CUDA ordinal; stream = a cudaStream_t to run on (e.g. torch's current stream), or NULL for a private one. */
+int kc_init(int device, void *stream, kc_ctx **out);
+void kc_destroy(kc_ctx *ctx);
+
+/* Whole path with HOST buffers: copies the input to the GPU, runs every stage, copies the result back into
+ * context-owned pinned buffers (valid until the next call on this context or kc_destroy). */
+int kc_compute(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *out);
+/* Same with DEVICE buffers in and out (outputs live in the context arena until the next call). */
+int kc_compute_device(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *out);
+
+/* Stage 1 only (host buffers): sorted distinct k-mers (n * limbs uint64) and min(occurrences-1, 255) per k-mer,
+ * after the -z filter.  Outputs are malloc'ed by the library; release with kc_free. */
+int kc_count_kmers(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t **keys, uint8_t **counts, uint64_t *n);
+
+/* Overlap stage only (host buffers).  first/last: n * limbs limbs.  edge_from: N = n * (1 + complements) entries,
+ * -1 = none; overlaps: N entries, 255 = none — the overlapPath of src/global.h:35.  strict = 1 reproduces the
+ * reference's tie order exactly; lower_bound = 1 is the cycle-cover mode of src/lower_bound.h. */
+int kc_overlap_path(kc_ctx *ctx, const uint64_t *first, const uint64_t *last, uint64_t n, int k, int complements,
+                    int lower_bound, int strict, int64_t *edge_from, uint8_t *overlaps);
+
+/* Host-only FASTA/FASTQ framing with kseq semantics (src/kseq.h:182-224 as driven by src/parser.h:106-118).
+ * Outputs are malloc'ed; release each with kc_free. */
+int kc_frame_fasta(const uint8_t *data, uint64_t n, uint8_t **seq, uint64_t *n_bytes, uint64_t **rec_off,
+                   uint64_t **rec_len, uint64_t *n_recs);
+
+/* Per-kernel-class device timing for roofline reports.  Enable, run kc_compute*, then read the table:
+ * names[i], milliseconds, launches, algorithmic bytes (read once + written once). */
+int kc_profile_enable(kc_ctx *ctx, int on);
+int kc_profile_count(void);
+int kc_profile_get(kc_ctx *ctx, int i, const char **name, double *ms, uint64_t *launches, uint64_t *bytes);
+int kc_profile_reset(kc_ctx *ctx);
+
+int kc_limbs_for_k(int k);
+void kc_free(void *p);
+const char *kc_strerror(int code);
+const char *kc_last_error(const kc_ctx *ctx); /* file:line detail of the last failure on this context */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

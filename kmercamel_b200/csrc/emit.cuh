@@ -1,0 +1,169 @@
+// Masked-superstring emission (reference src/global.h:149-210 SuperstringFromPath and its k-mer-node twin
+// src/global_sparse.h:137-202).
+//
+// The reference walks edgeFrom[] from the lowest-numbered node without a predecessor and streams characters.
+// Here the walk becomes a weighted list ranking (pointer doubling over edge_from with the number of characters
+// each node contributes as weight), after which every node of the printed strand knows its output offset and
+// all characters are written in parallel:
+//     node v contributes its first len(v) - overlap(v) bases: the first len(v)-k+1 of them upper case (a
+//     represented k-mer starts there), the rest lower case; the last node of the path contributes all len(v).
+// `-M` (max-one mask, src/global.h:185-195): a lower-case position outside the final k-1 becomes upper case
+// iff the k-mer that starts there in the superstring (or its reverse complement) is in the k-mer set; the
+// hash-set probe becomes a binary search in the sorted set.
+#pragma once
+#include "engine.cuh"
+
+template <int L> struct NodeSeq {
+    const KWord<L> *kmers;  // != nullptr: node v < n is the single k-mer kmers[v]
+    const u8 *seq;          // otherwise node v < n is the record seq[rec_off[v] .. +rec_len[v])
+    const u64 *rec_off, *rec_len;
+    u32 n;
+    int k;
+    KC_HD u64 length(u32 v) const { return kmers ? (u64) k : rec_len[v < n ? v : v - n]; }
+    // 2-bit symbol at position pos of virtual node v (v >= n: reverse complement, src/global.h:24-25)
+    KC_HD u32 symbol(u32 v, u64 pos) const {
+        if (kmers) {
+            if (v < n) return kmer_symbol(kmers[v], k, (int) pos);
+            return 3u - kmer_symbol(kmers[v - n], k, k - 1 - (int) pos);
+        }
+        if (v < n) return kc_nucleotide_code(seq[rec_off[v] + pos]);
+        u32 u = v - n;
+        return 3u - kc_nucleotide_code(seq[rec_off[u] + rec_len[u] - 1 - pos]);
+    }
+};
+
+KC_HD u8 kc_letter(u32 sym, bool upper) {
+    const u32 packed = 'A' | ('C' << 8) | ('G' << 16) | ('T' << 24);  // src/kmers.h:97 letters
+    u8 c = (u8) (packed >> (8 * sym));
+    return upper ? c : (u8) (c + ('a' - 'A'));  // src/kmers.h:124-127 Masked
+}
+
+// first index in [0, n) with keys[i] >= x
+template <int L> KC_HD u64 kmer_lower_bound(const KWord<L> *keys, u64 n, const KWord<L> &x) {
+    u64 lo = 0, hi = n;
+    while (lo < hi) {
+        u64 mid = (lo + hi) >> 1;
+        if (keys[mid] < x) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+struct EmitResult {
+    u8 *ms = nullptr;      // device, `length` bytes
+    u8 *maxone = nullptr;  // device, `length` bytes, or nullptr
+    u64 length = 0;
+    u64 n_printed = 0;     // nodes on the printed strand
+};
+
+// set_keys: sorted distinct (canonical when complements) k-mers, needed only for want_maxone.
+template <class Exec, int L>
+EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L> &nv, const PathState &st,
+                               const KWord<L> *set_keys, u64 n_set, bool want_maxone) {
+    EmitResult res;
+    const u64 N = nv.N;
+    const int k = nv.k;
+    size_t mark = ex.arena->mark();
+    u32 *jump_a = ex.template alloc<u32>(N), *jump_b = ex.template alloc<u32>(N);
+    u32 *fin_a = ex.template alloc<u32>(N), *fin_b = ex.template alloc<u32>(N);
+    u64 *dist_a = ex.template alloc<u64>(N), *dist_b = ex.template alloc<u64>(N);
+    u64 *cell = ex.template alloc<u64>(2);
+    const PathState s = st;
+    const NodeSeq<L> q = ns;
+    ex.fill_bytes(cell, 0xFF, 16);
+    ex.for_each(N, [=] KC_HD_LAMBDA(u64 vv) {
+        u32 v = (u32) vv;
+        u32 nx = s.edge_from[v];
+        jump_a[v] = nx;
+        fin_a[v] = v;
+        dist_a[v] = q.length(v) - (nx != KC_NONE ? (u64) s.ovl[v] : 0);  // characters contributed by v
+        if (s.edge_to[v] == KC_NONE) KC_ATOMIC_MIN((kc_ull *) &cell[0], (kc_ull) v);  // src/global.h:156-161 start
+    });
+    int rounds = kc_ceil_log2(N) + 1;
+    for (int it = 0; it < rounds; ++it) {
+        const u32 *ja = jump_a, *fa = fin_a;
+        const u64 *da = dist_a;
+        u32 *jb = jump_b, *fb = fin_b;
+        u64 *db = dist_b;
+        ex.for_each(N, [=] KC_HD_LAMBDA(u64 v) {
+            u32 j = ja[v];
+            if (j == KC_NONE) {
+                jb[v] = KC_NONE;
+                fb[v] = fa[v];
+                db[v] = da[v];
+            } else {
+                jb[v] = ja[j];
+                fb[v] = fa[j];
+                db[v] = da[v] + da[j];
+            }
+        });
+        u32 *t = jump_a; jump_a = jump_b; jump_b = t;
+        t = fin_a; fin_a = fin_b; fin_b = t;
+        u64 *m = dist_a; dist_a = dist_b; dist_b = m;
+    }
+    u64 start = ex.read(cell);
+    if (start >= N) KC_THROW(KC_ERR_INTERNAL, "no start node: the path cover contains only cycles");
+    {
+        const u32 *ja = jump_a;
+        ex.for_each(N, [=] KC_HD_LAMBDA(u64 v) {
+            if (ja[v] != KC_NONE) cell[1] = 0;  // a cycle survived: engine bug
+        });
+        if (ex.read(cell + 1) == 0) KC_THROW(KC_ERR_INTERNAL, "cycle in the final path cover");
+    }
+    const u64 total = ex.read(dist_a + start);
+    const u32 fin_start = ex.read(fin_a + start);
+    // results live below the scratch: release the scratch first, then allocate outputs, then re-reserve scratch
+    // is not possible with a bump arena, so outputs are allocated after the scratch and the scratch is leaked
+    // until the caller releases its own mark.
+    u8 *ms = ex.template alloc<u8>(total + 1);
+    res.ms = ms;
+    res.length = total;
+    const u32 *fa = fin_a;
+    const u64 *da = dist_a;
+    if (ns.kmers) {
+        ex.for_each(N, [=] KC_HD_LAMBDA(u64 vv) {
+            u32 v = (u32) vv;
+            if (fa[v] != fin_start) return;
+            u64 off = total - da[v];
+            u32 cnt = (u32) (k - (s.edge_from[v] != KC_NONE ? (int) s.ovl[v] : 0));
+            KWord<L> x = q.kmers[v < q.n ? v : v - q.n];
+            if (v >= q.n) x = kmer_reverse_complement(x, k);
+            for (u32 j = 0; j < cnt; ++j) ms[off + j] = kc_letter(kmer_symbol(x, k, (int) j), j == 0);
+        });
+    } else {
+        // one warp-sized group of 32 consecutive work items per node: coalesced writes for long records
+        ex.for_each(N * 32, [=] KC_HD_LAMBDA(u64 w) {
+            u32 v = (u32) (w >> 5), lane = (u32) (w & 31);
+            if (fa[v] != fin_start) return;
+            u64 off = total - da[v];
+            u64 len = q.length(v);
+            u64 cnt = len - (s.edge_from[v] != KC_NONE ? (u64) s.ovl[v] : 0);
+            u64 n_upper = len - k + 1;
+            for (u64 j = lane; j < cnt; j += 32) ms[off + j] = kc_letter(q.symbol(v, j), j < n_upper);
+        });
+    }
+    if (want_maxone) {
+        u8 *mo = ex.template alloc<u8>(total + 1);
+        res.maxone = mo;
+        const bool complements = nv.complements;
+        ex.for_each(total, [=] KC_HD_LAMBDA(u64 p) {
+            u8 c = ms[p];
+            if (c <= 'Z' || p + k > total) {  // already ON, or inside the trailing k-1 (src/global.h:200-208)
+                mo[p] = c;
+                return;
+            }
+            KWord<L> x = KWord<L>::zero();
+            for (int i = 0; i < k; ++i) x = x.shl(2) | KWord<L>::from_u64(kc_nucleotide_code(ms[p + i]));
+            if (complements) {
+                KWord<L> r = kmer_reverse_complement(x, k);
+                if (r < x) x = r;
+            }
+            u64 pos = kmer_lower_bound(set_keys, n_set, x);
+            bool present = pos < n_set && set_keys[pos] == x;  // src/khash_utils.h:98-103 containsKMer
+            mo[p] = present ? (u8) (c - ('a' - 'A')) : c;
+        });
+    }
+    res.n_printed = nv.n;  // one strand: every node or its mirror
+    (void) mark;
+    return res;
+}

@@ -1,0 +1,70 @@
+// Common definitions for libkcgpu: error handling, device arena, small helpers.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cuda_runtime.h>
+
+#include "../../include/kcgpu.h"
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int64_t i64;
+
+#define KC_HD __host__ __device__ __forceinline__
+#define KC_D __device__ __forceinline__
+#define KC_HD_LAMBDA __host__ __device__
+
+// Status codes of the C ABI: KC_OK / KC_ERR_* from include/kcgpu.h.
+
+struct KcError {
+    int code;
+    const char *what;
+    const char *file;
+    int line;
+};
+
+#define KC_THROW(code_, what_) throw KcError{(code_), (what_), __FILE__, __LINE__}
+
+#define KC_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t kc_e_ = (expr);                                                           \
+        if (kc_e_ != cudaSuccess) {                                                           \
+            cudaError_t kc_last_ = cudaGetLastError();                                        \
+            (void) kc_last_;                                                                  \
+            throw KcError{kc_e_ == cudaErrorMemoryAllocation ? KC_ERR_OOM : KC_ERR_CUDA,      \
+                          cudaGetErrorString(kc_e_), __FILE__, __LINE__};                     \
+        }                                                                                     \
+    } while (0)
+
+static const u32 KC_NONE = 0xFFFFFFFFu;
+
+KC_HD u64 kc_div_up(u64 a, u64 b) { return (a + b - 1) / b; }
+KC_HD u64 kc_align_up(u64 a, u64 b) { return (a + b - 1) / b * b; }
+inline int kc_ceil_log2(u64 x) {
+    int r = 0;
+    while ((1ULL << r) < x) ++r;
+    return r;
+}
+
+// Bump allocator over one device (or, in the host-emulation test build, host) slab.  All temporaries of a
+// kc_compute call live here so the timed path never calls cudaMalloc.
+struct Arena {
+    char *base = nullptr;
+    size_t cap = 0;
+    size_t off = 0;
+    size_t high = 0;
+    template <typename T> T *alloc(size_t n) {
+        size_t bytes = kc_align_up((n ? n : 1) * sizeof(T), 256);
+        if (off + bytes > cap) KC_THROW(KC_ERR_OOM, "device arena exhausted");
+        T *p = reinterpret_cast<T *>(base + off);
+        off += bytes;
+        if (off > high) high = off;
+        return p;
+    }
+    size_t mark() const { return off; }
+    void release(size_t m) { off = m; }
+};

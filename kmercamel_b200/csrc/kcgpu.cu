@@ -1,0 +1,465 @@
+// libkcgpu: C ABI (include/kcgpu.h) over the CUDA pipeline.  Only CudaExec is instantiated here: the library has
+// no CPU path and fails with KC_ERR_NO_DEVICE when no GPU is present.
+#include "../../include/kcgpu.h"
+
+#include "emit.cuh"
+#include "engine.cuh"
+#include "exec.cuh"
+#include "kword.cuh"
+#include "sort.cuh"
+#include "stage1.cuh"
+
+#include <new>
+#include <string>
+
+struct kc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    Arena arena;
+    KernelProf prof;
+    // pinned host staging for kc_compute (grown on demand, reused across calls)
+    u8 *pin_in = nullptr;
+    size_t pin_in_cap = 0;
+    u8 *pin_out = nullptr;
+    size_t pin_out_cap = 0;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::string last_error;
+};
+
+namespace {
+
+void set_error(kc_ctx *ctx, const KcError &e) {
+    if (!ctx) return;
+    char buf[512];
+    std::snprintf(buf, sizeof(buf), "%s (%s:%d)", e.what, e.file, e.line);
+    ctx->last_error = buf;
+}
+
+#define KC_API_BEGIN try {
+#define KC_API_END(ctx)                                                \
+    }                                                                  \
+    catch (const KcError &e) {                                         \
+        set_error((ctx), e);                                           \
+        return e.code;                                                 \
+    }                                                                  \
+    catch (const std::bad_alloc &) {                                   \
+        if (ctx) (ctx)->last_error = "host allocation failed";         \
+        return KC_ERR_OOM;                                             \
+    }                                                                  \
+    catch (...) {                                                      \
+        if (ctx) (ctx)->last_error = "unknown failure";                \
+        return KC_ERR_INTERNAL;                                        \
+    }
+
+void check_params(const kc_params *p) {
+    if (!p) KC_THROW(KC_ERR_ARG, "params is NULL");
+    if (p->k < 1 || p->k > 127) KC_THROW(KC_ERR_ARG, "k must be in 1..127");                          // src/main.cpp:93,285-292
+    if (p->min_frequency < 1 || p->min_frequency > 255) KC_THROW(KC_ERR_ARG, "min_frequency must be in 1..255");  // :302-304
+    if (p->min_frequency != 1 && p->assume_simplitigs) KC_THROW(KC_ERR_ARG, "-z is not compatible with -S");   // :305-308
+}
+
+// Make sure the arena can hold `need` bytes (bounded by what the device can give).
+void ensure_arena(kc_ctx *ctx, size_t need) {
+    if (ctx->arena.cap >= need) return;
+    if (ctx->arena.base) {
+        KC_CUDA(cudaFree(ctx->arena.base));
+        ctx->arena.base = nullptr;
+        ctx->arena.cap = 0;
+    }
+    size_t free_b = 0, total_b = 0;
+    KC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t limit = (size_t) (free_b * 0.92);
+    size_t want = need < limit ? need : limit;
+    KC_CUDA(cudaMalloc(&ctx->arena.base, want));
+    ctx->arena.cap = want;
+    ctx->arena.off = 0;
+}
+
+// Generous upper estimate of the arena bytes one kc_compute needs (see DESIGN.md "memory").
+size_t estimate_arena(u64 n_bytes, u64 n_recs, int limbs, bool complements, bool simplitigs) {
+    const double wb = 8.0 * limbs;
+    const double c = complements ? 2.0 : 1.0;
+    double stage1 = n_bytes * (1.0 + 2.0 * wb + 4.0);
+    double nodes = simplitigs ? (double) n_recs : (double) n_bytes;
+    double N = c * nodes;
+    double engine = N * (60.0 + 2.0 * 2.0 * (wb + 8.0) + 12.0 + 40.0);
+    double emit = N * 32.0 + 3.0 * n_bytes;
+    double total = (stage1 + engine + emit) * 1.15 + (256u << 20);
+    return (size_t) total;
+}
+
+struct DevInput {
+    const u8 *seq;
+    u64 n_bytes;
+    const u64 *rec_off, *rec_len;
+    u64 n_recs;
+};
+
+struct DevResult {
+    const u8 *ms = nullptr, *maxone = nullptr;
+    u64 length = 0, n_kmers = 0, n_occ = 0, n_nodes = 0;
+};
+
+// Stage 1.  Leaves the sorted distinct k-mers (and their counts) at the current arena top and returns them.
+template <int L> u64 run_stage1(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, KWord<L> **uniq_out, u8 **cnt_out,
+                               u64 *n_occ) {
+    const size_t base_mark = ex.arena->mark();
+    KWord<L> *keys_a = ex.alloc<KWord<L>>(in.n_bytes);
+    KC_CUDA(cudaEventRecord(ctx->ev[0], ex.stream));
+    const u64 M = kc_extract_kmers<L>(ex, in.seq, in.n_bytes, p.k, p.complements != 0, keys_a);
+    KC_CUDA(cudaEventRecord(ctx->ev[1], ex.stream));
+    *n_occ = M;
+    if (M == 0) {
+        ex.arena->release(base_mark);
+        *uniq_out = nullptr;
+        *cnt_out = nullptr;
+        KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
+        return 0;
+    }
+    ex.arena->release(base_mark);
+    keys_a = ex.alloc<KWord<L>>(M);  // same address, trimmed to M
+    KWord<L> *keys_b = ex.alloc<KWord<L>>(M);
+    u8 *cnt_a = ex.alloc<u8>(M);
+    u8 *cnt_b = ex.alloc<u8>(M);
+    const u64 U = kc_sort_dedup<L>(ex, keys_a, keys_b, cnt_a, keys_b, cnt_b, M, 2 * p.k, p.min_frequency);
+    // compact the survivors down to the stage's base so everything above can be reused
+    ex.arena->release(base_mark);
+    KWord<L> *uniq = ex.alloc<KWord<L>>(U);
+    u8 *cnt = ex.alloc<u8>(U);
+    if (U) {
+        // uniq = [base, base + U*W) never overlaps keys_b = base + M*W (U <= M); cnt lies below cnt_b as well
+        ex.copy_bytes(uniq, keys_b, U * sizeof(KWord<L>));
+        ex.copy_bytes(cnt, cnt_b, U);
+    }
+    KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
+    *uniq_out = uniq;
+    *cnt_out = cnt;
+    return U;
+}
+
+template <int L> void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, DevResult &res) {
+    const bool complements = p.complements != 0;
+    KWord<L> *uniq = nullptr;
+    u8 *cnt = nullptr;
+    u64 U = 0, n_occ = 0;
+    NodeView<L> nv;
+    NodeSeq<L> ns;
+    nv.k = p.k;
+    nv.complements = complements;
+    ns.k = p.k;
+    ns.kmers = nullptr;
+    ns.seq = in.seq;
+    ns.rec_off = in.rec_off;
+    ns.rec_len = in.rec_len;
+    if (!p.assume_simplitigs) {
+        U = run_stage1<L>(ctx, ex, in, p, &uniq, &cnt, &n_occ);
+        if (U == 0) KC_THROW(KC_ERR_EMPTY, "the input contains no k-mers");  // src/main.cpp:155-158
+        if (U * (complements ? 2 : 1) >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "too many k-mers for one GPU");
+        nv.first = nv.last = uniq;
+        nv.n = (u32) U;
+        ns.kmers = uniq;
+    } else {
+        if (in.n_recs == 0) KC_THROW(KC_ERR_EMPTY, "input cannot be empty");  // src/global.h:219-221
+        if (in.n_recs * (complements ? 2 : 1) >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "too many records for one GPU");
+        KC_CUDA(cudaEventRecord(ctx->ev[0], ex.stream));
+        if (p.want_maxone) {  // kMersDict of src/global.h:165-167 = every k-mer of the records
+            U = run_stage1<L>(ctx, ex, in, p, &uniq, &cnt, &n_occ);
+        } else {
+            KC_CUDA(cudaEventRecord(ctx->ev[1], ex.stream));
+            KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
+        }
+        KWord<L> *first = ex.alloc<KWord<L>>(in.n_recs), *last = ex.alloc<KWord<L>>(in.n_recs);
+        u32 *err = ex.alloc<u32>(1);
+        ex.fill_bytes(err, 0, 4);
+        kc_extract_node_ends<L>(ex, in.seq, in.n_bytes, in.rec_off, in.rec_len, in.n_recs, p.k, first, last, err);
+        if (ex.read(err)) KC_THROW(KC_ERR_BAD_SEQ, "-S input must hold only ACGT records of at least k bases");
+        nv.first = first;
+        nv.last = last;
+        nv.n = (u32) in.n_recs;
+    }
+    nv.N = nv.n * (complements ? 2u : 1u);
+    ns.n = nv.n;
+    Engine<CudaExec, L> eng(ex, nv, /*strict=*/p.assume_simplitigs != 0, /*lower_bound=*/false);
+    eng.init_state();
+    eng.run();
+    KC_CUDA(cudaEventRecord(ctx->ev[3], ex.stream));
+    EmitResult er = kc_emit_superstring<CudaExec, L>(ex, ns, nv, eng.st, uniq, U, p.want_maxone != 0);
+    KC_CUDA(cudaEventRecord(ctx->ev[4], ex.stream));
+    res.ms = er.ms;
+    res.maxone = er.maxone;
+    res.length = er.length;
+    res.n_kmers = U;
+    res.n_occ = n_occ;
+    res.n_nodes = nv.n;
+}
+
+void dispatch_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, DevResult &res) {
+    if (p.k < 32) run_pipeline<1>(ctx, ex, in, p, res);
+    else if (p.k < 64) run_pipeline<2>(ctx, ex, in, p, res);
+    else run_pipeline<4>(ctx, ex, in, p, res);
+}
+
+void fill_times(kc_ctx *ctx, kc_output *out) {
+    float t = 0;
+    out->t = kc_stage_times{0, 0, 0, 0, 0};
+    if (cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]) == cudaSuccess) out->t.extract_ms = t;
+    if (cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[2]) == cudaSuccess) out->t.count_ms = t;
+    if (cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3]) == cudaSuccess) out->t.path_ms = t;
+    if (cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[4]) == cudaSuccess) out->t.emit_ms = t;
+    if (cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[4]) == cudaSuccess) out->t.total_ms = t;
+    (void) cudaGetLastError();
+}
+
+template <int L>
+void count_only(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, uint64_t **keys, uint8_t **counts, uint64_t *n) {
+    KWord<L> *uniq = nullptr;
+    u8 *cnt = nullptr;
+    u64 n_occ = 0;
+    u64 U = run_stage1<L>(ctx, ex, in, p, &uniq, &cnt, &n_occ);
+    *n = U;
+    *keys = (uint64_t *) std::malloc(U ? U * sizeof(KWord<L>) : 8);
+    *counts = (uint8_t *) std::malloc(U ? U : 1);
+    if (!*keys || !*counts) KC_THROW(KC_ERR_OOM, "host allocation failed");
+    if (U) {
+        KC_CUDA(cudaMemcpyAsync(*keys, uniq, U * sizeof(KWord<L>), cudaMemcpyDeviceToHost, ex.stream));
+        KC_CUDA(cudaMemcpyAsync(*counts, cnt, U, cudaMemcpyDeviceToHost, ex.stream));
+    }
+    KC_CUDA(cudaStreamSynchronize(ex.stream));
+}
+
+template <int L>
+void overlap_only(CudaExec &ex, const uint64_t *first, const uint64_t *last, u64 n, int k, bool complements, bool lower_bound,
+                  bool strict, int64_t *edge_from, uint8_t *overlaps) {
+    KWord<L> *df = ex.alloc<KWord<L>>(n), *dl = ex.alloc<KWord<L>>(n);
+    KC_CUDA(cudaMemcpyAsync(df, first, n * sizeof(KWord<L>), cudaMemcpyHostToDevice, ex.stream));
+    KC_CUDA(cudaMemcpyAsync(dl, last, n * sizeof(KWord<L>), cudaMemcpyHostToDevice, ex.stream));
+    NodeView<L> nv;
+    nv.first = df;
+    nv.last = dl;
+    nv.n = (u32) n;
+    nv.N = nv.n * (complements ? 2u : 1u);
+    nv.k = k;
+    nv.complements = complements;
+    Engine<CudaExec, L> eng(ex, nv, strict, lower_bound);
+    eng.init_state();
+    eng.run();
+    std::vector<u32> ef(nv.N);
+    KC_CUDA(cudaMemcpyAsync(ef.data(), eng.st.edge_from, (size_t) nv.N * 4, cudaMemcpyDeviceToHost, ex.stream));
+    KC_CUDA(cudaMemcpyAsync(overlaps, eng.st.ovl, nv.N, cudaMemcpyDeviceToHost, ex.stream));
+    KC_CUDA(cudaStreamSynchronize(ex.stream));
+    for (u32 i = 0; i < nv.N; ++i) edge_from[i] = ef[i] == KC_NONE ? -1 : (int64_t) ef[i];
+}
+
+}  // namespace
+
+extern "C" {
+
+int kc_limbs_for_k(int k) { return k < 32 ? 1 : (k < 64 ? 2 : 4); }
+
+int kc_init(int device, void *stream, kc_ctx **out) {
+    if (!out) return KC_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) {
+        (void) cudaGetLastError();
+        return KC_ERR_NO_DEVICE;
+    }
+    kc_ctx *ctx = new (std::nothrow) kc_ctx();
+    if (!ctx) return KC_ERR_OOM;
+    try {
+        ctx->device = device;
+        KC_CUDA(cudaSetDevice(device));
+        if (stream) {
+            ctx->stream = (cudaStream_t) stream;
+        } else {
+            KC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+            ctx->own_stream = true;
+        }
+        for (int i = 0; i < 6; ++i) KC_CUDA(cudaEventCreate(&ctx->ev[i]));
+    } catch (const KcError &e) {
+        int code = e.code;
+        kc_destroy(ctx);
+        return code;
+    }
+    *out = ctx;
+    return KC_OK;
+}
+
+void kc_destroy(kc_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->arena.base) cudaFree(ctx->arena.base);
+    if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
+    if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+    for (int i = 0; i < 6; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (cudaEvent_t e : ctx->prof.pool) cudaEventDestroy(e);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int kc_compute_device(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *out) {
+    if (!ctx || !in || !out) return KC_ERR_ARG;
+    KC_API_BEGIN
+    check_params(p);
+    if (in->n_bytes >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 sequence bytes on one GPU");
+    if ((reinterpret_cast<uintptr_t>(in->seq) & 15) != 0) KC_THROW(KC_ERR_ARG, "device sequence pointer must be 16-byte aligned");
+    KC_CUDA(cudaSetDevice(ctx->device));
+    const int limbs = kc_limbs_for_k(p->k);
+    ensure_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, p->assume_simplitigs != 0));
+    ctx->arena.off = 0;
+    CudaExec ex{ctx->stream, &ctx->arena};
+    ex.prof = &ctx->prof;
+    DevInput di{in->seq, in->n_bytes, in->rec_off, in->rec_len, in->n_recs};
+    DevResult res;
+    dispatch_pipeline(ctx, ex, di, *p, res);
+    KC_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->prof.resolve();
+    out->ms = const_cast<u8 *>(res.ms);
+    out->ms_maxone = const_cast<u8 *>(res.maxone);
+    out->length = res.length;
+    out->n_kmers = res.n_kmers;
+    out->n_occurrences = res.n_occ;
+    out->n_nodes = res.n_nodes;
+    out->n_launches = ex.launches;
+    fill_times(ctx, out);
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
+int kc_compute(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *out) {
+    if (!ctx || !in || !out) return KC_ERR_ARG;
+    KC_API_BEGIN
+    check_params(p);
+    if (in->n_bytes >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 sequence bytes on one GPU");
+    KC_CUDA(cudaSetDevice(ctx->device));
+    const int limbs = kc_limbs_for_k(p->k);
+    const bool simplitigs = p->assume_simplitigs != 0;
+    ensure_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, simplitigs));
+    ctx->arena.off = 0;
+    CudaExec ex{ctx->stream, &ctx->arena};
+    ex.prof = &ctx->prof;
+    // host -> device
+    u8 *d_seq = ex.alloc<u8>(in->n_bytes + 64);
+    KC_CUDA(cudaMemcpyAsync(d_seq, in->seq, in->n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    u64 *d_off = nullptr, *d_len = nullptr;
+    if (simplitigs) {
+        d_off = ex.alloc<u64>(in->n_recs);
+        d_len = ex.alloc<u64>(in->n_recs);
+        KC_CUDA(cudaMemcpyAsync(d_off, in->rec_off, in->n_recs * 8, cudaMemcpyHostToDevice, ctx->stream));
+        KC_CUDA(cudaMemcpyAsync(d_len, in->rec_len, in->n_recs * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    DevInput di{d_seq, in->n_bytes, d_off, d_len, in->n_recs};
+    DevResult res;
+    dispatch_pipeline(ctx, ex, di, *p, res);
+    // device -> pinned host
+    const size_t need = (size_t) res.length * (res.maxone ? 2 : 1) + 64;
+    if (ctx->pin_out_cap < need) {
+        if (ctx->pin_out) KC_CUDA(cudaFreeHost(ctx->pin_out));
+        ctx->pin_out = nullptr;
+        ctx->pin_out_cap = 0;
+        KC_CUDA(cudaMallocHost(&ctx->pin_out, need + need / 8));
+        ctx->pin_out_cap = need + need / 8;
+    }
+    KC_CUDA(cudaMemcpyAsync(ctx->pin_out, res.ms, res.length, cudaMemcpyDeviceToHost, ctx->stream));
+    if (res.maxone)
+        KC_CUDA(cudaMemcpyAsync(ctx->pin_out + res.length, res.maxone, res.length, cudaMemcpyDeviceToHost, ctx->stream));
+    KC_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->prof.resolve();
+    out->ms = ctx->pin_out;
+    out->ms_maxone = res.maxone ? ctx->pin_out + res.length : nullptr;
+    out->length = res.length;
+    out->n_kmers = res.n_kmers;
+    out->n_occurrences = res.n_occ;
+    out->n_nodes = res.n_nodes;
+    out->n_launches = ex.launches;
+    fill_times(ctx, out);
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
+int kc_count_kmers(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t **keys, uint8_t **counts, uint64_t *n) {
+    if (!ctx || !in || !keys || !counts || !n) return KC_ERR_ARG;
+    KC_API_BEGIN
+    check_params(p);
+    if (in->n_bytes >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 sequence bytes on one GPU");
+    KC_CUDA(cudaSetDevice(ctx->device));
+    const int limbs = kc_limbs_for_k(p->k);
+    size_t need = (size_t) ((double) in->n_bytes * (1.0 + 2.0 * 8 * limbs + 4.0) * 1.15) + (256u << 20);
+    ensure_arena(ctx, need);
+    ctx->arena.off = 0;
+    CudaExec ex{ctx->stream, &ctx->arena};
+    ex.prof = &ctx->prof;
+    u8 *d_seq = ex.alloc<u8>(in->n_bytes + 64);
+    KC_CUDA(cudaMemcpyAsync(d_seq, in->seq, in->n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    DevInput di{d_seq, in->n_bytes, nullptr, nullptr, in->n_recs};
+    if (p->k < 32) count_only<1>(ctx, ex, di, *p, keys, counts, n);
+    else if (p->k < 64) count_only<2>(ctx, ex, di, *p, keys, counts, n);
+    else count_only<4>(ctx, ex, di, *p, keys, counts, n);
+    ctx->prof.resolve();
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
+int kc_overlap_path(kc_ctx *ctx, const uint64_t *first, const uint64_t *last, uint64_t n, int k, int complements,
+                    int lower_bound, int strict, int64_t *edge_from, uint8_t *overlaps) {
+    if (!ctx || !first || !last || !edge_from || !overlaps) return KC_ERR_ARG;
+    KC_API_BEGIN
+    if (k < 1 || k > 127) KC_THROW(KC_ERR_ARG, "k must be in 1..127");
+    if (n == 0) KC_THROW(KC_ERR_EMPTY, "input cannot be empty");
+    if (n * (complements ? 2 : 1) >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "too many nodes for one GPU");
+    KC_CUDA(cudaSetDevice(ctx->device));
+    const int limbs = kc_limbs_for_k(k);
+    ensure_arena(ctx, estimate_arena(0, n, limbs, complements != 0, true) + n * 16 * limbs);
+    ctx->arena.off = 0;
+    CudaExec ex{ctx->stream, &ctx->arena};
+    ex.prof = &ctx->prof;
+    if (k < 32) overlap_only<1>(ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
+    else if (k < 64) overlap_only<2>(ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
+    else overlap_only<4>(ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
+    ctx->prof.resolve();
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
+int kc_profile_enable(kc_ctx *ctx, int on) {
+    if (!ctx) return KC_ERR_ARG;
+    ctx->prof.enabled = on != 0;
+    return KC_OK;
+}
+int kc_profile_count(void) { return KP_COUNT; }
+int kc_profile_get(kc_ctx *ctx, int i, const char **name, double *ms, uint64_t *launches, uint64_t *bytes) {
+    if (!ctx || i < 0 || i >= KP_COUNT) return KC_ERR_ARG;
+    if (name) *name = kc_prof_names[i];
+    if (ms) *ms = ctx->prof.ms[i];
+    if (launches) *launches = ctx->prof.launches[i];
+    if (bytes) *bytes = ctx->prof.bytes[i];
+    return KC_OK;
+}
+int kc_profile_reset(kc_ctx *ctx) {
+    if (!ctx) return KC_ERR_ARG;
+    ctx->prof.reset();
+    return KC_OK;
+}
+
+void kc_free(void *p) { std::free(p); }
+
+const char *kc_strerror(int code) {
+    switch (code) {
+        case KC_OK: return "ok";
+        case KC_ERR_CUDA: return "CUDA error";
+        case KC_ERR_ARG: return "invalid argument";
+        case KC_ERR_OOM: return "out of memory";
+        case KC_ERR_EMPTY: return "input contains no k-mers";
+        case KC_ERR_BAD_SEQ: return "invalid sequence for -S";
+        case KC_ERR_TOO_LARGE: return "input too large for one GPU";
+        case KC_ERR_INTERNAL: return "internal error";
+        case KC_ERR_NO_DEVICE: return "no CUDA device";
+        default: return "unknown error";
+    }
+}
+
+const char *kc_last_error(const kc_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+}  // extern "C"
