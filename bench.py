@@ -1,0 +1,300 @@
+#!/usr/bin/env python3
+"""bench.py — `kmercamel compute` hot path on B200 (driver contract, see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]                 our CUDA path
+  python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]   the reference's own CPU path (oracle/_ref)
+
+A step = one pass of the whole hot path (extract -> count -> overlap levels -> emission) over one synthetic input.
+Workload = BASELINE.json configs[1]: 50 x 1,000,000 bp uniform random multi-FASTA (seed 12345), k = 31, canonical.
+  value  = distinct k-mers represented per second, device-timed, input already resident in HBM;
+  e2e    = the same through kc_compute with pinned HOST buffers (H2D of the input and D2H of the superstring
+           inside the timed region).
+N > 1 (torchrun): every rank runs the path on its own independent genome (seed 12345 + rank) — the path shards by
+independent inputs, no data-path collective — weak scaling; value = k-mers of all ranks / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 31
+N_RECORDS = 50
+RECORD_LEN = 1_000_000
+SEED = 12345
+METRIC = "distinct k-mers/sec for `compute` (k=31, canonical, device-timed)"
+UNIT = "k-mers/s"
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(rank: int):
+    from kmercamel_b200 import synth
+    recs = synth.random_genome_records(N_RECORDS, RECORD_LEN, SEED + rank)
+    return recs, synth.frame_records(recs)
+
+
+def ref_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "kmercamel")
+    return p if os.path.exists(p) else None
+
+
+def time_reference(records, n_sample_records: int):
+    """The reference's CPU `compute` (oracle/_ref/kmercamel, unmodified sources) on the first n_sample_records records.
+    -> (k-mers/s, distinct k-mers, seconds, kind)"""
+    from kmercamel_b200 import synth
+    sample = records[:n_sample_records]
+    exe = ref_binary()
+    with tempfile.TemporaryDirectory() as td:
+        fa = os.path.join(td, "sample.fa")
+        with open(fa, "wb") as f:
+            f.write(synth.fasta_bytes(sample))
+        if exe:
+            t0 = time.perf_counter()
+            p = subprocess.run([exe, "compute", "-k", str(K), "-o", os.path.join(td, "out.msfa"), fa], capture_output=True, text=True)
+            dt = time.perf_counter() - t0
+            if p.returncode == 0:
+                n = None
+                for ln in p.stderr.splitlines():
+                    if "Finished collecting k-mers:" in ln:
+                        n = int(ln.split("k-mers:")[1].split()[0])
+                return n / dt, n, dt, "reference"
+    # oracle/_ref not built (no /root/reference at build time): time the oracle port of stage 1 instead
+    from oracle import orc
+    seq, off, ln = synth.frame_records(sample)
+    t0 = time.perf_counter()
+    keys, _ = orc.count_kmers(seq, off, ln, K, True)
+    dt = time.perf_counter() - t0
+    return len(keys) / dt, len(keys), dt, "port"
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    records, _ = make_workload(0)
+    n_sample = 5  # 5 Mbp per step: ~4 s of single-thread CPU work
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        time_reference(records, 1)
+    vals, secs, n_k, kind = [], [], 0, "reference"
+    for _ in range(args.steps):
+        v, n_k, dt, kind = time_reference(records, n_sample)
+        vals.append(v)
+        secs.append(dt)
+    value = n_k * len(secs) / sum(secs)
+    sample = f"first {n_sample} of the {N_RECORDS} records ({n_sample * RECORD_LEN / 1e6:.0f} Mbp, {n_k} distinct k-mers) per step; " \
+             f"wall clock of `kmercamel compute -k 31` incl. file read and output write"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_cores_available": os.cpu_count(),
+        "note": "the reference is single-threaded (no threads/OpenMP in its sources): cores = 1 is all it can use",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(world):
+    return {"workload": "BASELINE configs[1]: synthetic 50 Mbp random multi-FASTA (50 x 1 Mbp, default_rng(12345)), "
+                        "k=31 canonical, min-one mask, u64 word path",
+            "k": K, "bases_per_gpu": N_RECORDS * RECORD_LEN, "records_per_gpu": N_RECORDS,
+            "sharding": "independent genome per rank (seed 12345 + rank), no data-path collective" if world > 1 else "single GPU",
+            "l2": "no explicit flush: each step streams ~10 GB of intermediates (>> 126 MB L2), so the 51 MB input and "
+                  "every kernel's operands are cold when read"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import kmercamel_b200 as kb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    records, (seq, off, ln) = make_workload(rank)
+    stream = torch.cuda.current_stream()
+    ctx = kb.Context(local_rank, stream.cuda_stream)
+    d_seq = torch.from_numpy(seq).cuda()
+    pinned = torch.from_numpy(seq).pin_memory()
+    pinned_np = pinned.numpy()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed arm (input resident in HBM) ---------------------------------------------------------------
+    res = None
+    for _ in range(max(args.warmup, 3)):
+        res = ctx.compute_device(d_seq.data_ptr(), d_seq.numel(), k=K)
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    launches = 0
+    for _ in range(args.steps):
+        res = ctx.compute_device(d_seq.data_ptr(), d_seq.numel(), k=K)
+        launches += res.n_launches
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1)
+    prof = ctx.profile()
+    stage_ms = res.times_ms
+    ctx.profile_enable(False)
+
+    # ---- end-to-end arm (pinned host buffers in, host superstring out) ----------------------------------------
+    for _ in range(2):
+        r2 = ctx.compute(pinned_np, k=K, copy=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r2 = ctx.compute(pinned_np, k=K, copy=False)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    n_kmers = res.n_kmers
+    t = torch.tensor([dev_ms, e2e_s * 1000.0, float(n_kmers)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_ms, total_kmers = float(tmax[0]), float(tmax[1]), float(tsum[2])
+    else:
+        dev_ms, e2e_ms, total_kmers = float(t[0]), float(t[1]), float(t[2])
+
+    if rank == 0:
+        value = total_kmers * args.steps / (dev_ms / 1000.0)
+        e2e_value = total_kmers * args.steps / (e2e_ms / 1000.0)
+        peak, peak_src = measured_peak_gbs()
+        # dominant kernel class = largest share of device time in the timed region
+        dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        dname, d = dom
+        ach = (d["bytes"] / max(d["launches"], 1)) / (d["ms"] / max(d["launches"], 1) / 1000.0) / 1e9 if d["ms"] > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(dname)
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": dname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic, "peak_source": peak_src,
+                    "launches_per_step": d["launches"] / args.steps, "ms_per_launch": d["ms"] / max(d["launches"], 1),
+                    "algorithmic_bytes_per_launch": d["bytes"] / max(d["launches"], 1),
+                    "share_of_step": d["ms"] / dev_ms}
+        kernels = {n: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                       "gbs": (v["bytes"] / (v["ms"] / 1000.0) / 1e9) if v["ms"] > 0 and v["bytes"] else None}
+                   for n, v in prof.items() if v["launches"]}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            v, n_k, dt, kind = time_reference(records, 10)
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
+                   "sample": f"first 10 of the 50 records (10 Mbp, {n_k} distinct k-mers): `kmercamel compute -k 31` wall "
+                             f"clock {dt:.1f} s on one host core (the reference is single-threaded; {os.cpu_count()} cores present)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic", "config": workload_config(world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(seq.size), "d2h_bytes_per_step": int(r2.length),
+                    "ms_per_step": e2e_ms / args.steps, "timer": "host perf_counter around kc_compute (stream-synchronous), max over ranks"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "stage_ms_last_step": stage_ms, "kernel_classes": kernels,
+            "result": {"distinct_kmers_per_gpu": int(n_kmers), "superstring_length": int(res.length), "nodes": int(res.n_nodes)},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,222 @@
+// kmercamel (B200) — host side of `kmercamel compute`: flags, file reading, FASTA framing, output writing.
+// Everything between "bytes in memory" and "masked superstring in memory" happens on the GPU behind the C ABI of
+// include/kcgpu.h; this file mirrors the user-visible behaviour of the reference CLI for the compute sub-command:
+// flags and validation (reference src/main.cpp:214-316), the header line (src/parser.h:167-179), the stderr stage
+// log (src/parser.h:159-164, src/main.cpp:133,160,174, src/global.h:223,225) and the two-line .msfa output.
+#include <kcgpu.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <string>
+#include <vector>
+
+static const char *VERSION = "kmercamel-b200 0.1 (compute path of KmerCamel v2.3.0)";
+static const int MAX_K = 127;  // reference src/main.cpp:93
+
+static void write_log(const std::string &message) {  // src/parser.h:159-164
+    auto snapshot = std::chrono::system_clock::now();
+    std::time_t time = std::chrono::system_clock::to_time_t(snapshot);
+    std::tm *time_tm = std::localtime(&time);
+    std::cerr << "[" << std::put_time(time_tm, "%H:%M:%S") << "] " << message << std::endl;
+}
+
+static void write_name(const std::string &dataset, int k, bool maxone, bool unidirectional, std::ostream &of) {  // src/parser.h:167-179
+    of << ">maskedsuperstring dataset='" << dataset << "' k=" << k << " alg=greedy mask=" << (maxone ? "max-one " : "min-one ")
+       << "mode=" << (unidirectional ? "unidirectional" : "bidirectional") << std::endl;
+}
+
+static int usage() {
+    std::cerr << std::endl;
+    std::cerr << "Program: kmercamel (B200-native masked superstring computation)" << std::endl;
+    std::cerr << "Version: " << VERSION << std::endl;
+    std::cerr << std::endl;
+    std::cerr << "Usage:   kmercamel compute [options] <fasta>" << std::endl << std::endl;
+    std::cerr << "Options:" << std::endl;
+    std::cerr << "  -k INT   - k-mer size (required; up to " << MAX_K << ")" << std::endl;
+    std::cerr << "  -a STR   - the algorithm; only 'greedy' (global greedy, default) runs on the GPU" << std::endl;
+    std::cerr << "  -o FILE  - output file [default: stdout]" << std::endl;
+    std::cerr << "  -u       - treat k-mer and its reverse complement as distinct" << std::endl;
+    std::cerr << "  -S       - assume the input are simplitigs / matchtigs / unitigs" << std::endl;
+    std::cerr << "  -M FILE  - also output the masked superstring with the mask maximizing the number of ones" << std::endl;
+    std::cerr << "  -z INT   - keep only k-mers with at least this many occurrences [default: 1]" << std::endl;
+    std::cerr << "  -g INT   - CUDA device ordinal [default: 0]" << std::endl;
+    std::cerr << "  -h       - print help" << std::endl;
+    std::cerr << std::endl;
+    return 1;
+}
+
+// Whole file (plain or gzip, "-" = stdin) into memory; zlib detects the format as in src/parser.h:88-101.
+static bool read_all(const std::string &path, std::vector<unsigned char> &data) {
+    FILE *in = path == "-" ? stdin : std::fopen(path.c_str(), "r");
+    if (!in) return false;
+    gzFile fp = gzdopen(fileno(in), "r");
+    if (!fp) return false;
+    gzbuffer(fp, 1 << 20);
+    size_t cap = 1 << 24;
+    data.resize(cap);
+    size_t len = 0;
+    while (true) {
+        if (len == cap) {
+            cap *= 2;
+            data.resize(cap);
+        }
+        int got = gzread(fp, data.data() + len, (unsigned) std::min<size_t>(cap - len, 1u << 30));
+        if (got <= 0) break;
+        len += (size_t) got;
+    }
+    data.resize(len);
+    gzclose(fp);
+    return true;
+}
+
+int main(int argc, char **argv) {
+    if (argc < 2) return usage();
+    if (std::string(argv[1]) == "-h") {
+        usage();
+        return 0;
+    }
+    if (std::string(argv[1]) == "-v") {
+        std::cerr << VERSION << std::endl;
+        return 0;
+    }
+    if (std::string(argv[1]) != "compute") {
+        std::cerr << "Only the 'compute' sub-command is implemented by the B200 build." << std::endl;
+        return usage();
+    }
+    argc--;
+    argv++;
+    std::string path;
+    if (argc > 1 && std::string(argv[argc - 1]) != "-h") {  // src/main.cpp:217-220: the input is the LAST argument
+        path = argv[argc - 1];
+        argc--;
+    }
+    int k = 0, device = 0;
+    long min_frequency = 1;
+    std::string out_path, mask_path, algorithm = "greedy";
+    bool complements = true, assume_simplitigs = false, d_set = false;
+    int opt;
+    try {
+        while ((opt = getopt(argc, argv, "k:d:a:o:huxM:Sz:g:")) != -1) {  // src/main.cpp:234
+            switch (opt) {
+                case 'o': out_path = optarg; break;
+                case 'k': k = std::stoi(optarg); break;
+                case 'd': d_set = true; (void) std::stoi(optarg); break;
+                case 'a': algorithm = optarg; break;
+                case 'u': complements = false; break;
+                case 'x':
+                    std::cerr << "Warning: The parameter -x currently has no effect due to the improvement in the underlying algorithm." << std::endl;
+                    break;
+                case 'M': mask_path = optarg; break;
+                case 'S': assume_simplitigs = true; break;
+                case 'z': min_frequency = std::stol(optarg); break;
+                case 'g': device = std::stoi(optarg); break;
+                case 'h': usage(); return 0;
+                default: return usage();
+            }
+        }
+    } catch (std::exception &) {
+        return usage();
+    }
+    if (algorithm == "global") algorithm = "greedy";  // src/main.cpp:97-106
+    if (path.empty()) {
+        std::cerr << "Required positional parameter path to the file not set." << std::endl;
+        return usage();
+    }
+    if (k == 0) {
+        std::cerr << "Required parameter k not set." << std::endl;
+        return usage();
+    } else if (k < 0) {
+        std::cerr << "k must be positive." << std::endl;
+        return usage();
+    } else if (algorithm != "greedy") {
+        std::cerr << "Algorithm '" << algorithm << "' is not part of the GPU compute path; use the reference build for it." << std::endl;
+        return usage();
+    } else if (k > MAX_K) {
+        std::cerr << "k > " << MAX_K << " not supported for the algorithm 'greedy'." << std::endl;
+        return usage();
+    } else if (d_set) {
+        std::cerr << "Unsupported argument d for algorithm 'greedy'." << std::endl;
+        return usage();
+    } else if (min_frequency >= 256 || min_frequency < 1) {
+        std::cerr << "Minimum frequency '-z' must be between 1 and 255." << std::endl;
+        return usage();
+    } else if (min_frequency != 1 && assume_simplitigs) {
+        std::cerr << "Inputting simplitigs is not compatible with frequency filterring." << std::endl;
+        return usage();
+    }
+
+    write_log("Started computation of a masked superstring from '" + path + "'.");
+    std::vector<unsigned char> data;
+    if (!read_all(path, data)) {
+        std::cerr << "couldn't open file " << path << std::endl;  // src/parser.h:95-97 throws invalid_argument
+        return 1;
+    }
+    uint8_t *seq = nullptr;
+    uint64_t n_bytes = 0, n_recs = 0, *rec_off = nullptr, *rec_len = nullptr;
+    int rc = kc_frame_fasta(data.data(), data.size(), &seq, &n_bytes, &rec_off, &rec_len, &n_recs);
+    if (rc != KC_OK) {
+        std::cerr << "framing failed: " << kc_strerror(rc) << std::endl;
+        return 1;
+    }
+    std::vector<unsigned char>().swap(data);
+
+    kc_ctx *ctx = nullptr;
+    rc = kc_init(device, nullptr, &ctx);
+    if (rc != KC_OK) {
+        std::cerr << "cannot initialise CUDA device " << device << ": " << kc_strerror(rc) << " (this build has no CPU path)" << std::endl;
+        return 1;
+    }
+    kc_params p{k, complements ? 1 : 0, (int) min_frequency, assume_simplitigs ? 1 : 0, mask_path.empty() ? 0 : 1};
+    kc_input in{seq, n_bytes, rec_off, rec_len, n_recs};
+    kc_output out;
+    std::memset(&out, 0, sizeof(out));
+    rc = kc_compute(ctx, &p, &in, &out);
+    if (rc == KC_ERR_EMPTY && !assume_simplitigs) {  // src/main.cpp:155-158
+        std::cerr << "Path '" << path << "' contains no k-mers. Make sure that your file is a FASTA or gzipped FASTA." << std::endl;
+        kc_destroy(ctx);
+        return usage();
+    }
+    if (rc != KC_OK) {
+        std::cerr << "kmercamel compute failed: " << kc_strerror(rc) << ": " << kc_last_error(ctx) << std::endl;
+        kc_destroy(ctx);
+        return 1;
+    }
+    if (!assume_simplitigs)
+        write_log("Finished collecting k-mers: " + std::to_string(out.n_kmers) + " " + std::to_string(k) + "-mers.");
+    write_log("Finished 1. part: " + std::string(assume_simplitigs ? "simplitigs (" : "GPU k-mer nodes (") + std::to_string(out.n_nodes) + ").");
+    write_log("Finished 2. part: Hamiltonian path.");
+    write_log("Finished 3. part: masked superstring (l=" + std::to_string(out.length) + ").");
+    char times[256];
+    std::snprintf(times, sizeof(times), "GPU stages [ms]: extract %.3f, count %.3f, path %.3f, emit %.3f, total %.3f; %llu kernels",
+                  out.t.extract_ms, out.t.count_ms, out.t.path_ms, out.t.emit_ms, out.t.total_ms, (unsigned long long) out.n_launches);
+    write_log(times);
+
+    std::ofstream output, mask_output;
+    std::ostream *of = &std::cout;
+    if (!out_path.empty()) {
+        output.open(out_path);
+        of = &output;
+    }
+    write_name(path, k, false, !complements, *of);
+    of->write(reinterpret_cast<const char *>(out.ms), (std::streamsize) out.length);
+    *of << std::endl;  // src/main.cpp:210
+    if (!mask_path.empty()) {
+        mask_output.open(mask_path);
+        write_name(path, k, true, !complements, mask_output);
+        mask_output.write(reinterpret_cast<const char *>(out.ms_maxone), (std::streamsize) out.length);
+        mask_output << std::endl;  // src/global.h:206-208
+    }
+    kc_destroy(ctx);
+    kc_free(seq);
+    kc_free(rec_off);
+    kc_free(rec_len);
+    return 0;
+}

@@ -87,6 +87,9 @@ int kc_compute(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *o
 /* Same with DEVICE buffers in and out (outputs live in the context arena until the next call). */
 int kc_compute_device(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *out);
 
+/* Copy n bytes of a kc_compute_device result (or any device buffer) to host memory on the context stream. */
+int kc_copy_to_host(kc_ctx *ctx, void *dst_host, const void *src_device, uint64_t n);
+
 /* Stage 1 only (host buffers): sorted distinct k-mers (n * limbs uint64) and min(occurrences-1, 255) per k-mer,
  * after the -z filter.  Outputs are malloc'ed by the library; release with kc_free. */
 int kc_count_kmers(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t **keys, uint8_t **counts, uint64_t *n);

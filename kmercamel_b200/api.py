@@ -1,0 +1,246 @@
+"""ctypes binding of include/kcgpu.h.
+
+Mirrors the reference's call sequence for `compute` (reference src/main.cpp:122-212): ReadKMers[Filtered] ->
+get_simplitigs | simplitigs_from_fasta -> Global/GlobalSparse, exposed as Context.compute(); the stage entry points
+Context.count_kmers() and Context.overlap_path() exist so that parity tests can hit each stage.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+u8p = C.POINTER(C.c_uint8)
+u64p = C.POINTER(C.c_uint64)
+i64p = C.POINTER(C.c_int64)
+
+ERRORS = {0: "KC_OK", -1: "KC_ERR_CUDA", -2: "KC_ERR_ARG", -3: "KC_ERR_OOM", -4: "KC_ERR_EMPTY", -5: "KC_ERR_BAD_SEQ",
+          -6: "KC_ERR_TOO_LARGE", -7: "KC_ERR_INTERNAL", -8: "KC_ERR_NO_DEVICE"}
+
+
+class KcError(RuntimeError):
+    def __init__(self, code: int, detail: str = ""):
+        self.code = code
+        self.name = ERRORS.get(code, str(code))
+        super().__init__(f"{self.name}: {detail}" if detail else self.name)
+
+
+class kc_params(C.Structure):
+    _fields_ = [("k", C.c_int), ("complements", C.c_int), ("min_frequency", C.c_int), ("assume_simplitigs", C.c_int),
+                ("want_maxone", C.c_int)]
+
+
+class kc_input(C.Structure):
+    _fields_ = [("seq", C.c_void_p), ("n_bytes", C.c_uint64), ("rec_off", C.c_void_p), ("rec_len", C.c_void_p),
+                ("n_recs", C.c_uint64)]
+
+
+class kc_stage_times(C.Structure):
+    _fields_ = [("extract_ms", C.c_float), ("count_ms", C.c_float), ("path_ms", C.c_float), ("emit_ms", C.c_float),
+                ("total_ms", C.c_float)]
+
+
+class kc_output(C.Structure):
+    _fields_ = [("ms", C.c_void_p), ("ms_maxone", C.c_void_p), ("length", C.c_uint64), ("n_kmers", C.c_uint64),
+                ("n_occurrences", C.c_uint64), ("n_nodes", C.c_uint64), ("n_launches", C.c_uint64), ("t", kc_stage_times)]
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "csrc", "libkcgpu.so")
+
+
+def load_library():
+    """Load libkcgpu.so.  There is no fallback: a missing library is an error."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `make` (or __graft_entry__.build()); "
+                          "kmercamel_b200 has no CPU fallback")
+    L = C.CDLL(path)
+    L.kc_init.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.kc_destroy.argtypes = [C.c_void_p]
+    L.kc_destroy.restype = None
+    L.kc_compute.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.POINTER(kc_output)]
+    L.kc_compute_device.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.POINTER(kc_output)]
+    L.kc_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.kc_count_kmers.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.POINTER(u64p), C.POINTER(u8p),
+                                 u64p]
+    L.kc_overlap_path.argtypes = [C.c_void_p, u64p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, i64p, u8p]
+    L.kc_frame_fasta.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(u8p), u64p, C.POINTER(u64p), C.POINTER(u64p), u64p]
+    L.kc_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.kc_profile_count.restype = C.c_int
+    L.kc_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), u64p, u64p]
+    L.kc_profile_reset.argtypes = [C.c_void_p]
+    L.kc_limbs_for_k.argtypes = [C.c_int]
+    L.kc_free.argtypes = [C.c_void_p]
+    L.kc_free.restype = None
+    L.kc_strerror.argtypes = [C.c_int]
+    L.kc_strerror.restype = C.c_char_p
+    L.kc_last_error.argtypes = [C.c_void_p]
+    L.kc_last_error.restype = C.c_char_p
+    _LIB = L
+    return L
+
+
+EXPORTED_SYMBOLS = ["kc_init", "kc_destroy", "kc_compute", "kc_compute_device", "kc_copy_to_host", "kc_count_kmers", "kc_overlap_path",
+                    "kc_frame_fasta", "kc_profile_enable", "kc_profile_count", "kc_profile_get", "kc_profile_reset",
+                    "kc_limbs_for_k", "kc_free", "kc_strerror", "kc_last_error"]
+
+
+def limbs_for_k(k: int) -> int:
+    return 1 if k < 32 else (2 if k < 64 else 4)
+
+
+def _take(ptr, n, dtype):
+    out = np.ctypeslib.as_array(ptr, shape=(max(n, 1),))[:n].astype(dtype, copy=True)
+    load_library().kc_free(C.cast(ptr, C.c_void_p))
+    return out
+
+
+def frame_fasta(data: bytes):
+    """FASTA/FASTQ bytes -> (seq u8, rec_off u64, rec_len u64) with kseq semantics (host only, no GPU needed)."""
+    L = load_library()
+    seq, off, ln = u8p(), u64p(), u64p()
+    nb, nr = C.c_uint64(), C.c_uint64()
+    rc = L.kc_frame_fasta(data, len(data), C.byref(seq), C.byref(nb), C.byref(off), C.byref(ln), C.byref(nr))
+    if rc != 0:
+        raise KcError(rc)
+    return _take(seq, nb.value, np.uint8), _take(off, nr.value, np.uint64), _take(ln, nr.value, np.uint64)
+
+
+def frame_fasta_file(path: str):
+    import gzip
+    with open(path, "rb") as f:
+        data = f.read()
+    if data[:2] == b"\x1f\x8b":
+        data = gzip.decompress(data)
+    return frame_fasta(data)
+
+
+@dataclass
+class ComputeResult:
+    ms: bytes | None
+    maxone: bytes | None
+    length: int
+    n_kmers: int
+    n_occurrences: int
+    n_nodes: int
+    n_launches: int
+    times_ms: dict = field(default_factory=dict)
+    ms_ptr: int = 0        # device pointers for compute_device
+    maxone_ptr: int = 0
+
+
+class Context:
+    """One context per process and GPU (kc_init / kc_destroy)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.kc_init(device, C.c_void_p(stream) if stream else None, C.byref(self._h))
+        if rc != 0:
+            raise KcError(rc, "kc_init")
+
+    def close(self):
+        if self._h:
+            self._lib.kc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise KcError(rc, self._lib.kc_last_error(self._h).decode())
+
+    @staticmethod
+    def _params(k, complements, min_frequency, assume_simplitigs, want_maxone):
+        return kc_params(int(k), int(bool(complements)), int(min_frequency), int(bool(assume_simplitigs)),
+                         int(bool(want_maxone)))
+
+    def _result(self, out, copy_host: bool):
+        t = out.t
+        times = dict(extract=t.extract_ms, count=t.count_ms, path=t.path_ms, emit=t.emit_ms, total=t.total_ms)
+        ms = mo = None
+        if copy_host:
+            ms = C.string_at(out.ms, out.length)
+            mo = C.string_at(out.ms_maxone, out.length) if out.ms_maxone else None
+        return ComputeResult(ms, mo, out.length, out.n_kmers, out.n_occurrences, out.n_nodes, out.n_launches, times,
+                             out.ms or 0, out.ms_maxone or 0)
+
+    def compute(self, seq, rec_off=None, rec_len=None, *, k, complements=True, min_frequency=1, assume_simplitigs=False,
+                want_maxone=False, copy=True) -> ComputeResult:
+        """`kmercamel compute` on framed host buffers (H2D + all stages + D2H)."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        n_recs = 0 if rec_off is None else len(rec_off)
+        if rec_off is not None:
+            rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+            rec_len = np.ascontiguousarray(rec_len, dtype=np.uint64)
+        p = self._params(k, complements, min_frequency, assume_simplitigs, want_maxone)
+        inp = kc_input(seq.ctypes.data, seq.size, rec_off.ctypes.data if n_recs else None,
+                       rec_len.ctypes.data if n_recs else None, n_recs)
+        out = kc_output()
+        self._check(self._lib.kc_compute(self._h, C.byref(p), C.byref(inp), C.byref(out)))
+        return self._result(out, copy)
+
+    def compute_device(self, seq_ptr: int, n_bytes: int, rec_off_ptr: int = 0, rec_len_ptr: int = 0, n_recs: int = 0, *, k,
+                       complements=True, min_frequency=1, assume_simplitigs=False, want_maxone=False) -> ComputeResult:
+        """Same with device pointers in and out (results stay in the context arena until the next call)."""
+        p = self._params(k, complements, min_frequency, assume_simplitigs, want_maxone)
+        inp = kc_input(seq_ptr, n_bytes, rec_off_ptr or None, rec_len_ptr or None, n_recs)
+        out = kc_output()
+        self._check(self._lib.kc_compute_device(self._h, C.byref(p), C.byref(inp), C.byref(out)))
+        return self._result(out, False)
+
+    def copy_to_host(self, device_ptr: int, n: int) -> bytes:
+        buf = C.create_string_buffer(max(n, 1))
+        self._check(self._lib.kc_copy_to_host(self._h, buf, C.c_void_p(device_ptr), n))
+        return buf.raw[:n]
+
+    def count_kmers(self, seq, *, k, complements=True, min_frequency=1):
+        """Stage 1: -> (keys [n, limbs] u64 ascending, counts [n] u8 = min(occurrences-1, 255))."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        p = self._params(k, complements, min_frequency, False, False)
+        inp = kc_input(seq.ctypes.data, seq.size, None, None, 0)
+        keys, cnt, n = u64p(), u8p(), C.c_uint64()
+        self._check(self._lib.kc_count_kmers(self._h, C.byref(p), C.byref(inp), C.byref(keys), C.byref(cnt), C.byref(n)))
+        L = limbs_for_k(k)
+        return _take(keys, n.value * L, np.uint64).reshape(n.value, L), _take(cnt, n.value, np.uint8)
+
+    def overlap_path(self, first, last, *, k, complements=True, lower_bound=False, strict=True):
+        """Overlap stage: first/last [n, limbs] u64 -> (edge_from [N] i64, overlaps [N] u8)."""
+        first = np.ascontiguousarray(first, dtype=np.uint64)
+        last = np.ascontiguousarray(last, dtype=np.uint64)
+        n = first.shape[0]
+        N = n * (2 if complements else 1)
+        ef = np.zeros(N, dtype=np.int64)
+        ov = np.zeros(N, dtype=np.uint8)
+        self._check(self._lib.kc_overlap_path(self._h, first.ctypes.data_as(u64p), last.ctypes.data_as(u64p), n, k,
+                                              int(complements), int(lower_bound), int(strict), ef.ctypes.data_as(i64p),
+                                              ov.ctypes.data_as(u8p)))
+        return ef, ov
+
+    # ---- per-kernel-class timers ---------------------------------------------------------------------------
+    def profile_enable(self, on: bool = True):
+        self._lib.kc_profile_enable(self._h, int(on))
+
+    def profile_reset(self):
+        self._lib.kc_profile_reset(self._h)
+
+    def profile(self) -> dict:
+        out = {}
+        for i in range(self._lib.kc_profile_count()):
+            name, ms, n, b = C.c_char_p(), C.c_double(), C.c_uint64(), C.c_uint64()
+            self._lib.kc_profile_get(self._h, i, C.byref(name), C.byref(ms), C.byref(n), C.byref(b))
+            out[name.value.decode()] = dict(ms=ms.value, launches=n.value, bytes=b.value)
+        return out

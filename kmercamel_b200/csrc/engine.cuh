@@ -268,6 +268,7 @@ template <class Exec, int L> struct Engine {
         ex.fill_bytes(st.edge_to, 0xFF, N * 4);
         ex.fill_bytes(st.ovl, 0xFF, N);
         ex.fill_bytes(ban_flag, 0, N);
+        ex.fill_bytes(ban_ctr, 0, 16);
         PathState s = st;
         ex.for_each(N, [=] KC_HD_LAMBDA(u64 v) {
             s.chain_head[v] = (u32) v;

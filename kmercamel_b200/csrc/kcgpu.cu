@@ -379,6 +379,16 @@ int kc_compute(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *o
     KC_API_END(ctx)
 }
 
+int kc_copy_to_host(kc_ctx *ctx, void *dst_host, const void *src_device, uint64_t n) {
+    if (!ctx || (!dst_host && n) || (!src_device && n)) return KC_ERR_ARG;
+    KC_API_BEGIN
+    KC_CUDA(cudaSetDevice(ctx->device));
+    if (n) KC_CUDA(cudaMemcpyAsync(dst_host, src_device, n, cudaMemcpyDeviceToHost, ctx->stream));
+    KC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
 int kc_count_kmers(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t **keys, uint8_t **counts, uint64_t *n) {
     if (!ctx || !in || !keys || !counts || !n) return KC_ERR_ARG;
     KC_API_BEGIN
