@@ -58,7 +58,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -224,7 +224,6 @@ def main():
         launches += res.n_launches
     e1.record(stream)
     barrier()
-    clocks = sampler.stop()
     dev_ms = e0.elapsed_time(e1)
     prof = ctx.profile()
     stage_ms = res.times_ms
@@ -236,10 +235,14 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        t1 = time.perf_counter()
         r2 = ctx.compute(pinned_np, k=K, copy=False)
+        if os.environ.get("KC_BENCH_DEBUG"):
+            print(f"[debug] e2e step {time.perf_counter() - t1:.4f}s stages {r2.times_ms}", file=sys.stderr)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    clocks = sampler.stop()  # sampled through both timed regions; stopping it earlier stalls the next CUDA calls
 
     n_kmers = res.n_kmers
     t = torch.tensor([dev_ms, e2e_s * 1000.0, float(n_kmers)], dtype=torch.float64, device="cuda")

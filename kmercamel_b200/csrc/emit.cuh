@@ -49,6 +49,9 @@ template <int L> KC_HD u64 kmer_lower_bound(const KWord<L> *keys, u64 n, const K
     return lo;
 }
 
+static const u32 KC_EMIT_SHORT = 128;   // contributions up to this many characters: one thread
+static const u32 KC_EMIT_CHUNK = 4096;   // longer ones: chunks of this many characters, 256 work items each
+
 struct EmitResult {
     u8 *ms = nullptr;      // device, `length` bytes
     u8 *maxone = nullptr;  // device, `length` bytes, or nullptr
@@ -78,7 +81,7 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
         fin_a[v] = v;
         dist_a[v] = q.length(v) - (nx != KC_NONE ? (u64) s.ovl[v] : 0);  // characters contributed by v
         if (s.edge_to[v] == KC_NONE) KC_ATOMIC_MIN((kc_ull *) &cell[0], (kc_ull) v);  // src/global.h:156-161 start
-    });
+    }, KP_RANK, N * 25);
     int rounds = kc_ceil_log2(N) + 1;
     for (int it = 0; it < rounds; ++it) {
         const u32 *ja = jump_a, *fa = fin_a;
@@ -96,7 +99,7 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
                 fb[v] = fa[j];
                 db[v] = da[v] + da[j];
             }
-        });
+        }, KP_RANK, N * 32);
         u32 *t = jump_a; jump_a = jump_b; jump_b = t;
         t = fin_a; fin_a = fin_b; fin_b = t;
         u64 *m = dist_a; dist_a = dist_b; dist_b = m;
@@ -129,18 +132,50 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
             KWord<L> x = q.kmers[v < q.n ? v : v - q.n];
             if (v >= q.n) x = kmer_reverse_complement(x, k);
             for (u32 j = 0; j < cnt; ++j) ms[off + j] = kc_letter(kmer_symbol(x, k, (int) j), j == 0);
-        });
+        }, KP_EMIT, N * 12 + (u64) q.n * sizeof(KWord<L>) + total);
     } else {
-        // one warp-sized group of 32 consecutive work items per node: coalesced writes for long records
-        ex.for_each(N * 32, [=] KC_HD_LAMBDA(u64 w) {
-            u32 v = (u32) (w >> 5), lane = (u32) (w & 31);
+        // Record nodes.  Short contributions: one thread per node.  Long ones (simplitigs, first-occurrence runs of
+        // a genome can span megabases) are cut into chunks of KC_EMIT_CHUNK characters; one group of 256 work items
+        // writes one chunk with coalesced stores.
+        u32 *chunks = ex.template alloc<u32>(N + 1);
+        ex.for_each(N + 1, [=] KC_HD_LAMBDA(u64 vv) {
+            u32 c = 0;
+            if (vv < N && fa[vv] == fin_start) {
+                u32 v = (u32) vv;
+                u64 cnt = q.length(v) - (s.edge_from[v] != KC_NONE ? (u64) s.ovl[v] : 0);
+                if (cnt > KC_EMIT_SHORT) c = (u32) ((cnt + KC_EMIT_CHUNK - 1) / KC_EMIT_CHUNK);
+            }
+            chunks[vv] = c;
+        }, KP_EMIT, N * 12);
+        const u32 n_chunks = ex.exclusive_scan(chunks, chunks, N + 1);
+        ex.for_each(N, [=] KC_HD_LAMBDA(u64 vv) {
+            u32 v = (u32) vv;
             if (fa[v] != fin_start) return;
+            u64 len = q.length(v);
+            u64 cnt = len - (s.edge_from[v] != KC_NONE ? (u64) s.ovl[v] : 0);
+            if (cnt > KC_EMIT_SHORT) return;
             u64 off = total - da[v];
+            u64 n_upper = len - k + 1;
+            for (u64 j = 0; j < cnt; ++j) ms[off + j] = kc_letter(q.symbol(v, j), j < n_upper);
+        }, KP_EMIT, N * 12);
+        ex.for_each((u64) n_chunks * 256, [=] KC_HD_LAMBDA(u64 w) {
+            u32 chunk = (u32) (w >> 8), lane = (u32) (w & 255);
+            // node owning this chunk: last v with chunks[v] <= chunk (chunks[] is the exclusive prefix, N+1 entries)
+            u32 lo = 0, hi = (u32) N;
+            while (lo < hi) {
+                u32 mid = (lo + hi + 1) >> 1;
+                if (chunks[mid] <= chunk) lo = mid;
+                else hi = mid - 1;
+            }
+            u32 v = lo;
             u64 len = q.length(v);
             u64 cnt = len - (s.edge_from[v] != KC_NONE ? (u64) s.ovl[v] : 0);
             u64 n_upper = len - k + 1;
-            for (u64 j = lane; j < cnt; j += 32) ms[off + j] = kc_letter(q.symbol(v, j), j < n_upper);
-        });
+            u64 off = total - da[v];
+            u64 j0 = (u64) (chunk - chunks[v]) * KC_EMIT_CHUNK;
+            u64 j1 = j0 + KC_EMIT_CHUNK < cnt ? j0 + KC_EMIT_CHUNK : cnt;
+            for (u64 j = j0 + lane; j < j1; j += 256) ms[off + j] = kc_letter(q.symbol(v, j), j < n_upper);
+        }, KP_EMIT, 2 * total);
     }
     if (want_maxone) {
         u8 *mo = ex.template alloc<u8>(total + 1);
@@ -161,7 +196,7 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
             u64 pos = kmer_lower_bound(set_keys, n_set, x);
             bool present = pos < n_set && set_keys[pos] == x;  // src/khash_utils.h:98-103 containsKMer
             mo[p] = present ? (u8) (c - ('a' - 'A')) : c;
-        });
+        }, KP_MAXONE, 2 * total);
     }
     res.n_printed = nv.n;  // one strand: every node or its mirror
     (void) mark;

@@ -313,7 +313,7 @@ template <class Exec, int L> struct Engine {
                 T[i] = tuple_make(kmer_prefix(v.first_kmer(x), v.k, d), meta);
                 tw[x] = s.chain_tail[x];
             }
-        });
+        }, KP_TUPLES, nt * (sizeof(KWord<L>) + sizeof(TW)));
         // 2. sort by (key, role, batch, id order)
         exec_sort<L + 1>(ex, T, T2, nt, 64 + 2 * d);
         // 3. active groups = positions where a prefix run starts right after a suffix run of the same key
@@ -356,7 +356,7 @@ template <class Exec, int L> struct Engine {
             // 4. replay every pair of groups
             c.n_bans = n_bans;
             SimulatePairFn<L> sim{c, group_pstart};
-            ex.for_each(n_groups, sim);
+            ex.for_each(n_groups, sim, KP_SIMULATE);
             // 5. edges of this level, one slot per edge
             u32 *so = slot_of;
             n_edges = ex.compact_if(
@@ -439,7 +439,7 @@ template <class Exec, int L> struct Engine {
             jump_a[r] = cont ? so[t] : KC_NONE;
             fin_a[r] = t;
             max_a[r] = stp[x];
-        });
+        }, KP_DOUBLING, (u64) ne * 36);
         int rounds = kc_ceil_log2(ne) + 1;
         for (int it = 0; it < rounds; ++it) {
             const u32 *ja = jump_a, *fa = fin_a;
@@ -458,7 +458,7 @@ template <class Exec, int L> struct Engine {
                     u64 m1 = ma[r], m2 = ma[j];
                     mb[r] = m1 > m2 ? m1 : m2;
                 }
-            });
+            }, KP_DOUBLING, (u64) ne * 32);
             u32 *t = jump_a; jump_a = jump_b; jump_b = t;
             t = fin_a; fin_a = fin_b; fin_b = t;
             u64 *m = max_a; max_a = max_b; max_b = m;
@@ -489,7 +489,7 @@ template <class Exec, int L> struct Engine {
                     s.chain_tail[h] = t;
                     s.chain_head[t] = h;
                 }
-            });
+            }, KP_COMMIT, (u64) ne * 16);
             ex.arena->release(mark);
             return true;
         }

@@ -55,15 +55,27 @@ inline int kc_ceil_log2(u64 x) {
 struct Arena {
     char *base = nullptr;
     size_t cap = 0;
-    size_t off = 0;
+    size_t off = 0;   // bottom end: temporaries, stack discipline (mark / release)
+    size_t top = 0;   // top end: small results that must outlive the temporaries below them
     size_t high = 0;
+    void reset() {
+        off = 0;
+        top = cap;
+    }
     template <typename T> T *alloc(size_t n) {
         size_t bytes = kc_align_up((n ? n : 1) * sizeof(T), 256);
-        if (off + bytes > cap) KC_THROW(KC_ERR_OOM, "device arena exhausted");
+        if (off + bytes > top) KC_THROW(KC_ERR_OOM, "device arena exhausted");
         T *p = reinterpret_cast<T *>(base + off);
         off += bytes;
-        if (off > high) high = off;
+        if (off + (cap - top) > high) high = off + (cap - top);
         return p;
+    }
+    template <typename T> T *alloc_top(size_t n) {
+        size_t bytes = kc_align_up((n ? n : 1) * sizeof(T), 256);
+        if (off + bytes > top) KC_THROW(KC_ERR_OOM, "device arena exhausted");
+        top -= bytes;
+        if (off + (cap - top) > high) high = off + (cap - top);
+        return reinterpret_cast<T *>(base + top);
     }
     size_t mark() const { return off; }
     void release(size_t m) { off = m; }

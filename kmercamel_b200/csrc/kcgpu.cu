@@ -71,9 +71,10 @@ void ensure_arena(kc_ctx *ctx, size_t need) {
     KC_CUDA(cudaMemGetInfo(&free_b, &total_b));
     size_t limit = (size_t) (free_b * 0.92);
     size_t want = need < limit ? need : limit;
+    want &= ~(size_t) 4095;  // both arena ends stay 256-byte aligned
     KC_CUDA(cudaMalloc(&ctx->arena.base, want));
     ctx->arena.cap = want;
-    ctx->arena.off = 0;
+    ctx->arena.reset();
 }
 
 // Generous upper estimate of the arena bytes one kc_compute needs (see DESIGN.md "memory").
@@ -107,7 +108,7 @@ template <int L> u64 run_stage1(kc_ctx *ctx, CudaExec &ex, const DevInput &in, c
     const size_t base_mark = ex.arena->mark();
     KWord<L> *keys_a = ex.alloc<KWord<L>>(in.n_bytes);
     KC_CUDA(cudaEventRecord(ctx->ev[0], ex.stream));
-    const u64 M = kc_extract_kmers<L>(ex, in.seq, in.n_bytes, p.k, p.complements != 0, keys_a);
+    const u64 M = kc_extract_kmers<L, false>(ex, in.seq, in.n_bytes, p.k, p.complements != 0, keys_a);
     KC_CUDA(cudaEventRecord(ctx->ev[1], ex.stream));
     *n_occ = M;
     if (M == 0) {
@@ -122,7 +123,7 @@ template <int L> u64 run_stage1(kc_ctx *ctx, CudaExec &ex, const DevInput &in, c
     KWord<L> *keys_b = ex.alloc<KWord<L>>(M);
     u8 *cnt_a = ex.alloc<u8>(M);
     u8 *cnt_b = ex.alloc<u8>(M);
-    const u64 U = kc_sort_dedup<L>(ex, keys_a, keys_b, cnt_a, keys_b, cnt_b, M, 2 * p.k, p.min_frequency);
+    const u64 U = kc_sort_dedup<L, false>(ex, keys_a, keys_b, cnt_a, keys_b, cnt_b, M, 2 * p.k, p.min_frequency);
     // compact the survivors down to the stage's base so everything above can be reused
     ex.arena->release(base_mark);
     KWord<L> *uniq = ex.alloc<KWord<L>>(U);
@@ -135,6 +136,83 @@ template <int L> u64 run_stage1(kc_ctx *ctx, CudaExec &ex, const DevInput &in, c
     KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
     *uniq_out = uniq;
     *cnt_out = cnt;
+    return U;
+}
+
+// From-FASTA regime: the nodes handed to the overlap stage are FIRST-OCCURRENCE RUNS.
+//
+// The reference turns the k-mer set into simplitigs by walking a hash table (src/simplitigs.h:105-205); which
+// simplitigs come out depends on khash iteration order and is unspecified (its tests sort them before comparing).
+// Here every k-mer occurrence carries the position of its window through the dedup sort, the distinct k-mer keeps
+// its smallest position, and those positions are flagged in the input.  A maximal run of consecutive flagged
+// positions is a path of distinct k-mers whose neighbours overlap by k-1 (adjacent windows of one record): a
+// simplitig read directly off the input, with no hash walk and no per-k-mer pointer chasing.  Runs are numbered
+// in input order and go through the same overlap levels d = k-1..0 as `-S` records, so run ends that overlap by
+// k-1 are still joined first, exactly as BIGREEDY requires.
+struct RunNodes {
+    u64 *rec_off = nullptr, *rec_len = nullptr;  // arena top end
+    u64 n_runs = 0;
+};
+
+template <int L>
+u64 run_stage1_runs(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, RunNodes *runs, KWord<L> **set_out, u64 *n_occ) {
+    typedef KWord<L + 1> Item;
+    const size_t base_mark = ex.arena->mark();
+    Item *items_a = ex.alloc<Item>(in.n_bytes);
+    KC_CUDA(cudaEventRecord(ctx->ev[0], ex.stream));
+    const u64 M = kc_extract_kmers<L, true>(ex, in.seq, in.n_bytes, p.k, p.complements != 0, items_a);
+    KC_CUDA(cudaEventRecord(ctx->ev[1], ex.stream));
+    *n_occ = M;
+    *set_out = nullptr;
+    if (M == 0) {
+        ex.arena->release(base_mark);
+        KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
+        return 0;
+    }
+    ex.arena->release(base_mark);
+    items_a = ex.alloc<Item>(M);  // same address, trimmed to M
+    Item *items_b = ex.alloc<Item>(M);
+    u8 *cnt_a = ex.alloc<u8>(M);
+    u8 *cnt_b = ex.alloc<u8>(M);
+    const u64 U = kc_sort_dedup<L + 1, true>(ex, items_a, items_b, cnt_a, items_b, cnt_b, M, 64 + 2 * p.k, p.min_frequency);
+    if (U == 0) {
+        ex.arena->release(base_mark);
+        KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
+        return 0;
+    }
+    // flag the first occurrence of every kept k-mer
+    const u64 nb = in.n_bytes;
+    u8 *flags = ex.alloc<u8>(nb + 1);
+    ex.fill_bytes(flags, 0, nb + 1);
+    const Item *uq = items_b;
+    ex.for_each(U, [=] __device__(u64 i) { flags[uq[i].w[0]] = 1; }, KP_MISC, U * (sizeof(Item) + 1));
+    auto is_start = [=] __device__(u64 q) { return flags[q] && (q == 0 || !flags[q - 1]); };
+    auto is_end = [=] __device__(u64 q) { return flags[q] && !flags[q + 1]; };  // flags[nb] == 0
+    const u64 n_runs = ex.compact_if(nb, is_start, [=] __device__(u64, u32) {}, nb);
+    u64 *rec_off = ex.arena->alloc_top<u64>(n_runs), *rec_len = ex.arena->alloc_top<u64>(n_runs);
+    ex.compact_if(nb, is_start, [=] __device__(u64 q, u32 r) { rec_off[r] = q; }, nb);
+    const int k = p.k;
+    // window END positions e_s..e_t  ->  bytes [e_s - k + 1, e_t]
+    ex.compact_if(nb, is_end, [=] __device__(u64 q, u32 r) {
+        u64 e_s = rec_off[r];
+        rec_len[r] = q - e_s + k;
+        rec_off[r] = e_s - (k - 1);
+    }, nb);
+    if (p.want_maxone) {  // the sorted k-mer set doubles as kMersDict of src/global.h:165-167
+        KWord<L> *set = ex.arena->alloc_top<KWord<L>>(U);
+        ex.for_each(U, [=] __device__(u64 i) {
+            KWord<L> x;
+#pragma unroll
+            for (int j = 0; j < L; ++j) x.w[j] = uq[i].w[j + 1];
+            set[i] = x;
+        }, KP_MISC, U * (sizeof(Item) + sizeof(KWord<L>)));
+        *set_out = set;
+    }
+    ex.arena->release(base_mark);
+    KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
+    runs->rec_off = rec_off;
+    runs->rec_len = rec_len;
+    runs->n_runs = n_runs;
     return U;
 }
 
@@ -152,13 +230,16 @@ template <int L> void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in
     ns.seq = in.seq;
     ns.rec_off = in.rec_off;
     ns.rec_len = in.rec_len;
+    u64 n_nodes = 0;
+    const u64 *node_off = in.rec_off, *node_len = in.rec_len;
     if (!p.assume_simplitigs) {
-        U = run_stage1<L>(ctx, ex, in, p, &uniq, &cnt, &n_occ);
+        RunNodes runs;
+        U = run_stage1_runs<L>(ctx, ex, in, p, &runs, &uniq, &n_occ);
         if (U == 0) KC_THROW(KC_ERR_EMPTY, "the input contains no k-mers");  // src/main.cpp:155-158
-        if (U * (complements ? 2 : 1) >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "too many k-mers for one GPU");
-        nv.first = nv.last = uniq;
-        nv.n = (u32) U;
-        ns.kmers = uniq;
+        n_nodes = runs.n_runs;
+        node_off = runs.rec_off;
+        node_len = runs.rec_len;
+        if (n_nodes * (complements ? 2 : 1) >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "too many nodes for one GPU");
     } else {
         if (in.n_recs == 0) KC_THROW(KC_ERR_EMPTY, "input cannot be empty");  // src/global.h:219-221
         if (in.n_recs * (complements ? 2 : 1) >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "too many records for one GPU");
@@ -169,14 +250,20 @@ template <int L> void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in
             KC_CUDA(cudaEventRecord(ctx->ev[1], ex.stream));
             KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
         }
-        KWord<L> *first = ex.alloc<KWord<L>>(in.n_recs), *last = ex.alloc<KWord<L>>(in.n_recs);
+        n_nodes = in.n_recs;
+    }
+    {
+        KWord<L> *first = ex.alloc<KWord<L>>(n_nodes), *last = ex.alloc<KWord<L>>(n_nodes);
         u32 *err = ex.alloc<u32>(1);
         ex.fill_bytes(err, 0, 4);
-        kc_extract_node_ends<L>(ex, in.seq, in.n_bytes, in.rec_off, in.rec_len, in.n_recs, p.k, first, last, err);
+        kc_extract_node_ends<L>(ex, in.seq, in.n_bytes, node_off, node_len, n_nodes, p.k, first, last, err,
+                                /*validate_bytes=*/p.assume_simplitigs != 0);
         if (ex.read(err)) KC_THROW(KC_ERR_BAD_SEQ, "-S input must hold only ACGT records of at least k bases");
         nv.first = first;
         nv.last = last;
-        nv.n = (u32) in.n_recs;
+        nv.n = (u32) n_nodes;
+        ns.rec_off = node_off;
+        ns.rec_len = node_len;
     }
     nv.N = nv.n * (complements ? 2u : 1u);
     ns.n = nv.n;
@@ -308,14 +395,13 @@ int kc_compute_device(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_ou
     KC_CUDA(cudaSetDevice(ctx->device));
     const int limbs = kc_limbs_for_k(p->k);
     ensure_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, p->assume_simplitigs != 0));
-    ctx->arena.off = 0;
+    ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
     DevInput di{in->seq, in->n_bytes, in->rec_off, in->rec_len, in->n_recs};
     DevResult res;
     dispatch_pipeline(ctx, ex, di, *p, res);
     KC_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->prof.resolve();
     out->ms = const_cast<u8 *>(res.ms);
     out->ms_maxone = const_cast<u8 *>(res.maxone);
     out->length = res.length;
@@ -337,7 +423,7 @@ int kc_compute(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *o
     const int limbs = kc_limbs_for_k(p->k);
     const bool simplitigs = p->assume_simplitigs != 0;
     ensure_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, simplitigs));
-    ctx->arena.off = 0;
+    ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
     // host -> device
@@ -366,7 +452,6 @@ int kc_compute(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *o
     if (res.maxone)
         KC_CUDA(cudaMemcpyAsync(ctx->pin_out + res.length, res.maxone, res.length, cudaMemcpyDeviceToHost, ctx->stream));
     KC_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->prof.resolve();
     out->ms = ctx->pin_out;
     out->ms_maxone = res.maxone ? ctx->pin_out + res.length : nullptr;
     out->length = res.length;
@@ -398,7 +483,7 @@ int kc_count_kmers(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t
     const int limbs = kc_limbs_for_k(p->k);
     size_t need = (size_t) ((double) in->n_bytes * (1.0 + 2.0 * 8 * limbs + 4.0) * 1.15) + (256u << 20);
     ensure_arena(ctx, need);
-    ctx->arena.off = 0;
+    ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
     u8 *d_seq = ex.alloc<u8>(in->n_bytes + 64);
@@ -407,7 +492,6 @@ int kc_count_kmers(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t
     if (p->k < 32) count_only<1>(ctx, ex, di, *p, keys, counts, n);
     else if (p->k < 64) count_only<2>(ctx, ex, di, *p, keys, counts, n);
     else count_only<4>(ctx, ex, di, *p, keys, counts, n);
-    ctx->prof.resolve();
     return KC_OK;
     KC_API_END(ctx)
 }
@@ -422,13 +506,12 @@ int kc_overlap_path(kc_ctx *ctx, const uint64_t *first, const uint64_t *last, ui
     KC_CUDA(cudaSetDevice(ctx->device));
     const int limbs = kc_limbs_for_k(k);
     ensure_arena(ctx, estimate_arena(0, n, limbs, complements != 0, true) + n * 16 * limbs);
-    ctx->arena.off = 0;
+    ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
     if (k < 32) overlap_only<1>(ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
     else if (k < 64) overlap_only<2>(ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
     else overlap_only<4>(ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
-    ctx->prof.resolve();
     return KC_OK;
     KC_API_END(ctx)
 }
@@ -441,6 +524,10 @@ int kc_profile_enable(kc_ctx *ctx, int on) {
 int kc_profile_count(void) { return KP_COUNT; }
 int kc_profile_get(kc_ctx *ctx, int i, const char **name, double *ms, uint64_t *launches, uint64_t *bytes) {
     if (!ctx || i < 0 || i >= KP_COUNT) return KC_ERR_ARG;
+    if (!ctx->prof.pending.empty()) {
+        cudaStreamSynchronize(ctx->stream);
+        ctx->prof.resolve();
+    }
     if (name) *name = kc_prof_names[i];
     if (ms) *ms = ctx->prof.ms[i];
     if (launches) *launches = ctx->prof.launches[i];
@@ -449,6 +536,8 @@ int kc_profile_get(kc_ctx *ctx, int i, const char **name, double *ms, uint64_t *
 }
 int kc_profile_reset(kc_ctx *ctx) {
     if (!ctx) return KC_ERR_ARG;
+    cudaStreamSynchronize(ctx->stream);
+    ctx->prof.resolve();
     ctx->prof.reset();
     return KC_OK;
 }

@@ -60,7 +60,7 @@ __global__ void kc_sort_prep_kernel(SortBucket *big, u32 nb, u32 cap, u32 tile, 
 template <int L>
 __global__ void __launch_bounds__(256) kc_sort_hist_kernel(const KWord<L> *buf0, const KWord<L> *buf1, const SortBucket *big,
                                                            const u32 *tile_prefix, u32 nb, u32 n_tiles, u32 tiles_per_cta,
-                                                           u32 *hist) {
+                                                           u32 *hist, int low_bit) {
     constexpr int TILE = SortCfg<L>::TILE;
     __shared__ u32 sh[256];
     u32 t0 = blockIdx.x * tiles_per_cta;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) kc_sort_hist_kernel(const KWord<L> *buf0,
         u32 ti = t - tile_prefix[b];
         u32 start = ti * TILE;
         u32 cnt = min((u32) TILE, d.size - start);
-        int shift = d.rem - d.bits;
+        int shift = low_bit + d.rem - d.bits;
         for (u32 i = threadIdx.x; i < cnt; i += 256) {
             KWord<L> key = src[start + i];
             atomicAdd(&sh[key.digit(shift, d.bits)], 1u);
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) kc_sort_scan_kernel(const SortBucket *big
 template <int L>
 __global__ void __launch_bounds__(256) kc_sort_scatter_kernel(KWord<L> *buf0, KWord<L> *buf1, const SortBucket *big,
                                                               const u32 *tile_prefix, u32 nb, u32 n_tiles, u32 tiles_per_cta,
-                                                              u64 *cursor, const u8 *skip) {
+                                                              u64 *cursor, const u8 *skip, int low_bit) {
     constexpr int TILE = SortCfg<L>::TILE;
     constexpr int ITEMS = TILE / 256;
     extern __shared__ __align__(16) unsigned char kc_smem_raw[];
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256) kc_sort_scatter_kernel(KWord<L> *buf0, KW
         u32 ti = t - tile_prefix[b];
         u32 start = ti * TILE;
         u32 n_here = min((u32) TILE, d.size - start);
-        int shift = d.rem - d.bits;
+        int shift = low_bit + d.rem - d.bits;
         KWord<L> item[ITEMS];
         u32 rank[ITEMS];
 #pragma unroll
@@ -194,15 +194,68 @@ __global__ void __launch_bounds__(256) kc_sort_scatter_kernel(KWord<L> *buf0, KW
     }
 }
 
-// One CTA per bucket of at most CAP items: bitonic sort in shared memory.  In DEDUP mode the sorted run is
-// run-length encoded: unique keys go to the front of the bucket's slice of buf0, cnt[] receives
-// min(occurrences-1, 255) (the uint8 the reference keeps, src/parser.h:77,81) and the rest of the slice is filled
-// with the all-ones word, which is never a k-mer (2k < 64 L), for the compaction pass that follows.
-template <int L, bool DEDUP>
+// Sort modes: plain sort; dedup where the whole word is the key; dedup where limb 0 is a payload (the position of
+// the occurrence) and limbs 1.. are the key — the unique item keeps the smallest payload of its run.
+enum { KC_SORT_ONLY = 0, KC_SORT_DEDUP = 1, KC_SORT_DEDUP_PAYLOAD = 2 };
+
+template <int L, int MODE> KC_D bool kc_same_key(const KWord<L> &a, const KWord<L> &b) {
+    bool e = true;
+#pragma unroll
+    for (int i = (MODE == KC_SORT_DEDUP_PAYLOAD ? 1 : 0); i < L; ++i) e = e && (a.w[i] == b.w[i]);
+    return e;
+}
+
+// Cooperative bitonic sort of the shared-memory segment seg[0..m) by the whole CTA (any m: pairs whose partner
+// index is >= m are skipped, which is exact because every compare-exchange moves the larger word up).
+template <int L> KC_D void kc_block_bitonic(KWord<L> *seg, u32 m) {
+    u32 P = 2;
+    while (P < m) P <<= 1;
+    for (u32 k = 2; k <= P; k <<= 1) {
+        for (u32 j = k >> 1; j > 0; j >>= 1) {
+            for (u32 t = threadIdx.x; t < (P >> 1); t += 256) {
+                u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                u32 l = (j == (k >> 1)) ? (i ^ (k - 1)) : (i | j);  // first step of a merge mirrors, the rest are strides
+                if (l < m && i < m) {
+                    KWord<L> a = seg[i], c = seg[l];
+                    if (c < a) {
+                        seg[i] = c;
+                        seg[l] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// One CTA per bucket of at most CAP items.
+//   1. items go global -> registers; each takes a slot in a shared-memory counting sort on its next <= 11 key bits
+//      (one shared atomicAdd per item gives digit count and rank at once; order inside a digit is irrelevant);
+//   2. after a block scan of the digit counts the items are scattered into shared memory: they are now sorted
+//      except inside sub-buckets, which for k-mer data hold ~1 distinct key (plus its duplicates);
+//   3. sub-buckets of up to KC_SUB_SMALL items are finished by one thread each (insertion sort in shared memory),
+//      the rare larger ones by the whole CTA with a bitonic network (whole words are compared, so a payload limb
+//      orders equal keys by payload).
+// In the dedup modes the sorted run is then run-length encoded: unique items go to the front of the bucket's slice
+// of buf0, cnt[] receives min(occurrences-1, 255) (the uint8 the reference keeps, src/parser.h:77,81) and the rest
+// of the slice is filled with the all-ones word, whose top limb is never that of a k-mer (2k <= 64 L - 2), for
+// the compaction pass that follows.  ~10 shared-memory touches per item instead of ~110 for a full bitonic sort.
+static const u32 KC_SUB_SMALL = 24;
+static const int KC_SUB_BITS_MAX = 11;
+
+template <int L, int MODE>
 __global__ void __launch_bounds__(256) kc_sort_local_kernel(KWord<L> *buf0, const KWord<L> *buf1, const SortBucket *small,
-                                                            u8 *cnt_out) {
+                                                            u8 *cnt_out, int low_bit) {
+    constexpr int CAP = SortCfg<L>::CAP;
+    constexpr int ITEMS = CAP / 256;
     extern __shared__ __align__(16) unsigned char kc_smem_raw[];
     KWord<L> *s = reinterpret_cast<KWord<L> *>(kc_smem_raw);
+    u16 *hpos = reinterpret_cast<u16 *>(s + CAP);              // dedup: run heads (CAP entries)
+    __shared__ u32 sub_cnt[1 << KC_SUB_BITS_MAX];              // digit counts, then exclusive starts
+    __shared__ u32 big_list[64];
+    __shared__ u32 n_big;
+    __shared__ u32 sw[8];
+    __shared__ u32 uniq_total;
     SortBucket d = small[blockIdx.x];
     const KWord<L> *src = (d.parity ? buf1 : buf0) + d.off;
     KWord<L> *dst = buf0 + d.off;
@@ -210,41 +263,102 @@ __global__ void __launch_bounds__(256) kc_sort_local_kernel(KWord<L> *buf0, cons
     if (size == 1) {
         if (threadIdx.x == 0) {
             dst[0] = src[0];
-            if (DEDUP) cnt_out[d.off] = 0;
+            if (MODE != KC_SORT_ONLY) cnt_out[d.off] = 0;
         }
         return;
     }
-    u32 P = 2;
-    while (P < size) P <<= 1;
-    for (u32 i = threadIdx.x; i < P; i += 256) s[i] = i < size ? src[i] : KWord<L>::ones();
+    // digit width: about two sub-buckets per item, bounded by the key bits that are left
+    int bits = 1;
+    while ((1u << bits) < 2 * size && bits < KC_SUB_BITS_MAX) ++bits;
+    if (bits > (int) d.rem) bits = d.rem;
+    const u32 n_sub = 1u << bits;
+    const int shift = low_bit + d.rem - bits;
+    for (u32 i = threadIdx.x; i < n_sub; i += 256) sub_cnt[i] = 0;
+    if (threadIdx.x == 0) n_big = 0;
     __syncthreads();
-    for (u32 k = 2; k <= P; k <<= 1) {
-        for (u32 j = k >> 1; j > 0; j >>= 1) {
-            for (u32 t = threadIdx.x; t < (P >> 1); t += 256) {
-                u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                u32 l = i | j;
-                KWord<L> a = s[i], c = s[l];
-                bool up = (i & k) == 0;
-                if ((c < a) == up) {
-                    s[i] = c;
-                    s[l] = a;
-                }
-            }
-            __syncthreads();
+    KWord<L> item[ITEMS];
+    u32 slot[ITEMS];  // digit << 13 | rank inside the digit (rank < CAP <= 8192)
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        u32 i = threadIdx.x + j * 256;
+        if (i < size) {
+            item[j] = src[i];
+            u32 dg = bits ? item[j].digit(shift, bits) : 0;
+            slot[j] = (dg << 13) | atomicAdd(&sub_cnt[dg], 1u);
         }
     }
-    if (!DEDUP) {
+    __syncthreads();
+    // exclusive scan of the digit counts (n_sub <= 2048: 8 consecutive entries per thread)
+    {
+        u32 v[8], c = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            u32 i = threadIdx.x * 8 + j;
+            v[j] = i < n_sub ? sub_cnt[i] : 0;
+            c += v[j];
+        }
+        u32 total;
+        u32 p = kc_block_exclusive_scan_256(c, &total, sw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            u32 i = threadIdx.x * 8 + j;
+            if (i < n_sub) {
+                sub_cnt[i] = p;
+                // finish small sub-buckets later from [p, p + v[j]); remember the oversized ones
+                if (v[j] > KC_SUB_SMALL) {
+                    u32 q = atomicAdd(&n_big, 1u);
+                    if (q < 64) big_list[q] = i;
+                }
+            }
+            p += v[j];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        u32 i = threadIdx.x + j * 256;
+        if (i < size) s[sub_cnt[slot[j] >> 13] + (slot[j] & 8191u)] = item[j];
+    }
+    __syncthreads();
+    const u32 nbig = n_big;
+    if (nbig > 64) {
+        // pathological bucket (many oversized sub-buckets): sort it whole
+        kc_block_bitonic<L>(s, size);
+    } else {
+        // one thread per small sub-bucket: insertion sort of its segment
+        for (u32 b = threadIdx.x; b < n_sub; b += 256) {
+            u32 lo = sub_cnt[b];
+            u32 hi = (b + 1 < n_sub) ? sub_cnt[b + 1] : size;
+            u32 m = hi - lo;
+            if (m < 2 || m > KC_SUB_SMALL) continue;
+            for (u32 x = lo + 1; x < hi; ++x) {
+                KWord<L> key = s[x];
+                u32 y = x;
+                while (y > lo && key < s[y - 1]) {
+                    s[y] = s[y - 1];
+                    --y;
+                }
+                s[y] = key;
+            }
+        }
+        __syncthreads();
+        for (u32 q = 0; q < nbig; ++q) {  // uniform across the CTA
+            u32 b = big_list[q];
+            u32 lo = sub_cnt[b];
+            u32 hi = (b + 1 < n_sub) ? sub_cnt[b + 1] : size;
+            kc_block_bitonic<L>(s + lo, hi - lo);
+        }
+    }
+    __syncthreads();
+    if (MODE == KC_SORT_ONLY) {
         for (u32 i = threadIdx.x; i < size; i += 256) dst[i] = s[i];
         return;
     }
-    // run-length encode: hpos[u] = index of the first item of the u-th distinct key
-    u16 *hpos = reinterpret_cast<u16 *>(s + SortCfg<L>::CAP);
-    __shared__ u32 sw[8];
-    __shared__ u32 uniq_total;
+    // run-length encode: hpos[u] = index of the first item of the u-th distinct key (indices < CAP <= 8192 fit u16)
     u32 carry = 0;
     for (u32 base = 0; base < size; base += 256) {  // block-scan the head flags 256 at a time
         u32 i = base + threadIdx.x;
-        u32 head = (i < size && (i == 0 || s[i] != s[i - 1])) ? 1u : 0u;
+        u32 head = (i < size && (i == 0 || !kc_same_key<L, MODE>(s[i], s[i - 1]))) ? 1u : 0u;
         u32 total;
         u32 p = kc_block_exclusive_scan_256(head, &total, sw);
         if (head) hpos[carry + p] = (u16) i;
@@ -253,14 +367,11 @@ __global__ void __launch_bounds__(256) kc_sort_local_kernel(KWord<L> *buf0, cons
     if (threadIdx.x == 0) uniq_total = carry;
     __syncthreads();
     const u32 nu = uniq_total;
-    // hpos may hold CAP = 8192 > 65535?  No: indices are < CAP <= 8192, fine for u16.
     for (u32 u = threadIdx.x; u < size; u += 256) {
         if (u < nu) {
             u32 h = hpos[u];
             u32 e = (u + 1 < nu) ? hpos[u + 1] : size;
-            KWord<L> key = s[h];
-            // cannot write dst[u] before every thread has read s[]: s is shared memory, dst is global -> no hazard
-            dst[u] = key;
+            dst[u] = s[h];  // first of its run: with a payload limb, the smallest payload
             cnt_out[d.off + u] = (u8) min(e - h - 1, 255u);
         } else {
             dst[u] = KWord<L>::ones();
@@ -268,27 +379,39 @@ __global__ void __launch_bounds__(256) kc_sort_local_kernel(KWord<L> *buf0, cons
     }
 }
 
-// Buckets that ran out of key bits: all items equal.
-template <int L, bool DEDUP>
+// Buckets that ran out of key bits: all keys equal (payloads may differ).
+template <int L, int MODE>
 __global__ void __launch_bounds__(256) kc_sort_uniform_kernel(KWord<L> *buf0, const KWord<L> *buf1, const SortBucket *uniform,
                                                               u8 *cnt_out) {
+    __shared__ kc_ull min_payload;
     SortBucket d = uniform[blockIdx.x];
     const KWord<L> *src = (d.parity ? buf1 : buf0) + d.off;
     KWord<L> *dst = buf0 + d.off;
     KWord<L> key = src[0];
+    if (MODE == KC_SORT_DEDUP_PAYLOAD) {
+        if (threadIdx.x == 0) min_payload = ~0ULL;
+        __syncthreads();
+        u64 m = ~0ULL;
+        for (u32 i = threadIdx.x; i < d.size; i += 256) m = min(m, src[i].w[0]);
+        atomicMin(&min_payload, (kc_ull) m);
+        __syncthreads();
+        key.w[0] = min_payload;
+    }
     __syncthreads();
     for (u32 i = threadIdx.x; i < d.size; i += 256) {
-        if (DEDUP) {
+        if (MODE != KC_SORT_ONLY) {
             dst[i] = i == 0 ? key : KWord<L>::ones();
             if (i == 0) cnt_out[d.off] = (u8) min(d.size - 1, 255u);
         } else if (d.parity) {
-            dst[i] = key;
+            dst[i] = src[i];
         }
     }
 }
 
-template <int L, bool DEDUP>
-void kc_sort_impl(CudaExec &ex, KWord<L> *buf0, KWord<L> *buf1, u64 n, int key_bits, u8 *cnt_tmp) {
+// Radix levels consume the bits [low_bit, key_bits) from the top; bits below low_bit only matter to the final
+// shared-memory sort (which compares whole words).
+template <int L, int MODE>
+void kc_sort_impl(CudaExec &ex, KWord<L> *buf0, KWord<L> *buf1, u64 n, int key_bits, int low_bit, u8 *cnt_tmp) {
     typedef SortCfg<L> Cfg;
     if (n == 0) return;
     if (n >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "sort of more than 2^32 items");
@@ -310,10 +433,10 @@ void kc_sort_impl(CudaExec &ex, KWord<L> *buf0, KWord<L> *buf1, u64 n, int key_b
     ex.fill_bytes(ctr, 0, 16);
 
     static bool attr_done = false;
-    const int local_smem = Cfg::CAP * (int) sizeof(KWord<L>) + (DEDUP ? Cfg::CAP * 2 : 0);
+    const int local_smem = Cfg::CAP * (int) sizeof(KWord<L>) + Cfg::CAP * 2;
     const int scatter_smem = Cfg::TILE * (int) sizeof(KWord<L>);
     if (!attr_done) {
-        KC_CUDA(cudaFuncSetAttribute(kc_sort_local_kernel<L, DEDUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, local_smem));
+        KC_CUDA(cudaFuncSetAttribute(kc_sort_local_kernel<L, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, local_smem));
         KC_CUDA(cudaFuncSetAttribute(kc_sort_scatter_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_smem));
         attr_done = true;
     }
@@ -321,7 +444,7 @@ void kc_sort_impl(CudaExec &ex, KWord<L> *buf0, KWord<L> *buf1, u64 n, int key_b
     SortBucket root;
     root.off = 0;
     root.size = (u32) n;
-    root.rem = (u16) key_bits;
+    root.rem = (u16) (key_bits - low_bit);
     root.parity = 0;
     root.bits = 0;
     u32 nb = 0, n_small = 0, n_uniform = 0;
@@ -329,7 +452,7 @@ void kc_sort_impl(CudaExec &ex, KWord<L> *buf0, KWord<L> *buf1, u64 n, int key_b
         KC_CUDA(cudaMemcpyAsync(small, &root, sizeof(root), cudaMemcpyHostToDevice, st));
         KC_CUDA(cudaStreamSynchronize(st));
         n_small = 1;
-    } else if (key_bits == 0) {
+    } else if (root.rem == 0) {
         KC_CUDA(cudaMemcpyAsync(uniform, &root, sizeof(root), cudaMemcpyHostToDevice, st));
         KC_CUDA(cudaStreamSynchronize(st));
         n_uniform = 1;
@@ -352,7 +475,7 @@ void kc_sort_impl(CudaExec &ex, KWord<L> *buf0, KWord<L> *buf1, u64 n, int key_b
         const u64 level_bytes = (u64) n_tiles * Cfg::TILE * sizeof(KWord<L>);  // items still in oversized buckets
         {
             CudaExec::Scope sc(ex, KP_SORT_HIST, level_bytes);
-            kc_sort_hist_kernel<L><<<ctas, 256, 0, st>>>(buf0, buf1, cur, tile_prefix, nb, n_tiles, tiles_per_cta, hist);
+            kc_sort_hist_kernel<L><<<ctas, 256, 0, st>>>(buf0, buf1, cur, tile_prefix, nb, n_tiles, tiles_per_cta, hist, low_bit);
         }
         ++ex.launches;
         ex.fill_bytes(ctr, 0, 4);  // next-level big counter only
@@ -362,7 +485,7 @@ void kc_sort_impl(CudaExec &ex, KWord<L> *buf0, KWord<L> *buf1, u64 n, int key_b
         {
             CudaExec::Scope sc(ex, KP_SORT_SCATTER, 2 * level_bytes);
             kc_sort_scatter_kernel<L><<<ctas, 256, scatter_smem, st>>>(buf0, buf1, cur, tile_prefix, nb, n_tiles,
-                                                                        tiles_per_cta, cursor, skip);
+                                                                        tiles_per_cta, cursor, skip, low_bit);
         }
         ++ex.launches;
         KC_CUDA(cudaGetLastError());
@@ -379,11 +502,11 @@ void kc_sort_impl(CudaExec &ex, KWord<L> *buf0, KWord<L> *buf1, u64 n, int key_b
     }
     if (n_small) {
         CudaExec::Scope sc(ex, KP_SORT_LOCAL, 2 * n * sizeof(KWord<L>));
-        kc_sort_local_kernel<L, DEDUP><<<n_small, 256, local_smem, st>>>(buf0, buf1, small, cnt_tmp);
+        kc_sort_local_kernel<L, MODE><<<n_small, 256, local_smem, st>>>(buf0, buf1, small, cnt_tmp, low_bit);
         ++ex.launches;
     }
     if (n_uniform) {
-        kc_sort_uniform_kernel<L, DEDUP><<<n_uniform, 256, 0, st>>>(buf0, buf1, uniform, cnt_tmp);
+        kc_sort_uniform_kernel<L, MODE><<<n_uniform, 256, 0, st>>>(buf0, buf1, uniform, cnt_tmp);
         ++ex.launches;
     }
     KC_CUDA(cudaGetLastError());
@@ -392,25 +515,28 @@ void kc_sort_impl(CudaExec &ex, KWord<L> *buf0, KWord<L> *buf1, u64 n, int key_b
 
 // Sort buf0[0..n) ascending on its low key_bits bits (all higher bits must be zero); buf1 is scratch.
 template <int L> void kc_sort(CudaExec &ex, KWord<L> *buf0, KWord<L> *buf1, u64 n, int key_bits) {
-    kc_sort_impl<L, false>(ex, buf0, buf1, n, key_bits, nullptr);
+    kc_sort_impl<L, KC_SORT_ONLY>(ex, buf0, buf1, n, key_bits, 0, nullptr);
 }
 
 // Sort + dedup + count.  On return out_keys[0..U) holds the distinct keys with at least min_freq occurrences in
 // ascending order and out_cnt[0..U) their min(occurrences-1, 255); buf0 is destroyed.  out_keys may be buf1.
-template <int L>
+// PAYLOAD = true: limb 0 of every word is a payload (not part of the key); the surviving word of a key carries the
+// smallest payload of its occurrences.  key_bits counts from bit 0 of the whole word in both cases.
+template <int L, bool PAYLOAD>
 u64 kc_sort_dedup(CudaExec &ex, KWord<L> *buf0, KWord<L> *buf1, u8 *cnt_tmp, KWord<L> *out_keys, u8 *out_cnt, u64 n,
                   int key_bits, int min_freq) {
     if (n == 0) return 0;
-    kc_sort_impl<L, true>(ex, buf0, buf1, n, key_bits, cnt_tmp);
+    kc_sort_impl<L, PAYLOAD ? KC_SORT_DEDUP_PAYLOAD : KC_SORT_DEDUP>(ex, buf0, buf1, n, key_bits, PAYLOAD ? 64 : 0, cnt_tmp);
     const KWord<L> *src = buf0;
     const u8 *cs = cnt_tmp;
     const u32 need = (u32) (min_freq - 1);
     return ex.compact_if(
-        n, [=] __device__(u64 i) { return src[i] != KWord<L>::ones() && (u32) cs[i] >= need; },
+        n, [=] __device__(u64 i) { return src[i].w[L - 1] != ~0ULL && (u32) cs[i] >= need; },
         [=] __device__(u64 i, u32 r) {
             out_keys[r] = src[i];
             out_cnt[r] = cs[i];
-        });
+        },
+        n * (sizeof(KWord<L>) + 1));
 }
 
 #endif  // __CUDACC__

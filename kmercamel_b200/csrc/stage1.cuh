@@ -36,9 +36,12 @@ KC_D void kc_pack4(u32 w, u32 &codes, u32 &valid) {
     valid = (((m & 0x01010101u) * 0x08040201u) >> 24) & 0xFu;
 }
 
-template <int L>
+// WITH_POS = false: out[] receives the canonical k-mers (KWord<L>).
+// WITH_POS = true : out[] receives KWord<L+1> items {limb 0 = END position of the window in seq, limbs 1.. = k-mer},
+//                   the input of the first-occurrence dedup (kc_sort_dedup<L+1, true>).
+template <int L, bool WITH_POS>
 __global__ void __launch_bounds__(KC_EX_THREADS) kc_extract_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int complements,
-                                                                    KWord<L> *__restrict__ out, kc_ull *counter) {
+                                                                    KWord<L + (WITH_POS ? 1 : 0)> *__restrict__ out, kc_ull *counter) {
     __shared__ u64 pk[KC_EX_HALO + KC_EX_THREADS];
     __shared__ u32 vm[KC_EX_HALO + KC_EX_THREADS];
     __shared__ u32 sw[8];
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(KC_EX_THREADS) kc_extract_kernel(const u8 *__r
     if (block_total == 0) return;
 
     if (L == 1) {
-        // ---- 64-bit fast path (k < 32): funnel shifts, per-warp staging -------------------------------
+        // ---- 64-bit fast path (k < 32): funnel shifts ---------------------------------------------------
         u64 *stage = reinterpret_cast<u64 *>(kc_smem_raw) + (threadIdx.x >> 5) * (32 * KC_EX_STRIP);
         const u32 lane = threadIdx.x & 31;
         u32 warp_off = cnt;  // inclusive warp scan of cnt
@@ -115,6 +118,8 @@ __global__ void __launch_bounds__(KC_EX_THREADS) kc_extract_kernel(const u8 *__r
         }
         const u32 warp_total = __shfl_sync(0xFFFFFFFFu, warp_off, 31);
         u32 pos = warp_off - cnt;
+        kc_ull gpos = block_base + my_off;                     // WITH_POS: direct 16-byte stores
+        const u64 strip_pos0 = (u64) block_pos0 + (u64) threadIdx.x * KC_EX_STRIP;
         if (em) {
             const u64 prev = pk[widx - 1];
             const u64 mask = (k == 32) ? ~0ULL : ((1ULL << (2 * k)) - 1);
@@ -132,14 +137,23 @@ __global__ void __launch_bounds__(KC_EX_THREADS) kc_extract_kernel(const u8 *__r
                 u64 c = (mine >> sh) & 3;
                 u64 rcf = rcs | ((3 ^ c) << top);
                 rcs = rcf >> 2;
-                if ((em >> (31 - j)) & 1) stage[pos++] = (!complements || fwd < rcf) ? fwd : rcf;
+                if ((em >> (31 - j)) & 1) {
+                    const u64 canon = (!complements || fwd < rcf) ? fwd : rcf;
+                    if (WITH_POS) {
+                        *reinterpret_cast<ulonglong2 *>(&out[gpos++]) = make_ulonglong2(strip_pos0 + j, canon);
+                    } else {
+                        stage[pos++] = canon;
+                    }
+                }
             }
         }
-        __syncwarp();
-        // the warp's first global slot: block base + slots of the preceding warps = my_off of lane 0
-        const kc_ull warp_base = block_base + __shfl_sync(0xFFFFFFFFu, my_off, 0);
-        u64 *o64 = reinterpret_cast<u64 *>(out);
-        for (u32 q = lane; q < warp_total; q += 32) o64[warp_base + q] = stage[q];
+        if (!WITH_POS) {
+            __syncwarp();
+            // the warp's first global slot: block base + slots of the preceding warps = my_off of lane 0
+            const kc_ull warp_base = block_base + __shfl_sync(0xFFFFFFFFu, my_off, 0);
+            u64 *o64 = reinterpret_cast<u64 *>(out);
+            for (u32 q = lane; q < warp_total; q += 32) o64[warp_base + q] = stage[q];
+        }
     } else {
         // ---- generic path: roll both strands over KWord<L> ---------------------------------------------
         if (!em) return;
@@ -170,34 +184,42 @@ __global__ void __launch_bounds__(KC_EX_THREADS) kc_extract_kernel(const u8 *__r
             for (int i = 0; i < L; ++i)
                 if (i == top_limb) rcf.w[i] |= (3 ^ c) << top_off;
             rcs = rcf.shr(2);
-            if ((em >> (31 - j)) & 1) out[pos++] = (!complements || fwd < rcf) ? fwd : rcf;
+            if ((em >> (31 - j)) & 1) {
+                const KWord<L> canon = (!complements || fwd < rcf) ? fwd : rcf;
+                KWord<L + (WITH_POS ? 1 : 0)> item;
+                if (WITH_POS) item.w[0] = (u64) block_pos0 + (u64) threadIdx.x * KC_EX_STRIP + j;
+#pragma unroll
+                for (int i = 0; i < L; ++i) item.w[i + (WITH_POS ? 1 : 0)] = canon.w[i];
+                out[pos++] = item;
+            }
         }
     }
 }
 
 // Extract every canonical k-mer occurrence of seq[0..n_bytes) into out (capacity n_bytes); returns M.
-template <int L> u64 kc_extract_kmers(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, KWord<L> *out) {
+template <int L, bool WITH_POS>
+u64 kc_extract_kmers(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, KWord<L + (WITH_POS ? 1 : 0)> *out) {
     if (n_bytes == 0) return 0;
     size_t mark = ex.arena->mark();
     kc_ull *counter = reinterpret_cast<kc_ull *>(ex.alloc<u64>(1));
     ex.fill_bytes(counter, 0, 8);
     u64 blocks = kc_div_up(n_bytes, (u64) KC_EX_THREADS * KC_EX_STRIP);
-    const int smem = L == 1 ? 8 * 32 * KC_EX_STRIP * 8 : 0;
+    const int smem = (L == 1 && !WITH_POS) ? 8 * 32 * KC_EX_STRIP * 8 : 0;
     static bool attr_done = false;
     if (!attr_done && smem) {
-        KC_CUDA(cudaFuncSetAttribute(kc_extract_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        KC_CUDA(cudaFuncSetAttribute(kc_extract_kernel<L, WITH_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
     {
-        // algorithmic bytes: the input once; the M * 8L bytes written are added by the caller once M is known
+        // algorithmic bytes: the input once; the M item bytes written are added below once M is known
         CudaExec::Scope sc(ex, KP_EXTRACT, n_bytes);
-        kc_extract_kernel<L><<<(unsigned) blocks, KC_EX_THREADS, smem, ex.stream>>>(seq, n_bytes, k, complements ? 1 : 0, out,
-                                                                                     counter);
+        kc_extract_kernel<L, WITH_POS><<<(unsigned) blocks, KC_EX_THREADS, smem, ex.stream>>>(seq, n_bytes, k, complements ? 1 : 0,
+                                                                                               out, counter);
     }
     ++ex.launches;
     KC_CUDA(cudaGetLastError());
     u64 m = ex.read(reinterpret_cast<u64 *>(counter));
-    if (ex.prof && ex.prof->enabled) ex.prof->bytes[KP_EXTRACT] += m * sizeof(KWord<L>);
+    if (ex.prof && ex.prof->enabled) ex.prof->bytes[KP_EXTRACT] += m * sizeof(KWord<L + (WITH_POS ? 1 : 0)>);
     ex.arena->release(mark);
     return m;
 }
@@ -206,7 +228,7 @@ template <int L> u64 kc_extract_kmers(CudaExec &ex, const u8 *seq, u64 n_bytes, 
 // (src/simplitigs.h:82 asserts ACGT only; records shorter than k have no k-mer and are rejected here).
 template <int L>
 void kc_extract_node_ends(CudaExec &ex, const u8 *seq, u64 n_bytes, const u64 *rec_off, const u64 *rec_len, u64 n_recs, int k,
-                          KWord<L> *first, KWord<L> *last, u32 *error_flag) {
+                          KWord<L> *first, KWord<L> *last, u32 *error_flag, bool validate_bytes) {
     ex.for_each(n_recs, [=] __device__(u64 r) {
         u64 off = rec_off[r], len = rec_len[r];
         if (len < (u64) k) {
@@ -223,6 +245,7 @@ void kc_extract_node_ends(CudaExec &ex, const u8 *seq, u64 n_bytes, const u64 *r
         first[r] = f;
         last[r] = l;
     });
+    if (!validate_bytes) return;
     // every byte that is not a record separator must be a nucleotide
     ex.for_each(n_bytes, [=] __device__(u64 p) {
         u8 c = seq[p];

@@ -30,6 +30,7 @@ template <int L> int run(const std::string &mode, int k, bool complements, bool 
     Arena arena;
     arena.cap = (size_t) 1 << 30;
     arena.base = (char *) std::malloc(arena.cap);
+    arena.reset();
     HostExec ex{&arena};
     std::vector<KWord<L>> set;
     for (auto &r : recs)
