@@ -112,6 +112,9 @@ int kc_profile_count(void);
 int kc_profile_get(kc_ctx *ctx, int i, const char **name, double *ms, uint64_t *launches, uint64_t *bytes);
 int kc_profile_reset(kc_ctx *ctx);
 
+/* Tuning / test knobs.  "small_engine" (default 1): run the tail of the overlap levels in the single-CTA kernel. */
+int kc_set_option(kc_ctx *ctx, const char *name, int value);
+
 int kc_limbs_for_k(int k);
 void kc_free(void *p);
 const char *kc_strerror(int code);

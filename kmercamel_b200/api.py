@@ -74,6 +74,7 @@ def load_library():
                                  u64p]
     L.kc_overlap_path.argtypes = [C.c_void_p, u64p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, i64p, u8p]
     L.kc_frame_fasta.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(u8p), u64p, C.POINTER(u64p), C.POINTER(u64p), u64p]
+    L.kc_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.kc_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.kc_profile_count.restype = C.c_int
     L.kc_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), u64p, u64p]
@@ -90,7 +91,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ["kc_init", "kc_destroy", "kc_compute", "kc_compute_device", "kc_copy_to_host", "kc_count_kmers", "kc_overlap_path",
-                    "kc_frame_fasta", "kc_profile_enable", "kc_profile_count", "kc_profile_get", "kc_profile_reset",
+                    "kc_frame_fasta", "kc_set_option", "kc_profile_enable", "kc_profile_count", "kc_profile_get", "kc_profile_reset",
                     "kc_limbs_for_k", "kc_free", "kc_strerror", "kc_last_error"]
 
 
@@ -229,6 +230,9 @@ class Context:
                                               int(complements), int(lower_bound), int(strict), ef.ctypes.data_as(i64p),
                                               ov.ctypes.data_as(u8p)))
         return ef, ov
+
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.kc_set_option(self._h, name.encode(), int(value)))
 
     # ---- per-kernel-class timers ---------------------------------------------------------------------------
     def profile_enable(self, on: bool = True):

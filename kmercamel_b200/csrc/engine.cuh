@@ -224,6 +224,8 @@ template <int L> struct SimulatePairFn {
     }
 };
 
+#include "small_engine.cuh"
+
 // ---- engine -------------------------------------------------------------------------------------------
 struct EngineStats {
     u64 levels_run = 0, tuples_sorted = 0, groups = 0, edges = 0, ban_rounds = 0, bans = 0;
@@ -235,6 +237,7 @@ template <class Exec, int L> struct Engine {
     PathState st;
     bool strict;
     bool lower_bound;
+    bool use_small = true;  // hand the tail of the level loop to the single-CTA kernel (small_engine.cuh)
     EngineStats stats;
 
     // live end lists (ascending node id); nullptr = identity 0..N-1
@@ -282,8 +285,73 @@ template <class Exec, int L> struct Engine {
         for (int d = nv.k - 1; d >= 0; --d) {
             const u64 done = lower_bound ? 0 : (nv.complements ? 2 : 1);
             if (n_s <= done) break;  // one path (two mirror paths) left: nothing can merge any more
+            if (run_small(d)) break;
             run_level(d);
         }
+    }
+
+    // Runs levels d..0 in one kernel when the free ends fit in shared memory.  Device policy only.
+    bool run_small(int d) {
+#ifdef __CUDACC__
+        if constexpr (Exec::is_device) {
+            if (!use_small || lower_bound || n_s + n_p > SmallCfg<L>::T) return false;
+            if (!live_s) {  // identity lists were implicit
+                u32 *a = ex.template alloc<u32>(n_s), *b = ex.template alloc<u32>(n_p);
+                ex.for_each(nv.N, [=] KC_HD_LAMBDA(u64 i) {
+                    a[i] = (u32) i;
+                    b[i] = (u32) i;
+                });
+                live_s = a;
+                live_p = b;
+            }
+            SmallEngineArgs<L> a;
+            a.nv = nv;
+            a.st = st;
+            a.live_s_a = live_s;
+            a.live_p_a = live_p;
+            a.live_s_b = ex.template alloc<u32>(n_s);
+            a.live_p_b = ex.template alloc<u32>(n_p);
+            a.n_s = (u32) n_s;
+            a.n_p = (u32) n_p;
+            a.head_w = head_w;
+            a.tail_w = tail_w;
+            a.slot_of = slot_of;
+            a.stamp = stamp;
+            a.prim = prim;
+            a.ban_flag = ban_flag;
+            a.ban_i = ban_i;
+            a.ban_j = ban_j;
+            a.ban_cap = BAN_CAP;
+            a.d_start = d;
+            a.strict = strict;
+            a.out = ex.template alloc<u32>(8);
+            ex.fill_bytes(a.out, 0, 32);
+            static bool attr_done = false;
+            if (!attr_done) {
+                KC_CUDA(cudaFuncSetAttribute(kc_small_engine_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int) SmallCfg<L>::SMEM));
+                attr_done = true;
+            }
+            {
+                typename Exec::Scope sc(ex, KP_SMALL_ENGINE, 0);
+                kc_small_engine_kernel<L><<<1, 256, SmallCfg<L>::SMEM, ex.stream>>>(a);
+            }
+            ++ex.launches;
+            KC_CUDA(cudaGetLastError());
+            u32 h[8];
+            KC_CUDA(cudaMemcpyAsync(h, a.out, 32, cudaMemcpyDeviceToHost, ex.stream));
+            KC_CUDA(cudaStreamSynchronize(ex.stream));
+            if (h[0]) KC_THROW(KC_ERR_INTERNAL, "ban list overflow");
+            stats.levels_run += h[1];
+            stats.groups += h[2];
+            stats.edges += h[3];
+            stats.ban_rounds += h[4];
+            stats.bans += h[5];
+            return true;
+        }
+#endif
+        (void) d;
+        return false;
     }
 
     void run_level(int d) {

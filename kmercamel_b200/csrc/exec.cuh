@@ -35,11 +35,11 @@ typedef unsigned long long kc_ull;  // CUDA's 64-bit atomic type
 // Kernel classes for the per-kernel device timers (kc_profile_* in include/kcgpu.h).
 enum KcProfId {
     KP_EXTRACT, KP_SORT_HIST, KP_SORT_SCATTER, KP_SORT_LOCAL, KP_SORT_MISC, KP_COMPACT, KP_SCAN, KP_TUPLES,
-    KP_SIMULATE, KP_DOUBLING, KP_COMMIT, KP_RANK, KP_EMIT, KP_MAXONE, KP_MISC, KP_COUNT
+    KP_SIMULATE, KP_DOUBLING, KP_COMMIT, KP_SMALL_ENGINE, KP_RANK, KP_EMIT, KP_MAXONE, KP_MISC, KP_COUNT
 };
 static const char *const kc_prof_names[KP_COUNT] = {
     "extract", "sort_hist", "sort_scatter", "sort_local", "sort_misc", "compact", "scan", "tuples",
-    "simulate", "doubling", "commit", "rank", "emit", "maxone", "misc"};
+    "simulate", "doubling", "commit", "small_engine", "rank", "emit", "maxone", "misc"};
 
 // ---------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -9,8 +9,18 @@
 #include "sort.cuh"
 #include "stage1.cuh"
 
+#include <chrono>
 #include <new>
 #include <string>
+
+static double kc_now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static const bool kc_trace = std::getenv("KC_TRACE") != nullptr;
+#define KC_TRACE_POINT(label)                                                               \
+    do {                                                                                    \
+        if (kc_trace) std::fprintf(stderr, "[kc_trace] %-28s %.3f ms\n", (label), kc_now_ms()); \
+    } while (0)
 
 struct kc_ctx {
     int device = 0;
@@ -24,6 +34,8 @@ struct kc_ctx {
     u8 *pin_out = nullptr;
     size_t pin_out_cap = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool small_engine = true;
+    bool arena_limited = false;
     std::string last_error;
 };
 
@@ -61,7 +73,9 @@ void check_params(const kc_params *p) {
 
 // Make sure the arena can hold `need` bytes (bounded by what the device can give).
 void ensure_arena(kc_ctx *ctx, size_t need) {
+    need = (need + 4095) & ~(size_t) 4095;  // both arena ends stay 256-byte aligned
     if (ctx->arena.cap >= need) return;
+    if (ctx->arena.cap && ctx->arena_limited && need >= ctx->arena.cap) return;  // already holds all the device can give
     if (ctx->arena.base) {
         KC_CUDA(cudaFree(ctx->arena.base));
         ctx->arena.base = nullptr;
@@ -70,8 +84,8 @@ void ensure_arena(kc_ctx *ctx, size_t need) {
     size_t free_b = 0, total_b = 0;
     KC_CUDA(cudaMemGetInfo(&free_b, &total_b));
     size_t limit = (size_t) (free_b * 0.92);
-    size_t want = need < limit ? need : limit;
-    want &= ~(size_t) 4095;  // both arena ends stay 256-byte aligned
+    size_t want = need < limit ? need : (limit & ~(size_t) 4095);
+    ctx->arena_limited = want < need;
     KC_CUDA(cudaMalloc(&ctx->arena.base, want));
     ctx->arena.cap = want;
     ctx->arena.reset();
@@ -160,7 +174,9 @@ u64 run_stage1_runs(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_para
     const size_t base_mark = ex.arena->mark();
     Item *items_a = ex.alloc<Item>(in.n_bytes);
     KC_CUDA(cudaEventRecord(ctx->ev[0], ex.stream));
+    KC_TRACE_POINT("stage1: begin");
     const u64 M = kc_extract_kmers<L, true>(ex, in.seq, in.n_bytes, p.k, p.complements != 0, items_a);
+    KC_TRACE_POINT("stage1: extracted");
     KC_CUDA(cudaEventRecord(ctx->ev[1], ex.stream));
     *n_occ = M;
     *set_out = nullptr;
@@ -175,6 +191,7 @@ u64 run_stage1_runs(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_para
     u8 *cnt_a = ex.alloc<u8>(M);
     u8 *cnt_b = ex.alloc<u8>(M);
     const u64 U = kc_sort_dedup<L + 1, true>(ex, items_a, items_b, cnt_a, items_b, cnt_b, M, 64 + 2 * p.k, p.min_frequency);
+    KC_TRACE_POINT("stage1: deduped");
     if (U == 0) {
         ex.arena->release(base_mark);
         KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
@@ -209,6 +226,7 @@ u64 run_stage1_runs(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_para
         *set_out = set;
     }
     ex.arena->release(base_mark);
+    KC_TRACE_POINT("stage1: runs built");
     KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
     runs->rec_off = rec_off;
     runs->rec_len = rec_len;
@@ -267,9 +285,12 @@ template <int L> void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in
     }
     nv.N = nv.n * (complements ? 2u : 1u);
     ns.n = nv.n;
+    KC_TRACE_POINT("pipeline: nodes ready");
     Engine<CudaExec, L> eng(ex, nv, /*strict=*/p.assume_simplitigs != 0, /*lower_bound=*/false);
+    eng.use_small = ctx->small_engine;
     eng.init_state();
     eng.run();
+    KC_TRACE_POINT("pipeline: engine done");
     KC_CUDA(cudaEventRecord(ctx->ev[3], ex.stream));
     EmitResult er = kc_emit_superstring<CudaExec, L>(ex, ns, nv, eng.st, uniq, U, p.want_maxone != 0);
     KC_CUDA(cudaEventRecord(ctx->ev[4], ex.stream));
@@ -316,7 +337,7 @@ void count_only(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &
 }
 
 template <int L>
-void overlap_only(CudaExec &ex, const uint64_t *first, const uint64_t *last, u64 n, int k, bool complements, bool lower_bound,
+void overlap_only(kc_ctx *ctx, CudaExec &ex, const uint64_t *first, const uint64_t *last, u64 n, int k, bool complements, bool lower_bound,
                   bool strict, int64_t *edge_from, uint8_t *overlaps) {
     KWord<L> *df = ex.alloc<KWord<L>>(n), *dl = ex.alloc<KWord<L>>(n);
     KC_CUDA(cudaMemcpyAsync(df, first, n * sizeof(KWord<L>), cudaMemcpyHostToDevice, ex.stream));
@@ -329,6 +350,7 @@ void overlap_only(CudaExec &ex, const uint64_t *first, const uint64_t *last, u64
     nv.k = k;
     nv.complements = complements;
     Engine<CudaExec, L> eng(ex, nv, strict, lower_bound);
+    eng.use_small = ctx->small_engine;
     eng.init_state();
     eng.run();
     std::vector<u32> ef(nv.N);
@@ -400,8 +422,11 @@ int kc_compute_device(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_ou
     ex.prof = &ctx->prof;
     DevInput di{in->seq, in->n_bytes, in->rec_off, in->rec_len, in->n_recs};
     DevResult res;
+    KC_TRACE_POINT("compute_device: start");
     dispatch_pipeline(ctx, ex, di, *p, res);
+    KC_TRACE_POINT("compute_device: launched");
     KC_CUDA(cudaStreamSynchronize(ctx->stream));
+    KC_TRACE_POINT("compute_device: synced");
     out->ms = const_cast<u8 *>(res.ms);
     out->ms_maxone = const_cast<u8 *>(res.maxone);
     out->length = res.length;
@@ -509,11 +534,20 @@ int kc_overlap_path(kc_ctx *ctx, const uint64_t *first, const uint64_t *last, ui
     ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
-    if (k < 32) overlap_only<1>(ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
-    else if (k < 64) overlap_only<2>(ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
-    else overlap_only<4>(ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
+    if (k < 32) overlap_only<1>(ctx, ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
+    else if (k < 64) overlap_only<2>(ctx, ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
+    else overlap_only<4>(ctx, ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
     return KC_OK;
     KC_API_END(ctx)
+}
+
+int kc_set_option(kc_ctx *ctx, const char *name, int value) {
+    if (!ctx || !name) return KC_ERR_ARG;
+    if (std::strcmp(name, "small_engine") == 0) {
+        ctx->small_engine = value != 0;
+        return KC_OK;
+    }
+    return KC_ERR_ARG;
 }
 
 int kc_profile_enable(kc_ctx *ctx, int on) {

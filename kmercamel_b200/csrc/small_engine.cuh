@@ -1,0 +1,261 @@
+// Small-problem tail of the overlap stage: once the free suffix + prefix ends fit in shared memory, every remaining
+// level d runs inside ONE single-CTA kernel — tuples are built and sorted in shared memory, group pairs are
+// replayed by the same SimulatePairFn the multi-kernel path uses, and the cycle validation / ban / replay loop of
+// engine.cuh is done with __syncthreads() instead of kernel boundaries.  Results are identical to the host-driven
+// levels (same code for the pair replay, same ban rule); what disappears is ~10 launches and 2-3 host
+// synchronisations per level, which is what a genome-like input (few runs left after the first levels) pays for.
+#pragma once
+// (included from the middle of engine.cuh, after LevelCtx / SimulatePairFn)
+
+#ifdef __CUDACC__
+
+template <int L> struct SmallCfg {
+    static constexpr u32 T = L <= 2 ? 4096 : 2048;  // tuple capacity (free suffix ends + free prefix ends)
+    static constexpr u32 H = T / 2;
+    static constexpr size_t SMEM = (size_t) T * sizeof(KWord<L + 1>) + (size_t) H * (4 * 6 + 8 * 2);
+};
+
+template <int L> struct SmallEngineArgs {
+    NodeView<L> nv;
+    PathState st;
+    u32 *live_s_a, *live_p_a, *live_s_b, *live_p_b;  // ping-pong live lists
+    u32 n_s, n_p;
+    u32 *head_w, *tail_w, *slot_of;
+    u64 *stamp;
+    u8 *prim, *ban_flag;
+    u32 *ban_i, *ban_j;
+    u32 ban_cap;
+    int d_start;
+    bool strict;
+    u32 *out;  // [0] error, [1] levels run, [2] groups, [3] edges, [4] ban rounds, [5] bans
+};
+
+template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(SmallEngineArgs<L> a) {
+    typedef KWord<L + 1> TW;
+    constexpr u32 TCAP = SmallCfg<L>::T, HCAP = SmallCfg<L>::H;
+    extern __shared__ __align__(16) unsigned char kc_smem_raw[];
+    TW *T = reinterpret_cast<TW *>(kc_smem_raw);
+    u64 *max0 = reinterpret_cast<u64 *>(T + TCAP);
+    u64 *max1 = max0 + HCAP;
+    u32 *group_pstart = reinterpret_cast<u32 *>(max1 + HCAP);
+    u32 *new_tail = group_pstart + HCAP;
+    u32 *jump0 = new_tail + HCAP, *jump1 = jump0 + HCAP, *fin0 = jump1 + HCAP, *fin1 = fin0 + HCAP;
+    __shared__ u32 s_groups, s_edges, s_cyc, s_bans, s_live_s, s_live_p;
+    __shared__ kc_ull s_min;
+    const u32 tid = threadIdx.x;
+    const NodeView<L> v = a.nv;
+    const PathState s = a.st;
+    u32 n_s = a.n_s, n_p = a.n_p;
+    u32 *ls = a.live_s_a, *lp = a.live_p_a, *ls2 = a.live_s_b, *lp2 = a.live_p_b;
+    const u32 batch = v.N / 16 + 1;
+    const u32 done = v.complements ? 2u : 1u;
+    u32 st_levels = 0, st_groups = 0, st_edges = 0, st_rounds = 0, st_bans = 0;
+
+    for (int d = a.d_start; d >= 0; --d) {
+        if (n_s <= done || n_p == 0) break;
+        ++st_levels;
+        const u32 nt = n_s + n_p;
+        // 1. tuples + working copies of the chain ends
+        for (u32 i = tid; i < nt; i += 256) {
+            if (i < n_s) {
+                u32 x = ls[i];
+                T[i] = tuple_make(kmer_suffix(v.last_kmer(x), d), (u64) x);
+                a.head_w[x] = s.chain_head[x];
+            } else {
+                u32 x = lp[i - n_s];
+                u64 meta = KC_ROLE_P | ((u64) (x / batch) << 32) | (u64) (u32) ~x;
+                T[i] = tuple_make(kmer_prefix(v.first_kmer(x), v.k, d), meta);
+                a.tail_w[x] = s.chain_tail[x];
+            }
+        }
+        if (tid == 0) {
+            s_groups = 0;
+            s_bans = 0;
+        }
+        __syncthreads();
+        // 2. sort
+        kc_block_bitonic<L + 1>(T, nt);
+        // 3. active groups
+        for (u32 i = tid + 1; i < nt; i += 256) {
+            TW p = T[i - 1], q = T[i];
+            if (tuple_is_prefix(q) && !tuple_is_prefix(p) && tuple_key(p) == tuple_key(q)) group_pstart[atomicAdd(&s_groups, 1u)] = i;
+        }
+        __syncthreads();
+        const u32 n_groups = s_groups;
+        st_groups += n_groups;
+        if (n_groups) {
+            LevelCtx<L> c;
+            c.nv = v;
+            c.st = s;
+            c.T = T;
+            c.nt = nt;
+            c.d = d;
+            c.batch = batch;
+            c.head_w = a.head_w;
+            c.tail_w = a.tail_w;
+            c.stamp = a.stamp;
+            c.prim = a.prim;
+            c.ban_flag = a.ban_flag;
+            c.ban_i = a.ban_i;
+            c.ban_j = a.ban_j;
+            c.check_cycles = true;
+            u32 n_bans = 0;
+            while (true) {
+                // 4. replay every pair of groups
+                c.n_bans = n_bans;
+                SimulatePairFn<L> sim{c, group_pstart};
+                for (u32 g = tid; g < n_groups; g += 256) sim((u64) g);
+                if (tid == 0) {
+                    s_edges = 0;
+                    s_cyc = 0;
+                    s_min = ~0ULL;
+                }
+                __syncthreads();
+                // 5. this level's edges
+                for (u32 i = tid; i < n_s; i += 256) {
+                    u32 x = ls[i];
+                    if (s.edge_from[x] != KC_NONE) {
+                        u32 r = atomicAdd(&s_edges, 1u);
+                        new_tail[r] = x;
+                        a.slot_of[x] = r;
+                    }
+                }
+                __syncthreads();
+                const u32 ne = s_edges;
+                if (ne == 0) break;
+                for (u32 r = tid; r < ne; r += 256) {
+                    u32 x = new_tail[r];
+                    u32 t = s.chain_tail[s.edge_from[x]];
+                    bool cont = s.edge_from[t] != KC_NONE;
+                    jump0[r] = cont ? a.slot_of[t] : KC_NONE;
+                    fin0[r] = t;
+                    max0[r] = a.stamp[x];
+                }
+                __syncthreads();
+                u32 *ja = jump0, *jb = jump1, *fa = fin0, *fb = fin1;
+                u64 *ma = max0, *mb = max1;
+                int rounds = 1;
+                while ((1u << (rounds - 1)) < ne) ++rounds;
+                for (int it = 0; it < rounds; ++it) {
+                    for (u32 r = tid; r < ne; r += 256) {
+                        u32 j = ja[r];
+                        if (j == KC_NONE) {
+                            jb[r] = KC_NONE;
+                            fb[r] = fa[r];
+                            mb[r] = ma[r];
+                        } else {
+                            jb[r] = ja[j];
+                            fb[r] = fa[j];
+                            u64 m1 = ma[r], m2 = ma[j];
+                            mb[r] = m1 > m2 ? m1 : m2;
+                        }
+                    }
+                    __syncthreads();
+                    u32 *t32 = ja; ja = jb; jb = t32;
+                    t32 = fa; fa = fb; fb = t32;
+                    u64 *t64 = ma; ma = mb; mb = t64;
+                }
+                for (u32 r = tid; r < ne; r += 256)
+                    if (ja[r] != KC_NONE) {
+                        atomicAdd(&s_cyc, 1u);
+                        atomicMin(&s_min, (kc_ull) ma[r]);
+                    }
+                __syncthreads();
+                if (s_cyc == 0) {
+                    // 7. commit the chain ends
+                    for (u32 r = tid; r < ne; r += 256) {
+                        u32 x = new_tail[r];
+                        u32 h = s.chain_head[x];
+                        if (s.edge_to[h] == KC_NONE) {
+                            u32 t = fa[r];
+                            s.chain_tail[h] = t;
+                            s.chain_head[t] = h;
+                        }
+                    }
+                    st_edges += ne;
+                    __syncthreads();
+                    break;
+                }
+                // 6. ban the cycle closers, undo the level, replay
+                const kc_ull first_stamp = s_min;
+                for (u32 r = tid; r < ne; r += 256) {
+                    if (ja[r] == KC_NONE) continue;
+                    u32 x = new_tail[r];
+                    if (a.stamp[x] != ma[r]) continue;
+                    if (a.strict && ma[r] != first_stamp) continue;
+                    u32 y = s.edge_from[x];
+                    u32 pi = x, pj = y;
+                    if (!a.prim[x]) {
+                        pi = v.mirror(y);
+                        pj = v.mirror(x);
+                    }
+                    u32 slot = atomicAdd(&s_bans, v.complements ? 2u : 1u);
+                    if (slot + 2 <= a.ban_cap) {
+                        a.ban_i[slot] = pi;
+                        a.ban_j[slot] = pj;
+                        a.ban_flag[pi] = 1;
+                        if (v.complements) {
+                            a.ban_i[slot + 1] = v.mirror(pj);
+                            a.ban_j[slot + 1] = v.mirror(pi);
+                            a.ban_flag[v.mirror(pj)] = 1;
+                        }
+                    }
+                }
+                __syncthreads();
+                n_bans = s_bans;
+                ++st_rounds;
+                if (n_bans + 2 > a.ban_cap) {
+                    if (tid == 0) a.out[0] = 1;
+                    return;
+                }
+                for (u32 i = tid; i < nt; i += 256) {
+                    if (i < n_s) {
+                        u32 x = ls[i];
+                        u32 y = s.edge_from[x];
+                        if (y != KC_NONE) {
+                            s.edge_to[y] = KC_NONE;
+                            s.edge_from[x] = KC_NONE;
+                            s.ovl[x] = 255;
+                        }
+                        a.head_w[x] = s.chain_head[x];
+                    } else {
+                        u32 x = lp[i - n_s];
+                        a.tail_w[x] = s.chain_tail[x];
+                    }
+                }
+                __syncthreads();
+            }
+            for (u32 b = tid; b < n_bans; b += 256) a.ban_flag[a.ban_i[b]] = 0;
+            st_bans += n_bans;
+        }
+        // 8. shrink the live lists (their order is irrelevant: the tuple sort orders by id)
+        if (tid == 0) {
+            s_live_s = 0;
+            s_live_p = 0;
+        }
+        __syncthreads();
+        for (u32 i = tid; i < n_s; i += 256) {
+            u32 x = ls[i];
+            if (s.edge_from[x] == KC_NONE) ls2[atomicAdd(&s_live_s, 1u)] = x;
+        }
+        for (u32 i = tid; i < n_p; i += 256) {
+            u32 x = lp[i];
+            if (s.edge_to[x] == KC_NONE) lp2[atomicAdd(&s_live_p, 1u)] = x;
+        }
+        __syncthreads();
+        n_s = s_live_s;
+        n_p = s_live_p;
+        u32 *t32 = ls; ls = ls2; ls2 = t32;
+        t32 = lp; lp = lp2; lp2 = t32;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        a.out[1] = st_levels;
+        a.out[2] = st_groups;
+        a.out[3] = st_edges;
+        a.out[4] = st_rounds;
+        a.out[5] = st_bans;
+    }
+}
+
+#endif  // __CUDACC__

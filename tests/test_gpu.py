@@ -227,3 +227,21 @@ def test_compute_config2_full_size(ctx):
     want_k, want_v = orc.count_kmers(seq, off, ln, 31, True)
     assert np.array_equal(keys, want_k) and np.array_equal(vals, want_v)
     assert r.ms.upper() == r.maxone.upper()
+
+
+# ---- the multi-kernel level loop and the single-CTA small engine must agree ------------------------------------
+def test_small_engine_and_host_levels_agree(ctx, golden, simplitigs_bytes):
+    seq, off, ln = kb.frame_fasta(simplitigs_bytes)
+    g = golden["simplitigs_S"]["k31"]
+    try:
+        ctx.set_option("small_engine", 0)
+        for fz in golden["fuzz_S"]:
+            s2, o2, l2 = orc.records_to_arrays([r.encode() for r in fz["records"]])
+            r = ctx.compute(s2, o2, l2, k=fz["k"], complements=fz["complements"], assume_simplitigs=True, want_maxone=True)
+            assert r.ms.decode() == fz["ms"] and md5(r.maxone + b"\n") == fz["maxone_md5"]
+        r = ctx.compute(seq, off, ln, k=31, assume_simplitigs=True, want_maxone=True)
+        assert md5(r.ms + b"\n") == g["md5"] and md5(r.maxone + b"\n") == g["maxone_md5"]
+    finally:
+        ctx.set_option("small_engine", 1)
+    r = ctx.compute(seq, off, ln, k=31, assume_simplitigs=True, want_maxone=True)
+    assert md5(r.ms + b"\n") == g["md5"] and md5(r.maxone + b"\n") == g["maxone_md5"]
