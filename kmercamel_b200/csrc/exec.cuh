@@ -35,11 +35,13 @@ typedef unsigned long long kc_ull;  // CUDA's 64-bit atomic type
 // Kernel classes for the per-kernel device timers (kc_profile_* in include/kcgpu.h).
 enum KcProfId {
     KP_EXTRACT, KP_SORT_HIST, KP_SORT_SCATTER, KP_SORT_LOCAL, KP_SORT_MISC, KP_COMPACT, KP_SCAN, KP_TUPLES,
-    KP_SIMULATE, KP_DOUBLING, KP_COMMIT, KP_SMALL_ENGINE, KP_RANK, KP_EMIT, KP_MAXONE, KP_MISC, KP_COUNT
+    KP_SIMULATE, KP_DOUBLING, KP_COMMIT, KP_SMALL_ENGINE, KP_RANK, KP_EMIT, KP_MAXONE, KP_MISC,
+    KP_KS_HIST0, KP_KS_SCATTER0, KP_KS_RESOLVE, KP_RUNS, KP_COUNT
 };
 static const char *const kc_prof_names[KP_COUNT] = {
     "extract", "sort_hist", "sort_scatter", "sort_local", "sort_misc", "compact", "scan", "tuples",
-    "simulate", "doubling", "commit", "small_engine", "rank", "emit", "maxone", "misc"};
+    "simulate", "doubling", "commit", "small_engine", "rank", "emit", "maxone", "misc",
+    "ks_hist0", "ks_scatter0", "ks_resolve", "runs"};
 
 // ---------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -237,6 +239,14 @@ struct CudaExec {
         u32 total = scan_rec(in, out, n, true);
         arena->release(m);
         return total;
+    }
+
+    // Same without the synchronising read-back of the total (out[n-1] + in[n-1] holds it on the device).
+    void exclusive_scan_nosync(const u32 *in, u32 *out, u64 n) {
+        if (n == 0) return;
+        size_t m = arena->mark();
+        scan_rec(in, out, n, false);
+        arena->release(m);
     }
 
     template <typename Pred, typename Emit> u64 compact_if(u64 n, Pred pred, Emit emit, u64 bytes = 0) {

@@ -5,7 +5,9 @@
 #include "emit.cuh"
 #include "engine.cuh"
 #include "exec.cuh"
+#include "kmerset.cuh"
 #include "kword.cuh"
+#include "runs.cuh"
 #include "sort.cuh"
 #include "stage1.cuh"
 
@@ -116,122 +118,51 @@ struct DevResult {
     u64 length = 0, n_kmers = 0, n_occ = 0, n_nodes = 0;
 };
 
-// Stage 1.  Leaves the sorted distinct k-mers (and their counts) at the current arena top and returns them.
+// Stage 1 alone.  Leaves the sorted distinct k-mers (and their counts) at the current arena top and returns them.
 template <int L> u64 run_stage1(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, KWord<L> **uniq_out, u8 **cnt_out,
                                u64 *n_occ) {
-    const size_t base_mark = ex.arena->mark();
-    KWord<L> *keys_a = ex.alloc<KWord<L>>(in.n_bytes);
     KC_CUDA(cudaEventRecord(ctx->ev[0], ex.stream));
-    const u64 M = kc_extract_kmers<L, false>(ex, in.seq, in.n_bytes, p.k, p.complements != 0, keys_a);
-    KC_CUDA(cudaEventRecord(ctx->ev[1], ex.stream));
-    *n_occ = M;
-    if (M == 0) {
-        ex.arena->release(base_mark);
-        *uniq_out = nullptr;
-        *cnt_out = nullptr;
-        KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
-        return 0;
-    }
-    ex.arena->release(base_mark);
-    keys_a = ex.alloc<KWord<L>>(M);  // same address, trimmed to M
-    KWord<L> *keys_b = ex.alloc<KWord<L>>(M);
-    u8 *cnt_a = ex.alloc<u8>(M);
-    u8 *cnt_b = ex.alloc<u8>(M);
-    const u64 U = kc_sort_dedup<L, false>(ex, keys_a, keys_b, cnt_a, keys_b, cnt_b, M, 2 * p.k, p.min_frequency);
-    // compact the survivors down to the stage's base so everything above can be reused
-    ex.arena->release(base_mark);
-    KWord<L> *uniq = ex.alloc<KWord<L>>(U);
-    u8 *cnt = ex.alloc<u8>(U);
-    if (U) {
-        // uniq = [base, base + U*W) never overlaps keys_b = base + M*W (U <= M); cnt lies below cnt_b as well
-        ex.copy_bytes(uniq, keys_b, U * sizeof(KWord<L>));
-        ex.copy_bytes(cnt, cnt_b, U);
-    }
+    KC_CUDA(cudaEventRecord(ctx->ev[1], ex.stream));  // extraction is fused into the partition passes
+    KmerSet<L> set = kc_kmerset_build<L>(ex, in.seq, in.n_bytes, p.k, p.complements != 0, p.min_frequency, nullptr, true);
     KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
-    *uniq_out = uniq;
-    *cnt_out = cnt;
-    return U;
+    *n_occ = set.n_occ;
+    *uniq_out = set.keys;
+    *cnt_out = set.cnt;
+    return set.n_kept;
 }
 
 // From-FASTA regime: the nodes handed to the overlap stage are FIRST-OCCURRENCE RUNS.
 //
 // The reference turns the k-mer set into simplitigs by walking a hash table (src/simplitigs.h:105-205); which
 // simplitigs come out depends on khash iteration order and is unspecified (its tests sort them before comparing).
-// Here every k-mer occurrence carries the position of its window through the dedup sort, the distinct k-mer keeps
-// its smallest position, and those positions are flagged in the input.  A maximal run of consecutive flagged
+// Here every k-mer occurrence carries the position of its window through the partition passes, the distinct k-mer
+// keeps its smallest position, and those positions are flagged in the input.  A maximal run of consecutive flagged
 // positions is a path of distinct k-mers whose neighbours overlap by k-1 (adjacent windows of one record): a
 // simplitig read directly off the input, with no hash walk and no per-k-mer pointer chasing.  Runs are numbered
 // in input order and go through the same overlap levels d = k-1..0 as `-S` records, so run ends that overlap by
 // k-1 are still joined first, exactly as BIGREEDY requires.
-struct RunNodes {
-    u64 *rec_off = nullptr, *rec_len = nullptr;  // arena top end
-    u64 n_runs = 0;
-};
-
 template <int L>
 u64 run_stage1_runs(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, RunNodes *runs, KWord<L> **set_out, u64 *n_occ) {
-    typedef KWord<L + 1> Item;
-    const size_t base_mark = ex.arena->mark();
-    Item *items_a = ex.alloc<Item>(in.n_bytes);
     KC_CUDA(cudaEventRecord(ctx->ev[0], ex.stream));
+    KC_CUDA(cudaEventRecord(ctx->ev[1], ex.stream));  // extraction is fused into the partition passes
     KC_TRACE_POINT("stage1: begin");
-    const u64 M = kc_extract_kmers<L, true>(ex, in.seq, in.n_bytes, p.k, p.complements != 0, items_a);
-    KC_TRACE_POINT("stage1: extracted");
-    KC_CUDA(cudaEventRecord(ctx->ev[1], ex.stream));
-    *n_occ = M;
-    *set_out = nullptr;
-    if (M == 0) {
-        ex.arena->release(base_mark);
-        KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
-        return 0;
-    }
-    ex.arena->release(base_mark);
-    items_a = ex.alloc<Item>(M);  // same address, trimmed to M
-    Item *items_b = ex.alloc<Item>(M);
-    u8 *cnt_a = ex.alloc<u8>(M);
-    u8 *cnt_b = ex.alloc<u8>(M);
-    const u64 U = kc_sort_dedup<L + 1, true>(ex, items_a, items_b, cnt_a, items_b, cnt_b, M, 64 + 2 * p.k, p.min_frequency);
-    KC_TRACE_POINT("stage1: deduped");
-    if (U == 0) {
-        ex.arena->release(base_mark);
-        KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
-        return 0;
-    }
-    // flag the first occurrence of every kept k-mer
     const u64 nb = in.n_bytes;
-    u8 *flags = ex.alloc<u8>(nb + 1);
-    ex.fill_bytes(flags, 0, nb + 1);
-    const Item *uq = items_b;
-    ex.for_each(U, [=] __device__(u64 i) { flags[uq[i].w[0]] = 1; }, KP_MISC, U * (sizeof(Item) + 1));
-    auto is_start = [=] __device__(u64 q) { return flags[q] && (q == 0 || !flags[q - 1]); };
-    auto is_end = [=] __device__(u64 q) { return flags[q] && !flags[q + 1]; };  // flags[nb] == 0
-    const u64 n_runs = ex.compact_if(nb, is_start, [=] __device__(u64, u32) {}, nb);
-    u64 *rec_off = ex.arena->alloc_top<u64>(n_runs), *rec_len = ex.arena->alloc_top<u64>(n_runs);
-    ex.compact_if(nb, is_start, [=] __device__(u64 q, u32 r) { rec_off[r] = q; }, nb);
-    const int k = p.k;
-    // window END positions e_s..e_t  ->  bytes [e_s - k + 1, e_t]
-    ex.compact_if(nb, is_end, [=] __device__(u64 q, u32 r) {
-        u64 e_s = rec_off[r];
-        rec_len[r] = q - e_s + k;
-        rec_off[r] = e_s - (k - 1);
-    }, nb);
-    if (p.want_maxone) {  // the sorted k-mer set doubles as kMersDict of src/global.h:165-167
-        KWord<L> *set = ex.arena->alloc_top<KWord<L>>(U);
-        ex.for_each(U, [=] __device__(u64 i) {
-            KWord<L> x;
-#pragma unroll
-            for (int j = 0; j < L; ++j) x.w[j] = uq[i].w[j + 1];
-            set[i] = x;
-        }, KP_MISC, U * (sizeof(Item) + sizeof(KWord<L>)));
-        *set_out = set;
+    const size_t fwords = kc_runs_flag_words(nb);
+    u32 *flags = ex.arena->alloc_top<u32>(fwords);
+    ex.fill_bytes(flags, 0, fwords * 4);
+    // with -M the sorted k-mer set doubles as kMersDict of src/global.h:165-167; it stays at the arena bottom
+    KmerSet<L> set = kc_kmerset_build<L>(ex, in.seq, nb, p.k, p.complements != 0, p.min_frequency, flags, p.want_maxone != 0);
+    KC_TRACE_POINT("stage1: set built");
+    *n_occ = set.n_occ;
+    *set_out = set.keys;
+    if (set.n_kept == 0) {
+        KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
+        return 0;
     }
-    ex.arena->release(base_mark);
+    *runs = kc_runs_from_flags(ex, flags, nb, p.k);
     KC_TRACE_POINT("stage1: runs built");
     KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
-    runs->rec_off = rec_off;
-    runs->rec_len = rec_len;
-    runs->n_runs = n_runs;
-    return U;
+    return set.n_kept;
 }
 
 template <int L> void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, DevResult &res) {

@@ -1,0 +1,106 @@
+// First-occurrence runs: the nodes of the overlap stage in the from-FASTA regime (see kcgpu.cu run_stage1_runs).
+//
+// Bit p of the flag array marks a window END position p whose k-mer is a kept k-mer occurring there for the first time.  A
+// maximal run of consecutive flagged positions e_s..e_t is the node seq[e_s - k + 1 .. e_t].  Every run has one
+// start and one end and both appear in the same order, so one count pass + one scan + one emit pass number them:
+// the run of an end at position q is (number of starts at positions <= q) - 1.
+#pragma once
+#include "exec.cuh"
+#include "kmerset.cuh"
+
+#ifdef __CUDACC__
+
+static const int KC_RUN_PER_THREAD = 32;  // one word of the bit array
+static const int KC_RUN_TILE = 256 * KC_RUN_PER_THREAD;
+
+// The thread's 32 flags (bit i = position base + i) and the flags just before and after them.  The bit array has
+// one zero word of padding at the end.
+KC_D void kc_runs_load(const u32 *flags, u64 word, u32 &f, u32 &prev, u32 &next) {
+    f = flags[word];
+    prev = word ? flags[word - 1] >> 31 : 0u;
+    next = flags[word + 1] & 1u;
+}
+
+__global__ void __launch_bounds__(256) kc_runs_count_kernel(const u32 *flags, u64 n_words, u32 *block_counts) {
+    __shared__ u32 sw[8];
+    const u64 word = (u64) blockIdx.x * 256 + threadIdx.x;
+    u32 c = 0;
+    if (word < n_words) {
+        u32 f, prev, next;
+        kc_runs_load(flags, word, f, prev, next);
+        c = __popc(f & ~((f << 1) | prev));
+    }
+    u32 total;
+    kc_block_exclusive_scan<256>(c, &total, sw);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+
+// rec_off[r] = END position of the first window of run r, rec_len[r] = END position of its last window.
+__global__ void __launch_bounds__(256) kc_runs_emit_kernel(const u32 *flags, u64 n_words, const u32 *block_offsets, u64 *rec_off, u64 *rec_len) {
+    __shared__ u32 sw[8];
+    const u64 word = (u64) blockIdx.x * 256 + threadIdx.x;
+    const u64 base = word * 32;
+    u32 f = 0, prev = 0, next = 0;
+    if (word < n_words) kc_runs_load(flags, word, f, prev, next);
+    const u32 starts = f & ~((f << 1) | prev);
+    const u32 ends = f & ~((f >> 1) | (next << 31));
+    u32 total;
+    const u32 before = kc_block_exclusive_scan<256>(__popc(starts), &total, sw) + block_offsets[blockIdx.x];
+    u32 s = starts;
+    u32 r = before;
+    while (s) {
+        const int i = __ffs(s) - 1;
+        s &= s - 1;
+        rec_off[r++] = base + i;
+    }
+    u32 e = ends;
+    while (e) {
+        const int i = __ffs(e) - 1;
+        e &= e - 1;
+        rec_len[before + __popc(starts & (0xFFFFFFFFu >> (31 - i))) - 1] = base + i;
+    }
+}
+
+struct RunNodes {
+    u64 *rec_off = nullptr, *rec_len = nullptr;  // arena top end
+    u64 n_runs = 0;
+};
+
+// flags: bit array of kc_runs_flag_words(n_pos) words, bits >= n_pos zero.
+inline size_t kc_runs_flag_words(u64 n_pos) { return (size_t) kc_div_up(n_pos, 32) + 1; }
+
+inline RunNodes kc_runs_from_flags(CudaExec &ex, const u32 *flags, u64 n_pos, int k) {
+    RunNodes runs;
+    if (n_pos == 0) return runs;
+    const size_t mark = ex.arena->mark();
+    const u64 n_words = kc_div_up(n_pos, 32);
+    const u32 blocks = (u32) kc_div_up(n_pos, (u64) KC_RUN_TILE);
+    u32 *counts = ex.alloc<u32>(blocks);
+    {
+        CudaExec::Scope sc(ex, KP_RUNS, n_pos / 8);
+        kc_runs_count_kernel<<<blocks, 256, 0, ex.stream>>>(flags, n_words, counts);
+    }
+    ++ex.launches;
+    KC_CUDA(cudaGetLastError());
+    const u64 n_runs = ex.exclusive_scan(counts, counts, blocks);
+    u64 *rec_off = ex.arena->alloc_top<u64>(n_runs), *rec_len = ex.arena->alloc_top<u64>(n_runs);
+    {
+        CudaExec::Scope sc(ex, KP_RUNS, n_pos / 8 + 16 * n_runs);
+        kc_runs_emit_kernel<<<blocks, 256, 0, ex.stream>>>(flags, n_words, counts, rec_off, rec_len);
+    }
+    ++ex.launches;
+    KC_CUDA(cudaGetLastError());
+    // window END positions e_s..e_t  ->  bytes [e_s - k + 1, e_t]
+    ex.for_each(n_runs, [=] __device__(u64 r) {
+        const u64 e_s = rec_off[r], e_t = rec_len[r];
+        rec_len[r] = e_t - e_s + k;
+        rec_off[r] = e_s - (k - 1);
+    }, KP_RUNS, 32 * n_runs);
+    ex.arena->release(mark);
+    runs.rec_off = rec_off;
+    runs.rec_len = rec_len;
+    runs.n_runs = n_runs;
+    return runs;
+}
+
+#endif  // __CUDACC__

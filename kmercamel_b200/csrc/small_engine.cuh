@@ -40,7 +40,8 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
     u32 *group_pstart = reinterpret_cast<u32 *>(max1 + HCAP);
     u32 *new_tail = group_pstart + HCAP;
     u32 *jump0 = new_tail + HCAP, *jump1 = jump0 + HCAP, *fin0 = jump1 + HCAP, *fin1 = fin0 + HCAP;
-    __shared__ u32 s_groups, s_edges, s_cyc, s_bans, s_live_s, s_live_p;
+    __shared__ u32 s_groups, s_edges, s_cyc, s_bans, s_live_s, s_live_p, s_hit;
+    __shared__ u32 bloom[512];  // 16384-bit filter over the prefix keys of the level
     __shared__ kc_ull s_min;
     const u32 tid = threadIdx.x;
     const NodeView<L> v = a.nv;
@@ -53,6 +54,33 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
 
     for (int d = a.d_start; d >= 0; --d) {
         if (n_s <= done || n_p == 0) break;
+        // Cheap pre-test: a level can only accept an edge if some free suffix key equals some free prefix key.  Hash the
+        // prefix keys into a bit filter and probe it with the suffix keys; when nothing hits the level is a no-op and
+        // is skipped without building / sorting tuples (a false positive merely runs the level as usual).
+        for (u32 i = tid; i < 512; i += 256) bloom[i] = 0;
+        if (tid == 0) s_hit = 0;
+        __syncthreads();
+        for (u32 i = tid; i < n_p; i += 256) {
+            const KWord<L> key = kmer_prefix(v.first_kmer(lp[i]), v.k, d);
+            u64 h = 0;
+#pragma unroll
+            for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
+            h >>= 50;
+            atomicOr(&bloom[h >> 5], 1u << (h & 31));
+        }
+        __syncthreads();
+        for (u32 i = tid; i < n_s; i += 256) {
+            const KWord<L> key = kmer_suffix(v.last_kmer(ls[i]), d);
+            u64 h = 0;
+#pragma unroll
+            for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
+            h >>= 50;
+            if ((bloom[h >> 5] >> (h & 31)) & 1u) s_hit = 1;
+        }
+        __syncthreads();
+        const u32 hit = s_hit;
+        __syncthreads();  // s_hit / bloom are rewritten at the top of the next level
+        if (!hit) continue;
         ++st_levels;
         const u32 nt = n_s + n_p;
         // 1. tuples + working copies of the chain ends
