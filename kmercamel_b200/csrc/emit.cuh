@@ -52,6 +52,63 @@ template <int L> KC_HD u64 kmer_lower_bound(const KWord<L> *keys, u64 n, const K
 static const u32 KC_EMIT_SHORT = 128;   // contributions up to this many characters: one thread
 static const u32 KC_EMIT_CHUNK = 4096;   // longer ones: chunks of this many characters, 256 work items each
 
+#ifdef __CUDACC__
+static const u32 KC_RANK_SMALL = 1024;
+
+// List ranking of up to KC_RANK_SMALL nodes by one CTA in shared memory (same recurrences as the multi-kernel path).
+template <int L>
+__global__ void __launch_bounds__(256) kc_rank_small_kernel(PathState s, NodeSeq<L> q, u32 N, u32 *fin_out, u64 *dist_out, u64 *cell) {
+    __shared__ u32 jump[2][KC_RANK_SMALL], fin[2][KC_RANK_SMALL];
+    __shared__ u64 dist[2][KC_RANK_SMALL];
+    __shared__ u32 s_start, s_cyc;
+    if (threadIdx.x == 0) {
+        s_start = KC_NONE;
+        s_cyc = 0;
+    }
+    __syncthreads();
+    for (u32 v = threadIdx.x; v < N; v += 256) {
+        const u32 nx = s.edge_from[v];
+        jump[0][v] = nx;
+        fin[0][v] = v;
+        dist[0][v] = q.length(v) - (nx != KC_NONE ? (u64) s.ovl[v] : 0);
+        if (s.edge_to[v] == KC_NONE) atomicMin(&s_start, v);  // src/global.h:156-161 start
+    }
+    __syncthreads();
+    int rounds = 1;
+    while ((1u << (rounds - 1)) < N) ++rounds;
+    int cur = 0;
+    for (int it = 0; it < rounds; ++it) {
+        for (u32 v = threadIdx.x; v < N; v += 256) {
+            const u32 j = jump[cur][v];
+            if (j == KC_NONE) {
+                jump[cur ^ 1][v] = KC_NONE;
+                fin[cur ^ 1][v] = fin[cur][v];
+                dist[cur ^ 1][v] = dist[cur][v];
+            } else {
+                jump[cur ^ 1][v] = jump[cur][j];
+                fin[cur ^ 1][v] = fin[cur][j];
+                dist[cur ^ 1][v] = dist[cur][v] + dist[cur][j];
+            }
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    for (u32 v = threadIdx.x; v < N; v += 256) {
+        fin_out[v] = fin[cur][v];
+        dist_out[v] = dist[cur][v];
+        if (jump[cur][v] != KC_NONE) s_cyc = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const u32 st0 = s_start;
+        cell[0] = st0 == KC_NONE ? ~0ULL : (u64) st0;
+        cell[1] = s_cyc ? 0 : 1;
+        cell[2] = st0 < N ? dist[cur][st0] : 0;
+        cell[3] = st0 < N ? fin[cur][st0] : 0;
+    }
+}
+#endif
+
 struct EmitResult {
     u8 *ms = nullptr;      // device, `length` bytes
     u8 *maxone = nullptr;  // device, `length` bytes, or nullptr
@@ -70,51 +127,75 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
     u32 *jump_a = ex.template alloc<u32>(N), *jump_b = ex.template alloc<u32>(N);
     u32 *fin_a = ex.template alloc<u32>(N), *fin_b = ex.template alloc<u32>(N);
     u64 *dist_a = ex.template alloc<u64>(N), *dist_b = ex.template alloc<u64>(N);
-    u64 *cell = ex.template alloc<u64>(2);
+    u64 *cell = ex.template alloc<u64>(6);  // [0] start node, [1] 0 if a cycle survived, [2..4] info for the host
     const PathState s = st;
     const NodeSeq<L> q = ns;
-    ex.fill_bytes(cell, 0xFF, 16);
-    ex.for_each(N, [=] KC_HD_LAMBDA(u64 vv) {
-        u32 v = (u32) vv;
-        u32 nx = s.edge_from[v];
-        jump_a[v] = nx;
-        fin_a[v] = v;
-        dist_a[v] = q.length(v) - (nx != KC_NONE ? (u64) s.ovl[v] : 0);  // characters contributed by v
-        if (s.edge_to[v] == KC_NONE) KC_ATOMIC_MIN((kc_ull *) &cell[0], (kc_ull) v);  // src/global.h:156-161 start
-    }, KP_RANK, N * 25);
-    int rounds = kc_ceil_log2(N) + 1;
-    for (int it = 0; it < rounds; ++it) {
-        const u32 *ja = jump_a, *fa = fin_a;
-        const u64 *da = dist_a;
-        u32 *jb = jump_b, *fb = fin_b;
-        u64 *db = dist_b;
-        ex.for_each(N, [=] KC_HD_LAMBDA(u64 v) {
-            u32 j = ja[v];
-            if (j == KC_NONE) {
-                jb[v] = KC_NONE;
-                fb[v] = fa[v];
-                db[v] = da[v];
-            } else {
-                jb[v] = ja[j];
-                fb[v] = fa[j];
-                db[v] = da[v] + da[j];
-            }
-        }, KP_RANK, N * 32);
-        u32 *t = jump_a; jump_a = jump_b; jump_b = t;
-        t = fin_a; fin_a = fin_b; fin_b = t;
-        u64 *m = dist_a; dist_a = dist_b; dist_b = m;
+    bool ranked = false;
+#ifdef __CUDACC__
+    if constexpr (Exec::is_device) {
+        if (N <= KC_RANK_SMALL) {  // the whole list ranking in one CTA (a genome leaves a few dozen nodes)
+            typename Exec::Scope sc(ex, KP_RANK, N * 25);
+            kc_rank_small_kernel<L><<<1, 256, 0, ex.stream>>>(s, q, (u32) N, fin_a, dist_a, cell);
+            ++ex.launches;
+            KC_CUDA(cudaGetLastError());
+            ranked = true;
+        }
     }
-    u64 start = ex.read(cell);
+#endif
+    if (!ranked) {
+        ex.fill_bytes(cell, 0xFF, 16);
+        ex.for_each(N, [=] KC_HD_LAMBDA(u64 vv) {
+            u32 v = (u32) vv;
+            u32 nx = s.edge_from[v];
+            jump_a[v] = nx;
+            fin_a[v] = v;
+            dist_a[v] = q.length(v) - (nx != KC_NONE ? (u64) s.ovl[v] : 0);  // characters contributed by v
+            if (s.edge_to[v] == KC_NONE) KC_ATOMIC_MIN((kc_ull *) &cell[0], (kc_ull) v);  // src/global.h:156-161 start
+        }, KP_RANK, N * 25);
+        int rounds = kc_ceil_log2(N) + 1;
+        for (int it = 0; it < rounds; ++it) {
+            const u32 *ja = jump_a, *fa = fin_a;
+            const u64 *da = dist_a;
+            u32 *jb = jump_b, *fb = fin_b;
+            u64 *db = dist_b;
+            ex.for_each(N, [=] KC_HD_LAMBDA(u64 v) {
+                u32 j = ja[v];
+                if (j == KC_NONE) {
+                    jb[v] = KC_NONE;
+                    fb[v] = fa[v];
+                    db[v] = da[v];
+                } else {
+                    jb[v] = ja[j];
+                    fb[v] = fa[j];
+                    db[v] = da[v] + da[j];
+                }
+            }, KP_RANK, N * 32);
+            u32 *t = jump_a; jump_a = jump_b; jump_b = t;
+            t = fin_a; fin_a = fin_b; fin_b = t;
+            u64 *m = dist_a; dist_a = dist_b; dist_b = m;
+        }
+        {
+            const u32 *ja = jump_a;
+            ex.for_each(N, [=] KC_HD_LAMBDA(u64 v) {
+                if (ja[v] != KC_NONE) cell[1] = 0;  // a cycle survived: engine bug
+            });
+            const u32 *fa = fin_a;
+            const u64 *da = dist_a;
+            const u64 NN = N;
+            ex.for_each(1, [=] KC_HD_LAMBDA(u64) {  // everything the host needs, in one place
+                const u64 st0 = cell[0];
+                cell[2] = st0 < NN ? da[st0] : 0;
+                cell[3] = st0 < NN ? fa[st0] : 0;
+            });
+        }
+    }
+    u64 info[4];
+    ex.read_n(cell, info, 4);
+    const u64 start = info[0];
     if (start >= N) KC_THROW(KC_ERR_INTERNAL, "no start node: the path cover contains only cycles");
-    {
-        const u32 *ja = jump_a;
-        ex.for_each(N, [=] KC_HD_LAMBDA(u64 v) {
-            if (ja[v] != KC_NONE) cell[1] = 0;  // a cycle survived: engine bug
-        });
-        if (ex.read(cell + 1) == 0) KC_THROW(KC_ERR_INTERNAL, "cycle in the final path cover");
-    }
-    const u64 total = ex.read(dist_a + start);
-    const u32 fin_start = ex.read(fin_a + start);
+    if (info[1] == 0) KC_THROW(KC_ERR_INTERNAL, "cycle in the final path cover");
+    const u64 total = info[2];
+    const u32 fin_start = (u32) info[3];
     // results live below the scratch: release the scratch first, then allocate outputs, then re-reserve scratch
     // is not possible with a bump arena, so outputs are allocated after the scratch and the scratch is leaked
     // until the caller releases its own mark.

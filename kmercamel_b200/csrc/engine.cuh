@@ -334,7 +334,10 @@ template <class Exec, int L> struct Engine {
             }
             {
                 typename Exec::Scope sc(ex, KP_SMALL_ENGINE, 0);
-                kc_small_engine_kernel<L><<<1, 256, SmallCfg<L>::SMEM, ex.stream>>>(a);
+                // (measured: one warp instead of 256 threads makes the kernel 1.7x slower on configs[1] — the levels are
+                // bound by the work per phase, not by the block barriers)
+                const unsigned small_threads = 256u;
+                kc_small_engine_kernel<L><<<1, small_threads, SmallCfg<L>::SMEM, ex.stream>>>(a);
             }
             ++ex.launches;
             KC_CUDA(cudaGetLastError());

@@ -231,6 +231,10 @@ struct CudaExec {
         return v;
     }
     void sync() { KC_CUDA(cudaStreamSynchronize(stream)); }
+    template <typename T> void read_n(const T *p, T *host, size_t n) {  // one synchronising read-back of n values
+        KC_CUDA(cudaMemcpyAsync(host, p, n * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        KC_CUDA(cudaStreamSynchronize(stream));
+    }
 
     // out may alias in.  Returns the sum of all inputs.
     u32 exclusive_scan(const u32 *in, u32 *out, u64 n) {
@@ -305,6 +309,7 @@ struct HostExec {
     void fill_bytes(void *p, int value, size_t bytes) { std::memset(p, value, bytes); }
     void copy_bytes(void *dst, const void *src, size_t bytes) { std::memmove(dst, src, bytes); }
     template <typename T> T read(const T *p) { return *p; }
+    template <typename T> void read_n(const T *p, T *host, size_t n) { std::memcpy(host, p, n * sizeof(T)); }
     void sync() {}
     u32 exclusive_scan(const u32 *in, u32 *out, u64 n) {
         u32 s = 0;

@@ -150,19 +150,27 @@ u64 run_stage1_runs(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_para
     const size_t fwords = kc_runs_flag_words(nb);
     u32 *flags = ex.arena->alloc_top<u32>(fwords);
     ex.fill_bytes(flags, 0, fwords * 4);
+    u64 *cells = ex.arena->alloc_top<u64>(2);  // {kept distinct k-mers, runs}
+    ex.fill_bytes(cells, 0, 16);
     // with -M the sorted k-mer set doubles as kMersDict of src/global.h:165-167; it stays at the arena bottom
-    KmerSet<L> set = kc_kmerset_build<L>(ex, in.seq, nb, p.k, p.complements != 0, p.min_frequency, flags, p.want_maxone != 0);
+    KmerSet<L> set = kc_kmerset_build<L>(ex, in.seq, nb, p.k, p.complements != 0, p.min_frequency, flags, p.want_maxone != 0, cells);
     KC_TRACE_POINT("stage1: set built");
     *n_occ = set.n_occ;
     *set_out = set.keys;
-    if (set.n_kept == 0) {
+    if (set.n_occ == 0 || set.n_kept == 0) {
         KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
         return 0;
     }
-    *runs = kc_runs_from_flags(ex, flags, nb, p.k);
+    if (p.want_maxone) {  // the KEYS path has read the count back already
+        const u64 kept = set.n_kept;
+        KC_CUDA(cudaMemcpyAsync(cells, &kept, 8, cudaMemcpyHostToDevice, ex.stream));
+    }
+    u64 host_cells[2];
+    *runs = kc_runs_from_flags(ex, flags, nb, p.k, cells, host_cells);
+    const u64 n_kept = p.want_maxone ? set.n_kept : host_cells[0];
     KC_TRACE_POINT("stage1: runs built");
     KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
-    return set.n_kept;
+    return n_kept;
 }
 
 template <int L> void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, DevResult &res) {
@@ -207,7 +215,8 @@ template <int L> void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in
         ex.fill_bytes(err, 0, 4);
         kc_extract_node_ends<L>(ex, in.seq, in.n_bytes, node_off, node_len, n_nodes, p.k, first, last, err,
                                 /*validate_bytes=*/p.assume_simplitigs != 0);
-        if (ex.read(err)) KC_THROW(KC_ERR_BAD_SEQ, "-S input must hold only ACGT records of at least k bases");
+        // first-occurrence runs are valid by construction; only -S records need the check (and its read-back)
+        if (p.assume_simplitigs && ex.read(err)) KC_THROW(KC_ERR_BAD_SEQ, "-S input must hold only ACGT records of at least k bases");
         nv.first = first;
         nv.last = last;
         nv.n = (u32) n_nodes;

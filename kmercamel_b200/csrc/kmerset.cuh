@@ -196,7 +196,7 @@ template <int L> KC_D KWord<L> kmer_scramble(const KWord<L> &x) {
 // ---- level 0 -------------------------------------------------------------------------------------------------------
 template <int L, bool SCR>
 __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ks_hist0_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int complements,
-                                                                            int shift, int bits, u32 *hist) {
+                                                                            int shift, int bits, u32 *hist, u16 *tile_hist) {
     constexpr int T = KsCfg<L>::EX_THREADS;
     __shared__ u64 pk[KC_EX_HALO + T];
     __shared__ u32 vm[KC_EX_HALO + T];
@@ -212,8 +212,12 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ks_hist0_kernel(const
         atomicAdd(&sh[c.digit(shift, bits)], 1u);
     });
     __syncthreads();
-    for (int i = threadIdx.x; i < 256; i += T)
-        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+    // the tile's digit counts are kept (512 bytes per 8L KB of k-mers) so that the scatter pass needs no counting pass
+    for (int i = threadIdx.x; i < 256; i += T) {
+        const u32 c = sh[i];
+        tile_hist[(u64) blockIdx.x * 256 + i] = (u16) c;
+        if (c) atomicAdd(&hist[i], c);
+    }
 }
 
 // One CTA: level-0 digit counts -> bucket offsets (cursor) and the classified child buckets.
@@ -254,8 +258,8 @@ __global__ void __launch_bounds__(256) kc_ks_scan0_kernel(const u32 *hist, u64 *
 
 template <int L, bool PAY, bool SCR>
 __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ks_scatter0_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int complements,
-                                                                               int shift, int bits, u64 *cursor, KWord<L> *__restrict__ keys,
-                                                                               u32 *__restrict__ pos) {
+                                                                               int shift, int bits, u64 *cursor, const u16 *__restrict__ tile_hist,
+                                                                               KWord<L> *__restrict__ keys, u32 *__restrict__ pos) {
     constexpr int T = KsCfg<L>::EX_THREADS;
     constexpr int R = 256 / T;
     constexpr int TILE = KsCfg<L>::EX_TILE;
@@ -274,18 +278,13 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ks_scatter0_kernel(co
     __syncthreads();
     const int widx = KC_EX_HALO + threadIdx.x;
     const u32 em = kc_strip_emit_mask(vm, widx, k);
-    // pass 1: digit counts of the tile
-    kc_strip_windows<L>(pk, widx, em, k, complements, [&](int, const KWord<L> &c0) {
-        const KWord<L> c = SCR ? kmer_scramble(c0) : c0;
-        atomicAdd(&cnt[c.digit(shift, bits)], 1u);
-    });
-    __syncthreads();
+    // digit counts of the tile, left behind by kc_ks_hist0_kernel
     u32 total;
     {
         u32 v[R], c = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            v[r] = cnt[threadIdx.x * R + r];
+            v[r] = tile_hist[(u64) blockIdx.x * 256 + threadIdx.x * R + r];
             c += v[r];
         }
         u32 p = kc_block_exclusive_scan<T>(c, &total, sw);
@@ -295,12 +294,11 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ks_scatter0_kernel(co
             loff[i] = p;
             if (v[r]) gbase[i] = atomicAdd((kc_ull *) &cursor[i], (kc_ull) v[r]);  // reserve the tile's slots of bucket i
             p += v[r];
-            cnt[i] = 0;
         }
     }
     __syncthreads();
     if (total == 0) return;
-    // pass 2: the k-mers again, now into their slot of the staged (digit-ordered) tile
+    // the k-mers again, now into their slot of the staged (digit-ordered) tile
     kc_strip_windows<L>(pk, widx, em, k, complements, [&](int j, const KWord<L> &c0) {
         const KWord<L> c = SCR ? kmer_scramble(c0) : c0;
         const u32 dg = c.digit(shift, bits);
@@ -400,6 +398,7 @@ __global__ void __launch_bounds__(256) kc_kv_scatter_kernel(KWord<L> *k0, KWord<
     extern __shared__ __align__(16) unsigned char kc_smem_raw[];
     KWord<L> *stage_k = reinterpret_cast<KWord<L> *>(kc_smem_raw);
     u32 *stage_p = reinterpret_cast<u32 *>(stage_k + TILE);
+    u16 *rk = reinterpret_cast<u16 *>(stage_p + (PAY ? TILE : 0));  // rank of every item inside its digit (one shared atomic per item)
     __shared__ u32 cnt[256];
     __shared__ u32 loff[256];
     __shared__ u64 gbase[256];
@@ -440,7 +439,7 @@ __global__ void __launch_bounds__(256) kc_kv_scatter_kernel(KWord<L> *k0, KWord<
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
             u32 i = threadIdx.x + j * 256;
-            if (i < n_here) atomicAdd(&cnt[item[j].digit(shift, d.bits)], 1u);
+            if (i < n_here) rk[i] = (u16) atomicAdd(&cnt[item[j].digit(shift, d.bits)], 1u);
         }
         __syncthreads();
         const u32 c = cnt[threadIdx.x];
@@ -456,13 +455,12 @@ __global__ void __launch_bounds__(256) kc_kv_scatter_kernel(KWord<L> *k0, KWord<
             u32 i = threadIdx.x + j * 256;
             if (i < n_here) {
                 const u32 dg = item[j].digit(shift, d.bits);
-                const u32 q = loff[dg] + atomicAdd(&cnt[dg], 1u);
+                const u32 q = loff[dg] + rk[i];
                 stage_k[q] = item[j];
                 if (PAY) stage_p[q] = pay[j];
             }
         }
         __syncthreads();
-        if (threadIdx.x < 256) cnt[threadIdx.x] = 0;
         for (u32 q = threadIdx.x; q < n_here; q += 256) {
             const KWord<L> v = stage_k[q];
             const u32 dg = v.digit(shift, d.bits);
@@ -874,11 +872,10 @@ template <int L> struct KmerSet {
 //                     window ending at p  (positions travel as the payload);
 //   want_keys:        the kept keys (sorted) and their counts are left at the arena position current on entry.
 // Everything else this function allocates is released before it returns.
-template <int L> KmerSet<L> kc_kmerset_build(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, int min_freq, u32 *flags,
-                                             bool want_keys);
 
 template <int L, bool PAY, bool KEYS>
-KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, int min_freq, u32 *flags) {
+KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, int min_freq, u32 *flags,
+                                 u64 *ext_kept_cell) {
     typedef KsCfg<L> Cfg;
     KmerSet<L> res;
     if (n_bytes == 0) return res;
@@ -903,6 +900,7 @@ KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k
     u8 *skip = ex.alloc<u8>(big_cap);
     u32 *ctr = ex.alloc<u32>(8);
     u64 *cells = ex.alloc<u64>(2);  // [0] = M, [1] = kept distinct keys
+    u16 *tile_hist = ex.alloc<u16>(kc_div_up(n_bytes, (u64) Cfg::EX_TILE) * 256);
     ex.fill_bytes(ctr, 0, 32);
     ex.fill_bytes(cells, 0, 16);
     ex.fill_bytes(hist, 0, 256 * 4);
@@ -910,7 +908,7 @@ KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k
     constexpr bool SCRAMBLE = PAY && !KEYS;  // FLAGS-only: bucket by a bijective hash of the k-mer (see kmer_scramble)
     static bool attr_done = false;
     const int scatter0_smem = Cfg::EX_TILE * ((int) sizeof(KWord<L>) + (PAY ? 2 : 0));
-    const int scatter_smem = Cfg::TILE * ((int) sizeof(KWord<L>) + (PAY ? 4 : 0));
+    const int scatter_smem = Cfg::TILE * ((int) sizeof(KWord<L>) + (PAY ? 4 : 0) + 2);
     const int resolve_smem = Cfg::CAP * ((int) sizeof(KWord<L>) + (PAY ? 4 : 0) + 2);
     if (!attr_done) {
         KC_CUDA(cudaFuncSetAttribute(kc_ks_scatter0_kernel<L, PAY, SCRAMBLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter0_smem));
@@ -926,7 +924,7 @@ KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k
     const u32 ex_blocks = (u32) kc_div_up(n_bytes, (u64) Cfg::EX_TILE);
     {
         CudaExec::Scope sc(ex, KP_KS_HIST0, n_bytes);
-        kc_ks_hist0_kernel<L, SCRAMBLE><<<ex_blocks, Cfg::EX_THREADS, 0, st>>>(seq, n_bytes, k, complements ? 1 : 0, shift0, bits0, hist);
+        kc_ks_hist0_kernel<L, SCRAMBLE><<<ex_blocks, Cfg::EX_THREADS, 0, st>>>(seq, n_bytes, k, complements ? 1 : 0, shift0, bits0, hist, tile_hist);
     }
     ++ex.launches;
     kc_ks_scan0_kernel<<<1, 256, 0, st>>>(hist, cursor, big_a, big_cap, small, small_cap, uniform, uniform_cap, ctr, cells, cap, Cfg::TILE,
@@ -958,7 +956,7 @@ KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k
     {
         CudaExec::Scope sc(ex, KP_KS_SCATTER0, n_bytes + M * (sizeof(KWord<L>) + (PAY ? 4 : 0)));
         kc_ks_scatter0_kernel<L, PAY, SCRAMBLE><<<ex_blocks, Cfg::EX_THREADS, scatter0_smem, st>>>(seq, n_bytes, k, complements ? 1 : 0, shift0, bits0,
-                                                                                          cursor, k0, p0);
+                                                                                          cursor, tile_hist, k0, p0);
     }
     ++ex.launches;
     KC_CUDA(cudaGetLastError());
@@ -1004,7 +1002,9 @@ KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k
         nxt = t;
     }
     // ---- resolve ----
-    kc_ull *n_unique = reinterpret_cast<kc_ull *>(cells + 1);
+    // FLAGS-only callers may pass a cell of their own: the count is then left on the device (no read-back here)
+    const bool defer_count = !KEYS && ext_kept_cell != nullptr;
+    kc_ull *n_unique = reinterpret_cast<kc_ull *>(defer_count ? ext_kept_cell : cells + 1);
     if (n_small) {
         CudaExec::Scope sc(ex, KP_KS_RESOLVE, M * (sizeof(KWord<L>) + (PAY ? 4 : 0)) + (KEYS ? M * (sizeof(KWord<L>) + 1) : 0));
         if constexpr (PAY && !KEYS) {
@@ -1054,7 +1054,7 @@ KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k
         ++ex.launches;
     }
     KC_CUDA(cudaGetLastError());
-    const u64 U = ex.read(cells + 1);
+    const u64 U = defer_count ? ~0ULL : ex.read(cells + 1);
     res.n_kept = U;
     if (KEYS && U) {
         // compact the kept keys into k1 (free by now), then down to the arena position current on entry
@@ -1088,12 +1088,13 @@ KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k
 }
 
 template <int L>
-KmerSet<L> kc_kmerset_build(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, int min_freq, u32 *flags, bool want_keys) {
+KmerSet<L> kc_kmerset_build(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, int min_freq, u32 *flags, bool want_keys,
+                            u64 *ext_kept_cell = nullptr) {
     if (flags) {
-        if (want_keys) return kc_kmerset_build_impl<L, true, true>(ex, seq, n_bytes, k, complements, min_freq, flags);
-        return kc_kmerset_build_impl<L, true, false>(ex, seq, n_bytes, k, complements, min_freq, flags);
+        if (want_keys) return kc_kmerset_build_impl<L, true, true>(ex, seq, n_bytes, k, complements, min_freq, flags, nullptr);
+        return kc_kmerset_build_impl<L, true, false>(ex, seq, n_bytes, k, complements, min_freq, flags, ext_kept_cell);
     }
-    return kc_kmerset_build_impl<L, false, true>(ex, seq, n_bytes, k, complements, min_freq, nullptr);
+    return kc_kmerset_build_impl<L, false, true>(ex, seq, n_bytes, k, complements, min_freq, nullptr, nullptr);
 }
 
 #endif  // __CUDACC__

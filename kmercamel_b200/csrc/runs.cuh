@@ -21,7 +21,7 @@ KC_D void kc_runs_load(const u32 *flags, u64 word, u32 &f, u32 &prev, u32 &next)
     next = flags[word + 1] & 1u;
 }
 
-__global__ void __launch_bounds__(256) kc_runs_count_kernel(const u32 *flags, u64 n_words, u32 *block_counts) {
+__global__ void __launch_bounds__(256) kc_runs_count_kernel(const u32 *flags, u64 n_words, u32 *block_counts, kc_ull *total_runs) {
     __shared__ u32 sw[8];
     const u64 word = (u64) blockIdx.x * 256 + threadIdx.x;
     u32 c = 0;
@@ -32,7 +32,10 @@ __global__ void __launch_bounds__(256) kc_runs_count_kernel(const u32 *flags, u6
     }
     u32 total;
     kc_block_exclusive_scan<256>(c, &total, sw);
-    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+    if (threadIdx.x == 0) {
+        block_counts[blockIdx.x] = total;
+        if (total) atomicAdd(total_runs, (kc_ull) total);
+    }
 }
 
 // rec_off[r] = END position of the first window of run r, rec_len[r] = END position of its last window.
@@ -69,8 +72,11 @@ struct RunNodes {
 // flags: bit array of kc_runs_flag_words(n_pos) words, bits >= n_pos zero.
 inline size_t kc_runs_flag_words(u64 n_pos) { return (size_t) kc_div_up(n_pos, 32) + 1; }
 
-inline RunNodes kc_runs_from_flags(CudaExec &ex, const u32 *flags, u64 n_pos, int k) {
+// cells: two device words {kept distinct k-mers (already accumulated), number of runs (zero on entry)}; both come back
+// to the host with ONE synchronising read (host_cells).
+inline RunNodes kc_runs_from_flags(CudaExec &ex, const u32 *flags, u64 n_pos, int k, u64 *cells, u64 *host_cells) {
     RunNodes runs;
+    host_cells[0] = host_cells[1] = 0;
     if (n_pos == 0) return runs;
     const size_t mark = ex.arena->mark();
     const u64 n_words = kc_div_up(n_pos, 32);
@@ -78,11 +84,17 @@ inline RunNodes kc_runs_from_flags(CudaExec &ex, const u32 *flags, u64 n_pos, in
     u32 *counts = ex.alloc<u32>(blocks);
     {
         CudaExec::Scope sc(ex, KP_RUNS, n_pos / 8);
-        kc_runs_count_kernel<<<blocks, 256, 0, ex.stream>>>(flags, n_words, counts);
+        kc_runs_count_kernel<<<blocks, 256, 0, ex.stream>>>(flags, n_words, counts, reinterpret_cast<kc_ull *>(cells + 1));
     }
     ++ex.launches;
     KC_CUDA(cudaGetLastError());
-    const u64 n_runs = ex.exclusive_scan(counts, counts, blocks);
+    ex.exclusive_scan_nosync(counts, counts, blocks);
+    ex.read_n(cells, host_cells, 2);
+    const u64 n_runs = host_cells[1];
+    if (n_runs == 0) {
+        ex.arena->release(mark);
+        return runs;
+    }
     u64 *rec_off = ex.arena->alloc_top<u64>(n_runs), *rec_len = ex.arena->alloc_top<u64>(n_runs);
     {
         CudaExec::Scope sc(ex, KP_RUNS, n_pos / 8 + 16 * n_runs);

@@ -12,7 +12,8 @@
 template <int L> struct SmallCfg {
     static constexpr u32 T = L <= 2 ? 4096 : 2048;  // tuple capacity (free suffix ends + free prefix ends)
     static constexpr u32 H = T / 2;
-    static constexpr size_t SMEM = (size_t) T * sizeof(KWord<L + 1>) + (size_t) H * (4 * 6 + 8 * 2);
+    static constexpr u32 NS = 1024;  // up to this many virtual nodes the whole path state lives in shared memory
+    static constexpr size_t SMEM = (size_t) T * sizeof(KWord<L + 1>) + (size_t) H * (4 * 6 + 8 * 2) + (size_t) NS * (8 + 4 * 7 + 3);
 };
 
 template <int L> struct SmallEngineArgs {
@@ -44,8 +45,42 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
     __shared__ u32 bloom[512];  // 16384-bit filter over the prefix keys of the level
     __shared__ kc_ull s_min;
     const u32 tid = threadIdx.x;
+    const u32 NT = blockDim.x;  // 256, or one warp for tiny problems (block barriers then cost next to nothing)
     const NodeView<L> v = a.nv;
-    const PathState s = a.st;
+    PathState s = a.st;
+    u32 *head_w = a.head_w, *tail_w = a.tail_w, *slot_of = a.slot_of;
+    u64 *stamp = a.stamp;
+    u8 *prim = a.prim, *ban_flag = a.ban_flag;
+    // Small inputs (a genome: a few dozen first-occurrence runs): the replay of a big group is ONE thread chasing
+    // edge / chain-end entries it has just written, i.e. an L2 round trip per access when the state is in global
+    // memory.  With N <= NS the state is staged in shared memory for the whole kernel and written back at the end.
+    const bool local_state = v.N <= SmallCfg<L>::NS;
+    if (local_state) {
+        constexpr u32 NS = SmallCfg<L>::NS;
+        u64 *l_stamp = reinterpret_cast<u64 *>(fin1 + HCAP);
+        u32 *l32 = reinterpret_cast<u32 *>(l_stamp + NS);
+        u8 *l8 = reinterpret_cast<u8 *>(l32 + 7 * NS);
+        for (u32 i = tid; i < v.N; i += NT) {
+            l32[i] = s.edge_from[i];
+            l32[NS + i] = s.edge_to[i];
+            l32[2 * NS + i] = s.chain_head[i];
+            l32[3 * NS + i] = s.chain_tail[i];
+            l8[i] = s.ovl[i];
+            l8[2 * NS + i] = 0;
+        }
+        s.edge_from = l32;
+        s.edge_to = l32 + NS;
+        s.chain_head = l32 + 2 * NS;
+        s.chain_tail = l32 + 3 * NS;
+        head_w = l32 + 4 * NS;
+        tail_w = l32 + 5 * NS;
+        slot_of = l32 + 6 * NS;
+        stamp = l_stamp;
+        s.ovl = l8;
+        prim = l8 + NS;
+        ban_flag = l8 + 2 * NS;
+        __syncthreads();
+    }
     u32 n_s = a.n_s, n_p = a.n_p;
     u32 *ls = a.live_s_a, *lp = a.live_p_a, *ls2 = a.live_s_b, *lp2 = a.live_p_b;
     const u32 batch = v.N / 16 + 1;
@@ -57,10 +92,10 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
         // Cheap pre-test: a level can only accept an edge if some free suffix key equals some free prefix key.  Hash the
         // prefix keys into a bit filter and probe it with the suffix keys; when nothing hits the level is a no-op and
         // is skipped without building / sorting tuples (a false positive merely runs the level as usual).
-        for (u32 i = tid; i < 512; i += 256) bloom[i] = 0;
+        for (u32 i = tid; i < 512; i += NT) bloom[i] = 0;
         if (tid == 0) s_hit = 0;
         __syncthreads();
-        for (u32 i = tid; i < n_p; i += 256) {
+        for (u32 i = tid; i < n_p; i += NT) {
             const KWord<L> key = kmer_prefix(v.first_kmer(lp[i]), v.k, d);
             u64 h = 0;
 #pragma unroll
@@ -69,7 +104,7 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
             atomicOr(&bloom[h >> 5], 1u << (h & 31));
         }
         __syncthreads();
-        for (u32 i = tid; i < n_s; i += 256) {
+        for (u32 i = tid; i < n_s; i += NT) {
             const KWord<L> key = kmer_suffix(v.last_kmer(ls[i]), d);
             u64 h = 0;
 #pragma unroll
@@ -84,16 +119,16 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
         ++st_levels;
         const u32 nt = n_s + n_p;
         // 1. tuples + working copies of the chain ends
-        for (u32 i = tid; i < nt; i += 256) {
+        for (u32 i = tid; i < nt; i += NT) {
             if (i < n_s) {
                 u32 x = ls[i];
                 T[i] = tuple_make(kmer_suffix(v.last_kmer(x), d), (u64) x);
-                a.head_w[x] = s.chain_head[x];
+                head_w[x] = s.chain_head[x];
             } else {
                 u32 x = lp[i - n_s];
                 u64 meta = KC_ROLE_P | ((u64) (x / batch) << 32) | (u64) (u32) ~x;
                 T[i] = tuple_make(kmer_prefix(v.first_kmer(x), v.k, d), meta);
-                a.tail_w[x] = s.chain_tail[x];
+                tail_w[x] = s.chain_tail[x];
             }
         }
         if (tid == 0) {
@@ -102,9 +137,9 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
         }
         __syncthreads();
         // 2. sort
-        kc_block_bitonic<L + 1>(T, nt);
+        kc_block_bitonic<L + 1>(T, nt, NT);
         // 3. active groups
-        for (u32 i = tid + 1; i < nt; i += 256) {
+        for (u32 i = tid + 1; i < nt; i += NT) {
             TW p = T[i - 1], q = T[i];
             if (tuple_is_prefix(q) && !tuple_is_prefix(p) && tuple_key(p) == tuple_key(q)) group_pstart[atomicAdd(&s_groups, 1u)] = i;
         }
@@ -119,11 +154,11 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
             c.nt = nt;
             c.d = d;
             c.batch = batch;
-            c.head_w = a.head_w;
-            c.tail_w = a.tail_w;
-            c.stamp = a.stamp;
-            c.prim = a.prim;
-            c.ban_flag = a.ban_flag;
+            c.head_w = head_w;
+            c.tail_w = tail_w;
+            c.stamp = stamp;
+            c.prim = prim;
+            c.ban_flag = ban_flag;
             c.ban_i = a.ban_i;
             c.ban_j = a.ban_j;
             c.check_cycles = true;
@@ -132,7 +167,7 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
                 // 4. replay every pair of groups
                 c.n_bans = n_bans;
                 SimulatePairFn<L> sim{c, group_pstart};
-                for (u32 g = tid; g < n_groups; g += 256) sim((u64) g);
+                for (u32 g = tid; g < n_groups; g += NT) sim((u64) g);
                 if (tid == 0) {
                     s_edges = 0;
                     s_cyc = 0;
@@ -140,24 +175,24 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
                 }
                 __syncthreads();
                 // 5. this level's edges
-                for (u32 i = tid; i < n_s; i += 256) {
+                for (u32 i = tid; i < n_s; i += NT) {
                     u32 x = ls[i];
                     if (s.edge_from[x] != KC_NONE) {
                         u32 r = atomicAdd(&s_edges, 1u);
                         new_tail[r] = x;
-                        a.slot_of[x] = r;
+                        slot_of[x] = r;
                     }
                 }
                 __syncthreads();
                 const u32 ne = s_edges;
                 if (ne == 0) break;
-                for (u32 r = tid; r < ne; r += 256) {
+                for (u32 r = tid; r < ne; r += NT) {
                     u32 x = new_tail[r];
                     u32 t = s.chain_tail[s.edge_from[x]];
                     bool cont = s.edge_from[t] != KC_NONE;
-                    jump0[r] = cont ? a.slot_of[t] : KC_NONE;
+                    jump0[r] = cont ? slot_of[t] : KC_NONE;
                     fin0[r] = t;
-                    max0[r] = a.stamp[x];
+                    max0[r] = stamp[x];
                 }
                 __syncthreads();
                 u32 *ja = jump0, *jb = jump1, *fa = fin0, *fb = fin1;
@@ -165,7 +200,7 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
                 int rounds = 1;
                 while ((1u << (rounds - 1)) < ne) ++rounds;
                 for (int it = 0; it < rounds; ++it) {
-                    for (u32 r = tid; r < ne; r += 256) {
+                    for (u32 r = tid; r < ne; r += NT) {
                         u32 j = ja[r];
                         if (j == KC_NONE) {
                             jb[r] = KC_NONE;
@@ -183,7 +218,7 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
                     t32 = fa; fa = fb; fb = t32;
                     u64 *t64 = ma; ma = mb; mb = t64;
                 }
-                for (u32 r = tid; r < ne; r += 256)
+                for (u32 r = tid; r < ne; r += NT)
                     if (ja[r] != KC_NONE) {
                         atomicAdd(&s_cyc, 1u);
                         atomicMin(&s_min, (kc_ull) ma[r]);
@@ -191,7 +226,7 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
                 __syncthreads();
                 if (s_cyc == 0) {
                     // 7. commit the chain ends
-                    for (u32 r = tid; r < ne; r += 256) {
+                    for (u32 r = tid; r < ne; r += NT) {
                         u32 x = new_tail[r];
                         u32 h = s.chain_head[x];
                         if (s.edge_to[h] == KC_NONE) {
@@ -206,14 +241,14 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
                 }
                 // 6. ban the cycle closers, undo the level, replay
                 const kc_ull first_stamp = s_min;
-                for (u32 r = tid; r < ne; r += 256) {
+                for (u32 r = tid; r < ne; r += NT) {
                     if (ja[r] == KC_NONE) continue;
                     u32 x = new_tail[r];
-                    if (a.stamp[x] != ma[r]) continue;
+                    if (stamp[x] != ma[r]) continue;
                     if (a.strict && ma[r] != first_stamp) continue;
                     u32 y = s.edge_from[x];
                     u32 pi = x, pj = y;
-                    if (!a.prim[x]) {
+                    if (!prim[x]) {
                         pi = v.mirror(y);
                         pj = v.mirror(x);
                     }
@@ -221,11 +256,11 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
                     if (slot + 2 <= a.ban_cap) {
                         a.ban_i[slot] = pi;
                         a.ban_j[slot] = pj;
-                        a.ban_flag[pi] = 1;
+                        ban_flag[pi] = 1;
                         if (v.complements) {
                             a.ban_i[slot + 1] = v.mirror(pj);
                             a.ban_j[slot + 1] = v.mirror(pi);
-                            a.ban_flag[v.mirror(pj)] = 1;
+                            ban_flag[v.mirror(pj)] = 1;
                         }
                     }
                 }
@@ -236,7 +271,7 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
                     if (tid == 0) a.out[0] = 1;
                     return;
                 }
-                for (u32 i = tid; i < nt; i += 256) {
+                for (u32 i = tid; i < nt; i += NT) {
                     if (i < n_s) {
                         u32 x = ls[i];
                         u32 y = s.edge_from[x];
@@ -245,15 +280,15 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
                             s.edge_from[x] = KC_NONE;
                             s.ovl[x] = 255;
                         }
-                        a.head_w[x] = s.chain_head[x];
+                        head_w[x] = s.chain_head[x];
                     } else {
                         u32 x = lp[i - n_s];
-                        a.tail_w[x] = s.chain_tail[x];
+                        tail_w[x] = s.chain_tail[x];
                     }
                 }
                 __syncthreads();
             }
-            for (u32 b = tid; b < n_bans; b += 256) a.ban_flag[a.ban_i[b]] = 0;
+            for (u32 b = tid; b < n_bans; b += NT) ban_flag[a.ban_i[b]] = 0;
             st_bans += n_bans;
         }
         // 8. shrink the live lists (their order is irrelevant: the tuple sort orders by id)
@@ -262,11 +297,11 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
             s_live_p = 0;
         }
         __syncthreads();
-        for (u32 i = tid; i < n_s; i += 256) {
+        for (u32 i = tid; i < n_s; i += NT) {
             u32 x = ls[i];
             if (s.edge_from[x] == KC_NONE) ls2[atomicAdd(&s_live_s, 1u)] = x;
         }
-        for (u32 i = tid; i < n_p; i += 256) {
+        for (u32 i = tid; i < n_p; i += NT) {
             u32 x = lp[i];
             if (s.edge_to[x] == KC_NONE) lp2[atomicAdd(&s_live_p, 1u)] = x;
         }
@@ -276,6 +311,16 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
         u32 *t32 = ls; ls = ls2; ls2 = t32;
         t32 = lp; lp = lp2; lp2 = t32;
         __syncthreads();
+    }
+    if (local_state) {  // write the path back for the emission stage
+        __syncthreads();
+        for (u32 i = tid; i < v.N; i += NT) {
+            a.st.edge_from[i] = s.edge_from[i];
+            a.st.edge_to[i] = s.edge_to[i];
+            a.st.chain_head[i] = s.chain_head[i];
+            a.st.chain_tail[i] = s.chain_tail[i];
+            a.st.ovl[i] = s.ovl[i];
+        }
     }
     if (tid == 0) {
         a.out[1] = st_levels;

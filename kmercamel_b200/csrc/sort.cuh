@@ -207,12 +207,12 @@ template <int L, int MODE> KC_D bool kc_same_key(const KWord<L> &a, const KWord<
 
 // Cooperative bitonic sort of the shared-memory segment seg[0..m) by the whole CTA (any m: pairs whose partner
 // index is >= m are skipped, which is exact because every compare-exchange moves the larger word up).
-template <int L> KC_D void kc_block_bitonic(KWord<L> *seg, u32 m) {
+template <int L> KC_D void kc_block_bitonic(KWord<L> *seg, u32 m, u32 nthreads = 256) {
     u32 P = 2;
     while (P < m) P <<= 1;
     for (u32 k = 2; k <= P; k <<= 1) {
         for (u32 j = k >> 1; j > 0; j >>= 1) {
-            for (u32 t = threadIdx.x; t < (P >> 1); t += 256) {
+            for (u32 t = threadIdx.x; t < (P >> 1); t += nthreads) {
                 u32 i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 u32 l = (j == (k >> 1)) ? (i ^ (k - 1)) : (i | j);  // first step of a merge mirrors, the rest are strides
                 if (l < m && i < m) {
