@@ -9,8 +9,11 @@ Workload = BASELINE.json configs[1]: 50 x 1,000,000 bp uniform random multi-FAST
   value  = distinct k-mers represented per second, device-timed, input already resident in HBM;
   e2e    = the same through kc_compute with pinned HOST buffers (H2D of the input and D2H of the superstring
            inside the timed region).
-N > 1 (torchrun): every rank runs the path on its own independent genome (seed 12345 + rank) — the path shards by
-independent inputs, no data-path collective — weak scaling; value = k-mers of all ranks / max-over-ranks time.
+N > 1 (torchrun): ONE job over a genome of N x 50 Mbp (rank r contributes the 50 records of seed 12345 + r), hash-range
+sharded as the north star asks: every rank extracts the k-mers of its slice, the (k-mer, position) items go to their
+owner rank with an NCCL all-to-all over NVLink, every rank resolves its hash range, the first-occurrence flags are
+reduced onto rank 0, which runs the (sequential) greedy merge and emits the whole superstring.  Per-GPU counting work is
+fixed as N grows (weak scaling); value = distinct k-mers of the whole job / max-over-ranks time.
 """
 import argparse
 import json
@@ -162,11 +165,113 @@ def run_reference_arm(args, rank, world):
 
 def workload_config(world):
     return {"workload": "BASELINE configs[1]: synthetic 50 Mbp random multi-FASTA (50 x 1 Mbp, default_rng(12345)), "
-                        "k=31 canonical, min-one mask, u64 word path",
+                        "k=31 canonical, min-one mask, u64 word path" + (f"; x{world}: one genome of {world} x 50 Mbp" if world > 1 else ""),
             "k": K, "bases_per_gpu": N_RECORDS * RECORD_LEN, "records_per_gpu": N_RECORDS,
-            "sharding": "independent genome per rank (seed 12345 + rank), no data-path collective" if world > 1 else "single GPU",
+            "sharding": ("k-mer set construction sharded by hash range (NCCL all-to-all of (k-mer, position) items, flag bit "
+                         "arrays reduced onto rank 0), greedy merge + emission of the whole superstring on rank 0") if world > 1 else "single GPU",
             "l2": "no explicit flush: each step streams ~10 GB of intermediates (>> 126 MB L2), so the 51 MB input and "
                   "every kernel's operands are cold when read"}
+
+
+def run_sharded_arm(args, rank, local_rank, world, ctx, part):
+    """N > 1: one hash-range sharded job over the concatenation of every rank's 50 Mbp (see the module docstring)."""
+    import torch
+    import torch.distributed as dist
+    from kmercamel_b200 import sharded
+
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream()
+    part_len = int(part.size)                       # identical on every rank (same record count and lengths)
+    pinned = torch.from_numpy(part).pin_memory()
+    full = torch.empty(world * part_len, dtype=torch.uint8, device=dev)
+    own = torch.empty(part_len, dtype=torch.uint8, device=dev)
+    comm = sharded.TorchComm(dev)
+    ops = sharded.GpuOps(ctx, full)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def load():                                      # H2D of the rank's own part + all-gather of the parts over NVLink
+        own.copy_(pinned, non_blocking=True)
+        dist.all_gather_into_tensor(full, own)
+
+    def step():
+        return sharded.sharded_compute(ops, comm, full.numel(), k=K)
+
+    load()
+    for _ in range(max(args.warmup, 3)):
+        r = step()
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = ctx.total_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        r = step()
+    e1.record(stream)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    launches = ctx.total_launches() - launches0
+    prof = ctx.profile()
+    ctx.profile_enable(False)
+
+    # end to end: pinned host part -> device -> all-gather -> sharded job -> superstring back on rank 0's host
+    host_out = torch.empty(world * part_len + 64, dtype=torch.uint8).pin_memory() if rank == 0 else None
+    d2h = 0
+    for timed in (False, True):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps if timed else 2):
+            load()
+            r = step()
+            if rank == 0:
+                ctx._check(ctx._lib.kc_copy_to_host(ctx._h, host_out.data_ptr(), r.result.ms_ptr, r.result.length))
+                d2h = r.result.length
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop()
+
+    t = torch.tensor([dev_ms, e2e_s * 1000.0, float(launches)], dtype=torch.float64, device=dev)
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tsum = t.clone()
+    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        return
+    dev_ms, e2e_ms, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
+    n_kmers = r.n_kept
+    value = n_kmers * args.steps / (dev_ms / 1000.0)
+    e2e_value = n_kmers * args.steps / (e2e_ms / 1000.0)
+    peak, peak_src = measured_peak_gbs()
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    dname, d = dom
+    ach = d["bytes"] / (d["ms"] / 1000.0) / 1e9 if d["ms"] > 0 else 0.0
+    kernels = {n: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                   "gbs": (v["bytes"] / (v["ms"] / 1000.0) / 1e9) if v["ms"] > 0 and v["bytes"] else None}
+               for n, v in prof.items() if v["launches"]}
+    item_bytes = 12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic", "config": workload_config(world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": part_len * world, "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_ms / args.steps,
+                "timer": "host perf_counter around H2D + all-gather + sharded job + D2H on rank 0, max over ranks"},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": dname + " (rank 0)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": None, "peak_source": peak_src, "share_of_step": d["ms"] / dev_ms},
+        "cpu_baseline": None, "kernel_classes_rank0": kernels,
+        "exchange": {"items_sent_rank0_per_step": r.items_sent, "items_resolved_rank0_per_step": r.items_received,
+                     "all_to_all_bytes_rank0_per_step": r.items_sent * item_bytes,
+                     "flag_reduce_bytes": int(ops.flags.numel() * 4)},
+        "result": {"distinct_kmers": int(n_kmers), "superstring_length": int(r.result.length), "nodes": int(r.result.n_nodes)},
+    }
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -198,6 +303,10 @@ def main():
     records, (seq, off, ln) = make_workload(rank)
     stream = torch.cuda.current_stream()
     ctx = kb.Context(local_rank, stream.cuda_stream)
+    if world > 1:
+        run_sharded_arm(args, rank, local_rank, world, ctx, seq)
+        dist.destroy_process_group()
+        return
     d_seq = torch.from_numpy(seq).cuda()
     pinned = torch.from_numpy(seq).pin_memory()
     pinned_np = pinned.numpy()

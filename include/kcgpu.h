@@ -105,12 +105,37 @@ int kc_overlap_path(kc_ctx *ctx, const uint64_t *first, const uint64_t *last, ui
 int kc_frame_fasta(const uint8_t *data, uint64_t n, uint8_t **seq, uint64_t *n_bytes, uint64_t **rec_off,
                    uint64_t **rec_len, uint64_t *n_recs);
 
+/* ---- multi-GPU: hash-range sharded k-mer set construction ------------------------------------------------------------
+ * The reference is single-process; this is the north star's "counting shards by hash range, all-to-all over NVLink,
+ * greedy merge on one GPU".  The library does the per-GPU halves, the caller (kmercamel_b200/sharded.py, over
+ * torch.distributed / NCCL) does the exchange.  All pointers are DEVICE pointers unless noted; the whole framed
+ * sequence is resident on every GPU.  From-FASTA regime only (no -S, no -M).
+ *
+ *   kc_shard_partition   k-mers of the windows ENDING in [pos_begin, pos_end) (multiples of kc_shard_granule(k), or
+ *                        n_bytes), as scrambled words + global positions, grouped by the top 8 bits of the scrambled
+ *                        word; digit_counts[256] (host) says how many fell into each group.  Owner of group g among
+ *                        G ranks: g * G / 256, so the items of one owner are contiguous.
+ *   kc_shard_resolve     all occurrences of this rank's groups (gathered by the caller) -> sets the bit of the FIRST
+ *                        occurrence of every k-mer with >= min_frequency occurrences in flags_dev (a zeroed bit array
+ *                        over all n_bytes positions, (n_bytes + 31) / 32 + 1 words); keys_dev / pos_dev are clobbered.
+ *   kc_compute_from_flags  the flags of all ranks OR-ed together (their bits are disjoint, so a SUM reduce is an OR) ->
+ *                        first-occurrence runs -> overlap levels -> superstring, as kc_compute_device. */
+uint64_t kc_shard_granule(int k);
+int kc_shard_partition(kc_ctx *ctx, const kc_params *p, const uint8_t *seq_dev, uint64_t n_bytes, uint64_t pos_begin, uint64_t pos_end,
+                       void *keys_dev_out, uint32_t *pos_dev_out, uint64_t *digit_counts, uint64_t *n_items);
+int kc_shard_resolve(kc_ctx *ctx, const kc_params *p, void *keys_dev, uint32_t *pos_dev, uint64_t n_items, uint32_t *flags_dev,
+                     uint64_t *n_kept);
+int kc_compute_from_flags(kc_ctx *ctx, const kc_params *p, const kc_input *in, const uint32_t *flags_dev, uint64_t n_kept, kc_output *out);
+
 /* Per-kernel-class device timing for roofline reports.  Enable, run kc_compute*, then read the table:
  * names[i], milliseconds, launches, algorithmic bytes (read once + written once). */
 int kc_profile_enable(kc_ctx *ctx, int on);
 int kc_profile_count(void);
 int kc_profile_get(kc_ctx *ctx, int i, const char **name, double *ms, uint64_t *launches, uint64_t *bytes);
 int kc_profile_reset(kc_ctx *ctx);
+
+/* CUDA kernels launched through this context since kc_init (every entry point adds its own). */
+uint64_t kc_total_launches(const kc_ctx *ctx);
 
 /* Tuning / test knobs.  "small_engine" (default 1): run the tail of the overlap levels in the single-CTA kernel. */
 int kc_set_option(kc_ctx *ctx, const char *name, int value);

@@ -74,6 +74,15 @@ def load_library():
                                  u64p]
     L.kc_overlap_path.argtypes = [C.c_void_p, u64p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, i64p, u8p]
     L.kc_frame_fasta.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(u8p), u64p, C.POINTER(u64p), C.POINTER(u64p), u64p]
+    L.kc_shard_granule.argtypes = [C.c_int]
+    L.kc_shard_granule.restype = C.c_uint64
+    L.kc_shard_partition.argtypes = [C.c_void_p, C.POINTER(kc_params), C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
+                                     C.c_void_p, u64p, u64p]
+    L.kc_shard_resolve.argtypes = [C.c_void_p, C.POINTER(kc_params), C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, u64p]
+    L.kc_compute_from_flags.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.c_void_p, C.c_uint64,
+                                        C.POINTER(kc_output)]
+    L.kc_total_launches.argtypes = [C.c_void_p]
+    L.kc_total_launches.restype = C.c_uint64
     L.kc_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.kc_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.kc_profile_count.restype = C.c_int
@@ -91,6 +100,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ["kc_init", "kc_destroy", "kc_compute", "kc_compute_device", "kc_copy_to_host", "kc_count_kmers", "kc_overlap_path",
+                    "kc_total_launches", "kc_shard_granule", "kc_shard_partition", "kc_shard_resolve", "kc_compute_from_flags",
                     "kc_frame_fasta", "kc_set_option", "kc_profile_enable", "kc_profile_count", "kc_profile_get", "kc_profile_reset",
                     "kc_limbs_for_k", "kc_free", "kc_strerror", "kc_last_error"]
 
@@ -230,6 +240,35 @@ class Context:
                                               int(complements), int(lower_bound), int(strict), ef.ctypes.data_as(i64p),
                                               ov.ctypes.data_as(u8p)))
         return ef, ov
+
+    # ---- multi-GPU halves (device pointers; the exchange is the caller's, see sharded.py) ---------------------------
+    def shard_partition(self, seq_ptr: int, n_bytes: int, pos_begin: int, pos_end: int, keys_out_ptr: int, pos_out_ptr: int, *, k,
+                        complements=True):
+        """-> (digit_counts[256] int64, n_items)"""
+        p = self._params(k, complements, 1, False, False)
+        counts = np.zeros(256, dtype=np.uint64)
+        n = C.c_uint64()
+        self._check(self._lib.kc_shard_partition(self._h, C.byref(p), C.c_void_p(seq_ptr), n_bytes, pos_begin, pos_end,
+                                                 C.c_void_p(keys_out_ptr or None), C.c_void_p(pos_out_ptr or None),
+                                                 counts.ctypes.data_as(u64p), C.byref(n)))
+        return counts.astype(np.int64), n.value
+
+    def shard_resolve(self, keys_ptr: int, pos_ptr: int, n_items: int, flags_ptr: int, *, k, complements=True, min_frequency=1) -> int:
+        p = self._params(k, complements, min_frequency, False, False)
+        kept = C.c_uint64()
+        self._check(self._lib.kc_shard_resolve(self._h, C.byref(p), C.c_void_p(keys_ptr or None), C.c_void_p(pos_ptr or None), n_items,
+                                               C.c_void_p(flags_ptr), C.byref(kept)))
+        return kept.value
+
+    def compute_from_flags(self, seq_ptr: int, n_bytes: int, flags_ptr: int, n_kept: int, *, k, complements=True) -> ComputeResult:
+        p = self._params(k, complements, 1, False, False)
+        inp = kc_input(seq_ptr, n_bytes, None, None, 0)
+        out = kc_output()
+        self._check(self._lib.kc_compute_from_flags(self._h, C.byref(p), C.byref(inp), C.c_void_p(flags_ptr), n_kept, C.byref(out)))
+        return self._result(out, False)
+
+    def total_launches(self) -> int:
+        return int(self._lib.kc_total_launches(self._h))
 
     def set_option(self, name: str, value: int):
         self._check(self._lib.kc_set_option(self._h, name.encode(), int(value)))

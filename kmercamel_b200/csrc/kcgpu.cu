@@ -37,6 +37,7 @@ struct kc_ctx {
     size_t pin_out_cap = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool small_engine = true;
+    u64 total_launches = 0;  // kernels launched through this context since kc_init
     bool arena_limited = false;
     std::string last_error;
 };
@@ -173,7 +174,9 @@ u64 run_stage1_runs(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_para
     return n_kept;
 }
 
-template <int L> void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, DevResult &res) {
+template <int L>
+void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, DevResult &res, const u32 *ext_flags = nullptr,
+                  u64 ext_kept = 0) {
     const bool complements = p.complements != 0;
     KWord<L> *uniq = nullptr;
     u8 *cnt = nullptr;
@@ -191,7 +194,18 @@ template <int L> void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in
     const u64 *node_off = in.rec_off, *node_len = in.rec_len;
     if (!p.assume_simplitigs) {
         RunNodes runs;
-        U = run_stage1_runs<L>(ctx, ex, in, p, &runs, &uniq, &n_occ);
+        if (ext_flags) {  // sharded construction: the first-occurrence flags were reduced onto this GPU by the caller
+            KC_CUDA(cudaEventRecord(ctx->ev[0], ex.stream));
+            KC_CUDA(cudaEventRecord(ctx->ev[1], ex.stream));
+            u64 *cells = ex.arena->alloc_top<u64>(2);
+            ex.fill_bytes(cells, 0, 16);
+            u64 host_cells[2];
+            runs = kc_runs_from_flags(ex, ext_flags, in.n_bytes, p.k, cells, host_cells);
+            U = runs.n_runs ? ext_kept : 0;
+            KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
+        } else {
+            U = run_stage1_runs<L>(ctx, ex, in, p, &runs, &uniq, &n_occ);
+        }
         if (U == 0) KC_THROW(KC_ERR_EMPTY, "the input contains no k-mers");  // src/main.cpp:155-158
         n_nodes = runs.n_runs;
         node_off = runs.rec_off;
@@ -375,6 +389,7 @@ int kc_compute_device(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_ou
     out->n_nodes = res.n_nodes;
     out->n_launches = ex.launches;
     fill_times(ctx, out);
+    ctx->total_launches += ex.launches;
     return KC_OK;
     KC_API_END(ctx)
 }
@@ -425,6 +440,7 @@ int kc_compute(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *o
     out->n_nodes = res.n_nodes;
     out->n_launches = ex.launches;
     fill_times(ctx, out);
+    ctx->total_launches += ex.launches;
     return KC_OK;
     KC_API_END(ctx)
 }
@@ -457,6 +473,7 @@ int kc_count_kmers(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t
     if (p->k < 32) count_only<1>(ctx, ex, di, *p, keys, counts, n);
     else if (p->k < 64) count_only<2>(ctx, ex, di, *p, keys, counts, n);
     else count_only<4>(ctx, ex, di, *p, keys, counts, n);
+    ctx->total_launches += ex.launches;
     return KC_OK;
     KC_API_END(ctx)
 }
@@ -477,9 +494,106 @@ int kc_overlap_path(kc_ctx *ctx, const uint64_t *first, const uint64_t *last, ui
     if (k < 32) overlap_only<1>(ctx, ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
     else if (k < 64) overlap_only<2>(ctx, ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
     else overlap_only<4>(ctx, ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
+    ctx->total_launches += ex.launches;
     return KC_OK;
     KC_API_END(ctx)
 }
+
+uint64_t kc_shard_granule(int k) {
+    const int limbs = kc_limbs_for_k(k);
+    return limbs == 1 ? KsCfg<1>::EX_TILE : (limbs == 2 ? KsCfg<2>::EX_TILE : KsCfg<4>::EX_TILE);
+}
+
+int kc_shard_partition(kc_ctx *ctx, const kc_params *p, const uint8_t *seq_dev, uint64_t n_bytes, uint64_t pos_begin, uint64_t pos_end,
+                       void *keys_dev_out, uint32_t *pos_dev_out, uint64_t *digit_counts, uint64_t *n_items) {
+    if (!ctx || !seq_dev || !digit_counts || !n_items) return KC_ERR_ARG;
+    KC_API_BEGIN
+    check_params(p);
+    if (p->assume_simplitigs || p->want_maxone) KC_THROW(KC_ERR_ARG, "sharded construction supports neither -S nor -M");
+    if (n_bytes >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 sequence bytes");
+    if ((reinterpret_cast<uintptr_t>(seq_dev) & 15) != 0) KC_THROW(KC_ERR_ARG, "device sequence pointer must be 16-byte aligned");
+    if (pos_end > pos_begin && (!keys_dev_out || !pos_dev_out)) KC_THROW(KC_ERR_ARG, "output buffers missing");
+    KC_CUDA(cudaSetDevice(ctx->device));
+    const u64 span = pos_end > pos_begin ? pos_end - pos_begin : 0;
+    ensure_arena(ctx, (size_t) (span * 2 + (64u << 20)));  // control arrays and tile histograms only: the items go to the caller's buffers
+    ctx->arena.reset();
+    CudaExec ex{ctx->stream, &ctx->arena};
+    ex.prof = &ctx->prof;
+    KsShard sh;
+    sh.pos_begin = pos_begin;
+    sh.pos_end = pos_end;
+    sh.keys = keys_dev_out;
+    sh.pos = pos_dev_out;
+    u64 m = 0;
+    const bool c = p->complements != 0;
+    if (p->k < 32) m = kc_kmerset_partition<1>(ex, seq_dev, n_bytes, p->k, c, &sh);
+    else if (p->k < 64) m = kc_kmerset_partition<2>(ex, seq_dev, n_bytes, p->k, c, &sh);
+    else m = kc_kmerset_partition<4>(ex, seq_dev, n_bytes, p->k, c, &sh);
+    for (int i = 0; i < 256; ++i) digit_counts[i] = sh.host_hist[i];
+    *n_items = m;
+    ctx->total_launches += ex.launches;
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
+int kc_shard_resolve(kc_ctx *ctx, const kc_params *p, void *keys_dev, uint32_t *pos_dev, uint64_t n_items, uint32_t *flags_dev,
+                     uint64_t *n_kept) {
+    if (!ctx || !n_kept || !flags_dev) return KC_ERR_ARG;
+    KC_API_BEGIN
+    check_params(p);
+    *n_kept = 0;
+    if (n_items == 0) return KC_OK;
+    if (!keys_dev || !pos_dev) KC_THROW(KC_ERR_ARG, "item buffers missing");
+    KC_CUDA(cudaSetDevice(ctx->device));
+    const int limbs = kc_limbs_for_k(p->k);
+    ensure_arena(ctx, (size_t) ((double) n_items * (8.0 * limbs + 4.0 + 2.0) * 1.1) + (128u << 20));
+    ctx->arena.reset();
+    CudaExec ex{ctx->stream, &ctx->arena};
+    ex.prof = &ctx->prof;
+    KsShard sh;
+    sh.keys = keys_dev;
+    sh.pos = pos_dev;
+    sh.n_items = n_items;
+    if (limbs == 1) *n_kept = kc_kmerset_resolve<1>(ex, p->k, p->min_frequency, flags_dev, &sh);
+    else if (limbs == 2) *n_kept = kc_kmerset_resolve<2>(ex, p->k, p->min_frequency, flags_dev, &sh);
+    else *n_kept = kc_kmerset_resolve<4>(ex, p->k, p->min_frequency, flags_dev, &sh);
+    ctx->total_launches += ex.launches;
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
+int kc_compute_from_flags(kc_ctx *ctx, const kc_params *p, const kc_input *in, const uint32_t *flags_dev, uint64_t n_kept, kc_output *out) {
+    if (!ctx || !in || !out || !flags_dev) return KC_ERR_ARG;
+    KC_API_BEGIN
+    check_params(p);
+    if (p->assume_simplitigs || p->want_maxone) KC_THROW(KC_ERR_ARG, "sharded construction supports neither -S nor -M");
+    if (in->n_bytes >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 sequence bytes on one GPU");
+    KC_CUDA(cudaSetDevice(ctx->device));
+    const int limbs = kc_limbs_for_k(p->k);
+    ensure_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, false));
+    ctx->arena.reset();
+    CudaExec ex{ctx->stream, &ctx->arena};
+    ex.prof = &ctx->prof;
+    DevInput di{in->seq, in->n_bytes, in->rec_off, in->rec_len, in->n_recs};
+    DevResult res;
+    if (p->k < 32) run_pipeline<1>(ctx, ex, di, *p, res, flags_dev, n_kept);
+    else if (p->k < 64) run_pipeline<2>(ctx, ex, di, *p, res, flags_dev, n_kept);
+    else run_pipeline<4>(ctx, ex, di, *p, res, flags_dev, n_kept);
+    KC_CUDA(cudaStreamSynchronize(ctx->stream));
+    out->ms = const_cast<u8 *>(res.ms);
+    out->ms_maxone = nullptr;
+    out->length = res.length;
+    out->n_kmers = res.n_kmers;
+    out->n_occurrences = 0;
+    out->n_nodes = res.n_nodes;
+    out->n_launches = ex.launches;
+    fill_times(ctx, out);
+    ctx->total_launches += ex.launches;
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
+uint64_t kc_total_launches(const kc_ctx *ctx) { return ctx ? ctx->total_launches : 0; }
 
 int kc_set_option(kc_ctx *ctx, const char *name, int value) {
     if (!ctx || !name) return KC_ERR_ARG;

@@ -196,12 +196,12 @@ template <int L> KC_D KWord<L> kmer_scramble(const KWord<L> &x) {
 // ---- level 0 -------------------------------------------------------------------------------------------------------
 template <int L, bool SCR>
 __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ks_hist0_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int complements,
-                                                                            int shift, int bits, u32 *hist, u16 *tile_hist) {
+                                                                            int shift, int bits, u32 *hist, u16 *tile_hist, u32 tile0) {
     constexpr int T = KsCfg<L>::EX_THREADS;
     __shared__ u64 pk[KC_EX_HALO + T];
     __shared__ u32 vm[KC_EX_HALO + T];
     __shared__ u32 sh[256];
-    const i64 block_pos0 = (i64) blockIdx.x * KsCfg<L>::EX_TILE;
+    const i64 block_pos0 = (i64) (tile0 + blockIdx.x) * KsCfg<L>::EX_TILE;
     kc_tile_load<T>(seq, n_bytes, block_pos0, pk, vm);
     for (int i = threadIdx.x; i < 256; i += T) sh[i] = 0;
     __syncthreads();
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) kc_ks_scan0_kernel(const u32 *hist, u64 *
 template <int L, bool PAY, bool SCR>
 __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ks_scatter0_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int complements,
                                                                                int shift, int bits, u64 *cursor, const u16 *__restrict__ tile_hist,
-                                                                               KWord<L> *__restrict__ keys, u32 *__restrict__ pos) {
+                                                                               KWord<L> *__restrict__ keys, u32 *__restrict__ pos, u32 tile0) {
     constexpr int T = KsCfg<L>::EX_THREADS;
     constexpr int R = 256 / T;
     constexpr int TILE = KsCfg<L>::EX_TILE;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ks_scatter0_kernel(co
     __shared__ u32 loff[256];
     __shared__ u64 gbase[256];
     __shared__ u32 sw[T / 32];
-    const i64 block_pos0 = (i64) blockIdx.x * TILE;
+    const i64 block_pos0 = (i64) (tile0 + blockIdx.x) * TILE;
     kc_tile_load<T>(seq, n_bytes, block_pos0, pk, vm);
     for (int i = threadIdx.x; i < 256; i += T) cnt[i] = 0;
     __syncthreads();
@@ -860,6 +860,22 @@ __global__ void __launch_bounds__(256) kc_ks_uniform_kernel(KWord<L> *k0, const 
 }
 
 // ---- host driver -----------------------------------------------------------------------------------------------------
+// Multi-GPU use (hash-range sharding, see kmercamel_b200/sharded.py): the construction is cut at the level-0 boundary.
+//   KS_PARTITION  level 0 only, over the window END positions [pos_begin, pos_end) of a sequence that is resident in
+//                 full: the scrambled keys and their GLOBAL positions land in caller buffers, ordered by level-0 digit
+//                 (= by owner rank, owner = digit * n_ranks / 256); the 256 digit counts go back to the host.
+//   KS_RESOLVE    the items are given (after the all-to-all: every occurrence of this rank's hash range) and level 0
+//                 is skipped; first-occurrence bits are set at global positions.
+enum { KS_WHOLE = 0, KS_PARTITION = 1, KS_RESOLVE = 2 };
+struct KsShard {
+    int mode = KS_WHOLE;
+    u64 pos_begin = 0, pos_end = 0;  // KS_PARTITION: multiples of EX_TILE (pos_end may also be n_bytes)
+    void *keys = nullptr;            // caller buffers (device): KS_PARTITION out (capacity pos_end - pos_begin), KS_RESOLVE in/scratch
+    u32 *pos = nullptr;
+    u64 n_items = 0;                 // KS_RESOLVE
+    u32 host_hist[256];              // KS_PARTITION out
+};
+
 template <int L> struct KmerSet {
     u64 n_occ = 0;            // M: k-mer windows seen
     u64 n_kept = 0;           // U: distinct k-mers with >= min_freq occurrences
@@ -875,14 +891,22 @@ template <int L> struct KmerSet {
 
 template <int L, bool PAY, bool KEYS>
 KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, int min_freq, u32 *flags,
-                                 u64 *ext_kept_cell) {
+                                 u64 *ext_kept_cell, KsShard *shard = nullptr) {
     typedef KsCfg<L> Cfg;
     KmerSet<L> res;
-    if (n_bytes == 0) return res;
+    const int mode = shard ? shard->mode : KS_WHOLE;
+    if (mode != KS_WHOLE && (!PAY || KEYS)) KC_THROW(KC_ERR_INTERNAL, "sharded construction is FLAGS-only");
+    const u64 pos_begin = mode == KS_PARTITION ? shard->pos_begin : 0;
+    const u64 pos_end = mode == KS_PARTITION ? shard->pos_end : n_bytes;
+    if (mode == KS_PARTITION)
+        for (int i = 0; i < 256; ++i) shard->host_hist[i] = 0;
+    if (mode == KS_RESOLVE ? shard->n_items == 0 : pos_end <= pos_begin) return res;
+    if (mode == KS_PARTITION && (pos_begin % Cfg::EX_TILE != 0 || (pos_end % Cfg::EX_TILE != 0 && pos_end != n_bytes) || pos_end > n_bytes))
+        KC_THROW(KC_ERR_ARG, "shard boundaries must be multiples of the extraction tile");
     cudaStream_t st = ex.stream;
     const size_t base_mark = ex.arena->mark();
     const u32 cap = Cfg::CAP;
-    const u64 n = n_bytes;  // upper bound of M
+    const u64 n = mode == KS_RESOLVE ? shard->n_items : pos_end - pos_begin;  // upper bound of M
     const u32 big_cap = (u32) (n / cap + 258);
     const u32 small_cap = (u32) (16 * (n / cap) + 4096);
     const u32 uniform_cap = big_cap;
@@ -900,7 +924,9 @@ KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k
     u8 *skip = ex.alloc<u8>(big_cap);
     u32 *ctr = ex.alloc<u32>(8);
     u64 *cells = ex.alloc<u64>(2);  // [0] = M, [1] = kept distinct keys
-    u16 *tile_hist = ex.alloc<u16>(kc_div_up(n_bytes, (u64) Cfg::EX_TILE) * 256);
+    const u32 ex_blocks = mode == KS_RESOLVE ? 0u : (u32) kc_div_up(pos_end - pos_begin, (u64) Cfg::EX_TILE);
+    const u32 tile0 = (u32) (pos_begin / Cfg::EX_TILE);
+    u16 *tile_hist = ex.alloc<u16>((u64) (ex_blocks ? ex_blocks : 1) * 256);
     ex.fill_bytes(ctr, 0, 32);
     ex.fill_bytes(cells, 0, 16);
     ex.fill_bytes(hist, 0, 256 * 4);
@@ -921,48 +947,92 @@ KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k
     const int key_bits = SCRAMBLE ? 64 * L : 2 * k;
     const int bits0 = key_bits < Cfg::D0 ? key_bits : Cfg::D0;
     const int shift0 = key_bits - bits0;
-    const u32 ex_blocks = (u32) kc_div_up(n_bytes, (u64) Cfg::EX_TILE);
-    {
-        CudaExec::Scope sc(ex, KP_KS_HIST0, n_bytes);
-        kc_ks_hist0_kernel<L, SCRAMBLE><<<ex_blocks, Cfg::EX_THREADS, 0, st>>>(seq, n_bytes, k, complements ? 1 : 0, shift0, bits0, hist, tile_hist);
-    }
-    ++ex.launches;
-    kc_ks_scan0_kernel<<<1, 256, 0, st>>>(hist, cursor, big_a, big_cap, small, small_cap, uniform, uniform_cap, ctr, cells, cap, Cfg::TILE,
-                                         key_bits - bits0);
-    ++ex.launches;
-    KC_CUDA(cudaGetLastError());
-    u32 h[8];
+    u32 h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     u64 M = 0;
-    KC_CUDA(cudaMemcpyAsync(h, ctr, 32, cudaMemcpyDeviceToHost, st));
-    KC_CUDA(cudaMemcpyAsync(&M, cells, 8, cudaMemcpyDeviceToHost, st));
-    KC_CUDA(cudaStreamSynchronize(st));
-    res.n_occ = M;
-    if (M == 0) {
+    KWord<L> *k0 = nullptr, *k1 = nullptr;
+    u32 *p0 = nullptr, *p1 = nullptr;
+    u8 *cnt_tmp = nullptr;
+    if (mode != KS_RESOLVE) {
+        {
+            CudaExec::Scope sc(ex, KP_KS_HIST0, pos_end - pos_begin);
+            kc_ks_hist0_kernel<L, SCRAMBLE><<<ex_blocks, Cfg::EX_THREADS, 0, st>>>(seq, n_bytes, k, complements ? 1 : 0, shift0, bits0, hist, tile_hist,
+                                                                                   tile0);
+        }
+        ++ex.launches;
+        kc_ks_scan0_kernel<<<1, 256, 0, st>>>(hist, cursor, big_a, big_cap, small, small_cap, uniform, uniform_cap, ctr, cells, cap, Cfg::TILE,
+                                             key_bits - bits0);
+        ++ex.launches;
+        KC_CUDA(cudaGetLastError());
+        KC_CUDA(cudaMemcpyAsync(h, ctr, 32, cudaMemcpyDeviceToHost, st));
+        KC_CUDA(cudaMemcpyAsync(&M, cells, 8, cudaMemcpyDeviceToHost, st));
+        if (mode == KS_PARTITION) KC_CUDA(cudaMemcpyAsync(shard->host_hist, hist, 256 * 4, cudaMemcpyDeviceToHost, st));
+        KC_CUDA(cudaStreamSynchronize(st));
+        res.n_occ = M;
+        if (M == 0) {
+            ex.arena->release(base_mark);
+            return res;
+        }
+        if (h[3]) KC_THROW(KC_ERR_INTERNAL, "k-mer set bucket list overflow");
+        if (M >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 k-mer occurrences on one GPU");
+    } else {
+        M = shard->n_items;
+        res.n_occ = M;
+        if (M >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 k-mer occurrences on one GPU");
+        SortBucket root;
+        root.off = 0;
+        root.size = (u32) M;
+        root.rem = (u16) key_bits;
+        root.parity = 0;
+        root.bits = 0;
+        if (M <= cap) {
+            KC_CUDA(cudaMemcpyAsync(small, &root, sizeof(root), cudaMemcpyHostToDevice, st));
+            h[1] = 1;
+            h[5] = M > 1024 ? 1 : 0;
+        } else {
+            KC_CUDA(cudaMemcpyAsync(big_a, &root, sizeof(root), cudaMemcpyHostToDevice, st));
+            h[0] = 1;
+            h[4] = (u32) kc_div_up(M, (u64) Cfg::TILE);
+        }
+        u32 init[8] = {h[0], h[1], 0, 0, h[4], h[5], 0, 0};
+        KC_CUDA(cudaMemcpyAsync(ctr, init, 32, cudaMemcpyHostToDevice, st));
+        KC_CUDA(cudaStreamSynchronize(st));  // root / init live on this stack frame
+    }
+    // k1 is allocated last: the KEYS result is compacted into k1 and then copied down to base_mark, and everything
+    // allocated before k1 (control arrays, k0, payloads, counts: > U * (8L + 1) bytes) separates the two regions.
+    if (mode == KS_WHOLE) {
+        k0 = ex.alloc<KWord<L>>(M);
+        if (PAY) {
+            p0 = ex.alloc<u32>(M);
+            p1 = ex.alloc<u32>(M);
+        }
+        cnt_tmp = KEYS ? ex.alloc<u8>(M) : nullptr;
+        k1 = ex.alloc<KWord<L>>(M);
+    } else {
+        k0 = reinterpret_cast<KWord<L> *>(shard->keys);
+        p0 = shard->pos;
+        if (mode == KS_RESOLVE) {
+            k1 = ex.alloc<KWord<L>>(M);
+            p1 = ex.alloc<u32>(M);
+        }
+    }
+    if (mode != KS_RESOLVE) {
+        {
+            CudaExec::Scope sc(ex, KP_KS_SCATTER0, (pos_end - pos_begin) + M * (sizeof(KWord<L>) + (PAY ? 4 : 0)));
+            kc_ks_scatter0_kernel<L, PAY, SCRAMBLE><<<ex_blocks, Cfg::EX_THREADS, scatter0_smem, st>>>(seq, n_bytes, k, complements ? 1 : 0, shift0,
+                                                                                                   bits0, cursor, tile_hist, k0, p0, tile0);
+        }
+        ++ex.launches;
+        KC_CUDA(cudaGetLastError());
+    }
+    if (mode == KS_PARTITION) {
+        KC_CUDA(cudaStreamSynchronize(st));
         ex.arena->release(base_mark);
         return res;
     }
-    if (h[3]) KC_THROW(KC_ERR_INTERNAL, "k-mer set bucket list overflow");
-    if (M >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 k-mer occurrences on one GPU");
-    // k1 is allocated last: the KEYS result is compacted into k1 and then copied down to base_mark, and everything
-    // allocated before k1 (control arrays, k0, payloads, counts: > U * (8L + 1) bytes) separates the two regions.
-    KWord<L> *k0 = ex.alloc<KWord<L>>(M);
-    u32 *p0 = nullptr, *p1 = nullptr;
-    if (PAY) {
-        p0 = ex.alloc<u32>(M);
-        p1 = ex.alloc<u32>(M);
-    }
-    u8 *cnt_tmp = KEYS ? ex.alloc<u8>(M) : nullptr;
-    KWord<L> *k1 = ex.alloc<KWord<L>>(M);
-    {
-        CudaExec::Scope sc(ex, KP_KS_SCATTER0, n_bytes + M * (sizeof(KWord<L>) + (PAY ? 4 : 0)));
-        kc_ks_scatter0_kernel<L, PAY, SCRAMBLE><<<ex_blocks, Cfg::EX_THREADS, scatter0_smem, st>>>(seq, n_bytes, k, complements ? 1 : 0, shift0, bits0,
-                                                                                          cursor, tile_hist, k0, p0);
-    }
-    ++ex.launches;
-    KC_CUDA(cudaGetLastError());
 
     // ---- levels >= 1 ----
     u32 nb = h[0], n_small = h[1], n_uniform = h[2], n_tiles = h[4], n_small_b = h[5];
+    (void) n_small_b;
     SortBucket *cur = big_a, *nxt = big_b;
     const u32 max_ctas = 148 * 8;
     while (nb > 0) {
@@ -1095,6 +1165,16 @@ KmerSet<L> kc_kmerset_build(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, boo
         return kc_kmerset_build_impl<L, true, false>(ex, seq, n_bytes, k, complements, min_freq, flags, ext_kept_cell);
     }
     return kc_kmerset_build_impl<L, false, true>(ex, seq, n_bytes, k, complements, min_freq, nullptr, nullptr);
+}
+
+// Sharded entry points (FLAGS-only; see KsShard).
+template <int L> u64 kc_kmerset_partition(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, KsShard *shard) {
+    shard->mode = KS_PARTITION;
+    return kc_kmerset_build_impl<L, true, false>(ex, seq, n_bytes, k, complements, 1, nullptr, nullptr, shard).n_occ;
+}
+template <int L> u64 kc_kmerset_resolve(CudaExec &ex, int k, int min_freq, u32 *flags, KsShard *shard) {
+    shard->mode = KS_RESOLVE;
+    return kc_kmerset_build_impl<L, true, false>(ex, nullptr, 0, k, true, min_freq, flags, nullptr, shard).n_kept;
 }
 
 #endif  // __CUDACC__

@@ -1,0 +1,163 @@
+"""Hash-range sharded `compute` across the GPUs of one box (the reference is single-process).
+
+    rank r:  partition   the k-mers of its slice of window positions, grouped by owner rank        (kc_shard_partition)
+             exchange    counts, then (scrambled k-mer, global position) items: all-to-all over NVLink   (NCCL)
+             resolve     every occurrence of its hash range: first occurrence per kept k-mer -> flag bits  (kc_shard_resolve)
+             reduce      the disjoint flag bit arrays onto rank 0 (SUM == OR)                            (NCCL)
+    rank 0:  runs -> overlap levels -> superstring (the greedy merge is sequential)                       (kc_compute_from_flags)
+
+The orchestration below is backend-agnostic: `ops` does the per-rank halves and `comm` the collectives.  The product
+pairing is GpuOps (libkcgpu through ctypes, torch CUDA tensors as buffers) + TorchComm over NCCL; tests/ pair the same
+orchestration with a CPU stand-in for the kernels and TorchComm over gloo to check the host-side logic with
+world_size 2 on a machine without a GPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+N_DIGITS = 256  # level-0 groups of the k-mer set construction (top 8 bits of the scrambled word)
+
+
+def plan_slices(n_bytes: int, world: int, granule: int):
+    """Window-END position slices [begin, end) per rank: multiples of `granule`, the last one ends at n_bytes."""
+    tiles = -(-n_bytes // granule)
+    out = []
+    for r in range(world):
+        b = min(n_bytes, (tiles * r // world) * granule)
+        e = n_bytes if r == world - 1 else min(n_bytes, (tiles * (r + 1) // world) * granule)
+        out.append((b, e))
+    return out
+
+
+def owner_of_digit(digit: int, world: int) -> int:
+    return digit * world // N_DIGITS
+
+
+def owner_counts(digit_counts, world: int):
+    """Items per owner rank from the 256 digit counts (the owners' digit ranges are contiguous and ascending)."""
+    owners = np.arange(N_DIGITS) * world // N_DIGITS
+    return np.bincount(owners, weights=np.asarray(digit_counts, dtype=np.float64), minlength=world).astype(np.int64)
+
+
+@dataclass
+class ShardedResult:
+    result: object          # rank 0: what ops.finish returned; other ranks: None
+    n_kept: int             # distinct k-mers kept (all ranks)
+    n_occurrences: int      # k-mer windows seen (all ranks)
+    items_sent: int         # items this rank sent to other ranks
+    items_received: int     # items this rank resolved
+
+
+def sharded_compute(ops, comm, n_bytes: int, *, k: int, complements: bool = True, min_frequency: int = 1) -> ShardedResult:
+    """One pass of the sharded path.  `ops` already holds the framed sequence of n_bytes bytes."""
+    world, rank = comm.world, comm.rank
+    b, e = plan_slices(n_bytes, world, ops.granule(k))[rank]
+    digit_counts, n_items = ops.partition(b, e, k=k, complements=complements)           # items grouped by owner
+    send = owner_counts(digit_counts, world)
+    assert int(send.sum()) == n_items
+    recv = comm.exchange_counts(send)                                                    # recv[s] = items rank s sends here
+    keys, pos = ops.exchange_items(comm, send, recv)                                     # all-to-all (two tensors)
+    n_recv = int(recv.sum())
+    kept = ops.resolve(keys, pos, n_recv, k=k, complements=complements, min_frequency=min_frequency)
+    ops.reduce_flags(comm)                                                               # disjoint bits: SUM == OR, onto rank 0
+    tot = comm.sum_scalars([kept, n_items])
+    res = ops.finish(int(tot[0]), k=k, complements=complements) if rank == 0 else None
+    return ShardedResult(res, int(tot[0]), int(tot[1]), int(n_items - send[rank]), n_recv)
+
+
+class TorchComm:
+    """torch.distributed plumbing (NCCL on the GPU box, gloo in the CPU tests)."""
+
+    def __init__(self, device):
+        import torch.distributed as dist
+        self.dist = dist
+        self.device = device
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+
+    def exchange_counts(self, send):
+        import torch
+        s = torch.as_tensor(np.asarray(send, dtype=np.int64), device=self.device)
+        r = torch.empty_like(s)
+        if self.world > 1:
+            self.dist.all_to_all_single(r, s)
+        else:
+            r.copy_(s)
+        return r.cpu().numpy()
+
+    def all_to_all(self, out, inp, recv_counts, send_counts, width: int = 1):
+        """Variable-size all-to-all of rows of `width` elements."""
+        if self.world > 1:
+            self.dist.all_to_all_single(out, inp, [int(c) * width for c in recv_counts], [int(c) * width for c in send_counts])
+        else:
+            out.copy_(inp[:out.numel()])
+
+    def reduce_sum(self, t, dst: int = 0):
+        if self.world > 1:
+            self.dist.reduce(t, dst=dst, op=self.dist.ReduceOp.SUM)
+
+    def sum_scalars(self, values):
+        import torch
+        t = torch.as_tensor(np.asarray(values, dtype=np.int64), device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+
+class GpuOps:
+    """The per-rank halves on the GPU: libkcgpu entry points over torch CUDA buffers (device memory plumbing only)."""
+
+    def __init__(self, ctx, seq_dev):
+        import torch
+        self.torch = torch
+        self.ctx = ctx
+        self.seq = seq_dev                      # uint8 CUDA tensor: the whole framed sequence
+        self.n_bytes = seq_dev.numel()
+        self.flags = torch.zeros((self.n_bytes + 31) // 32 + 1, dtype=torch.int32, device=seq_dev.device)
+        self._send_k = self._send_p = None
+        self._limbs = 1
+
+    def granule(self, k):
+        return int(self.ctx._lib.kc_shard_granule(k))
+
+    def partition(self, b, e, *, k, complements):
+        torch = self.torch
+        from .api import limbs_for_k
+        self._limbs = limbs_for_k(k)
+        cap = max(e - b, 1)
+        if self._send_k is None or self._send_k.numel() < cap * self._limbs:
+            self._send_k = torch.empty(cap * self._limbs, dtype=torch.int64, device=self.seq.device)
+            self._send_p = torch.empty(cap, dtype=torch.int32, device=self.seq.device)
+        counts, n = self.ctx.shard_partition(self.seq.data_ptr(), self.n_bytes, b, e, self._send_k.data_ptr(), self._send_p.data_ptr(),
+                                             k=k, complements=complements)
+        self._n_send = n
+        return counts, n
+
+    def exchange_items(self, comm, send, recv):
+        torch = self.torch
+        n_recv = int(recv.sum())
+        L = self._limbs
+        keys = torch.empty(max(n_recv, 1) * L, dtype=torch.int64, device=self.seq.device)
+        pos = torch.empty(max(n_recv, 1), dtype=torch.int32, device=self.seq.device)
+        comm.all_to_all(keys[:n_recv * L], self._send_k[:self._n_send * L], recv, send, L)
+        comm.all_to_all(pos[:n_recv], self._send_p[:self._n_send], recv, send, 1)
+        return keys, pos
+
+    def resolve(self, keys, pos, n, *, k, complements, min_frequency):
+        self.flags.zero_()
+        self.torch.cuda.current_stream().synchronize()
+        return self.ctx.shard_resolve(keys.data_ptr(), pos.data_ptr(), n, self.flags.data_ptr(), k=k, complements=complements,
+                                      min_frequency=min_frequency)
+
+    def reduce_flags(self, comm):
+        comm.reduce_sum(self.flags, 0)
+
+    def finish(self, n_kept, *, k, complements):
+        self.torch.cuda.current_stream().synchronize()
+        return self.ctx.compute_from_flags(self.seq.data_ptr(), self.n_bytes, self.flags.data_ptr(), n_kept, k=k, complements=complements)
