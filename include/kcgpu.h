@@ -134,6 +134,23 @@ int kc_profile_count(void);
 int kc_profile_get(kc_ctx *ctx, int i, const char **name, double *ms, uint64_t *launches, uint64_t *bytes);
 int kc_profile_reset(kc_ctx *ctx);
 
+/* Fused partition + exchange (the product multi-GPU path): the level-0 scatter pass stores every item straight into the
+ * receive buffer of its owner GPU through peer pointers (CUDA IPC, NVLink), so the partition pass IS the all-to-all and
+ * the owner finds complete, contiguous level-0 buckets.  Sequence of calls per rank:
+ *   once:      kc_p2p_alloc (receive buffers of capacity_items items; returns two 64-byte IPC handles = 128 bytes)
+ *              -> all-gather the handles -> kc_p2p_open (all_handles: n_ranks * 128 bytes, rank order)
+ *   per job:   kc_p2p_hist (256 digit counts of the slice, host) -> all-gather the counts ->
+ *              kc_p2p_scatter (all_counts[n_ranks][256], host) -> barrier across ranks ->
+ *              kc_p2p_resolve (flags as kc_shard_resolve) -> reduce flags -> kc_compute_from_flags on rank 0.
+ * A barrier is also needed before the NEXT kc_p2p_scatter (peers must be done resolving). */
+int kc_p2p_alloc(kc_ctx *ctx, int k, uint64_t capacity_items, uint8_t *handles_out);
+int kc_p2p_open(kc_ctx *ctx, int n_ranks, int rank, const uint8_t *all_handles);
+int kc_p2p_hist(kc_ctx *ctx, const kc_params *p, const uint8_t *seq_dev, uint64_t n_bytes, uint64_t pos_begin, uint64_t pos_end,
+                uint64_t *digit_counts);
+int kc_p2p_scatter(kc_ctx *ctx, const kc_params *p, const uint8_t *seq_dev, uint64_t n_bytes, uint64_t pos_begin, uint64_t pos_end,
+                   const uint64_t *all_counts);
+int kc_p2p_resolve(kc_ctx *ctx, const kc_params *p, const uint64_t *all_counts, uint32_t *flags_dev, uint64_t *n_kept, uint64_t *n_owned);
+
 /* CUDA kernels launched through this context since kc_init (every entry point adds its own). */
 uint64_t kc_total_launches(const kc_ctx *ctx);
 

@@ -81,6 +81,11 @@ def load_library():
     L.kc_shard_resolve.argtypes = [C.c_void_p, C.POINTER(kc_params), C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, u64p]
     L.kc_compute_from_flags.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.c_void_p, C.c_uint64,
                                         C.POINTER(kc_output)]
+    L.kc_p2p_alloc.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]
+    L.kc_p2p_open.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.kc_p2p_hist.argtypes = [C.c_void_p, C.POINTER(kc_params), C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, u64p]
+    L.kc_p2p_scatter.argtypes = [C.c_void_p, C.POINTER(kc_params), C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, u64p]
+    L.kc_p2p_resolve.argtypes = [C.c_void_p, C.POINTER(kc_params), u64p, C.c_void_p, u64p, u64p]
     L.kc_total_launches.argtypes = [C.c_void_p]
     L.kc_total_launches.restype = C.c_uint64
     L.kc_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
@@ -100,7 +105,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ["kc_init", "kc_destroy", "kc_compute", "kc_compute_device", "kc_copy_to_host", "kc_count_kmers", "kc_overlap_path",
-                    "kc_total_launches", "kc_shard_granule", "kc_shard_partition", "kc_shard_resolve", "kc_compute_from_flags",
+                    "kc_p2p_alloc", "kc_p2p_open", "kc_p2p_hist", "kc_p2p_scatter", "kc_p2p_resolve", "kc_total_launches", "kc_shard_granule", "kc_shard_partition", "kc_shard_resolve", "kc_compute_from_flags",
                     "kc_frame_fasta", "kc_set_option", "kc_profile_enable", "kc_profile_count", "kc_profile_get", "kc_profile_reset",
                     "kc_limbs_for_k", "kc_free", "kc_strerror", "kc_last_error"]
 
@@ -266,6 +271,36 @@ class Context:
         out = kc_output()
         self._check(self._lib.kc_compute_from_flags(self._h, C.byref(p), C.byref(inp), C.c_void_p(flags_ptr), n_kept, C.byref(out)))
         return self._result(out, False)
+
+    # ---- fused partition + exchange over peer memory (see include/kcgpu.h kc_p2p_*) ------------------------------------
+    def p2p_alloc(self, k: int, capacity_items: int) -> np.ndarray:
+        h = np.zeros(128, dtype=np.uint8)
+        self._check(self._lib.kc_p2p_alloc(self._h, k, capacity_items, h.ctypes.data))
+        return h
+
+    def p2p_open(self, n_ranks: int, rank: int, all_handles: np.ndarray):
+        all_handles = np.ascontiguousarray(all_handles, dtype=np.uint8)
+        assert all_handles.size == n_ranks * 128
+        self._check(self._lib.kc_p2p_open(self._h, n_ranks, rank, all_handles.ctypes.data))
+
+    def p2p_hist(self, seq_ptr: int, n_bytes: int, pos_begin: int, pos_end: int, *, k, complements=True) -> np.ndarray:
+        p = self._params(k, complements, 1, False, False)
+        counts = np.zeros(256, dtype=np.uint64)
+        self._check(self._lib.kc_p2p_hist(self._h, C.byref(p), C.c_void_p(seq_ptr), n_bytes, pos_begin, pos_end, counts.ctypes.data_as(u64p)))
+        return counts.astype(np.int64)
+
+    def p2p_scatter(self, seq_ptr: int, n_bytes: int, pos_begin: int, pos_end: int, all_counts: np.ndarray, *, k, complements=True):
+        p = self._params(k, complements, 1, False, False)
+        ac = np.ascontiguousarray(all_counts, dtype=np.uint64)
+        self._check(self._lib.kc_p2p_scatter(self._h, C.byref(p), C.c_void_p(seq_ptr), n_bytes, pos_begin, pos_end, ac.ctypes.data_as(u64p)))
+
+    def p2p_resolve(self, all_counts: np.ndarray, flags_ptr: int, *, k, complements=True, min_frequency=1):
+        """-> (kept distinct k-mers of this rank's hash range, items resolved)"""
+        p = self._params(k, complements, min_frequency, False, False)
+        ac = np.ascontiguousarray(all_counts, dtype=np.uint64)
+        kept, owned = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.kc_p2p_resolve(self._h, C.byref(p), ac.ctypes.data_as(u64p), C.c_void_p(flags_ptr), C.byref(kept), C.byref(owned)))
+        return kept.value, owned.value
 
     def total_launches(self) -> int:
         return int(self._lib.kc_total_launches(self._h))

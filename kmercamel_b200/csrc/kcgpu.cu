@@ -24,6 +24,8 @@ static const bool kc_trace = std::getenv("KC_TRACE") != nullptr;
         if (kc_trace) std::fprintf(stderr, "[kc_trace] %-28s %.3f ms\n", (label), kc_now_ms()); \
     } while (0)
 
+static const int KC_MAX_PEERS = 16;
+
 struct kc_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -38,6 +40,21 @@ struct kc_ctx {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool small_engine = true;
     u64 total_launches = 0;  // kernels launched through this context since kc_init
+    // fused partition + exchange over peer memory (kc_p2p_*)
+    struct P2P {
+        int n_ranks = 0, rank = 0, limbs = 0;
+        u64 capacity = 0;                 // items per receive buffer
+        void *recv_k = nullptr;           // own receive buffers (cudaMalloc, exported through CUDA IPC)
+        u32 *recv_p = nullptr;
+        void *peer_k[KC_MAX_PEERS] = {};  // every rank's receive buffers as seen from this process
+        u32 *peer_p[KC_MAX_PEERS] = {};
+        bool opened[KC_MAX_PEERS] = {};
+        u16 *tile_hist = nullptr;         // kept between kc_p2p_hist and kc_p2p_scatter
+        size_t tile_hist_cap = 0;
+        void **dst_k = nullptr;           // device tables of 256 destination pointers
+        u32 **dst_p = nullptr;
+        u64 n_items = 0;                  // items of this rank's slice (from kc_p2p_hist)
+    } p2p;
     bool arena_limited = false;
     std::string last_error;
 };
@@ -355,6 +372,16 @@ void kc_destroy(kc_ctx *ctx) {
     if (ctx->arena.base) cudaFree(ctx->arena.base);
     if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
     if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+    for (int r = 0; r < ctx->p2p.n_ranks && r < KC_MAX_PEERS; ++r)
+        if (ctx->p2p.opened[r]) {
+            cudaIpcCloseMemHandle(ctx->p2p.peer_k[r]);
+            cudaIpcCloseMemHandle(ctx->p2p.peer_p[r]);
+        }
+    if (ctx->p2p.recv_k) cudaFree(ctx->p2p.recv_k);
+    if (ctx->p2p.recv_p) cudaFree(ctx->p2p.recv_p);
+    if (ctx->p2p.tile_hist) cudaFree(ctx->p2p.tile_hist);
+    if (ctx->p2p.dst_k) cudaFree(ctx->p2p.dst_k);
+    if (ctx->p2p.dst_p) cudaFree(ctx->p2p.dst_p);
     for (int i = 0; i < 6; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (cudaEvent_t e : ctx->prof.pool) cudaEventDestroy(e);
@@ -588,6 +615,194 @@ int kc_compute_from_flags(kc_ctx *ctx, const kc_params *p, const kc_input *in, c
     out->n_nodes = res.n_nodes;
     out->n_launches = ex.launches;
     fill_times(ctx, out);
+    ctx->total_launches += ex.launches;
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
+// ---- fused partition + exchange over peer memory -------------------------------------------------------------------------
+int kc_p2p_alloc(kc_ctx *ctx, int k, uint64_t capacity_items, uint8_t *handles_out) {
+    if (!ctx || !handles_out || capacity_items == 0) return KC_ERR_ARG;
+    KC_API_BEGIN
+    if (k < 1 || k > 127) KC_THROW(KC_ERR_ARG, "k must be in 1..127");
+    KC_CUDA(cudaSetDevice(ctx->device));
+    kc_ctx::P2P &q = ctx->p2p;
+    if (q.recv_k || q.n_ranks) KC_THROW(KC_ERR_ARG, "peer buffers already allocated on this context");
+    q.limbs = kc_limbs_for_k(k);
+    q.capacity = capacity_items;
+    KC_CUDA(cudaMalloc(&q.recv_k, capacity_items * 8 * q.limbs));
+    KC_CUDA(cudaMalloc(&q.recv_p, capacity_items * 4));
+    KC_CUDA(cudaMalloc(&q.dst_k, 256 * sizeof(void *)));
+    KC_CUDA(cudaMalloc(&q.dst_p, 256 * sizeof(u32 *)));
+    cudaIpcMemHandle_t hk, hp;
+    KC_CUDA(cudaIpcGetMemHandle(&hk, q.recv_k));
+    KC_CUDA(cudaIpcGetMemHandle(&hp, q.recv_p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::memcpy(handles_out, &hk, 64);
+    std::memcpy(handles_out + 64, &hp, 64);
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
+int kc_p2p_open(kc_ctx *ctx, int n_ranks, int rank, const uint8_t *all_handles) {
+    if (!ctx || !all_handles) return KC_ERR_ARG;
+    KC_API_BEGIN
+    if (n_ranks < 1 || n_ranks > KC_MAX_PEERS || rank < 0 || rank >= n_ranks) KC_THROW(KC_ERR_ARG, "bad rank / world size");
+    kc_ctx::P2P &q = ctx->p2p;
+    if (!q.recv_k) KC_THROW(KC_ERR_ARG, "kc_p2p_alloc first");
+    KC_CUDA(cudaSetDevice(ctx->device));
+    for (int r = 0; r < n_ranks; ++r) {
+        if (r == rank) {
+            q.peer_k[r] = q.recv_k;
+            q.peer_p[r] = q.recv_p;
+            continue;
+        }
+        cudaIpcMemHandle_t hk, hp;
+        std::memcpy(&hk, all_handles + (size_t) r * 128, 64);
+        std::memcpy(&hp, all_handles + (size_t) r * 128 + 64, 64);
+        KC_CUDA(cudaIpcOpenMemHandle(&q.peer_k[r], hk, cudaIpcMemLazyEnablePeerAccess));
+        void *pp = nullptr;
+        KC_CUDA(cudaIpcOpenMemHandle(&pp, hp, cudaIpcMemLazyEnablePeerAccess));
+        q.peer_p[r] = reinterpret_cast<u32 *>(pp);
+        q.opened[r] = true;
+    }
+    q.n_ranks = n_ranks;
+    q.rank = rank;
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
+int kc_p2p_hist(kc_ctx *ctx, const kc_params *p, const uint8_t *seq_dev, uint64_t n_bytes, uint64_t pos_begin, uint64_t pos_end,
+                uint64_t *digit_counts) {
+    if (!ctx || !seq_dev || !digit_counts) return KC_ERR_ARG;
+    KC_API_BEGIN
+    check_params(p);
+    if (p->assume_simplitigs || p->want_maxone) KC_THROW(KC_ERR_ARG, "sharded construction supports neither -S nor -M");
+    if (n_bytes >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 sequence bytes");
+    if ((reinterpret_cast<uintptr_t>(seq_dev) & 15) != 0) KC_THROW(KC_ERR_ARG, "device sequence pointer must be 16-byte aligned");
+    kc_ctx::P2P &q = ctx->p2p;
+    if (!q.n_ranks || kc_limbs_for_k(p->k) != q.limbs) KC_THROW(KC_ERR_ARG, "peer buffers not set up for this word width");
+    KC_CUDA(cudaSetDevice(ctx->device));
+    const u64 span = pos_end > pos_begin ? pos_end - pos_begin : 0;
+    const size_t need = (size_t) (kc_div_up(span, kc_shard_granule(p->k)) + 1) * 256 * sizeof(u16);
+    if (q.tile_hist_cap < need) {
+        if (q.tile_hist) KC_CUDA(cudaFree(q.tile_hist));
+        q.tile_hist = nullptr;
+        q.tile_hist_cap = 0;
+        KC_CUDA(cudaMalloc(&q.tile_hist, need));
+        q.tile_hist_cap = need;
+    }
+    ensure_arena(ctx, 64u << 20);
+    ctx->arena.reset();
+    CudaExec ex{ctx->stream, &ctx->arena};
+    ex.prof = &ctx->prof;
+    KsShard sh;
+    sh.pos_begin = pos_begin;
+    sh.pos_end = pos_end;
+    sh.tile_hist_keep = q.tile_hist;
+    const bool c = p->complements != 0;
+    if (q.limbs == 1) q.n_items = kc_kmerset_hist_only<1>(ex, seq_dev, n_bytes, p->k, c, &sh);
+    else if (q.limbs == 2) q.n_items = kc_kmerset_hist_only<2>(ex, seq_dev, n_bytes, p->k, c, &sh);
+    else q.n_items = kc_kmerset_hist_only<4>(ex, seq_dev, n_bytes, p->k, c, &sh);
+    for (int i = 0; i < 256; ++i) digit_counts[i] = sh.host_hist[i];
+    ctx->total_launches += ex.launches;
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
+// all_counts[s * 256 + g] = items of digit g on rank s.  Layout of an owner's receive buffer: its digits ascending,
+// inside a digit the ranks ascending.
+static void p2p_layout(const kc_ctx::P2P &q, const uint64_t *all_counts, u64 *bucket_off /*[256]*/, u64 *bucket_size /*[256]*/, u64 *owned /*[n_ranks]*/) {
+    for (int r = 0; r < q.n_ranks; ++r) owned[r] = 0;
+    for (int g = 0; g < 256; ++g) {
+        const int o = g * q.n_ranks / 256;
+        u64 sz = 0;
+        for (int s = 0; s < q.n_ranks; ++s) sz += all_counts[(size_t) s * 256 + g];
+        bucket_off[g] = owned[o];
+        bucket_size[g] = sz;
+        owned[o] += sz;
+    }
+}
+
+int kc_p2p_scatter(kc_ctx *ctx, const kc_params *p, const uint8_t *seq_dev, uint64_t n_bytes, uint64_t pos_begin, uint64_t pos_end,
+                   const uint64_t *all_counts) {
+    if (!ctx || !seq_dev || !all_counts) return KC_ERR_ARG;
+    KC_API_BEGIN
+    check_params(p);
+    kc_ctx::P2P &q = ctx->p2p;
+    if (!q.n_ranks || kc_limbs_for_k(p->k) != q.limbs || !q.tile_hist) KC_THROW(KC_ERR_ARG, "kc_p2p_hist first");
+    KC_CUDA(cudaSetDevice(ctx->device));
+    u64 off[256], size[256], owned[KC_MAX_PEERS], cursor0[256];
+    p2p_layout(q, all_counts, off, size, owned);
+    for (int r = 0; r < q.n_ranks; ++r)
+        if (owned[r] > q.capacity) KC_THROW(KC_ERR_TOO_LARGE, "a rank's hash range exceeds the peer buffer capacity");
+    void *hk[256];
+    u32 *hp[256];
+    for (int g = 0; g < 256; ++g) {
+        const int o = g * q.n_ranks / 256;
+        u64 before = 0;
+        for (int s = 0; s < q.rank; ++s) before += all_counts[(size_t) s * 256 + g];
+        cursor0[g] = off[g] + before;
+        hk[g] = q.peer_k[o];
+        hp[g] = q.peer_p[o];
+    }
+    KC_CUDA(cudaMemcpyAsync(q.dst_k, hk, sizeof(hk), cudaMemcpyHostToDevice, ctx->stream));
+    KC_CUDA(cudaMemcpyAsync(q.dst_p, hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
+    ensure_arena(ctx, 64u << 20);
+    ctx->arena.reset();
+    CudaExec ex{ctx->stream, &ctx->arena};
+    ex.prof = &ctx->prof;
+    KsShard sh;
+    sh.pos_begin = pos_begin;
+    sh.pos_end = pos_end;
+    sh.tile_hist_keep = q.tile_hist;
+    sh.cursor0 = cursor0;
+    sh.dst_k = q.dst_k;
+    sh.dst_p = q.dst_p;
+    const bool c = p->complements != 0;
+    if (q.limbs == 1) kc_kmerset_scatter_p2p<1>(ex, seq_dev, n_bytes, p->k, c, q.n_items, &sh);
+    else if (q.limbs == 2) kc_kmerset_scatter_p2p<2>(ex, seq_dev, n_bytes, p->k, c, q.n_items, &sh);
+    else kc_kmerset_scatter_p2p<4>(ex, seq_dev, n_bytes, p->k, c, q.n_items, &sh);
+    KC_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->total_launches += ex.launches;
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
+int kc_p2p_resolve(kc_ctx *ctx, const kc_params *p, const uint64_t *all_counts, uint32_t *flags_dev, uint64_t *n_kept, uint64_t *n_owned) {
+    if (!ctx || !all_counts || !flags_dev || !n_kept) return KC_ERR_ARG;
+    KC_API_BEGIN
+    check_params(p);
+    kc_ctx::P2P &q = ctx->p2p;
+    if (!q.n_ranks || kc_limbs_for_k(p->k) != q.limbs) KC_THROW(KC_ERR_ARG, "peer buffers not set up for this word width");
+    KC_CUDA(cudaSetDevice(ctx->device));
+    u64 off[256], size[256], owned[KC_MAX_PEERS];
+    p2p_layout(q, all_counts, off, size, owned);
+    *n_kept = 0;
+    if (n_owned) *n_owned = owned[q.rank];
+    if (owned[q.rank] == 0) return KC_OK;
+    u64 my_off[256], my_size[256];
+    u32 n_pre = 0;
+    for (int g = 0; g < 256; ++g)
+        if (g * q.n_ranks / 256 == q.rank) {
+            my_off[n_pre] = off[g];
+            my_size[n_pre] = size[g];
+            ++n_pre;
+        }
+    ensure_arena(ctx, (size_t) ((double) owned[q.rank] * (8.0 * q.limbs + 4.0 + 2.0) * 1.1) + (128u << 20));
+    ctx->arena.reset();
+    CudaExec ex{ctx->stream, &ctx->arena};
+    ex.prof = &ctx->prof;
+    KsShard sh;
+    sh.keys = q.recv_k;
+    sh.pos = q.recv_p;
+    sh.n_items = owned[q.rank];
+    sh.n_pre = n_pre;
+    sh.pre_off = my_off;
+    sh.pre_size = my_size;
+    if (q.limbs == 1) *n_kept = kc_kmerset_resolve<1>(ex, p->k, p->min_frequency, flags_dev, &sh);
+    else if (q.limbs == 2) *n_kept = kc_kmerset_resolve<2>(ex, p->k, p->min_frequency, flags_dev, &sh);
+    else *n_kept = kc_kmerset_resolve<4>(ex, p->k, p->min_frequency, flags_dev, &sh);
     ctx->total_launches += ex.launches;
     return KC_OK;
     KC_API_END(ctx)

@@ -23,6 +23,7 @@
 #include "kword.cuh"
 #include "sort.cuh"
 #include "stage1.cuh"
+#include <vector>
 
 template <int L> struct KsCfg {
     static constexpr int EX_THREADS = L == 1 ? 256 : (L == 2 ? 128 : 64);  // level 0: one 32-base strip per thread
@@ -256,10 +257,16 @@ __global__ void __launch_bounds__(256) kc_ks_scan0_kernel(const u32 *hist, u64 *
     }
 }
 
-template <int L, bool PAY, bool SCR>
+// P2P = true (multi-GPU): bucket g is stored through dst_k[g] / dst_p[g], which point into the receive buffers of the
+// bucket's OWNER GPU (peer memory mapped over NVLink); cursor[g] then starts at this rank's segment of that bucket, so
+// the partition pass IS the all-to-all: no intermediate send buffer, no separate collective, and the owner finds its
+// level-0 buckets complete and contiguous.
+template <int L, bool PAY, bool SCR, bool P2P = false>
 __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ks_scatter0_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int complements,
                                                                                int shift, int bits, u64 *cursor, const u16 *__restrict__ tile_hist,
-                                                                               KWord<L> *__restrict__ keys, u32 *__restrict__ pos, u32 tile0) {
+                                                                               KWord<L> *__restrict__ keys, u32 *__restrict__ pos, u32 tile0,
+                                                                               KWord<L> *const *__restrict__ dst_k = nullptr,
+                                                                               u32 *const *__restrict__ dst_p = nullptr) {
     constexpr int T = KsCfg<L>::EX_THREADS;
     constexpr int R = 256 / T;
     constexpr int TILE = KsCfg<L>::EX_TILE;
@@ -311,8 +318,14 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ks_scatter0_kernel(co
         const KWord<L> v = stage_k[q];
         const u32 dg = v.digit(shift, bits);
         const u64 idx = gbase[dg] + (q - loff[dg]);
-        keys[idx] = v;
-        if (PAY) pos[idx] = (u32) ((u64) block_pos0 + stage_s[q]);
+        KWord<L> *kb = keys;
+        u32 *pb = pos;
+        if (P2P) {
+            kb = dst_k[dg];
+            pb = dst_p[dg];
+        }
+        kb[idx] = v;
+        if (PAY) pb[idx] = (u32) ((u64) block_pos0 + stage_s[q]);
     }
 }
 
@@ -866,14 +879,22 @@ __global__ void __launch_bounds__(256) kc_ks_uniform_kernel(KWord<L> *k0, const 
 //                 (= by owner rank, owner = digit * n_ranks / 256); the 256 digit counts go back to the host.
 //   KS_RESOLVE    the items are given (after the all-to-all: every occurrence of this rank's hash range) and level 0
 //                 is skipped; first-occurrence bits are set at global positions.
-enum { KS_WHOLE = 0, KS_PARTITION = 1, KS_RESOLVE = 2 };
+enum { KS_WHOLE = 0, KS_PARTITION = 1, KS_RESOLVE = 2, KS_HIST = 3, KS_SCATTER_P2P = 4 };
 struct KsShard {
     int mode = KS_WHOLE;
     u64 pos_begin = 0, pos_end = 0;  // KS_PARTITION: multiples of EX_TILE (pos_end may also be n_bytes)
     void *keys = nullptr;            // caller buffers (device): KS_PARTITION out (capacity pos_end - pos_begin), KS_RESOLVE in/scratch
     u32 *pos = nullptr;
     u64 n_items = 0;                 // KS_RESOLVE
-    u32 host_hist[256];              // KS_PARTITION out
+    u32 host_hist[256];              // KS_PARTITION / KS_HIST out
+    // fused partition + exchange (peer memory): KS_HIST = histogram pass only (tile counts stay in tile_hist_keep),
+    // KS_SCATTER_P2P = scatter pass through the peer tables, KS_RESOLVE with n_pre > 0 = the owner's level-0 buckets
+    u16 *tile_hist_keep = nullptr;   // caller-owned, (tiles of the slice) * 256 entries
+    const u64 *cursor0 = nullptr;    // KS_SCATTER_P2P: host, 256 start cursors (this rank's segment inside each bucket)
+    void *const *dst_k = nullptr;    // KS_SCATTER_P2P: device tables of 256 pointers each
+    u32 *const *dst_p = nullptr;
+    u32 n_pre = 0;                   // KS_RESOLVE: level-0 buckets already in place
+    const u64 *pre_off = nullptr, *pre_size = nullptr;  // host arrays
 };
 
 template <int L> struct KmerSet {
@@ -978,6 +999,38 @@ KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k
         M = shard->n_items;
         res.n_occ = M;
         if (M >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 k-mer occurrences on one GPU");
+        if (shard->n_pre) {
+            // the owner's level-0 buckets, delivered complete and contiguous by the peers' scatter passes
+            std::vector<SortBucket> hs, hb, hu;
+            for (u32 i = 0; i < shard->n_pre; ++i) {
+                if (shard->pre_size[i] == 0) continue;
+                SortBucket b;
+                b.off = shard->pre_off[i];
+                b.size = (u32) shard->pre_size[i];
+                b.rem = (u16) (key_bits - bits0);
+                b.parity = 0;
+                b.bits = 0;
+                if (b.size <= cap) {
+                    hs.push_back(b);
+                    if (b.size > 1024u) ++h[5];
+                } else if (b.rem == 0) {
+                    hu.push_back(b);
+                } else {
+                    hb.push_back(b);
+                    h[4] += (u32) kc_div_up(b.size, (u64) Cfg::TILE);
+                }
+            }
+            h[0] = (u32) hb.size();
+            h[1] = (u32) hs.size();
+            h[2] = (u32) hu.size();
+            if (h[0] > big_cap || h[1] > small_cap || h[2] > uniform_cap) KC_THROW(KC_ERR_INTERNAL, "k-mer set bucket list overflow");
+            if (h[0]) KC_CUDA(cudaMemcpyAsync(big_a, hb.data(), hb.size() * sizeof(SortBucket), cudaMemcpyHostToDevice, st));
+            if (h[1]) KC_CUDA(cudaMemcpyAsync(small, hs.data(), hs.size() * sizeof(SortBucket), cudaMemcpyHostToDevice, st));
+            if (h[2]) KC_CUDA(cudaMemcpyAsync(uniform, hu.data(), hu.size() * sizeof(SortBucket), cudaMemcpyHostToDevice, st));
+            u32 init[8] = {h[0], h[1], h[2], 0, h[4], h[5], 0, 0};
+            KC_CUDA(cudaMemcpyAsync(ctr, init, 32, cudaMemcpyHostToDevice, st));
+            KC_CUDA(cudaStreamSynchronize(st));  // the staging vectors live on this stack frame
+        } else {
         SortBucket root;
         root.off = 0;
         root.size = (u32) M;
@@ -996,6 +1049,7 @@ KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k
         u32 init[8] = {h[0], h[1], 0, 0, h[4], h[5], 0, 0};
         KC_CUDA(cudaMemcpyAsync(ctr, init, 32, cudaMemcpyHostToDevice, st));
         KC_CUDA(cudaStreamSynchronize(st));  // root / init live on this stack frame
+        }
     }
     // k1 is allocated last: the KEYS result is compacted into k1 and then copied down to base_mark, and everything
     // allocated before k1 (control arrays, k0, payloads, counts: > U * (8L + 1) bytes) separates the two regions.
@@ -1165,6 +1219,57 @@ KmerSet<L> kc_kmerset_build(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, boo
         return kc_kmerset_build_impl<L, true, false>(ex, seq, n_bytes, k, complements, min_freq, flags, ext_kept_cell);
     }
     return kc_kmerset_build_impl<L, false, true>(ex, seq, n_bytes, k, complements, min_freq, nullptr, nullptr);
+}
+
+// Fused partition + exchange, phase A: histogram pass over the slice (tile counts are kept in shard->tile_hist_keep).
+template <int L> u64 kc_kmerset_hist_only(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, KsShard *sh) {
+    typedef KsCfg<L> Cfg;
+    for (int i = 0; i < 256; ++i) sh->host_hist[i] = 0;
+    if (sh->pos_end <= sh->pos_begin) return 0;
+    if (sh->pos_begin % Cfg::EX_TILE != 0 || (sh->pos_end % Cfg::EX_TILE != 0 && sh->pos_end != n_bytes) || sh->pos_end > n_bytes)
+        KC_THROW(KC_ERR_ARG, "shard boundaries must be multiples of the extraction tile");
+    const size_t mark = ex.arena->mark();
+    u32 *hist = ex.alloc<u32>(256);
+    ex.fill_bytes(hist, 0, 1024);
+    const u32 blocks = (u32) kc_div_up(sh->pos_end - sh->pos_begin, (u64) Cfg::EX_TILE);
+    {
+        CudaExec::Scope sc(ex, KP_KS_HIST0, sh->pos_end - sh->pos_begin);
+        kc_ks_hist0_kernel<L, true><<<blocks, Cfg::EX_THREADS, 0, ex.stream>>>(seq, n_bytes, k, complements ? 1 : 0, 64 * L - Cfg::D0, Cfg::D0, hist,
+                                                                            sh->tile_hist_keep, (u32) (sh->pos_begin / Cfg::EX_TILE));
+    }
+    ++ex.launches;
+    KC_CUDA(cudaGetLastError());
+    ex.read_n(hist, sh->host_hist, 256);
+    ex.arena->release(mark);
+    u64 m = 0;
+    for (int i = 0; i < 256; ++i) m += sh->host_hist[i];
+    return m;
+}
+
+// Phase B: scatter pass through the peer tables (see kc_ks_scatter0_kernel, P2P = true).  n_items = this rank's items.
+template <int L> void kc_kmerset_scatter_p2p(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, u64 n_items, KsShard *sh) {
+    typedef KsCfg<L> Cfg;
+    if (sh->pos_end <= sh->pos_begin) return;
+    const size_t mark = ex.arena->mark();
+    u64 *cursor = ex.alloc<u64>(256);
+    KC_CUDA(cudaMemcpyAsync(cursor, sh->cursor0, 256 * 8, cudaMemcpyHostToDevice, ex.stream));
+    const int smem = Cfg::EX_TILE * ((int) sizeof(KWord<L>) + 2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        KC_CUDA(cudaFuncSetAttribute(kc_ks_scatter0_kernel<L, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    const u32 blocks = (u32) kc_div_up(sh->pos_end - sh->pos_begin, (u64) Cfg::EX_TILE);
+    {
+        CudaExec::Scope sc(ex, KP_KS_SCATTER0, (sh->pos_end - sh->pos_begin) + n_items * (sizeof(KWord<L>) + 4));
+        kc_ks_scatter0_kernel<L, true, true, true><<<blocks, Cfg::EX_THREADS, smem, ex.stream>>>(
+            seq, n_bytes, k, complements ? 1 : 0, 64 * L - Cfg::D0, Cfg::D0, cursor, sh->tile_hist_keep, nullptr, nullptr,
+            (u32) (sh->pos_begin / Cfg::EX_TILE), reinterpret_cast<KWord<L> *const *>(sh->dst_k), sh->dst_p);
+    }
+    ++ex.launches;
+    KC_CUDA(cudaGetLastError());
+    KC_CUDA(cudaStreamSynchronize(ex.stream));  // cursor0 is a host stack array of the caller; peers wait on this kernel
+    ex.arena->release(mark);
 }
 
 // Sharded entry points (FLAGS-only; see KsShard).

@@ -67,6 +67,23 @@ def sharded_compute(ops, comm, n_bytes: int, *, k: int, complements: bool = True
     return ShardedResult(res, int(tot[0]), int(tot[1]), int(n_items - send[rank]), n_recv)
 
 
+def sharded_compute_p2p(ops, comm, n_bytes: int, *, k: int, complements: bool = True, min_frequency: int = 1) -> ShardedResult:
+    """The product multi-GPU pass: the level-0 scatter stores every item straight into its owner's buffer over NVLink
+    (peer pointers), so there is no item all-to-all at all — only the 256 digit counts travel through a collective."""
+    world, rank = comm.world, comm.rank
+    b, e = plan_slices(n_bytes, world, ops.granule(k))[rank]
+    counts = ops.p2p_hist(b, e, k=k, complements=complements)                            # 256 digit counts of the slice
+    all_counts = comm.all_gather_counts(counts)                                          # [world, 256]
+    ops.p2p_scatter(b, e, all_counts, k=k, complements=complements)                      # partition pass == all-to-all
+    comm.barrier()                                                                       # every peer's stores have landed
+    kept, owned = ops.p2p_resolve(all_counts, k=k, complements=complements, min_frequency=min_frequency)
+    ops.reduce_flags(comm)
+    tot = comm.sum_scalars([kept, int(counts.sum())])                                    # also fences the next pass's stores
+    res = ops.finish(int(tot[0]), k=k, complements=complements) if rank == 0 else None
+    mine = int(all_counts[rank][[g for g in range(N_DIGITS) if owner_of_digit(g, world) == rank]].sum())
+    return ShardedResult(res, int(tot[0]), int(tot[1]), int(counts.sum()) - mine, int(owned))
+
+
 class TorchComm:
     """torch.distributed plumbing (NCCL on the GPU box, gloo in the CPU tests)."""
 
@@ -86,6 +103,26 @@ class TorchComm:
         else:
             r.copy_(s)
         return r.cpu().numpy()
+
+    def all_gather_counts(self, counts):
+        import torch
+        c = torch.as_tensor(np.asarray(counts, dtype=np.int64), device=self.device)
+        out = torch.empty((self.world, c.numel()), dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(out, c)
+        else:
+            out[0].copy_(c)
+        return out.cpu().numpy()
+
+    def all_gather_bytes(self, b: np.ndarray) -> np.ndarray:
+        import torch
+        t = torch.as_tensor(np.asarray(b, dtype=np.uint8), device=self.device)
+        out = torch.empty((self.world, t.numel()), dtype=torch.uint8, device=self.device)
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(out, t)
+        else:
+            out[0].copy_(t)
+        return out.cpu().numpy()
 
     def all_to_all(self, out, inp, recv_counts, send_counts, width: int = 1):
         """Variable-size all-to-all of rows of `width` elements."""
@@ -157,6 +194,25 @@ class GpuOps:
 
     def reduce_flags(self, comm):
         comm.reduce_sum(self.flags, 0)
+
+    # ---- fused partition + exchange (peer memory) --------------------------------------------------------------
+    def setup_p2p(self, comm, k: int, slack: float = 1.25):
+        """Allocate this rank's receive buffers, exchange the CUDA IPC handles, map every peer's buffers."""
+        cap = int(self.n_bytes / comm.world * slack) + (1 << 20)
+        handles = self.ctx.p2p_alloc(k, cap)
+        allh = comm.all_gather_bytes(handles)
+        self.ctx.p2p_open(comm.world, comm.rank, allh.reshape(-1))
+        comm.barrier()
+
+    def p2p_hist(self, b, e, *, k, complements):
+        return self.ctx.p2p_hist(self.seq.data_ptr(), self.n_bytes, b, e, k=k, complements=complements)
+
+    def p2p_scatter(self, b, e, all_counts, *, k, complements):
+        self.ctx.p2p_scatter(self.seq.data_ptr(), self.n_bytes, b, e, all_counts, k=k, complements=complements)
+
+    def p2p_resolve(self, all_counts, *, k, complements, min_frequency):
+        self.flags.zero_()
+        return self.ctx.p2p_resolve(all_counts, self.flags.data_ptr(), k=k, complements=complements, min_frequency=min_frequency)
 
     def finish(self, n_kept, *, k, complements):
         self.torch.cuda.current_stream().synchronize()

@@ -25,7 +25,10 @@ comm = sharded.TorchComm(dev); ops = sharded.GpuOps(ctx, full)
 K = 31
 def T():
     torch.cuda.synchronize(); return time.perf_counter()
-for it in range(6):
+P2P = len(sys.argv) > 1 and sys.argv[1] == "p2p"
+if P2P:
+    ops.setup_p2p(comm, K)
+for it in range(6 if not P2P else 0):
     if world > 1: dist.barrier()
     t = [T()]
     b, e = sharded.plan_slices(full.numel(), world, ops.granule(K))[rank]
@@ -39,5 +42,20 @@ for it in range(6):
     names = ["partition", "counts", "all_to_all", "resolve", "reduce_flags", "sum_scalars", "finish"]
     if it >= 3:
         print(f"rank {rank} it {it}: " + "  ".join(f"{nm} {1000*(t[i+1]-t[i]):.3f}" for i, nm in enumerate(names)) + f"  total {1000*(t[-1]-t[0]):.3f} ms", flush=True)
+for it in range(6 if P2P else 0):
+    if world > 1: dist.barrier()
+    t = [T()]
+    b, e = sharded.plan_slices(full.numel(), world, ops.granule(K))[rank]
+    counts = ops.p2p_hist(b, e, k=K, complements=True); t.append(T())
+    allc = comm.all_gather_counts(counts); t.append(T())
+    ops.p2p_scatter(b, e, allc, k=K, complements=True); t.append(T())
+    comm.barrier(); t.append(T())
+    kept, owned = ops.p2p_resolve(allc, k=K, complements=True, min_frequency=1); t.append(T())
+    ops.reduce_flags(comm); t.append(T())
+    tot = comm.sum_scalars([kept, int(counts.sum())]); t.append(T())
+    res = ops.finish(int(tot[0]), k=K, complements=True) if rank == 0 else None; t.append(T())
+    names = ["hist", "gather_counts", "scatter_p2p", "barrier", "resolve", "reduce_flags", "sum_scalars", "finish"]
+    if it >= 3:
+        print(f"rank {rank} it {it}: " + "  ".join(f"{nm} {1000*(t[i+1]-t[i]):.3f}" for i, nm in enumerate(names)) + f"  total {1000*(t[-1]-t[0]):.3f} ms" + (f" kmers {int(tot[0])} len {res.length}" if res else ""), flush=True)
 if world > 1:
     dist.destroy_process_group()

@@ -200,3 +200,26 @@ def test_sharded_world1_matches_kc_compute(ctx, k, complements, z):
     r = sharded.sharded_compute(ops, comm, d.numel(), k=k, complements=complements, min_frequency=z)
     assert r.n_kept == want.n_kmers and r.result.length == want.length
     assert ctx.copy_to_host(r.result.ms_ptr, r.result.length) == want.ms
+
+
+@pytest.mark.gpu
+def test_sharded_p2p_world1_matches_kc_compute():
+    """The fused partition + exchange path with a single rank (its own buffers stand in for the peers')."""
+    import kmercamel_b200 as kb
+    c = kb.Context(0)      # peer buffers are per context: use a private one
+    try:
+        recs = synth.random_genome_records(6, 40_000, 11)
+        recs.append(recs[2][100:3000].copy())
+        seq, _, _ = synth.frame_records(recs)
+        d = torch.from_numpy(seq).cuda()
+        torch.cuda.synchronize()
+        ops = sharded.GpuOps(c, d)
+        comm = sharded.TorchComm(d.device)
+        ops.setup_p2p(comm, 31)
+        for z in (1, 2):
+            want = c.compute(seq, k=31, min_frequency=z)
+            r = sharded.sharded_compute_p2p(ops, comm, d.numel(), k=31, min_frequency=z)
+            assert r.n_kept == want.n_kmers and r.result.length == want.length
+            assert c.copy_to_host(r.result.ms_ptr, r.result.length) == want.ms
+    finally:
+        c.close()
