@@ -303,6 +303,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # stdout carries exactly one JSON line (NCCL prints its version at VERSION/INFO)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     records, (seq, off, ln) = make_workload(rank)
