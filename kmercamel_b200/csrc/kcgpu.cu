@@ -111,17 +111,36 @@ void ensure_arena(kc_ctx *ctx, size_t need) {
     ctx->arena.reset();
 }
 
-// Generous upper estimate of the arena bytes one kc_compute needs (see DESIGN.md "memory").
-size_t estimate_arena(u64 n_bytes, u64 n_recs, int limbs, bool complements, bool simplitigs) {
+// Arena bytes one kc_compute needs (see DESIGN.md "Data layout in HBM").  Stage 1 is an exact upper bound; the overlap
+// stage depends on the number of nodes, which for a FASTA input (first-occurrence runs) is only known after stage 1:
+// `pessimistic = false` assumes one run per 64 sequence bytes (reads with 1 % errors give one per ~650), and a call that
+// runs out of arena is repeated once with the worst case (one run per 2 bytes), see run_with_arena.
+size_t estimate_arena(u64 n_bytes, u64 n_recs, int limbs, bool complements, bool simplitigs, bool pessimistic = false) {
     const double wb = 8.0 * limbs;
     const double c = complements ? 2.0 : 1.0;
-    double stage1 = n_bytes * (1.0 + 2.0 * wb + 4.0);
-    double nodes = simplitigs ? (double) n_recs : (double) n_bytes;
+    double stage1 = n_bytes * (1.0 + 2.0 * (wb + 4.0) + 1.0 + 1.0 + 0.2);  // sequence, keys + positions x2, counts, control, flags
+    double nodes = simplitigs ? (double) n_recs : (pessimistic ? n_bytes / 2.0 : n_bytes / 64.0 + 1e6);
     double N = c * nodes;
     double engine = N * (60.0 + 2.0 * 2.0 * (wb + 8.0) + 12.0 + 40.0);
     double emit = N * 32.0 + 3.0 * n_bytes;
-    double total = (stage1 + engine + emit) * 1.15 + (256u << 20);
+    double total = (stage1 + engine + emit) * 1.1 + (256u << 20);
     return (size_t) total;
+}
+
+// Runs body() with an arena of `need` bytes; if the arena is exhausted (more nodes than the estimate assumed) the call is
+// repeated once with `need_max`.
+template <class F> void run_with_arena(kc_ctx *ctx, size_t need, size_t need_max, F body) {
+    ensure_arena(ctx, need);
+    try {
+        ctx->arena.reset();
+        body();
+    } catch (const KcError &e) {
+        if (e.code != KC_ERR_OOM || need_max <= ctx->arena.cap || ctx->arena_limited) throw;
+        KC_CUDA(cudaStreamSynchronize(ctx->stream));
+        ensure_arena(ctx, need_max);
+        ctx->arena.reset();
+        body();
+    }
 }
 
 struct DevInput {
@@ -397,14 +416,14 @@ int kc_compute_device(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_ou
     if ((reinterpret_cast<uintptr_t>(in->seq) & 15) != 0) KC_THROW(KC_ERR_ARG, "device sequence pointer must be 16-byte aligned");
     KC_CUDA(cudaSetDevice(ctx->device));
     const int limbs = kc_limbs_for_k(p->k);
-    ensure_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, p->assume_simplitigs != 0));
-    ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
     DevInput di{in->seq, in->n_bytes, in->rec_off, in->rec_len, in->n_recs};
     DevResult res;
     KC_TRACE_POINT("compute_device: start");
-    dispatch_pipeline(ctx, ex, di, *p, res);
+    run_with_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, p->assume_simplitigs != 0),
+                   estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, p->assume_simplitigs != 0, true),
+                   [&] { dispatch_pipeline(ctx, ex, di, *p, res); });
     KC_TRACE_POINT("compute_device: launched");
     KC_CUDA(cudaStreamSynchronize(ctx->stream));
     KC_TRACE_POINT("compute_device: synced");
@@ -429,23 +448,24 @@ int kc_compute(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *o
     KC_CUDA(cudaSetDevice(ctx->device));
     const int limbs = kc_limbs_for_k(p->k);
     const bool simplitigs = p->assume_simplitigs != 0;
-    ensure_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, simplitigs));
-    ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
-    // host -> device
-    u8 *d_seq = ex.alloc<u8>(in->n_bytes + 64);
-    KC_CUDA(cudaMemcpyAsync(d_seq, in->seq, in->n_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    u64 *d_off = nullptr, *d_len = nullptr;
-    if (simplitigs) {
-        d_off = ex.alloc<u64>(in->n_recs);
-        d_len = ex.alloc<u64>(in->n_recs);
-        KC_CUDA(cudaMemcpyAsync(d_off, in->rec_off, in->n_recs * 8, cudaMemcpyHostToDevice, ctx->stream));
-        KC_CUDA(cudaMemcpyAsync(d_len, in->rec_len, in->n_recs * 8, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    DevInput di{d_seq, in->n_bytes, d_off, d_len, in->n_recs};
     DevResult res;
-    dispatch_pipeline(ctx, ex, di, *p, res);
+    run_with_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, simplitigs),
+                   estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, simplitigs, true), [&] {
+        // host -> device
+        u8 *d_seq = ex.alloc<u8>(in->n_bytes + 64);
+        KC_CUDA(cudaMemcpyAsync(d_seq, in->seq, in->n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        u64 *d_off = nullptr, *d_len = nullptr;
+        if (simplitigs) {
+            d_off = ex.alloc<u64>(in->n_recs);
+            d_len = ex.alloc<u64>(in->n_recs);
+            KC_CUDA(cudaMemcpyAsync(d_off, in->rec_off, in->n_recs * 8, cudaMemcpyHostToDevice, ctx->stream));
+            KC_CUDA(cudaMemcpyAsync(d_len, in->rec_len, in->n_recs * 8, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        DevInput di{d_seq, in->n_bytes, d_off, d_len, in->n_recs};
+        dispatch_pipeline(ctx, ex, di, *p, res);
+    });
     // device -> pinned host
     const size_t need = (size_t) res.length * (res.maxone ? 2 : 1) + 64;
     if (ctx->pin_out_cap < need) {
@@ -597,15 +617,18 @@ int kc_compute_from_flags(kc_ctx *ctx, const kc_params *p, const kc_input *in, c
     if (in->n_bytes >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 sequence bytes on one GPU");
     KC_CUDA(cudaSetDevice(ctx->device));
     const int limbs = kc_limbs_for_k(p->k);
-    ensure_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, false));
-    ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
     DevInput di{in->seq, in->n_bytes, in->rec_off, in->rec_len, in->n_recs};
     DevResult res;
-    if (p->k < 32) run_pipeline<1>(ctx, ex, di, *p, res, flags_dev, n_kept);
-    else if (p->k < 64) run_pipeline<2>(ctx, ex, di, *p, res, flags_dev, n_kept);
-    else run_pipeline<4>(ctx, ex, di, *p, res, flags_dev, n_kept);
+    // no stage 1 here: only the node-dependent part (+ the emission scratch) is needed
+    const double c = p->complements ? 2.0 : 1.0;
+    auto need = [&](double nodes) { return (size_t) ((c * nodes * (240.0 + 32.0 * limbs) + 3.0 * in->n_bytes) * 1.1) + (256u << 20); };
+    run_with_arena(ctx, need(in->n_bytes / 64.0 + 1e6), need(in->n_bytes / 2.0), [&] {
+        if (p->k < 32) run_pipeline<1>(ctx, ex, di, *p, res, flags_dev, n_kept);
+        else if (p->k < 64) run_pipeline<2>(ctx, ex, di, *p, res, flags_dev, n_kept);
+        else run_pipeline<4>(ctx, ex, di, *p, res, flags_dev, n_kept);
+    });
     KC_CUDA(cudaStreamSynchronize(ctx->stream));
     out->ms = const_cast<u8 *>(res.ms);
     out->ms_maxone = nullptr;
