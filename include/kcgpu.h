@@ -154,8 +154,13 @@ int kc_p2p_resolve(kc_ctx *ctx, const kc_params *p, const uint64_t *all_counts, 
 /* CUDA kernels launched through this context since kc_init (every entry point adds its own). */
 uint64_t kc_total_launches(const kc_ctx *ctx);
 
-/* Tuning / test knobs.  "small_engine" (default 1): run the tail of the overlap levels in the single-CTA kernel. */
+/* Tuning / test knobs.  "small_engine" (default 1): run the tail of the overlap levels in the single-CTA kernel.
+ * "fast_set" (default 1): try the histogram-free k-mer set construction first (from-FASTA compute without -M);
+ * "fast_leaf_target", "fast_sigmas", "fast_min_items": its plan parameters, exposed so that tests reach the
+ * multi-level plan and the overflow fallback with small inputs.  Results never depend on these options. */
 int kc_set_option(kc_ctx *ctx, const char *name, int value);
+/* Counters since kc_init: "fast_runs", "fast_fallbacks", "total_launches". */
+int kc_get_stat(const kc_ctx *ctx, const char *name, uint64_t *value);
 
 int kc_limbs_for_k(int k);
 void kc_free(void *p);

@@ -89,6 +89,8 @@ def load_library():
     L.kc_total_launches.argtypes = [C.c_void_p]
     L.kc_total_launches.restype = C.c_uint64
     L.kc_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    L.kc_get_stat.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint64)]
+    L.kc_get_stat.restype = C.c_int
     L.kc_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.kc_profile_count.restype = C.c_int
     L.kc_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), u64p, u64p]
@@ -106,7 +108,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ["kc_init", "kc_destroy", "kc_compute", "kc_compute_device", "kc_copy_to_host", "kc_count_kmers", "kc_overlap_path",
                     "kc_p2p_alloc", "kc_p2p_open", "kc_p2p_hist", "kc_p2p_scatter", "kc_p2p_resolve", "kc_total_launches", "kc_shard_granule", "kc_shard_partition", "kc_shard_resolve", "kc_compute_from_flags",
-                    "kc_frame_fasta", "kc_set_option", "kc_profile_enable", "kc_profile_count", "kc_profile_get", "kc_profile_reset",
+                    "kc_frame_fasta", "kc_set_option", "kc_get_stat", "kc_profile_enable", "kc_profile_count", "kc_profile_get", "kc_profile_reset",
                     "kc_limbs_for_k", "kc_free", "kc_strerror", "kc_last_error"]
 
 
@@ -307,6 +309,11 @@ class Context:
 
     def set_option(self, name: str, value: int):
         self._check(self._lib.kc_set_option(self._h, name.encode(), int(value)))
+
+    def stat(self, name: str) -> int:
+        v = C.c_uint64()
+        self._check(self._lib.kc_get_stat(self._h, name.encode(), C.byref(v)))
+        return int(v.value)
 
     # ---- per-kernel-class timers ---------------------------------------------------------------------------
     def profile_enable(self, on: bool = True):

@@ -324,8 +324,8 @@ template <class Exec, int L> struct Engine {
             a.ban_cap = BAN_CAP;
             a.d_start = d;
             a.strict = strict;
-            a.out = ex.template alloc<u32>(8);
-            ex.fill_bytes(a.out, 0, 32);
+            a.out = ex.template alloc<u32>(8 + 128);
+            ex.fill_bytes(a.out, 0, (8 + 128) * 4);
             static bool attr_done = false;
             if (!attr_done) {
                 KC_CUDA(cudaFuncSetAttribute(kc_small_engine_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -341,9 +341,15 @@ template <class Exec, int L> struct Engine {
             }
             ++ex.launches;
             KC_CUDA(cudaGetLastError());
-            u32 h[8];
-            KC_CUDA(cudaMemcpyAsync(h, a.out, 32, cudaMemcpyDeviceToHost, ex.stream));
+            u32 h[8 + 128];
+            KC_CUDA(cudaMemcpyAsync(h, a.out, sizeof(h), cudaMemcpyDeviceToHost, ex.stream));
             KC_CUDA(cudaStreamSynchronize(ex.stream));
+            if (std::getenv("KC_TRACE")) {
+                std::fprintf(stderr, "[kc_trace] small engine: n_s=%llu n_p=%llu levels=%u groups=%u edges=%u ban_rounds=%u bans=%u; clocks per level (* = run):",
+                             (unsigned long long) n_s, (unsigned long long) n_p, h[1], h[2], h[3], h[4], h[5]);
+                for (int dd = d; dd >= 0; --dd) std::fprintf(stderr, " d%d=%u%s", dd, h[8 + dd] & 0x7FFFFFFFu, (h[8 + dd] >> 31) ? "*" : "");
+                std::fprintf(stderr, "\n");
+            }
             if (h[0]) KC_THROW(KC_ERR_INTERNAL, "ban list overflow");
             stats.levels_run += h[1];
             stats.groups += h[2];

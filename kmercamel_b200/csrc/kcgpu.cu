@@ -6,6 +6,7 @@
 #include "engine.cuh"
 #include "exec.cuh"
 #include "kmerset.cuh"
+#include "kmerset_fast.cuh"
 #include "kword.cuh"
 #include "runs.cuh"
 #include "sort.cuh"
@@ -39,6 +40,8 @@ struct kc_ctx {
     size_t pin_out_cap = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool small_engine = true;
+    KsfTuning fast;          // histogram-free set construction (kmerset_fast.cuh); KC_FAST_* environment knobs for tests
+    u64 fast_runs = 0, fast_fallbacks = 0;
     u64 total_launches = 0;  // kernels launched through this context since kc_init
     // fused partition + exchange over peer memory (kc_p2p_*)
     struct P2P {
@@ -115,10 +118,18 @@ void ensure_arena(kc_ctx *ctx, size_t need) {
 // stage depends on the number of nodes, which for a FASTA input (first-occurrence runs) is only known after stage 1:
 // `pessimistic = false` assumes one run per 64 sequence bytes (reads with 1 % errors give one per ~650), and a call that
 // runs out of arena is repeated once with the worst case (one run per 2 bytes), see run_with_arena.
-size_t estimate_arena(u64 n_bytes, u64 n_recs, int limbs, bool complements, bool simplitigs, bool pessimistic = false) {
+size_t estimate_arena(u64 n_bytes, u64 n_recs, int limbs, bool complements, bool simplitigs, bool pessimistic = false,
+                      const KsfTuning *fast = nullptr) {
     const double wb = 8.0 * limbs;
     const double c = complements ? 2.0 : 1.0;
     double stage1 = n_bytes * (1.0 + 2.0 * (wb + 4.0) + 1.0 + 1.0 + 0.2);  // sequence, keys + positions x2, counts, control, flags
+    if (fast) {  // fixed-slot buckets of the histogram-free construction (tried first, released before the exact one runs)
+        const KsfPlan pl = kc_ksf_plan(n_bytes, *fast);
+        if (pl.ok) {
+            const double f = n_bytes * 1.2 + (double) (pl.slots[0] + pl.slots[1]) * (wb + 4.0) + (double) pl.n_leaf * 28.0 + 65536.0;
+            if (f > stage1) stage1 = f;
+        }
+    }
     double nodes = simplitigs ? (double) n_recs : (pessimistic ? n_bytes / 2.0 : n_bytes / 64.0 + 1e6);
     double N = c * nodes;
     double engine = N * (60.0 + 2.0 * 2.0 * (wb + 8.0) + 12.0 + 40.0);
@@ -189,6 +200,34 @@ u64 run_stage1_runs(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_para
     ex.fill_bytes(flags, 0, fwords * 4);
     u64 *cells = ex.arena->alloc_top<u64>(2);  // {kept distinct k-mers, runs}
     ex.fill_bytes(cells, 0, 16);
+    // FLAGS-only: try the histogram-free construction first (no host synchronisation until the runs are counted)
+    if (!p.want_maxone) {
+        KsfPlan plan;
+        u64 *cells4 = ex.arena->alloc_top<u64>(4);  // {kept, runs, M, overflow status}
+        ex.fill_bytes(cells4, 0, 32);
+        if (kc_kmerset_build_fast<L>(ex, in.seq, nb, p.k, p.complements != 0, p.min_frequency, flags, cells4, ctx->fast, &plan)) {
+            KC_TRACE_POINT("stage1: fast set launched");
+            u64 hc[4];
+            bool aborted = false;
+            *runs = kc_runs_from_flags(ex, flags, nb, p.k, cells4, hc, 4, &aborted);
+            if (!aborted) {
+                ++ctx->fast_runs;
+                // the timers charged the partition passes with M = n_bytes; now that M is known, correct the byte counts
+                if (ex.prof && ex.prof->enabled && nb > hc[2]) {
+                    const u64 d = (nb - hc[2]) * (sizeof(KWord<L>) + 4);
+                    ex.prof->bytes[KP_KS_SCATTER0] -= d;
+                    ex.prof->bytes[KP_SORT_SCATTER] -= 2 * d * (u64) (plan.n_levels - 1);
+                    ex.prof->bytes[KP_KS_RESOLVE] -= d;
+                }
+                *n_occ = hc[2];
+                *set_out = nullptr;
+                KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
+                return hc[2] ? hc[0] : 0;
+            }
+            ++ctx->fast_fallbacks;  // a slot overflowed: discard the flags, fall through to the exact construction
+            ex.fill_bytes(flags, 0, fwords * 4);
+        }
+    }
     // with -M the sorted k-mer set doubles as kMersDict of src/global.h:165-167; it stays at the arena bottom
     KmerSet<L> set = kc_kmerset_build<L>(ex, in.seq, nb, p.k, p.complements != 0, p.min_frequency, flags, p.want_maxone != 0, cells);
     KC_TRACE_POINT("stage1: set built");
@@ -376,6 +415,8 @@ int kc_init(int device, void *stream, kc_ctx **out) {
             ctx->own_stream = true;
         }
         for (int i = 0; i < 6; ++i) KC_CUDA(cudaEventCreate(&ctx->ev[i]));
+        if (const char *e = std::getenv("KC_FAST_SET")) ctx->fast.enabled = std::atoi(e) != 0;
+        if (const char *e = std::getenv("KC_FAST_RESOLVE")) ctx->fast.resolve = std::atoi(e) != 0;
     } catch (const KcError &e) {
         int code = e.code;
         kc_destroy(ctx);
@@ -421,8 +462,8 @@ int kc_compute_device(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_ou
     DevInput di{in->seq, in->n_bytes, in->rec_off, in->rec_len, in->n_recs};
     DevResult res;
     KC_TRACE_POINT("compute_device: start");
-    run_with_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, p->assume_simplitigs != 0),
-                   estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, p->assume_simplitigs != 0, true),
+    run_with_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, p->assume_simplitigs != 0, false, &ctx->fast),
+                   estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, p->assume_simplitigs != 0, true, &ctx->fast),
                    [&] { dispatch_pipeline(ctx, ex, di, *p, res); });
     KC_TRACE_POINT("compute_device: launched");
     KC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -451,8 +492,8 @@ int kc_compute(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *o
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
     DevResult res;
-    run_with_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, simplitigs),
-                   estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, simplitigs, true), [&] {
+    run_with_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, simplitigs, false, &ctx->fast),
+                   estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, simplitigs, true, &ctx->fast), [&] {
         // host -> device
         u8 *d_seq = ex.alloc<u8>(in->n_bytes + 64);
         KC_CUDA(cudaMemcpyAsync(d_seq, in->seq, in->n_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -833,10 +874,41 @@ int kc_p2p_resolve(kc_ctx *ctx, const kc_params *p, const uint64_t *all_counts, 
 
 uint64_t kc_total_launches(const kc_ctx *ctx) { return ctx ? ctx->total_launches : 0; }
 
+int kc_get_stat(const kc_ctx *ctx, const char *name, uint64_t *value) {
+    if (!ctx || !name || !value) return KC_ERR_ARG;
+    if (std::strcmp(name, "fast_runs") == 0) *value = ctx->fast_runs;
+    else if (std::strcmp(name, "fast_fallbacks") == 0) *value = ctx->fast_fallbacks;
+    else if (std::strcmp(name, "total_launches") == 0) *value = ctx->total_launches;
+    else return KC_ERR_ARG;
+    return KC_OK;
+}
+
 int kc_set_option(kc_ctx *ctx, const char *name, int value) {
     if (!ctx || !name) return KC_ERR_ARG;
     if (std::strcmp(name, "small_engine") == 0) {
         ctx->small_engine = value != 0;
+        return KC_OK;
+    }
+    // histogram-free set construction (kmerset_fast.cuh); the last three exist so that tests can reach the multi-level
+    // plan and the overflow fallback with small inputs
+    if (std::strcmp(name, "fast_set") == 0) {
+        ctx->fast.enabled = value != 0;
+        return KC_OK;
+    }
+    if (std::strcmp(name, "fast_leaf_target") == 0 && value >= 1 && value <= 1024) {
+        ctx->fast.leaf_target = (u32) value;
+        return KC_OK;
+    }
+    if (std::strcmp(name, "fast_sigmas") == 0 && value >= 0) {
+        ctx->fast.sigmas = (double) value;
+        return KC_OK;
+    }
+    if (std::strcmp(name, "fast_resolve") == 0 && (value == 0 || value == 1)) {
+        ctx->fast.resolve = value;
+        return KC_OK;
+    }
+    if (std::strcmp(name, "fast_min_items") == 0 && value >= 0) {
+        ctx->fast.min_items = (u64) value;
         return KC_OK;
     }
     return KC_ERR_ARG;

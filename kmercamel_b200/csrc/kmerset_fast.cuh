@@ -1,0 +1,562 @@
+// Histogram-free k-mer set construction for the FLAGS-only regime (from-FASTA `compute` without -M): the same
+// decode -> canonical k-mer -> MSD partition -> shared-memory hash resolve as kmerset.cuh (reference src/parser.h:22-141
+// AddKMers / AddKMersWithFrequencies + khash), but planned from the input size alone so that NO counting pass and NO
+// host synchronisation sits between the kernels.
+//
+// Why this is possible: FLAGS-only buckets by a bijective multiplicative hash of the k-mer word (kmer_scramble), so for
+// any input made of mostly distinct k-mers the bucket sizes are Poisson-tight around M / ways.  Every bucket of every
+// level therefore gets a FIXED slot of  mean + 8 sigma  items (the leaves: 1024, the capacity of the hash resolve) and
+// a tile reserves its place inside a slot with one atomicAdd per digit.  What disappears against kmerset.cuh:
+//   * kc_ks_hist0_kernel   — the sequence is decoded and the canonical k-mers are computed ONCE (they wait in shared
+//                            memory while the tile's digit counts are scanned), not twice;
+//   * kc_kv_hist_kernel    — no second read of the level-0 output (8L bytes per k-mer);
+//   * two host read-backs (bucket lists / tile counts) and six scan / bookkeeping launches.
+// Algorithmic HBM bytes per k-mer (L = 1): 1 + 12 (level 0) + 12 + 12 (level 1) + 12 (resolve) = 49 instead of 58.
+//
+// Inputs that break the assumption (30x read sets: every k-mer ~30 times, so sigma grows by sqrt(30); low-complexity
+// sequence) overflow a slot.  Overflow is detected on the device (items beyond the slot are dropped, a status word is
+// set) and reported with the same read-back that returns the counts; the caller then discards the flags and runs the
+// exact histogram-based construction of kmerset.cuh.  Results never depend on which of the two ran.
+#pragma once
+#include "kmerset.cuh"
+#include <cmath>
+
+static const u32 KSF_LEAF_CAP = 1024;  // capacity of kc_ks_resolve_hash_kernel<L, 1024, *>
+static const int KSF_MAX_LEVELS = 4;
+
+struct KsfTuning {
+    bool enabled = true;
+    u32 leaf_target = 768;   // mean leaf size aimed at (the leaf slot holds KSF_LEAF_CAP)
+    double sigmas = 8.0;     // slot = mean + sigmas * sqrt(mean) (+ 2 %) items; 0 forces overflows (tests)
+    u64 min_items = 1u << 16;  // smaller inputs take the exact path (nothing to gain)
+    int resolve = 1;         // 1 = kc_ksf_resolve_kernel (cp.async, two barriers), 0 = kc_ks_resolve_hash_kernel over a bucket list
+};
+
+struct KsfPlan {
+    bool ok = false;
+    int n_levels = 0;
+    int bits[KSF_MAX_LEVELS];   // digit width of level i
+    int cum[KSF_MAX_LEVELS];    // key bits consumed after level i
+    u64 cap[KSF_MAX_LEVELS];    // slot size (items) of one bucket produced by level i
+    u64 slots[2] = {0, 0};      // items the ping (even levels) / pong (odd levels) buffers must hold
+    u64 n_leaf = 0;
+};
+
+inline KsfPlan kc_ksf_plan(u64 m_upper, const KsfTuning &t) {
+    KsfPlan p;
+    if (!t.enabled || m_upper < t.min_items) return p;
+    int total_bits = 1;
+    while (total_bits < 40 && (m_upper >> total_bits) > t.leaf_target) ++total_bits;
+    const int levels = (total_bits + 7) / 8;
+    if (levels > KSF_MAX_LEVELS) return p;
+    p.n_levels = levels;
+    int cum = 0;
+    for (int i = 0; i < levels; ++i) {
+        p.bits[i] = total_bits / levels + (i < total_bits % levels ? 1 : 0);
+        cum += p.bits[i];
+        p.cum[i] = cum;
+        const double mean = (double) m_upper / (double) (1ULL << cum);
+        u64 cap = (u64) std::ceil(mean + t.sigmas * std::sqrt(mean) + (t.sigmas > 0 ? 0.02 * mean + 64.0 : 0.0));
+        cap = (cap + 31) / 32 * 32;
+        if (i == levels - 1) cap = KSF_LEAF_CAP;
+        if (cap >= 0xFFFFFFFFULL) return p;
+        p.cap[i] = cap;
+        const u64 need = (1ULL << cum) * cap;
+        if (need > p.slots[i & 1]) p.slots[i & 1] = need;
+    }
+    p.n_leaf = 1ULL << cum;
+    p.ok = true;
+    return p;
+}
+
+#ifdef __CUDACC__
+
+// status[0] = 1: some slot overflowed (the flags are incomplete and must be discarded)
+// ---- level 0: sequence -> fixed-slot buckets, one compute pass ----------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int complements,
+                                                                                int shift, int bits, u32 *bucket_cnt, u32 cap0,
+                                                                                KWord<L> *__restrict__ keys, u32 *__restrict__ pos, u32 *status) {
+    constexpr int T = KsCfg<L>::EX_THREADS;
+    constexpr int LOG_T = T == 256 ? 8 : (T == 128 ? 7 : 6);
+    constexpr int R = 256 / T;
+    constexpr int TILE = KsCfg<L>::EX_TILE;
+    extern __shared__ __align__(16) unsigned char kc_smem_raw[];
+    KWord<L> *stash = reinterpret_cast<KWord<L> *>(kc_smem_raw);  // slot j * T + t = window j of thread t (conflict-free)
+    u16 *rk = reinterpret_cast<u16 *>(stash + TILE);               // rank of the slot's k-mer inside its digit, 0xFFFF = no k-mer
+    u16 *perm = rk + TILE;                                         // digit-ordered position -> slot
+    __shared__ u64 pk[KC_EX_HALO + T];
+    __shared__ u32 vm[KC_EX_HALO + T];
+    __shared__ u32 cnt[256];
+    __shared__ u32 loff[256];
+    __shared__ u32 gbase[256];
+    __shared__ u32 sw[T / 32];
+    const i64 block_pos0 = (i64) blockIdx.x * TILE;
+    kc_tile_load<T>(seq, n_bytes, block_pos0, pk, vm);
+    for (int i = threadIdx.x; i < 256; i += T) cnt[i] = 0;
+#pragma unroll
+    for (int j = 0; j < KC_EX_STRIP; ++j) rk[j * T + threadIdx.x] = 0xFFFFu;
+    __syncthreads();
+    const int widx = KC_EX_HALO + threadIdx.x;
+    const u32 em = kc_strip_emit_mask(vm, widx, k);
+    kc_strip_windows<L>(pk, widx, em, k, complements, [&](int j, const KWord<L> &c0) {
+        const KWord<L> c = kmer_scramble(c0);
+        const u32 slot = (u32) j * T + threadIdx.x;
+        stash[slot] = c;
+        rk[slot] = (u16) atomicAdd(&cnt[c.digit(shift, bits)], 1u);
+    });
+    __syncthreads();
+    u32 total;
+    {
+        u32 v[R], c = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            v[r] = cnt[threadIdx.x * R + r];
+            c += v[r];
+        }
+        u32 p = kc_block_exclusive_scan<T>(c, &total, sw);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = threadIdx.x * R + r;
+            loff[i] = p;
+            if (v[r]) gbase[i] = atomicAdd(&bucket_cnt[i], v[r]);  // reserve the tile's place inside the slot of bucket i
+            p += v[r];
+        }
+    }
+    __syncthreads();
+    if (total == 0) return;
+    for (u32 slot = threadIdx.x; slot < (u32) TILE; slot += T) {
+        const u32 r = rk[slot];
+        if (r != 0xFFFFu) perm[loff[stash[slot].digit(shift, bits)] + r] = (u16) slot;
+    }
+    __syncthreads();
+    bool over = false;
+    for (u32 q = threadIdx.x; q < total; q += T) {
+        const u32 slot = perm[q];
+        const KWord<L> v = stash[slot];
+        const u32 dg = v.digit(shift, bits);
+        const u32 idx = gbase[dg] + (q - loff[dg]);
+        if (idx < cap0) {
+            const u64 at = (u64) dg * cap0 + idx;
+            keys[at] = v;
+            pos[at] = (u32) ((u64) block_pos0 + (slot & (T - 1)) * KC_EX_STRIP + (slot >> LOG_T));
+        } else {
+            over = true;
+        }
+    }
+    if (over) status[0] = 1;
+}
+
+// Between two levels: clamp the fill counts of the nP parent slots, count their tiles (tile_count[nP] = 0 for the scan
+// that follows) and, after level 0, add up M.
+__global__ void __launch_bounds__(256) kc_ksf_prep_kernel(const u32 *cnt, u32 nP, u32 capP, u32 tile, u32 *size_out, u32 *tile_count, u32 *status,
+                                                          kc_ull *m_cell) {
+    const u32 p = blockIdx.x * 256 + threadIdx.x;
+    if (p > nP) return;
+    if (p == nP) {
+        tile_count[p] = 0;
+        return;
+    }
+    u32 c = cnt[p];
+    if (m_cell && c) atomicAdd(m_cell, (kc_ull) (c < capP ? c : capP));
+    if (c > capP) {
+        status[0] = 1;
+        c = capP;
+    }
+    size_out[p] = c;
+    tile_count[p] = (c + tile - 1) / tile;
+}
+
+// ---- levels >= 1: fixed-slot parents -> fixed-slot children (kc_kv_scatter_kernel without the counting pass) ---------------
+template <int L>
+__global__ void __launch_bounds__(256, 3) kc_ksf_scatter_kernel(const KWord<L> *__restrict__ ksrc, const u32 *__restrict__ psrc, KWord<L> *__restrict__ kdst,
+                                                             u32 *__restrict__ pdst, const u32 *__restrict__ P_size, const u32 *__restrict__ tile_prefix,
+                                                             u32 nP, u64 capP, u32 tiles_per_cta, int shift, int bits, u32 *C_cnt, u32 capC, u32 *status) {
+    constexpr int TILE = KsCfg<L>::TILE;
+    constexpr int ITEMS = TILE / 256;
+    extern __shared__ __align__(16) unsigned char kc_smem_raw[];
+    KWord<L> *stage_k = reinterpret_cast<KWord<L> *>(kc_smem_raw);
+    u32 *stage_p = reinterpret_cast<u32 *>(stage_k + TILE);
+    u16 *rk = reinterpret_cast<u16 *>(stage_p + TILE);
+    __shared__ u32 cnt[256];
+    __shared__ u32 loff[256];
+    __shared__ u32 gbase[256];
+    __shared__ u32 sw[8];
+    const u32 n_tiles = tile_prefix[nP];
+    const u32 t0 = blockIdx.x * tiles_per_cta;
+    const u32 t1 = min(n_tiles, t0 + tiles_per_cta);
+    if (t0 >= t1) return;
+    u32 b = kc_upper_bound_u32(tile_prefix, nP + 1, t0) - 1;
+    cnt[threadIdx.x] = 0;
+    bool over = false;
+    __syncthreads();
+    for (u32 t = t0; t < t1; ++t) {
+        while (t >= tile_prefix[b + 1]) ++b;
+        const KWord<L> *src = ksrc + (u64) b * capP;
+        const u32 *ps = psrc + (u64) b * capP;
+        const u32 start = (t - tile_prefix[b]) * TILE;
+        const u32 n_here = min((u32) TILE, P_size[b] - start);
+        KWord<L> item[ITEMS];
+        u32 pay[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const u32 i = threadIdx.x + j * 256;
+            if (i < n_here) item[j] = src[start + i];
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const u32 i = threadIdx.x + j * 256;
+            if (i < n_here) pay[j] = ps[start + i];
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const u32 i = threadIdx.x + j * 256;
+            if (i < n_here) rk[i] = (u16) atomicAdd(&cnt[item[j].digit(shift, bits)], 1u);
+        }
+        __syncthreads();
+        const u32 c = cnt[threadIdx.x];
+        u32 total;
+        const u32 p = kc_block_exclusive_scan<256>(c, &total, sw);
+        loff[threadIdx.x] = p;
+        if (c) gbase[threadIdx.x] = atomicAdd(&C_cnt[((u64) b << bits) + threadIdx.x], c);
+        cnt[threadIdx.x] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const u32 i = threadIdx.x + j * 256;
+            if (i < n_here) {
+                const u32 q = loff[item[j].digit(shift, bits)] + rk[i];
+                stage_k[q] = item[j];
+                stage_p[q] = pay[j];
+            }
+        }
+        __syncthreads();
+        for (u32 q = threadIdx.x; q < n_here; q += 256) {
+            const KWord<L> v = stage_k[q];
+            const u32 dg = v.digit(shift, bits);
+            const u32 idx = gbase[dg] + (q - loff[dg]);
+            if (idx < capC) {
+                const u64 at = (((u64) b << bits) + dg) * capC + idx;
+                kdst[at] = v;
+                pdst[at] = stage_p[q];
+            } else {
+                over = true;
+            }
+        }
+        __syncthreads();
+    }
+    if (over) status[0] = 1;
+}
+
+// Leaf slots -> the bucket list kc_ks_resolve_hash_kernel walks.
+__global__ void __launch_bounds__(256) kc_ksf_leaf_kernel(const u32 *cnt, u64 n_leaf, u32 cap, u8 parity, SortBucket *small, u32 *status) {
+    const u64 c = (u64) blockIdx.x * 256 + threadIdx.x;
+    if (c >= n_leaf) return;
+    u32 s = cnt[c];
+    if (s > cap) {
+        status[0] = 1;
+        s = cap;
+    }
+    SortBucket d;
+    d.off = c * cap;
+    d.size = s;
+    d.rem = 0;
+    d.parity = parity;
+    d.bits = 0;
+    small[c] = d;
+}
+
+// ---- leaf resolve: exact dedup of one fixed slot through shared-memory tables, two barriers per bucket ------------------------
+// Persistent CTAs walk the leaf slots with stride gridDim.x.  The slot of bucket n + 1 streams into the second staging
+// buffer with cp.async while bucket n is resolved, so no thread ever waits on HBM between the barriers.
+//   A  every item writes its index into T1[h1(key)] with a plain store (some writer wins);
+//   -- barrier --
+//   B  the winner of a slot represents its key.  An item that finds an EQUAL key there is a duplicate: it folds its
+//      position into the winner's with atomicMin (and bumps the occurrence count for -z).  An item that finds a
+//      DIFFERENT key (~16 % at load 0.37) inserts itself into T2 with atomicCAS + linear probing, folding into an
+//      equal key if it meets one.  All copies of a key take the same route, so they always meet;
+//   -- barrier --
+//   C  every representative with >= min_count occurrences sets the bit of its smallest position.
+// Against kc_ks_resolve_hash_kernel (up to six write-then-verify rounds, each ending in a barrier + vote): 2 barriers
+// instead of ~5 per bucket, no register staging (64 -> 40 registers), twice the resident CTAs.
+KC_D void kc_cp_async16(void *smem_dst, const void *gmem_src) {
+    const u32 d = (u32) __cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+KC_D void kc_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+KC_D void kc_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+template <int L, bool COUNTED>
+__global__ void __launch_bounds__(256) kc_ksf_resolve_kernel(const KWord<L> *__restrict__ keys, const u32 *__restrict__ pos, const u32 *__restrict__ cnt,
+                                                             u32 n_leaf, u32 *flags, u32 min_count, kc_ull *n_unique, u32 *status) {
+    constexpr u32 CAP = KSF_LEAF_CAP;
+    constexpr u32 T1N = 2 * CAP, T2N = CAP;
+    constexpr int KPC = 16 / (int) sizeof(KWord<L>) > 0 ? 16 / (int) sizeof(KWord<L>) : 1;  // keys per 16-byte chunk (L = 1: 2)
+    constexpr int CPK = (int) sizeof(KWord<L>) / 16 > 0 ? (int) sizeof(KWord<L>) / 16 : 1;  // 16-byte chunks per key (L = 4: 2)
+    extern __shared__ __align__(16) unsigned char kc_smem_raw[];
+    KWord<L> *sk0 = reinterpret_cast<KWord<L> *>(kc_smem_raw);
+    u32 *sp0 = reinterpret_cast<u32 *>(sk0 + 2 * CAP);
+    u32 *T1 = sp0 + 2 * CAP;
+    u32 *T2 = T1 + T1N;
+    u32 *occ = T2 + T2N;  // COUNTED only
+    const u32 stride = gridDim.x;
+    u32 c = blockIdx.x;
+    if (c >= n_leaf) return;
+    auto fetch = [&](u32 bucket, u32 size, int buf) {
+        const char *gk = reinterpret_cast<const char *>(keys + (u64) bucket * CAP);
+        const char *gp = reinterpret_cast<const char *>(pos + (u64) bucket * CAP);
+        char *dk = reinterpret_cast<char *>(sk0 + (u32) buf * CAP);
+        char *dp = reinterpret_cast<char *>(sp0 + (u32) buf * CAP);
+        // a thread copies whole units (L = 1: a pair of keys, otherwise one key), so the keys it hashes in phase A are
+        // the ones it fetched itself
+        const u32 n_units = (size + KPC - 1) / KPC, pchunks = (size * 4 + 15) / 16;
+        for (u32 u = threadIdx.x; u < n_units; u += 256) {
+#pragma unroll
+            for (int cc = 0; cc < CPK; ++cc) kc_cp_async16(dk + 16 * (u * CPK + cc), gk + 16 * (u * CPK + cc));
+        }
+        for (u32 q = threadIdx.x; q < pchunks; q += 256) kc_cp_async16(dp + 16 * q, gp + 16 * q);
+        kc_cp_async_commit();
+    };
+    u32 size = cnt[c];
+    if (size > CAP) {
+        size = CAP;
+        if (threadIdx.x == 0) status[0] = 1;
+    }
+    fetch(c, size, 0);
+    int buf = 0;
+    u32 kept = 0;
+    while (true) {
+        const u32 cn = c + stride;
+        u32 size_n = 0;
+        if (cn < n_leaf) {
+            size_n = cnt[cn];
+            if (size_n > CAP) {
+                size_n = CAP;
+                if (threadIdx.x == 0) status[0] = 1;
+            }
+        }
+        KWord<L> *sk = sk0 + (u32) buf * CAP;
+        u32 *sp = sp0 + (u32) buf * CAP;
+        kc_cp_async_wait_all();  // the thread's own chunks of bucket c have landed
+        // A: own items = the keys of the chunks this thread copied itself (visible without a barrier)
+        const u32 n_chunk_items = (size + KPC - 1) / KPC;  // L = 1: pairs of keys; L >= 2: single keys
+        {
+            const uint4 e = make_uint4(KC_NONE, KC_NONE, KC_NONE, KC_NONE);
+            reinterpret_cast<uint4 *>(T2)[threadIdx.x] = e;  // T2N = 1024 slots = 256 x 16 bytes
+        }
+        for (u32 q = threadIdx.x; q < n_chunk_items; q += 256) {
+#pragma unroll
+            for (int e = 0; e < KPC; ++e) {
+                const u32 i = q * KPC + e;
+                if (i < size) {
+                    u64 h = 0;
+#pragma unroll
+                    for (int w = 0; w < L; ++w) h = (h ^ sk[i].w[w]) * 0xD6E8FEB86659FD93ULL;
+                    T1[h >> 53] = i;
+                    if (COUNTED) occ[i] = 1;
+                }
+            }
+        }
+        __syncthreads();
+        if (cn < n_leaf) fetch(cn, size_n, buf ^ 1);  // every thread is past phase C of the bucket that used that buffer
+        // B
+        u32 rep = 0;  // bit (2 m + e): item e of the thread's m-th chunk represents its key
+        {
+            u32 m = 0;
+            for (u32 q = threadIdx.x; q < n_chunk_items; q += 256, ++m) {
+#pragma unroll
+                for (int e = 0; e < KPC; ++e) {
+                    const u32 i = q * KPC + e;
+                    if (i >= size) continue;
+                    const KWord<L> key = sk[i];
+                    u64 h = 0;
+#pragma unroll
+                    for (int w = 0; w < L; ++w) h = (h ^ key.w[w]) * 0xD6E8FEB86659FD93ULL;
+                    const u32 o = T1[h >> 53];
+                    if (o == i) {
+                        rep |= 1u << (m * KPC + e);
+                    } else if (sk[o] == key) {
+                        atomicMin(&sp[o], sp[i]);
+                        if (COUNTED) atomicAdd(&occ[o], 1u);
+                    } else {
+                        u32 s = (u32) (h >> 43) & (T2N - 1);
+                        while (true) {
+                            const u32 old = atomicCAS(&T2[s], KC_NONE, i);
+                            if (old == KC_NONE) {
+                                rep |= 1u << (m * KPC + e);
+                                break;
+                            }
+                            if (sk[old] == key) {
+                                atomicMin(&sp[old], sp[i]);
+                                if (COUNTED) atomicAdd(&occ[old], 1u);
+                                break;
+                            }
+                            s = (s + 1) & (T2N - 1);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // C
+        {
+            u32 m = 0;
+            for (u32 q = threadIdx.x; q < n_chunk_items; q += 256, ++m) {
+#pragma unroll
+                for (int e = 0; e < KPC; ++e) {
+                    const u32 i = q * KPC + e;
+                    if (((rep >> (m * KPC + e)) & 1u) && (!COUNTED || occ[i] >= min_count)) {
+                        kc_flag_set(flags, sp[i]);
+                        ++kept;
+                    }
+                }
+            }
+        }
+        if (cn >= n_leaf) break;
+        c = cn;
+        size = size_n;
+        buf ^= 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kept += __shfl_down_sync(0xFFFFFFFFu, kept, o);
+    if ((threadIdx.x & 31) == 0 && kept) atomicAdd(n_unique, (kc_ull) kept);
+}
+
+// Launches the whole construction on ex.stream and returns without synchronising.
+//   cells[0] += distinct k-mers with >= min_freq occurrences, cells[2] = M (k-mer windows), low word of cells[3] = overflow status;
+//   flags: zeroed bit array over the n_bytes positions (see kc_kmerset_build).
+// Returns false (nothing launched) when the plan does not apply; the caller then uses kc_kmerset_build.
+template <int L>
+bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, int min_freq, u32 *flags, u64 *cells,
+                           const KsfTuning &tune, KsfPlan *plan_out = nullptr) {
+    typedef KsCfg<L> Cfg;
+    const KsfPlan pl = kc_ksf_plan(n_bytes, tune);
+    if (plan_out) *plan_out = pl;
+    if (!pl.ok) return false;
+    cudaStream_t st = ex.stream;
+    const size_t base_mark = ex.arena->mark();
+    const u64 item_bytes = sizeof(KWord<L>) + 4;
+    KWord<L> *kb[2];
+    u32 *pb[2];
+    for (int i = 0; i < 2; ++i) {
+        kb[i] = ex.alloc<KWord<L>>(pl.slots[i] ? pl.slots[i] : 1);
+        pb[i] = ex.alloc<u32>(pl.slots[i] ? pl.slots[i] : 1);
+    }
+    u64 n_cnt = 0;
+    for (int i = 0; i < pl.n_levels; ++i) n_cnt += 1ULL << pl.cum[i];
+    u32 *cnt_all = ex.alloc<u32>(n_cnt);
+    ex.fill_bytes(cnt_all, 0, n_cnt * 4);
+    u32 *status = reinterpret_cast<u32 *>(cells + 3);
+    kc_ull *m_cell = reinterpret_cast<kc_ull *>(cells + 2);
+
+    const int smem0 = Cfg::EX_TILE * ((int) sizeof(KWord<L>) + 4);
+    const int smem1 = Cfg::TILE * ((int) sizeof(KWord<L>) + 4 + 2);
+    const bool counted = min_freq > 1;
+    constexpr int CA = KSF_LEAF_CAP;
+    const int per_item = (int) sizeof(KWord<L>) + 12 + 4;
+    const int smem_r = CA * (per_item + (counted ? 4 : 0));
+    static bool attr_done = false;
+    static int occ_r[2] = {0, 0}, n_sm = 0;
+    if (!attr_done) {
+        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter0_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem0));
+        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+        KC_CUDA(cudaFuncSetAttribute(kc_ks_resolve_hash_kernel<L, CA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CA * per_item));
+        KC_CUDA(cudaFuncSetAttribute(kc_ks_resolve_hash_kernel<L, CA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CA * (per_item + 4)));
+        int dev = 0;
+        KC_CUDA(cudaGetDevice(&dev));
+        KC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r[0], kc_ks_resolve_hash_kernel<L, CA, false>, 256, CA * per_item));
+        KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r[1], kc_ks_resolve_hash_kernel<L, CA, true>, 256, CA * (per_item + 4)));
+        attr_done = true;
+    }
+
+    // ---- level 0 ----
+    u32 *cnt_cur = cnt_all;
+    {
+        const u32 blocks = (u32) kc_div_up(n_bytes, (u64) Cfg::EX_TILE);
+        CudaExec::Scope sc(ex, KP_KS_SCATTER0, n_bytes + n_bytes * item_bytes);
+        kc_ksf_scatter0_kernel<L><<<blocks, Cfg::EX_THREADS, smem0, st>>>(seq, n_bytes, k, complements ? 1 : 0, 64 * L - pl.cum[0], pl.bits[0], cnt_cur,
+                                                                         (u32) pl.cap[0], kb[0], pb[0], status);
+        ++ex.launches;
+        KC_CUDA(cudaGetLastError());
+    }
+    // ---- levels >= 1 ----
+    const u32 max_ctas = 148 * 8;
+    for (int lv = 1; lv < pl.n_levels; ++lv) {
+        const u32 nP = (u32) (1ULL << pl.cum[lv - 1]);
+        const size_t mark = ex.arena->mark();
+        u32 *P_size = ex.alloc<u32>(nP);
+        u32 *tile_prefix = ex.alloc<u32>((u64) nP + 1);
+        kc_ksf_prep_kernel<<<(unsigned) kc_div_up((u64) nP + 1, 256), 256, 0, st>>>(cnt_cur, nP, (u32) pl.cap[lv - 1], (u32) Cfg::TILE, P_size, tile_prefix,
+                                                                                  status, lv == 1 ? m_cell : nullptr);
+        ++ex.launches;
+        ex.exclusive_scan_nosync(tile_prefix, tile_prefix, (u64) nP + 1);
+        u32 *cnt_next = cnt_cur + nP;
+        const u64 tiles_ub = n_bytes / Cfg::TILE + nP + 1;
+        const u32 tiles_per_cta = (u32) kc_div_up(tiles_ub, max_ctas);
+        const u32 ctas = (u32) kc_div_up(tiles_ub, tiles_per_cta);
+        {
+            CudaExec::Scope sc(ex, KP_SORT_SCATTER, 2 * n_bytes * item_bytes);
+            kc_ksf_scatter_kernel<L><<<ctas, 256, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
+                                                               pl.cap[lv - 1], tiles_per_cta, 64 * L - pl.cum[lv], pl.bits[lv], cnt_next, (u32) pl.cap[lv],
+                                                               status);
+            ++ex.launches;
+            KC_CUDA(cudaGetLastError());
+        }
+        cnt_cur = cnt_next;
+        ex.arena->release(mark);  // stream order keeps P_size / tile_prefix alive until the scatter has run
+    }
+    // ---- leaves -> hash resolve ----
+    const int last = pl.n_levels - 1;
+    if (pl.n_leaf >= 0xFFFFFFFFULL) KC_THROW(KC_ERR_TOO_LARGE, "too many leaf buckets");
+    const u32 n_small = (u32) pl.n_leaf;
+    kc_ull *n_unique = reinterpret_cast<kc_ull *>(cells);
+    if (pl.n_levels == 1) {  // M has not been added up by a prep kernel
+        const u32 *cc = cnt_cur;
+        const u64 nl = pl.n_leaf;
+        ex.for_each(nl, [=] __device__(u64 i) {
+            const u32 c = cc[i] < KSF_LEAF_CAP ? cc[i] : KSF_LEAF_CAP;
+            if (c) atomicAdd(m_cell, (kc_ull) c);
+        });
+    }
+    if (tune.resolve == 1) {
+        const int smem2 = (int) KSF_LEAF_CAP * (16 * L + 20 + (counted ? 4 : 0));
+        static bool attr2_done = false;
+        static int occ2[2] = {0, 0};
+        if (!attr2_done) {
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (16 * L + 20)));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (16 * L + 24)));
+            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2[0], kc_ksf_resolve_kernel<L, false>, 256, (int) KSF_LEAF_CAP * (16 * L + 20)));
+            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2[1], kc_ksf_resolve_kernel<L, true>, 256, (int) KSF_LEAF_CAP * (16 * L + 24)));
+            attr2_done = true;
+        }
+        const u32 fit = (u32) (n_sm * (occ2[counted] > 0 ? occ2[counted] : 1));
+        const u32 grid = n_small < fit ? n_small : fit;
+        CudaExec::Scope sc(ex, KP_KS_RESOLVE, n_bytes * item_bytes);
+        if (counted)
+            kc_ksf_resolve_kernel<L, true><<<grid, 256, smem2, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, (u32) min_freq, n_unique, status);
+        else
+            kc_ksf_resolve_kernel<L, false><<<grid, 256, smem2, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, (u32) min_freq, n_unique, status);
+        ++ex.launches;
+        KC_CUDA(cudaGetLastError());
+    } else {
+        SortBucket *small = ex.alloc<SortBucket>(pl.n_leaf);
+        kc_ksf_leaf_kernel<<<(unsigned) kc_div_up(pl.n_leaf, 256), 256, 0, st>>>(cnt_cur, pl.n_leaf, KSF_LEAF_CAP, (u8) (last & 1), small, status);
+        ++ex.launches;
+        const u32 fit = (u32) (n_sm * (occ_r[counted] > 0 ? occ_r[counted] : 1));
+        const u32 grid = n_small < fit ? n_small : fit;
+        CudaExec::Scope sc(ex, KP_KS_RESOLVE, n_bytes * item_bytes);
+        if (counted)
+            kc_ks_resolve_hash_kernel<L, CA, true><<<grid, 256, smem_r, st>>>(kb[0], kb[1], pb[0], pb[1], small, n_small, 0u, (u32) CA, flags,
+                                                                              (u32) min_freq, n_unique);
+        else
+            kc_ks_resolve_hash_kernel<L, CA, false><<<grid, 256, smem_r, st>>>(kb[0], kb[1], pb[0], pb[1], small, n_small, 0u, (u32) CA, flags,
+                                                                               (u32) min_freq, n_unique);
+        ++ex.launches;
+        KC_CUDA(cudaGetLastError());
+    }
+    ex.arena->release(base_mark);
+    return true;
+}
+
+#endif  // __CUDACC__

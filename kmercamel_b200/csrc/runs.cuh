@@ -72,11 +72,15 @@ struct RunNodes {
 // flags: bit array of kc_runs_flag_words(n_pos) words, bits >= n_pos zero.
 inline size_t kc_runs_flag_words(u64 n_pos) { return (size_t) kc_div_up(n_pos, 32) + 1; }
 
-// cells: two device words {kept distinct k-mers (already accumulated), number of runs (zero on entry)}; both come back
-// to the host with ONE synchronising read (host_cells).
-inline RunNodes kc_runs_from_flags(CudaExec &ex, const u32 *flags, u64 n_pos, int k, u64 *cells, u64 *host_cells) {
+// cells: device words {kept distinct k-mers (already accumulated), number of runs (zero on entry) [, M, status]}; all
+// n_cells of them come back to the host with ONE synchronising read (host_cells).  With n_cells == 4 a non-zero status
+// word (kmerset_fast.cuh: a slot overflowed, the flags are incomplete) makes the function return before it allocates
+// anything: *aborted = true and the caller rebuilds the flags with the exact construction.
+inline RunNodes kc_runs_from_flags(CudaExec &ex, const u32 *flags, u64 n_pos, int k, u64 *cells, u64 *host_cells, int n_cells = 2,
+                                   bool *aborted = nullptr) {
     RunNodes runs;
-    host_cells[0] = host_cells[1] = 0;
+    for (int i = 0; i < n_cells; ++i) host_cells[i] = 0;
+    if (aborted) *aborted = false;
     if (n_pos == 0) return runs;
     const size_t mark = ex.arena->mark();
     const u64 n_words = kc_div_up(n_pos, 32);
@@ -89,7 +93,12 @@ inline RunNodes kc_runs_from_flags(CudaExec &ex, const u32 *flags, u64 n_pos, in
     ++ex.launches;
     KC_CUDA(cudaGetLastError());
     ex.exclusive_scan_nosync(counts, counts, blocks);
-    ex.read_n(cells, host_cells, 2);
+    ex.read_n(cells, host_cells, (size_t) n_cells);
+    if (n_cells >= 4 && host_cells[3] != 0) {
+        if (aborted) *aborted = true;
+        ex.arena->release(mark);
+        return runs;
+    }
     const u64 n_runs = host_cells[1];
     if (n_runs == 0) {
         ex.arena->release(mark);

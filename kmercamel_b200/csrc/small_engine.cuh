@@ -28,7 +28,7 @@ template <int L> struct SmallEngineArgs {
     u32 ban_cap;
     int d_start;
     bool strict;
-    u32 *out;  // [0] error, [1] levels run, [2] groups, [3] edges, [4] ban rounds, [5] bans
+    u32 *out;  // [0] error, [1] levels run, [2] groups, [3] edges, [4] ban rounds, [5] bans, [8 + d] clocks spent in level d (KC_TRACE)
 };
 
 template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(SmallEngineArgs<L> a) {
@@ -89,6 +89,7 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
 
     for (int d = a.d_start; d >= 0; --d) {
         if (n_s <= done || n_p == 0) break;
+        const long long lvl_t0 = clock64();
         // Cheap pre-test: a level can only accept an edge if some free suffix key equals some free prefix key.  Hash the
         // prefix keys into a bit filter and probe it with the suffix keys; when nothing hits the level is a no-op and
         // is skipped without building / sorting tuples (a false positive merely runs the level as usual).
@@ -115,7 +116,10 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
         __syncthreads();
         const u32 hit = s_hit;
         __syncthreads();  // s_hit / bloom are rewritten at the top of the next level
-        if (!hit) continue;
+        if (!hit) {
+            if (tid == 0) a.out[8 + d] = (u32) (clock64() - lvl_t0);
+            continue;
+        }
         ++st_levels;
         const u32 nt = n_s + n_p;
         // 1. tuples + working copies of the chain ends
@@ -311,6 +315,7 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
         u32 *t32 = ls; ls = ls2; ls2 = t32;
         t32 = lp; lp = lp2; lp2 = t32;
         __syncthreads();
+        if (tid == 0) a.out[8 + d] = (u32) (clock64() - lvl_t0) | 0x80000000u;  // top bit: the level was run, not skipped
     }
     if (local_state) {  // write the path back for the emission stage
         __syncthreads();

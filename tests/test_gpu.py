@@ -245,3 +245,92 @@ def test_small_engine_and_host_levels_agree(ctx, golden, simplitigs_bytes):
         ctx.set_option("small_engine", 1)
     r = ctx.compute(seq, off, ln, k=31, assume_simplitigs=True, want_maxone=True)
     assert md5(r.ms + b"\n") == g["md5"] and md5(r.maxone + b"\n") == g["maxone_md5"]
+
+
+# ---- histogram-free set construction (kmerset_fast.cuh) must agree with the exact one -----------------------------
+def _fast_options(ctx, **kw):
+    defaults = dict(fast_set=1, fast_leaf_target=768, fast_sigmas=8, fast_min_items=1 << 16)
+    defaults.update(kw)
+    for name, value in defaults.items():
+        ctx.set_option(name, value)
+
+
+@pytest.mark.parametrize("k,compl,z", [(31, True, 1), (21, False, 1), (31, True, 2), (47, True, 1), (95, False, 2), (127, True, 1)])
+def test_fast_set_matches_exact(ctx, k, compl, z):
+    recs = synth.random_genome_records(6, 50_000, 7 + k)
+    recs.append(recs[0][1000:9000].copy())                      # duplicates
+    recs.append(np.frombuffer(b"ACGTNNNNNACGT" * 50, dtype=np.uint8).copy())  # N breaks, low complexity
+    recs += list(synth.reads_from_genome(20000, 4.0, 150, 0.01, seed=k))
+    seq, off, ln = synth.frame_records(recs)
+    try:
+        _fast_options(ctx, fast_set=0)
+        want = ctx.compute(seq, k=k, complements=compl, min_frequency=z)
+        for leaf_target in (768, 16, 1):                         # 2, 2 and 3 partition levels on this input
+            _fast_options(ctx, fast_min_items=0, fast_leaf_target=leaf_target)
+            runs0, fb0 = ctx.stat("fast_runs"), ctx.stat("fast_fallbacks")
+            got = ctx.compute(seq, k=k, complements=compl, min_frequency=z)
+            assert ctx.stat("fast_runs") == runs0 + 1 and ctx.stat("fast_fallbacks") == fb0, leaf_target
+            assert got.n_kmers == want.n_kmers and got.ms == want.ms, leaf_target
+        _fast_options(ctx, fast_min_items=0, fast_leaf_target=16)
+        ctx.set_option("fast_resolve", 0)                        # the bucket-list resolve of kmerset.cuh over the same slots
+        got = ctx.compute(seq, k=k, complements=compl, min_frequency=z)
+        assert got.n_kmers == want.n_kmers and got.ms == want.ms
+    finally:
+        ctx.set_option("fast_resolve", 1)
+        _fast_options(ctx)
+    want_k, want_v = orc.count_kmers(seq, off, ln, k, compl)
+    want_k = want_k[want_v.astype(int) + 1 >= z]
+    assert got.n_kmers == len(want_k) and orc.verify_ms(got.ms, k, compl, want_k)
+
+
+def test_fast_set_single_level(ctx):
+    recs = synth.random_genome_records(2, 50_000, 5)             # 100 K windows: one 8-bit level straight into the leaves
+    seq, off, ln = synth.frame_records(recs)
+    try:
+        _fast_options(ctx, fast_set=0)
+        want = ctx.compute(seq, k=31)
+        _fast_options(ctx, fast_min_items=0)
+        runs0 = ctx.stat("fast_runs")
+        got = ctx.compute(seq, k=31)
+        assert ctx.stat("fast_runs") == runs0 + 1
+        assert got.ms == want.ms and got.n_kmers == want.n_kmers == 2 * (50_000 - 30)
+    finally:
+        _fast_options(ctx)
+
+
+def test_fast_set_overflow_falls_back(ctx):
+    recs = synth.random_genome_records(4, 60_000, 99)
+    seq, off, ln = synth.frame_records(recs)
+    try:
+        _fast_options(ctx, fast_set=0)
+        want = ctx.compute(seq, k=31)
+        _fast_options(ctx, fast_min_items=0, fast_leaf_target=16, fast_sigmas=0)  # slots of exactly the mean: must overflow
+        fb0 = ctx.stat("fast_fallbacks")
+        got = ctx.compute(seq, k=31)
+        assert ctx.stat("fast_fallbacks") == fb0 + 1
+        assert got.ms == want.ms and got.n_kmers == want.n_kmers
+        # one k-mer repeated far beyond any slot: a leaf overflows with the default plan
+        text = b"A" * 300_000 + b"\n" + bytes(recs[0]) + b"\n"
+        s2 = np.frombuffer(text, dtype=np.uint8)
+        _fast_options(ctx, fast_set=0)
+        want = ctx.compute(s2, k=31)
+        _fast_options(ctx)
+        fb0 = ctx.stat("fast_fallbacks")
+        got = ctx.compute(s2, k=31)
+        assert ctx.stat("fast_fallbacks") == fb0 + 1
+        assert got.ms == want.ms and got.n_kmers == want.n_kmers
+    finally:
+        _fast_options(ctx)
+
+
+def test_fast_set_config2_full_size(ctx):
+    """configs[1] at full size through the path bench.py times (no -M): fast construction, exact set."""
+    recs = synth.random_genome_records(50, 1_000_000, 12345)
+    seq, off, ln = synth.frame_records(recs)
+    runs0, fb0 = ctx.stat("fast_runs"), ctx.stat("fast_fallbacks")
+    r = ctx.compute(seq, k=31)
+    assert ctx.stat("fast_runs") == runs0 + 1 and ctx.stat("fast_fallbacks") == fb0
+    assert r.n_kmers == 49_998_500 and abs(r.length - 49_999_860) <= 0.001 * 49_999_860
+    got, n_on = orc.ms_kmers(r.ms, 31, True)
+    keys, _ = ctx.count_kmers(seq, k=31)
+    assert n_on == r.n_kmers and np.array_equal(got, keys)
