@@ -38,7 +38,8 @@ static int usage() {
     std::cerr << "Program: kmercamel (B200-native masked superstring computation)" << std::endl;
     std::cerr << "Version: " << VERSION << std::endl;
     std::cerr << std::endl;
-    std::cerr << "Usage:   kmercamel compute [options] <fasta>" << std::endl << std::endl;
+    std::cerr << "Usage:   kmercamel compute [options] <fasta>" << std::endl;
+    std::cerr << "         kmercamel lowerbound [-k INT] [-u] [-S] [-z INT] [-g INT] <fasta>" << std::endl << std::endl;
     std::cerr << "Options:" << std::endl;
     std::cerr << "  -k INT   - k-mer size (required; up to " << MAX_K << ")" << std::endl;
     std::cerr << "  -a STR   - the algorithm; only 'greedy' (global greedy, default) runs on the GPU" << std::endl;
@@ -77,22 +78,8 @@ static bool read_all(const std::string &path, std::vector<unsigned char> &data) 
     return true;
 }
 
-int main(int argc, char **argv) {
-    if (argc < 2) return usage();
-    if (std::string(argv[1]) == "-h") {
-        usage();
-        return 0;
-    }
-    if (std::string(argv[1]) == "-v") {
-        std::cerr << VERSION << std::endl;
-        return 0;
-    }
-    if (std::string(argv[1]) != "compute") {
-        std::cerr << "Only the 'compute' sub-command is implemented by the B200 build." << std::endl;
-        return usage();
-    }
-    argc--;
-    argv++;
+// `compute` (src/main.cpp:214-316) and `lowerbound` (src/main.cpp:378-443) share everything up to the overlap stage.
+static int camel_compute(int argc, char **argv, bool lower_bound) {
     std::string path;
     if (argc > 1 && std::string(argv[argc - 1]) != "-h") {  // src/main.cpp:217-220: the input is the LAST argument
         path = argv[argc - 1];
@@ -104,7 +91,7 @@ int main(int argc, char **argv) {
     bool complements = true, assume_simplitigs = false, d_set = false;
     int opt;
     try {
-        while ((opt = getopt(argc, argv, "k:d:a:o:huxM:Sz:g:")) != -1) {  // src/main.cpp:234
+        while ((opt = getopt(argc, argv, lower_bound ? "k:huxSz:g:" : "k:d:a:o:huxM:Sz:g:")) != -1) {  // src/main.cpp:234,391
             switch (opt) {
                 case 'o': out_path = optarg; break;
                 case 'k': k = std::stoi(optarg); break;
@@ -153,7 +140,8 @@ int main(int argc, char **argv) {
         return usage();
     }
 
-    write_log("Started computation of a masked superstring from '" + path + "'.");
+    if (!lower_bound) write_log("Started computation of a masked superstring from '" + path + "'.");
+    else write_log("Started computation of a masked superstring length lower bound from '" + path + "'.");  // src/main.cpp:134
     std::vector<unsigned char> data;
     if (!read_all(path, data)) {
         std::cerr << "couldn't open file " << path << std::endl;  // src/parser.h:95-97 throws invalid_argument
@@ -178,14 +166,15 @@ int main(int argc, char **argv) {
     kc_input in{seq, n_bytes, rec_off, rec_len, n_recs};
     kc_output out;
     std::memset(&out, 0, sizeof(out));
-    rc = kc_compute(ctx, &p, &in, &out);
+    uint64_t bound = 0;
+    rc = lower_bound ? kc_lower_bound(ctx, &p, &in, &bound, &out) : kc_compute(ctx, &p, &in, &out);
     if (rc == KC_ERR_EMPTY && !assume_simplitigs) {  // src/main.cpp:155-158
         std::cerr << "Path '" << path << "' contains no k-mers. Make sure that your file is a FASTA or gzipped FASTA." << std::endl;
         kc_destroy(ctx);
         return usage();
     }
     if (rc != KC_OK) {
-        std::cerr << "kmercamel compute failed: " << kc_strerror(rc) << ": " << kc_last_error(ctx) << std::endl;
+        std::cerr << "kmercamel " << (lower_bound ? "lowerbound" : "compute") << " failed: " << kc_strerror(rc) << ": " << kc_last_error(ctx) << std::endl;
         kc_destroy(ctx);
         return 1;
     }
@@ -193,6 +182,15 @@ int main(int argc, char **argv) {
         write_log("Finished collecting k-mers: " + std::to_string(out.n_kmers) + " " + std::to_string(k) + "-mers.");
     write_log("Finished 1. part: " + std::string(assume_simplitigs ? "simplitigs (" : "GPU k-mer nodes (") + std::to_string(out.n_nodes) + ").");
     write_log("Finished 2. part: Hamiltonian path.");
+    if (lower_bound) {  // src/lower_bound.h:21, src/main.cpp:182,210
+        write_log("Finished 3. part: lower bound = " + std::to_string(bound) + ".");
+        std::cout << bound << std::endl;
+        kc_destroy(ctx);
+        kc_free(seq);
+        kc_free(rec_off);
+        kc_free(rec_len);
+        return 0;
+    }
     write_log("Finished 3. part: masked superstring (l=" + std::to_string(out.length) + ").");
     char times[256];
     std::snprintf(times, sizeof(times), "GPU stages [ms]: extract %.3f, count %.3f, path %.3f, emit %.3f, total %.3f; %llu kernels",
@@ -219,4 +217,21 @@ int main(int argc, char **argv) {
     kc_free(rec_off);
     kc_free(rec_len);
     return 0;
+}
+
+int main(int argc, char **argv) {
+    if (argc < 2) return usage();
+    const std::string sub = argv[1];
+    if (sub == "-h") {
+        usage();
+        return 0;
+    }
+    if (sub == "-v") {
+        std::cerr << VERSION << std::endl;
+        return 0;
+    }
+    if (sub == "compute") return camel_compute(argc - 1, argv + 1, false);
+    if (sub == "lowerbound") return camel_compute(argc - 1, argv + 1, true);
+    std::cerr << "Only the 'compute' and 'lowerbound' sub-commands are implemented by the B200 build." << std::endl;
+    return usage();
 }

@@ -87,6 +87,12 @@ int kc_compute(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *o
 /* Same with DEVICE buffers in and out (outputs live in the context arena until the next call). */
 int kc_compute_device(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *out);
 
+/* `kmercamel lowerbound` (reference src/main.cpp:378-443, LowerBoundLength src/lower_bound.h:9-22): the same path with
+ * the cycle and reverse-complement tests of the greedy switched off (src/global.h:95-97), i.e. a cycle cover; returns
+ * (sum of node lengths - sum of accepted overlaps) per strand.  Host buffers as kc_compute; want_maxone must be 0.
+ * `stats` (may be NULL) receives the counters and stage times, no superstring. */
+int kc_lower_bound(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t *lower_bound, kc_output *stats);
+
 /* Copy n bytes of a kc_compute_device result (or any device buffer) to host memory on the context stream. */
 int kc_copy_to_host(kc_ctx *ctx, void *dst_host, const void *src_device, uint64_t n);
 

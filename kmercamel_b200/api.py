@@ -69,6 +69,7 @@ def load_library():
     L.kc_destroy.restype = None
     L.kc_compute.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.POINTER(kc_output)]
     L.kc_compute_device.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.POINTER(kc_output)]
+    L.kc_lower_bound.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), u64p, C.POINTER(kc_output)]
     L.kc_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.kc_count_kmers.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.POINTER(u64p), C.POINTER(u8p),
                                  u64p]
@@ -106,7 +107,7 @@ def load_library():
     return L
 
 
-EXPORTED_SYMBOLS = ["kc_init", "kc_destroy", "kc_compute", "kc_compute_device", "kc_copy_to_host", "kc_count_kmers", "kc_overlap_path",
+EXPORTED_SYMBOLS = ["kc_init", "kc_destroy", "kc_compute", "kc_compute_device", "kc_lower_bound", "kc_copy_to_host", "kc_count_kmers", "kc_overlap_path",
                     "kc_p2p_alloc", "kc_p2p_open", "kc_p2p_hist", "kc_p2p_scatter", "kc_p2p_resolve", "kc_total_launches", "kc_shard_granule", "kc_shard_partition", "kc_shard_resolve", "kc_compute_from_flags",
                     "kc_frame_fasta", "kc_set_option", "kc_get_stat", "kc_profile_enable", "kc_profile_count", "kc_profile_get", "kc_profile_reset",
                     "kc_limbs_for_k", "kc_free", "kc_strerror", "kc_last_error"]
@@ -210,6 +211,21 @@ class Context:
         out = kc_output()
         self._check(self._lib.kc_compute(self._h, C.byref(p), C.byref(inp), C.byref(out)))
         return self._result(out, copy)
+
+    def lower_bound(self, seq, rec_off=None, rec_len=None, *, k, complements=True, min_frequency=1, assume_simplitigs=False):
+        """`kmercamel lowerbound` (reference src/lower_bound.h:9-22): -> (cycle-cover lower bound, ComputeResult stats)."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        n_recs = 0 if rec_off is None else len(rec_off)
+        if rec_off is not None:
+            rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+            rec_len = np.ascontiguousarray(rec_len, dtype=np.uint64)
+        p = self._params(k, complements, min_frequency, assume_simplitigs, False)
+        inp = kc_input(seq.ctypes.data, seq.size, rec_off.ctypes.data if n_recs else None,
+                       rec_len.ctypes.data if n_recs else None, n_recs)
+        out = kc_output()
+        lb = C.c_uint64()
+        self._check(self._lib.kc_lower_bound(self._h, C.byref(p), C.byref(inp), C.byref(lb), C.byref(out)))
+        return lb.value, self._result(out, False)
 
     def compute_device(self, seq_ptr: int, n_bytes: int, rec_off_ptr: int = 0, rec_len_ptr: int = 0, n_recs: int = 0, *, k,
                        complements=True, min_frequency=1, assume_simplitigs=False, want_maxone=False) -> ComputeResult:

@@ -265,7 +265,46 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
             u64 b0 = a0 < off ? off : a0;
             u64 b1 = a0 + 16 < off + cnt ? a0 + 16 : off + cnt;
             if (b0 >= b1) return;
-            if (b1 - b0 == 16) {
+            const u64 j0 = b0 - off;
+#ifdef __CUDA_ARCH__
+            const bool one_case = j0 + 16 <= n_upper || j0 >= n_upper;
+#else
+            const bool one_case = false;  // host emulation (tests): the per-character path below
+#endif
+            if (b1 - b0 == 16 && one_case) {
+#ifdef __CUDA_ARCH__
+                // Whole item with one case: 16 source bytes in five aligned words, case (and, on the mirror strand, order and
+                // complement) changed four characters at a time.  Node characters are ACGT in either case by construction
+                // (first-occurrence runs span valid windows only, -S records were validated).
+                const u32 u = v < q.n ? v : v - q.n;
+                const u64 src0 = v < q.n ? q.rec_off[u] + j0 : q.rec_off[u] + q.rec_len[u] - 16 - j0;
+                const u32 *wp = reinterpret_cast<const u32 *>(q.seq + (src0 & ~(u64) 3));
+                const u32 sh = (u32) (src0 & 3) * 8;
+                u32 in[5];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) in[x] = wp[x];
+                in[4] = sh ? wp[4] : 0u;
+                u32 wd[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) wd[x] = __funnelshift_r(in[x], in[x + 1], sh) & 0xDFDFDFDFu;  // upper case
+                if (v >= q.n) {
+                    u32 r[4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const u32 t = __byte_perm(wd[3 - x], 0u, 0x0123);
+                        const u32 cg = ((t >> 1) & 0x01010101u) * 0xFFu;              // bytes holding C or G
+                        r[x] = t ^ ((cg & 0x04040404u) | (~cg & 0x15151515u));        // C <-> G, A <-> T
+                    }
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) wd[x] = r[x];
+                }
+                if (j0 >= n_upper) {
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) wd[x] |= 0x20202020u;
+                }
+                *reinterpret_cast<uint4 *>(ms + b0) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+#endif
+            } else if (b1 - b0 == 16) {
                 u32 wd[4];
                 u64 j = b0 - off;
                 for (int x = 0; x < 4; ++x) {

@@ -373,7 +373,10 @@ template <class Exec, int L> struct Engine {
         TW *T = ex.template alloc<TW>(nt);
         TW *T2 = ex.template alloc<TW>(nt);
         const NodeView<L> v = nv;
-        const u32 batch = nv.N / 16 + 1;
+        // The 16 prefix batches of src/global.h:48,66-72 only fix the reference's tie order.  It is reproduced for -S
+        // input (strict); from FASTA the reference's own node order is khash order, i.e. unspecified, so every prefix
+        // goes into batch 0 and a group is replayed with one pass over its suffixes instead of 16.
+        const u32 batch = strict ? nv.N / 16 + 1 : nv.N + 1;
         const u32 *ls = live_s, *lp = live_p;
         const u64 ns = n_s, np = n_p;
         u32 *hw = head_w, *tw = tail_w;

@@ -164,6 +164,7 @@ struct DevInput {
 struct DevResult {
     const u8 *ms = nullptr, *maxone = nullptr;
     u64 length = 0, n_kmers = 0, n_occ = 0, n_nodes = 0;
+    u64 lower_bound = 0;  // only with run_pipeline(..., lower_bound = true)
 };
 
 // Stage 1 alone.  Leaves the sorted distinct k-mers (and their counts) at the current arena top and returns them.
@@ -251,7 +252,7 @@ u64 run_stage1_runs(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_para
 
 template <int L>
 void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, DevResult &res, const u32 *ext_flags = nullptr,
-                  u64 ext_kept = 0) {
+                  u64 ext_kept = 0, bool lower_bound = false) {
     const bool complements = p.complements != 0;
     KWord<L> *uniq = nullptr;
     u8 *cnt = nullptr;
@@ -315,12 +316,34 @@ void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params
     nv.N = nv.n * (complements ? 2u : 1u);
     ns.n = nv.n;
     KC_TRACE_POINT("pipeline: nodes ready");
-    Engine<CudaExec, L> eng(ex, nv, /*strict=*/p.assume_simplitigs != 0, /*lower_bound=*/false);
+    Engine<CudaExec, L> eng(ex, nv, /*strict=*/p.assume_simplitigs != 0, lower_bound);
     eng.use_small = ctx->small_engine;
     eng.init_state();
     eng.run();
     KC_TRACE_POINT("pipeline: engine done");
     KC_CUDA(cudaEventRecord(ctx->ev[3], ex.stream));
+    if (lower_bound) {
+        // src/lower_bound.h:10-22: (sum of node lengths over both strands - sum of the cycle cover's overlaps) / strands.
+        // In this mode every virtual node has an out-edge after d = 0, so no 255 is left among the overlaps.
+        kc_ull *acc = reinterpret_cast<kc_ull *>(ex.alloc<u64>(2));
+        ex.fill_bytes(acc, 0, 16);
+        const u64 *len = node_off == in.rec_off ? in.rec_len : node_len;
+        const u8 *ovl = eng.st.ovl;
+        const u32 n = nv.n;
+        ex.for_each(nv.N, [=] __device__(u64 i) {
+            if (i < n) atomicAdd(&acc[0], (kc_ull) len[i]);
+            if (ovl[i]) atomicAdd(&acc[1], (kc_ull) ovl[i]);
+        });
+        u64 h[2];
+        ex.read_n(reinterpret_cast<const u64 *>(acc), h, 2);
+        const u64 strands = complements ? 2 : 1;
+        res.lower_bound = (h[0] * strands - h[1]) / strands;
+        KC_CUDA(cudaEventRecord(ctx->ev[4], ex.stream));
+        res.n_kmers = U;
+        res.n_occ = n_occ;
+        res.n_nodes = nv.n;
+        return;
+    }
     EmitResult er = kc_emit_superstring<CudaExec, L>(ex, ns, nv, eng.st, uniq, U, p.want_maxone != 0);
     KC_CUDA(cudaEventRecord(ctx->ev[4], ex.stream));
     res.ms = er.ms;
@@ -331,10 +354,10 @@ void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params
     res.n_nodes = nv.n;
 }
 
-void dispatch_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, DevResult &res) {
-    if (p.k < 32) run_pipeline<1>(ctx, ex, in, p, res);
-    else if (p.k < 64) run_pipeline<2>(ctx, ex, in, p, res);
-    else run_pipeline<4>(ctx, ex, in, p, res);
+void dispatch_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, DevResult &res, bool lower_bound = false) {
+    if (p.k < 32) run_pipeline<1>(ctx, ex, in, p, res, nullptr, 0, lower_bound);
+    else if (p.k < 64) run_pipeline<2>(ctx, ex, in, p, res, nullptr, 0, lower_bound);
+    else run_pipeline<4>(ctx, ex, in, p, res, nullptr, 0, lower_bound);
 }
 
 void fill_times(kc_ctx *ctx, kc_output *out) {
@@ -528,6 +551,47 @@ int kc_compute(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *o
     out->n_nodes = res.n_nodes;
     out->n_launches = ex.launches;
     fill_times(ctx, out);
+    ctx->total_launches += ex.launches;
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
+int kc_lower_bound(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t *lower_bound, kc_output *stats) {
+    if (!ctx || !in || !lower_bound) return KC_ERR_ARG;
+    KC_API_BEGIN
+    check_params(p);
+    if (p->want_maxone) KC_THROW(KC_ERR_ARG, "lowerbound has no mask output");
+    if (in->n_bytes >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 sequence bytes on one GPU");
+    KC_CUDA(cudaSetDevice(ctx->device));
+    const int limbs = kc_limbs_for_k(p->k);
+    const bool simplitigs = p->assume_simplitigs != 0;
+    CudaExec ex{ctx->stream, &ctx->arena};
+    ex.prof = &ctx->prof;
+    DevResult res;
+    run_with_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, simplitigs, false, &ctx->fast),
+                   estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, simplitigs, true, &ctx->fast), [&] {
+        u8 *d_seq = ex.alloc<u8>(in->n_bytes + 64);
+        KC_CUDA(cudaMemcpyAsync(d_seq, in->seq, in->n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        u64 *d_off = nullptr, *d_len = nullptr;
+        if (simplitigs) {
+            d_off = ex.alloc<u64>(in->n_recs);
+            d_len = ex.alloc<u64>(in->n_recs);
+            KC_CUDA(cudaMemcpyAsync(d_off, in->rec_off, in->n_recs * 8, cudaMemcpyHostToDevice, ctx->stream));
+            KC_CUDA(cudaMemcpyAsync(d_len, in->rec_len, in->n_recs * 8, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        DevInput di{d_seq, in->n_bytes, d_off, d_len, in->n_recs};
+        dispatch_pipeline(ctx, ex, di, *p, res, /*lower_bound=*/true);
+    });
+    KC_CUDA(cudaStreamSynchronize(ctx->stream));
+    *lower_bound = res.lower_bound;
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->n_kmers = res.n_kmers;
+        stats->n_occurrences = res.n_occ;
+        stats->n_nodes = res.n_nodes;
+        stats->n_launches = ex.launches;
+        fill_times(ctx, stats);
+    }
     ctx->total_launches += ex.launches;
     return KC_OK;
     KC_API_END(ctx)

@@ -13,6 +13,8 @@ template <int L> struct SmallCfg {
     static constexpr u32 T = L <= 2 ? 4096 : 2048;  // tuple capacity (free suffix ends + free prefix ends)
     static constexpr u32 H = T / 2;
     static constexpr u32 NS = 1024;  // up to this many virtual nodes the whole path state lives in shared memory
+    static constexpr u64 MASK_BUDGET = 1u << 20;  // pairs x levels x limbs up to which the level mask is computed up front
+    static constexpr u32 RANK_SORT = 384;      // up to this many tuples: rank sort (no barriers) instead of the bitonic network
     static constexpr size_t SMEM = (size_t) T * sizeof(KWord<L + 1>) + (size_t) H * (4 * 6 + 8 * 2) + (size_t) NS * (8 + 4 * 7 + 3);
 };
 
@@ -35,13 +37,15 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
     typedef KWord<L + 1> TW;
     constexpr u32 TCAP = SmallCfg<L>::T, HCAP = SmallCfg<L>::H;
     extern __shared__ __align__(16) unsigned char kc_smem_raw[];
-    TW *T = reinterpret_cast<TW *>(kc_smem_raw);
-    u64 *max0 = reinterpret_cast<u64 *>(T + TCAP);
+    TW *const T0 = reinterpret_cast<TW *>(kc_smem_raw);
+    TW *T = T0;
+    u64 *max0 = reinterpret_cast<u64 *>(T0 + TCAP);
     u64 *max1 = max0 + HCAP;
     u32 *group_pstart = reinterpret_cast<u32 *>(max1 + HCAP);
     u32 *new_tail = group_pstart + HCAP;
     u32 *jump0 = new_tail + HCAP, *jump1 = jump0 + HCAP, *fin0 = jump1 + HCAP, *fin1 = fin0 + HCAP;
     __shared__ u32 s_groups, s_edges, s_cyc, s_bans, s_live_s, s_live_p, s_hit;
+    __shared__ u32 lvl_mask[4];  // bit d: some (suffix, prefix) pair of the initial free ends agrees on d bases
     __shared__ u32 bloom[512];  // 16384-bit filter over the prefix keys of the level
     __shared__ kc_ull s_min;
     const u32 tid = threadIdx.x;
@@ -83,9 +87,32 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
     }
     u32 n_s = a.n_s, n_p = a.n_p;
     u32 *ls = a.live_s_a, *lp = a.live_p_a, *ls2 = a.live_s_b, *lp2 = a.live_p_b;
-    const u32 batch = v.N / 16 + 1;
+    const u32 batch = a.strict ? v.N / 16 + 1 : v.N + 1;  // see Engine::run_level
     const u32 done = v.complements ? 2u : 1u;
     u32 st_levels = 0, st_groups = 0, st_edges = 0, st_rounds = 0, st_bans = 0;
+
+    // Few ends (a genome leaves ~100 x 100): find out ONCE at which levels any free suffix can meet any free prefix.  The
+    // live sets only shrink, so a level whose bit is clear can never accept an edge and is skipped without touching
+    // memory; per-level filtering (below) cost more than the levels that really run (a 16384-bit filter alone also gave
+    // a false positive on every second level).  Full k-mers of the ends are parked in the still unused tuple buffer.
+    const bool have_mask = (u64) n_s * n_p * (u64) (a.d_start + 1) * L <= SmallCfg<L>::MASK_BUDGET;
+    if (have_mask) {
+        KWord<L> *pk = reinterpret_cast<KWord<L> *>(T0), *sk = pk + n_p;
+        if (tid < 4) lvl_mask[tid] = 0;
+        for (u32 i = tid; i < n_p; i += NT) pk[i] = v.first_kmer(lp[i]);
+        for (u32 i = tid; i < n_s; i += NT) sk[i] = v.last_kmer(ls[i]);
+        __syncthreads();
+        u32 m[4] = {0, 0, 0, 0};
+        for (u32 q = tid, pairs = n_s * n_p; q < pairs; q += NT) {
+            const KWord<L> x = sk[q % n_s], y = pk[q / n_s];
+            for (int d = 0; d <= a.d_start; ++d)
+                if (kmer_suffix(x, d) == kmer_prefix(y, v.k, d)) m[d >> 5] |= 1u << (d & 31);
+        }
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+            if (m[w]) atomicOr(&lvl_mask[w], m[w]);
+        __syncthreads();
+    }
 
     for (int d = a.d_start; d >= 0; --d) {
         if (n_s <= done || n_p == 0) break;
@@ -93,35 +120,40 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
         // Cheap pre-test: a level can only accept an edge if some free suffix key equals some free prefix key.  Hash the
         // prefix keys into a bit filter and probe it with the suffix keys; when nothing hits the level is a no-op and
         // is skipped without building / sorting tuples (a false positive merely runs the level as usual).
-        for (u32 i = tid; i < 512; i += NT) bloom[i] = 0;
-        if (tid == 0) s_hit = 0;
-        __syncthreads();
-        for (u32 i = tid; i < n_p; i += NT) {
-            const KWord<L> key = kmer_prefix(v.first_kmer(lp[i]), v.k, d);
-            u64 h = 0;
+        if (have_mask) {  // uniform: no barrier needed
+            if (!((lvl_mask[d >> 5] >> (d & 31)) & 1u)) continue;
+        } else {
+            if (tid == 0) s_hit = 0;
+            for (u32 i = tid; i < 512; i += NT) bloom[i] = 0;
+            __syncthreads();
+            for (u32 i = tid; i < n_p; i += NT) {
+                const KWord<L> key = kmer_prefix(v.first_kmer(lp[i]), v.k, d);
+                u64 h = 0;
 #pragma unroll
-            for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
-            h >>= 50;
-            atomicOr(&bloom[h >> 5], 1u << (h & 31));
-        }
-        __syncthreads();
-        for (u32 i = tid; i < n_s; i += NT) {
-            const KWord<L> key = kmer_suffix(v.last_kmer(ls[i]), d);
-            u64 h = 0;
+                for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
+                h >>= 50;
+                atomicOr(&bloom[h >> 5], 1u << (h & 31));
+            }
+            __syncthreads();
+            for (u32 i = tid; i < n_s; i += NT) {
+                const KWord<L> key = kmer_suffix(v.last_kmer(ls[i]), d);
+                u64 h = 0;
 #pragma unroll
-            for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
-            h >>= 50;
-            if ((bloom[h >> 5] >> (h & 31)) & 1u) s_hit = 1;
-        }
-        __syncthreads();
-        const u32 hit = s_hit;
-        __syncthreads();  // s_hit / bloom are rewritten at the top of the next level
-        if (!hit) {
-            if (tid == 0) a.out[8 + d] = (u32) (clock64() - lvl_t0);
-            continue;
+                for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
+                h >>= 50;
+                if ((bloom[h >> 5] >> (h & 31)) & 1u) s_hit = 1;
+            }
+            __syncthreads();
+            const u32 hit = s_hit;
+            __syncthreads();  // s_hit / bloom are rewritten at the top of the next level
+            if (!hit) {
+                if (tid == 0) a.out[8 + d] = (u32) (clock64() - lvl_t0);
+                continue;
+            }
         }
         ++st_levels;
         const u32 nt = n_s + n_p;
+        T = T0;
         // 1. tuples + working copies of the chain ends
         for (u32 i = tid; i < nt; i += NT) {
             if (i < n_s) {
@@ -140,8 +172,22 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
             s_bans = 0;
         }
         __syncthreads();
-        // 2. sort
-        kc_block_bitonic<L + 1>(T, nt, NT);
+        // 2. sort.  Tiny levels: every thread ranks its tuple against all others (tuples are distinct: they carry role
+        // and node id) and drops it at its rank in the upper half of the tuple buffer — two barriers instead of the
+        // 36+ of a bitonic network over 256 slots.
+        if (nt <= SmallCfg<L>::RANK_SORT) {
+            TW *dst = T0 + HCAP;
+            for (u32 i = tid; i < nt; i += NT) {
+                const TW mine = T0[i];
+                u32 r = 0;
+                for (u32 j = 0; j < nt; ++j) r += T0[j] < mine ? 1u : 0u;
+                dst[r] = mine;
+            }
+            T = dst;
+            __syncthreads();
+        } else {
+            kc_block_bitonic<L + 1>(T, nt, NT);
+        }
         // 3. active groups
         for (u32 i = tid + 1; i < nt; i += NT) {
             TW p = T[i - 1], q = T[i];

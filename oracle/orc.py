@@ -225,6 +225,16 @@ def compute_from_simplitigs(records, k: int, complements: bool, want_maxone: boo
     return out, (_take(mo, n.value, np.uint8).tobytes() if want_maxone else None)
 
 
+def lower_bound_from_simplitigs(records, k: int, complements: bool) -> int:
+    """`kmercamel lowerbound -S` (reference src/lower_bound.h:9-22 LowerBoundLength): cycle cover of the records as
+    nodes, (sum of lengths over the strands - sum of overlaps) / strands."""
+    first = np.stack([kmer_from_string(r[:k].decode(), k) for r in records])
+    last = np.stack([kmer_from_string(r[len(r) - k:].decode(), k) for r in records])
+    _, ov = overlap_path(first, last, k, complements, lower_bound=True)
+    strands = 2 if complements else 1
+    return (sum(len(r) for r in records) * strands - int(ov.astype(np.int64).sum())) // strands
+
+
 def ms_kmers(ms: bytes, k: int, complements: bool):
     """-> (sorted unique ON k-mers [n, limbs] u64, number of ON positions)."""
     L = limbs_for_k(k)

@@ -51,6 +51,28 @@ def run_ref(path, k, flags=(), want_maxone=False):
         return out, line2
 
 
+def run_ref_lowerbound(path, k, flags=()):
+    """`kmercamel lowerbound` of the reference (src/main.cpp:378-443): the integer it prints."""
+    p = subprocess.run([REF, "lowerbound", "-k", str(k), *flags, path], capture_output=True)
+    assert p.returncode == 0, p.stderr
+    return int(p.stdout.split()[0])
+
+
+def add_lowerbound(G, td, sp, st):
+    """Section "lowerbound": -S inputs are exact (pure function of record order); from-FASTA values depend on the
+    reference's khash-order simplitigs and are compared with a tolerance."""
+    L = dict(fuzz_S=[], simplitigs_S={}, spneumoniae={})
+    for g in G["fuzz_S"]:
+        f = os.path.join(td, "fzlb.fa")
+        open(f, "w").write("".join(f">{i}\n{r}\n" for i, r in enumerate(g["records"])))
+        L["fuzz_S"].append(run_ref_lowerbound(f, g["k"], ("-S",) + (() if g["complements"] else ("-u",))))
+    for name, k, flags in [("k31", 31, ("-S",)), ("k31u", 31, ("-S", "-u")), ("k25", 25, ("-S",)), ("k17u", 17, ("-S", "-u"))]:
+        L["simplitigs_S"][name] = run_ref_lowerbound(st, k, flags)
+    for name, k, flags in [("k31", 31, ()), ("k31u", 31, ("-u",)), ("k13", 13, ()), ("k63", 63, ()), ("k31z2", 31, ("-z", "2"))]:
+        L["spneumoniae"][name] = run_ref_lowerbound(sp, k, flags)
+    G["lowerbound"] = L
+
+
 def kmers_dump(path, k, complements):
     with tempfile.TemporaryDirectory() as td:
         o = os.path.join(td, "k.bin")
@@ -91,12 +113,19 @@ def fuzz_records(rng, k, n, alpha):
 
 
 def main():
+    import sys
     G = {}
     with tempfile.TemporaryDirectory() as td:
         sp = os.path.join(td, "spneumoniae.fa")
         open(sp, "wb").write(gzip.open(os.path.join(HERE, "spneumoniae.fa.gz")).read())
         st = os.path.join(td, "simplitigs-k31.fa")
         open(st, "wb").write(gzip.open(os.path.join(HERE, "simplitigs-k31.fa.gz")).read())
+        if "--only-lowerbound" in sys.argv:  # extend the committed JSON without re-running the other sections
+            G = json.load(open(os.path.join(HERE, "golden.json")))
+            add_lowerbound(G, td, sp, st)
+            json.dump(G, open(os.path.join(HERE, "golden.json"), "w"), indent=1, sort_keys=True)
+            print("lowerbound:", G["lowerbound"]["simplitigs_S"], G["lowerbound"]["spneumoniae"])
+            return
         # from-FASTA regime: sizes/lengths (output bytes depend on khash order -> compared by set + tolerance)
         G["spneumoniae_compute"] = {}
         for name, k, flags, mo in [("k31", 31, (), True), ("k13", 13, (), False), ("k63", 63, (), False),
@@ -151,6 +180,7 @@ def main():
             res, line2 = run_ref(f, k, ("-S",) + (() if compl else ("-u",)), True)
             mo = None
             G["fuzz_S"].append(dict(k=k, complements=compl, records=recs, ms=line2.decode(), maxone_md5=res["maxone_md5"]))
+        add_lowerbound(G, td, sp, st)
     json.dump(G, open(os.path.join(HERE, "golden.json"), "w"), indent=1, sort_keys=True)
     print("wrote golden.json:", {k: len(v) for k, v in G.items()})
 

@@ -122,6 +122,44 @@ def test_overlap_path_random_vs_oracle(ctx, seed):
         assert np.array_equal(ef, want_ef) and np.array_equal(ov, want_ov), (k, n, compl)
 
 
+# ---- lowerbound: kc_lower_bound against the reference CLI and its unit tests ------------------------
+def test_lower_bound_kats(ctx):
+    """reference tests/lower_bound_unittest.h:11-41"""
+    from test_oracle import LOWER_BOUND_KATS
+    for records, k, compl, want in LOWER_BOUND_KATS:
+        seq, off, ln = orc.records_to_arrays([r.encode() for r in records])
+        lb, _ = ctx.lower_bound(seq, off, ln, k=k, complements=compl, assume_simplitigs=True)
+        assert lb == want, records
+
+
+def test_lower_bound_S_exact(ctx, golden, simplitigs_bytes):
+    """-S inputs: the value is a pure function of the record order -> equal to `kmercamel lowerbound -S` of the reference"""
+    for g, want in zip(golden["fuzz_S"], golden["lowerbound"]["fuzz_S"]):
+        seq, off, ln = orc.records_to_arrays([r.encode() for r in g["records"]])
+        lb, _ = ctx.lower_bound(seq, off, ln, k=g["k"], complements=g["complements"], assume_simplitigs=True)
+        assert lb == want, g
+    seq, off, ln = kb.frame_fasta(simplitigs_bytes)
+    for name, want in golden["lowerbound"]["simplitigs_S"].items():
+        k = int(name[1:].rstrip("u"))
+        lb, st = ctx.lower_bound(seq, off, ln, k=k, complements=not name.endswith("u"), assume_simplitigs=True)
+        assert lb == want and st.n_nodes == len(off), name
+
+
+@pytest.mark.parametrize("name", ["k31", "k31u", "k13", "k63", "k31z2"])
+def test_lower_bound_from_fasta(ctx, golden, spneumoniae_bytes, name):
+    """From FASTA the reference's value depends on its khash-order simplitigs: within 0.1 %, and never above the
+    length of the superstring computed from the same input (it is a lower bound of it)."""
+    want = golden["lowerbound"]["spneumoniae"][name]
+    flags = name.lstrip("k0123456789")
+    k = int(name[1:len(name) - len(flags)])
+    z = 2 if "z2" in flags else 1
+    seq, _, _ = kb.frame_fasta(spneumoniae_bytes)
+    lb, st = ctx.lower_bound(seq, k=k, complements="u" not in flags, min_frequency=z)
+    assert abs(lb - want) <= 0.001 * want, (lb, want)
+    r = ctx.compute(seq, k=k, complements="u" not in flags, min_frequency=z)
+    assert st.n_kmers == r.n_kmers and lb <= r.length
+
+
 # ---- -S regime: byte-exact superstring and max-one mask ---------------------------------------------------------
 def test_compute_S_fuzz_byte_exact(ctx, golden):
     for g in golden["fuzz_S"]:

@@ -118,6 +118,21 @@ def test_overlap_path_kats(records, k, compl, lb, want_ef, want_ov):
     assert ef.tolist() == want_ef and ov.tolist() == want_ov
 
 
+# ---- lowerbound: tests/lower_bound_unittest.h:11-41 and the reference CLI on the fuzzed -S inputs -------------
+LOWER_BOUND_KATS = [(["ACG", "CGT", "TAA"], 3, False, 5), (["ACGT", "TAA"], 3, False, 5), (["AC", "GG"], 2, True, 3),
+                    (["AAACCC", "CCCAAA", "TGGGGT"], 6, False, 11)]
+
+
+@pytest.mark.parametrize("records,k,compl,want", LOWER_BOUND_KATS)
+def test_lower_bound_kats(records, k, compl, want):
+    assert orc.lower_bound_from_simplitigs([r.encode() for r in records], k, compl) == want
+
+
+def test_lower_bound_fuzz_vs_reference_cli(golden):
+    for g, want in zip(golden["fuzz_S"], golden["lowerbound"]["fuzz_S"]):
+        assert orc.lower_bound_from_simplitigs([r.encode() for r in g["records"]], g["k"], g["complements"]) == want, g
+
+
 # ---- Global end to end: tests/global_unittest.h:120-129 -----------------------------------------------------
 GLOBAL_KATS = [
     ("TACgt", 3, ["CGT", "TAC", "ACG"], False), ("ACGT", 1, ["ACGT"], False), ("ACgTtt", 3, ["CGT", "TTT", "ACG"], False),
