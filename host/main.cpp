@@ -3,6 +3,9 @@
 // include/kcgpu.h; this file mirrors the user-visible behaviour of the reference CLI for the compute sub-command:
 // flags and validation (reference src/main.cpp:214-316), the header line (src/parser.h:167-179), the stderr stage
 // log (src/parser.h:159-164, src/main.cpp:133,160,174, src/global.h:223,225) and the two-line .msfa output.
+// The neighbouring sub-commands are mirrored as well: lowerbound (src/main.cpp:378-443), `compute -a streaming`
+// (src/main.cpp:139-144), maskopt -t max-one|min-one (src/main.cpp:318-376) and the four text conversions ms2mssep,
+// mssep2ms, ms2spss, spss2ms (src/main.cpp:444-667, src/conversions.h).
 #include <kcgpu.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -28,8 +31,9 @@ static void write_log(const std::string &message) {  // src/parser.h:159-164
     std::cerr << "[" << std::put_time(time_tm, "%H:%M:%S") << "] " << message << std::endl;
 }
 
-static void write_name(const std::string &dataset, int k, bool maxone, bool unidirectional, std::ostream &of) {  // src/parser.h:167-179
-    of << ">maskedsuperstring dataset='" << dataset << "' k=" << k << " alg=greedy mask=" << (maxone ? "max-one " : "min-one ")
+static void write_name(const std::string &dataset, int k, bool maxone, bool unidirectional, std::ostream &of,
+                       const char *algorithm = "greedy") {  // src/parser.h:167-179
+    of << ">maskedsuperstring dataset='" << dataset << "' k=" << k << " alg=" << algorithm << " mask=" << (maxone ? "max-one " : "min-one ")
        << "mode=" << (unidirectional ? "unidirectional" : "bidirectional") << std::endl;
 }
 
@@ -39,10 +43,13 @@ static int usage() {
     std::cerr << "Version: " << VERSION << std::endl;
     std::cerr << std::endl;
     std::cerr << "Usage:   kmercamel compute [options] <fasta>" << std::endl;
-    std::cerr << "         kmercamel lowerbound [-k INT] [-u] [-S] [-z INT] [-g INT] <fasta>" << std::endl << std::endl;
+    std::cerr << "         kmercamel lowerbound [-k INT] [-u] [-S] [-z INT] [-g INT] <fasta>" << std::endl;
+    std::cerr << "         kmercamel maskopt -k INT [-t max-one|min-one] [-u] [-o FILE] [-g INT] <ms>" << std::endl;
+    std::cerr << "         kmercamel ms2mssep -m FILE [-s FILE] <ms>     |  mssep2ms [-m FILE] [-s FILE] [-o FILE]" << std::endl;
+    std::cerr << "         kmercamel ms2spss -k INT [-o FILE] <ms>       |  spss2ms -k INT [-o FILE] <fasta>" << std::endl << std::endl;
     std::cerr << "Options:" << std::endl;
     std::cerr << "  -k INT   - k-mer size (required; up to " << MAX_K << ")" << std::endl;
-    std::cerr << "  -a STR   - the algorithm; only 'greedy' (global greedy, default) runs on the GPU" << std::endl;
+    std::cerr << "  -a STR   - the algorithm [greedy (default), streaming]" << std::endl;
     std::cerr << "  -o FILE  - output file [default: stdout]" << std::endl;
     std::cerr << "  -u       - treat k-mer and its reverse complement as distinct" << std::endl;
     std::cerr << "  -S       - assume the input are simplitigs / matchtigs / unitigs" << std::endl;
@@ -123,14 +130,20 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
     } else if (k < 0) {
         std::cerr << "k must be positive." << std::endl;
         return usage();
-    } else if (algorithm != "greedy") {
+    } else if (algorithm != "greedy" && (algorithm != "streaming" || lower_bound)) {
         std::cerr << "Algorithm '" << algorithm << "' is not part of the GPU compute path; use the reference build for it." << std::endl;
         return usage();
     } else if (k > MAX_K) {
         std::cerr << "k > " << MAX_K << " not supported for the algorithm 'greedy'." << std::endl;
         return usage();
     } else if (d_set) {
-        std::cerr << "Unsupported argument d for algorithm 'greedy'." << std::endl;
+        std::cerr << "Unsupported argument d for algorithm '" << algorithm << "'." << std::endl;
+        return usage();
+    } else if (!mask_path.empty() && algorithm != "greedy") {  // src/main.cpp:296-298
+        std::cerr << "Outputting mask with maximum number of ones is only supported for the global greedy algorithm." << std::endl;
+        return usage();
+    } else if (assume_simplitigs && algorithm != "greedy") {  // src/main.cpp:299-301
+        std::cerr << "Assuming simplitigs is only supported for the global greedy algorithm." << std::endl;
         return usage();
     } else if (min_frequency >= 256 || min_frequency < 1) {
         std::cerr << "Minimum frequency '-z' must be between 1 and 255." << std::endl;
@@ -167,6 +180,29 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
     kc_output out;
     std::memset(&out, 0, sizeof(out));
     uint64_t bound = 0;
+    if (algorithm == "streaming") {  // src/main.cpp:139-144: header, then Streaming / StreamingFiltered
+        rc = kc_streaming(ctx, &p, &in, &out);
+        if (rc != KC_OK) {
+            std::cerr << "kmercamel compute -a streaming failed: " << kc_strerror(rc) << ": " << kc_last_error(ctx) << std::endl;
+            kc_destroy(ctx);
+            return 1;
+        }
+        std::ofstream output;
+        std::ostream *of = &std::cout;
+        if (!out_path.empty()) {
+            output.open(out_path);
+            of = &output;
+        }
+        write_name(path, k, false, !complements, *of, "streaming");
+        of->write(reinterpret_cast<const char *>(out.ms), (std::streamsize) out.length);
+        *of << std::endl;
+        write_log("Finished masked superstring computation.");
+        kc_destroy(ctx);
+        kc_free(seq);
+        kc_free(rec_off);
+        kc_free(rec_len);
+        return 0;
+    }
     rc = lower_bound ? kc_lower_bound(ctx, &p, &in, &bound, &out) : kc_compute(ctx, &p, &in, &out);
     if (rc == KC_ERR_EMPTY && !assume_simplitigs) {  // src/main.cpp:155-158
         std::cerr << "Path '" << path << "' contains no k-mers. Make sure that your file is a FASTA or gzipped FASTA." << std::endl;
@@ -219,6 +255,258 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
     return 0;
 }
 
+// Reads the file and frames it; returns false after printing the reason.
+static bool load_framed(const std::string &path, std::vector<unsigned char> &data, uint8_t **seq, uint64_t *n_bytes, uint64_t **rec_off,
+                        uint64_t **rec_len, uint64_t *n_recs) {
+    if (!read_all(path, data)) {
+        std::cerr << "couldn't open file " << path << std::endl;
+        return false;
+    }
+    int rc = kc_frame_fasta(data.data(), data.size(), seq, n_bytes, rec_off, rec_len, n_recs);
+    if (rc != KC_OK) {
+        std::cerr << "framing failed: " << kc_strerror(rc) << std::endl;
+        return false;
+    }
+    return true;
+}
+
+// `maskopt` (src/main.cpp:318-376, src/masks.h:240-261): max-one and min-one on the GPU; min-run needs an ILP solver.
+static int camel_optimize(int argc, char **argv) {
+    std::string path;
+    if (argc > 1 && std::string(argv[argc - 1]) != "-h") {
+        path = argv[argc - 1];
+        argc--;
+    }
+    int k = 0, device = 0;
+    std::string out_path, algorithm = "max-one";
+    bool complements = true;
+    int opt;
+    try {
+        while ((opt = getopt(argc, argv, "k:t:o:hug:")) != -1) {
+            switch (opt) {
+                case 'o': out_path = optarg; break;
+                case 'k': k = std::stoi(optarg); break;
+                case 't': algorithm = optarg; break;
+                case 'u': complements = false; break;
+                case 'g': device = std::stoi(optarg); break;
+                case 'h': usage(); return 0;
+                default: return usage();
+            }
+        }
+    } catch (std::exception &) {
+        return usage();
+    }
+    if (algorithm == "maxone") algorithm = "max-one";  // src/main.cpp:109-115
+    if (algorithm == "minone") algorithm = "min-one";
+    if (path.empty()) {
+        std::cerr << "Required positional parameter path to the file not set." << std::endl;
+        return usage();
+    }
+    if (k == 0) {
+        std::cerr << "Required parameter k not set." << std::endl;
+        return usage();
+    } else if (k < 0) {
+        std::cerr << "k must be positive." << std::endl;
+        return usage();
+    } else if (k > MAX_K) {
+        std::cerr << "k > " << MAX_K << " not supported." << std::endl;
+        return usage();
+    }
+    if (algorithm != "max-one" && algorithm != "min-one") {
+        std::cerr << "Algorithm '" + algorithm + "' not recognized by the GPU build (max-one, min-one)." << std::endl;
+        return usage();
+    }
+    write_log("Started optimization of a masked superstring from '" + path + "'.");
+    std::vector<unsigned char> data;
+    uint8_t *seq = nullptr;
+    uint64_t n_bytes = 0, n_recs = 0, *rec_off = nullptr, *rec_len = nullptr;
+    if (!load_framed(path, data, &seq, &n_bytes, &rec_off, &rec_len, &n_recs)) return 1;
+    uint64_t span[5] = {0, 0, 0, 0, 0};
+    kc_fasta_first_header(data.data(), data.size(), span);
+    kc_ctx *ctx = nullptr;
+    int rc = kc_init(device, nullptr, &ctx);
+    if (rc != KC_OK) {
+        std::cerr << "cannot initialise CUDA device " << device << ": " << kc_strerror(rc) << " (this build has no CPU path)" << std::endl;
+        return 1;
+    }
+    const uint64_t len = n_recs ? rec_len[0] : 0;  // ReadMaskedSuperstring: the first record (src/parser.h:145-150)
+    kc_output out;
+    std::memset(&out, 0, sizeof(out));
+    rc = kc_maskopt(ctx, seq + (n_recs ? rec_off[0] : 0), len, k, complements ? 1 : 0, algorithm == "min-one" ? 1 : 0, &out);
+    if (rc != KC_OK) {
+        std::cerr << "kmercamel maskopt failed: " << kc_strerror(rc) << ": " << kc_last_error(ctx) << std::endl;
+        kc_destroy(ctx);
+        return 1;
+    }
+    std::ofstream output;
+    std::ostream *of = &std::cout;
+    if (!out_path.empty()) {
+        output.open(out_path);
+        of = &output;
+    }
+    *of << ">";  // ReprintSequenceHeader, src/masks.h:27-37
+    of->write(reinterpret_cast<const char *>(data.data() + span[0]), (std::streamsize) span[1]);
+    *of << " reoptimized=" << algorithm;
+    if (span[2]) {
+        *of << " ";
+        of->write(reinterpret_cast<const char *>(data.data() + span[3]), (std::streamsize) span[4]);
+    }
+    *of << std::endl;
+    of->write(reinterpret_cast<const char *>(out.ms), (std::streamsize) out.length);
+    *of << std::endl;
+    if (len >= (uint64_t) k && out.ms[len - k] > 'Z')  // src/masks.h:63-66 mask convention
+        std::cerr << "Warning: the mask after optimization violates the mask convention as there are more than k-1 trailing zeros "
+                     "(more than k-1 trailing lowercase characters)." << std::endl;
+    kc_destroy(ctx);
+    if (n_recs > 1) {  // AssertEOF, src/masks.h:258 (the reference throws after having written the output)
+        std::cerr << "Expecting only a single FASTA record -- the masked superstring." << std::endl;
+        return 1;
+    }
+    write_log("Finished optimization.");
+    kc_free(seq);
+    kc_free(rec_off);
+    kc_free(rec_len);
+    return 0;
+}
+
+// The four text conversions (src/main.cpp:444-667): host only.
+static int camel_convert(const std::string &sub, int argc, char **argv) {
+    const bool has_path = sub != "mssep2ms";
+    std::string path;
+    if (has_path && argc > 1 && std::string(argv[argc - 1]) != "-h") {
+        path = argv[argc - 1];
+        argc--;
+    }
+    std::string out_path, mask_path, sup_path;
+    int k = 0, opt;
+    const bool needs_k = sub == "ms2spss" || sub == "spss2ms";
+    try {
+        while ((opt = getopt(argc, argv, needs_k ? "o:k:h" : (sub == "ms2mssep" ? "m:s:h" : "m:s:o:h"))) != -1) {
+            switch (opt) {
+                case 'o': out_path = optarg; break;
+                case 'k': k = std::stoi(optarg); break;
+                case 'm':
+                    if (!mask_path.empty()) {
+                        std::cerr << "Error: -m parameter provided multiple times" << std::endl;
+                        return usage();
+                    }
+                    mask_path = optarg;
+                    break;
+                case 's':
+                    if (!sup_path.empty()) {
+                        std::cerr << "Error: -s parameter provided multiple times" << std::endl;
+                        return usage();
+                    }
+                    sup_path = optarg;
+                    break;
+                case 'h': usage(); return 0;
+                default: return usage();
+            }
+        }
+    } catch (std::exception &) {
+        return usage();
+    }
+    if (has_path && path.empty()) {
+        std::cerr << "Required positional parameter path to the file not set." << std::endl;
+        return usage();
+    }
+    if (needs_k && k == 0) {
+        std::cerr << "Required parameter k not set." << std::endl;
+        return usage();
+    } else if (needs_k && k < 0) {
+        std::cerr << "k must be positive." << std::endl;
+        return usage();
+    }
+    std::ofstream output;
+    std::ostream *of = &std::cout;
+    if (!out_path.empty()) {
+        output.open(out_path);
+        of = &output;
+    }
+    if (sub == "mssep2ms") {
+        if (mask_path.empty() && sup_path.empty()) {
+            std::cerr << "Cannot have both superstring and mask redirected from stdin." << std::endl;
+            return usage();
+        }
+        write_log("Started masked superstring joining.");
+        std::ifstream mf, sf;
+        std::istream *maskf = &std::cin, *supf = &std::cin;
+        if (!mask_path.empty()) {
+            mf.open(mask_path);
+            maskf = &mf;
+        }
+        if (!sup_path.empty()) {
+            sf.open(sup_path);
+            supf = &sf;
+        }
+        std::string superstring, mask;  // join_ms reads one white-space delimited token from each (src/conversions.h:36-38)
+        *supf >> superstring;
+        *maskf >> mask;
+        uint8_t *joined = nullptr;
+        uint64_t n = 0;
+        if (kc_join_ms(reinterpret_cast<const uint8_t *>(superstring.data()), superstring.size(),
+                       reinterpret_cast<const uint8_t *>(mask.data()), mask.size(), &joined, &n) != KC_OK) return 1;
+        *of << ">superstring" << std::endl;
+        of->write(reinterpret_cast<const char *>(joined), (std::streamsize) n);
+        *of << std::endl;
+        kc_free(joined);
+        write_log("Finished masked superstring joining.");
+        return 0;
+    }
+    if (sub == "ms2mssep" && mask_path.empty()) {
+        // src/main.cpp:476-480,493-496: the reference never records that -s was given, so -m is what it insists on
+        std::cerr << "Cannot have both superstring and mask redirected to stdout." << std::endl;
+        return usage();
+    }
+    if (sub == "ms2mssep") write_log("Started splitting masked superstring '" + path + "'.");
+    else if (sub == "ms2spss") write_log("Started rSPSS computation from masked supertring '" + path + "'.");
+    else write_log("Started masked superstring computation corresponding to (r)SPSS '" + path + "'.");
+    std::vector<unsigned char> data;
+    uint8_t *seq = nullptr;
+    uint64_t n_bytes = 0, n_recs = 0, *rec_off = nullptr, *rec_len = nullptr;
+    if (!load_framed(path, data, &seq, &n_bytes, &rec_off, &rec_len, &n_recs)) return 1;
+    const uint8_t *first = seq + (n_recs ? rec_off[0] : 0);
+    const uint64_t first_len = n_recs ? rec_len[0] : 0;
+    if (sub == "ms2mssep") {
+        uint8_t *sup = nullptr, *mask = nullptr;
+        if (kc_split_ms(first, first_len, &sup, &mask) != KC_OK) return 1;
+        std::ofstream mf(mask_path), sf;
+        std::ostream *supf = &std::cout;
+        if (!sup_path.empty()) {
+            sf.open(sup_path);
+            supf = &sf;
+        }
+        mf.write(reinterpret_cast<const char *>(mask), (std::streamsize) first_len);
+        mf << std::endl;
+        supf->write(reinterpret_cast<const char *>(sup), (std::streamsize) first_len);
+        *supf << std::endl;
+        kc_free(sup);
+        kc_free(mask);
+        write_log("Finished masked superstring splitting.");
+    } else if (sub == "ms2spss") {
+        uint8_t *text = nullptr;
+        uint64_t n = 0;
+        if (kc_ms_to_spss(first, first_len, k, &text, &n) != KC_OK) return 1;
+        of->write(reinterpret_cast<const char *>(text), (std::streamsize) n);
+        of->flush();
+        kc_free(text);
+        write_log("Finished computing a rSPSS representing the same set.");
+    } else {
+        uint8_t *ms = nullptr;
+        uint64_t n = 0;
+        if (kc_spss_to_ms(seq, rec_off, rec_len, n_recs, k, &ms, &n) != KC_OK) return 1;
+        *of << ">superstring " << path << std::endl;
+        of->write(reinterpret_cast<const char *>(ms), (std::streamsize) n);
+        *of << std::endl;
+        kc_free(ms);
+        write_log("Finished computing a masked superstring corresponding to the (r)SPSS.");
+    }
+    kc_free(seq);
+    kc_free(rec_off);
+    kc_free(rec_len);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) return usage();
     const std::string sub = argv[1];
@@ -232,6 +520,8 @@ int main(int argc, char **argv) {
     }
     if (sub == "compute") return camel_compute(argc - 1, argv + 1, false);
     if (sub == "lowerbound") return camel_compute(argc - 1, argv + 1, true);
-    std::cerr << "Only the 'compute' and 'lowerbound' sub-commands are implemented by the B200 build." << std::endl;
+    if (sub == "maskopt") return camel_optimize(argc - 1, argv + 1);
+    if (sub == "ms2mssep" || sub == "mssep2ms" || sub == "ms2spss" || sub == "spss2ms") return camel_convert(sub, argc - 1, argv + 1);
+    std::cerr << "Unknown sub-command '" << sub << "'." << std::endl;
     return usage();
 }

@@ -8,6 +8,9 @@
  *     Global / GlobalSparse                src/global.h:218, src/global_sparse.h:211  -> kc_compute (all stages)
  *     OverlapHamiltonianPath[Sparse]       src/global.h:43, src/global_sparse.h:42     -> kc_overlap_path
  *     kseq_read loop                       src/kseq.h:182-224, src/parser.h:106-118    -> kc_frame_fasta (host only)
+ *     Streaming / StreamingFiltered        src/streaming.h:12-107                      -> kc_streaming
+ *     Optimize (max-one, min-one)          src/masks.h:240-261                         -> kc_maskopt
+ *     split_ms / join_ms / ms_to_spss / spss_to_ms   src/conversions.h:16-91          -> kc_split_ms ... (host only)
  *
  * Conventions: plain C types only; every function returns 0 (KC_OK) or a negative KC_ERR_* code and never throws;
  * one context per process and GPU; calls are synchronous and not thread-safe per context.  There is no CPU
@@ -92,6 +95,37 @@ int kc_compute_device(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_ou
  * (sum of node lengths - sum of accepted overlaps) per strand.  Host buffers as kc_compute; want_maxone must be 0.
  * `stats` (may be NULL) receives the counters and stage times, no superstring. */
 int kc_lower_bound(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t *lower_bound, kc_output *stats);
+
+/* ---- neighbours of the compute path, same conventions as kc_compute (host buffers, pinned result) ---------
+ *
+ * kc_streaming   `compute -a streaming [-z Z]` (reference src/main.cpp:139-144, Streaming / StreamingFiltered
+ *                src/streaming.h:12-107): out->ms = the masked superstring of the one-pass algorithm (the Z-th occurrence
+ *                of every k-mer with at least Z occurrences is ON, the k-1 characters after an ON window are kept in
+ *                lower case, everything else is dropped); out->n_kmers = k-mers turned ON.  assume_simplitigs and
+ *                want_maxone must be 0.  An input without k-mers gives length 0 (the reference prints an empty line).
+ * kc_maskopt     `maskopt -t max-one | min-one` (src/main.cpp:318-376, Optimize / OptimizeOnes src/masks.h:40-78,240-261):
+ *                ms = the sequence of the single record (n letters, ACGTacgt only, else KC_ERR_BAD_SEQ); out->ms = the same
+ *                letters with the mask that maximises (minimize = 0) or minimises (1) the number of ones while representing
+ *                the same k-mer set; out->n_kmers = size of that set.  `-t min-run` needs an ILP solver (GLPK in the
+ *                reference) and is not provided. */
+int kc_streaming(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *out);
+int kc_maskopt(kc_ctx *ctx, const uint8_t *ms, uint64_t n, int k, int complements, int minimize, kc_output *out);
+
+/* Host-only text conversions (reference src/conversions.h:16-91; sub-commands ms2mssep, mssep2ms, ms2spss, spss2ms).
+ * Outputs are malloc'ed (NUL-terminated for convenience); release each with kc_free.
+ *   kc_split_ms    superstring in upper case + mask as '0'/'1' characters, n bytes each (split_ms, :16-33)
+ *   kc_join_ms     letter i of the superstring in the case given by mask[i] == '1' (join_ms, :35-44)
+ *   kc_ms_to_spss  the complete FASTA text of the rSPSS (ms_to_spss, :46-72)
+ *   kc_spss_to_ms  the masked superstring of framed records (kc_frame_fasta layout): last k-1 letters of each record OFF,
+ *                  records shorter than k skipped (spss_to_ms, :74-91)
+ *   kc_fasta_first_header  span = {name_off, name_len, has_comment, comment_off, comment_len} of the first record, as
+ *                  kseq parses the header line (src/kseq.h:187-194); used to reprint it (src/masks.h:27-37). */
+int kc_split_ms(const uint8_t *ms, uint64_t n, uint8_t **superstring, uint8_t **mask);
+int kc_join_ms(const uint8_t *superstring, uint64_t n_s, const uint8_t *mask, uint64_t n_m, uint8_t **out, uint64_t *n_out);
+int kc_ms_to_spss(const uint8_t *ms, uint64_t n, int k, uint8_t **out, uint64_t *n_out);
+int kc_spss_to_ms(const uint8_t *seq, const uint64_t *rec_off, const uint64_t *rec_len, uint64_t n_recs, int k, uint8_t **out,
+                  uint64_t *n_out);
+int kc_fasta_first_header(const uint8_t *data, uint64_t n, uint64_t *span);
 
 /* Copy n bytes of a kc_compute_device result (or any device buffer) to host memory on the context stream. */
 int kc_copy_to_host(kc_ctx *ctx, void *dst_host, const void *src_device, uint64_t n);

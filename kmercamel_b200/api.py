@@ -71,6 +71,13 @@ def load_library():
     L.kc_compute_device.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.POINTER(kc_output)]
     L.kc_lower_bound.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), u64p, C.POINTER(kc_output)]
     L.kc_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.kc_streaming.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.POINTER(kc_output)]
+    L.kc_maskopt.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(kc_output)]
+    L.kc_split_ms.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(u8p), C.POINTER(u8p)]
+    L.kc_join_ms.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(u8p), u64p]
+    L.kc_ms_to_spss.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.POINTER(u8p), u64p]
+    L.kc_spss_to_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(u8p), u64p]
+    L.kc_fasta_first_header.argtypes = [C.c_char_p, C.c_uint64, u64p]
     L.kc_count_kmers.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.POINTER(u64p), C.POINTER(u8p),
                                  u64p]
     L.kc_overlap_path.argtypes = [C.c_void_p, u64p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, i64p, u8p]
@@ -109,6 +116,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ["kc_init", "kc_destroy", "kc_compute", "kc_compute_device", "kc_lower_bound", "kc_copy_to_host", "kc_count_kmers", "kc_overlap_path",
                     "kc_p2p_alloc", "kc_p2p_open", "kc_p2p_hist", "kc_p2p_scatter", "kc_p2p_resolve", "kc_total_launches", "kc_shard_granule", "kc_shard_partition", "kc_shard_resolve", "kc_compute_from_flags",
+                    "kc_streaming", "kc_maskopt", "kc_split_ms", "kc_join_ms", "kc_ms_to_spss", "kc_spss_to_ms", "kc_fasta_first_header",
                     "kc_frame_fasta", "kc_set_option", "kc_get_stat", "kc_profile_enable", "kc_profile_count", "kc_profile_get", "kc_profile_reset",
                     "kc_limbs_for_k", "kc_free", "kc_strerror", "kc_last_error"]
 
@@ -141,6 +149,61 @@ def frame_fasta_file(path: str):
     if data[:2] == b"\x1f\x8b":
         data = gzip.decompress(data)
     return frame_fasta(data)
+
+
+# ---- host-only text conversions (reference src/conversions.h) -------------------------------------------------------
+def split_ms(ms: bytes):
+    """`ms2mssep` (src/conversions.h:16-33) -> (superstring in upper case, mask as b'0'/b'1' characters)."""
+    L = load_library()
+    sup, mask = u8p(), u8p()
+    rc = L.kc_split_ms(ms, len(ms), C.byref(sup), C.byref(mask))
+    if rc != 0:
+        raise KcError(rc)
+    return _take(sup, len(ms), np.uint8).tobytes(), _take(mask, len(ms), np.uint8).tobytes()
+
+
+def join_ms(superstring: bytes, mask: bytes) -> bytes:
+    """`mssep2ms` (src/conversions.h:35-44): the sequence line."""
+    L = load_library()
+    out, n = u8p(), C.c_uint64()
+    rc = L.kc_join_ms(superstring, len(superstring), mask, len(mask), C.byref(out), C.byref(n))
+    if rc != 0:
+        raise KcError(rc)
+    return _take(out, n.value, np.uint8).tobytes()
+
+
+def ms_to_spss(ms: bytes, k: int) -> bytes:
+    """`ms2spss` (src/conversions.h:46-72): the complete FASTA text."""
+    L = load_library()
+    out, n = u8p(), C.c_uint64()
+    rc = L.kc_ms_to_spss(ms, len(ms), k, C.byref(out), C.byref(n))
+    if rc != 0:
+        raise KcError(rc)
+    return _take(out, n.value, np.uint8).tobytes()
+
+
+def spss_to_ms(seq, rec_off, rec_len, k: int) -> bytes:
+    """`spss2ms` (src/conversions.h:74-91) on framed records: the sequence line."""
+    L = load_library()
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+    rec_len = np.ascontiguousarray(rec_len, dtype=np.uint64)
+    out, n = u8p(), C.c_uint64()
+    rc = L.kc_spss_to_ms(seq.ctypes.data, rec_off.ctypes.data, rec_len.ctypes.data, len(rec_off), k, C.byref(out), C.byref(n))
+    if rc != 0:
+        raise KcError(rc)
+    return _take(out, n.value, np.uint8).tobytes()
+
+
+def fasta_first_header(data: bytes):
+    """-> (name, comment | None) of the first record as kseq parses the header line."""
+    L = load_library()
+    span = (C.c_uint64 * 5)()
+    rc = L.kc_fasta_first_header(data, len(data), span)
+    if rc != 0:
+        raise KcError(rc)
+    name = data[span[0]:span[0] + span[1]]
+    return name, (data[span[3]:span[3] + span[4]] if span[2] else None)
 
 
 @dataclass
@@ -226,6 +289,21 @@ class Context:
         lb = C.c_uint64()
         self._check(self._lib.kc_lower_bound(self._h, C.byref(p), C.byref(inp), C.byref(lb), C.byref(out)))
         return lb.value, self._result(out, False)
+
+    def streaming(self, seq, *, k, complements=True, min_frequency=1) -> ComputeResult:
+        """`kmercamel compute -a streaming [-z]` (reference src/streaming.h:12-107) on framed host buffers."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        p = self._params(k, complements, min_frequency, False, False)
+        inp = kc_input(seq.ctypes.data, seq.size, None, None, 0)
+        out = kc_output()
+        self._check(self._lib.kc_streaming(self._h, C.byref(p), C.byref(inp), C.byref(out)))
+        return self._result(out, True)
+
+    def maskopt(self, ms: bytes, *, k, complements=True, minimize=False) -> ComputeResult:
+        """`kmercamel maskopt -t max-one|min-one` (reference src/masks.h:40-78,240-261) on one record's sequence."""
+        out = kc_output()
+        self._check(self._lib.kc_maskopt(self._h, ms, len(ms), int(k), int(bool(complements)), int(bool(minimize)), C.byref(out)))
+        return self._result(out, True)
 
     def compute_device(self, seq_ptr: int, n_bytes: int, rec_off_ptr: int = 0, rec_len_ptr: int = 0, n_recs: int = 0, *, k,
                        complements=True, min_frequency=1, assume_simplitigs=False, want_maxone=False) -> ComputeResult:

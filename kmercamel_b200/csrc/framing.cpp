@@ -6,6 +6,7 @@
 // never span records on the GPU), plus the offset and length of every record.
 #include "../../include/kcgpu.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -113,4 +114,123 @@ extern "C" int kc_frame_fasta(const uint8_t *data, uint64_t n, uint8_t **seq_out
     } catch (const std::bad_alloc &) {
         return KC_ERR_OOM;
     }
+}
+
+// ---- masked-superstring text conversions (reference src/conversions.h; host only) ----------------------
+namespace {
+inline bool ms_is_upper(uint8_t c) { return c <= 'Z'; }                                         // src/conversions.h:6-8
+inline uint8_t ms_to_upper(uint8_t c) { return ms_is_upper(c) ? c : (uint8_t) (c - ('a' - 'A')); }  // :10-14
+inline uint8_t ms_masked(uint8_t c, bool mask) {                                                // src/kmers.h:124-127
+    const int d = (int) (c <= 'Z') - (int) mask;
+    return (uint8_t) (c + d * ('a' - 'A'));
+}
+int give(const std::vector<uint8_t> &v, uint8_t **out, uint64_t *n_out) {
+    *out = (uint8_t *) std::malloc(v.size() + 1);
+    if (!*out) return KC_ERR_OOM;
+    if (!v.empty()) std::memcpy(*out, v.data(), v.size());
+    (*out)[v.size()] = 0;
+    *n_out = v.size();
+    return KC_OK;
+}
+}  // namespace
+
+// split_ms, src/conversions.h:16-33: mask as '0'/'1' characters, superstring in upper case (no newlines added here).
+extern "C" int kc_split_ms(const uint8_t *ms, uint64_t n, uint8_t **superstring, uint8_t **mask) {
+    if ((!ms && n) || !superstring || !mask) return KC_ERR_ARG;
+    *superstring = (uint8_t *) std::malloc(n + 1);
+    *mask = (uint8_t *) std::malloc(n + 1);
+    if (!*superstring || !*mask) return KC_ERR_OOM;
+    for (uint64_t i = 0; i < n; ++i) {
+        (*mask)[i] = ms_is_upper(ms[i]) ? '1' : '0';
+        (*superstring)[i] = ms_to_upper(ms[i]);
+    }
+    (*superstring)[n] = (*mask)[n] = 0;
+    return KC_OK;
+}
+
+// join_ms, src/conversions.h:35-44 (the text after ">superstring\n"): a missing mask character counts as '0'.
+extern "C" int kc_join_ms(const uint8_t *superstring, uint64_t n_s, const uint8_t *mask, uint64_t n_m, uint8_t **out, uint64_t *n_out) {
+    if ((!superstring && n_s) || (!mask && n_m) || !out || !n_out) return KC_ERR_ARG;
+    try {
+        std::vector<uint8_t> v(n_s);
+        for (uint64_t i = 0; i < n_s; ++i) v[i] = ms_masked(superstring[i], i < n_m && mask[i] == '1');
+        return give(v, out, n_out);
+    } catch (const std::bad_alloc &) {
+        return KC_ERR_OOM;
+    }
+}
+
+// ms_to_spss, src/conversions.h:46-72: the complete FASTA text.  Each maximal run of upper-case letters plus the k-1
+// letters after it (upper-cased, clipped at the end) is one record ">i"; a run that reaches the end of the superstring
+// is left without its newline, exactly as the reference prints it.
+extern "C" int kc_ms_to_spss(const uint8_t *ms, uint64_t n, int k, uint8_t **out, uint64_t *n_out) {
+    if ((!ms && n) || !out || !n_out || k < 1) return KC_ERR_ARG;
+    try {
+        std::vector<uint8_t> v;
+        v.reserve(n + n / 8 + 64);
+        bool masked = false;
+        uint64_t counter = 0;
+        char num[32];
+        for (uint64_t i = 0; i < n; ++i) {
+            if (ms_is_upper(ms[i])) {
+                if (!masked) {
+                    const int w = std::snprintf(num, sizeof(num), ">%llu\n", (unsigned long long) counter++);
+                    v.insert(v.end(), num, num + w);
+                }
+                masked = true;
+                v.push_back(ms[i]);
+            } else {
+                if (!masked) continue;
+                masked = false;
+                for (int j = 0; j < k - 1; ++j)
+                    if (i + (uint64_t) j < n) v.push_back(ms_to_upper(ms[i + j]));
+                v.push_back('\n');
+            }
+        }
+        return give(v, out, n_out);
+    } catch (const std::bad_alloc &) {
+        return KC_ERR_OOM;
+    }
+}
+
+// spss_to_ms, src/conversions.h:74-91 (the text after the header line): records shorter than k are skipped, the last
+// k-1 letters of every record are OFF.
+extern "C" int kc_spss_to_ms(const uint8_t *seq, const uint64_t *rec_off, const uint64_t *rec_len, uint64_t n_recs, int k, uint8_t **out,
+                             uint64_t *n_out) {
+    if (!out || !n_out || k < 1 || (n_recs && (!seq || !rec_off || !rec_len))) return KC_ERR_ARG;
+    try {
+        std::vector<uint8_t> v;
+        for (uint64_t r = 0; r < n_recs; ++r) {
+            const uint64_t l = rec_len[r];
+            if (l < (uint64_t) k) continue;
+            const uint8_t *s = seq + rec_off[r];
+            for (uint64_t i = 0; i < l; ++i) v.push_back(ms_masked(s[i], i + (uint64_t) k <= l));
+        }
+        return give(v, out, n_out);
+    } catch (const std::bad_alloc &) {
+        return KC_ERR_OOM;
+    }
+}
+
+// Name and comment of the FIRST record as kseq_read parses them (src/kseq.h:187-194), for ReprintSequenceHeader
+// (src/masks.h:27-37).  span = {name_off, name_len, has_comment, comment_off, comment_len}; all zero without a record.
+extern "C" int kc_fasta_first_header(const uint8_t *data, uint64_t n, uint64_t *span) {
+    if ((!data && n) || !span) return KC_ERR_ARG;
+    for (int i = 0; i < 5; ++i) span[i] = 0;
+    uint64_t p = 0;
+    while (p < n && data[p] != '>' && data[p] != '@') ++p;
+    if (p >= n) return KC_OK;
+    ++p;
+    span[0] = p;
+    while (p < n && !kseq_isspace(data[p])) ++p;
+    span[1] = p - span[0];
+    if (p >= n || data[p] == '\n') return KC_OK;
+    ++p;  // the delimiter
+    span[2] = 1;
+    span[3] = p;
+    const uint8_t *nl = p < n ? (const uint8_t *) std::memchr(data + p, '\n', n - p) : nullptr;
+    uint64_t end = nl ? (uint64_t) (nl - data) : n;
+    if (end - p > 1 && data[end - 1] == '\r') --end;
+    span[4] = end - p;
+    return KC_OK;
 }

@@ -8,6 +8,7 @@
 #include "kmerset.cuh"
 #include "kmerset_fast.cuh"
 #include "kword.cuh"
+#include "masks.cuh"
 #include "runs.cuh"
 #include "sort.cuh"
 #include "stage1.cuh"
@@ -592,6 +593,89 @@ int kc_lower_bound(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t
         stats->n_launches = ex.launches;
         fill_times(ctx, stats);
     }
+    ctx->total_launches += ex.launches;
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
+// device result -> the context's pinned host buffer
+static u8 *copy_result_to_pinned(kc_ctx *ctx, const u8 *dev, u64 n) {
+    const size_t need = (size_t) n + 64;
+    if (ctx->pin_out_cap < need) {
+        if (ctx->pin_out) KC_CUDA(cudaFreeHost(ctx->pin_out));
+        ctx->pin_out = nullptr;
+        ctx->pin_out_cap = 0;
+        KC_CUDA(cudaMallocHost(&ctx->pin_out, need + need / 8));
+        ctx->pin_out_cap = need + need / 8;
+    }
+    if (n) KC_CUDA(cudaMemcpyAsync(ctx->pin_out, dev, n, cudaMemcpyDeviceToHost, ctx->stream));
+    KC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ctx->pin_out;
+}
+
+int kc_streaming(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *out) {
+    if (!ctx || !in || !out) return KC_ERR_ARG;
+    KC_API_BEGIN
+    check_params(p);
+    if (p->assume_simplitigs || p->want_maxone) KC_THROW(KC_ERR_ARG, "-S and -M belong to the greedy algorithm");  // src/main.cpp:296-301
+    if (in->n_bytes >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 sequence bytes on one GPU");
+    KC_CUDA(cudaSetDevice(ctx->device));
+    const int limbs = kc_limbs_for_k(p->k);
+    ensure_arena(ctx, estimate_arena(in->n_bytes, 0, limbs, false, true, false, &ctx->fast));
+    ctx->arena.reset();
+    CudaExec ex{ctx->stream, &ctx->arena};
+    ex.prof = &ctx->prof;
+    std::memset(out, 0, sizeof(*out));
+    KC_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    const u64 padded = (in->n_bytes + 31) / 32 * 32 + 64;
+    u8 *d_seq = ex.alloc<u8>(padded);
+    ex.fill_bytes(d_seq + (in->n_bytes & ~(u64) 31), '\n', padded - (in->n_bytes & ~(u64) 31));
+    KC_CUDA(cudaMemcpyAsync(d_seq, in->seq, in->n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    KC_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    StreamingResult r;
+    const bool compl_ = p->complements != 0;
+    if (limbs == 1) r = kc_streaming_run<1>(ex, d_seq, in->n_bytes, p->k, compl_, p->min_frequency, ctx->fast, &ctx->fast_runs, &ctx->fast_fallbacks);
+    else if (limbs == 2) r = kc_streaming_run<2>(ex, d_seq, in->n_bytes, p->k, compl_, p->min_frequency, ctx->fast, &ctx->fast_runs, &ctx->fast_fallbacks);
+    else r = kc_streaming_run<4>(ex, d_seq, in->n_bytes, p->k, compl_, p->min_frequency, ctx->fast, &ctx->fast_runs, &ctx->fast_fallbacks);
+    for (int i = 2; i <= 4; ++i) KC_CUDA(cudaEventRecord(ctx->ev[i], ctx->stream));
+    out->ms = copy_result_to_pinned(ctx, r.ms, r.length);
+    out->length = r.length;
+    out->n_kmers = r.n_kept;
+    out->n_occurrences = r.n_occ;
+    out->n_launches = ex.launches;
+    fill_times(ctx, out);
+    ctx->total_launches += ex.launches;
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
+int kc_maskopt(kc_ctx *ctx, const uint8_t *ms, uint64_t n, int k, int complements, int minimize, kc_output *out) {
+    if (!ctx || (!ms && n) || !out) return KC_ERR_ARG;
+    KC_API_BEGIN
+    if (k < 1 || k > 127) KC_THROW(KC_ERR_ARG, "k must be in 1..127");
+    if (n + 1 >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 sequence bytes on one GPU");
+    KC_CUDA(cudaSetDevice(ctx->device));
+    const int limbs = kc_limbs_for_k(k);
+    ensure_arena(ctx, estimate_arena(n + 1, 0, limbs, false, true) + 2 * n);
+    ctx->arena.reset();
+    CudaExec ex{ctx->stream, &ctx->arena};
+    ex.prof = &ctx->prof;
+    std::memset(out, 0, sizeof(*out));
+    KC_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    u8 *d_seq = ex.alloc<u8>(n + 64);
+    ex.fill_bytes(d_seq + (n & ~(u64) 31), '\n', n + 64 - (n & ~(u64) 31));
+    if (n) KC_CUDA(cudaMemcpyAsync(d_seq, ms, n, cudaMemcpyHostToDevice, ctx->stream));
+    KC_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    MaskoptResult r;
+    if (limbs == 1) r = kc_maskopt_run<1>(ex, d_seq, n, k, complements != 0, minimize != 0);
+    else if (limbs == 2) r = kc_maskopt_run<2>(ex, d_seq, n, k, complements != 0, minimize != 0);
+    else r = kc_maskopt_run<4>(ex, d_seq, n, k, complements != 0, minimize != 0);
+    for (int i = 2; i <= 4; ++i) KC_CUDA(cudaEventRecord(ctx->ev[i], ctx->stream));
+    out->ms = copy_result_to_pinned(ctx, r.ms, r.length);
+    out->length = r.length;
+    out->n_kmers = r.n_kmers;
+    out->n_launches = ex.launches;
+    fill_times(ctx, out);
     ctx->total_launches += ex.launches;
     return KC_OK;
     KC_API_END(ctx)

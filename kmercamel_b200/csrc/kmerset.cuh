@@ -119,6 +119,13 @@ KC_D u32 kc_strip_emit_mask(const u32 *vm, int widx, int k) {
     return em;
 }
 
+// Optional window filter (maskopt, src/parser.h:41-42 case_sensitive): win_mask is a bit array over window END positions
+// (bit p & 31 of word p >> 5, padded to whole extraction tiles); only windows whose bit is set are emitted.
+KC_D u32 kc_strip_window_filter(const u32 *__restrict__ win_mask, i64 block_pos0) {
+    if (!win_mask) return 0xFFFFFFFFu;
+    return __brev(win_mask[(block_pos0 >> 5) + threadIdx.x]);  // strip base j <-> em bit 31 - j
+}
+
 // f(j, canonical k-mer) for every valid window ending at base j of the strip (src/parser.h:38-46).
 template <int L, class F> KC_D void kc_strip_windows(const u64 *pk, int widx, u32 em, int k, int complements, F &&f) {
     if (!em) return;
@@ -197,7 +204,8 @@ template <int L> KC_D KWord<L> kmer_scramble(const KWord<L> &x) {
 // ---- level 0 -------------------------------------------------------------------------------------------------------
 template <int L, bool SCR>
 __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ks_hist0_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int complements,
-                                                                            int shift, int bits, u32 *hist, u16 *tile_hist, u32 tile0) {
+                                                                            int shift, int bits, u32 *hist, u16 *tile_hist, u32 tile0,
+                                                                            const u32 *__restrict__ win_mask = nullptr) {
     constexpr int T = KsCfg<L>::EX_THREADS;
     __shared__ u64 pk[KC_EX_HALO + T];
     __shared__ u32 vm[KC_EX_HALO + T];
@@ -207,7 +215,7 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ks_hist0_kernel(const
     for (int i = threadIdx.x; i < 256; i += T) sh[i] = 0;
     __syncthreads();
     const int widx = KC_EX_HALO + threadIdx.x;
-    const u32 em = kc_strip_emit_mask(vm, widx, k);
+    const u32 em = kc_strip_emit_mask(vm, widx, k) & kc_strip_window_filter(win_mask, block_pos0);
     kc_strip_windows<L>(pk, widx, em, k, complements, [&](int, const KWord<L> &c0) {
         const KWord<L> c = SCR ? kmer_scramble(c0) : c0;
         atomicAdd(&sh[c.digit(shift, bits)], 1u);
@@ -266,7 +274,8 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ks_scatter0_kernel(co
                                                                                int shift, int bits, u64 *cursor, const u16 *__restrict__ tile_hist,
                                                                                KWord<L> *__restrict__ keys, u32 *__restrict__ pos, u32 tile0,
                                                                                KWord<L> *const *__restrict__ dst_k = nullptr,
-                                                                               u32 *const *__restrict__ dst_p = nullptr) {
+                                                                               u32 *const *__restrict__ dst_p = nullptr,
+                                                                               const u32 *__restrict__ win_mask = nullptr) {
     constexpr int T = KsCfg<L>::EX_THREADS;
     constexpr int R = 256 / T;
     constexpr int TILE = KsCfg<L>::EX_TILE;
@@ -284,7 +293,7 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ks_scatter0_kernel(co
     for (int i = threadIdx.x; i < 256; i += T) cnt[i] = 0;
     __syncthreads();
     const int widx = KC_EX_HALO + threadIdx.x;
-    const u32 em = kc_strip_emit_mask(vm, widx, k);
+    const u32 em = kc_strip_emit_mask(vm, widx, k) & kc_strip_window_filter(win_mask, block_pos0);
     // digit counts of the tile, left behind by kc_ks_hist0_kernel
     u32 total;
     {
@@ -912,7 +921,7 @@ template <int L> struct KmerSet {
 
 template <int L, bool PAY, bool KEYS>
 KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, int min_freq, u32 *flags,
-                                 u64 *ext_kept_cell, KsShard *shard = nullptr) {
+                                 u64 *ext_kept_cell, KsShard *shard = nullptr, const u32 *win_mask = nullptr) {
     typedef KsCfg<L> Cfg;
     KmerSet<L> res;
     const int mode = shard ? shard->mode : KS_WHOLE;
@@ -977,7 +986,7 @@ KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k
         {
             CudaExec::Scope sc(ex, KP_KS_HIST0, pos_end - pos_begin);
             kc_ks_hist0_kernel<L, SCRAMBLE><<<ex_blocks, Cfg::EX_THREADS, 0, st>>>(seq, n_bytes, k, complements ? 1 : 0, shift0, bits0, hist, tile_hist,
-                                                                                   tile0);
+                                                                                   tile0, win_mask);
         }
         ++ex.launches;
         kc_ks_scan0_kernel<<<1, 256, 0, st>>>(hist, cursor, big_a, big_cap, small, small_cap, uniform, uniform_cap, ctr, cells, cap, Cfg::TILE,
@@ -1073,7 +1082,8 @@ KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k
         {
             CudaExec::Scope sc(ex, KP_KS_SCATTER0, (pos_end - pos_begin) + M * (sizeof(KWord<L>) + (PAY ? 4 : 0)));
             kc_ks_scatter0_kernel<L, PAY, SCRAMBLE><<<ex_blocks, Cfg::EX_THREADS, scatter0_smem, st>>>(seq, n_bytes, k, complements ? 1 : 0, shift0,
-                                                                                                   bits0, cursor, tile_hist, k0, p0, tile0);
+                                                                                                   bits0, cursor, tile_hist, k0, p0, tile0, nullptr,
+                                                                                                   nullptr, win_mask);
         }
         ++ex.launches;
         KC_CUDA(cudaGetLastError());
@@ -1213,7 +1223,11 @@ KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k
 
 template <int L>
 KmerSet<L> kc_kmerset_build(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, int min_freq, u32 *flags, bool want_keys,
-                            u64 *ext_kept_cell = nullptr) {
+                            u64 *ext_kept_cell = nullptr, const u32 *win_mask = nullptr) {
+    if (win_mask) {  // maskopt: the set of the k-mers whose window passes the filter, keys only
+        if (flags || !want_keys) KC_THROW(KC_ERR_INTERNAL, "window filter is KEYS-only");
+        return kc_kmerset_build_impl<L, false, true>(ex, seq, n_bytes, k, complements, min_freq, nullptr, nullptr, nullptr, win_mask);
+    }
     if (flags) {
         if (want_keys) return kc_kmerset_build_impl<L, true, true>(ex, seq, n_bytes, k, complements, min_freq, flags, nullptr);
         return kc_kmerset_build_impl<L, true, false>(ex, seq, n_bytes, k, complements, min_freq, flags, ext_kept_cell);

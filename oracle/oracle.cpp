@@ -434,6 +434,113 @@ int ms_kmers(const uint8_t *ms, uint64_t len, int k, bool complements, uint64_t 
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// `compute -a streaming [-z]`: src/streaming.h:12-48 (Streaming) and :51-107 (StreamingFiltered), restated with one
+// occurrence counter per canonical k-mer.  Streaming stores the k-mer as read and probes both orientations
+// (src/khash_utils.h:98-103 containsKMer), which is the same as one entry per canonical k-mer; StreamingFiltered keeps
+// min(255, occurrences - 1) and turns a window ON when `count + 1 == min_frequency` (:96), i.e. at the z-th occurrence.
+inline uint8_t masked_char(uint8_t c, bool mask) {  // src/kmers.h:124-127
+    const int d = (int) (c <= 'Z') - (int) mask;
+    return (uint8_t) (c + d * ('a' - 'A'));
+}
+
+template <int L>
+int streaming(const uint8_t *seq, const uint64_t *rec_off, const uint64_t *rec_len, uint64_t n_rec, int k, bool complements,
+              int min_frequency, uint8_t **out, uint64_t *len_out) {
+    std::unordered_map<Word<L>, uint32_t, WordHash<L>> seen;  // canonical k-mer -> stored uint8 value (occurrences - 1, saturating)
+    std::vector<uint8_t> of;
+    const Word<L> mask = Word<L>::low_mask(2 * k);
+    for (uint64_t r = 0; r < n_rec; ++r) {
+        const uint8_t *s = seq + rec_off[r];
+        const uint64_t l = rec_len[r];
+        Word<L> kmer;
+        uint64_t first_index = (uint64_t) k - 1;
+        int64_t last_one = -(int64_t) k;
+        for (uint64_t i = 0; i < l + (uint64_t) k - 1; ++i) {
+            int c = 4;
+            if (i < l) c = nucleotide_to_int(s[i]);
+            if (c >= 4) {
+                kmer = Word<L>();
+                first_index = i + (uint64_t) k;
+            }
+            kmer = (kmer.shl(2) | Word<L>((uint64_t) c)) & mask;  // c = 4 spills into the next symbol exactly as in the reference
+            bool on = false;
+            if (i >= first_index) {
+                Word<L> canon = kmer;
+                if (complements) {
+                    const Word<L> rc = reverse_complement(kmer, k);
+                    if (rc < canon) canon = rc;
+                }
+                auto it = seen.find(canon);
+                uint32_t count = 0;
+                if (it != seen.end()) {
+                    count = it->second + 1;
+                    it->second = std::min<uint32_t>(255, count);
+                } else {
+                    seen.emplace(canon, 0u);
+                }
+                on = count + 1 == (uint32_t) min_frequency;
+            }
+            if (on) {
+                of.push_back(masked_char(s[i - k + 1], true));
+                last_one = (int64_t) i;
+            } else if ((int64_t) i <= last_one + k - 1) {
+                of.push_back(masked_char(s[i - k + 1], false));
+            }
+        }
+    }
+    *len_out = of.size();
+    *out = (uint8_t *) std::malloc(of.size() + 1);
+    if (!*out) return -1;
+    if (!of.empty()) std::memcpy(*out, of.data(), of.size());
+    return 0;
+}
+
+// `maskopt -t max-one | min-one`: Optimize (src/masks.h:240-261) = AddKMers(case_sensitive = true) (src/parser.h:22-49)
+// followed by OptimizeOnes (src/masks.h:40-78).  Returns 1 when the superstring holds a non-ACGT letter (the reference
+// throws std::invalid_argument after printing).  out: n letters.
+template <int L>
+int maskopt(const uint8_t *ms, uint64_t n, int k, bool complements, bool minimize, uint8_t *out) {
+    std::unordered_map<Word<L>, uint32_t, WordHash<L>> set;
+    const Word<L> mask = Word<L>::low_mask(2 * k);
+    const int shift = 2 * (k - 1);
+    {   // AddKMers, case sensitive: the window must start with an upper-case letter
+        Word<L> cur, rc;
+        int64_t cur_len = 0;
+        std::vector<uint8_t> upper(n, 0);
+        for (uint64_t i = 0; i < n; ++i) {
+            const int d = nucleotide_to_int(ms[i]);
+            if (d >= 4) {
+                cur = rc = Word<L>();
+                cur_len = 0;
+                continue;
+            }
+            cur = (cur.shl(2) | Word<L>((uint64_t) d)) & mask;
+            rc = rc.shr(2) | Word<L>((uint64_t) (3 ^ d)).shl(shift);
+            upper[i] = ms[i] <= 'Z';
+            if (++cur_len >= k && upper[i - k + 1]) set.emplace((!complements || cur < rc) ? cur : rc, 1u);
+        }
+    }
+    int bad = 0;
+    Word<L> cur, rc;
+    for (uint64_t i = 0; i < n; ++i) {
+        const int d = nucleotide_to_int(ms[i]);
+        if (d >= 4) bad = 1;
+        cur = (cur.shl(2) | Word<L>((uint64_t) d)) & mask;
+        rc = rc.shr(2) | Word<L>((uint64_t) (3 ^ d)).shl(shift);
+        if (i + 1 >= (uint64_t) k) {
+            const Word<L> canon = (!complements || cur < rc) ? cur : rc;
+            auto it = set.find(canon);
+            const bool contained = it != set.end();
+            out[i - k + 1] = masked_char(ms[i - k + 1], contained);
+            if (minimize && contained) set.erase(it);
+        }
+    }
+    for (uint64_t i = n >= (uint64_t) k ? n - k + 1 : n; i < n; ++i) out[i] = masked_char(ms[i], false);
+    return bad;
+}
+
 }  // namespace
 
 #define DISPATCH(k, fn, ...)                                  \
@@ -493,6 +600,15 @@ int orc_compute_from_simplitigs(const uint8_t *seq, const uint64_t *rec_off, con
 int orc_ms_kmers(const uint8_t *ms, uint64_t len, int k, int complements, uint64_t **keys_out, uint64_t *n_out,
                  uint64_t *n_on_out) {
     DISPATCH(k, ms_kmers, ms, len, k, complements != 0, keys_out, n_out, n_on_out);
+}
+
+int orc_streaming(const uint8_t *seq, const uint64_t *rec_off, const uint64_t *rec_len, uint64_t n_rec, int k, int complements,
+                  int min_frequency, uint8_t **out, uint64_t *len_out) {
+    DISPATCH(k, streaming, seq, rec_off, rec_len, n_rec, k, complements != 0, min_frequency, out, len_out);
+}
+
+int orc_maskopt(const uint8_t *ms, uint64_t n, int k, int complements, int minimize, uint8_t *out) {
+    DISPATCH(k, maskopt, ms, n, k, complements != 0, minimize != 0, out);
 }
 
 void orc_free(void *p) { std::free(p); }

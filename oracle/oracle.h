@@ -58,6 +58,15 @@ int orc_compute_from_simplitigs(const uint8_t *seq, const uint64_t *rec_off, con
 int orc_ms_kmers(const uint8_t *ms, uint64_t len, int k, int complements, uint64_t **keys_out, uint64_t *n_out,
                  uint64_t *n_on_out);
 
+/* `compute -a streaming [-z]`, reference src/streaming.h:12-107 over framed records (any bytes; non-ACGT restarts the
+ * window).  out: malloc'ed, *len_out bytes. */
+int orc_streaming(const uint8_t *seq, const uint64_t *rec_off, const uint64_t *rec_len, uint64_t n_rec, int k, int complements,
+                  int min_frequency, uint8_t **out, uint64_t *len_out);
+
+/* `maskopt -t max-one` (minimize = 0) / `-t min-one` (1), reference src/masks.h:40-78,240-261 + src/parser.h:22-49
+ * (case_sensitive).  out: caller buffer of n bytes.  Returns 1 if a non-ACGT letter was seen (the reference throws). */
+int orc_maskopt(const uint8_t *ms, uint64_t n, int k, int complements, int minimize, uint8_t *out);
+
 void orc_free(void *p);
 
 #ifdef __cplusplus

@@ -43,6 +43,8 @@ def lib():
         L.orc_reverse_complement.argtypes = [u64p, C.c_int, u64p]
         L.orc_bit_prefix.argtypes = [u64p, C.c_int, C.c_int, u64p]
         L.orc_bit_suffix.argtypes = [u64p, C.c_int, C.c_int, u64p]
+        L.orc_streaming.argtypes = [u8p, u64p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(u8p), u64p]
+        L.orc_maskopt.argtypes = [u8p, C.c_uint64, C.c_int, C.c_int, C.c_int, u8p]
         L.orc_free.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
@@ -250,6 +252,81 @@ def verify_ms(ms: bytes, k: int, complements: bool, expected_keys) -> bool:
     got, _ = ms_kmers(ms, k, complements)
     exp = np.ascontiguousarray(expected_keys, dtype=np.uint64).reshape(-1, limbs_for_k(k))
     return got.shape == exp.shape and bool(np.array_equal(got, exp))
+
+
+def streaming(seq, rec_off, rec_len, k: int, complements: bool, min_frequency: int = 1) -> bytes:
+    """`kmercamel compute -a streaming [-z]` (reference src/streaming.h:12-107) over framed records -> sequence line."""
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+    rec_len = np.ascontiguousarray(rec_len, dtype=np.uint64)
+    out, n = u8p(), C.c_uint64()
+    rc = lib().orc_streaming(_ptr(seq, u8p), _ptr(rec_off, u64p), _ptr(rec_len, u64p), len(rec_off), k, int(complements),
+                             int(min_frequency), C.byref(out), C.byref(n))
+    assert rc == 0, rc
+    return _take(out, n.value, np.uint8).tobytes()
+
+
+def maskopt(ms: bytes, k: int, complements: bool, minimize: bool) -> bytes:
+    """`kmercamel maskopt -t min-one|max-one` (reference src/masks.h:40-78,240-261) on the sequence of one record."""
+    a = np.frombuffer(ms, dtype=np.uint8).copy() if len(ms) else np.zeros(1, dtype=np.uint8)
+    out = np.zeros(max(len(ms), 1), dtype=np.uint8)
+    rc = lib().orc_maskopt(_ptr(a, u8p), len(ms), k, int(complements), int(minimize), _ptr(out, u8p))
+    if rc != 0:
+        raise ValueError("Masked superstring contains invalid characters.")
+    return out[:len(ms)].tobytes()
+
+
+# reference src/conversions.h, restated in pure Python (small inputs)
+def _is_upper(c: int) -> bool:  # src/conversions.h:6-8
+    return c <= ord("Z")
+
+
+def _masked(c: int, mask: bool) -> int:  # src/kmers.h:124-127
+    return c + (int(c <= ord("Z")) - int(mask)) * 32
+
+
+def split_ms(ms: bytes):
+    """src/conversions.h:16-33 -> (superstring, mask) without the trailing newlines."""
+    return bytes(c if _is_upper(c) else c - 32 for c in ms), bytes(ord("1") if _is_upper(c) else ord("0") for c in ms)
+
+
+def join_ms(superstring: bytes, mask: bytes) -> bytes:
+    """src/conversions.h:35-44, the text after the header line."""
+    return bytes(_masked(c, i < len(mask) and mask[i] == ord("1")) for i, c in enumerate(superstring))
+
+
+def ms_to_spss(ms: bytes, k: int) -> bytes:
+    """src/conversions.h:46-72, the complete output text."""
+    out = bytearray()
+    masked, counter, l = False, 0, len(ms)
+    for i in range(l):
+        if _is_upper(ms[i]):
+            if not masked:
+                out += b">%d\n" % counter
+                counter += 1
+            masked = True
+            out.append(ms[i])
+        else:
+            if not masked:
+                continue
+            masked = False
+            for j in range(k - 1):
+                if i + j < l:
+                    c = ms[i + j]
+                    out.append(c if _is_upper(c) else c - 32)
+            out += b"\n"
+    return bytes(out)
+
+
+def spss_to_ms(records, k: int) -> bytes:
+    """src/conversions.h:74-91, the text after the header line."""
+    out = bytearray()
+    for r in records:
+        l = len(r)
+        if l < k:
+            continue
+        out += bytes(_masked(c, i <= l - k) for i, c in enumerate(r))
+    return bytes(out)
 
 
 def kmer_from_string(s: str, k: int | None = None):
