@@ -235,7 +235,20 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
             }
             chunks[vv] = c;
         }, KP_EMIT, N * 12);
-        const u32 n_chunks = ex.exclusive_scan(chunks, chunks, N + 1);
+        // Few nodes: launch for an upper bound of the chunk count (a node's chunks span at most its characters + 15 bytes of
+        // alignment) and let the surplus work items exit, instead of reading the exact count back.
+        u32 n_chunks = 0;
+        bool bounded = false;
+#ifdef __CUDACC__
+        if constexpr (Exec::is_device) {
+            if (N <= 65536) {
+                bounded = true;
+                ex.exclusive_scan_nosync(chunks, chunks, N + 1);
+                n_chunks = (u32) (total / KC_EMIT_CHUNK + 2 * N + 1);
+            }
+        }
+#endif
+        if (!bounded) n_chunks = ex.exclusive_scan(chunks, chunks, N + 1);
         ex.for_each(N, [=] KC_HD_LAMBDA(u64 vv) {
             u32 v = (u32) vv;
             if (fa[v] != fin_start) return;
@@ -248,6 +261,7 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
         }, KP_EMIT, N * 12);
         ex.for_each((u64) n_chunks * 256, [=] KC_HD_LAMBDA(u64 w) {
             u32 chunk = (u32) (w >> 8), lane = (u32) (w & 255);
+            if (chunk >= chunks[N]) return;  // chunks[N] = the exact number of chunks
             // node owning this chunk: last v with chunks[v] <= chunk (chunks[] is the exclusive prefix, N+1 entries)
             u32 lo = 0, hi = (u32) N;
             while (lo < hi) {

@@ -290,6 +290,33 @@ template <class Exec, int L> struct Engine {
         }
     }
 
+    u32 *small_out = nullptr;  // device status words of a launched kc_small_engine_kernel that have not been checked yet
+    int small_d = 0;
+
+    // Deferred error check + statistics of run_small (synchronises the stream).
+    void check_small() {
+#ifdef __CUDACC__
+        if constexpr (Exec::is_device) {
+            if (!small_out) return;
+            u32 h[8 + 128];
+            ex.read_n(small_out, h, 8 + 128);
+            small_out = nullptr;
+            if (std::getenv("KC_TRACE")) {
+                std::fprintf(stderr, "[kc_trace] small engine: n_s=%llu n_p=%llu levels=%u groups=%u edges=%u ban_rounds=%u bans=%u; clocks per level (* = run):",
+                             (unsigned long long) n_s, (unsigned long long) n_p, h[1], h[2], h[3], h[4], h[5]);
+                for (int dd = small_d; dd >= 0; --dd) std::fprintf(stderr, " d%d=%u%s", dd, h[8 + dd] & 0x7FFFFFFFu, (h[8 + dd] >> 31) ? "*" : "");
+                std::fprintf(stderr, "\n");
+            }
+            if (h[0]) KC_THROW(KC_ERR_INTERNAL, "ban list overflow");
+            stats.levels_run += h[1];
+            stats.groups += h[2];
+            stats.edges += h[3];
+            stats.ban_rounds += h[4];
+            stats.bans += h[5];
+        }
+#endif
+    }
+
     // Runs levels d..0 in one kernel when the free ends fit in shared memory.  Device policy only.
     bool run_small(int d) {
 #ifdef __CUDACC__
@@ -341,21 +368,10 @@ template <class Exec, int L> struct Engine {
             }
             ++ex.launches;
             KC_CUDA(cudaGetLastError());
-            u32 h[8 + 128];
-            KC_CUDA(cudaMemcpyAsync(h, a.out, sizeof(h), cudaMemcpyDeviceToHost, ex.stream));
-            KC_CUDA(cudaStreamSynchronize(ex.stream));
-            if (std::getenv("KC_TRACE")) {
-                std::fprintf(stderr, "[kc_trace] small engine: n_s=%llu n_p=%llu levels=%u groups=%u edges=%u ban_rounds=%u bans=%u; clocks per level (* = run):",
-                             (unsigned long long) n_s, (unsigned long long) n_p, h[1], h[2], h[3], h[4], h[5]);
-                for (int dd = d; dd >= 0; --dd) std::fprintf(stderr, " d%d=%u%s", dd, h[8 + dd] & 0x7FFFFFFFu, (h[8 + dd] >> 31) ? "*" : "");
-                std::fprintf(stderr, "\n");
-            }
-            if (h[0]) KC_THROW(KC_ERR_INTERNAL, "ban list overflow");
-            stats.levels_run += h[1];
-            stats.groups += h[2];
-            stats.edges += h[3];
-            stats.ban_rounds += h[4];
-            stats.bans += h[5];
+            // The status words are read back by check_small() after the caller's next synchronisation point: the kernels of the
+            // emission stage are queued behind this one without a host round trip.
+            small_out = a.out;
+            small_d = d;
             return true;
         }
 #endif

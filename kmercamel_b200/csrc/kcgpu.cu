@@ -337,6 +337,7 @@ void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params
         });
         u64 h[2];
         ex.read_n(reinterpret_cast<const u64 *>(acc), h, 2);
+        eng.check_small();
         const u64 strands = complements ? 2 : 1;
         res.lower_bound = (h[0] * strands - h[1]) / strands;
         KC_CUDA(cudaEventRecord(ctx->ev[4], ex.stream));
@@ -345,8 +346,15 @@ void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params
         res.n_nodes = nv.n;
         return;
     }
-    EmitResult er = kc_emit_superstring<CudaExec, L>(ex, ns, nv, eng.st, uniq, U, p.want_maxone != 0);
+    EmitResult er;
+    try {
+        er = kc_emit_superstring<CudaExec, L>(ex, ns, nv, eng.st, uniq, U, p.want_maxone != 0);
+    } catch (const KcError &) {
+        eng.check_small();  // a failed small-engine run is the cause, report that one
+        throw;
+    }
     KC_CUDA(cudaEventRecord(ctx->ev[4], ex.stream));
+    eng.check_small();  // deferred status of the single-CTA engine kernel: everything above is queued already
     res.ms = er.ms;
     res.maxone = er.maxone;
     res.length = er.length;
@@ -406,6 +414,7 @@ void overlap_only(kc_ctx *ctx, CudaExec &ex, const uint64_t *first, const uint64
     eng.use_small = ctx->small_engine;
     eng.init_state();
     eng.run();
+    eng.check_small();
     std::vector<u32> ef(nv.N);
     KC_CUDA(cudaMemcpyAsync(ef.data(), eng.st.edge_from, (size_t) nv.N * 4, cudaMemcpyDeviceToHost, ex.stream));
     KC_CUDA(cudaMemcpyAsync(overlaps, eng.st.ovl, nv.N, cudaMemcpyDeviceToHost, ex.stream));
@@ -441,6 +450,8 @@ int kc_init(int device, void *stream, kc_ctx **out) {
         for (int i = 0; i < 6; ++i) KC_CUDA(cudaEventCreate(&ctx->ev[i]));
         if (const char *e = std::getenv("KC_FAST_SET")) ctx->fast.enabled = std::atoi(e) != 0;
         if (const char *e = std::getenv("KC_FAST_RESOLVE")) ctx->fast.resolve = std::atoi(e) != 0;
+        if (const char *e = std::getenv("KC_FAST_TILE")) ctx->fast.tile_variant = std::atoi(e);
+        if (const char *e = std::getenv("KC_FAST_SPLIT0")) ctx->fast.split0 = std::atoi(e) != 0;
     } catch (const KcError &e) {
         int code = e.code;
         kc_destroy(ctx);
@@ -1053,6 +1064,14 @@ int kc_set_option(kc_ctx *ctx, const char *name, int value) {
     }
     if (std::strcmp(name, "fast_resolve") == 0 && (value == 0 || value == 1)) {
         ctx->fast.resolve = value;
+        return KC_OK;
+    }
+    if (std::strcmp(name, "fast_tile_variant") == 0 && value >= 0 && value <= 2) {
+        ctx->fast.tile_variant = value;
+        return KC_OK;
+    }
+    if (std::strcmp(name, "fast_split0") == 0 && (value == 0 || value == 1)) {
+        ctx->fast.split0 = value;
         return KC_OK;
     }
     if (std::strcmp(name, "fast_min_items") == 0 && value >= 0) {

@@ -30,6 +30,8 @@ struct KsfTuning {
     double sigmas = 8.0;     // slot = mean + sigmas * sqrt(mean) (+ 2 %) items; 0 forces overflows (tests)
     u64 min_items = 1u << 16;  // smaller inputs take the exact path (nothing to gain)
     int resolve = 1;         // 1 = kc_ksf_resolve_kernel (cp.async, two barriers), 0 = kc_ks_resolve_hash_kernel over a bucket list
+    int tile_variant = 0;    // level >= 1 scatter: 0 = KsCfg<L>::TILE items per tile, 3 CTAs/SM; 1 = half tiles, 5 CTAs/SM; 2 = 3/4 tiles, 4 CTAs/SM
+    int split0 = 0;          // level 0 (L = 1): two threads per 32-base strip (512-thread CTAs); measured slower (0.327 vs 0.315 ms), kept as an option
 };
 
 struct KsfPlan {
@@ -147,6 +149,106 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(c
     if (over) status[0] = 1;
 }
 
+// L = 1 with TWO threads per 32-base strip: thread t handles the windows ending at bases [16 h, 16 h + 16) of strip
+// t & 255, h = t >> 8.  Same tile, same shared memory, same output as kc_ksf_scatter0_kernel<1>, but 16 instead of 8 warps
+// per CTA: the kernel is limited to 2 CTAs per SM by its 96 KB stash, and ncu showed it waiting on shared-memory
+// round trips (short scoreboard) at 24 % occupancy.
+__global__ void __launch_bounds__(512) kc_ksf_scatter0_split_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int complements, int shift, int bits,
+                                                                    u32 *bucket_cnt, u32 cap0, KWord<1> *__restrict__ keys, u32 *__restrict__ pos,
+                                                                    u32 *status) {
+    constexpr int S = 256;   // strips per tile
+    constexpr int T = 512;
+    constexpr int TILE = KsCfg<1>::EX_TILE;
+    extern __shared__ __align__(16) unsigned char kc_smem_raw[];
+    u64 *stash = reinterpret_cast<u64 *>(kc_smem_raw);  // slot j * S + strip = window j of the strip (conflict-free)
+    u16 *rk = reinterpret_cast<u16 *>(stash + TILE);
+    u16 *perm = rk + TILE;
+    __shared__ u64 pk[KC_EX_HALO + S];
+    __shared__ u32 vm[KC_EX_HALO + S];
+    __shared__ u32 cnt[256];
+    __shared__ u32 loff[256];
+    __shared__ u32 gbase[256];
+    __shared__ u32 sw[T / 32];
+    const i64 block_pos0 = (i64) blockIdx.x * TILE;
+    if (threadIdx.x < S) {
+        kc_tile_load<S>(seq, n_bytes, block_pos0, pk, vm);
+        cnt[threadIdx.x] = 0;
+    }
+    const u32 strip = threadIdx.x & (S - 1);
+    const int j0 = (int) (threadIdx.x >> 8) * 16;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) rk[(u32) (j0 + j) * S + strip] = 0xFFFFu;
+    __syncthreads();
+    const int widx = KC_EX_HALO + (int) strip;
+    const u32 em = kc_strip_emit_mask(vm, widx, k);
+    if ((em >> (16 - j0)) & 0xFFFFu) {  // bit 31 - j for base j: the half's 16 bits
+        const u64 mine = pk[widx], prev = pk[widx - 1];
+        const u64 mask = (1ULL << (2 * k)) - 1;
+        const int top = 2 * (k - 1);
+        // the k-1 bases before base j0 of the strip: the low end of (prev : mine) cut after base j0 - 1
+        const u64 before = j0 ? ((prev << 32) | (mine >> 32)) : prev;
+        KWord<1> pw;
+        pw.w[0] = before & ((1ULL << top) - 1);
+        u64 rcs = k > 1 ? kmer_reverse_complement(pw, k - 1).w[0] : 0;
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            const int j = j0 + jj;
+            const int sh = 2 * (31 - j);
+            u64 fwd = mine >> sh;
+            if (j < 31) fwd |= prev << (2 * (j + 1));
+            fwd &= mask;
+            const u64 c = (mine >> sh) & 3;
+            const u64 rcf = rcs | ((3 ^ c) << top);
+            rcs = rcf >> 2;
+            if ((em >> (31 - j)) & 1) {
+                KWord<1> canon;
+                canon.w[0] = (!complements || fwd < rcf) ? fwd : rcf;
+                const KWord<1> cs = kmer_scramble(canon);
+                const u32 slot = (u32) j * S + strip;
+                stash[slot] = cs.w[0];
+                rk[slot] = (u16) atomicAdd(&cnt[cs.digit(shift, bits)], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    u32 total;
+    {
+        const u32 c = threadIdx.x < 256 ? cnt[threadIdx.x] : 0u;
+        const u32 p = kc_block_exclusive_scan<T>(c, &total, sw);
+        if (threadIdx.x < 256) {
+            loff[threadIdx.x] = p;
+            if (c) gbase[threadIdx.x] = atomicAdd(&bucket_cnt[threadIdx.x], c);
+        }
+    }
+    __syncthreads();
+    if (total == 0) return;
+    for (u32 slot = threadIdx.x; slot < (u32) TILE; slot += T) {
+        const u32 r = rk[slot];
+        if (r != 0xFFFFu) {
+            KWord<1> v;
+            v.w[0] = stash[slot];
+            perm[loff[v.digit(shift, bits)] + r] = (u16) slot;
+        }
+    }
+    __syncthreads();
+    bool over = false;
+    for (u32 q = threadIdx.x; q < total; q += T) {
+        const u32 slot = perm[q];
+        KWord<1> v;
+        v.w[0] = stash[slot];
+        const u32 dg = v.digit(shift, bits);
+        const u32 idx = gbase[dg] + (q - loff[dg]);
+        if (idx < cap0) {
+            const u64 at = (u64) dg * cap0 + idx;
+            keys[at] = v;
+            pos[at] = (u32) ((u64) block_pos0 + (slot & (S - 1)) * KC_EX_STRIP + (slot >> 8));
+        } else {
+            over = true;
+        }
+    }
+    if (over) status[0] = 1;
+}
+
 // Between two levels: clamp the fill counts of the nP parent slots, count their tiles (tile_count[nP] = 0 for the scan
 // that follows) and, after level 0, add up M.
 __global__ void __launch_bounds__(256) kc_ksf_prep_kernel(const u32 *cnt, u32 nP, u32 capP, u32 tile, u32 *size_out, u32 *tile_count, u32 *status,
@@ -168,11 +270,10 @@ __global__ void __launch_bounds__(256) kc_ksf_prep_kernel(const u32 *cnt, u32 nP
 }
 
 // ---- levels >= 1: fixed-slot parents -> fixed-slot children (kc_kv_scatter_kernel without the counting pass) ---------------
-template <int L>
-__global__ void __launch_bounds__(256, 3) kc_ksf_scatter_kernel(const KWord<L> *__restrict__ ksrc, const u32 *__restrict__ psrc, KWord<L> *__restrict__ kdst,
+template <int L, int TILE, int MINB>
+__global__ void __launch_bounds__(256, MINB) kc_ksf_scatter_kernel(const KWord<L> *__restrict__ ksrc, const u32 *__restrict__ psrc, KWord<L> *__restrict__ kdst,
                                                              u32 *__restrict__ pdst, const u32 *__restrict__ P_size, const u32 *__restrict__ tile_prefix,
                                                              u32 nP, u64 capP, u32 tiles_per_cta, int shift, int bits, u32 *C_cnt, u32 capC, u32 *status) {
-    constexpr int TILE = KsCfg<L>::TILE;
     constexpr int ITEMS = TILE / 256;
     extern __shared__ __align__(16) unsigned char kc_smem_raw[];
     KWord<L> *stage_k = reinterpret_cast<KWord<L> *>(kc_smem_raw);
@@ -450,7 +551,9 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
     kc_ull *m_cell = reinterpret_cast<kc_ull *>(cells + 2);
 
     const int smem0 = Cfg::EX_TILE * ((int) sizeof(KWord<L>) + 4);
-    const int smem1 = Cfg::TILE * ((int) sizeof(KWord<L>) + 4 + 2);
+    const int tv = tune.tile_variant;
+    const int tile1 = tv == 1 ? Cfg::TILE / 2 : (tv == 2 ? Cfg::TILE * 3 / 4 : Cfg::TILE);
+    const int smem1 = tile1 * ((int) sizeof(KWord<L>) + 4 + 2);
     const bool counted = min_freq > 1;
     constexpr int CA = KSF_LEAF_CAP;
     const int per_item = (int) sizeof(KWord<L>) + 12 + 4;
@@ -459,7 +562,13 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
     static int occ_r[2] = {0, 0}, n_sm = 0;
     if (!attr_done) {
         KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter0_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem0));
-        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_kernel<L, Cfg::TILE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::TILE * ((int) sizeof(KWord<L>) + 4 + 2)));
+        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_kernel<L, Cfg::TILE / 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::TILE / 2 * ((int) sizeof(KWord<L>) + 4 + 2)));
+        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_kernel<L, Cfg::TILE * 3 / 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::TILE * 3 / 4 * ((int) sizeof(KWord<L>) + 4 + 2)));
+        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter0_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KsCfg<1>::EX_TILE * 12));
         KC_CUDA(cudaFuncSetAttribute(kc_ks_resolve_hash_kernel<L, CA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CA * per_item));
         KC_CUDA(cudaFuncSetAttribute(kc_ks_resolve_hash_kernel<L, CA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CA * (per_item + 4)));
         int dev = 0;
@@ -475,7 +584,15 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
     {
         const u32 blocks = (u32) kc_div_up(n_bytes, (u64) Cfg::EX_TILE);
         CudaExec::Scope sc(ex, KP_KS_SCATTER0, n_bytes + n_bytes * item_bytes);
-        kc_ksf_scatter0_kernel<L><<<blocks, Cfg::EX_THREADS, smem0, st>>>(seq, n_bytes, k, complements ? 1 : 0, 64 * L - pl.cum[0], pl.bits[0], cnt_cur,
+        bool split = false;
+        if constexpr (L == 1) {
+            if (tune.split0) {
+                split = true;
+                kc_ksf_scatter0_split_kernel<<<blocks, 512, smem0, st>>>(seq, n_bytes, k, complements ? 1 : 0, 64 * L - pl.cum[0], pl.bits[0], cnt_cur,
+                                                                         (u32) pl.cap[0], kb[0], pb[0], status);
+            }
+        }
+        if (!split) kc_ksf_scatter0_kernel<L><<<blocks, Cfg::EX_THREADS, smem0, st>>>(seq, n_bytes, k, complements ? 1 : 0, 64 * L - pl.cum[0], pl.bits[0], cnt_cur,
                                                                          (u32) pl.cap[0], kb[0], pb[0], status);
         ++ex.launches;
         KC_CUDA(cudaGetLastError());
@@ -487,17 +604,23 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
         const size_t mark = ex.arena->mark();
         u32 *P_size = ex.alloc<u32>(nP);
         u32 *tile_prefix = ex.alloc<u32>((u64) nP + 1);
-        kc_ksf_prep_kernel<<<(unsigned) kc_div_up((u64) nP + 1, 256), 256, 0, st>>>(cnt_cur, nP, (u32) pl.cap[lv - 1], (u32) Cfg::TILE, P_size, tile_prefix,
+        kc_ksf_prep_kernel<<<(unsigned) kc_div_up((u64) nP + 1, 256), 256, 0, st>>>(cnt_cur, nP, (u32) pl.cap[lv - 1], (u32) tile1, P_size, tile_prefix,
                                                                                   status, lv == 1 ? m_cell : nullptr);
         ++ex.launches;
         ex.exclusive_scan_nosync(tile_prefix, tile_prefix, (u64) nP + 1);
         u32 *cnt_next = cnt_cur + nP;
-        const u64 tiles_ub = n_bytes / Cfg::TILE + nP + 1;
+        const u64 tiles_ub = n_bytes / tile1 + nP + 1;
         const u32 tiles_per_cta = (u32) kc_div_up(tiles_ub, max_ctas);
         const u32 ctas = (u32) kc_div_up(tiles_ub, tiles_per_cta);
         {
             CudaExec::Scope sc(ex, KP_SORT_SCATTER, 2 * n_bytes * item_bytes);
-            kc_ksf_scatter_kernel<L><<<ctas, 256, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
+            if (tv == 1) kc_ksf_scatter_kernel<L, Cfg::TILE / 2, 5><<<ctas, 256, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
+                                                               pl.cap[lv - 1], tiles_per_cta, 64 * L - pl.cum[lv], pl.bits[lv], cnt_next, (u32) pl.cap[lv],
+                                                               status);
+            else if (tv == 2) kc_ksf_scatter_kernel<L, Cfg::TILE * 3 / 4, 4><<<ctas, 256, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
+                                                               pl.cap[lv - 1], tiles_per_cta, 64 * L - pl.cum[lv], pl.bits[lv], cnt_next, (u32) pl.cap[lv],
+                                                               status);
+            else kc_ksf_scatter_kernel<L, Cfg::TILE, 3><<<ctas, 256, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
                                                                pl.cap[lv - 1], tiles_per_cta, 64 * L - pl.cum[lv], pl.bits[lv], cnt_next, (u32) pl.cap[lv],
                                                                status);
             ++ex.launches;
