@@ -72,7 +72,7 @@ def load_library():
     L.kc_lower_bound.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), u64p, C.POINTER(kc_output)]
     L.kc_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.kc_streaming.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.POINTER(kc_output)]
-    L.kc_maskopt.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(kc_output)]
+    L.kc_maskopt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(kc_output)]
     L.kc_split_ms.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(u8p), C.POINTER(u8p)]
     L.kc_join_ms.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(u8p), u64p]
     L.kc_ms_to_spss.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.POINTER(u8p), u64p]
@@ -290,20 +290,26 @@ class Context:
         self._check(self._lib.kc_lower_bound(self._h, C.byref(p), C.byref(inp), C.byref(lb), C.byref(out)))
         return lb.value, self._result(out, False)
 
-    def streaming(self, seq, *, k, complements=True, min_frequency=1) -> ComputeResult:
+    def streaming(self, seq, *, k, complements=True, min_frequency=1, copy=True) -> ComputeResult:
         """`kmercamel compute -a streaming [-z]` (reference src/streaming.h:12-107) on framed host buffers."""
         seq = np.ascontiguousarray(seq, dtype=np.uint8)
         p = self._params(k, complements, min_frequency, False, False)
         inp = kc_input(seq.ctypes.data, seq.size, None, None, 0)
         out = kc_output()
         self._check(self._lib.kc_streaming(self._h, C.byref(p), C.byref(inp), C.byref(out)))
-        return self._result(out, True)
+        return self._result(out, copy)
 
-    def maskopt(self, ms: bytes, *, k, complements=True, minimize=False) -> ComputeResult:
-        """`kmercamel maskopt -t max-one|min-one` (reference src/masks.h:40-78,240-261) on one record's sequence."""
+    def maskopt(self, ms, *, k, complements=True, minimize=False, copy=True) -> ComputeResult:
+        """`kmercamel maskopt -t max-one|min-one` (reference src/masks.h:40-78,240-261) on one record's sequence
+        (bytes, or a uint8 numpy array, e.g. a view of pinned memory)."""
         out = kc_output()
-        self._check(self._lib.kc_maskopt(self._h, ms, len(ms), int(k), int(bool(complements)), int(bool(minimize)), C.byref(out)))
-        return self._result(out, True)
+        if isinstance(ms, (bytes, bytearray)):
+            ptr, n = C.cast(C.c_char_p(bytes(ms)), C.c_void_p), len(ms)
+        else:
+            ms = np.ascontiguousarray(ms, dtype=np.uint8)
+            ptr, n = C.c_void_p(ms.ctypes.data), ms.size
+        self._check(self._lib.kc_maskopt(self._h, ptr, n, int(k), int(bool(complements)), int(bool(minimize)), C.byref(out)))
+        return self._result(out, copy)
 
     def compute_device(self, seq_ptr: int, n_bytes: int, rec_off_ptr: int = 0, rec_len_ptr: int = 0, n_recs: int = 0, *, k,
                        complements=True, min_frequency=1, assume_simplitigs=False, want_maxone=False) -> ComputeResult:

@@ -49,10 +49,53 @@ template <int L> KC_HD u64 kmer_lower_bound(const KWord<L> *keys, u64 n, const K
     return lo;
 }
 
+// Bucket index over the top `bits` bits of the 2k-bit k-mers of a SORTED set: start[b] = first position whose k-mer has a
+// top-bits value >= b (start[2^bits] = n).  Cuts the ~log2(n) dependent DRAM probes of a binary search down to the index
+// read plus a search inside one bucket (about two keys when 2^bits ~ n / 2).
+template <int L> struct KmerIndex {
+    const u32 *start = nullptr;
+    int bits = 0, shift = 0;
+};
+
+template <int L> KC_HD bool kmer_set_contains(const KWord<L> *keys, u64 n, const KmerIndex<L> &ix, const KWord<L> &x) {
+    u64 lo = 0, hi = n;
+    if (ix.start) {
+        const u32 b = x.digit(ix.shift, ix.bits);
+        lo = ix.start[b];
+        hi = ix.start[b + 1];
+    }
+    while (lo < hi) {
+        const u64 mid = (lo + hi) >> 1;
+        if (keys[mid] < x) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo < n && keys[lo] == x;  // src/khash_utils.h:98-103 containsKMer on the canonical k-mer
+}
+
 static const u32 KC_EMIT_SHORT = 128;   // contributions up to this many characters: one thread
 static const u32 KC_EMIT_CHUNK = 4096;   // longer ones: chunks of this many characters, 256 work items each
 
 #ifdef __CUDACC__
+template <int L> KmerIndex<L> kc_kmer_index_build(CudaExec &ex, const KWord<L> *keys, u64 n, int k) {
+    KmerIndex<L> ix;
+    if (n < 1024 || n >= 0xFFFFFFFFULL) return ix;  // small sets: a plain binary search stays in cache
+    int bits = kc_ceil_log2(n) - 1;
+    if (bits > 24) bits = 24;
+    if (bits > 2 * k) bits = 2 * k;
+    const u64 nb = 1ULL << bits;
+    u32 *start = ex.alloc<u32>(nb + 1);
+    const int shift = 2 * k - bits;
+    ex.for_each(n + 1, [=] __device__(u64 i) {
+        const u64 b_prev = i == 0 ? 0 : (u64) keys[i - 1].digit(shift, bits) + 1;  // first bucket not yet started
+        const u64 b_cur = i == n ? nb : (u64) keys[i].digit(shift, bits);
+        for (u64 b = b_prev; b <= b_cur; ++b) start[b] = (u32) i;
+    }, KP_MISC, n * sizeof(KWord<L>) + nb * 4);
+    ix.start = start;
+    ix.bits = bits;
+    ix.shift = shift;
+    return ix;
+}
+
 static const u32 KC_RANK_SMALL = 1024;
 
 // List ranking of up to KC_RANK_SMALL nodes by one CTA in shared memory (same recurrences as the multi-kernel path).

@@ -225,23 +225,54 @@ MaskoptResult kc_maskopt_run(CudaExec &ex, const u8 *seq, u64 len, int k, bool c
     }
     const KWord<L> *keys = set.keys;
     const u64 n_set = set.n_kept;
-    ex.for_each(len, [=] __device__(u64 q) {
-        const u8 c = seq[q];
-        bool on = false;
-        if (q + k <= len && n_set) {
-            const u64 e = q + k - 1;  // END position of the window
-            if (!minimize || ((flags[e >> 5] >> (e & 31)) & 1u)) {
-                KWord<L> x = KWord<L>::zero();
-                for (int i = 0; i < k; ++i) x = x.shl(2) | KWord<L>::from_u64(kc_nucleotide_code(seq[q + i]));
-                if (complements) {
-                    const KWord<L> r = kmer_reverse_complement(x, k);
-                    if (r < x) x = r;
-                }
-                const u64 at = kmer_lower_bound(keys, n_set, x);
-                on = at < n_set && keys[at] == x;  // src/masks.h:57-59
-            }
+    const KmerIndex<L> ix = kc_kmer_index_build<L>(ex, keys, n_set, k);
+    // One thread per 32 consecutive window starts: the k-mer rolls from window to window (src/masks.h:50-54), the hash probe of
+    // src/masks.h:57-58 is an indexed search in the sorted set, the 32 output letters leave as two 16-byte stores.
+    const int top = 2 * (k - 1);
+    const int top_limb = top >> 6, top_off = top & 63;
+    ex.for_each(kc_div_up(len, 32), [=] __device__(u64 t) {
+        const u64 q0 = t * 32;
+        const KWord<L> mask = KWord<L>::low_mask(2 * k);
+        KWord<L> fwd = KWord<L>::zero(), rc = KWord<L>::zero();
+        for (int i = 0; i + 1 < k; ++i) {
+            const u64 c = q0 + i < len ? (kc_nucleotide_code(seq[q0 + i]) & 3u) : 0u;
+            fwd = fwd.shl(2);
+            fwd.w[0] |= c;
+            rc = rc.shr(2);
+#pragma unroll
+            for (int l = 0; l < L; ++l)
+                if (l == top_limb) rc.w[l] |= (3 ^ c) << top_off;
         }
-        out[q] = on ? (u8) (c & 0xDFu) : (u8) (c | 0x20u);
+        u32 wd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < 32; ++j) {
+            const u64 q = q0 + j;
+            if (q >= len) break;
+            const u64 e = q + k - 1;  // END position of the window
+            bool on = false;
+            if (e < len) {
+                const u64 c = kc_nucleotide_code(seq[e]) & 3u;
+                fwd = fwd.shl(2);
+                fwd.w[0] |= c;
+                fwd = fwd & mask;
+                rc = rc.shr(2);
+#pragma unroll
+                for (int l = 0; l < L; ++l)
+                    if (l == top_limb) rc.w[l] |= (3 ^ c) << top_off;
+                if (n_set && (!minimize || ((flags[e >> 5] >> (e & 31)) & 1u))) {
+                    const KWord<L> x = (!complements || fwd < rc) ? fwd : rc;
+                    on = kmer_set_contains(keys, n_set, ix, x);
+                }
+            }
+            const u32 ch = seq[q];
+            wd[j >> 2] |= (on ? (ch & 0xDFu) : (ch | 0x20u)) << (8 * (j & 3));
+        }
+        if (q0 + 32 <= len) {
+            uint4 *dst = reinterpret_cast<uint4 *>(out + q0);  // `out` is 256-byte aligned (arena), q0 a multiple of 32
+            dst[0] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+            dst[1] = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+        } else {
+            for (u64 q = q0; q < len; ++q) out[q] = (u8) (wd[(q - q0) >> 2] >> (8 * ((q - q0) & 3)));
+        }
     }, KP_MAXONE, 2 * len + n_set * sizeof(KWord<L>));
     return res;
 }
