@@ -379,6 +379,10 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
         u8 *mo = ex.template alloc<u8>(total + 1);
         res.maxone = mo;
         const bool complements = nv.complements;
+        KmerIndex<L> ix;
+#ifdef __CUDACC__
+        if constexpr (Exec::is_device) ix = kc_kmer_index_build<L>(ex, set_keys, n_set, k);
+#endif
         ex.for_each(total, [=] KC_HD_LAMBDA(u64 p) {
             u8 c = ms[p];
             if (c <= 'Z' || p + k > total) {  // already ON, or inside the trailing k-1 (src/global.h:200-208)
@@ -391,8 +395,7 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
                 KWord<L> r = kmer_reverse_complement(x, k);
                 if (r < x) x = r;
             }
-            u64 pos = kmer_lower_bound(set_keys, n_set, x);
-            bool present = pos < n_set && set_keys[pos] == x;  // src/khash_utils.h:98-103 containsKMer
+            const bool present = kmer_set_contains(set_keys, n_set, ix, x);
             mo[p] = present ? (u8) (c - ('a' - 'A')) : c;
         }, KP_MAXONE, 2 * total);
     }
