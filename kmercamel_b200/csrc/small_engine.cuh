@@ -44,9 +44,8 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
     u32 *group_pstart = reinterpret_cast<u32 *>(max1 + HCAP);
     u32 *new_tail = group_pstart + HCAP;
     u32 *jump0 = new_tail + HCAP, *jump1 = jump0 + HCAP, *fin0 = jump1 + HCAP, *fin1 = fin0 + HCAP;
-    __shared__ u32 s_groups, s_edges, s_cyc, s_bans, s_live_s, s_live_p, s_hit;
+    __shared__ u32 s_groups, s_edges, s_cyc, s_bans, s_live_s, s_live_p;
     __shared__ u32 lvl_mask[4];  // bit d: some (suffix, prefix) pair of the initial free ends agrees on d bases
-    __shared__ u32 bloom[512];  // 16384-bit filter over the prefix keys of the level
     __shared__ kc_ull s_min;
     const u32 tid = threadIdx.x;
     const u32 NT = blockDim.x;  // 256, or one warp for tiny problems (block barriers then cost next to nothing)
@@ -91,66 +90,79 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
     const u32 done = v.complements ? 2u : 1u;
     u32 st_levels = 0, st_groups = 0, st_edges = 0, st_rounds = 0, st_bans = 0;
 
-    // Few ends (a genome leaves ~100 x 100): find out ONCE at which levels any free suffix can meet any free prefix.  The
-    // live sets only shrink, so a level whose bit is clear can never accept an edge and is skipped without touching
-    // memory; per-level filtering (below) cost more than the levels that really run (a 16384-bit filter alone also gave
-    // a false positive on every second level).  Full k-mers of the ends are parked in the still unused tuple buffer.
-    const bool have_mask = (u64) n_s * n_p * (u64) (a.d_start + 1) * L <= SmallCfg<L>::MASK_BUDGET;
-    if (have_mask) {
+    // Find out ONCE at which levels any free suffix can meet any free prefix.  The live sets only shrink, so a level whose
+    // bit is clear can never accept an edge and is skipped.  Full k-mers of the ends are parked in the still unused tuple
+    // buffer.  Few ends (a genome leaves ~100 x 100): all pairs x all levels, no barriers.
+    const bool all_pairs = (u64) n_s * n_p * (u64) (a.d_start + 1) * L <= SmallCfg<L>::MASK_BUDGET;
+    {
         KWord<L> *pk = reinterpret_cast<KWord<L> *>(T0), *sk = pk + n_p;
         if (tid < 4) lvl_mask[tid] = 0;
         for (u32 i = tid; i < n_p; i += NT) pk[i] = v.first_kmer(lp[i]);
         for (u32 i = tid; i < n_s; i += NT) sk[i] = v.last_kmer(ls[i]);
         __syncthreads();
-        u32 m[4] = {0, 0, 0, 0};
-        for (u32 q = tid, pairs = n_s * n_p; q < pairs; q += NT) {
-            const KWord<L> x = sk[q % n_s], y = pk[q / n_s];
-            for (int d = 0; d <= a.d_start; ++d)
-                if (kmer_suffix(x, d) == kmer_prefix(y, v.k, d)) m[d >> 5] |= 1u << (d & 31);
-        }
+        if (all_pairs) {
+            u32 m[4] = {0, 0, 0, 0};
+            for (u32 q = tid, pairs = n_s * n_p; q < pairs; q += NT) {
+                const KWord<L> x = sk[q % n_s], y = pk[q / n_s];
+                for (int d = 0; d <= a.d_start; ++d)
+                    if (kmer_suffix(x, d) == kmer_prefix(y, v.k, d)) m[d >> 5] |= 1u << (d & 31);
+            }
 #pragma unroll
-        for (int w = 0; w < 4; ++w)
-            if (m[w]) atomicOr(&lvl_mask[w], m[w]);
-        __syncthreads();
+            for (int w = 0; w < 4; ++w)
+                if (m[w]) atomicOr(&lvl_mask[w], m[w]);
+            __syncthreads();
+        } else {
+            // More ends (hundreds to thousands): an EXACT hash join per level instead of all pairs.  The prefix keys of level d
+            // go into an open-addressing table of end indices (keys are compared through the parked k-mers, so there are no
+            // false positives — a bit filter lit up at every level once ~800 x 800 ends were alive, and all 31 levels of a
+            // 400-record genome ran at ~40 us each although only 7 could accept an edge); the suffix keys probe it.
+            u32 *tab = reinterpret_cast<u32 *>(sk + n_s);
+            u32 H2 = 64;
+            while (H2 < 2 * n_p) H2 <<= 1;  // <= 8192 slots; k-mers + table fit the tuple buffer for every L (see SmallCfg)
+            for (int d = a.d_start; d >= 0; --d) {
+                for (u32 i = tid; i < H2; i += NT) tab[i] = KC_NONE;
+                __syncthreads();
+                for (u32 i = tid; i < n_p; i += NT) {
+                    const KWord<L> key = kmer_prefix(pk[i], v.k, d);
+                    u64 h = 0;
+#pragma unroll
+                    for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
+                    u32 sl = (u32) (h >> 40) & (H2 - 1);
+                    while (true) {
+                        const u32 old = atomicCAS(&tab[sl], KC_NONE, i);
+                        if (old == KC_NONE || kmer_prefix(pk[old], v.k, d) == key) break;
+                        sl = (sl + 1) & (H2 - 1);
+                    }
+                }
+                __syncthreads();
+                int hit = 0;
+                for (u32 i = tid; i < n_s && !hit; i += NT) {
+                    const KWord<L> key = kmer_suffix(sk[i], d);
+                    u64 h = 0;
+#pragma unroll
+                    for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
+                    u32 sl = (u32) (h >> 40) & (H2 - 1);
+                    while (true) {
+                        const u32 o = tab[sl];
+                        if (o == KC_NONE) break;
+                        if (kmer_prefix(pk[o], v.k, d) == key) {
+                            hit = 1;
+                            break;
+                        }
+                        sl = (sl + 1) & (H2 - 1);
+                    }
+                }
+                if (__syncthreads_or(hit) && tid == 0) lvl_mask[d >> 5] |= 1u << (d & 31);
+            }
+            __syncthreads();
+        }
     }
 
     for (int d = a.d_start; d >= 0; --d) {
         if (n_s <= done || n_p == 0) break;
         const long long lvl_t0 = clock64();
-        // Cheap pre-test: a level can only accept an edge if some free suffix key equals some free prefix key.  Hash the
-        // prefix keys into a bit filter and probe it with the suffix keys; when nothing hits the level is a no-op and
-        // is skipped without building / sorting tuples (a false positive merely runs the level as usual).
-        if (have_mask) {  // uniform: no barrier needed
-            if (!((lvl_mask[d >> 5] >> (d & 31)) & 1u)) continue;
-        } else {
-            if (tid == 0) s_hit = 0;
-            for (u32 i = tid; i < 512; i += NT) bloom[i] = 0;
-            __syncthreads();
-            for (u32 i = tid; i < n_p; i += NT) {
-                const KWord<L> key = kmer_prefix(v.first_kmer(lp[i]), v.k, d);
-                u64 h = 0;
-#pragma unroll
-                for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
-                h >>= 50;
-                atomicOr(&bloom[h >> 5], 1u << (h & 31));
-            }
-            __syncthreads();
-            for (u32 i = tid; i < n_s; i += NT) {
-                const KWord<L> key = kmer_suffix(v.last_kmer(ls[i]), d);
-                u64 h = 0;
-#pragma unroll
-                for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
-                h >>= 50;
-                if ((bloom[h >> 5] >> (h & 31)) & 1u) s_hit = 1;
-            }
-            __syncthreads();
-            const u32 hit = s_hit;
-            __syncthreads();  // s_hit / bloom are rewritten at the top of the next level
-            if (!hit) {
-                if (tid == 0) a.out[8 + d] = (u32) (clock64() - lvl_t0);
-                continue;
-            }
-        }
+        // A level whose bit is clear cannot accept an edge (the live sets only shrink): skipped without touching memory.
+        if (!((lvl_mask[d >> 5] >> (d & 31)) & 1u)) continue;  // uniform: no barrier needed
         ++st_levels;
         const u32 nt = n_s + n_p;
         T = T0;
