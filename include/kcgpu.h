@@ -80,7 +80,8 @@ typedef struct kc_output {
     kc_stage_times t;
 } kc_output;
 
-/* device = CUDA ordinal; stream = a cudaStream_t to run on (e.g. torch's current stream), or NULL for a private one. */
+/* device = CUDA ordinal; stream = a cudaStream_t to run on (e.g. torch's current stream), or NULL for a private non-blocking
+ * one.  To run on the legacy default stream (handle 0) pass cudaStreamLegacy, i.e. (void *) 1. */
 int kc_init(int device, void *stream, kc_ctx **out);
 void kc_destroy(kc_ctx *ctx);
 

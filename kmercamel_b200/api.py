@@ -224,8 +224,14 @@ class Context:
     """One context per process and GPU (kc_init / kc_destroy)."""
 
     def __init__(self, device: int = 0, stream: int | None = None):
+        """stream: a cudaStream_t handle to run on (e.g. torch.cuda.current_stream().cuda_stream), None = a private
+        non-blocking stream.  Handle 0 is the legacy default stream (what torch uses unless told otherwise): it is passed as
+        cudaStreamLegacy, so the library's kernels are ordered with the caller's work on that stream (NULL would mean "private")."""
         self._lib = load_library()
         self._h = C.c_void_p()
+        self.stream_handle = None if stream is None else int(stream)  # as given by the caller (0 = legacy default stream)
+        if stream is not None and int(stream) == 0:
+            stream = 1  # cudaStreamLegacy
         rc = self._lib.kc_init(device, C.c_void_p(stream) if stream else None, C.byref(self._h))
         if rc != 0:
             raise KcError(rc, "kc_init")

@@ -1012,7 +1012,7 @@ int kc_p2p_resolve(kc_ctx *ctx, const kc_params *p, const uint64_t *all_counts, 
             my_size[n_pre] = size[g];
             ++n_pre;
         }
-    ensure_arena(ctx, (size_t) ((double) owned[q.rank] * (8.0 * q.limbs + 4.0 + 2.0) * 1.1) + (128u << 20));
+    ensure_arena(ctx, (size_t) ((double) owned[q.rank] * (8.0 * q.limbs + 4.0 + 2.0) * 4.0) + (192u << 20));  // two ping-pong levels of fixed slots (leaf slots hold 1024 for a mean of 384..768)
     ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
@@ -1023,9 +1023,21 @@ int kc_p2p_resolve(kc_ctx *ctx, const kc_params *p, const uint64_t *all_counts, 
     sh.n_pre = n_pre;
     sh.pre_off = my_off;
     sh.pre_size = my_size;
-    if (q.limbs == 1) *n_kept = kc_kmerset_resolve<1>(ex, p->k, p->min_frequency, flags_dev, &sh);
-    else if (q.limbs == 2) *n_kept = kc_kmerset_resolve<2>(ex, p->k, p->min_frequency, flags_dev, &sh);
-    else *n_kept = kc_kmerset_resolve<4>(ex, p->k, p->min_frequency, flags_dev, &sh);
+    // fixed-slot levels first (no counting passes); exact construction when the plan does not apply or a slot overflowed
+    u64 kept = 0;
+    bool fast = false;
+    if (q.limbs == 1) fast = kc_kmerset_resolve_fast<1>(ex, p->k, p->min_frequency, flags_dev, &sh, ctx->fast, &kept);
+    else if (q.limbs == 2) fast = kc_kmerset_resolve_fast<2>(ex, p->k, p->min_frequency, flags_dev, &sh, ctx->fast, &kept);
+    else fast = kc_kmerset_resolve_fast<4>(ex, p->k, p->min_frequency, flags_dev, &sh, ctx->fast, &kept);
+    if (fast) {
+        ++ctx->fast_runs;
+        *n_kept = kept;
+    } else {
+        ++ctx->fast_fallbacks;
+        if (q.limbs == 1) *n_kept = kc_kmerset_resolve<1>(ex, p->k, p->min_frequency, flags_dev, &sh);
+        else if (q.limbs == 2) *n_kept = kc_kmerset_resolve<2>(ex, p->k, p->min_frequency, flags_dev, &sh);
+        else *n_kept = kc_kmerset_resolve<4>(ex, p->k, p->min_frequency, flags_dev, &sh);
+    }
     ctx->total_launches += ex.launches;
     return KC_OK;
     KC_API_END(ctx)

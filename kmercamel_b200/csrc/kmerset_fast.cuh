@@ -273,7 +273,8 @@ __global__ void __launch_bounds__(256) kc_ksf_prep_kernel(const u32 *cnt, u32 nP
 template <int L, int TILE, int MINB>
 __global__ void __launch_bounds__(256, MINB) kc_ksf_scatter_kernel(const KWord<L> *__restrict__ ksrc, const u32 *__restrict__ psrc, KWord<L> *__restrict__ kdst,
                                                              u32 *__restrict__ pdst, const u32 *__restrict__ P_size, const u32 *__restrict__ tile_prefix,
-                                                             u32 nP, u64 capP, u32 tiles_per_cta, int shift, int bits, u32 *C_cnt, u32 capC, u32 *status) {
+                                                             u32 nP, u64 capP, u32 tiles_per_cta, int shift, int bits, u32 *C_cnt, u32 capC, u32 *status,
+                                                             const u64 *__restrict__ P_off = nullptr) {
     constexpr int ITEMS = TILE / 256;
     extern __shared__ __align__(16) unsigned char kc_smem_raw[];
     KWord<L> *stage_k = reinterpret_cast<KWord<L> *>(kc_smem_raw);
@@ -293,8 +294,9 @@ __global__ void __launch_bounds__(256, MINB) kc_ksf_scatter_kernel(const KWord<L
     __syncthreads();
     for (u32 t = t0; t < t1; ++t) {
         while (t >= tile_prefix[b + 1]) ++b;
-        const KWord<L> *src = ksrc + (u64) b * capP;
-        const u32 *ps = psrc + (u64) b * capP;
+        const u64 pbase = P_off ? P_off[b] : (u64) b * capP;  // P_off: parents laid out back to back (multi-GPU receive buffer)
+        const KWord<L> *src = ksrc + pbase;
+        const u32 *ps = psrc + pbase;
         const u32 start = (t - tile_prefix[b]) * TILE;
         const u32 n_here = min((u32) TILE, P_size[b] - start);
         KWord<L> item[ITEMS];
@@ -678,6 +680,147 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
         ++ex.launches;
         KC_CUDA(cudaGetLastError());
     }
+    ex.arena->release(base_mark);
+    return true;
+}
+
+// Multi-GPU owner side (kc_p2p_resolve): the rank's level-0 buckets arrive complete and back to back in the receive buffer
+// (sh->pre_off / pre_size).  The same fixed-slot levels + leaf resolve as above take over from there, instead of the
+// histogram-based levels of kmerset.cuh: no counting passes and no host read-backs between the kernels.  Returns false —
+// with NOTHING written to `flags` — when the plan does not apply or a slot overflowed (checked on the device before the
+// resolve is launched); the caller then runs the exact construction.
+template <int L>
+bool kc_kmerset_resolve_fast(CudaExec &ex, int k, int min_freq, u32 *flags, const KsShard *sh, const KsfTuning &tune, u64 *n_kept_out) {
+    typedef KsCfg<L> Cfg;
+    (void) k;
+    const u32 nP0 = sh->n_pre;
+    const u64 total = sh->n_items;
+    if (!tune.enabled || nP0 == 0 || total < tune.min_items) return false;
+    u64 max0 = 0;
+    for (u32 i = 0; i < nP0; ++i) max0 = sh->pre_size[i] > max0 ? sh->pre_size[i] : max0;
+    if (max0 >= 0xFFFFFFF0ULL) return false;
+    int sub_bits = 0;
+    while (sub_bits < 32 && (max0 >> sub_bits) > tune.leaf_target) ++sub_bits;
+    if (sub_bits == 0) return false;
+    const int levels = (sub_bits + 7) / 8;
+    if (levels > KSF_MAX_LEVELS - 1) return false;
+    int bits[KSF_MAX_LEVELS], cum[KSF_MAX_LEVELS];
+    u64 cap[KSF_MAX_LEVELS], slots[2] = {1, 1};
+    int c = 0;
+    for (int i = 0; i < levels; ++i) {
+        bits[i] = sub_bits / levels + (i < sub_bits % levels ? 1 : 0);
+        c += bits[i];
+        cum[i] = c;
+        const double mean = (double) max0 / (double) (1ULL << c);
+        u64 cp = (u64) std::ceil(mean + tune.sigmas * std::sqrt(mean) + (tune.sigmas > 0 ? 0.02 * mean + 64.0 : 0.0));
+        cp = (cp + 31) / 32 * 32;
+        if (i == levels - 1) cp = KSF_LEAF_CAP;
+        cap[i] = cp;
+        const u64 need = ((u64) nP0 << c) * cp;
+        if (need > slots[i & 1]) slots[i & 1] = need;
+    }
+    const u64 n_leaf = (u64) nP0 << cum[levels - 1];
+    if (n_leaf >= 0xFFFFFFFFULL) return false;
+    cudaStream_t st = ex.stream;
+    const size_t base_mark = ex.arena->mark();
+    u64 n_cnt = 0;
+    for (int i = 0; i < levels; ++i) n_cnt += (u64) nP0 << cum[i];
+    {   // the slots must fit what is left of the arena (the caller falls back to the exact construction otherwise)
+        const u64 need = (slots[0] + slots[1]) * (sizeof(KWord<L>) + 4) + n_cnt * 4 + ((u64) nP0 << cum[levels - 1]) * 8 + (1u << 20);
+        if (ex.arena->off + need > ex.arena->top) return false;
+    }
+    KWord<L> *kb[2];
+    u32 *pb[2];
+    for (int i = 0; i < 2; ++i) {
+        kb[i] = ex.alloc<KWord<L>>(slots[i]);
+        pb[i] = ex.alloc<u32>(slots[i]);
+    }
+    u32 *cnt_all = ex.alloc<u32>(n_cnt);
+    ex.fill_bytes(cnt_all, 0, n_cnt * 4);
+    u64 *d_off = ex.alloc<u64>(nP0);
+    u32 *d_size = ex.alloc<u32>(nP0);
+    u64 *cells = ex.alloc<u64>(2);  // [0] kept, [1] low word = overflow status
+    ex.fill_bytes(cells, 0, 16);
+    u32 *status = reinterpret_cast<u32 *>(cells + 1);
+    kc_ull *n_unique = reinterpret_cast<kc_ull *>(cells);
+    {
+        std::vector<u32> hs(nP0);
+        for (u32 i = 0; i < nP0; ++i) hs[i] = (u32) sh->pre_size[i];
+        KC_CUDA(cudaMemcpyAsync(d_off, sh->pre_off, (size_t) nP0 * 8, cudaMemcpyHostToDevice, st));
+        KC_CUDA(cudaMemcpyAsync(d_size, hs.data(), (size_t) nP0 * 4, cudaMemcpyHostToDevice, st));
+        KC_CUDA(cudaStreamSynchronize(st));  // hs goes out of scope
+    }
+    const int tile1 = Cfg::TILE;
+    const int smem1 = tile1 * ((int) sizeof(KWord<L>) + 4 + 2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_kernel<L, Cfg::TILE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+        KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (16 * L + 20)));
+        KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (16 * L + 24)));
+        attr_done = true;
+    }
+    const u64 item_bytes = sizeof(KWord<L>) + 4;
+    const u32 max_ctas = 148 * 8;
+    const KWord<L> *ksrc = reinterpret_cast<const KWord<L> *>(sh->keys);
+    const u32 *psrc = sh->pos;
+    const u32 *cnt_par = d_size;
+    u32 *cnt_cur = cnt_all;
+    for (int lv = 0; lv < levels; ++lv) {
+        const u32 nP = lv == 0 ? nP0 : (u32) ((u64) nP0 << cum[lv - 1]);
+        const size_t mark = ex.arena->mark();
+        u32 *P_size = ex.alloc<u32>(nP);
+        u32 *tile_prefix = ex.alloc<u32>((u64) nP + 1);
+        const u32 capP = lv == 0 ? 0xFFFFFFFFu : (u32) cap[lv - 1];
+        kc_ksf_prep_kernel<<<(unsigned) kc_div_up((u64) nP + 1, 256), 256, 0, st>>>(cnt_par, nP, capP, (u32) tile1, P_size, tile_prefix, status, nullptr);
+        ++ex.launches;
+        ex.exclusive_scan_nosync(tile_prefix, tile_prefix, (u64) nP + 1);
+        const u64 tiles_ub = total / tile1 + nP + 1;
+        const u32 tiles_per_cta = (u32) kc_div_up(tiles_ub, max_ctas);
+        const u32 ctas = (u32) kc_div_up(tiles_ub, tiles_per_cta);
+        {
+            CudaExec::Scope sc(ex, KP_SORT_SCATTER, 2 * total * item_bytes);
+            kc_ksf_scatter_kernel<L, Cfg::TILE, 3><<<ctas, 256, smem1, st>>>(ksrc, psrc, kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP, (u64) capP, tiles_per_cta,
+                                                                             64 * L - Cfg::D0 - cum[lv], bits[lv], cnt_cur, (u32) cap[lv], status,
+                                                                             lv == 0 ? d_off : nullptr);
+            ++ex.launches;
+            KC_CUDA(cudaGetLastError());
+        }
+        ksrc = kb[lv & 1];
+        psrc = pb[lv & 1];
+        cnt_par = cnt_cur;
+        cnt_cur += (u64) nP0 << cum[lv];
+        ex.arena->release(mark);
+    }
+    {   // no leaf may exceed the resolve capacity: decided BEFORE a single flag bit is written
+        const u32 *cc = cnt_par;
+        ex.for_each(n_leaf, [=] __device__(u64 i) {
+            if (cc[i] > KSF_LEAF_CAP) status[0] = 1;
+        });
+    }
+    if (ex.read(status)) {
+        ex.arena->release(base_mark);
+        return false;
+    }
+    const bool counted = min_freq > 1;
+    const int smem2 = (int) KSF_LEAF_CAP * (16 * L + 20 + (counted ? 4 : 0));
+    int occ = 0, n_sm = 0, dev = 0;
+    KC_CUDA(cudaGetDevice(&dev));
+    KC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    if (counted) KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kc_ksf_resolve_kernel<L, true>, 256, smem2));
+    else KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kc_ksf_resolve_kernel<L, false>, 256, smem2));
+    const u32 fit = (u32) (n_sm * (occ > 0 ? occ : 1));
+    const u32 grid = (u32) n_leaf < fit ? (u32) n_leaf : fit;
+    {
+        CudaExec::Scope sc(ex, KP_KS_RESOLVE, total * item_bytes);
+        const int last = levels - 1;
+        if (counted)
+            kc_ksf_resolve_kernel<L, true><<<grid, 256, smem2, st>>>(kb[last & 1], pb[last & 1], cnt_par, (u32) n_leaf, flags, (u32) min_freq, n_unique, status);
+        else
+            kc_ksf_resolve_kernel<L, false><<<grid, 256, smem2, st>>>(kb[last & 1], pb[last & 1], cnt_par, (u32) n_leaf, flags, (u32) min_freq, n_unique, status);
+        ++ex.launches;
+        KC_CUDA(cudaGetLastError());
+    }
+    *n_kept_out = ex.read(cells);
     ex.arena->release(base_mark);
     return true;
 }

@@ -159,6 +159,14 @@ class GpuOps:
         self.flags = torch.zeros((self.n_bytes + 31) // 32 + 1, dtype=torch.int32, device=seq_dev.device)
         self._send_k = self._send_p = None
         self._limbs = 1
+        # torch work (copies, memsets, NCCL collectives) is ordered on torch's current stream; the library's kernels are
+        # ordered with it only when the context runs on that same stream.  Otherwise every hand-over needs a host sync.
+        self._shared_stream = ctx.stream_handle is not None and ctx.stream_handle == torch.cuda.current_stream().cuda_stream
+
+    def _order(self):
+        """Make torch-side work visible to the library's stream (no-op when both use one stream)."""
+        if not self._shared_stream:
+            self.torch.cuda.current_stream().synchronize()
 
     def granule(self, k):
         return int(self.ctx._lib.kc_shard_granule(k))
@@ -167,6 +175,7 @@ class GpuOps:
         torch = self.torch
         from .api import limbs_for_k
         self._limbs = limbs_for_k(k)
+        self._order()
         cap = max(e - b, 1)
         if self._send_k is None or self._send_k.numel() < cap * self._limbs:
             self._send_k = torch.empty(cap * self._limbs, dtype=torch.int64, device=self.seq.device)
@@ -188,7 +197,7 @@ class GpuOps:
 
     def resolve(self, keys, pos, n, *, k, complements, min_frequency):
         self.flags.zero_()
-        self.torch.cuda.current_stream().synchronize()
+        self._order()
         return self.ctx.shard_resolve(keys.data_ptr(), pos.data_ptr(), n, self.flags.data_ptr(), k=k, complements=complements,
                                       min_frequency=min_frequency)
 
@@ -205,6 +214,7 @@ class GpuOps:
         comm.barrier()
 
     def p2p_hist(self, b, e, *, k, complements):
+        self._order()
         return self.ctx.p2p_hist(self.seq.data_ptr(), self.n_bytes, b, e, k=k, complements=complements)
 
     def p2p_scatter(self, b, e, all_counts, *, k, complements):
@@ -212,8 +222,9 @@ class GpuOps:
 
     def p2p_resolve(self, all_counts, *, k, complements, min_frequency):
         self.flags.zero_()
+        self._order()
         return self.ctx.p2p_resolve(all_counts, self.flags.data_ptr(), k=k, complements=complements, min_frequency=min_frequency)
 
     def finish(self, n_kept, *, k, complements):
-        self.torch.cuda.current_stream().synchronize()
+        self._order()
         return self.ctx.compute_from_flags(self.seq.data_ptr(), self.n_bytes, self.flags.data_ptr(), n_kept, k=k, complements=complements)

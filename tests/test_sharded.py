@@ -203,16 +203,17 @@ def test_sharded_world1_matches_kc_compute(ctx, k, complements, z):
 
 
 @pytest.mark.gpu
-def test_sharded_p2p_world1_matches_kc_compute():
-    """The fused partition + exchange path with a single rank (its own buffers stand in for the peers')."""
+@pytest.mark.parametrize("stream_mode", ["private", "torch"])
+def test_sharded_p2p_world1_matches_kc_compute(stream_mode):
+    """The fused partition + exchange path with a single rank (its own buffers stand in for the peers'), on a private
+    library stream and on torch's current stream (then no host synchronisation separates torch's work from the kernels)."""
     import kmercamel_b200 as kb
-    c = kb.Context(0)      # peer buffers are per context: use a private one
+    c = kb.Context(0, None if stream_mode == "private" else torch.cuda.current_stream().cuda_stream)
     try:
         recs = synth.random_genome_records(6, 40_000, 11)
         recs.append(recs[2][100:3000].copy())
         seq, _, _ = synth.frame_records(recs)
         d = torch.from_numpy(seq).cuda()
-        torch.cuda.synchronize()
         ops = sharded.GpuOps(c, d)
         comm = sharded.TorchComm(d.device)
         ops.setup_p2p(comm, 31)
@@ -223,3 +224,39 @@ def test_sharded_p2p_world1_matches_kc_compute():
             assert c.copy_to_host(r.result.ms_ptr, r.result.length) == want.ms
     finally:
         c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,z", [(31, 1), (31, 2), (47, 1), (100, 2)])
+def test_sharded_p2p_fixed_slot_resolve_with_duplicates(k, z):
+    """Owner-side fixed-slot levels (kc_kmerset_resolve_fast) on inputs where every k-mer occurs twice or three times, with the
+    data set changing between jobs (stale receive-buffer contents must never leak into a result)."""
+    import kmercamel_b200 as kb
+    c = kb.Context(0, torch.cuda.current_stream().cuda_stream)
+    one = kb.Context(0)
+    try:
+        comm = sharded.TorchComm(torch.device("cuda", 0))
+        a = synth.frame_records(synth.random_genome_records(4, 500_000, 21))[0]
+        b = synth.frame_records(synth.random_genome_records(4, 500_000, 22))[0]
+        first = True
+        for parts in ((a, b), (b, b), (a, a[:700_000], b, a), (a, b)):
+            seq = np.concatenate(parts)
+            d = torch.from_numpy(seq).cuda()
+            ops = sharded.GpuOps(c, d)
+            if first:
+                ops.setup_p2p(comm, k, slack=2.0)
+                first = False
+            try:
+                want = one.compute(seq, k=k, min_frequency=z)
+            except kb.api.KcError as e:      # all k-mers distinct and z = 2: nothing is kept
+                assert e.code == -4
+                with pytest.raises(kb.api.KcError):
+                    sharded.sharded_compute_p2p(ops, comm, d.numel(), k=k, min_frequency=z)
+                continue
+            r = sharded.sharded_compute_p2p(ops, comm, d.numel(), k=k, min_frequency=z)
+            assert r.n_kept == want.n_kmers and r.result.length == want.length
+            assert c.copy_to_host(r.result.ms_ptr, r.result.length) == want.ms
+        assert c.stat("fast_runs") >= 3
+    finally:
+        c.close()
+        one.close()
