@@ -198,7 +198,9 @@ uint64_t kc_total_launches(const kc_ctx *ctx);
 /* Tuning / test knobs.  "small_engine" (default 1): run the tail of the overlap levels in the single-CTA kernel.
  * "fast_set" (default 1): try the histogram-free k-mer set construction first (from-FASTA compute without -M);
  * "fast_leaf_target", "fast_sigmas", "fast_min_items": its plan parameters, exposed so that tests reach the
- * multi-level plan and the overflow fallback with small inputs.  Results never depend on these options. */
+ * multi-level plan and the overflow fallback with small inputs; "fast_heuristics" (default 1): skip the attempt when
+ * duplicates are expected (-z > 1, or the previous call on an input of similar size overflowed).  "fast_split0",
+ * "fast_tile_variant": measured-and-rejected kernel variants kept for re-measurement.  Results never depend on these options. */
 int kc_set_option(kc_ctx *ctx, const char *name, int value);
 /* Counters since kc_init: "fast_runs", "fast_fallbacks", "total_launches". */
 int kc_get_stat(const kc_ctx *ctx, const char *name, uint64_t *value);

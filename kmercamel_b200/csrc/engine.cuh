@@ -298,14 +298,15 @@ template <class Exec, int L> struct Engine {
 #ifdef __CUDACC__
         if constexpr (Exec::is_device) {
             if (!small_out) return;
-            u32 h[8 + 128];
-            ex.read_n(small_out, h, 8 + 128);
+            u32 h[8 + 128 + 8];
+            ex.read_n(small_out, h, 8 + 128 + 8);
             small_out = nullptr;
             if (std::getenv("KC_TRACE")) {
                 std::fprintf(stderr, "[kc_trace] small engine: n_s=%llu n_p=%llu levels=%u groups=%u edges=%u ban_rounds=%u bans=%u; clocks per level (* = run):",
                              (unsigned long long) n_s, (unsigned long long) n_p, h[1], h[2], h[3], h[4], h[5]);
                 for (int dd = small_d; dd >= 0; --dd) std::fprintf(stderr, " d%d=%u%s", dd, h[8 + dd] & 0x7FFFFFFFu, (h[8 + dd] >> 31) ? "*" : "");
-                std::fprintf(stderr, "\n");
+                std::fprintf(stderr, "; phases: stage+mask=%u tuples=%u sort=%u groups=%u replay=%u validate+commit=%u lists=%u writeback=%u\n", h[136], h[137],
+                             h[138], h[139], h[140], h[141], h[142], h[143]);
             }
             if (h[0]) KC_THROW(KC_ERR_INTERNAL, "ban list overflow");
             stats.levels_run += h[1];
@@ -351,8 +352,8 @@ template <class Exec, int L> struct Engine {
             a.ban_cap = BAN_CAP;
             a.d_start = d;
             a.strict = strict;
-            a.out = ex.template alloc<u32>(8 + 128);
-            ex.fill_bytes(a.out, 0, (8 + 128) * 4);
+            a.out = ex.template alloc<u32>(8 + 128 + 8);
+            ex.fill_bytes(a.out, 0, (8 + 128 + 8) * 4);
             static bool attr_done = false;
             if (!attr_done) {
                 KC_CUDA(cudaFuncSetAttribute(kc_small_engine_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -43,6 +43,8 @@ struct kc_ctx {
     bool small_engine = true;
     KsfTuning fast;          // histogram-free set construction (kmerset_fast.cuh); KC_FAST_* environment knobs for tests
     u64 fast_runs = 0, fast_fallbacks = 0;
+    bool fast_heuristics = true;  // skip the fixed-slot attempt when duplicates are expected (see run_stage1_runs)
+    u64 fast_overflow_bytes = 0;  // input size of the last call whose fixed-slot attempt overflowed (0 = none)
     u64 total_launches = 0;  // kernels launched through this context since kc_init
     // fused partition + exchange over peer memory (kc_p2p_*)
     struct P2P {
@@ -202,8 +204,12 @@ u64 run_stage1_runs(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_para
     ex.fill_bytes(flags, 0, fwords * 4);
     u64 *cells = ex.arena->alloc_top<u64>(2);  // {kept distinct k-mers, runs}
     ex.fill_bytes(cells, 0, 16);
-    // FLAGS-only: try the histogram-free construction first (no host synchronisation until the runs are counted)
-    if (!p.want_maxone) {
+    // FLAGS-only: try the histogram-free construction first (no host synchronisation until the runs are counted).  Its
+    // fixed slots assume mostly distinct k-mers; `-z Z > 1` announces a read set with coverage (every k-mer ~coverage times:
+    // the leaf slots overflow and the attempt is wasted — configs[3] at full size lost 70 ms to it), and so does an
+    // overflow in the previous call of this context on an input of similar size.
+    const bool expect_duplicates = ctx->fast_heuristics && (p.min_frequency > 1 || (ctx->fast_overflow_bytes && nb >= ctx->fast_overflow_bytes / 2 && nb <= ctx->fast_overflow_bytes * 2));
+    if (!p.want_maxone && !expect_duplicates) {
         KsfPlan plan;
         u64 *cells4 = ex.arena->alloc_top<u64>(4);  // {kept, runs, M, overflow status}
         ex.fill_bytes(cells4, 0, 32);
@@ -227,6 +233,7 @@ u64 run_stage1_runs(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_para
                 return hc[2] ? hc[0] : 0;
             }
             ++ctx->fast_fallbacks;  // a slot overflowed: discard the flags, fall through to the exact construction
+            ctx->fast_overflow_bytes = nb;
             ex.fill_bytes(flags, 0, fwords * 4);
         }
     }
@@ -1076,6 +1083,11 @@ int kc_set_option(kc_ctx *ctx, const char *name, int value) {
     }
     if (std::strcmp(name, "fast_resolve") == 0 && (value == 0 || value == 1)) {
         ctx->fast.resolve = value;
+        return KC_OK;
+    }
+    if (std::strcmp(name, "fast_heuristics") == 0 && (value == 0 || value == 1)) {
+        ctx->fast_heuristics = value != 0;
+        ctx->fast_overflow_bytes = 0;
         return KC_OK;
     }
     if (std::strcmp(name, "fast_tile_variant") == 0 && value >= 0 && value <= 2) {

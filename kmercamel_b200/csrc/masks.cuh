@@ -111,7 +111,7 @@ StreamingResult kc_streaming_run(CudaExec &ex, const u8 *seq, u64 n_bytes, int k
     ex.fill_bytes(cells4, 0, 32);
     u64 hc[4] = {0, 0, 0, 0};
     bool done = false;
-    if (kc_kmerset_build_fast<L>(ex, seq, n_bytes, k, complements, 1, flags, cells4, fast)) {
+    if (min_freq == 1 && kc_kmerset_build_fast<L>(ex, seq, n_bytes, k, complements, 1, flags, cells4, fast)) {  // -z > 1: a read set, see run_stage1_runs
         ex.read_n(cells4, hc, 4);
         if (hc[3] == 0) {
             done = true;

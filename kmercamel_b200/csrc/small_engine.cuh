@@ -13,7 +13,6 @@ template <int L> struct SmallCfg {
     static constexpr u32 T = L <= 2 ? 4096 : 2048;  // tuple capacity (free suffix ends + free prefix ends)
     static constexpr u32 H = T / 2;
     static constexpr u32 NS = 1024;  // up to this many virtual nodes the whole path state lives in shared memory
-    static constexpr u64 MASK_BUDGET = 1u << 20;  // pairs x levels x limbs up to which the level mask is computed up front
     static constexpr u32 RANK_SORT = 384;      // up to this many tuples: rank sort (no barriers) instead of the bitonic network
     static constexpr size_t SMEM = (size_t) T * sizeof(KWord<L + 1>) + (size_t) H * (4 * 6 + 8 * 2) + (size_t) NS * (8 + 4 * 7 + 3);
 };
@@ -89,75 +88,90 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
     const u32 batch = a.strict ? v.N / 16 + 1 : v.N + 1;  // see Engine::run_level
     const u32 done = v.complements ? 2u : 1u;
     u32 st_levels = 0, st_groups = 0, st_edges = 0, st_rounds = 0, st_bans = 0;
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // KC_TRACE: clocks per phase, summed over the levels (thread 0)
+    long long ph_t = clock64();
+#define KC_PH(i) do { const long long kc_now = clock64(); ph[i] += kc_now - ph_t; ph_t = kc_now; } while (0)
 
     // Find out ONCE at which levels any free suffix can meet any free prefix.  The live sets only shrink, so a level whose
     // bit is clear can never accept an edge and is skipped.  Full k-mers of the ends are parked in the still unused tuple
-    // buffer.  Few ends (a genome leaves ~100 x 100): all pairs x all levels, no barriers.
-    const bool all_pairs = (u64) n_s * n_p * (u64) (a.d_start + 1) * L <= SmallCfg<L>::MASK_BUDGET;
+    // buffer.
     {
         KWord<L> *pk = reinterpret_cast<KWord<L> *>(T0), *sk = pk + n_p;
         if (tid < 4) lvl_mask[tid] = 0;
         for (u32 i = tid; i < n_p; i += NT) pk[i] = v.first_kmer(lp[i]);
         for (u32 i = tid; i < n_s; i += NT) sk[i] = v.last_kmer(ls[i]);
         __syncthreads();
-        if (all_pairs) {
-            u32 m[4] = {0, 0, 0, 0};
-            for (u32 q = tid, pairs = n_s * n_p; q < pairs; q += NT) {
-                const KWord<L> x = sk[q % n_s], y = pk[q / n_s];
-                for (int d = 0; d <= a.d_start; ++d)
-                    if (kmer_suffix(x, d) == kmer_prefix(y, v.k, d)) m[d >> 5] |= 1u << (d & 31);
-            }
-#pragma unroll
-            for (int w = 0; w < 4; ++w)
-                if (m[w]) atomicOr(&lvl_mask[w], m[w]);
-            __syncthreads();
-        } else {
-            // More ends (hundreds to thousands): an EXACT hash join per level instead of all pairs.  The prefix keys of level d
-            // go into an open-addressing table of end indices (keys are compared through the parked k-mers, so there are no
-            // false positives — a bit filter lit up at every level once ~800 x 800 ends were alive, and all 31 levels of a
-            // 400-record genome ran at ~40 us each although only 7 could accept an edge); the suffix keys probe it.
+        {
+            // An EXACT hash join per level: the prefix keys of level d go into an open-addressing table of end indices (keys
+            // are compared through the parked k-mers, so there are no false positives — a bit filter lit up at every level
+            // once ~800 x 800 ends were alive, and all 31 levels of a 400-record genome ran at ~40 us each although only 11
+            // could accept an edge); the suffix keys probe it.  ~1.5 k clocks per level; all pairs x all levels cost 140 k
+            // clocks even for the 100 x 100 ends of configs[1].
+            // Several levels share one pass: each level has its own table, so only three barriers separate clear / insert /
+            // probe for a whole group of levels (all 31 at once for the 100 x 100 ends of configs[1]).
             u32 *tab = reinterpret_cast<u32 *>(sk + n_s);
             u32 H2 = 64;
-            while (H2 < 2 * n_p) H2 <<= 1;  // <= 8192 slots; k-mers + table fit the tuple buffer for every L (see SmallCfg)
-            for (int d = a.d_start; d >= 0; --d) {
-                for (u32 i = tid; i < H2; i += NT) tab[i] = KC_NONE;
+            while (H2 < 2 * n_p) H2 <<= 1;  // <= 8192 slots; k-mers + one table fit the tuple buffer for every L (see SmallCfg)
+            const u32 avail = (u32) ((SmallCfg<L>::T * sizeof(TW) - (size_t) (n_s + n_p) * sizeof(KWord<L>)) / 4);
+            u32 G = avail / H2;
+            if (G > 32) G = 32;
+            if (G < 1) G = 1;
+            for (int d_hi = a.d_start; d_hi >= 0; d_hi -= (int) G) {
+                const u32 g = (u32) (d_hi + 1) < G ? (u32) (d_hi + 1) : G;  // levels d_hi, d_hi - 1, ..., d_hi - g + 1
+                for (u32 i = tid; i < g * H2; i += NT) tab[i] = KC_NONE;
+                if (tid == 0) s_groups = 0;  // reused as the hit mask of the group
                 __syncthreads();
-                for (u32 i = tid; i < n_p; i += NT) {
-                    const KWord<L> key = kmer_prefix(pk[i], v.k, d);
-                    u64 h = 0;
+                for (u32 lev = 0; lev < g; ++lev) {
+                    const int d = d_hi - (int) lev;
+                    u32 *tb = tab + lev * H2;
+                    for (u32 i = tid; i < n_p; i += NT) {
+                        const KWord<L> key = kmer_prefix(pk[i], v.k, d);
+                        u64 h = 0;
 #pragma unroll
-                    for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
-                    u32 sl = (u32) (h >> 40) & (H2 - 1);
-                    while (true) {
-                        const u32 old = atomicCAS(&tab[sl], KC_NONE, i);
-                        if (old == KC_NONE || kmer_prefix(pk[old], v.k, d) == key) break;
-                        sl = (sl + 1) & (H2 - 1);
-                    }
-                }
-                __syncthreads();
-                int hit = 0;
-                for (u32 i = tid; i < n_s && !hit; i += NT) {
-                    const KWord<L> key = kmer_suffix(sk[i], d);
-                    u64 h = 0;
-#pragma unroll
-                    for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
-                    u32 sl = (u32) (h >> 40) & (H2 - 1);
-                    while (true) {
-                        const u32 o = tab[sl];
-                        if (o == KC_NONE) break;
-                        if (kmer_prefix(pk[o], v.k, d) == key) {
-                            hit = 1;
-                            break;
+                        for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
+                        u32 sl = (u32) (h >> 40) & (H2 - 1);
+                        while (true) {
+                            const u32 old = atomicCAS(&tb[sl], KC_NONE, i);
+                            if (old == KC_NONE || kmer_prefix(pk[old], v.k, d) == key) break;
+                            sl = (sl + 1) & (H2 - 1);
                         }
-                        sl = (sl + 1) & (H2 - 1);
                     }
                 }
-                if (__syncthreads_or(hit) && tid == 0) lvl_mask[d >> 5] |= 1u << (d & 31);
+                __syncthreads();
+                u32 hits = 0;
+                for (u32 lev = 0; lev < g; ++lev) {
+                    const int d = d_hi - (int) lev;
+                    const u32 *tb = tab + lev * H2;
+                    for (u32 i = tid; i < n_s && !((hits >> lev) & 1u); i += NT) {
+                        const KWord<L> key = kmer_suffix(sk[i], d);
+                        u64 h = 0;
+#pragma unroll
+                        for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
+                        u32 sl = (u32) (h >> 40) & (H2 - 1);
+                        while (true) {
+                            const u32 o = tb[sl];
+                            if (o == KC_NONE) break;
+                            if (kmer_prefix(pk[o], v.k, d) == key) {
+                                hits |= 1u << lev;
+                                break;
+                            }
+                            sl = (sl + 1) & (H2 - 1);
+                        }
+                    }
+                }
+                if (hits) atomicOr(&s_groups, hits);
+                __syncthreads();
+                if (tid == 0) {
+                    const u32 hm = s_groups;
+                    for (u32 lev = 0; lev < g; ++lev)
+                        if ((hm >> lev) & 1u) lvl_mask[(d_hi - (int) lev) >> 5] |= 1u << ((d_hi - (int) lev) & 31);
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
     }
 
+    KC_PH(0);  // state staging + level mask
     for (int d = a.d_start; d >= 0; --d) {
         if (n_s <= done || n_p == 0) break;
         const long long lvl_t0 = clock64();
@@ -184,6 +198,7 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
             s_bans = 0;
         }
         __syncthreads();
+        KC_PH(1);  // tuples
         // 2. sort.  Tiny levels: every thread ranks its tuple against all others (tuples are distinct: they carry role
         // and node id) and drops it at its rank in the upper half of the tuple buffer — two barriers instead of the
         // 36+ of a bitonic network over 256 slots.
@@ -192,6 +207,7 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
             for (u32 i = tid; i < nt; i += NT) {
                 const TW mine = T0[i];
                 u32 r = 0;
+#pragma unroll 8
                 for (u32 j = 0; j < nt; ++j) r += T0[j] < mine ? 1u : 0u;
                 dst[r] = mine;
             }
@@ -200,6 +216,7 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
         } else {
             kc_block_bitonic<L + 1>(T, nt, NT);
         }
+        KC_PH(2);  // sort
         // 3. active groups
         for (u32 i = tid + 1; i < nt; i += NT) {
             TW p = T[i - 1], q = T[i];
@@ -208,6 +225,7 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
         __syncthreads();
         const u32 n_groups = s_groups;
         st_groups += n_groups;
+        KC_PH(3);  // group detection
         if (n_groups) {
             LevelCtx<L> c;
             c.nv = v;
@@ -236,6 +254,7 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
                     s_min = ~0ULL;
                 }
                 __syncthreads();
+                KC_PH(4);  // replay
                 // 5. this level's edges
                 for (u32 i = tid; i < n_s; i += NT) {
                     u32 x = ls[i];
@@ -352,6 +371,7 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
             }
             for (u32 b = tid; b < n_bans; b += NT) ban_flag[a.ban_i[b]] = 0;
             st_bans += n_bans;
+            KC_PH(5);  // edges, cycle validation, commit
         }
         // 8. shrink the live lists (their order is irrelevant: the tuple sort orders by id)
         if (tid == 0) {
@@ -373,6 +393,7 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
         u32 *t32 = ls; ls = ls2; ls2 = t32;
         t32 = lp; lp = lp2; lp2 = t32;
         __syncthreads();
+        KC_PH(6);  // live lists
         if (tid == 0) a.out[8 + d] = (u32) (clock64() - lvl_t0) | 0x80000000u;  // top bit: the level was run, not skipped
     }
     if (local_state) {  // write the path back for the emission stage
@@ -385,7 +406,9 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
             a.st.ovl[i] = s.ovl[i];
         }
     }
+    KC_PH(7);  // write-back
     if (tid == 0) {
+        for (int i = 0; i < 8; ++i) a.out[8 + 128 + i] = (u32) ph[i];
         a.out[1] = st_levels;
         a.out[2] = st_groups;
         a.out[3] = st_edges;
@@ -393,5 +416,7 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
         a.out[5] = st_bans;
     }
 }
+
+#undef KC_PH
 
 #endif  // __CUDACC__

@@ -287,7 +287,7 @@ def test_small_engine_and_host_levels_agree(ctx, golden, simplitigs_bytes):
 
 # ---- histogram-free set construction (kmerset_fast.cuh) must agree with the exact one -----------------------------
 def _fast_options(ctx, **kw):
-    defaults = dict(fast_set=1, fast_leaf_target=768, fast_sigmas=8, fast_min_items=1 << 16)
+    defaults = dict(fast_set=1, fast_leaf_target=768, fast_sigmas=8, fast_min_items=1 << 16, fast_heuristics=0)
     defaults.update(kw)
     for name, value in defaults.items():
         ctx.set_option(name, value)
@@ -359,6 +359,28 @@ def test_fast_set_overflow_falls_back(ctx):
         assert got.ms == want.ms and got.n_kmers == want.n_kmers
     finally:
         _fast_options(ctx)
+
+
+def test_fast_set_heuristics(ctx):
+    """-z > 1 announces a read set: the fixed-slot attempt is skipped; so is the call after an overflow on a similar input."""
+    reads = synth.reads_from_genome(30_000, 10.0, 150, 0.01, seed=3)
+    seq, off, ln = synth.frame_records(list(reads))
+    try:
+        _fast_options(ctx, fast_min_items=0, fast_heuristics=1)
+        runs0, fb0 = ctx.stat("fast_runs"), ctx.stat("fast_fallbacks")
+        a = ctx.compute(seq, k=31, min_frequency=2)
+        assert (ctx.stat("fast_runs"), ctx.stat("fast_fallbacks")) == (runs0, fb0)          # not even tried
+        s2 = np.frombuffer(b"A" * 300_000 + b"\n" + bytes(reads[0]) + b"\n", dtype=np.uint8)   # one k-mer far beyond any slot
+        b = ctx.compute(s2, k=31)                                                             # tried, overflows
+        assert ctx.stat("fast_fallbacks") == fb0 + 1
+        c = ctx.compute(s2, k=31)                                                             # remembered: not tried again
+        assert (ctx.stat("fast_runs"), ctx.stat("fast_fallbacks")) == (runs0, fb0 + 1)
+        assert b.ms == c.ms and b.n_kmers == c.n_kmers and a.n_kmers > 0
+        d = ctx.compute(seq[:40_000], k=31)                                                   # a much smaller input: tried again
+        assert ctx.stat("fast_runs") == runs0 + 1 and d.n_kmers > 0
+    finally:
+        _fast_options(ctx)
+        ctx.set_option("fast_heuristics", 1)
 
 
 def test_fast_set_config2_full_size(ctx):
