@@ -121,42 +121,41 @@ template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(S
                 for (u32 i = tid; i < g * H2; i += NT) tab[i] = KC_NONE;
                 if (tid == 0) s_groups = 0;  // reused as the hit mask of the group
                 __syncthreads();
-                for (u32 lev = 0; lev < g; ++lev) {
+                for (u32 item = tid; item < g * n_p; item += NT) {  // (level, prefix end) pairs spread over the whole block
+                    const u32 lev = item / n_p, i = item - lev * n_p;
                     const int d = d_hi - (int) lev;
                     u32 *tb = tab + lev * H2;
-                    for (u32 i = tid; i < n_p; i += NT) {
-                        const KWord<L> key = kmer_prefix(pk[i], v.k, d);
-                        u64 h = 0;
+                    const KWord<L> key = kmer_prefix(pk[i], v.k, d);
+                    u64 h = 0;
 #pragma unroll
-                        for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
-                        u32 sl = (u32) (h >> 40) & (H2 - 1);
-                        while (true) {
-                            const u32 old = atomicCAS(&tb[sl], KC_NONE, i);
-                            if (old == KC_NONE || kmer_prefix(pk[old], v.k, d) == key) break;
-                            sl = (sl + 1) & (H2 - 1);
-                        }
+                    for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
+                    u32 sl = (u32) (h >> 40) & (H2 - 1);
+                    while (true) {
+                        const u32 old = atomicCAS(&tb[sl], KC_NONE, i);
+                        if (old == KC_NONE || kmer_prefix(pk[old], v.k, d) == key) break;
+                        sl = (sl + 1) & (H2 - 1);
                     }
                 }
                 __syncthreads();
                 u32 hits = 0;
-                for (u32 lev = 0; lev < g; ++lev) {
+                for (u32 item = tid; item < g * n_s; item += NT) {
+                    const u32 lev = item / n_s, i = item - lev * n_s;
+                    if ((hits >> lev) & 1u) continue;
                     const int d = d_hi - (int) lev;
                     const u32 *tb = tab + lev * H2;
-                    for (u32 i = tid; i < n_s && !((hits >> lev) & 1u); i += NT) {
-                        const KWord<L> key = kmer_suffix(sk[i], d);
-                        u64 h = 0;
+                    const KWord<L> key = kmer_suffix(sk[i], d);
+                    u64 h = 0;
 #pragma unroll
-                        for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
-                        u32 sl = (u32) (h >> 40) & (H2 - 1);
-                        while (true) {
-                            const u32 o = tb[sl];
-                            if (o == KC_NONE) break;
-                            if (kmer_prefix(pk[o], v.k, d) == key) {
-                                hits |= 1u << lev;
-                                break;
-                            }
-                            sl = (sl + 1) & (H2 - 1);
+                    for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
+                    u32 sl = (u32) (h >> 40) & (H2 - 1);
+                    while (true) {
+                        const u32 o = tb[sl];
+                        if (o == KC_NONE) break;
+                        if (kmer_prefix(pk[o], v.k, d) == key) {
+                            hits |= 1u << lev;
+                            break;
                         }
+                        sl = (sl + 1) & (H2 - 1);
                     }
                 }
                 if (hits) atomicOr(&s_groups, hits);
