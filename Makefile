@@ -18,7 +18,7 @@ $(CSRC)/libkcgpu.so: $(CSRC)/kcgpu.o $(CSRC)/framing.o
 	$(NVCC) -shared -o $@ $^
 
 host/kmercamel: host/main.cpp include/kcgpu.h $(CSRC)/libkcgpu.so
-	$(CXX) -std=c++17 -O2 -Wall -Iinclude host/main.cpp -o $@ -L$(CSRC) -lkcgpu -lz -Wl,-rpath,'$$ORIGIN/../$(CSRC)'
+	$(CXX) -std=c++17 -O2 -Wall -pthread -Iinclude host/main.cpp -o $@ -L$(CSRC) -lkcgpu -lz -Wl,-rpath,'$$ORIGIN/../$(CSRC)'
 
 # tests-only: serial host emulation of the engine/emission control flow (no GPU needed, not part of the product)
 tests/host_emul: tests/host_emul.cu $(HDRS)

@@ -19,10 +19,25 @@
 #include <iomanip>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 static const char *VERSION = "kmercamel-b200 0.1 (compute path of KmerCamel v2.3.0)";
 static const int MAX_K = 127;  // reference src/main.cpp:93
+
+// Successful end of a GPU sub-command: everything has been written and flushed by the caller.  Tearing the CUDA context
+// down in user mode costs about as much as creating it (~1 s on a B200 box, more than all the work on a 50 Mbp input), so
+// the process leaves it to the operating system.
+[[noreturn]] static void finish_ok() {
+    std::cout.flush();
+    std::cerr.flush();
+    std::fflush(nullptr);
+    _exit(0);
+}
+
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 static void write_log(const std::string &message) {  // src/parser.h:159-164
     auto snapshot = std::chrono::system_clock::now();
@@ -155,11 +170,27 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
 
     if (!lower_bound) write_log("Started computation of a masked superstring from '" + path + "'.");
     else write_log("Started computation of a masked superstring length lower bound from '" + path + "'.");  // src/main.cpp:134
+    const double t_start = now_ms();
+    // the CUDA context (~1 s) is created while the file is read and framed
+    kc_ctx *ctx = nullptr;
+    int rc_init = KC_OK;
+    double t_init_done = 0;
+    std::thread init_thread([&] {
+        rc_init = kc_init(device, nullptr, &ctx);
+        t_init_done = now_ms();
+    });
+    struct Joiner {
+        std::thread &t;
+        ~Joiner() {
+            if (t.joinable()) t.join();
+        }
+    } joiner{init_thread};
     std::vector<unsigned char> data;
     if (!read_all(path, data)) {
         std::cerr << "couldn't open file " << path << std::endl;  // src/parser.h:95-97 throws invalid_argument
         return 1;
     }
+    const double t_read = now_ms();
     uint8_t *seq = nullptr;
     uint64_t n_bytes = 0, n_recs = 0, *rec_off = nullptr, *rec_len = nullptr;
     int rc = kc_frame_fasta(data.data(), data.size(), &seq, &n_bytes, &rec_off, &rec_len, &n_recs);
@@ -168,9 +199,11 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
         return 1;
     }
     std::vector<unsigned char>().swap(data);
+    const double t_frame = now_ms();
 
-    kc_ctx *ctx = nullptr;
-    rc = kc_init(device, nullptr, &ctx);
+    init_thread.join();
+    rc = rc_init;
+    const double t_init = now_ms();
     if (rc != KC_OK) {
         std::cerr << "cannot initialise CUDA device " << device << ": " << kc_strerror(rc) << " (this build has no CPU path)" << std::endl;
         return 1;
@@ -197,13 +230,11 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
         of->write(reinterpret_cast<const char *>(out.ms), (std::streamsize) out.length);
         *of << std::endl;
         write_log("Finished masked superstring computation.");
-        kc_destroy(ctx);
-        kc_free(seq);
-        kc_free(rec_off);
-        kc_free(rec_len);
-        return 0;
+        if (output.is_open()) output.close();
+        finish_ok();
     }
     rc = lower_bound ? kc_lower_bound(ctx, &p, &in, &bound, &out) : kc_compute(ctx, &p, &in, &out);
+    const double t_compute = now_ms();
     if (rc == KC_ERR_EMPTY && !assume_simplitigs) {  // src/main.cpp:155-158
         std::cerr << "Path '" << path << "' contains no k-mers. Make sure that your file is a FASTA or gzipped FASTA." << std::endl;
         kc_destroy(ctx);
@@ -221,11 +252,7 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
     if (lower_bound) {  // src/lower_bound.h:21, src/main.cpp:182,210
         write_log("Finished 3. part: lower bound = " + std::to_string(bound) + ".");
         std::cout << bound << std::endl;
-        kc_destroy(ctx);
-        kc_free(seq);
-        kc_free(rec_off);
-        kc_free(rec_len);
-        return 0;
+        finish_ok();
     }
     write_log("Finished 3. part: masked superstring (l=" + std::to_string(out.length) + ").");
     char times[256];
@@ -248,11 +275,13 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
         mask_output.write(reinterpret_cast<const char *>(out.ms_maxone), (std::streamsize) out.length);
         mask_output << std::endl;  // src/global.h:206-208
     }
-    kc_destroy(ctx);
-    kc_free(seq);
-    kc_free(rec_off);
-    kc_free(rec_len);
-    return 0;
+    if (of == &output) output.flush();
+    std::snprintf(times, sizeof(times), "Host stages [ms]: read %.1f, frame %.1f, CUDA context %.1f (in the background; waited %.1f), compute incl. H2D/D2H and arena %.1f, write %.1f",
+                  t_read - t_start, t_frame - t_read, t_init_done - t_start, t_init - t_frame, t_compute - t_init, now_ms() - t_compute);
+    write_log(times);
+    if (output.is_open()) output.close();
+    if (mask_output.is_open()) mask_output.close();
+    finish_ok();
 }
 
 // Reads the file and frames it; returns false after printing the reason.
@@ -357,16 +386,13 @@ static int camel_optimize(int argc, char **argv) {
     if (len >= (uint64_t) k && out.ms[len - k] > 'Z')  // src/masks.h:63-66 mask convention
         std::cerr << "Warning: the mask after optimization violates the mask convention as there are more than k-1 trailing zeros "
                      "(more than k-1 trailing lowercase characters)." << std::endl;
-    kc_destroy(ctx);
     if (n_recs > 1) {  // AssertEOF, src/masks.h:258 (the reference throws after having written the output)
         std::cerr << "Expecting only a single FASTA record -- the masked superstring." << std::endl;
         return 1;
     }
     write_log("Finished optimization.");
-    kc_free(seq);
-    kc_free(rec_off);
-    kc_free(rec_len);
-    return 0;
+    if (output.is_open()) output.close();
+    finish_ok();
 }
 
 // The four text conversions (src/main.cpp:444-667): host only.
