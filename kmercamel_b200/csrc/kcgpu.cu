@@ -40,6 +40,10 @@ struct kc_ctx {
     u8 *pin_out = nullptr;
     size_t pin_out_cap = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // kc_compute with host buffers: the input is copied in chunks on its own stream, the first partition pass follows the copy front
+    static const int KC_H2D_CHUNKS = 4;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_ev[KC_H2D_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
     bool small_engine = true;
     KsfTuning fast;          // histogram-free set construction (kmerset_fast.cuh); KC_FAST_* environment knobs for tests
     u64 fast_runs = 0, fast_fallbacks = 0;
@@ -162,6 +166,7 @@ struct DevInput {
     u64 n_bytes;
     const u64 *rec_off, *rec_len;
     u64 n_recs;
+    InputChunks *chunks = nullptr;  // != nullptr: seq is still being copied in (see InputChunks); wait before reading it
 };
 
 struct DevResult {
@@ -175,6 +180,7 @@ template <int L> u64 run_stage1(kc_ctx *ctx, CudaExec &ex, const DevInput &in, c
                                u64 *n_occ) {
     KC_CUDA(cudaEventRecord(ctx->ev[0], ex.stream));
     KC_CUDA(cudaEventRecord(ctx->ev[1], ex.stream));  // extraction is fused into the partition passes
+    if (in.chunks) in.chunks->wait_all(ex.stream);
     KmerSet<L> set = kc_kmerset_build<L>(ex, in.seq, in.n_bytes, p.k, p.complements != 0, p.min_frequency, nullptr, true);
     KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
     *n_occ = set.n_occ;
@@ -213,7 +219,7 @@ u64 run_stage1_runs(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_para
         KsfPlan plan;
         u64 *cells4 = ex.arena->alloc_top<u64>(4);  // {kept, runs, M, overflow status}
         ex.fill_bytes(cells4, 0, 32);
-        if (kc_kmerset_build_fast<L>(ex, in.seq, nb, p.k, p.complements != 0, p.min_frequency, flags, cells4, ctx->fast, &plan)) {
+        if (kc_kmerset_build_fast<L>(ex, in.seq, nb, p.k, p.complements != 0, p.min_frequency, flags, cells4, ctx->fast, &plan, in.chunks)) {
             KC_TRACE_POINT("stage1: fast set launched");
             u64 hc[4];
             bool aborted = false;
@@ -238,6 +244,7 @@ u64 run_stage1_runs(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_para
         }
     }
     // with -M the sorted k-mer set doubles as kMersDict of src/global.h:165-167; it stays at the arena bottom
+    if (in.chunks) in.chunks->wait_all(ex.stream);
     KmerSet<L> set = kc_kmerset_build<L>(ex, in.seq, nb, p.k, p.complements != 0, p.min_frequency, flags, p.want_maxone != 0, cells);
     KC_TRACE_POINT("stage1: set built");
     *n_occ = set.n_occ;
@@ -276,6 +283,7 @@ void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params
     ns.rec_len = in.rec_len;
     u64 n_nodes = 0;
     const u64 *node_off = in.rec_off, *node_len = in.rec_len;
+    if (in.chunks && (p.assume_simplitigs || ext_flags)) in.chunks->wait_all(ex.stream);
     if (!p.assume_simplitigs) {
         RunNodes runs;
         if (ext_flags) {  // sharded construction: the first-occurrence flags were reduced onto this GPU by the caller
@@ -486,6 +494,9 @@ void kc_destroy(kc_ctx *ctx) {
     if (ctx->p2p.dst_p) cudaFree(ctx->p2p.dst_p);
     for (int i = 0; i < 6; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < kc_ctx::KC_H2D_CHUNKS; ++i)
+        if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (cudaEvent_t e : ctx->prof.pool) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -536,9 +547,27 @@ int kc_compute(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *o
     DevResult res;
     run_with_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, simplitigs, false, &ctx->fast),
                    estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, simplitigs, true, &ctx->fast), [&] {
-        // host -> device
+        // host -> device.  Large from-FASTA inputs go in chunks on the copy stream: the level-0 partition pass of chunk c starts
+        // as soon as chunk c has landed (InputChunks), instead of after the whole copy.
         u8 *d_seq = ex.alloc<u8>(in->n_bytes + 64);
-        KC_CUDA(cudaMemcpyAsync(d_seq, in->seq, in->n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        InputChunks chunks;
+        const bool chunked = !simplitigs && in->n_bytes >= (8u << 20);
+        if (chunked) {
+            if (!ctx->copy_stream) {
+                KC_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+                for (int c = 0; c < kc_ctx::KC_H2D_CHUNKS; ++c) KC_CUDA(cudaEventCreateWithFlags(&ctx->chunk_ev[c], cudaEventDisableTiming));
+            }
+            const u64 granule = 32768;  // whole level-0 tiles for every word width
+            chunks.chunk_bytes = (in->n_bytes / kc_ctx::KC_H2D_CHUNKS + granule) / granule * granule;
+            chunks.ev = ctx->chunk_ev;
+            for (u64 off = 0; off < in->n_bytes; off += chunks.chunk_bytes) {
+                const u64 len = std::min<u64>(chunks.chunk_bytes, in->n_bytes - off);
+                KC_CUDA(cudaMemcpyAsync(d_seq + off, in->seq + off, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+                KC_CUDA(cudaEventRecord(ctx->chunk_ev[chunks.n++], ctx->copy_stream));
+            }
+        } else {
+            KC_CUDA(cudaMemcpyAsync(d_seq, in->seq, in->n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        }
         u64 *d_off = nullptr, *d_len = nullptr;
         if (simplitigs) {
             d_off = ex.alloc<u64>(in->n_recs);
@@ -546,8 +575,14 @@ int kc_compute(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *o
             KC_CUDA(cudaMemcpyAsync(d_off, in->rec_off, in->n_recs * 8, cudaMemcpyHostToDevice, ctx->stream));
             KC_CUDA(cudaMemcpyAsync(d_len, in->rec_len, in->n_recs * 8, cudaMemcpyHostToDevice, ctx->stream));
         }
-        DevInput di{d_seq, in->n_bytes, d_off, d_len, in->n_recs};
-        dispatch_pipeline(ctx, ex, di, *p, res);
+        DevInput di{d_seq, in->n_bytes, d_off, d_len, in->n_recs, chunked ? &chunks : nullptr};
+        try {
+            dispatch_pipeline(ctx, ex, di, *p, res);
+        } catch (...) {
+            if (chunked) cudaStreamSynchronize(ctx->copy_stream);  // `chunks` and the caller's buffer must outlive the copy
+            throw;
+        }
+        if (chunked) chunks.wait_all(ctx->stream);
     });
     // device -> pinned host
     const size_t need = (size_t) res.length * (res.maxone ? 2 : 1) + 64;

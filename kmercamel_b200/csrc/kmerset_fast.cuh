@@ -34,6 +34,20 @@ struct KsfTuning {
     int split0 = 0;          // level 0 (L = 1): two threads per 32-base strip (512-thread CTAs); measured slower (0.327 vs 0.315 ms), kept as an option
 };
 
+// Host-to-device copy of the sequence in flight on another stream, cut into chunks of whole level-0 tiles: event c is recorded
+// once bytes [0, (c + 1) * chunk_bytes) have landed.  The level-0 scatter of the fixed-slot construction waits per chunk, so
+// the first partition pass runs behind the copy front instead of after the whole copy (kc_compute with host buffers).
+struct InputChunks {
+    int n = 0;
+    u64 chunk_bytes = 0;     // a multiple of every KsCfg<L>::EX_TILE
+    cudaEvent_t *ev = nullptr;
+    bool waited = false;     // every chunk has been waited for on the compute stream
+    void wait_all(cudaStream_t st) {
+        if (n && !waited) KC_CUDA(cudaStreamWaitEvent(st, ev[n - 1], 0));
+        waited = true;
+    }
+};
+
 struct KsfPlan {
     bool ok = false;
     int n_levels = 0;
@@ -78,7 +92,7 @@ inline KsfPlan kc_ksf_plan(u64 m_upper, const KsfTuning &t) {
 template <int L>
 __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int complements,
                                                                                 int shift, int bits, u32 *bucket_cnt, u32 cap0,
-                                                                                KWord<L> *__restrict__ keys, u32 *__restrict__ pos, u32 *status) {
+                                                                                KWord<L> *__restrict__ keys, u32 *__restrict__ pos, u32 *status, u32 tile0) {
     constexpr int T = KsCfg<L>::EX_THREADS;
     constexpr int LOG_T = T == 256 ? 8 : (T == 128 ? 7 : 6);
     constexpr int R = 256 / T;
@@ -93,7 +107,7 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(c
     __shared__ u32 loff[256];
     __shared__ u32 gbase[256];
     __shared__ u32 sw[T / 32];
-    const i64 block_pos0 = (i64) blockIdx.x * TILE;
+    const i64 block_pos0 = (i64) (tile0 + blockIdx.x) * TILE;
     kc_tile_load<T>(seq, n_bytes, block_pos0, pk, vm);
     for (int i = threadIdx.x; i < 256; i += T) cnt[i] = 0;
 #pragma unroll
@@ -155,7 +169,7 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(c
 // round trips (short scoreboard) at 24 % occupancy.
 __global__ void __launch_bounds__(512) kc_ksf_scatter0_split_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int complements, int shift, int bits,
                                                                     u32 *bucket_cnt, u32 cap0, KWord<1> *__restrict__ keys, u32 *__restrict__ pos,
-                                                                    u32 *status) {
+                                                                    u32 *status, u32 tile0) {
     constexpr int S = 256;   // strips per tile
     constexpr int T = 512;
     constexpr int TILE = KsCfg<1>::EX_TILE;
@@ -169,7 +183,7 @@ __global__ void __launch_bounds__(512) kc_ksf_scatter0_split_kernel(const u8 *__
     __shared__ u32 loff[256];
     __shared__ u32 gbase[256];
     __shared__ u32 sw[T / 32];
-    const i64 block_pos0 = (i64) blockIdx.x * TILE;
+    const i64 block_pos0 = (i64) (tile0 + blockIdx.x) * TILE;
     if (threadIdx.x < S) {
         kc_tile_load<S>(seq, n_bytes, block_pos0, pk, vm);
         cnt[threadIdx.x] = 0;
@@ -531,7 +545,7 @@ __global__ void __launch_bounds__(256) kc_ksf_resolve_kernel(const KWord<L> *__r
 // Returns false (nothing launched) when the plan does not apply; the caller then uses kc_kmerset_build.
 template <int L>
 bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, int min_freq, u32 *flags, u64 *cells,
-                           const KsfTuning &tune, KsfPlan *plan_out = nullptr) {
+                           const KsfTuning &tune, KsfPlan *plan_out = nullptr, InputChunks *chunks = nullptr) {
     typedef KsCfg<L> Cfg;
     const KsfPlan pl = kc_ksf_plan(n_bytes, tune);
     if (plan_out) *plan_out = pl;
@@ -585,19 +599,34 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
     u32 *cnt_cur = cnt_all;
     {
         const u32 blocks = (u32) kc_div_up(n_bytes, (u64) Cfg::EX_TILE);
-        CudaExec::Scope sc(ex, KP_KS_SCATTER0, n_bytes + n_bytes * item_bytes);
-        bool split = false;
-        if constexpr (L == 1) {
-            if (tune.split0) {
-                split = true;
-                kc_ksf_scatter0_split_kernel<<<blocks, 512, smem0, st>>>(seq, n_bytes, k, complements ? 1 : 0, 64 * L - pl.cum[0], pl.bits[0], cnt_cur,
-                                                                         (u32) pl.cap[0], kb[0], pb[0], status);
+        // one launch, or one launch per chunk of an input that is still being copied in (each waits for its own chunk only)
+        const int n_parts = chunks && chunks->n > 1 && !chunks->waited ? chunks->n : 1;
+        if (chunks && n_parts == 1) chunks->wait_all(st);
+        for (int c = 0; c < n_parts; ++c) {
+            u32 t0 = 0, t1 = blocks;
+            if (n_parts > 1) {
+                KC_CUDA(cudaStreamWaitEvent(st, chunks->ev[c], 0));
+                t0 = (u32) std::min<u64>(blocks, (u64) c * (chunks->chunk_bytes / Cfg::EX_TILE));
+                t1 = c == n_parts - 1 ? blocks : (u32) std::min<u64>(blocks, (u64) (c + 1) * (chunks->chunk_bytes / Cfg::EX_TILE));
             }
+            if (t1 <= t0) continue;
+            const u64 part_bytes = std::min<u64>(n_bytes, (u64) t1 * Cfg::EX_TILE) - (u64) t0 * Cfg::EX_TILE;
+            CudaExec::Scope sc(ex, KP_KS_SCATTER0, part_bytes + part_bytes * item_bytes);
+            bool split = false;
+            if constexpr (L == 1) {
+                if (tune.split0) {
+                    split = true;
+                    kc_ksf_scatter0_split_kernel<<<t1 - t0, 512, smem0, st>>>(seq, n_bytes, k, complements ? 1 : 0, 64 * L - pl.cum[0], pl.bits[0], cnt_cur,
+                                                                              (u32) pl.cap[0], kb[0], pb[0], status, t0);
+                }
+            }
+            if (!split)
+                kc_ksf_scatter0_kernel<L><<<t1 - t0, Cfg::EX_THREADS, smem0, st>>>(seq, n_bytes, k, complements ? 1 : 0, 64 * L - pl.cum[0], pl.bits[0], cnt_cur,
+                                                                                 (u32) pl.cap[0], kb[0], pb[0], status, t0);
+            ++ex.launches;
+            KC_CUDA(cudaGetLastError());
         }
-        if (!split) kc_ksf_scatter0_kernel<L><<<blocks, Cfg::EX_THREADS, smem0, st>>>(seq, n_bytes, k, complements ? 1 : 0, 64 * L - pl.cum[0], pl.bits[0], cnt_cur,
-                                                                         (u32) pl.cap[0], kb[0], pb[0], status);
-        ++ex.launches;
-        KC_CUDA(cudaGetLastError());
+        if (chunks) chunks->waited = true;
     }
     // ---- levels >= 1 ----
     const u32 max_ctas = 148 * 8;
