@@ -201,8 +201,8 @@ def run_sharded_arm(args, rank, local_rank, world, ctx, part):
 
     ops.setup_p2p(comm, K)
 
-    def step():  # partition pass == all-to-all (peer stores over NVLink); see sharded.sharded_compute_p2p
-        return sharded.sharded_compute_p2p(ops, comm, full.numel(), k=K)
+    def step():  # partition pass == all-to-all (peer stores over NVLink); every rank emits its own slice of the superstring
+        return sharded.sharded_compute_p2p(ops, comm, full.numel(), k=K, slice_output=True)
 
     load()
     for _ in range(max(args.warmup, 3)):
@@ -224,8 +224,8 @@ def run_sharded_arm(args, rank, local_rank, world, ctx, part):
     prof = ctx.profile()
     ctx.profile_enable(False)
 
-    # end to end: pinned host part -> device -> all-gather -> sharded job -> superstring back on rank 0's host
-    host_out = torch.empty(world * part_len + 64, dtype=torch.uint8).pin_memory() if rank == 0 else None
+    # end to end: pinned host part -> device -> all-gather -> sharded job -> every rank's slice of the superstring back on its host
+    host_out = torch.empty(part_len + (1 << 20), dtype=torch.uint8).pin_memory()
     d2h = 0
     for timed in (False, True):
         barrier()
@@ -233,12 +233,17 @@ def run_sharded_arm(args, rank, local_rank, world, ctx, part):
         for _ in range(args.steps if timed else 2):
             load()
             r = step()
-            if rank == 0:
-                ctx._check(ctx._lib.kc_copy_to_host(ctx._h, host_out.data_ptr(), r.result.ms_ptr, r.result.length))
-                d2h = r.result.length
+            assert r.result.slice_len <= host_out.numel()
+            ctx._check(ctx._lib.kc_copy_to_host(ctx._h, host_out.data_ptr(), r.result.ms_ptr, r.result.slice_len))
+            d2h = r.result.slice_len
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
     barrier()
+    # the slices must tile the superstring: lengths add up, and each rank's slice carries the mask bits of its own range
+    ones = int((host_out[:d2h] <= 90).sum())
+    chk = torch.tensor([float(d2h), float(ones)], dtype=torch.float64, device=dev)
+    dist.all_reduce(chk, op=dist.ReduceOp.SUM)
+    assert int(chk[0]) == r.result.length and int(chk[1]) == r.n_kept, (chk.tolist(), r.result.length, r.n_kept)
     clocks = sampler.stop()
 
     t = torch.tensor([dev_ms, e2e_s * 1000.0, float(launches)], dtype=torch.float64, device=dev)
@@ -264,9 +269,9 @@ def run_sharded_arm(args, rank, local_rank, world, ctx, part):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic", "config": workload_config(world),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": part_len * world, "d2h_bytes_per_step": int(d2h),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": part_len * world, "d2h_bytes_per_step": int(r.result.length),
                 "ms_per_step": e2e_ms / args.steps,
-                "timer": "host perf_counter around H2D + all-gather + sharded job + D2H on rank 0, max over ranks"},
+                "timer": "host perf_counter around H2D + all-gather + sharded job + D2H of every rank's superstring slice, max over ranks"},
         "gpu_launches": launches, "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dname + " (rank 0)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": None, "peak_source": peak_src, "share_of_step": d["ms"] / dev_ms},

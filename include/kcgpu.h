@@ -167,6 +167,12 @@ int kc_shard_partition(kc_ctx *ctx, const kc_params *p, const uint8_t *seq_dev, 
 int kc_shard_resolve(kc_ctx *ctx, const kc_params *p, void *keys_dev, uint32_t *pos_dev, uint64_t n_items, uint32_t *flags_dev,
                      uint64_t *n_kept);
 int kc_compute_from_flags(kc_ctx *ctx, const kc_params *p, const kc_input *in, const uint32_t *flags_dev, uint64_t n_kept, kc_output *out);
+/* Same, but only slice `slice_index` of `n_slices` of the superstring is written: out->ms holds bytes [*slice_begin, *slice_begin +
+ * *slice_len) of it (boundaries are multiples of 16, the slices of indices 0..n_slices-1 tile the whole string), out->length is the
+ * length of the WHOLE superstring.  With the flags all-reduced, every rank runs the (deterministic) greedy stage and emits and
+ * copies back only its own slice, so the device-to-host copy of the result is spread over all the GPUs' links. */
+int kc_compute_from_flags_slice(kc_ctx *ctx, const kc_params *p, const kc_input *in, const uint32_t *flags_dev, uint64_t n_kept,
+                                uint32_t slice_index, uint32_t n_slices, kc_output *out, uint64_t *slice_begin, uint64_t *slice_len);
 
 /* Per-kernel-class device timing for roofline reports.  Enable, run kc_compute*, then read the table:
  * names[i], milliseconds, launches, algorithmic bytes (read once + written once). */

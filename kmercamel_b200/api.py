@@ -89,6 +89,8 @@ def load_library():
     L.kc_shard_resolve.argtypes = [C.c_void_p, C.POINTER(kc_params), C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, u64p]
     L.kc_compute_from_flags.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.c_void_p, C.c_uint64,
                                         C.POINTER(kc_output)]
+    L.kc_compute_from_flags_slice.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.c_void_p, C.c_uint64, C.c_uint32,
+                                              C.c_uint32, C.POINTER(kc_output), u64p, u64p]
     L.kc_p2p_alloc.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]
     L.kc_p2p_open.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.kc_p2p_hist.argtypes = [C.c_void_p, C.POINTER(kc_params), C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, u64p]
@@ -115,7 +117,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ["kc_init", "kc_destroy", "kc_compute", "kc_compute_device", "kc_lower_bound", "kc_copy_to_host", "kc_count_kmers", "kc_overlap_path",
-                    "kc_p2p_alloc", "kc_p2p_open", "kc_p2p_hist", "kc_p2p_scatter", "kc_p2p_resolve", "kc_total_launches", "kc_shard_granule", "kc_shard_partition", "kc_shard_resolve", "kc_compute_from_flags",
+                    "kc_p2p_alloc", "kc_p2p_open", "kc_p2p_hist", "kc_p2p_scatter", "kc_p2p_resolve", "kc_total_launches", "kc_shard_granule", "kc_shard_partition", "kc_shard_resolve", "kc_compute_from_flags", "kc_compute_from_flags_slice",
                     "kc_streaming", "kc_maskopt", "kc_split_ms", "kc_join_ms", "kc_ms_to_spss", "kc_spss_to_ms", "kc_fasta_first_header",
                     "kc_frame_fasta", "kc_set_option", "kc_get_stat", "kc_profile_enable", "kc_profile_count", "kc_profile_get", "kc_profile_reset",
                     "kc_limbs_for_k", "kc_free", "kc_strerror", "kc_last_error"]
@@ -218,6 +220,8 @@ class ComputeResult:
     times_ms: dict = field(default_factory=dict)
     ms_ptr: int = 0        # device pointers for compute_device
     maxone_ptr: int = 0
+    slice_begin: int = 0   # compute_from_flags(..., slice=(i, n)): ms_ptr holds bytes [slice_begin, slice_begin + slice_len)
+    slice_len: int = 0     # of the superstring (length = the whole superstring)
 
 
 class Context:
@@ -373,12 +377,22 @@ class Context:
                                                C.c_void_p(flags_ptr), C.byref(kept)))
         return kept.value
 
-    def compute_from_flags(self, seq_ptr: int, n_bytes: int, flags_ptr: int, n_kept: int, *, k, complements=True) -> ComputeResult:
+    def compute_from_flags(self, seq_ptr: int, n_bytes: int, flags_ptr: int, n_kept: int, *, k, complements=True, slice=None) -> ComputeResult:
+        """slice = (index, count): emit only that slice of the superstring (kc_compute_from_flags_slice)."""
         p = self._params(k, complements, 1, False, False)
         inp = kc_input(seq_ptr, n_bytes, None, None, 0)
         out = kc_output()
-        self._check(self._lib.kc_compute_from_flags(self._h, C.byref(p), C.byref(inp), C.c_void_p(flags_ptr), n_kept, C.byref(out)))
-        return self._result(out, False)
+        if slice is None:
+            self._check(self._lib.kc_compute_from_flags(self._h, C.byref(p), C.byref(inp), C.c_void_p(flags_ptr), n_kept, C.byref(out)))
+            r = self._result(out, False)
+            r.slice_len = r.length
+            return r
+        sb, sl = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.kc_compute_from_flags_slice(self._h, C.byref(p), C.byref(inp), C.c_void_p(flags_ptr), n_kept, int(slice[0]),
+                                                          int(slice[1]), C.byref(out), C.byref(sb), C.byref(sl)))
+        r = self._result(out, False)
+        r.slice_begin, r.slice_len = sb.value, sl.value
+        return r
 
     # ---- fused partition + exchange over peer memory (see include/kcgpu.h kc_p2p_*) ------------------------------------
     def p2p_alloc(self, k: int, capacity_items: int) -> np.ndarray:

@@ -155,14 +155,15 @@ __global__ void __launch_bounds__(256) kc_rank_small_kernel(PathState s, NodeSeq
 struct EmitResult {
     u8 *ms = nullptr;      // device, `length` bytes
     u8 *maxone = nullptr;  // device, `length` bytes, or nullptr
-    u64 length = 0;
+    u64 length = 0;        // of the WHOLE superstring
     u64 n_printed = 0;     // nodes on the printed strand
+    u64 slice_begin = 0, slice_len = 0;  // the part of it that `ms` holds (the whole superstring unless a slice was asked for)
 };
 
 // set_keys: sorted distinct (canonical when complements) k-mers, needed only for want_maxone.
 template <class Exec, int L>
 EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L> &nv, const PathState &st,
-                               const KWord<L> *set_keys, u64 n_set, bool want_maxone) {
+                               const KWord<L> *set_keys, u64 n_set, bool want_maxone, u32 slice_index = 0, u32 n_slices = 1) {
     EmitResult res;
     const u64 N = nv.N;
     const int k = nv.k;
@@ -242,9 +243,17 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
     // results live below the scratch: release the scratch first, then allocate outputs, then re-reserve scratch
     // is not possible with a bump arena, so outputs are allocated after the scratch and the scratch is leaked
     // until the caller releases its own mark.
-    u8 *ms = ex.template alloc<u8>(total + 1);
-    res.ms = ms;
+    // Multi-GPU: every rank walks the same path and writes only its slice [s_begin, s_end) of the superstring (boundaries are
+    // multiples of 16, so the 16-byte stores below stay aligned); `ms` is biased so that ms[a] is superstring position a.
+    if (n_slices > 1 && (ns.kmers || want_maxone)) KC_THROW(KC_ERR_ARG, "sliced emission is for record nodes without -M");
+    const u64 s_begin = n_slices > 1 ? ((total / n_slices) * slice_index) & ~(u64) 15 : 0;
+    const u64 s_end = n_slices > 1 && slice_index + 1 < n_slices ? ((total / n_slices) * (slice_index + 1)) & ~(u64) 15 : total;
+    u8 *ms_base = ex.template alloc<u8>(s_end - s_begin + 1);
+    u8 *ms = ms_base - s_begin;
+    res.ms = ms_base;
     res.length = total;
+    res.slice_begin = s_begin;
+    res.slice_len = s_end - s_begin;
     const u32 *fa = fin_a;
     const u64 *da = dist_a;
     if (ns.kmers) {
@@ -299,8 +308,10 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
             u64 cnt = len - (s.edge_from[v] != KC_NONE ? (u64) s.ovl[v] : 0);
             if (cnt > KC_EMIT_SHORT) return;
             u64 off = total - da[v];
+            if (off >= s_end || off + cnt <= s_begin) return;
             u64 n_upper = len - k + 1;
-            for (u64 j = 0; j < cnt; ++j) ms[off + j] = kc_letter(q.symbol(v, j), j < n_upper);
+            for (u64 j = 0; j < cnt; ++j)
+                if (off + j >= s_begin && off + j < s_end) ms[off + j] = kc_letter(q.symbol(v, j), j < n_upper);
         }, KP_EMIT, N * 12);
         ex.for_each((u64) n_chunks * 256, [=] KC_HD_LAMBDA(u64 w) {
             u32 chunk = (u32) (w >> 8), lane = (u32) (w & 255);
@@ -321,6 +332,8 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
             u64 a0 = (off & ~(u64) 15) + (u64) (chunk - chunks[v]) * KC_EMIT_CHUNK + (u64) lane * 16;
             u64 b0 = a0 < off ? off : a0;
             u64 b1 = a0 + 16 < off + cnt ? a0 + 16 : off + cnt;
+            if (b0 < s_begin) b0 = s_begin;  // slice boundaries are multiples of 16: an item is inside or outside as a whole
+            if (b1 > s_end) b1 = s_end;
             if (b0 >= b1) return;
             const u64 j0 = b0 - off;
 #ifdef __CUDA_ARCH__

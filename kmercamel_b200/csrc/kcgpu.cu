@@ -173,6 +173,7 @@ struct DevResult {
     const u8 *ms = nullptr, *maxone = nullptr;
     u64 length = 0, n_kmers = 0, n_occ = 0, n_nodes = 0;
     u64 lower_bound = 0;  // only with run_pipeline(..., lower_bound = true)
+    u64 slice_begin = 0, slice_len = 0;
 };
 
 // Stage 1 alone.  Leaves the sorted distinct k-mers (and their counts) at the current arena top and returns them.
@@ -267,7 +268,7 @@ u64 run_stage1_runs(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_para
 
 template <int L>
 void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, DevResult &res, const u32 *ext_flags = nullptr,
-                  u64 ext_kept = 0, bool lower_bound = false) {
+                  u64 ext_kept = 0, bool lower_bound = false, u32 slice_index = 0, u32 n_slices = 1) {
     const bool complements = p.complements != 0;
     KWord<L> *uniq = nullptr;
     u8 *cnt = nullptr;
@@ -363,7 +364,7 @@ void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params
     }
     EmitResult er;
     try {
-        er = kc_emit_superstring<CudaExec, L>(ex, ns, nv, eng.st, uniq, U, p.want_maxone != 0);
+        er = kc_emit_superstring<CudaExec, L>(ex, ns, nv, eng.st, uniq, U, p.want_maxone != 0, slice_index, n_slices);
     } catch (const KcError &) {
         eng.check_small();  // a failed small-engine run is the cause, report that one
         throw;
@@ -373,6 +374,8 @@ void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params
     res.ms = er.ms;
     res.maxone = er.maxone;
     res.length = er.length;
+    res.slice_begin = er.slice_begin;
+    res.slice_len = er.slice_len;
     res.n_kmers = U;
     res.n_occ = n_occ;
     res.n_nodes = nv.n;
@@ -852,7 +855,12 @@ int kc_shard_resolve(kc_ctx *ctx, const kc_params *p, void *keys_dev, uint32_t *
 }
 
 int kc_compute_from_flags(kc_ctx *ctx, const kc_params *p, const kc_input *in, const uint32_t *flags_dev, uint64_t n_kept, kc_output *out) {
-    if (!ctx || !in || !out || !flags_dev) return KC_ERR_ARG;
+    return kc_compute_from_flags_slice(ctx, p, in, flags_dev, n_kept, 0, 1, out, nullptr, nullptr);
+}
+
+int kc_compute_from_flags_slice(kc_ctx *ctx, const kc_params *p, const kc_input *in, const uint32_t *flags_dev, uint64_t n_kept, uint32_t slice_index,
+                                uint32_t n_slices, kc_output *out, uint64_t *slice_begin, uint64_t *slice_len) {
+    if (!ctx || !in || !out || !flags_dev || n_slices == 0 || slice_index >= n_slices) return KC_ERR_ARG;
     KC_API_BEGIN
     check_params(p);
     if (p->assume_simplitigs || p->want_maxone) KC_THROW(KC_ERR_ARG, "sharded construction supports neither -S nor -M");
@@ -867,11 +875,13 @@ int kc_compute_from_flags(kc_ctx *ctx, const kc_params *p, const kc_input *in, c
     const double c = p->complements ? 2.0 : 1.0;
     auto need = [&](double nodes) { return (size_t) ((c * nodes * (240.0 + 32.0 * limbs) + 3.0 * in->n_bytes) * 1.1) + (256u << 20); };
     run_with_arena(ctx, need(in->n_bytes / 64.0 + 1e6), need(in->n_bytes / 2.0), [&] {
-        if (p->k < 32) run_pipeline<1>(ctx, ex, di, *p, res, flags_dev, n_kept);
-        else if (p->k < 64) run_pipeline<2>(ctx, ex, di, *p, res, flags_dev, n_kept);
-        else run_pipeline<4>(ctx, ex, di, *p, res, flags_dev, n_kept);
+        if (p->k < 32) run_pipeline<1>(ctx, ex, di, *p, res, flags_dev, n_kept, false, slice_index, n_slices);
+        else if (p->k < 64) run_pipeline<2>(ctx, ex, di, *p, res, flags_dev, n_kept, false, slice_index, n_slices);
+        else run_pipeline<4>(ctx, ex, di, *p, res, flags_dev, n_kept, false, slice_index, n_slices);
     });
     KC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (slice_begin) *slice_begin = res.slice_begin;
+    if (slice_len) *slice_len = res.slice_len;
     out->ms = const_cast<u8 *>(res.ms);
     out->ms_maxone = nullptr;
     out->length = res.length;

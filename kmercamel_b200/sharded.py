@@ -67,9 +67,12 @@ def sharded_compute(ops, comm, n_bytes: int, *, k: int, complements: bool = True
     return ShardedResult(res, int(tot[0]), int(tot[1]), int(n_items - send[rank]), n_recv)
 
 
-def sharded_compute_p2p(ops, comm, n_bytes: int, *, k: int, complements: bool = True, min_frequency: int = 1) -> ShardedResult:
+def sharded_compute_p2p(ops, comm, n_bytes: int, *, k: int, complements: bool = True, min_frequency: int = 1,
+                        slice_output: bool = False) -> ShardedResult:
     """The product multi-GPU pass: the level-0 scatter stores every item straight into its owner's buffer over NVLink
-    (peer pointers), so there is no item all-to-all at all — only the 256 digit counts travel through a collective."""
+    (peer pointers), so there is no item all-to-all at all — only the 256 digit counts travel through a collective.
+    slice_output: the flags are ALL-reduced, every rank runs the (deterministic, sequential) greedy stage and emits slice
+    `rank` of the superstring; result.slice_begin / slice_len say which bytes result.ms_ptr holds on this rank."""
     world, rank = comm.world, comm.rank
     b, e = plan_slices(n_bytes, world, ops.granule(k))[rank]
     counts = ops.p2p_hist(b, e, k=k, complements=complements)                            # 256 digit counts of the slice
@@ -77,9 +80,12 @@ def sharded_compute_p2p(ops, comm, n_bytes: int, *, k: int, complements: bool = 
     ops.p2p_scatter(b, e, all_counts, k=k, complements=complements)                      # partition pass == all-to-all
     comm.barrier()                                                                       # every peer's stores have landed
     kept, owned = ops.p2p_resolve(all_counts, k=k, complements=complements, min_frequency=min_frequency)
-    ops.reduce_flags(comm)
+    ops.reduce_flags(comm, all_ranks=slice_output)
     tot = comm.sum_scalars([kept, int(counts.sum())])                                    # also fences the next pass's stores
-    res = ops.finish(int(tot[0]), k=k, complements=complements) if rank == 0 else None
+    if slice_output:
+        res = ops.finish(int(tot[0]), k=k, complements=complements, slice=(rank, world))
+    else:
+        res = ops.finish(int(tot[0]), k=k, complements=complements) if rank == 0 else None
     mine = int(all_counts[rank][[g for g in range(N_DIGITS) if owner_of_digit(g, world) == rank]].sum())
     return ShardedResult(res, int(tot[0]), int(tot[1]), int(counts.sum()) - mine, int(owned))
 
@@ -134,6 +140,10 @@ class TorchComm:
     def reduce_sum(self, t, dst: int = 0):
         if self.world > 1:
             self.dist.reduce(t, dst=dst, op=self.dist.ReduceOp.SUM)
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
 
     def sum_scalars(self, values):
         import torch
@@ -201,8 +211,11 @@ class GpuOps:
         return self.ctx.shard_resolve(keys.data_ptr(), pos.data_ptr(), n, self.flags.data_ptr(), k=k, complements=complements,
                                       min_frequency=min_frequency)
 
-    def reduce_flags(self, comm):
-        comm.reduce_sum(self.flags, 0)
+    def reduce_flags(self, comm, all_ranks: bool = False):
+        if all_ranks:
+            comm.all_reduce_sum(self.flags)
+        else:
+            comm.reduce_sum(self.flags, 0)
 
     # ---- fused partition + exchange (peer memory) --------------------------------------------------------------
     def setup_p2p(self, comm, k: int, slack: float = 1.25):
@@ -225,6 +238,7 @@ class GpuOps:
         self._order()
         return self.ctx.p2p_resolve(all_counts, self.flags.data_ptr(), k=k, complements=complements, min_frequency=min_frequency)
 
-    def finish(self, n_kept, *, k, complements):
+    def finish(self, n_kept, *, k, complements, slice=None):
         self._order()
-        return self.ctx.compute_from_flags(self.seq.data_ptr(), self.n_bytes, self.flags.data_ptr(), n_kept, k=k, complements=complements)
+        return self.ctx.compute_from_flags(self.seq.data_ptr(), self.n_bytes, self.flags.data_ptr(), n_kept, k=k, complements=complements,
+                                           slice=slice)

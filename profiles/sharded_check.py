@@ -35,6 +35,15 @@ for name, seed, zs in (("A", 12345 + rank, (1,)), ("B", 777, (1, 2))):
             print(f"{name} z={z}: sharded kept={r.n_kept} len={len(got)} | single kept={one.n_kmers} len={one.length} | identical={ok} md5={hashlib.md5(got).hexdigest()}", flush=True)
             ctx1.close()
         dist.barrier()
+        # sliced output: every rank emits its part; rank 0 checks that the parts tile the single-GPU superstring
+        rs = sharded.sharded_compute_p2p(ops, comm, full.numel(), k=K, min_frequency=z, slice_output=True)
+        mine = ctx.copy_to_host(rs.result.ms_ptr, rs.result.slice_len)
+        parts = [None] * world
+        dist.all_gather_object(parts, (rs.result.slice_begin, hashlib.md5(mine).hexdigest(), len(mine)))
+        if rank == 0:
+            ok = sum(p[2] for p in parts) == len(want) and all(hashlib.md5(want[b:b + n]).hexdigest() == h for b, h, n in parts)
+            print(f"{name} z={z}: sliced output over {world} ranks tiles the single-GPU superstring: {ok}", flush=True)
+        dist.barrier()
 print(f"rank {rank}: fast_runs={ctx.stat('fast_runs')} fast_fallbacks={ctx.stat('fast_fallbacks')}", flush=True)
 def T():
     torch.cuda.synchronize(); return time.perf_counter()

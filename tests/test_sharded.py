@@ -106,10 +106,13 @@ class CpuStandInOps:
         self.flags.copy_(torch.from_numpy(words.view(np.int32)))
         return int(keep.sum())
 
-    def reduce_flags(self, comm):
-        comm.reduce_sum(self.flags, 0)
+    def reduce_flags(self, comm, all_ranks: bool = False):
+        if all_ranks:
+            comm.all_reduce_sum(self.flags)
+        else:
+            comm.reduce_sum(self.flags, 0)
 
-    def finish(self, n_kept, *, k, complements):
+    def finish(self, n_kept, *, k, complements, slice=None):
         return self.flags.numpy().view(np.uint32).copy()
 
 
@@ -222,6 +225,37 @@ def test_sharded_p2p_world1_matches_kc_compute(stream_mode):
             r = sharded.sharded_compute_p2p(ops, comm, d.numel(), k=31, min_frequency=z)
             assert r.n_kept == want.n_kmers and r.result.length == want.length
             assert c.copy_to_host(r.result.ms_ptr, r.result.length) == want.ms
+    finally:
+        c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,n_slices", [(31, 3), (63, 8), (15, 2)])
+def test_sliced_emission_tiles_the_superstring(k, n_slices):
+    """kc_compute_from_flags_slice: the slices of indices 0..n-1 (what the ranks of a multi-GPU job emit) concatenate to exactly
+    the superstring of the unsliced call, for long runs (chunked 16-byte emission) and for thousands of short ones."""
+    import kmercamel_b200 as kb
+    c = kb.Context(0, torch.cuda.current_stream().cuda_stream)
+    try:
+        recs = synth.random_genome_records(3, 200_000, 31) + list(synth.reads_from_genome(30_000, 6.0, 150, 0.01, seed=k))
+        seq, _, _ = synth.frame_records(recs)
+        d = torch.from_numpy(seq).cuda()
+        ops = sharded.GpuOps(c, d)
+        comm = sharded.TorchComm(d.device)
+        ops.setup_p2p(comm, k)
+        whole = sharded.sharded_compute_p2p(ops, comm, d.numel(), k=k)
+        want = c.copy_to_host(whole.result.ms_ptr, whole.result.length)
+        assert want == kb.Context(0).compute(seq, k=k).ms
+        parts, at = [], 0
+        for i in range(n_slices):
+            r = c.compute_from_flags(d.data_ptr(), d.numel(), ops.flags.data_ptr(), whole.n_kept, k=k, slice=(i, n_slices))
+            assert r.length == len(want) and r.slice_begin == at and (r.slice_begin % 16 == 0)
+            parts.append(c.copy_to_host(r.ms_ptr, r.slice_len))
+            at += r.slice_len
+        assert at == len(want) and b"".join(parts) == want
+        sliced = sharded.sharded_compute_p2p(ops, comm, d.numel(), k=k, slice_output=True)     # world 1: one slice = everything
+        assert (sliced.result.slice_begin, sliced.result.slice_len) == (0, len(want))
+        assert c.copy_to_host(sliced.result.ms_ptr, sliced.result.slice_len) == want
     finally:
         c.close()
 
