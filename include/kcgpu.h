@@ -208,7 +208,8 @@ uint64_t kc_total_launches(const kc_ctx *ctx);
  * duplicates are expected (-z > 1, or the previous call on an input of similar size overflowed).  "fast_split0",
  * "fast_tile_variant": measured-and-rejected kernel variants kept for re-measurement.  Results never depend on these options. */
 int kc_set_option(kc_ctx *ctx, const char *name, int value);
-/* Counters since kc_init: "fast_runs", "fast_fallbacks", "total_launches". */
+/* Counters since kc_init: "fast_runs", "fast_fallbacks", "total_launches"; current value of the options "fast_resolve",
+ * "fast_tile_variant". */
 int kc_get_stat(const kc_ctx *ctx, const char *name, uint64_t *value);
 
 int kc_limbs_for_k(int k);

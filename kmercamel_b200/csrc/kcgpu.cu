@@ -467,7 +467,7 @@ int kc_init(int device, void *stream, kc_ctx **out) {
         }
         for (int i = 0; i < 6; ++i) KC_CUDA(cudaEventCreate(&ctx->ev[i]));
         if (const char *e = std::getenv("KC_FAST_SET")) ctx->fast.enabled = std::atoi(e) != 0;
-        if (const char *e = std::getenv("KC_FAST_RESOLVE")) ctx->fast.resolve = std::atoi(e) != 0;
+        if (const char *e = std::getenv("KC_FAST_RESOLVE")) ctx->fast.resolve = std::atoi(e);
         if (const char *e = std::getenv("KC_FAST_TILE")) ctx->fast.tile_variant = std::atoi(e);
         if (const char *e = std::getenv("KC_FAST_SPLIT0")) ctx->fast.split0 = std::atoi(e) != 0;
     } catch (const KcError &e) {
@@ -1102,6 +1102,8 @@ int kc_get_stat(const kc_ctx *ctx, const char *name, uint64_t *value) {
     if (std::strcmp(name, "fast_runs") == 0) *value = ctx->fast_runs;
     else if (std::strcmp(name, "fast_fallbacks") == 0) *value = ctx->fast_fallbacks;
     else if (std::strcmp(name, "total_launches") == 0) *value = ctx->total_launches;
+    else if (std::strcmp(name, "fast_resolve") == 0) *value = (uint64_t) ctx->fast.resolve;
+    else if (std::strcmp(name, "fast_tile_variant") == 0) *value = (uint64_t) ctx->fast.tile_variant;
     else return KC_ERR_ARG;
     return KC_OK;
 }
@@ -1126,7 +1128,7 @@ int kc_set_option(kc_ctx *ctx, const char *name, int value) {
         ctx->fast.sigmas = (double) value;
         return KC_OK;
     }
-    if (std::strcmp(name, "fast_resolve") == 0 && (value == 0 || value == 1)) {
+    if (std::strcmp(name, "fast_resolve") == 0 && value >= 0 && value <= 3) {
         ctx->fast.resolve = value;
         return KC_OK;
     }
@@ -1135,7 +1137,7 @@ int kc_set_option(kc_ctx *ctx, const char *name, int value) {
         ctx->fast_overflow_bytes = 0;
         return KC_OK;
     }
-    if (std::strcmp(name, "fast_tile_variant") == 0 && value >= 0 && value <= 2) {
+    if (std::strcmp(name, "fast_tile_variant") == 0 && value >= 0 && value <= 4) {
         ctx->fast.tile_variant = value;
         return KC_OK;
     }

@@ -29,8 +29,11 @@ struct KsfTuning {
     u32 leaf_target = 768;   // mean leaf size aimed at (the leaf slot holds KSF_LEAF_CAP)
     double sigmas = 8.0;     // slot = mean + sigmas * sqrt(mean) (+ 2 %) items; 0 forces overflows (tests)
     u64 min_items = 1u << 16;  // smaller inputs take the exact path (nothing to gain)
-    int resolve = 1;         // 1 = kc_ksf_resolve_kernel (cp.async, two barriers), 0 = kc_ks_resolve_hash_kernel over a bucket list
-    int tile_variant = 0;    // level >= 1 scatter: 0 = KsCfg<L>::TILE items per tile, 3 CTAs/SM; 1 = half tiles, 5 CTAs/SM; 2 = 3/4 tiles, 4 CTAs/SM
+    int resolve = 3;         // 1 = kc_ksf_resolve_kernel (cp.async, two barriers), 0 = kc_ks_resolve_hash_kernel over a bucket list,
+                             // 2 = as 1 with clear-the-losers flags (level 0 writes the valid-window bits, a duplicate clears one),
+                             // 3 = kc_ksf_resolve1_kernel: clear-the-losers + double-buffered tables, ONE barrier per leaf (-z 1 only)
+    int tile_variant = 3;    // level >= 1 scatter: 0 = KsCfg<L>::TILE items per tile, 3 CTAs/SM; 1 = half tiles, 5 CTAs/SM; 2 = 3/4 tiles, 4 CTAs/SM;
+                             // 3 / 4 = kc_ksf_scatter_pf_kernel (next tile streams in with cp.async) with full / half tiles
     int split0 = 0;          // level 0 (L = 1): two threads per 32-base strip (512-thread CTAs); measured slower (0.327 vs 0.315 ms), kept as an option
 };
 
@@ -92,7 +95,8 @@ inline KsfPlan kc_ksf_plan(u64 m_upper, const KsfTuning &t) {
 template <int L>
 __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int complements,
                                                                                 int shift, int bits, u32 *bucket_cnt, u32 cap0,
-                                                                                KWord<L> *__restrict__ keys, u32 *__restrict__ pos, u32 *status, u32 tile0) {
+                                                                                KWord<L> *__restrict__ keys, u32 *__restrict__ pos, u32 *status, u32 tile0,
+                                                                                u32 *__restrict__ valid_flags = nullptr, u32 n_flag_words = 0) {
     constexpr int T = KsCfg<L>::EX_THREADS;
     constexpr int LOG_T = T == 256 ? 8 : (T == 128 ? 7 : 6);
     constexpr int R = 256 / T;
@@ -115,6 +119,10 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(c
     __syncthreads();
     const int widx = KC_EX_HALO + threadIdx.x;
     const u32 em = kc_strip_emit_mask(vm, widx, k);
+    if (valid_flags) {  // clear-the-losers flags: every window starts as "first occurrence" (bit p & 31 of word p >> 5 = window END p)
+        const u64 w = (u64) (block_pos0 >> 5) + threadIdx.x;
+        if (em && w < n_flag_words) valid_flags[w] = __brev(em);
+    }
     kc_strip_windows<L>(pk, widx, em, k, complements, [&](int j, const KWord<L> &c0) {
         const KWord<L> c = kmer_scramble(c0);
         const u32 slot = (u32) j * T + threadIdx.x;
@@ -403,7 +411,13 @@ KC_D void kc_cp_async16(void *smem_dst, const void *gmem_src) {
 KC_D void kc_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 KC_D void kc_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-template <int L, bool COUNTED>
+KC_D void kc_flag_clear(u32 *flags, u32 pos) { atomicAnd(&flags[pos >> 5], ~(1u << (pos & 31))); }
+
+// CLEAR = false: `flags` arrives zeroed and every kept k-mer sets the bit of its smallest position (M scattered REDs).
+// CLEAR = true : `flags` arrives with the bit of every valid window set (written by level 0, one coalesced word per strip);
+//                every atomicMin that folds a duplicate knocks out exactly one position — the larger of the two it compared —
+//                so only the DUPLICATES cost a scattered RED (a genome: ~0 of them) and the kept bits are never touched.
+template <int L, bool COUNTED, bool CLEAR = false>
 __global__ void __launch_bounds__(256) kc_ksf_resolve_kernel(const KWord<L> *__restrict__ keys, const u32 *__restrict__ pos, const u32 *__restrict__ cnt,
                                                              u32 n_leaf, u32 *flags, u32 min_count, kc_ull *n_unique, u32 *status) {
     constexpr u32 CAP = KSF_LEAF_CAP;
@@ -493,7 +507,9 @@ __global__ void __launch_bounds__(256) kc_ksf_resolve_kernel(const KWord<L> *__r
                     if (o == i) {
                         rep |= 1u << (m * KPC + e);
                     } else if (sk[o] == key) {
-                        atomicMin(&sp[o], sp[i]);
+                        const u32 mine = sp[i];
+                        const u32 was = atomicMin(&sp[o], mine);
+                        if (CLEAR) kc_flag_clear(flags, was > mine ? was : mine);
                         if (COUNTED) atomicAdd(&occ[o], 1u);
                     } else {
                         u32 s = (u32) (h >> 43) & (T2N - 1);
@@ -504,7 +520,9 @@ __global__ void __launch_bounds__(256) kc_ksf_resolve_kernel(const KWord<L> *__r
                                 break;
                             }
                             if (sk[old] == key) {
-                                atomicMin(&sp[old], sp[i]);
+                                const u32 mine = sp[i];
+                                const u32 was = atomicMin(&sp[old], mine);
+                                if (CLEAR) kc_flag_clear(flags, was > mine ? was : mine);
                                 if (COUNTED) atomicAdd(&occ[old], 1u);
                                 break;
                             }
@@ -522,9 +540,12 @@ __global__ void __launch_bounds__(256) kc_ksf_resolve_kernel(const KWord<L> *__r
 #pragma unroll
                 for (int e = 0; e < KPC; ++e) {
                     const u32 i = q * KPC + e;
-                    if (((rep >> (m * KPC + e)) & 1u) && (!COUNTED || occ[i] >= min_count)) {
-                        kc_flag_set(flags, sp[i]);
+                    if (!((rep >> (m * KPC + e)) & 1u)) continue;
+                    if (!COUNTED || occ[i] >= min_count) {
+                        if (!CLEAR) kc_flag_set(flags, sp[i]);
                         ++kept;
+                    } else if (CLEAR) {
+                        kc_flag_clear(flags, sp[i]);  // too few occurrences: the surviving (smallest) position goes as well
                     }
                 }
             }
@@ -537,6 +558,231 @@ __global__ void __launch_bounds__(256) kc_ksf_resolve_kernel(const KWord<L> *__r
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) kept += __shfl_down_sync(0xFFFFFFFFu, kept, o);
     if ((threadIdx.x & 31) == 0 && kept) atomicAdd(n_unique, (kc_ull) kept);
+}
+
+// ---- leaf resolve, one barrier per leaf (-z 1, clear-the-losers flags) ---------------------------------------------------------
+// With clear-the-losers flags phase C of kc_ksf_resolve_kernel has nothing left to write, so the barrier in front of it only
+// protects the tables from the next leaf's phase A.  Two sets of tables (T1 as u16 indices, T2 as u32 for the CAS) alternate
+// with the staging buffers instead: leaf n + 1 fills the set that leaf n - 1 used, and every thread is past leaf n - 1 once it
+// has crossed the barrier of leaf n.  Shared memory per CTA (L = 1): 16 + 8 + 8 + 8 = 40 KB -> 5 CTAs per SM.
+template <int L>
+__global__ void __launch_bounds__(256) kc_ksf_resolve1_kernel(const KWord<L> *__restrict__ keys, const u32 *__restrict__ pos, const u32 *__restrict__ cnt,
+                                                              u32 n_leaf, u32 *flags, kc_ull *n_unique, u32 *status) {
+    constexpr u32 CAP = KSF_LEAF_CAP;
+    constexpr u32 T1N = 2 * CAP, T2N = CAP;
+    constexpr int KPC = 16 / (int) sizeof(KWord<L>) > 0 ? 16 / (int) sizeof(KWord<L>) : 1;
+    constexpr int CPK = (int) sizeof(KWord<L>) / 16 > 0 ? (int) sizeof(KWord<L>) / 16 : 1;
+    extern __shared__ __align__(16) unsigned char kc_smem_raw[];
+    KWord<L> *sk0 = reinterpret_cast<KWord<L> *>(kc_smem_raw);
+    u32 *sp0 = reinterpret_cast<u32 *>(sk0 + 2 * CAP);
+    u32 *T2a = sp0 + 2 * CAP;                                  // [2][T2N]
+    u16 *T1a = reinterpret_cast<u16 *>(T2a + 2 * T2N);         // [2][T1N]
+    const u32 stride = gridDim.x;
+    u32 c = blockIdx.x;
+    if (c >= n_leaf) return;
+    auto fetch = [&](u32 bucket, u32 size, int buf) {
+        const char *gk = reinterpret_cast<const char *>(keys + (u64) bucket * CAP);
+        const char *gp = reinterpret_cast<const char *>(pos + (u64) bucket * CAP);
+        char *dk = reinterpret_cast<char *>(sk0 + (u32) buf * CAP);
+        char *dp = reinterpret_cast<char *>(sp0 + (u32) buf * CAP);
+        const u32 n_units = (size + KPC - 1) / KPC, pchunks = (size * 4 + 15) / 16;
+        for (u32 u = threadIdx.x; u < n_units; u += 256) {
+#pragma unroll
+            for (int cc = 0; cc < CPK; ++cc) kc_cp_async16(dk + 16 * (u * CPK + cc), gk + 16 * (u * CPK + cc));
+        }
+        for (u32 q = threadIdx.x; q < pchunks; q += 256) kc_cp_async16(dp + 16 * q, gp + 16 * q);
+        kc_cp_async_commit();
+    };
+    u32 size = cnt[c];
+    if (size > CAP) {
+        size = CAP;
+        if (threadIdx.x == 0) status[0] = 1;
+    }
+    fetch(c, size, 0);
+    int buf = 0;
+    u32 kept = 0;
+    while (true) {
+        const u32 cn = c + stride;
+        u32 size_n = 0;
+        if (cn < n_leaf) {
+            size_n = cnt[cn];
+            if (size_n > CAP) {
+                size_n = CAP;
+                if (threadIdx.x == 0) status[0] = 1;
+            }
+        }
+        KWord<L> *sk = sk0 + (u32) buf * CAP;
+        u32 *sp = sp0 + (u32) buf * CAP;
+        u32 *T2 = T2a + (u32) buf * T2N;
+        u16 *T1 = T1a + (u32) buf * T1N;
+        kc_cp_async_wait_all();  // the thread's own chunks of leaf c have landed
+        const u32 n_chunk_items = (size + KPC - 1) / KPC;
+        reinterpret_cast<uint4 *>(T2)[threadIdx.x] = make_uint4(KC_NONE, KC_NONE, KC_NONE, KC_NONE);  // T2N = 256 x 4 slots
+        // A: some item of every key group wins the group's T1 slot (plain 16-bit stores)
+        for (u32 q = threadIdx.x; q < n_chunk_items; q += 256) {
+#pragma unroll
+            for (int e = 0; e < KPC; ++e) {
+                const u32 i = q * KPC + e;
+                if (i < size) {
+                    u64 h = 0;
+#pragma unroll
+                    for (int w = 0; w < L; ++w) h = (h ^ sk[i].w[w]) * 0xD6E8FEB86659FD93ULL;
+                    T1[h >> 53] = (u16) i;
+                }
+            }
+        }
+        __syncthreads();
+        if (cn < n_leaf) fetch(cn, size_n, buf ^ 1);  // every thread is past phase B of the leaf that used that buffer
+        // B: winners represent their key; a duplicate folds its position and clears the larger of the two
+        for (u32 q = threadIdx.x; q < n_chunk_items; q += 256) {
+#pragma unroll
+            for (int e = 0; e < KPC; ++e) {
+                const u32 i = q * KPC + e;
+                if (i >= size) continue;
+                const KWord<L> key = sk[i];
+                u64 h = 0;
+#pragma unroll
+                for (int w = 0; w < L; ++w) h = (h ^ key.w[w]) * 0xD6E8FEB86659FD93ULL;
+                const u32 o = T1[h >> 53];
+                if (o == i) {
+                    ++kept;
+                } else if (sk[o] == key) {
+                    const u32 mine = sp[i];
+                    const u32 was = atomicMin(&sp[o], mine);
+                    kc_flag_clear(flags, was > mine ? was : mine);
+                } else {
+                    u32 s = (u32) (h >> 43) & (T2N - 1);
+                    while (true) {
+                        const u32 old = atomicCAS(&T2[s], KC_NONE, i);
+                        if (old == KC_NONE) {
+                            ++kept;
+                            break;
+                        }
+                        if (sk[old] == key) {
+                            const u32 mine = sp[i];
+                            const u32 was = atomicMin(&sp[old], mine);
+                            kc_flag_clear(flags, was > mine ? was : mine);
+                            break;
+                        }
+                        s = (s + 1) & (T2N - 1);
+                    }
+                }
+            }
+        }
+        if (cn >= n_leaf) break;
+        c = cn;
+        size = size_n;
+        buf ^= 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kept += __shfl_down_sync(0xFFFFFFFFu, kept, o);
+    if ((threadIdx.x & 31) == 0 && kept) atomicAdd(n_unique, (kc_ull) kept);
+}
+
+// ---- levels >= 1 with the next tile in flight ---------------------------------------------------------------------------------
+// kc_ksf_scatter_kernel issues a tile's loads and then waits for them (ncu: long scoreboard, 47 % of the HBM peak).  Here the
+// tile after the current one streams into a shared-memory input buffer with cp.async while the current tile is ranked,
+// staged and written out: a thread takes its items out of the input buffer into registers, and the barrier that ends the
+// ranking phase frees the buffer for the next copy.  Tiles are contiguous in their parent slot, slots are 128-byte aligned.
+template <int L, int TILE, int MINB>
+__global__ void __launch_bounds__(256, MINB) kc_ksf_scatter_pf_kernel(const KWord<L> *__restrict__ ksrc, const u32 *__restrict__ psrc, KWord<L> *__restrict__ kdst,
+                                                                u32 *__restrict__ pdst, const u32 *__restrict__ P_size, const u32 *__restrict__ tile_prefix,
+                                                                u32 nP, u64 capP, u32 tiles_per_cta, int shift, int bits, u32 *C_cnt, u32 capC, u32 *status) {
+    constexpr int ITEMS = TILE / 256;
+    extern __shared__ __align__(16) unsigned char kc_smem_raw[];
+    KWord<L> *in_k = reinterpret_cast<KWord<L> *>(kc_smem_raw);
+    KWord<L> *stage_k = in_k + TILE;
+    u32 *in_p = reinterpret_cast<u32 *>(stage_k + TILE);
+    u32 *stage_p = in_p + TILE;
+    u16 *rk = reinterpret_cast<u16 *>(stage_p + TILE);
+    __shared__ u32 cnt[256];
+    __shared__ u32 loff[256];
+    __shared__ u32 gbase[256];
+    __shared__ u32 sw[8];
+    const u32 n_tiles = tile_prefix[nP];
+    const u32 t0 = blockIdx.x * tiles_per_cta;
+    const u32 t1 = min(n_tiles, t0 + tiles_per_cta);
+    if (t0 >= t1) return;
+    u32 b = kc_upper_bound_u32(tile_prefix, nP + 1, t0) - 1;
+    cnt[threadIdx.x] = 0;
+    bool over = false;
+    // tile t of the CTA -> (parent bucket, first item inside the source arrays, items)
+    auto describe = [&](u32 t, u32 &bb, u64 &first, u32 &n_here) {
+        while (t >= tile_prefix[bb + 1]) ++bb;
+        const u32 start = (t - tile_prefix[bb]) * TILE;
+        n_here = min((u32) TILE, P_size[bb] - start);
+        first = (u64) bb * capP + start;
+    };
+    auto prefetch = [&](u64 first, u32 n_here) {
+        const char *gk = reinterpret_cast<const char *>(ksrc + first);
+        const char *gp = reinterpret_cast<const char *>(psrc + first);
+        const u32 kch = (n_here * (u32) sizeof(KWord<L>) + 15) / 16, pch = (n_here * 4 + 15) / 16;
+        for (u32 q = threadIdx.x; q < kch; q += 256) kc_cp_async16(reinterpret_cast<char *>(in_k) + 16 * q, gk + 16 * q);
+        for (u32 q = threadIdx.x; q < pch; q += 256) kc_cp_async16(reinterpret_cast<char *>(in_p) + 16 * q, gp + 16 * q);
+        kc_cp_async_commit();
+    };
+    u64 first;
+    u32 n_here;
+    describe(t0, b, first, n_here);
+    prefetch(first, n_here);
+    for (u32 t = t0; t < t1; ++t) {
+        kc_cp_async_wait_all();
+        __syncthreads();  // tile t is complete in the input buffer; the write-out of tile t - 1 has left the staging buffers
+        KWord<L> item[ITEMS];
+        u32 pay[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const u32 i = threadIdx.x + j * 256;
+            if (i < n_here) {
+                item[j] = in_k[i];
+                pay[j] = in_p[i];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const u32 i = threadIdx.x + j * 256;
+            if (i < n_here) rk[i] = (u16) atomicAdd(&cnt[item[j].digit(shift, bits)], 1u);
+        }
+        __syncthreads();  // counts complete, input buffer free
+        u32 b_next = b, n_next = 0;
+        u64 first_next = 0;
+        if (t + 1 < t1) {
+            describe(t + 1, b_next, first_next, n_next);
+            prefetch(first_next, n_next);
+        }
+        const u32 c = cnt[threadIdx.x];
+        u32 total;
+        const u32 p = kc_block_exclusive_scan<256>(c, &total, sw);
+        loff[threadIdx.x] = p;
+        if (c) gbase[threadIdx.x] = atomicAdd(&C_cnt[((u64) b << bits) + threadIdx.x], c);
+        cnt[threadIdx.x] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const u32 i = threadIdx.x + j * 256;
+            if (i < n_here) {
+                const u32 q = loff[item[j].digit(shift, bits)] + rk[i];
+                stage_k[q] = item[j];
+                stage_p[q] = pay[j];
+            }
+        }
+        __syncthreads();
+        for (u32 q = threadIdx.x; q < n_here; q += 256) {
+            const KWord<L> v = stage_k[q];
+            const u32 dg = v.digit(shift, bits);
+            const u32 idx = gbase[dg] + (q - loff[dg]);
+            if (idx < capC) {
+                const u64 at = (((u64) b << bits) + dg) * capC + idx;
+                kdst[at] = v;
+                pdst[at] = stage_p[q];
+            } else {
+                over = true;
+            }
+        }
+        b = b_next;
+        n_here = n_next;
+    }
+    if (over) status[0] = 1;
 }
 
 // Launches the whole construction on ex.stream and returns without synchronising.
@@ -568,8 +814,10 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
 
     const int smem0 = Cfg::EX_TILE * ((int) sizeof(KWord<L>) + 4);
     const int tv = tune.tile_variant;
-    const int tile1 = tv == 1 ? Cfg::TILE / 2 : (tv == 2 ? Cfg::TILE * 3 / 4 : Cfg::TILE);
-    const int smem1 = tile1 * ((int) sizeof(KWord<L>) + 4 + 2);
+    const int tile1 = (tv == 1 || tv == 4) ? Cfg::TILE / 2 : (tv == 2 ? Cfg::TILE * 3 / 4 : Cfg::TILE);
+    const bool pf = tv == 3 || tv == 4;  // input tile double-buffered in shared memory
+    const int smem1 = tile1 * ((pf ? 2 : 1) * ((int) sizeof(KWord<L>) + 4) + 2);
+    const bool clear_flags = tune.resolve >= 2;  // level 0 writes the valid-window bits, the resolve clears the losers
     const bool counted = min_freq > 1;
     constexpr int CA = KSF_LEAF_CAP;
     const int per_item = (int) sizeof(KWord<L>) + 12 + 4;
@@ -585,6 +833,10 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
         KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_kernel<L, Cfg::TILE * 3 / 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::TILE * 3 / 4 * ((int) sizeof(KWord<L>) + 4 + 2)));
         KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter0_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KsCfg<1>::EX_TILE * 12));
+        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_pf_kernel<L, Cfg::TILE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::TILE * (2 * ((int) sizeof(KWord<L>) + 4) + 2)));
+        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_pf_kernel<L, Cfg::TILE / 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::TILE / 2 * (2 * ((int) sizeof(KWord<L>) + 4) + 2)));
         KC_CUDA(cudaFuncSetAttribute(kc_ks_resolve_hash_kernel<L, CA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CA * per_item));
         KC_CUDA(cudaFuncSetAttribute(kc_ks_resolve_hash_kernel<L, CA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CA * (per_item + 4)));
         int dev = 0;
@@ -614,7 +866,7 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
             CudaExec::Scope sc(ex, KP_KS_SCATTER0, part_bytes + part_bytes * item_bytes);
             bool split = false;
             if constexpr (L == 1) {
-                if (tune.split0) {
+                if (tune.split0 && !clear_flags) {
                     split = true;
                     kc_ksf_scatter0_split_kernel<<<t1 - t0, 512, smem0, st>>>(seq, n_bytes, k, complements ? 1 : 0, 64 * L - pl.cum[0], pl.bits[0], cnt_cur,
                                                                               (u32) pl.cap[0], kb[0], pb[0], status, t0);
@@ -622,7 +874,8 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
             }
             if (!split)
                 kc_ksf_scatter0_kernel<L><<<t1 - t0, Cfg::EX_THREADS, smem0, st>>>(seq, n_bytes, k, complements ? 1 : 0, 64 * L - pl.cum[0], pl.bits[0], cnt_cur,
-                                                                                 (u32) pl.cap[0], kb[0], pb[0], status, t0);
+                                                                                 (u32) pl.cap[0], kb[0], pb[0], status, t0, clear_flags ? flags : nullptr,
+                                                                                 (u32) (kc_div_up(n_bytes, (u64) 32) + 1));  // = kc_runs_flag_words(n_bytes)
             ++ex.launches;
             KC_CUDA(cudaGetLastError());
         }
@@ -645,7 +898,13 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
         const u32 ctas = (u32) kc_div_up(tiles_ub, tiles_per_cta);
         {
             CudaExec::Scope sc(ex, KP_SORT_SCATTER, 2 * n_bytes * item_bytes);
-            if (tv == 1) kc_ksf_scatter_kernel<L, Cfg::TILE / 2, 5><<<ctas, 256, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
+            if (tv == 3) kc_ksf_scatter_pf_kernel<L, Cfg::TILE, 2><<<ctas, 256, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
+                                                               pl.cap[lv - 1], tiles_per_cta, 64 * L - pl.cum[lv], pl.bits[lv], cnt_next, (u32) pl.cap[lv],
+                                                               status);
+            else if (tv == 4) kc_ksf_scatter_pf_kernel<L, Cfg::TILE / 2, 4><<<ctas, 256, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
+                                                               pl.cap[lv - 1], tiles_per_cta, 64 * L - pl.cum[lv], pl.bits[lv], cnt_next, (u32) pl.cap[lv],
+                                                               status);
+            else if (tv == 1) kc_ksf_scatter_kernel<L, Cfg::TILE / 2, 5><<<ctas, 256, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
                                                                pl.cap[lv - 1], tiles_per_cta, 64 * L - pl.cum[lv], pl.bits[lv], cnt_next, (u32) pl.cap[lv],
                                                                status);
             else if (tv == 2) kc_ksf_scatter_kernel<L, Cfg::TILE * 3 / 4, 4><<<ctas, 256, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
@@ -673,13 +932,30 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
             if (c) atomicAdd(m_cell, (kc_ull) c);
         });
     }
-    if (tune.resolve == 1) {
+    if (tune.resolve == 3 && !counted) {
+        const int smem3 = (int) KSF_LEAF_CAP * (16 * L + 8 + 8 + 8);  // per leaf item: keys x2, positions x2, T2 x2 (u32), T1 x2 (two u16 slots per item)
+        static bool attr3_done = false;
+        static int occ3 = 0;
+        if (!attr3_done) {
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve1_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, kc_ksf_resolve1_kernel<L>, 256, smem3));
+            attr3_done = true;
+        }
+        const u32 fit = (u32) (n_sm * (occ3 > 0 ? occ3 : 1));
+        const u32 grid = n_small < fit ? n_small : fit;
+        CudaExec::Scope sc(ex, KP_KS_RESOLVE, n_bytes * item_bytes);
+        kc_ksf_resolve1_kernel<L><<<grid, 256, smem3, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, n_unique, status);
+        ++ex.launches;
+        KC_CUDA(cudaGetLastError());
+    } else if (tune.resolve >= 1) {
         const int smem2 = (int) KSF_LEAF_CAP * (16 * L + 20 + (counted ? 4 : 0));
         static bool attr2_done = false;
         static int occ2[2] = {0, 0};
         if (!attr2_done) {
             KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (16 * L + 20)));
             KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (16 * L + 24)));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (16 * L + 20)));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (16 * L + 24)));
             KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2[0], kc_ksf_resolve_kernel<L, false>, 256, (int) KSF_LEAF_CAP * (16 * L + 20)));
             KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2[1], kc_ksf_resolve_kernel<L, true>, 256, (int) KSF_LEAF_CAP * (16 * L + 24)));
             attr2_done = true;
@@ -687,8 +963,12 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
         const u32 fit = (u32) (n_sm * (occ2[counted] > 0 ? occ2[counted] : 1));
         const u32 grid = n_small < fit ? n_small : fit;
         CudaExec::Scope sc(ex, KP_KS_RESOLVE, n_bytes * item_bytes);
-        if (counted)
+        if (counted && clear_flags)
+            kc_ksf_resolve_kernel<L, true, true><<<grid, 256, smem2, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, (u32) min_freq, n_unique, status);
+        else if (counted)
             kc_ksf_resolve_kernel<L, true><<<grid, 256, smem2, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, (u32) min_freq, n_unique, status);
+        else if (clear_flags)
+            kc_ksf_resolve_kernel<L, false, true><<<grid, 256, smem2, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, (u32) min_freq, n_unique, status);
         else
             kc_ksf_resolve_kernel<L, false><<<grid, 256, smem2, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, (u32) min_freq, n_unique, status);
         ++ex.launches;
