@@ -205,11 +205,19 @@ uint64_t kc_total_launches(const kc_ctx *ctx);
  * "fast_set" (default 1): try the histogram-free k-mer set construction first (from-FASTA compute without -M);
  * "fast_leaf_target", "fast_sigmas", "fast_min_items": its plan parameters, exposed so that tests reach the
  * multi-level plan and the overflow fallback with small inputs; "fast_heuristics" (default 1): skip the attempt when
- * duplicates are expected (-z > 1, or the previous call on an input of similar size overflowed).  "fast_split0",
- * "fast_tile_variant": measured-and-rejected kernel variants kept for re-measurement.  Results never depend on these options. */
+ * duplicates are expected (-z > 1, or the previous call on an input of similar size overflowed).
+ * Kernel variants of that construction, kept selectable so that every measurement in profiles/ can be repeated
+ * (profiles/variant_sweep.py; defaults = the fastest measured):
+ *   "fast_resolve"      0 bucket-list resolve of the exact path, 1 two-barrier leaf resolve (set-the-winners flags),
+ *                       2 the same with clear-the-losers flags, 3 / 4 / 5 one-barrier resolve with 2 / 3 / 4 staging buffers,
+ *                       6 / 7 one-barrier resolve with a thread's items staged in registers (256 / 512 threads);
+ *   "fast_tile_variant" level >= 1 scatter: 0 / 1 / 2 plain with full / half / three-quarter tiles, 3 / 4 next tile streaming
+ *                       in through cp.async with full / half tiles, 5 as 3 with 512-thread CTAs;
+ *   "fast_max_ctas"     upper bound of that scatter's grid (0 = 148 * 8);  "fast_split0": two threads per level-0 strip.
+ * Results never depend on these options. */
 int kc_set_option(kc_ctx *ctx, const char *name, int value);
 /* Counters since kc_init: "fast_runs", "fast_fallbacks", "total_launches"; current value of the options "fast_resolve",
- * "fast_tile_variant". */
+ * "fast_tile_variant", "fast_max_ctas". */
 int kc_get_stat(const kc_ctx *ctx, const char *name, uint64_t *value);
 
 int kc_limbs_for_k(int k);

@@ -11,6 +11,7 @@
 //   exclusive_scan(in, out, n)     u32 exclusive prefix sum, returns the total
 //   fill / copy / read             memset-like helpers and a synchronising scalar read-back
 #pragma once
+#include <cstring>
 #include "kc_common.cuh"
 #include <vector>
 
@@ -183,6 +184,8 @@ struct CudaExec {
     Arena *arena;
     KernelProf *prof = nullptr;
     u64 launches = 0;  // kernels launched through this policy (bench.py reports it as gpu_launches)
+    u8 *pinned = nullptr;  // page-locked host scratch of the context for the synchronising read-backs below: a pageable
+    size_t pinned_cap = 0;  // destination makes the driver stage the copy, which costs several us per read on an idle stream
 
     // RAII timer around one kernel launch (or a short fixed group of launches) of class `id`.
     struct Scope {
@@ -226,13 +229,19 @@ struct CudaExec {
     }
     template <typename T> T read(const T *p) {
         T v;
-        KC_CUDA(cudaMemcpyAsync(&v, p, sizeof(T), cudaMemcpyDeviceToHost, stream));
-        KC_CUDA(cudaStreamSynchronize(stream));
+        read_n(p, &v, 1);
         return v;
     }
     void sync() { KC_CUDA(cudaStreamSynchronize(stream)); }
     template <typename T> void read_n(const T *p, T *host, size_t n) {  // one synchronising read-back of n values
-        KC_CUDA(cudaMemcpyAsync(host, p, n * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        const size_t bytes = n * sizeof(T);
+        if (pinned && bytes <= pinned_cap) {
+            KC_CUDA(cudaMemcpyAsync(pinned, p, bytes, cudaMemcpyDeviceToHost, stream));
+            KC_CUDA(cudaStreamSynchronize(stream));
+            std::memcpy(host, pinned, bytes);
+            return;
+        }
+        KC_CUDA(cudaMemcpyAsync(host, p, bytes, cudaMemcpyDeviceToHost, stream));
         KC_CUDA(cudaStreamSynchronize(stream));
     }
 

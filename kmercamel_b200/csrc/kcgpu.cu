@@ -39,6 +39,8 @@ struct kc_ctx {
     size_t pin_in_cap = 0;
     u8 *pin_out = nullptr;
     size_t pin_out_cap = 0;
+    static const size_t KC_PIN_SMALL = 4096;
+    u8 *pin_small = nullptr;  // page-locked scratch for the small synchronising read-backs (CudaExec::read_n)
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // kc_compute with host buffers: the input is copied in chunks on its own stream, the first partition pass follows the copy front
     static const int KC_H2D_CHUNKS = 4;
@@ -466,9 +468,11 @@ int kc_init(int device, void *stream, kc_ctx **out) {
             ctx->own_stream = true;
         }
         for (int i = 0; i < 6; ++i) KC_CUDA(cudaEventCreate(&ctx->ev[i]));
+        KC_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->pin_small), kc_ctx::KC_PIN_SMALL, cudaHostAllocDefault));
         if (const char *e = std::getenv("KC_FAST_SET")) ctx->fast.enabled = std::atoi(e) != 0;
         if (const char *e = std::getenv("KC_FAST_RESOLVE")) ctx->fast.resolve = std::atoi(e);
         if (const char *e = std::getenv("KC_FAST_TILE")) ctx->fast.tile_variant = std::atoi(e);
+        if (const char *e = std::getenv("KC_FAST_MAX_CTAS")) ctx->fast.max_ctas = std::atoi(e);
         if (const char *e = std::getenv("KC_FAST_SPLIT0")) ctx->fast.split0 = std::atoi(e) != 0;
     } catch (const KcError &e) {
         int code = e.code;
@@ -485,6 +489,7 @@ void kc_destroy(kc_ctx *ctx) {
     if (ctx->arena.base) cudaFree(ctx->arena.base);
     if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
     if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+    if (ctx->pin_small) cudaFreeHost(ctx->pin_small);
     for (int r = 0; r < ctx->p2p.n_ranks && r < KC_MAX_PEERS; ++r)
         if (ctx->p2p.opened[r]) {
             cudaIpcCloseMemHandle(ctx->p2p.peer_k[r]);
@@ -515,6 +520,8 @@ int kc_compute_device(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_ou
     const int limbs = kc_limbs_for_k(p->k);
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
+    ex.pinned = ctx->pin_small;
+    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
     DevInput di{in->seq, in->n_bytes, in->rec_off, in->rec_len, in->n_recs};
     DevResult res;
     KC_TRACE_POINT("compute_device: start");
@@ -547,6 +554,8 @@ int kc_compute(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *o
     const bool simplitigs = p->assume_simplitigs != 0;
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
+    ex.pinned = ctx->pin_small;
+    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
     DevResult res;
     run_with_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, simplitigs, false, &ctx->fast),
                    estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, simplitigs, true, &ctx->fast), [&] {
@@ -624,6 +633,8 @@ int kc_lower_bound(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t
     const bool simplitigs = p->assume_simplitigs != 0;
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
+    ex.pinned = ctx->pin_small;
+    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
     DevResult res;
     run_with_arena(ctx, estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, simplitigs, false, &ctx->fast),
                    estimate_arena(in->n_bytes, in->n_recs, limbs, p->complements != 0, simplitigs, true, &ctx->fast), [&] {
@@ -681,6 +692,8 @@ int kc_streaming(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output 
     ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
+    ex.pinned = ctx->pin_small;
+    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
     std::memset(out, 0, sizeof(*out));
     KC_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     const u64 padded = (in->n_bytes + 31) / 32 * 32 + 64;
@@ -716,6 +729,8 @@ int kc_maskopt(kc_ctx *ctx, const uint8_t *ms, uint64_t n, int k, int complement
     ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
+    ex.pinned = ctx->pin_small;
+    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
     std::memset(out, 0, sizeof(*out));
     KC_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     u8 *d_seq = ex.alloc<u8>(n + 64);
@@ -759,6 +774,8 @@ int kc_count_kmers(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t
     ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
+    ex.pinned = ctx->pin_small;
+    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
     u8 *d_seq = ex.alloc<u8>(in->n_bytes + 64);
     KC_CUDA(cudaMemcpyAsync(d_seq, in->seq, in->n_bytes, cudaMemcpyHostToDevice, ctx->stream));
     DevInput di{d_seq, in->n_bytes, nullptr, nullptr, in->n_recs};
@@ -783,6 +800,8 @@ int kc_overlap_path(kc_ctx *ctx, const uint64_t *first, const uint64_t *last, ui
     ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
+    ex.pinned = ctx->pin_small;
+    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
     if (k < 32) overlap_only<1>(ctx, ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
     else if (k < 64) overlap_only<2>(ctx, ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
     else overlap_only<4>(ctx, ex, first, last, n, k, complements != 0, lower_bound != 0, strict != 0, edge_from, overlaps);
@@ -811,6 +830,8 @@ int kc_shard_partition(kc_ctx *ctx, const kc_params *p, const uint8_t *seq_dev, 
     ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
+    ex.pinned = ctx->pin_small;
+    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
     KsShard sh;
     sh.pos_begin = pos_begin;
     sh.pos_end = pos_end;
@@ -842,6 +863,8 @@ int kc_shard_resolve(kc_ctx *ctx, const kc_params *p, void *keys_dev, uint32_t *
     ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
+    ex.pinned = ctx->pin_small;
+    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
     KsShard sh;
     sh.keys = keys_dev;
     sh.pos = pos_dev;
@@ -869,6 +892,8 @@ int kc_compute_from_flags_slice(kc_ctx *ctx, const kc_params *p, const kc_input 
     const int limbs = kc_limbs_for_k(p->k);
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
+    ex.pinned = ctx->pin_small;
+    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
     DevInput di{in->seq, in->n_bytes, in->rec_off, in->rec_len, in->n_recs};
     DevResult res;
     // no stage 1 here: only the node-dependent part (+ the emission scratch) is needed
@@ -971,6 +996,8 @@ int kc_p2p_hist(kc_ctx *ctx, const kc_params *p, const uint8_t *seq_dev, uint64_
     ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
+    ex.pinned = ctx->pin_small;
+    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
     KsShard sh;
     sh.pos_begin = pos_begin;
     sh.pos_end = pos_end;
@@ -1027,6 +1054,8 @@ int kc_p2p_scatter(kc_ctx *ctx, const kc_params *p, const uint8_t *seq_dev, uint
     ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
+    ex.pinned = ctx->pin_small;
+    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
     KsShard sh;
     sh.pos_begin = pos_begin;
     sh.pos_end = pos_end;
@@ -1068,6 +1097,8 @@ int kc_p2p_resolve(kc_ctx *ctx, const kc_params *p, const uint64_t *all_counts, 
     ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
+    ex.pinned = ctx->pin_small;
+    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
     KsShard sh;
     sh.keys = q.recv_k;
     sh.pos = q.recv_p;
@@ -1104,6 +1135,7 @@ int kc_get_stat(const kc_ctx *ctx, const char *name, uint64_t *value) {
     else if (std::strcmp(name, "total_launches") == 0) *value = ctx->total_launches;
     else if (std::strcmp(name, "fast_resolve") == 0) *value = (uint64_t) ctx->fast.resolve;
     else if (std::strcmp(name, "fast_tile_variant") == 0) *value = (uint64_t) ctx->fast.tile_variant;
+    else if (std::strcmp(name, "fast_max_ctas") == 0) *value = (uint64_t) ctx->fast.max_ctas;
     else return KC_ERR_ARG;
     return KC_OK;
 }
@@ -1128,7 +1160,7 @@ int kc_set_option(kc_ctx *ctx, const char *name, int value) {
         ctx->fast.sigmas = (double) value;
         return KC_OK;
     }
-    if (std::strcmp(name, "fast_resolve") == 0 && value >= 0 && value <= 3) {
+    if (std::strcmp(name, "fast_resolve") == 0 && value >= 0 && value <= 8) {
         ctx->fast.resolve = value;
         return KC_OK;
     }
@@ -1137,8 +1169,12 @@ int kc_set_option(kc_ctx *ctx, const char *name, int value) {
         ctx->fast_overflow_bytes = 0;
         return KC_OK;
     }
-    if (std::strcmp(name, "fast_tile_variant") == 0 && value >= 0 && value <= 4) {
+    if (std::strcmp(name, "fast_tile_variant") == 0 && value >= 0 && value <= 5) {
         ctx->fast.tile_variant = value;
+        return KC_OK;
+    }
+    if (std::strcmp(name, "fast_max_ctas") == 0 && value >= 0 && value <= (1 << 20)) {
+        ctx->fast.max_ctas = value;
         return KC_OK;
     }
     if (std::strcmp(name, "fast_split0") == 0 && (value == 0 || value == 1)) {

@@ -29,11 +29,16 @@ struct KsfTuning {
     u32 leaf_target = 768;   // mean leaf size aimed at (the leaf slot holds KSF_LEAF_CAP)
     double sigmas = 8.0;     // slot = mean + sigmas * sqrt(mean) (+ 2 %) items; 0 forces overflows (tests)
     u64 min_items = 1u << 16;  // smaller inputs take the exact path (nothing to gain)
-    int resolve = 3;         // 1 = kc_ksf_resolve_kernel (cp.async, two barriers), 0 = kc_ks_resolve_hash_kernel over a bucket list,
+    int resolve = 6;         // 1 = kc_ksf_resolve_kernel (cp.async, two barriers), 0 = kc_ks_resolve_hash_kernel over a bucket list,
                              // 2 = as 1 with clear-the-losers flags (level 0 writes the valid-window bits, a duplicate clears one),
-                             // 3 = kc_ksf_resolve1_kernel: clear-the-losers + double-buffered tables, ONE barrier per leaf (-z 1 only)
-    int tile_variant = 3;    // level >= 1 scatter: 0 = KsCfg<L>::TILE items per tile, 3 CTAs/SM; 1 = half tiles, 5 CTAs/SM; 2 = 3/4 tiles, 4 CTAs/SM;
-                             // 3 / 4 = kc_ksf_scatter_pf_kernel (next tile streams in with cp.async) with full / half tiles
+                             // 3 = kc_ksf_resolve1_kernel: clear-the-losers + double-buffered tables, ONE barrier per leaf (-z 1 only),
+                             // 4 / 5 = the same with 3 / 4 staging buffers in the ring (two / three leaves in flight per CTA),
+                             // 6 / 7 = kc_ksf_resolve2_kernel: as 3 with a thread's items staged in registers, 256 / 512 threads,
+                             // 8 = as 6 with 8-byte copy units (every thread the same number of items) and the leaf size loaded a leaf ahead
+    int tile_variant = 5;    // level >= 1 scatter: 0 = KsCfg<L>::TILE items per tile, 3 CTAs/SM; 1 = half tiles, 5 CTAs/SM; 2 = 3/4 tiles, 4 CTAs/SM;
+                             // 3 / 4 = kc_ksf_scatter_pf_kernel (next tile streams in with cp.async) with full / half tiles,
+                             // 5 = full tiles and 512-thread CTAs (2 per SM: 32 instead of 16 warps)
+    int max_ctas = 148 * 16; // level >= 1 scatter grid: at most this many CTAs, each walking a run of consecutive tiles (0 = 148 * 8)
     int split0 = 0;          // level 0 (L = 1): two threads per 32-base strip (512-thread CTAs); measured slower (0.327 vs 0.315 ms), kept as an option
 };
 
@@ -563,9 +568,15 @@ __global__ void __launch_bounds__(256) kc_ksf_resolve_kernel(const KWord<L> *__r
 // ---- leaf resolve, one barrier per leaf (-z 1, clear-the-losers flags) ---------------------------------------------------------
 // With clear-the-losers flags phase C of kc_ksf_resolve_kernel has nothing left to write, so the barrier in front of it only
 // protects the tables from the next leaf's phase A.  Two sets of tables (T1 as u16 indices, T2 as u32 for the CAS) alternate
-// with the staging buffers instead: leaf n + 1 fills the set that leaf n - 1 used, and every thread is past leaf n - 1 once it
-// has crossed the barrier of leaf n.  Shared memory per CTA (L = 1): 16 + 8 + 8 + 8 = 40 KB -> 5 CTAs per SM.
-template <int L>
+// instead: leaf n + 1 fills the set that leaf n - 1 used, and every thread is past leaf n - 1 once it has crossed the barrier
+// of leaf n.
+// STAGES staging buffers form a ring: while leaf n is resolved, leaves n + 1 .. n + STAGES - 1 are in flight (cp.async groups,
+// one per leaf).  With two stages the kernel ran at 2.5 TB/s = exactly the bytes in flight (5 CTAs x 9 KB per SM) over the
+// ~2.7 us a leaf took, i.e. it was bound by DRAM latency through Little's law, not by its instructions.
+// Shared memory per CTA (L = 1): STAGES x 12 KB + 16 KB of tables.
+template <int N> KC_D void kc_cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <int L, int STAGES>
 __global__ void __launch_bounds__(256) kc_ksf_resolve1_kernel(const KWord<L> *__restrict__ keys, const u32 *__restrict__ pos, const u32 *__restrict__ cnt,
                                                               u32 n_leaf, u32 *flags, kc_ull *n_unique, u32 *status) {
     constexpr u32 CAP = KSF_LEAF_CAP;
@@ -574,48 +585,56 @@ __global__ void __launch_bounds__(256) kc_ksf_resolve1_kernel(const KWord<L> *__
     constexpr int CPK = (int) sizeof(KWord<L>) / 16 > 0 ? (int) sizeof(KWord<L>) / 16 : 1;
     extern __shared__ __align__(16) unsigned char kc_smem_raw[];
     KWord<L> *sk0 = reinterpret_cast<KWord<L> *>(kc_smem_raw);
-    u32 *sp0 = reinterpret_cast<u32 *>(sk0 + 2 * CAP);
-    u32 *T2a = sp0 + 2 * CAP;                                  // [2][T2N]
+    u32 *sp0 = reinterpret_cast<u32 *>(sk0 + STAGES * CAP);
+    u32 *T2a = sp0 + STAGES * CAP;                             // [2][T2N]
     u16 *T1a = reinterpret_cast<u16 *>(T2a + 2 * T2N);         // [2][T1N]
-    const u32 stride = gridDim.x;
-    u32 c = blockIdx.x;
+    const u64 stride = gridDim.x;
+    u64 c = blockIdx.x;
     if (c >= n_leaf) return;
-    auto fetch = [&](u32 bucket, u32 size, int buf) {
-        const char *gk = reinterpret_cast<const char *>(keys + (u64) bucket * CAP);
-        const char *gp = reinterpret_cast<const char *>(pos + (u64) bucket * CAP);
-        char *dk = reinterpret_cast<char *>(sk0 + (u32) buf * CAP);
-        char *dp = reinterpret_cast<char *>(sp0 + (u32) buf * CAP);
-        const u32 n_units = (size + KPC - 1) / KPC, pchunks = (size * 4 + 15) / 16;
-        for (u32 u = threadIdx.x; u < n_units; u += 256) {
-#pragma unroll
-            for (int cc = 0; cc < CPK; ++cc) kc_cp_async16(dk + 16 * (u * CPK + cc), gk + 16 * (u * CPK + cc));
+    auto leaf_size = [&](u64 leaf) -> u32 {
+        if (leaf >= n_leaf) return 0u;
+        u32 sz = cnt[leaf];
+        if (sz > CAP) {
+            sz = CAP;
+            if (threadIdx.x == 0) status[0] = 1;
         }
-        for (u32 q = threadIdx.x; q < pchunks; q += 256) kc_cp_async16(dp + 16 * q, gp + 16 * q);
+        return sz;
+    };
+    // one cp.async group per leaf, empty when the CTA has run out of leaves (keeps the group count uniform)
+    auto fetch = [&](u64 bucket, u32 size, int buf) {
+        if (bucket < n_leaf) {
+            const char *gk = reinterpret_cast<const char *>(keys + bucket * CAP);
+            const char *gp = reinterpret_cast<const char *>(pos + bucket * CAP);
+            char *dk = reinterpret_cast<char *>(sk0 + (u32) buf * CAP);
+            char *dp = reinterpret_cast<char *>(sp0 + (u32) buf * CAP);
+            // a thread copies whole units (L = 1: a pair of keys, otherwise one key), so the keys it hashes in phase A are the
+            // ones it fetched itself
+            const u32 n_units = (size + KPC - 1) / KPC, pchunks = (size * 4 + 15) / 16;
+            for (u32 u = threadIdx.x; u < n_units; u += 256) {
+#pragma unroll
+                for (int cc = 0; cc < CPK; ++cc) kc_cp_async16(dk + 16 * (u * CPK + cc), gk + 16 * (u * CPK + cc));
+            }
+            for (u32 q = threadIdx.x; q < pchunks; q += 256) kc_cp_async16(dp + 16 * q, gp + 16 * q);
+        }
         kc_cp_async_commit();
     };
-    u32 size = cnt[c];
-    if (size > CAP) {
-        size = CAP;
-        if (threadIdx.x == 0) status[0] = 1;
+    u32 sz[STAGES];  // sz[i] = size of leaf c + i * stride
+#pragma unroll
+    for (int i = 0; i < STAGES - 1; ++i) {
+        sz[i] = leaf_size(c + (u64) i * stride);
+        fetch(c + (u64) i * stride, sz[i], i);
     }
-    fetch(c, size, 0);
-    int buf = 0;
+    int buf = 0, par = 0;
     u32 kept = 0;
     while (true) {
-        const u32 cn = c + stride;
-        u32 size_n = 0;
-        if (cn < n_leaf) {
-            size_n = cnt[cn];
-            if (size_n > CAP) {
-                size_n = CAP;
-                if (threadIdx.x == 0) status[0] = 1;
-            }
-        }
+        const u64 c_far = c + (u64) (STAGES - 1) * stride;
+        sz[STAGES - 1] = leaf_size(c_far);
+        const u32 size = sz[0];
         KWord<L> *sk = sk0 + (u32) buf * CAP;
         u32 *sp = sp0 + (u32) buf * CAP;
-        u32 *T2 = T2a + (u32) buf * T2N;
-        u16 *T1 = T1a + (u32) buf * T1N;
-        kc_cp_async_wait_all();  // the thread's own chunks of leaf c have landed
+        u32 *T2 = T2a + (u32) par * T2N;
+        u16 *T1 = T1a + (u32) par * T1N;
+        kc_cp_async_wait_group<STAGES - 2>();  // the thread's own chunks of leaf c have landed
         const u32 n_chunk_items = (size + KPC - 1) / KPC;
         reinterpret_cast<uint4 *>(T2)[threadIdx.x] = make_uint4(KC_NONE, KC_NONE, KC_NONE, KC_NONE);  // T2N = 256 x 4 slots
         // A: some item of every key group wins the group's T1 slot (plain 16-bit stores)
@@ -632,7 +651,11 @@ __global__ void __launch_bounds__(256) kc_ksf_resolve1_kernel(const KWord<L> *__
             }
         }
         __syncthreads();
-        if (cn < n_leaf) fetch(cn, size_n, buf ^ 1);  // every thread is past phase B of the leaf that used that buffer
+        {   // every thread is past phase B of the leaf that used the ring slot behind the newest one
+            int far = buf + STAGES - 1;
+            if (far >= STAGES) far -= STAGES;
+            fetch(c_far, sz[STAGES - 1], far);
+        }
         // B: winners represent their key; a duplicate folds its position and clears the larger of the two
         for (u32 q = threadIdx.x; q < n_chunk_items; q += 256) {
 #pragma unroll
@@ -669,13 +692,175 @@ __global__ void __launch_bounds__(256) kc_ksf_resolve1_kernel(const KWord<L> *__
                 }
             }
         }
+        if (c + stride >= n_leaf) break;
+        c += stride;
+#pragma unroll
+        for (int i = 0; i < STAGES - 1; ++i) sz[i] = sz[i + 1];
+        buf = buf + 1 == STAGES ? 0 : buf + 1;
+        par ^= 1;
+    }
+    kc_cp_async_wait_group<0>();  // only empty groups are left
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kept += __shfl_down_sync(0xFFFFFFFFu, kept, o);
+    if ((threadIdx.x & 31) == 0 && kept) atomicAdd(n_unique, (kc_ull) kept);
+}
+
+// ---- one-barrier leaf resolve with the thread's items staged in registers ------------------------------------------------------
+// The stage sweep of kc_ksf_resolve1_kernel (profiles/r01h_variant_sweep2.json) showed its time going with 1 / (CTAs per SM):
+// 0.235 ms at 5 CTAs (2 stages), 0.270 at 4 (3 stages), 0.324 at 3 (4 stages) — the kernel is bound by the latency of one
+// leaf's dependent chain (LDS key -> hash -> STS/LDS table -> compare, item after item), not by DRAM.  Here a thread loads
+// ALL its keys first, hashes them together, then issues the table accesses together, so the chain is paid once per phase
+// instead of once per item; key and hash stay in registers between the phases.  THREADS = 512 halves the items per thread.
+// BAL (measured next, ncu r01h: 30 % of the samples wait at the barrier, 6 % on the load of the next leaf's size): with 16-byte
+// copy units a leaf of ~763 u64 keys gives threads 0..125 four items and the others two, so half the warps idle at the barrier;
+// 8-byte units (cp.async.ca) give every thread three.  The size of leaf n + 2 is loaded one iteration before it is needed.
+KC_D void kc_cp_async8(void *smem_dst, const void *gmem_src) {
+    const u32 d = (u32) __cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+template <int L, int THREADS, bool BAL = false>
+__global__ void __launch_bounds__(THREADS) kc_ksf_resolve2_kernel(const KWord<L> *__restrict__ keys, const u32 *__restrict__ pos, const u32 *__restrict__ cnt,
+                                                                  u32 n_leaf, u32 *flags, kc_ull *n_unique, u32 *status) {
+    constexpr u32 CAP = KSF_LEAF_CAP;
+    constexpr u32 T1N = 2 * CAP, T2N = CAP;
+    constexpr int KPC = (BAL && L == 1) ? 1 : (16 / (int) sizeof(KWord<L>) > 0 ? 16 / (int) sizeof(KWord<L>) : 1);
+    constexpr int CPK = (int) sizeof(KWord<L>) / 16 > 0 ? (int) sizeof(KWord<L>) / 16 : 1;
+    constexpr int UNITS = (int) CAP / KPC / THREADS;  // copy units (and hash rounds) per thread
+    constexpr int NI = UNITS * KPC;                   // items per thread
+    static_assert(UNITS >= 1 && UNITS * KPC * THREADS == (int) CAP, "CAP must be a whole number of units per thread");
+    extern __shared__ __align__(16) unsigned char kc_smem_raw[];
+    KWord<L> *sk0 = reinterpret_cast<KWord<L> *>(kc_smem_raw);
+    u32 *sp0 = reinterpret_cast<u32 *>(sk0 + 2 * CAP);
+    u32 *T2a = sp0 + 2 * CAP;                                  // [2][T2N]
+    u16 *T1a = reinterpret_cast<u16 *>(T2a + 2 * T2N);         // [2][T1N]
+    const u64 stride = gridDim.x;
+    u64 c = blockIdx.x;
+    if (c >= n_leaf) return;
+    auto leaf_size = [&](u64 leaf) -> u32 {
+        if (leaf >= n_leaf) return 0u;
+        u32 sz = cnt[leaf];
+        if (sz > CAP) {
+            sz = CAP;
+            if (threadIdx.x == 0) status[0] = 1;
+        }
+        return sz;
+    };
+    auto fetch = [&](u64 bucket, u32 size, int buf) {
+        if (bucket < n_leaf) {
+            const char *gk = reinterpret_cast<const char *>(keys + bucket * CAP);
+            const char *gp = reinterpret_cast<const char *>(pos + bucket * CAP);
+            char *dk = reinterpret_cast<char *>(sk0 + (u32) buf * CAP);
+            char *dp = reinterpret_cast<char *>(sp0 + (u32) buf * CAP);
+            const u32 n_units = (size + KPC - 1) / KPC, pchunks = (size * 4 + 15) / 16;
+#pragma unroll
+            for (int m = 0; m < UNITS; ++m) {  // unit u holds items u * KPC .. u * KPC + KPC - 1: the ones this thread hashes
+                const u32 u = threadIdx.x + (u32) m * THREADS;
+                if (u < n_units) {
+                    if constexpr (BAL && L == 1) {
+                        kc_cp_async8(dk + 8 * u, gk + 8 * u);
+                    } else {
+#pragma unroll
+                        for (int cc = 0; cc < CPK; ++cc) kc_cp_async16(dk + 16 * (u * CPK + cc), gk + 16 * (u * CPK + cc));
+                    }
+                }
+            }
+            for (u32 q = threadIdx.x; q < pchunks; q += THREADS) kc_cp_async16(dp + 16 * q, gp + 16 * q);
+        }
+        kc_cp_async_commit();
+    };
+    u32 size = leaf_size(c);
+    u32 size_n = leaf_size(c + stride);
+    fetch(c, size, 0);
+    int buf = 0;
+    u32 kept = 0;
+    while (true) {
+        const u64 cn = c + stride;
+        u32 raw_nn = 0;  // size of leaf c + 2 * stride: loaded here, first used at the bottom of the loop
+        if (BAL) {
+            if (cn + stride < n_leaf) raw_nn = cnt[cn + stride];
+        }
+        KWord<L> *sk = sk0 + (u32) buf * CAP;
+        u32 *sp = sp0 + (u32) buf * CAP;
+        u32 *T2 = T2a + (u32) buf * T2N;
+        u16 *T1 = T1a + (u32) buf * T1N;
+        kc_cp_async_wait_group<0>();  // the thread's own key units of leaf c have landed
+        if (threadIdx.x < 256) reinterpret_cast<uint4 *>(T2)[threadIdx.x] = make_uint4(KC_NONE, KC_NONE, KC_NONE, KC_NONE);  // T2N = 256 x 4 slots
+        // A: all keys, then all hashes, then all table stores
+        KWord<L> key[NI];
+        u32 h1[NI], h2[NI];
+#pragma unroll
+        for (int m = 0; m < NI; ++m) {
+            const u32 i = (threadIdx.x + (u32) (m / KPC) * THREADS) * KPC + (u32) (m % KPC);
+            if (i < size) key[m] = sk[i];
+        }
+#pragma unroll
+        for (int m = 0; m < NI; ++m) {
+            u64 h = 0;
+#pragma unroll
+            for (int w = 0; w < L; ++w) h = (h ^ key[m].w[w]) * 0xD6E8FEB86659FD93ULL;
+            h1[m] = (u32) (h >> 53);
+            h2[m] = (u32) (h >> 43) & (T2N - 1);
+        }
+#pragma unroll
+        for (int m = 0; m < NI; ++m) {
+            const u32 i = (threadIdx.x + (u32) (m / KPC) * THREADS) * KPC + (u32) (m % KPC);
+            if (i < size) T1[h1[m]] = (u16) i;
+        }
+        __syncthreads();
+        fetch(cn, size_n, buf ^ 1);  // every thread is past phase B of the leaf that used that buffer
+        // B: all table reads first; winners are done, the others compare against their slot's winner
+        u32 o[NI];
+#pragma unroll
+        for (int m = 0; m < NI; ++m) {
+            const u32 i = (threadIdx.x + (u32) (m / KPC) * THREADS) * KPC + (u32) (m % KPC);
+            o[m] = i < size ? (u32) T1[h1[m]] : i;
+        }
+#pragma unroll
+        for (int m = 0; m < NI; ++m) {
+            const u32 i = (threadIdx.x + (u32) (m / KPC) * THREADS) * KPC + (u32) (m % KPC);
+            if (i >= size) continue;
+            if (o[m] == i) {
+                ++kept;
+            } else if (sk[o[m]] == key[m]) {
+                const u32 mine = sp[i];
+                const u32 was = atomicMin(&sp[o[m]], mine);
+                kc_flag_clear(flags, was > mine ? was : mine);
+            } else {
+                u32 s = h2[m];
+                while (true) {
+                    const u32 old = atomicCAS(&T2[s], KC_NONE, i);
+                    if (old == KC_NONE) {
+                        ++kept;
+                        break;
+                    }
+                    if (sk[old] == key[m]) {
+                        const u32 mine = sp[i];
+                        const u32 was = atomicMin(&sp[old], mine);
+                        kc_flag_clear(flags, was > mine ? was : mine);
+                        break;
+                    }
+                    s = (s + 1) & (T2N - 1);
+                }
+            }
+        }
         if (cn >= n_leaf) break;
         c = cn;
         size = size_n;
+        if (BAL) {
+            if (raw_nn > CAP) {
+                raw_nn = CAP;
+                if (threadIdx.x == 0) status[0] = 1;
+            }
+            size_n = raw_nn;
+        } else {
+            size_n = leaf_size(c + stride);
+        }
         buf ^= 1;
     }
+    kc_cp_async_wait_group<0>();
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) kept += __shfl_down_sync(0xFFFFFFFFu, kept, o);
+    for (int o2 = 16; o2 > 0; o2 >>= 1) kept += __shfl_down_sync(0xFFFFFFFFu, kept, o2);
     if ((threadIdx.x & 31) == 0 && kept) atomicAdd(n_unique, (kc_ull) kept);
 }
 
@@ -684,11 +869,11 @@ __global__ void __launch_bounds__(256) kc_ksf_resolve1_kernel(const KWord<L> *__
 // tile after the current one streams into a shared-memory input buffer with cp.async while the current tile is ranked,
 // staged and written out: a thread takes its items out of the input buffer into registers, and the barrier that ends the
 // ranking phase frees the buffer for the next copy.  Tiles are contiguous in their parent slot, slots are 128-byte aligned.
-template <int L, int TILE, int MINB>
-__global__ void __launch_bounds__(256, MINB) kc_ksf_scatter_pf_kernel(const KWord<L> *__restrict__ ksrc, const u32 *__restrict__ psrc, KWord<L> *__restrict__ kdst,
+template <int L, int TILE, int MINB, int THREADS = 256>
+__global__ void __launch_bounds__(THREADS, MINB) kc_ksf_scatter_pf_kernel(const KWord<L> *__restrict__ ksrc, const u32 *__restrict__ psrc, KWord<L> *__restrict__ kdst,
                                                                 u32 *__restrict__ pdst, const u32 *__restrict__ P_size, const u32 *__restrict__ tile_prefix,
                                                                 u32 nP, u64 capP, u32 tiles_per_cta, int shift, int bits, u32 *C_cnt, u32 capC, u32 *status) {
-    constexpr int ITEMS = TILE / 256;
+    constexpr int ITEMS = TILE / THREADS;
     extern __shared__ __align__(16) unsigned char kc_smem_raw[];
     KWord<L> *in_k = reinterpret_cast<KWord<L> *>(kc_smem_raw);
     KWord<L> *stage_k = in_k + TILE;
@@ -698,13 +883,13 @@ __global__ void __launch_bounds__(256, MINB) kc_ksf_scatter_pf_kernel(const KWor
     __shared__ u32 cnt[256];
     __shared__ u32 loff[256];
     __shared__ u32 gbase[256];
-    __shared__ u32 sw[8];
+    __shared__ u32 sw[THREADS / 32];
     const u32 n_tiles = tile_prefix[nP];
     const u32 t0 = blockIdx.x * tiles_per_cta;
     const u32 t1 = min(n_tiles, t0 + tiles_per_cta);
     if (t0 >= t1) return;
     u32 b = kc_upper_bound_u32(tile_prefix, nP + 1, t0) - 1;
-    cnt[threadIdx.x] = 0;
+    if (threadIdx.x < 256) cnt[threadIdx.x] = 0;
     bool over = false;
     // tile t of the CTA -> (parent bucket, first item inside the source arrays, items)
     auto describe = [&](u32 t, u32 &bb, u64 &first, u32 &n_here) {
@@ -717,8 +902,8 @@ __global__ void __launch_bounds__(256, MINB) kc_ksf_scatter_pf_kernel(const KWor
         const char *gk = reinterpret_cast<const char *>(ksrc + first);
         const char *gp = reinterpret_cast<const char *>(psrc + first);
         const u32 kch = (n_here * (u32) sizeof(KWord<L>) + 15) / 16, pch = (n_here * 4 + 15) / 16;
-        for (u32 q = threadIdx.x; q < kch; q += 256) kc_cp_async16(reinterpret_cast<char *>(in_k) + 16 * q, gk + 16 * q);
-        for (u32 q = threadIdx.x; q < pch; q += 256) kc_cp_async16(reinterpret_cast<char *>(in_p) + 16 * q, gp + 16 * q);
+        for (u32 q = threadIdx.x; q < kch; q += THREADS) kc_cp_async16(reinterpret_cast<char *>(in_k) + 16 * q, gk + 16 * q);
+        for (u32 q = threadIdx.x; q < pch; q += THREADS) kc_cp_async16(reinterpret_cast<char *>(in_p) + 16 * q, gp + 16 * q);
         kc_cp_async_commit();
     };
     u64 first;
@@ -732,7 +917,7 @@ __global__ void __launch_bounds__(256, MINB) kc_ksf_scatter_pf_kernel(const KWor
         u32 pay[ITEMS];
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
-            const u32 i = threadIdx.x + j * 256;
+            const u32 i = threadIdx.x + j * THREADS;
             if (i < n_here) {
                 item[j] = in_k[i];
                 pay[j] = in_p[i];
@@ -740,7 +925,7 @@ __global__ void __launch_bounds__(256, MINB) kc_ksf_scatter_pf_kernel(const KWor
         }
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
-            const u32 i = threadIdx.x + j * 256;
+            const u32 i = threadIdx.x + j * THREADS;
             if (i < n_here) rk[i] = (u16) atomicAdd(&cnt[item[j].digit(shift, bits)], 1u);
         }
         __syncthreads();  // counts complete, input buffer free
@@ -750,16 +935,18 @@ __global__ void __launch_bounds__(256, MINB) kc_ksf_scatter_pf_kernel(const KWor
             describe(t + 1, b_next, first_next, n_next);
             prefetch(first_next, n_next);
         }
-        const u32 c = cnt[threadIdx.x];
+        const u32 c = threadIdx.x < 256 ? cnt[threadIdx.x] : 0u;
         u32 total;
-        const u32 p = kc_block_exclusive_scan<256>(c, &total, sw);
-        loff[threadIdx.x] = p;
-        if (c) gbase[threadIdx.x] = atomicAdd(&C_cnt[((u64) b << bits) + threadIdx.x], c);
-        cnt[threadIdx.x] = 0;
+        const u32 p = kc_block_exclusive_scan<THREADS>(c, &total, sw);
+        if (threadIdx.x < 256) {
+            loff[threadIdx.x] = p;
+            if (c) gbase[threadIdx.x] = atomicAdd(&C_cnt[((u64) b << bits) + threadIdx.x], c);
+            cnt[threadIdx.x] = 0;
+        }
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
-            const u32 i = threadIdx.x + j * 256;
+            const u32 i = threadIdx.x + j * THREADS;
             if (i < n_here) {
                 const u32 q = loff[item[j].digit(shift, bits)] + rk[i];
                 stage_k[q] = item[j];
@@ -767,7 +954,7 @@ __global__ void __launch_bounds__(256, MINB) kc_ksf_scatter_pf_kernel(const KWor
             }
         }
         __syncthreads();
-        for (u32 q = threadIdx.x; q < n_here; q += 256) {
+        for (u32 q = threadIdx.x; q < n_here; q += THREADS) {
             const KWord<L> v = stage_k[q];
             const u32 dg = v.digit(shift, bits);
             const u32 idx = gbase[dg] + (q - loff[dg]);
@@ -815,7 +1002,7 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
     const int smem0 = Cfg::EX_TILE * ((int) sizeof(KWord<L>) + 4);
     const int tv = tune.tile_variant;
     const int tile1 = (tv == 1 || tv == 4) ? Cfg::TILE / 2 : (tv == 2 ? Cfg::TILE * 3 / 4 : Cfg::TILE);
-    const bool pf = tv == 3 || tv == 4;  // input tile double-buffered in shared memory
+    const bool pf = tv >= 3;  // input tile double-buffered in shared memory
     const int smem1 = tile1 * ((pf ? 2 : 1) * ((int) sizeof(KWord<L>) + 4) + 2);
     const bool clear_flags = tune.resolve >= 2;  // level 0 writes the valid-window bits, the resolve clears the losers
     const bool counted = min_freq > 1;
@@ -834,6 +1021,8 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
                                      Cfg::TILE * 3 / 4 * ((int) sizeof(KWord<L>) + 4 + 2)));
         KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter0_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KsCfg<1>::EX_TILE * 12));
         KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_pf_kernel<L, Cfg::TILE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::TILE * (2 * ((int) sizeof(KWord<L>) + 4) + 2)));
+        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_pf_kernel<L, Cfg::TILE, 2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::TILE * (2 * ((int) sizeof(KWord<L>) + 4) + 2)));
         KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_pf_kernel<L, Cfg::TILE / 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg::TILE / 2 * (2 * ((int) sizeof(KWord<L>) + 4) + 2)));
@@ -882,7 +1071,7 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
         if (chunks) chunks->waited = true;
     }
     // ---- levels >= 1 ----
-    const u32 max_ctas = 148 * 8;
+    const u32 max_ctas = tune.max_ctas > 0 ? (u32) tune.max_ctas : 148 * 8;
     for (int lv = 1; lv < pl.n_levels; ++lv) {
         const u32 nP = (u32) (1ULL << pl.cum[lv - 1]);
         const size_t mark = ex.arena->mark();
@@ -899,6 +1088,9 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
         {
             CudaExec::Scope sc(ex, KP_SORT_SCATTER, 2 * n_bytes * item_bytes);
             if (tv == 3) kc_ksf_scatter_pf_kernel<L, Cfg::TILE, 2><<<ctas, 256, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
+                                                               pl.cap[lv - 1], tiles_per_cta, 64 * L - pl.cum[lv], pl.bits[lv], cnt_next, (u32) pl.cap[lv],
+                                                               status);
+            else if (tv == 5) kc_ksf_scatter_pf_kernel<L, Cfg::TILE, 2, 512><<<ctas, 512, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
                                                                pl.cap[lv - 1], tiles_per_cta, 64 * L - pl.cum[lv], pl.bits[lv], cnt_next, (u32) pl.cap[lv],
                                                                status);
             else if (tv == 4) kc_ksf_scatter_pf_kernel<L, Cfg::TILE / 2, 4><<<ctas, 256, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
@@ -932,19 +1124,50 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
             if (c) atomicAdd(m_cell, (kc_ull) c);
         });
     }
-    if (tune.resolve == 3 && !counted) {
-        const int smem3 = (int) KSF_LEAF_CAP * (16 * L + 8 + 8 + 8);  // per leaf item: keys x2, positions x2, T2 x2 (u32), T1 x2 (two u16 slots per item)
-        static bool attr3_done = false;
-        static int occ3 = 0;
-        if (!attr3_done) {
-            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve1_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, kc_ksf_resolve1_kernel<L>, 256, smem3));
-            attr3_done = true;
+    if (tune.resolve >= 6 && !counted) {
+        const int smem4 = (int) KSF_LEAF_CAP * (2 * (8 * L + 4) + 16);
+        static bool attr4_done = false;
+        static int occ4[2] = {0, 0};
+        if (!attr4_done) {
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve2_kernel<L, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve2_kernel<L, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve2_kernel<L, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4[0], kc_ksf_resolve2_kernel<L, 256>, 256, smem4));
+            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4[1], kc_ksf_resolve2_kernel<L, 512>, 512, smem4));
+            attr4_done = true;
         }
-        const u32 fit = (u32) (n_sm * (occ3 > 0 ? occ3 : 1));
+        const int wide = tune.resolve == 7 ? 1 : 0;
+        const u32 fit = (u32) (n_sm * (occ4[wide] > 0 ? occ4[wide] : 1));
         const u32 grid = n_small < fit ? n_small : fit;
         CudaExec::Scope sc(ex, KP_KS_RESOLVE, n_bytes * item_bytes);
-        kc_ksf_resolve1_kernel<L><<<grid, 256, smem3, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, n_unique, status);
+        if (tune.resolve == 8) kc_ksf_resolve2_kernel<L, 256, true><<<grid, 256, smem4, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, n_unique, status);
+        else if (wide) kc_ksf_resolve2_kernel<L, 512><<<grid, 512, smem4, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, n_unique, status);
+        else kc_ksf_resolve2_kernel<L, 256><<<grid, 256, smem4, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, n_unique, status);
+        ++ex.launches;
+        KC_CUDA(cudaGetLastError());
+    } else if (tune.resolve >= 3 && !counted) {
+        const int stages = tune.resolve == 3 ? 2 : (tune.resolve == 4 ? 3 : 4);
+        // per ring stage: keys + positions of one leaf; tables: T2 x2 (u32), T1 x2 (two u16 slots per item)
+        const int smem3 = (int) KSF_LEAF_CAP * (stages * (8 * L + 4) + 8 + 8);
+        static bool attr3_done = false;
+        static int occ3[3] = {0, 0, 0};
+        if (!attr3_done) {
+            const int per = 8 * L + 4;
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve1_kernel<L, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (2 * per + 16)));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve1_kernel<L, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (3 * per + 16)));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve1_kernel<L, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (4 * per + 16)));
+            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3[0], kc_ksf_resolve1_kernel<L, 2>, 256, (int) KSF_LEAF_CAP * (2 * per + 16)));
+            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3[1], kc_ksf_resolve1_kernel<L, 3>, 256, (int) KSF_LEAF_CAP * (3 * per + 16)));
+            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3[2], kc_ksf_resolve1_kernel<L, 4>, 256, (int) KSF_LEAF_CAP * (4 * per + 16)));
+            attr3_done = true;
+        }
+        const int occ = occ3[stages - 2];
+        const u32 fit = (u32) (n_sm * (occ > 0 ? occ : 1));
+        const u32 grid = n_small < fit ? n_small : fit;
+        CudaExec::Scope sc(ex, KP_KS_RESOLVE, n_bytes * item_bytes);
+        if (stages == 2) kc_ksf_resolve1_kernel<L, 2><<<grid, 256, smem3, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, n_unique, status);
+        else if (stages == 3) kc_ksf_resolve1_kernel<L, 3><<<grid, 256, smem3, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, n_unique, status);
+        else kc_ksf_resolve1_kernel<L, 4><<<grid, 256, smem3, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, n_unique, status);
         ++ex.launches;
         KC_CUDA(cudaGetLastError());
     } else if (tune.resolve >= 1) {

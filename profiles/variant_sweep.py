@@ -47,7 +47,7 @@ def battery():
     return out
 
 
-def run_variant(r, t, steps, ref):
+def run_variant(r, t, steps, ref, w=0):  # w = fast_max_ctas
     """One (fast_resolve, fast_tile_variant) pair in THIS process -> result row (ref: signatures of the baseline or {})."""
     import torch
     import kmercamel_b200 as kb
@@ -57,9 +57,10 @@ def run_variant(r, t, steps, ref):
     stream = torch.cuda.current_stream()
     ctx = kb.Context(0, stream.cuda_stream)
     d_seq = torch.from_numpy(seq).cuda()
-    row = {"fast_resolve": r, "fast_tile_variant": t, "ok": True, "cases": {}}
+    row = {"fast_resolve": r, "fast_tile_variant": t, "fast_max_ctas": w, "ok": True, "cases": {}}
     ctx.set_option("fast_resolve", r)
     ctx.set_option("fast_tile_variant", t)
+    ctx.set_option("fast_max_ctas", w)
     cases = [("configs1", seq, dict(k=bench.K), {})] + battery()
     for name, s, kw, opts in cases:
         for o, v in opts.items():
@@ -98,9 +99,9 @@ def main():
     ap.add_argument("--ref", default=None)
     args = ap.parse_args()
     if args.variant:
-        r, t = (int(x) for x in args.variant.split(","))
+        r, t, w = (int(x) for x in args.variant.split(","))
         ref = json.load(open(args.ref)) if args.ref and os.path.exists(args.ref) else {}
-        print("ROW " + json.dumps(run_variant(r, t, args.steps, ref)), flush=True)
+        print("ROW " + json.dumps(run_variant(r, t, args.steps, ref, w)), flush=True)
         return
     # parent: one process per variant (a faulting kernel poisons its CUDA context), each under a timeout
     import subprocess
@@ -108,12 +109,13 @@ def main():
     ref_path = args.out + ".ref"
     if os.path.exists(ref_path):
         os.remove(ref_path)
-    variants = [(1, 0), (2, 0), (3, 0), (1, 3), (1, 4), (3, 3), (3, 4)]
+    # (fast_resolve, fast_tile_variant, fast_max_ctas); (1, 0, 0) first: it supplies the reference signatures
+    variants = [(1, 0, 0), (6, 5, 2368), (8, 5, 2368)]
     rows = []
-    for (r, t) in variants:
-        row = {"fast_resolve": r, "fast_tile_variant": t, "ok": False}
+    for (r, t, w) in variants:
+        row = {"fast_resolve": r, "fast_tile_variant": t, "fast_max_ctas": w, "ok": False}
         try:
-            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--variant", f"{r},{t}", "--steps", str(args.steps), "--ref", ref_path],
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--variant", f"{r},{t},{w}", "--steps", str(args.steps), "--ref", ref_path],
                                capture_output=True, text=True, timeout=150)
             got = [ln for ln in p.stdout.splitlines() if ln.startswith("ROW ")]
             if got:
@@ -122,7 +124,7 @@ def main():
                 row["error"] = (p.stderr or "")[-600:]
         except subprocess.TimeoutExpired:
             row["error"] = "timeout"
-        if (r, t) == (1, 0):
+        if (r, t, w) == (1, 0, 0):
             if not row.get("ok"):
                 print("baseline variant failed: " + str(row.get("error")), file=sys.stderr)
             else:
@@ -134,11 +136,11 @@ def main():
     good = [x for x in rows if x.get("ok") and "ms_per_step" in x]
     best = min(good, key=lambda x: x["ms_per_step"]) if good else None
     with open(args.out, "w") as f:
-        json.dump({"rows": rows, "best": best and [best["fast_resolve"], best["fast_tile_variant"]]}, f, indent=1)
+        json.dump({"rows": rows, "best": best and [best["fast_resolve"], best["fast_tile_variant"], best["fast_max_ctas"]]}, f, indent=1)
     if best:
-        print(f"KC_FAST_RESOLVE={best['fast_resolve']} KC_FAST_TILE={best['fast_tile_variant']}")
+        print(f"KC_FAST_RESOLVE={best['fast_resolve']} KC_FAST_TILE={best['fast_tile_variant']} KC_FAST_MAX_CTAS={best['fast_max_ctas']}")
     else:
-        print("KC_FAST_RESOLVE=1 KC_FAST_TILE=0")
+        print("KC_FAST_RESOLVE=1 KC_FAST_TILE=0 KC_FAST_MAX_CTAS=0")
 
 
 if __name__ == "__main__":
