@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(c
     __shared__ u32 vm[KC_EX_HALO + T];
     __shared__ u32 cnt[256];
     __shared__ u32 loff[256];
-    __shared__ u32 gbase[256];
+    __shared__ u64 dbase[256];  // slot index of the digit's first item of this tile, minus its staged position: at = dbase + q
+    __shared__ u32 qlim[256];   // staged positions below this still fit into the digit's slot
     __shared__ u32 sw[T / 32];
     const i64 block_pos0 = (i64) (tile0 + blockIdx.x) * TILE;
     kc_tile_load<T>(seq, n_bytes, block_pos0, pk, vm);
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(c
         const KWord<L> c = kmer_scramble(c0);
         const u32 slot = (u32) j * T + threadIdx.x;
         stash[slot] = c;
-        rk[slot] = (u16) atomicAdd(&cnt[c.digit(shift, bits)], 1u);
+        rk[slot] = (u16) atomicAdd(&cnt[c.digit_top(shift, bits)], 1u);
     });
     __syncthreads();
     u32 total;
@@ -148,7 +149,11 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(c
         for (int r = 0; r < R; ++r) {
             const int i = threadIdx.x * R + r;
             loff[i] = p;
-            if (v[r]) gbase[i] = atomicAdd(&bucket_cnt[i], v[r]);  // reserve the tile's place inside the slot of bucket i
+            u32 gb = 0;
+            if (v[r]) gb = atomicAdd(&bucket_cnt[i], v[r]);  // reserve the tile's place inside the slot of bucket i
+            const u32 room = gb < cap0 ? cap0 - gb : 0u;
+            dbase[i] = (u64) i * cap0 + gb - p;
+            qlim[i] = p + (v[r] < room ? v[r] : room);
             p += v[r];
         }
     }
@@ -156,19 +161,18 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(c
     if (total == 0) return;
     for (u32 slot = threadIdx.x; slot < (u32) TILE; slot += T) {
         const u32 r = rk[slot];
-        if (r != 0xFFFFu) perm[loff[stash[slot].digit(shift, bits)] + r] = (u16) slot;
+        if (r != 0xFFFFu) perm[loff[stash[slot].digit_top(shift, bits)] + r] = (u16) slot;
     }
     __syncthreads();
     bool over = false;
     for (u32 q = threadIdx.x; q < total; q += T) {
         const u32 slot = perm[q];
         const KWord<L> v = stash[slot];
-        const u32 dg = v.digit(shift, bits);
-        const u32 idx = gbase[dg] + (q - loff[dg]);
-        if (idx < cap0) {
-            const u64 at = (u64) dg * cap0 + idx;
+        const u32 dg = v.digit_top(shift, bits);
+        if (q < qlim[dg]) {
+            const u64 at = dbase[dg] + q;
             keys[at] = v;
-            pos[at] = (u32) ((u64) block_pos0 + (slot & (T - 1)) * KC_EX_STRIP + (slot >> LOG_T));
+            pos[at] = (u32) block_pos0 + (slot & (T - 1)) * KC_EX_STRIP + (slot >> LOG_T);
         } else {
             over = true;
         }
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(512) kc_ksf_scatter0_split_kernel(const u8 *__
                 const KWord<1> cs = kmer_scramble(canon);
                 const u32 slot = (u32) j * S + strip;
                 stash[slot] = cs.w[0];
-                rk[slot] = (u16) atomicAdd(&cnt[cs.digit(shift, bits)], 1u);
+                rk[slot] = (u16) atomicAdd(&cnt[cs.digit_top(shift, bits)], 1u);
             }
         }
     }
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(512) kc_ksf_scatter0_split_kernel(const u8 *__
         if (r != 0xFFFFu) {
             KWord<1> v;
             v.w[0] = stash[slot];
-            perm[loff[v.digit(shift, bits)] + r] = (u16) slot;
+            perm[loff[v.digit_top(shift, bits)] + r] = (u16) slot;
         }
     }
     __syncthreads();
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(512) kc_ksf_scatter0_split_kernel(const u8 *__
         const u32 slot = perm[q];
         KWord<1> v;
         v.w[0] = stash[slot];
-        const u32 dg = v.digit(shift, bits);
+        const u32 dg = v.digit_top(shift, bits);
         const u32 idx = gbase[dg] + (q - loff[dg]);
         if (idx < cap0) {
             const u64 at = (u64) dg * cap0 + idx;
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(256, MINB) kc_ksf_scatter_kernel(const KWord<L
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
             const u32 i = threadIdx.x + j * 256;
-            if (i < n_here) rk[i] = (u16) atomicAdd(&cnt[item[j].digit(shift, bits)], 1u);
+            if (i < n_here) rk[i] = (u16) atomicAdd(&cnt[item[j].digit_top(shift, bits)], 1u);
         }
         __syncthreads();
         const u32 c = cnt[threadIdx.x];
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(256, MINB) kc_ksf_scatter_kernel(const KWord<L
         for (int j = 0; j < ITEMS; ++j) {
             const u32 i = threadIdx.x + j * 256;
             if (i < n_here) {
-                const u32 q = loff[item[j].digit(shift, bits)] + rk[i];
+                const u32 q = loff[item[j].digit_top(shift, bits)] + rk[i];
                 stage_k[q] = item[j];
                 stage_p[q] = pay[j];
             }
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(256, MINB) kc_ksf_scatter_kernel(const KWord<L
         __syncthreads();
         for (u32 q = threadIdx.x; q < n_here; q += 256) {
             const KWord<L> v = stage_k[q];
-            const u32 dg = v.digit(shift, bits);
+            const u32 dg = v.digit_top(shift, bits);
             const u32 idx = gbase[dg] + (q - loff[dg]);
             if (idx < capC) {
                 const u64 at = (((u64) b << bits) + dg) * capC + idx;
@@ -882,7 +886,8 @@ __global__ void __launch_bounds__(THREADS, MINB) kc_ksf_scatter_pf_kernel(const 
     u16 *rk = reinterpret_cast<u16 *>(stage_p + TILE);
     __shared__ u32 cnt[256];
     __shared__ u32 loff[256];
-    __shared__ u32 gbase[256];
+    __shared__ u64 dbase[256];  // slot index of the digit's first item of this tile, minus its staged position: at = dbase + q
+    __shared__ u32 qlim[256];   // staged positions below this still fit into the child's slot
     __shared__ u32 sw[THREADS / 32];
     const u32 n_tiles = tile_prefix[nP];
     const u32 t0 = blockIdx.x * tiles_per_cta;
@@ -926,7 +931,7 @@ __global__ void __launch_bounds__(THREADS, MINB) kc_ksf_scatter_pf_kernel(const 
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
             const u32 i = threadIdx.x + j * THREADS;
-            if (i < n_here) rk[i] = (u16) atomicAdd(&cnt[item[j].digit(shift, bits)], 1u);
+            if (i < n_here) rk[i] = (u16) atomicAdd(&cnt[item[j].digit_top(shift, bits)], 1u);
         }
         __syncthreads();  // counts complete, input buffer free
         u32 b_next = b, n_next = 0;
@@ -940,7 +945,11 @@ __global__ void __launch_bounds__(THREADS, MINB) kc_ksf_scatter_pf_kernel(const 
         const u32 p = kc_block_exclusive_scan<THREADS>(c, &total, sw);
         if (threadIdx.x < 256) {
             loff[threadIdx.x] = p;
-            if (c) gbase[threadIdx.x] = atomicAdd(&C_cnt[((u64) b << bits) + threadIdx.x], c);
+            u32 gb = 0;
+            if (c) gb = atomicAdd(&C_cnt[((u64) b << bits) + threadIdx.x], c);
+            const u32 room = gb < capC ? capC - gb : 0u;
+            dbase[threadIdx.x] = (((u64) b << bits) + threadIdx.x) * capC + gb - p;
+            qlim[threadIdx.x] = p + (c < room ? c : room);
             cnt[threadIdx.x] = 0;
         }
         __syncthreads();
@@ -948,7 +957,7 @@ __global__ void __launch_bounds__(THREADS, MINB) kc_ksf_scatter_pf_kernel(const 
         for (int j = 0; j < ITEMS; ++j) {
             const u32 i = threadIdx.x + j * THREADS;
             if (i < n_here) {
-                const u32 q = loff[item[j].digit(shift, bits)] + rk[i];
+                const u32 q = loff[item[j].digit_top(shift, bits)] + rk[i];
                 stage_k[q] = item[j];
                 stage_p[q] = pay[j];
             }
@@ -956,10 +965,9 @@ __global__ void __launch_bounds__(THREADS, MINB) kc_ksf_scatter_pf_kernel(const 
         __syncthreads();
         for (u32 q = threadIdx.x; q < n_here; q += THREADS) {
             const KWord<L> v = stage_k[q];
-            const u32 dg = v.digit(shift, bits);
-            const u32 idx = gbase[dg] + (q - loff[dg]);
-            if (idx < capC) {
-                const u64 at = (((u64) b << bits) + dg) * capC + idx;
+            const u32 dg = v.digit_top(shift, bits);
+            if (q < qlim[dg]) {
+                const u64 at = dbase[dg] + q;
                 kdst[at] = v;
                 pdst[at] = stage_p[q];
             } else {
