@@ -159,12 +159,29 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(c
     }
     __syncthreads();
     if (total == 0) return;
-    for (u32 slot = threadIdx.x; slot < (u32) TILE; slot += T) {
-        const u32 r = rk[slot];
-        if (r != 0xFFFFu) perm[loff[stash[slot].digit_top(shift, bits)] + r] = (u16) slot;
+    // perm[] shares the dynamic array with rk[] / stash[], so the compiler must keep every store behind the loads of the same
+    // iteration and in front of the next one's (ncu r01h: 16 % of the kernel's samples on this one line).  Batches of 8 slots:
+    // all ranks, all top limbs, all offsets, then the stores — the shared-memory round trips overlap.
+#pragma unroll
+    for (int j0 = 0; j0 < KC_EX_STRIP; j0 += 8) {
+        u32 r[8], o[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) r[u] = rk[(u32) (j0 + u) * T + threadIdx.x];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            KWord<L> t = KWord<L>::zero();
+            t.w[L - 1] = stash[(u32) (j0 + u) * T + threadIdx.x].w[L - 1];  // the digit lives in the top limb
+            o[u] = t.digit_top(shift, bits);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = loff[o[u]];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (r[u] != 0xFFFFu) perm[o[u] + r[u]] = (u16) ((u32) (j0 + u) * T + threadIdx.x);
     }
     __syncthreads();
     bool over = false;
+#pragma unroll 4
     for (u32 q = threadIdx.x; q < total; q += T) {
         const u32 slot = perm[q];
         const KWord<L> v = stash[slot];
@@ -928,10 +945,20 @@ __global__ void __launch_bounds__(THREADS, MINB) kc_ksf_scatter_pf_kernel(const 
                 pay[j] = in_p[i];
             }
         }
+        // all atomics first, then the rank stores (a store behind every atomic would wait for its result before the next
+        // atomic is issued: one shared-memory round trip per item instead of one per tile)
+        {
+            u32 rr[ITEMS];
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const u32 i = threadIdx.x + j * THREADS;
-            if (i < n_here) rk[i] = (u16) atomicAdd(&cnt[item[j].digit_top(shift, bits)], 1u);
+            for (int j = 0; j < ITEMS; ++j) {
+                const u32 i = threadIdx.x + j * THREADS;
+                rr[j] = i < n_here ? atomicAdd(&cnt[item[j].digit_top(shift, bits)], 1u) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) {
+                const u32 i = threadIdx.x + j * THREADS;
+                if (i < n_here) rk[i] = (u16) rr[j];
+            }
         }
         __syncthreads();  // counts complete, input buffer free
         u32 b_next = b, n_next = 0;
@@ -953,16 +980,26 @@ __global__ void __launch_bounds__(THREADS, MINB) kc_ksf_scatter_pf_kernel(const 
             cnt[threadIdx.x] = 0;
         }
         __syncthreads();
+        {   // staged positions of all items first (rk[] shares the dynamic array with the staging buffers: no load may pass a store)
+            u32 qq[ITEMS];
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const u32 i = threadIdx.x + j * THREADS;
-            if (i < n_here) {
-                const u32 q = loff[item[j].digit_top(shift, bits)] + rk[i];
-                stage_k[q] = item[j];
-                stage_p[q] = pay[j];
+            for (int j = 0; j < ITEMS; ++j) {
+                const u32 i = threadIdx.x + j * THREADS;
+                qq[j] = i < n_here ? (u32) rk[i] : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) qq[j] += loff[item[j].digit_top(shift, bits)];
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) {
+                const u32 i = threadIdx.x + j * THREADS;
+                if (i < n_here) {
+                    stage_k[qq[j]] = item[j];
+                    stage_p[qq[j]] = pay[j];
+                }
             }
         }
         __syncthreads();
+#pragma unroll 4
         for (u32 q = threadIdx.x; q < n_here; q += THREADS) {
             const KWord<L> v = stage_k[q];
             const u32 dg = v.digit_top(shift, bits);
