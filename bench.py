@@ -12,9 +12,10 @@ Workload = BASELINE.json configs[1]: 50 x 1,000,000 bp uniform random multi-FAST
 N > 1 (torchrun): ONE job over a genome of N x 50 Mbp (rank r contributes the 50 records of seed 12345 + r), hash-range
 sharded as the north star asks: every rank extracts the k-mers of its slice, the (k-mer, position) items go to their
 owner rank over NVLink (the level-0 scatter kernel stores straight into the owner's buffer through peer pointers, so the
-partition pass is the all-to-all; only 256 counts per rank go through NCCL), every rank resolves its hash range, the first-occurrence flags are
-reduced onto rank 0, which runs the (sequential) greedy merge and emits the whole superstring.  Per-GPU counting work is
-fixed as N grows (weak scaling); value = distinct k-mers of the whole job / max-over-ranks time.
+partition pass is the all-to-all; only 256 counts per rank go through NCCL), every rank resolves its hash range, the first-occurrence
+flag bit arrays are all-reduced, every rank repeats the (sequential, deterministic, ~0.2-0.6 ms) greedy merge and emits — and in the
+end-to-end arm copies back — its own 16-byte-aligned slice of the superstring.  Per-GPU counting work is fixed as N grows (weak
+scaling); value = distinct k-mers of the whole job / max-over-ranks time.
 """
 import argparse
 import json
@@ -170,10 +171,10 @@ def workload_config(world):
             "k": K, "bases_per_gpu": N_RECORDS * RECORD_LEN, "records_per_gpu": N_RECORDS,
             "sharding": ("k-mer set construction sharded by hash range: the level-0 scatter kernel stores (k-mer, position) items "
                          "straight into the owner GPU's buffer over NVLink (CUDA IPC peer pointers), NCCL only for the 256 "
-                         "digit counts, the barrier and the flag bit-array reduce onto rank 0; greedy merge + emission of "
-                         "the whole superstring on rank 0") if world > 1 else "single GPU",
-            "l2": "no explicit flush: each step streams ~10 GB of intermediates (>> 126 MB L2), so the 51 MB input and "
-                  "every kernel's operands are cold when read"}
+                         "digit counts, the barrier and the all-reduce of the flag bit arrays; every rank repeats the greedy "
+                         "merge and emits its own slice of the superstring") if world > 1 else "single GPU",
+            "l2": "no explicit flush: each step streams ~2.4 GB of intermediates (600 MB written by level 0, read and rewritten by "
+                  "level 1, read by the resolve: >> 126 MB L2), so the 50 MB input and every kernel's operands are cold when read"}
 
 
 def run_sharded_arm(args, rank, local_rank, world, ctx, part):
