@@ -1,3 +1,6 @@
+#!/usr/bin/env python3
+"""Instructions executed and stall samples per SOURCE line of one kernel in an .ncu-rep (needs -lineinfo and
+`ncu --import-source on`): ncu_lines.py rep kernel-regex [topN]"""
 import csv,subprocess,sys,io,collections
 rep,rx=sys.argv[1],sys.argv[2]
 raw=subprocess.run(["ncu","-i",rep,"--page","source","--csv","--kernel-name","regex:"+rx,"--launch-count","1","--print-source","cuda,sass"],capture_output=True,text=True).stdout
