@@ -19,28 +19,8 @@
 // exact histogram-based construction of kmerset.cuh.  Results never depend on which of the two ran.
 #pragma once
 #include "kmerset.cuh"
-#include <cmath>
 
-static const u32 KSF_LEAF_CAP = 1024;  // capacity of kc_ks_resolve_hash_kernel<L, 1024, *>
-static const int KSF_MAX_LEVELS = 4;
-
-struct KsfTuning {
-    bool enabled = true;
-    u32 leaf_target = 768;   // mean leaf size aimed at (the leaf slot holds KSF_LEAF_CAP)
-    double sigmas = 8.0;     // slot = mean + sigmas * sqrt(mean) (+ 2 %) items; 0 forces overflows (tests)
-    u64 min_items = 1u << 16;  // smaller inputs take the exact path (nothing to gain)
-    int resolve = 6;         // 1 = kc_ksf_resolve_kernel (cp.async, two barriers), 0 = kc_ks_resolve_hash_kernel over a bucket list,
-                             // 2 = as 1 with clear-the-losers flags (level 0 writes the valid-window bits, a duplicate clears one),
-                             // 3 = kc_ksf_resolve1_kernel: clear-the-losers + double-buffered tables, ONE barrier per leaf (-z 1 only),
-                             // 4 / 5 = the same with 3 / 4 staging buffers in the ring (two / three leaves in flight per CTA),
-                             // 6 / 7 = kc_ksf_resolve2_kernel: as 3 with a thread's items staged in registers, 256 / 512 threads,
-                             // 8 = as 6 with 8-byte copy units (every thread the same number of items) and the leaf size loaded a leaf ahead
-    int tile_variant = 5;    // level >= 1 scatter: 0 = KsCfg<L>::TILE items per tile, 3 CTAs/SM; 1 = half tiles, 5 CTAs/SM; 2 = 3/4 tiles, 4 CTAs/SM;
-                             // 3 / 4 = kc_ksf_scatter_pf_kernel (next tile streams in with cp.async) with full / half tiles,
-                             // 5 = full tiles and 512-thread CTAs (2 per SM: 32 instead of 16 warps)
-    int max_ctas = 148 * 16; // level >= 1 scatter grid: at most this many CTAs, each walking a run of consecutive tiles (0 = 148 * 8)
-    int split0 = 0;          // level 0 (L = 1): two threads per 32-base strip (512-thread CTAs); measured slower (0.327 vs 0.315 ms), kept as an option
-};
+#include "ksf_plan.h"  // KSF_LEAF_CAP, KsfTuning, KsfPlan, kc_ksf_plan
 
 // Host-to-device copy of the sequence in flight on another stream, cut into chunks of whole level-0 tiles: event c is recorded
 // once bytes [0, (c + 1) * chunk_bytes) have landed.  The level-0 scatter of the fixed-slot construction waits per chunk, so
@@ -55,43 +35,6 @@ struct InputChunks {
         waited = true;
     }
 };
-
-struct KsfPlan {
-    bool ok = false;
-    int n_levels = 0;
-    int bits[KSF_MAX_LEVELS];   // digit width of level i
-    int cum[KSF_MAX_LEVELS];    // key bits consumed after level i
-    u64 cap[KSF_MAX_LEVELS];    // slot size (items) of one bucket produced by level i
-    u64 slots[2] = {0, 0};      // items the ping (even levels) / pong (odd levels) buffers must hold
-    u64 n_leaf = 0;
-};
-
-inline KsfPlan kc_ksf_plan(u64 m_upper, const KsfTuning &t) {
-    KsfPlan p;
-    if (!t.enabled || m_upper < t.min_items) return p;
-    int total_bits = 1;
-    while (total_bits < 40 && (m_upper >> total_bits) > t.leaf_target) ++total_bits;
-    const int levels = (total_bits + 7) / 8;
-    if (levels > KSF_MAX_LEVELS) return p;
-    p.n_levels = levels;
-    int cum = 0;
-    for (int i = 0; i < levels; ++i) {
-        p.bits[i] = total_bits / levels + (i < total_bits % levels ? 1 : 0);
-        cum += p.bits[i];
-        p.cum[i] = cum;
-        const double mean = (double) m_upper / (double) (1ULL << cum);
-        u64 cap = (u64) std::ceil(mean + t.sigmas * std::sqrt(mean) + (t.sigmas > 0 ? 0.02 * mean + 64.0 : 0.0));
-        cap = (cap + 31) / 32 * 32;
-        if (i == levels - 1) cap = KSF_LEAF_CAP;
-        if (cap >= 0xFFFFFFFFULL) return p;
-        p.cap[i] = cap;
-        const u64 need = (1ULL << cum) * cap;
-        if (need > p.slots[i & 1]) p.slots[i & 1] = need;
-    }
-    p.n_leaf = 1ULL << cum;
-    p.ok = true;
-    return p;
-}
 
 #ifdef __CUDACC__
 

@@ -10,8 +10,11 @@
 //       -> superstring, then (maxone) the max-one string
 //   host_emul kmers <k> <complements> <strict> <maxone>       records on stdin; nodes = sorted distinct canonical
 //       k-mers of the records (the from-FASTA regime) -> superstring [, max-one]
+//   host_emul plan <m_upper> <leaf_target> <sigmas> 0         the fixed-slot plan of csrc/ksf_plan.h for an input of m_upper
+//       windows -> "ok levels n_leaf slots0 slots1", then "bits cum cap" per level
 #include "../kmercamel_b200/csrc/emit.cuh"
 #include "../kmercamel_b200/csrc/engine.cuh"
+#include "../kmercamel_b200/csrc/ksf_plan.h"
 
 #include <iostream>
 #include <string>
@@ -98,6 +101,15 @@ template <int L> int run(const std::string &mode, int k, bool complements, bool 
 int main(int argc, char **argv) {
     if (argc < 6) return 64;
     std::string mode = argv[1];
+    if (mode == "plan") {
+        KsfTuning t;
+        t.leaf_target = (uint32_t) std::atoi(argv[3]);
+        t.sigmas = std::atof(argv[4]);
+        const KsfPlan pl = kc_ksf_plan(std::strtoull(argv[2], nullptr, 10), t);
+        std::cout << (pl.ok ? 1 : 0) << " " << pl.n_levels << " " << pl.n_leaf << " " << pl.slots[0] << " " << pl.slots[1] << "\n";
+        for (int i = 0; pl.ok && i < pl.n_levels; ++i) std::cout << pl.bits[i] << " " << pl.cum[i] << " " << pl.cap[i] << "\n";
+        return 0;
+    }
     int k = std::atoi(argv[2]);
     bool complements = std::atoi(argv[3]) != 0, strict = std::atoi(argv[4]) != 0, flag = std::atoi(argv[5]) != 0;
     std::vector<std::string> recs;

@@ -135,3 +135,42 @@ def test_host_emul_from_kmers_valid(host_emul):
         exp, _ = orc.count_kmers(seq, off, ln, k, compl)
         assert orc.verify_ms(out[0], k, compl, exp) and orc.verify_ms(out[1], k, compl, exp)
         assert sum(1 for c in out[0] if c <= 90) == len(exp)  # min-one: every k-mer ON exactly once
+
+
+# ---- plan of the fixed-slot k-mer set construction (csrc/ksf_plan.h) -----------------------------------------------
+def _ksf_plan(m, leaf_target=768, sigmas=8):
+    exe = os.path.join(ROOT, "tests", "host_emul")
+    out = subprocess.run([exe, "plan", str(m), str(leaf_target), str(sigmas), "0"], capture_output=True, check=True).stdout.split(b"\n")
+    ok, levels, n_leaf, s0, s1 = map(int, out[0].split())
+    return ok, levels, n_leaf, (s0, s1), [tuple(map(int, ln.split())) for ln in out[1:1 + levels]] if ok else []
+
+
+@pytest.mark.parametrize("m", [1 << 16, 100_000, 210_006, 6_500_007, 50_000_050, 400_000_400, 500_000_050, 3_100_000_024, 4_200_000_000])
+@pytest.mark.parametrize("leaf_target", [768, 16, 1])
+def test_ksf_plan_invariants(host_emul, m, leaf_target):
+    """What the fixed-slot kernels rely on (kmerset_fast.cuh): digits of at most 8 bits (256 counters per tile), slots that are
+    multiples of 32 items (16-byte cp.async copies of tiles and leaves stay aligned), all digits inside the top 40 bits of the
+    scrambled word (KWord::digit_top; the sharded path puts 8 more bits in front), leaf slots of KSF_LEAF_CAP items with a mean
+    fill of at most leaf_target, ping/pong buffers that hold every level they serve."""
+    ok, levels, n_leaf, slots, rows = _ksf_plan(m, leaf_target)
+    assert ok and 1 <= levels <= 4 and len(rows) == levels      # every size up to 2^32 positions is plannable, down to leaves of 1
+    cum = 0
+    for i, (bits, c, cap) in enumerate(rows):
+        assert 1 <= bits <= 8
+        cum += bits
+        assert c == cum and cum <= 40
+        assert cap % 32 == 0 and 0 < cap < 1 << 32
+        mean = m / (1 << cum)
+        if i == levels - 1:
+            assert cap == 1024 and (m >> cum) <= leaf_target
+        else:
+            assert cap >= mean + 8 * mean ** 0.5                     # mean + 8 sigma of a Poisson-tight bucket
+        assert slots[i & 1] >= (1 << cum) * cap
+    assert n_leaf == 1 << cum
+    assert max(b for b, _, _ in rows) - min(b for b, _, _ in rows) <= 1  # digits spread evenly over the levels
+
+
+def test_ksf_plan_small_inputs_take_the_exact_path(host_emul):
+    assert _ksf_plan((1 << 16) - 1)[0] == 0 and _ksf_plan(0)[0] == 0
+    ok, levels, n_leaf, _, rows = _ksf_plan(50_000_050)              # configs[1]: two 8-bit levels, 65536 leaves of ~763
+    assert (ok, levels, n_leaf) == (1, 2, 65536) and [r[0] for r in rows] == [8, 8]
