@@ -407,3 +407,19 @@ def test_fast_set_config2_full_size(ctx):
     got, n_on = orc.ms_kmers(r.ms, 31, True)
     keys, _ = ctx.count_kmers(seq, k=31)
     assert n_on == r.n_kmers and np.array_equal(got, keys)
+
+
+def test_compute_human_like_genome_with_repeats(ctx):
+    """Scale model of configs[4] with the repeat model of SURVEY.md §8d (synth.human_like_genome: 24 records, ~5 % of the bases
+    copied from earlier positions with 1-10 % divergence, half of the copies reverse-complemented, N runs): exact k-mer set,
+    every k-mer ON exactly once, and more simplitigs than records (the repeats break the first-occurrence runs)."""
+    recs = synth.human_like_genome(3_000_000, seed=3100)
+    seq, off, ln = synth.frame_records(recs)
+    want_k, _ = orc.count_kmers(seq, off, ln, 31, True)
+    r = ctx.compute(seq, k=31)
+    keys, _ = ctx.count_kmers(seq, k=31)
+    assert np.array_equal(keys, want_k) and r.n_kmers == len(want_k)
+    got, n_on = orc.ms_kmers(r.ms, 31, True)
+    assert n_on == r.n_kmers and np.array_equal(got, keys)
+    assert r.n_nodes > len(recs)
+    assert r.length < r.n_kmers + 30 * r.n_nodes + 1        # every overlap the greedy found shortens the superstring

@@ -193,3 +193,24 @@ def test_verifier_pinned(golden):
     assert len(got) <= len(exp)
     if len(set(map(bytes, got))) != len(exp):
         assert not orc.verify_ms(bytes(bad), g["k"], g["complements"], exp)
+
+
+def test_synth_human_like_genome_is_seeded_and_has_repeats():
+    """Generator of configs[4]: deterministic, 24 records in human-like proportions, a few N runs, and
+    ~1 % of the 31-mer windows are repeats of earlier ones (5 % of the bases are copies with 1-10 % divergence)."""
+    import hashlib
+    from kmercamel_b200 import synth
+    recs = synth.human_like_genome(2_000_000, seed=3100)
+    again = synth.human_like_genome(2_000_000, seed=3100)
+    assert len(recs) == 24 and sum(len(r) for r in recs) == 2_000_000
+    assert all(np.array_equal(a, b) for a, b in zip(recs, again))
+    assert len(recs[0]) > 4 * len(recs[21])                              # chr1 vs chr22
+    seq, off, ln = synth.frame_records(recs)
+    assert hashlib.md5(seq.tobytes()).hexdigest() == "e72bac7b262774df96c6416fdca95166"
+    n_frac = float((seq == ord("N")).mean())
+    assert 0.001 < n_frac < 0.03
+    keys, vals = orc.count_kmers(seq, off, ln, 31, True)
+    repeats = int(vals.astype(np.int64).sum())                           # occurrences beyond the first
+    assert 0.003 * len(keys) < repeats < 0.03 * len(keys)
+    other = synth.human_like_genome(2_000_000, seed=3101)
+    assert not np.array_equal(other[0], recs[0])
