@@ -135,6 +135,17 @@ int kc_copy_to_host(kc_ctx *ctx, void *dst_host, const void *src_device, uint64_
  * after the -z filter.  Outputs are malloc'ed by the library; release with kc_free. */
 int kc_count_kmers(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t **keys, uint8_t **counts, uint64_t *n);
 
+/* Stage 1 as an order-independent digest, for sets too large to bring back and compare: digest[0] = n (distinct k-mers kept),
+ * digest[1] = sum of h, digest[2] = xor of h, digest[3] = sum of h * c, all mod 2^64, where c = min(occurrences, 256) with
+ * min_frequency > 1 (the frequency map of ReadKMersFiltered) and c = 1 otherwise (ReadKMers keeps no counts), and h folds the limbs
+ * of a k-mer through the splitmix64 finaliser (h = mix(w0 + C); h = mix(h ^ (w_i + C * (i + 1))), C = 0x9e3779b97f4a7c15).
+ * masked = 0: `in` is a framed input as for kc_count_kmers (the digest of ReadKMers / ReadKMersFiltered, src/parser.h:107-141).
+ * masked = 1: in->seq is ONE masked superstring of in->n_bytes letters; the set is the k-mers of the windows that start with an
+ *             upper-case letter, i.e. the set the superstring REPRESENTS (what the reference's verify.py compares, and
+ *             src/parser.h:41-42 case_sensitive); min_frequency must be 1.
+ * `kmercamel compute` output verifies iff digest(masked = 1, output) == digest(masked = 0, input). */
+int kc_kmer_digest(kc_ctx *ctx, const kc_params *p, const kc_input *in, int masked, uint64_t *digest);
+
 /* Overlap stage only (host buffers).  first/last: n * limbs limbs.  edge_from: N = n * (1 + complements) entries,
  * -1 = none; overlaps: N entries, 255 = none — the overlapPath of src/global.h:35.  strict = 1 reproduces the
  * reference's tie order exactly; lower_bound = 1 is the cycle-cover mode of src/lower_bound.h. */

@@ -80,6 +80,7 @@ def load_library():
     L.kc_fasta_first_header.argtypes = [C.c_char_p, C.c_uint64, u64p]
     L.kc_count_kmers.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.POINTER(u64p), C.POINTER(u8p),
                                  u64p]
+    L.kc_kmer_digest.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.c_int, u64p]
     L.kc_overlap_path.argtypes = [C.c_void_p, u64p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, i64p, u8p]
     L.kc_frame_fasta.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(u8p), u64p, C.POINTER(u64p), C.POINTER(u64p), u64p]
     L.kc_shard_granule.argtypes = [C.c_int]
@@ -116,7 +117,7 @@ def load_library():
     return L
 
 
-EXPORTED_SYMBOLS = ["kc_init", "kc_destroy", "kc_compute", "kc_compute_device", "kc_lower_bound", "kc_copy_to_host", "kc_count_kmers", "kc_overlap_path",
+EXPORTED_SYMBOLS = ["kc_kmer_digest", "kc_init", "kc_destroy", "kc_compute", "kc_compute_device", "kc_lower_bound", "kc_copy_to_host", "kc_count_kmers", "kc_overlap_path",
                     "kc_p2p_alloc", "kc_p2p_open", "kc_p2p_hist", "kc_p2p_scatter", "kc_p2p_resolve", "kc_total_launches", "kc_shard_granule", "kc_shard_partition", "kc_shard_resolve", "kc_compute_from_flags", "kc_compute_from_flags_slice",
                     "kc_streaming", "kc_maskopt", "kc_split_ms", "kc_join_ms", "kc_ms_to_spss", "kc_spss_to_ms", "kc_fasta_first_header",
                     "kc_frame_fasta", "kc_set_option", "kc_get_stat", "kc_profile_enable", "kc_profile_count", "kc_profile_get", "kc_profile_reset",
@@ -344,6 +345,18 @@ class Context:
         self._check(self._lib.kc_count_kmers(self._h, C.byref(p), C.byref(inp), C.byref(keys), C.byref(cnt), C.byref(n)))
         L = limbs_for_k(k)
         return _take(keys, n.value * L, np.uint64).reshape(n.value, L), _take(cnt, n.value, np.uint8)
+
+    def kmer_digest(self, seq, *, k, complements=True, min_frequency=1, masked=False):
+        """Stage 1 as an order-independent digest [n, sum h, xor h, sum h * min(occurrences, 256)] (kc_kmer_digest).
+        masked=True: `seq` is one masked superstring; the digest is that of the k-mer set it represents."""
+        if isinstance(seq, (bytes, bytearray)):
+            seq = np.frombuffer(seq, dtype=np.uint8)
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        p = self._params(k, complements, min_frequency, False, False)
+        inp = kc_input(seq.ctypes.data, seq.size, None, None, 0)
+        d = (C.c_uint64 * 4)()
+        self._check(self._lib.kc_kmer_digest(self._h, C.byref(p), C.byref(inp), int(bool(masked)), d))
+        return [int(x) for x in d]
 
     def overlap_path(self, first, last, *, k, complements=True, lower_bound=False, strict=True):
         """Overlap stage: first/last [n, limbs] u64 -> (edge_from [N] i64, overlaps [N] u8)."""

@@ -417,6 +417,56 @@ void count_only(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &
     KC_CUDA(cudaStreamSynchronize(ex.stream));
 }
 
+// kc_kmer_digest: (n, sum h, xor h, sum h * c) over the kept (k-mer, c = min(occurrences, 256), or 1 without -z) pairs, h = the splitmix64 fold of
+// the limbs.  The same four numbers come out of oracle/ref_harness `full` for the reference's own hash table.
+KC_HD u64 kc_mix64(u64 x) {
+    x ^= x >> 30;
+    x *= 0xbf58476d1ce4e5b9ULL;
+    x ^= x >> 27;
+    x *= 0x94d049bb133111ebULL;
+    x ^= x >> 31;
+    return x;
+}
+
+template <int L>
+void digest_only(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, const u32 *win_mask, uint64_t *digest) {
+    KC_CUDA(cudaEventRecord(ctx->ev[0], ex.stream));
+    KmerSet<L> set = kc_kmerset_build<L>(ex, in.seq, in.n_bytes, p.k, p.complements != 0, p.min_frequency, nullptr, true, nullptr, win_mask);
+    const u64 U = set.n_kept;
+    kc_ull *acc = reinterpret_cast<kc_ull *>(ex.alloc<u64>(4));
+    ex.fill_bytes(acc, 0, 32);
+    const KWord<L> *keys = set.keys;
+    const u8 *cnt = set.cnt;
+    const bool counted = p.min_frequency > 1;  // ReadKMers (-z 1) keeps no counts: c = 1
+    ex.for_each(kc_div_up(U, 32) * 32, [=] __device__(u64 i) {
+        u64 h = 0, wv = 0;
+        if (i < U) {
+            h = kc_mix64(keys[i].w[0] + 0x9e3779b97f4a7c15ULL);
+#pragma unroll
+            for (int l = 1; l < L; ++l) h = kc_mix64(h ^ (keys[i].w[l] + 0x9e3779b97f4a7c15ULL * (u64) (l + 1)));
+            wv = counted ? h * ((u64) cnt[i] + 1) : h;
+        }
+        u64 s = h, x = h;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+            x ^= __shfl_xor_sync(0xFFFFFFFFu, x, o);
+            wv += __shfl_xor_sync(0xFFFFFFFFu, wv, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&acc[1], (kc_ull) s);
+            atomicXor(&acc[2], (kc_ull) x);
+            atomicAdd(&acc[3], (kc_ull) wv);
+        }
+    }, KP_MISC, U * (sizeof(KWord<L>) + 1));
+    u64 h4[4];
+    ex.read_n(reinterpret_cast<const u64 *>(acc), h4, 4);
+    digest[0] = U;
+    digest[1] = h4[1];
+    digest[2] = h4[2];
+    digest[3] = h4[3];
+}
+
 template <int L>
 void overlap_only(kc_ctx *ctx, CudaExec &ex, const uint64_t *first, const uint64_t *last, u64 n, int k, bool complements, bool lower_bound,
                   bool strict, int64_t *edge_from, uint8_t *overlaps) {
@@ -782,6 +832,53 @@ int kc_count_kmers(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t
     if (p->k < 32) count_only<1>(ctx, ex, di, *p, keys, counts, n);
     else if (p->k < 64) count_only<2>(ctx, ex, di, *p, keys, counts, n);
     else count_only<4>(ctx, ex, di, *p, keys, counts, n);
+    ctx->total_launches += ex.launches;
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
+int kc_kmer_digest(kc_ctx *ctx, const kc_params *p, const kc_input *in, int masked, uint64_t *digest) {
+    if (!ctx || !in || !digest) return KC_ERR_ARG;
+    KC_API_BEGIN
+    check_params(p);
+    if (masked && p->min_frequency != 1) KC_THROW(KC_ERR_ARG, "a masked superstring has no counts");
+    if (in->n_bytes + 1 >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 sequence bytes on one GPU");
+    KC_CUDA(cudaSetDevice(ctx->device));
+    const int limbs = kc_limbs_for_k(p->k);
+    // masked: the bytes are ONE masked superstring (no framing); a '\n' is appended so that it is a framed record
+    const u64 nb = masked ? in->n_bytes + 1 : in->n_bytes;
+    size_t need = (size_t) ((double) nb * (1.0 + 2.0 * 8 * limbs + 4.0 + 0.2) * 1.15) + (256u << 20);
+    ensure_arena(ctx, need);
+    ctx->arena.reset();
+    CudaExec ex{ctx->stream, &ctx->arena};
+    ex.prof = &ctx->prof;
+    ex.pinned = ctx->pin_small;
+    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
+    u8 *d_seq = ex.alloc<u8>(nb + 64);
+    if (in->n_bytes) KC_CUDA(cudaMemcpyAsync(d_seq, in->seq, in->n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    u32 *win_mask = nullptr;
+    if (masked) {  // the windows whose first letter is upper case are the represented k-mers (reference verify.py / src/parser.h:41-42)
+        ex.fill_bytes(d_seq + in->n_bytes, '\n', 64);
+        const u64 tile = kc_shard_granule(p->k);
+        const u64 mwords = kc_div_up(nb, tile) * (tile / 32) + 1;
+        win_mask = ex.arena->alloc_top<u32>(mwords);
+        const u64 len = in->n_bytes;
+        const int k = p->k;
+        u32 *wm = win_mask;
+        const u8 *sq = d_seq;
+        ex.for_each(mwords, [=] __device__(u64 w) {
+            u32 m = 0;
+            for (int i = 0; i < 32; ++i) {
+                const u64 q = w * 32 + i;
+                if (q + 1 >= (u64) k && q < len && sq[q + 1 - k] <= 'Z') m |= 1u << i;
+            }
+            wm[w] = m;
+        }, KP_MISC, len + len / 8);
+    }
+    DevInput di{d_seq, nb, nullptr, nullptr, in->n_recs};
+    if (limbs == 1) digest_only<1>(ctx, ex, di, *p, win_mask, digest);
+    else if (limbs == 2) digest_only<2>(ctx, ex, di, *p, win_mask, digest);
+    else digest_only<4>(ctx, ex, di, *p, win_mask, digest);
     ctx->total_launches += ex.launches;
     return KC_OK;
     KC_API_END(ctx)

@@ -178,6 +178,32 @@ def count_kmers(seq, rec_off, rec_len, k: int, complements: bool):
     return _take(keys, nn * L, np.uint64).reshape(nn, L), _take(vals, nn, np.uint8)
 
 
+def _mix64(x):
+    x = x ^ (x >> np.uint64(30))
+    x = x * np.uint64(0xbf58476d1ce4e5b9)
+    x = x ^ (x >> np.uint64(27))
+    x = x * np.uint64(0x94d049bb133111eb)
+    return x ^ (x >> np.uint64(31))
+
+
+def kmer_digest(keys, vals, min_frequency: int = 1):
+    """[n, sum h, xor h, sum h * c] mod 2^64 over the (key, val) pairs with val + 1 >= min_frequency, c = val + 1 with
+    min_frequency > 1 and 1 otherwise (the reference keeps no counts without -z) —
+    the digest of oracle/ref_harness.cpp `full` (kmer_digest there) and of the product's kc_kmer_digest.  numpy, wrapping."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    keys = keys.reshape(len(keys), -1)
+    vals = np.asarray(vals, dtype=np.uint64)
+    keep = vals + np.uint64(1) >= np.uint64(min_frequency)
+    keys, vals = keys[keep], vals[keep]
+    c = np.uint64(0x9e3779b97f4a7c15)
+    with np.errstate(over="ignore"):
+        h = _mix64(keys[:, 0] + c)
+        for i in range(1, keys.shape[1]):
+            h = _mix64(h ^ (keys[:, i] + c * np.uint64(i + 1)))
+        return [int(len(h)), int(h.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(h)) if len(h) else 0,
+                int((h * (vals + np.uint64(1)) if min_frequency > 1 else h).sum(dtype=np.uint64))]
+
+
 def overlap_path(first, last, k: int, complements: bool, lower_bound: bool = False):
     """first/last: [n, limbs] u64 -> (edge_from [N] i64, overlaps [N] u8)."""
     first = np.ascontiguousarray(first, dtype=np.uint64)
