@@ -247,7 +247,9 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
     }
     if (!assume_simplitigs)
         write_log("Finished collecting k-mers: " + std::to_string(out.n_kmers) + " " + std::to_string(k) + "-mers.");
-    write_log("Finished 1. part: " + std::string(assume_simplitigs ? "simplitigs (" : "GPU k-mer nodes (") + std::to_string(out.n_nodes) + ").");
+    write_log("Finished 1. part: simplitigs (" + std::to_string(out.n_simplitigs) + " simplitigs).");  // src/main.cpp:174
+    if (!assume_simplitigs && out.n_simplitigs * 5 >= out.n_kmers)                                       // src/main.cpp:175-176
+        write_log("2. part: Number of simplitigs over threshold, computing directly from k-mers.");
     write_log("Finished 2. part: Hamiltonian path.");
     if (lower_bound) {  // src/lower_bound.h:21, src/main.cpp:182,210
         write_log("Finished 3. part: lower bound = " + std::to_string(bound) + ".");

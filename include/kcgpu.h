@@ -77,6 +77,9 @@ typedef struct kc_output {
     uint64_t n_occurrences;/* k-mer windows seen (M) */
     uint64_t n_nodes;      /* nodes handed to the overlap stage (k-mers, or records with -S) */
     uint64_t n_launches;   /* CUDA kernels launched by this call */
+    uint64_t n_simplitigs; /* simplitigs of the d = k-1 level (first-occurrence runs, or records with -S): the count of the
+                              reference's "Finished 1. part" log line (src/main.cpp:174).  When 5 * n_simplitigs >= n_kmers the
+                              greedy ran on the individual k-mers (src/main.cpp:175-181) and n_nodes == n_kmers. */
     kc_stage_times t;
 } kc_output;
 
@@ -134,6 +137,11 @@ int kc_copy_to_host(kc_ctx *ctx, void *dst_host, const void *src_device, uint64_
 /* Stage 1 only (host buffers): sorted distinct k-mers (n * limbs uint64) and min(occurrences-1, 255) per k-mer,
  * after the -z filter.  Outputs are malloc'ed by the library; release with kc_free. */
 int kc_count_kmers(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t **keys, uint8_t **counts, uint64_t *n);
+
+/* PartialPreSort of the sparse path (reference src/global_sparse.h:14-35): the k-mers (n * limbs little-endian limbs, host)
+ * reordered by a stable counting sort on their top min(2k, 8) bits -> out (host, same size).  kc_compute applies it itself
+ * when the sparse switch is taken; this entry point exists for the known-answer tests (tests/global_sparse_unittest.h:11-41). */
+int kc_partial_presort(kc_ctx *ctx, const uint64_t *kmers, uint64_t n, int k, uint64_t *out);
 
 /* Stage 1 as an order-independent digest, for sets too large to bring back and compare: digest[0] = n (distinct k-mers kept),
  * digest[1] = sum of h, digest[2] = xor of h, digest[3] = sum of h * c, all mod 2^64, where c = min(occurrences, 256) with
@@ -212,7 +220,8 @@ int kc_p2p_resolve(kc_ctx *ctx, const kc_params *p, const uint64_t *all_counts, 
 /* CUDA kernels launched through this context since kc_init (every entry point adds its own). */
 uint64_t kc_total_launches(const kc_ctx *ctx);
 
-/* Tuning / test knobs.  "small_engine" (default 1): run the tail of the overlap levels in the single-CTA kernel.
+/* Tuning / test knobs.  "sparse_switch" (default 1): hand the individual k-mers to the greedy when 5 * simplitigs >= k-mers.
+ * "small_engine" (default 1): run the tail of the overlap levels in the single-CTA kernel.
  * "fast_set" (default 1): try the histogram-free k-mer set construction first (from-FASTA compute without -M);
  * "fast_leaf_target", "fast_sigmas", "fast_min_items": its plan parameters, exposed so that tests reach the
  * multi-level plan and the overflow fallback with small inputs; "fast_heuristics" (default 1): skip the attempt when

@@ -47,7 +47,7 @@ class kc_stage_times(C.Structure):
 
 class kc_output(C.Structure):
     _fields_ = [("ms", C.c_void_p), ("ms_maxone", C.c_void_p), ("length", C.c_uint64), ("n_kmers", C.c_uint64),
-                ("n_occurrences", C.c_uint64), ("n_nodes", C.c_uint64), ("n_launches", C.c_uint64), ("t", kc_stage_times)]
+                ("n_occurrences", C.c_uint64), ("n_nodes", C.c_uint64), ("n_launches", C.c_uint64), ("n_simplitigs", C.c_uint64), ("t", kc_stage_times)]
 
 
 def lib_path() -> str:
@@ -80,6 +80,7 @@ def load_library():
     L.kc_fasta_first_header.argtypes = [C.c_char_p, C.c_uint64, u64p]
     L.kc_count_kmers.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.POINTER(u64p), C.POINTER(u8p),
                                  u64p]
+    L.kc_partial_presort.argtypes = [C.c_void_p, u64p, C.c_uint64, C.c_int, u64p]
     L.kc_kmer_digest.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.c_int, u64p]
     L.kc_overlap_path.argtypes = [C.c_void_p, u64p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, i64p, u8p]
     L.kc_frame_fasta.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(u8p), u64p, C.POINTER(u64p), C.POINTER(u64p), u64p]
@@ -117,7 +118,7 @@ def load_library():
     return L
 
 
-EXPORTED_SYMBOLS = ["kc_kmer_digest", "kc_init", "kc_destroy", "kc_compute", "kc_compute_device", "kc_lower_bound", "kc_copy_to_host", "kc_count_kmers", "kc_overlap_path",
+EXPORTED_SYMBOLS = ["kc_kmer_digest", "kc_partial_presort", "kc_init", "kc_destroy", "kc_compute", "kc_compute_device", "kc_lower_bound", "kc_copy_to_host", "kc_count_kmers", "kc_overlap_path",
                     "kc_p2p_alloc", "kc_p2p_open", "kc_p2p_hist", "kc_p2p_scatter", "kc_p2p_resolve", "kc_total_launches", "kc_shard_granule", "kc_shard_partition", "kc_shard_resolve", "kc_compute_from_flags", "kc_compute_from_flags_slice",
                     "kc_streaming", "kc_maskopt", "kc_split_ms", "kc_join_ms", "kc_ms_to_spss", "kc_spss_to_ms", "kc_fasta_first_header",
                     "kc_frame_fasta", "kc_set_option", "kc_get_stat", "kc_profile_enable", "kc_profile_count", "kc_profile_get", "kc_profile_reset",
@@ -218,6 +219,7 @@ class ComputeResult:
     n_occurrences: int
     n_nodes: int
     n_launches: int
+    n_simplitigs: int = 0
     times_ms: dict = field(default_factory=dict)
     ms_ptr: int = 0        # device pointers for compute_device
     maxone_ptr: int = 0
@@ -268,7 +270,7 @@ class Context:
         if copy_host:
             ms = C.string_at(out.ms, out.length)
             mo = C.string_at(out.ms_maxone, out.length) if out.ms_maxone else None
-        return ComputeResult(ms, mo, out.length, out.n_kmers, out.n_occurrences, out.n_nodes, out.n_launches, times,
+        return ComputeResult(ms, mo, out.length, out.n_kmers, out.n_occurrences, out.n_nodes, out.n_launches, out.n_simplitigs, times,
                              out.ms or 0, out.ms_maxone or 0)
 
     def compute(self, seq, rec_off=None, rec_len=None, *, k, complements=True, min_frequency=1, assume_simplitigs=False,
@@ -345,6 +347,13 @@ class Context:
         self._check(self._lib.kc_count_kmers(self._h, C.byref(p), C.byref(inp), C.byref(keys), C.byref(cnt), C.byref(n)))
         L = limbs_for_k(k)
         return _take(keys, n.value * L, np.uint64).reshape(n.value, L), _take(cnt, n.value, np.uint8)
+
+    def partial_presort(self, kmers, *, k):
+        """PartialPreSort (reference src/global_sparse.h:14-35): kmers [n, limbs] u64 -> reordered copy."""
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint64).reshape(-1, limbs_for_k(k))
+        out = np.zeros_like(kmers)
+        self._check(self._lib.kc_partial_presort(self._h, kmers.ctypes.data_as(u64p), kmers.shape[0], int(k), out.ctypes.data_as(u64p)))
+        return out
 
     def kmer_digest(self, seq, *, k, complements=True, min_frequency=1, masked=False):
         """Stage 1 as an order-independent digest [n, sum h, xor h, sum h * min(occurrences, 256)] (kc_kmer_digest).

@@ -47,6 +47,7 @@ struct kc_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_ev[KC_H2D_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
     bool small_engine = true;
+    bool sparse_switch = true;  // src/main.cpp:175 (option "sparse_switch" = 0 keeps the runs as nodes whatever their number)
     KsfTuning fast;          // histogram-free set construction (kmerset_fast.cuh); KC_FAST_* environment knobs for tests
     u64 fast_runs = 0, fast_fallbacks = 0;
     bool fast_heuristics = true;  // skip the fixed-slot attempt when duplicates are expected (see run_stage1_runs)
@@ -139,7 +140,7 @@ size_t estimate_arena(u64 n_bytes, u64 n_recs, int limbs, bool complements, bool
             if (f > stage1) stage1 = f;
         }
     }
-    double nodes = simplitigs ? (double) n_recs : (pessimistic ? n_bytes / 2.0 : n_bytes / 64.0 + 1e6);
+    double nodes = simplitigs ? (double) n_recs : (pessimistic ? n_bytes * 0.85 : n_bytes / 64.0 + 1e6);  // sparse switch: up to 5 k-mer nodes per 6 bytes
     double N = c * nodes;
     double engine = N * (60.0 + 2.0 * 2.0 * (wb + 8.0) + 12.0 + 40.0);
     double emit = N * 32.0 + 3.0 * n_bytes;
@@ -173,7 +174,7 @@ struct DevInput {
 
 struct DevResult {
     const u8 *ms = nullptr, *maxone = nullptr;
-    u64 length = 0, n_kmers = 0, n_occ = 0, n_nodes = 0;
+    u64 length = 0, n_kmers = 0, n_occ = 0, n_nodes = 0, n_simplitigs = 0;
     u64 lower_bound = 0;  // only with run_pipeline(..., lower_bound = true)
     u64 slice_begin = 0, slice_len = 0;
 };
@@ -302,6 +303,9 @@ void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params
             U = run_stage1_runs<L>(ctx, ex, in, p, &runs, &uniq, &n_occ);
         }
         if (U == 0) KC_THROW(KC_ERR_EMPTY, "the input contains no k-mers");  // src/main.cpp:155-158
+        res.n_simplitigs = runs.n_runs;
+        // src/main.cpp:94,175-181: simplitigs barely longer than k-mers -> the greedy runs on the k-mers themselves (PartialPreSort order)
+        if (ctx->sparse_switch && runs.n_runs * 5 >= U) runs = kc_kmer_nodes_from_runs(ex, in.seq, runs, p.k);
         n_nodes = runs.n_runs;
         node_off = runs.rec_off;
         node_len = runs.rec_len;
@@ -317,6 +321,7 @@ void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params
             KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
         }
         n_nodes = in.n_recs;
+        res.n_simplitigs = in.n_recs;
     }
     {
         KWord<L> *first = ex.alloc<KWord<L>>(n_nodes), *last = ex.alloc<KWord<L>>(n_nodes);
@@ -587,6 +592,7 @@ int kc_compute_device(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_ou
     out->n_kmers = res.n_kmers;
     out->n_occurrences = res.n_occ;
     out->n_nodes = res.n_nodes;
+    out->n_simplitigs = res.n_simplitigs;
     out->n_launches = ex.launches;
     fill_times(ctx, out);
     ctx->total_launches += ex.launches;
@@ -665,6 +671,7 @@ int kc_compute(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *o
     out->n_kmers = res.n_kmers;
     out->n_occurrences = res.n_occ;
     out->n_nodes = res.n_nodes;
+    out->n_simplitigs = res.n_simplitigs;
     out->n_launches = ex.launches;
     fill_times(ctx, out);
     ctx->total_launches += ex.launches;
@@ -707,6 +714,7 @@ int kc_lower_bound(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t
         stats->n_kmers = res.n_kmers;
         stats->n_occurrences = res.n_occ;
         stats->n_nodes = res.n_nodes;
+        stats->n_simplitigs = res.n_simplitigs;
         stats->n_launches = ex.launches;
         fill_times(ctx, stats);
     }
@@ -832,6 +840,37 @@ int kc_count_kmers(kc_ctx *ctx, const kc_params *p, const kc_input *in, uint64_t
     if (p->k < 32) count_only<1>(ctx, ex, di, *p, keys, counts, n);
     else if (p->k < 64) count_only<2>(ctx, ex, di, *p, keys, counts, n);
     else count_only<4>(ctx, ex, di, *p, keys, counts, n);
+    ctx->total_launches += ex.launches;
+    return KC_OK;
+    KC_API_END(ctx)
+}
+
+int kc_partial_presort(kc_ctx *ctx, const uint64_t *kmers, uint64_t n, int k, uint64_t *out) {
+    if (!ctx || (n && (!kmers || !out))) return KC_ERR_ARG;
+    KC_API_BEGIN
+    if (k < 1 || k > 127) KC_THROW(KC_ERR_ARG, "k must be in 1..127");
+    if (n >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "too many k-mers");
+    if (n == 0) return KC_OK;
+    KC_CUDA(cudaSetDevice(ctx->device));
+    const int limbs = kc_limbs_for_k(k);
+    ensure_arena(ctx, (size_t) (n * (16.0 * limbs + 64.0)) + (64u << 20));
+    ctx->arena.reset();
+    CudaExec ex{ctx->stream, &ctx->arena};
+    ex.prof = &ctx->prof;
+    ex.pinned = ctx->pin_small;
+    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
+    u64 *src = ex.alloc<u64>(n * limbs), *dst = ex.alloc<u64>(n * limbs);
+    KC_CUDA(cudaMemcpyAsync(src, kmers, n * limbs * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const int sfb = 2 * k < 8 ? 2 * k : 8;  // SORT_FIRST_BITS, src/global_sparse.h:16
+    const int pos = 2 * k - sfb, limb = pos >> 6, off = pos & 63;
+    const u64 *perm = kc_partial_presort_perm(ex, n, [=] __device__(u64 i) {
+        u64 v = src[i * limbs + limb] >> off;
+        if (off + sfb > 64 && limb + 1 < limbs) v |= src[i * limbs + limb + 1] << (64 - off);
+        return (u32) (v & ((1u << sfb) - 1u));
+    });
+    ex.for_each(n * limbs, [=] __device__(u64 t) { dst[t] = src[(perm[t / limbs] & 0xFFFFFFFFULL) * limbs + t % limbs]; });
+    KC_CUDA(cudaMemcpyAsync(out, dst, n * limbs * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    KC_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->total_launches += ex.launches;
     return KC_OK;
     KC_API_END(ctx)
@@ -996,7 +1035,7 @@ int kc_compute_from_flags_slice(kc_ctx *ctx, const kc_params *p, const kc_input 
     // no stage 1 here: only the node-dependent part (+ the emission scratch) is needed
     const double c = p->complements ? 2.0 : 1.0;
     auto need = [&](double nodes) { return (size_t) ((c * nodes * (240.0 + 32.0 * limbs) + 3.0 * in->n_bytes) * 1.1) + (256u << 20); };
-    run_with_arena(ctx, need(in->n_bytes / 64.0 + 1e6), need(in->n_bytes / 2.0), [&] {
+    run_with_arena(ctx, need(in->n_bytes / 64.0 + 1e6), need(in->n_bytes * 0.85), [&] {
         if (p->k < 32) run_pipeline<1>(ctx, ex, di, *p, res, flags_dev, n_kept, false, slice_index, n_slices);
         else if (p->k < 64) run_pipeline<2>(ctx, ex, di, *p, res, flags_dev, n_kept, false, slice_index, n_slices);
         else run_pipeline<4>(ctx, ex, di, *p, res, flags_dev, n_kept, false, slice_index, n_slices);
@@ -1010,6 +1049,7 @@ int kc_compute_from_flags_slice(kc_ctx *ctx, const kc_params *p, const kc_input 
     out->n_kmers = res.n_kmers;
     out->n_occurrences = 0;
     out->n_nodes = res.n_nodes;
+    out->n_simplitigs = res.n_simplitigs;
     out->n_launches = ex.launches;
     fill_times(ctx, out);
     ctx->total_launches += ex.launches;
@@ -1239,6 +1279,10 @@ int kc_get_stat(const kc_ctx *ctx, const char *name, uint64_t *value) {
 
 int kc_set_option(kc_ctx *ctx, const char *name, int value) {
     if (!ctx || !name) return KC_ERR_ARG;
+    if (std::strcmp(name, "sparse_switch") == 0) {
+        ctx->sparse_switch = value != 0;
+        return KC_OK;
+    }
     if (std::strcmp(name, "small_engine") == 0) {
         ctx->small_engine = value != 0;
         return KC_OK;

@@ -7,6 +7,7 @@
 #pragma once
 #include "exec.cuh"
 #include "kmerset.cuh"
+#include "sort.cuh"
 
 #ifdef __CUDACC__
 
@@ -122,6 +123,54 @@ inline RunNodes kc_runs_from_flags(CudaExec &ex, const u32 *flags, u64 n_pos, in
     runs.rec_len = rec_len;
     runs.n_runs = n_runs;
     return runs;
+}
+
+// ---- sparse switch (reference src/main.cpp:94,175-181) ---------------------------------------------------------------------
+// PartialPreSort (src/global_sparse.h:14-35): a STABLE counting sort on the top min(2k, 8) bits of the k-mer.  Stable = sorted by
+// (digit, original index), a unique 40-bit key, so any sort of those keys is the stable order: key[i] = digit(i) << 32 | i goes
+// through the radix sort of sort.cuh and the low 32 bits come back as the permutation (new position -> old index).
+template <class DigitOf> u64 *kc_partial_presort_perm(CudaExec &ex, u64 n, DigitOf digit_of) {
+    KWord<1> *keys = ex.alloc<KWord<1>>(n), *tmp = ex.alloc<KWord<1>>(n);
+    ex.for_each(n, [=] __device__(u64 i) { keys[i].w[0] = ((u64) digit_of(i) << 32) | i; }, KP_MISC, n * 16);
+    kc_sort<1>(ex, keys, tmp, n, 40);
+    return reinterpret_cast<u64 *>(keys);
+}
+
+// When the simplitigs are barely longer than k-mers (5 n >= U) the reference drops them and runs the greedy on the individual
+// k-mers: simplitigs_to_kmer_vec (src/simplitigs.h:53-65: every k-mer of every simplitig, in simplitig order, in the
+// orientation it has there) followed by PartialPreSort.  Here a simplitig is a first-occurrence run, so its k-mers are the
+// windows of the run in input order and orientation: node i = k bytes at off[i], digit = its first min(k, 4) bases.
+inline RunNodes kc_kmer_nodes_from_runs(CudaExec &ex, const u8 *seq, const RunNodes &runs, int k) {
+    RunNodes out;
+    const u64 n_runs = runs.n_runs;
+    if (n_runs == 0) return out;
+    const size_t mark = ex.arena->mark();
+    u32 *pre = ex.alloc<u32>(n_runs + 1);
+    const u64 *r_off = runs.rec_off, *r_len = runs.rec_len;
+    ex.for_each(n_runs + 1, [=] __device__(u64 r) { pre[r] = r < n_runs ? (u32) (r_len[r] - (u64) k + 1) : 0u; }, KP_RUNS, n_runs * 12);
+    const u64 U = ex.exclusive_scan(pre, pre, n_runs + 1);
+    if (U >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "too many k-mer nodes for one GPU");
+    u64 *n_off = ex.arena->alloc_top<u64>(U), *n_len = ex.arena->alloc_top<u64>(U);
+    u64 *tmp_off = ex.alloc<u64>(U);
+    ex.for_each(U, [=] __device__(u64 i) {
+        const u32 r = kc_upper_bound_u32(pre, (u32) n_runs + 1, (u32) i) - 1;
+        tmp_off[i] = r_off[r] + (i - pre[r]);
+    }, KP_RUNS, U * 12);
+    const int nb = k < 4 ? k : 4;  // SORT_FIRST_BITS = min(2k, 8) bits = the first nb bases
+    const u64 *perm = kc_partial_presort_perm(ex, U, [=] __device__(u64 i) {
+        u32 d = 0;
+        for (int j = 0; j < nb; ++j) d = (d << 2) | (kc_nucleotide_code(seq[tmp_off[i] + j]) & 3u);
+        return d;
+    });
+    ex.for_each(U, [=] __device__(u64 j) {
+        n_off[j] = tmp_off[perm[j] & 0xFFFFFFFFULL];
+        n_len[j] = (u64) k;
+    }, KP_RUNS, U * 32);
+    ex.arena->release(mark);
+    out.rec_off = n_off;
+    out.rec_len = n_len;
+    out.n_runs = U;
+    return out;
 }
 
 #endif  // __CUDACC__

@@ -12,6 +12,14 @@ def random_genome_records(n_records: int, record_len: int, seed: int):
     return [_ACGT[rng.integers(0, 4, size=record_len, dtype=np.uint8)] for _ in range(n_records)]
 
 
+def short_records(n_records: int, min_len: int, max_len: int, seed: int):
+    """Records barely longer than k: their simplitigs are nearly single k-mers, which makes the reference hand the individual
+    k-mers to the greedy (5 * simplitigs >= k-mers, src/main.cpp:94,175-181)."""
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(min_len, max_len + 1, size=n_records)
+    return [_ACGT[rng.integers(0, 4, size=int(l), dtype=np.uint8)] for l in lens]
+
+
 def frame_records(records):
     """Records -> (seq, rec_off, rec_len) in the layout of kc_input (each record followed by '\\n')."""
     total = sum(len(r) + 1 for r in records)
@@ -151,6 +159,10 @@ BIG_CONFIGS = {
     # three tiny ones (all word widths, with and without counts) that the CPU suite checks the oracle's digest against
     "tiny_k31z2": dict(config="tiny: 30x reads of a 20 kbp genome, k=31 -z 2", generator="reads_chunks(20_000, 30.0, 150, 0.01, 7)",
                        k=31, complements=True, min_frequency=2, one_line=True),
+    "tiny_sparse_k31": dict(config="tiny: 3000 records of 31..34 bases (sparse switch, src/main.cpp:175)",
+                            generator="short_records(3000, 31, 34, 17)", k=31, complements=True, min_frequency=1),
+    "tiny_sparse_k9u": dict(config="tiny: 5000 records of 9..11 bases, k=9 -u (sparse switch, many overlaps)",
+                            generator="short_records(5000, 9, 11, 19)", k=9, complements=False, min_frequency=1),
     "tiny_k63": dict(config="tiny: 200 kbp repeat-model genome, k=63", generator="human_like_genome(200_000, 11)",
                      k=63, complements=True, min_frequency=1),
     "tiny_k127u": dict(config="tiny: 200 kbp repeat-model genome, k=127 -u", generator="human_like_genome(200_000, 11)",
@@ -180,6 +192,10 @@ def big_config_input(name: str):
         seq = frame_reads(reads_chunks(20_000, 30.0, 150, 0.01, 7), 150)
         n = len(seq) // 151
         return seq, np.arange(n, dtype=np.uint64) * np.uint64(151), np.full(n, 150, dtype=np.uint64)
+    if name == "tiny_sparse_k31":
+        return frame_records(short_records(3000, 31, 34, 17))
+    if name == "tiny_sparse_k9u":
+        return frame_records(short_records(5000, 9, 11, 19))
     if name in ("tiny_k63", "tiny_k127u"):
         return frame_records(human_like_genome(200_000, 11))
     if name == "cfg1_50M":

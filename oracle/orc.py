@@ -178,6 +178,20 @@ def count_kmers(seq, rec_off, rec_len, k: int, complements: bool):
     return _take(keys, nn * L, np.uint64).reshape(nn, L), _take(vals, nn, np.uint8)
 
 
+def partial_presort(kmers, k: int):
+    """PartialPreSort (reference src/global_sparse.h:14-35): stable counting sort of [n, limbs] u64 k-mers on their top
+    min(2k, 8) bits."""
+    kmers = np.ascontiguousarray(kmers, dtype=np.uint64).reshape(-1, limbs_for_k(k))
+    sfb = min(2 * k, 8)
+    pos = 2 * k - sfb
+    limb, off = pos >> 6, pos & 63
+    v = kmers[:, limb] >> np.uint64(off)
+    if off + sfb > 64 and limb + 1 < kmers.shape[1]:
+        v = v | (kmers[:, limb + 1] << np.uint64(64 - off))
+    digit = (v & np.uint64((1 << sfb) - 1)).astype(np.int64)
+    return kmers[np.argsort(digit, kind="stable")]
+
+
 def _mix64(x):
     x = x ^ (x >> np.uint64(30))
     x = x * np.uint64(0xbf58476d1ce4e5b9)

@@ -48,3 +48,13 @@ def test_golden_big_records_are_consistent():
         assert r["digest"][0] == r["n_kmers"]
         if "length" in r:
             assert r["ones"] == r["n_kmers"] and r["tail_lower"] and r["length"] >= r["n_kmers"] + g["k"] - 1
+
+
+def test_partial_presort_kats():
+    """reference tests/global_sparse_unittest.h:11-41"""
+    K = orc.kmer_from_string
+    for kmers, k, want in [(["GTA", "TAC", "GGC"], 3, ["GGC", "GTA", "TAC"]),
+                           (["TTTTTTTTTTTTT", "AAAAAAAAAAAAA", "GCGCGCGCGCGCG"], 13, ["AAAAAAAAAAAAA", "GCGCGCGCGCGCG", "TTTTTTTTTTTTT"]),
+                           (["AAAAAAAAAAAAT", "AAAAAAAAAAAAA"], 13, ["AAAAAAAAAAAAT", "AAAAAAAAAAAAA"])]:
+        got = orc.partial_presort(np.stack([K(x, k) for x in kmers]), k)
+        assert np.array_equal(got, np.stack([K(x, k) for x in want]))
