@@ -11,10 +11,11 @@ Workload = BASELINE.json configs[1]: 50 x 1,000,000 bp uniform random multi-FAST
            inside the timed region).
 N > 1 (torchrun): ONE job over a genome of N x 50 Mbp (rank r contributes the 50 records of seed 12345 + r), hash-range
 sharded as the north star asks: every rank extracts the k-mers of its slice, the (k-mer, position) items go to their
-owner rank over NVLink (the level-0 scatter kernel stores straight into the owner's buffer through peer pointers, so the
-partition pass is the all-to-all; only 256 counts per rank go through NCCL), every rank resolves its hash range, the first-occurrence
-flag bit arrays are all-reduced, every rank repeats the (sequential, deterministic, ~0.2-0.6 ms) greedy merge and emits — and in the
-end-to-end arm copies back — its own 16-byte-aligned slice of the superstring.  Per-GPU counting work is fixed as N grows (weak
+owner rank over NVLink (the level-0 scatter kernel stores straight into the owner's heap through peer pointers, so the
+partition pass is the all-to-all; ranks synchronise with device-side signal words, nothing goes through NCCL on the data path), every
+rank resolves its hash range and clears the duplicates' bits on every rank, every rank repeats the (sequential, deterministic) greedy
+merge and emits — and in the end-to-end arm copies back — its own 16-byte-aligned slice of the superstring.  After the warm-up the
+concatenated slices are compared (md5) with the single-GPU result of the same sequence: "parity_n".  Per-GPU counting work is fixed as N grows (weak
 scaling); value = distinct k-mers of the whole job / max-over-ranks time.
 """
 import argparse
@@ -170,17 +171,20 @@ def workload_config(world):
                         "k=31 canonical, min-one mask, u64 word path" + (f"; x{world}: one genome of {world} x 50 Mbp" if world > 1 else ""),
             "k": K, "bases_per_gpu": N_RECORDS * RECORD_LEN, "records_per_gpu": N_RECORDS,
             "sharding": ("k-mer set construction sharded by hash range: the level-0 scatter kernel stores (k-mer, position) items "
-                         "straight into the owner GPU's buffer over NVLink (CUDA IPC peer pointers), NCCL only for the 256 "
-                         "digit counts, the barrier and the all-reduce of the flag bit arrays; every rank repeats the greedy "
-                         "merge and emits its own slice of the superstring") if world > 1 else "single GPU",
+                         "straight into fixed sub-slots of the owner GPU's heap over NVLink (CUDA IPC peer pointers), ranks synchronise "
+                         "through device-side signal words (no collective and no host round trip on the data path), duplicates clear "
+                         "their first-occurrence bit on every rank; every rank repeats the greedy merge and emits its own slice of the "
+                         "superstring") if world > 1 else "single GPU",
             "l2": "no explicit flush: each step streams ~2.4 GB of intermediates (600 MB written by level 0, read and rewritten by "
                   "level 1, read by the resolve: >> 126 MB L2), so the 50 MB input and every kernel's operands are cold when read"}
 
 
 def run_sharded_arm(args, rank, local_rank, world, ctx, part):
     """N > 1: one hash-range sharded job over the concatenation of every rank's 50 Mbp (see the module docstring)."""
+    import hashlib
     import torch
     import torch.distributed as dist
+    import kmercamel_b200 as kb
     from kmercamel_b200 import sharded
 
     dev = torch.device("cuda", local_rank)
@@ -189,8 +193,6 @@ def run_sharded_arm(args, rank, local_rank, world, ctx, part):
     pinned = torch.from_numpy(part).pin_memory()
     full = torch.empty(world * part_len, dtype=torch.uint8, device=dev)
     own = torch.empty(part_len, dtype=torch.uint8, device=dev)
-    comm = sharded.TorchComm(dev)
-    ops = sharded.GpuOps(ctx, full)
 
     def barrier():
         dist.barrier()
@@ -200,14 +202,46 @@ def run_sharded_arm(args, rank, local_rank, world, ctx, part):
         own.copy_(pinned, non_blocking=True)
         dist.all_gather_into_tensor(full, own)
 
-    ops.setup_p2p(comm, K)
+    # set-up (not timed): every rank allocates its heap, the 64-byte IPC handles are all-gathered, the heaps are mapped
+    sharded.attach(ctx, rank, world, k=K, n_bytes_cap=full.numel(), device=dev)
 
-    def step():  # partition pass == all-to-all (peer stores over NVLink); every rank emits its own slice of the superstring
-        return sharded.sharded_compute_p2p(ops, comm, full.numel(), k=K, slice_output=True)
+    def step():  # no collective inside: peer stores over NVLink + device-side signals; every rank emits its own slice of the superstring
+        return sharded.sharded_compute(ctx, full.data_ptr(), full.numel(), k=K)
 
     load()
     for _ in range(max(args.warmup, 3)):
         r = step()
+    # ---- parity at N ranks: the concatenated slices against kc_compute_device of the same sequence on ONE GPU (rank 0) ----------
+    pad = (r.length // world + 4096 + 15) // 16 * 16
+    mine = torch.zeros(pad, dtype=torch.uint8, device=dev)
+    assert r.slice_len <= pad
+    ctx._check(ctx._lib.kc_copy_to_host(ctx._h, pinned_scratch(pad).data_ptr(), r.ms_ptr, r.slice_len))
+    mine[:r.slice_len] = pinned_scratch(pad)[:r.slice_len].to(dev)
+    allp = torch.empty(world * pad, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allp, mine)
+    meta = torch.tensor([r.slice_begin, r.slice_len], dtype=torch.int64, device=dev)
+    metas = torch.empty(world * 2, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(metas, meta)
+    parity = None
+    if rank == 0:
+        metas = metas.cpu().numpy().reshape(world, 2)
+        host = allp.cpu().numpy().reshape(world, pad)
+        h = hashlib.md5()
+        at = 0
+        tiles = True
+        for i in range(world):
+            tiles &= int(metas[i, 0]) == at
+            h.update(host[i, :int(metas[i, 1])].tobytes())
+            at += int(metas[i, 1])
+        single = kb.Context(local_rank)
+        want = single.compute_device(full.data_ptr(), full.numel(), k=K)
+        want_ms = single.copy_to_host(want.ms_ptr, want.length)
+        parity = bool(tiles and at == want.length == r.length and r.n_kmers == want.n_kmers and h.hexdigest() == hashlib.md5(want_ms).hexdigest())
+        single.close()
+        del want_ms
+    del allp, mine
+    barrier()
+
     ctx.profile_enable(True)
     ctx.profile_reset()
     sampler = ClockSampler(local_rank)
@@ -234,9 +268,9 @@ def run_sharded_arm(args, rank, local_rank, world, ctx, part):
         for _ in range(args.steps if timed else 2):
             load()
             r = step()
-            assert r.result.slice_len <= host_out.numel()
-            ctx._check(ctx._lib.kc_copy_to_host(ctx._h, host_out.data_ptr(), r.result.ms_ptr, r.result.slice_len))
-            d2h = r.result.slice_len
+            assert r.slice_len <= host_out.numel()
+            ctx._check(ctx._lib.kc_copy_to_host(ctx._h, host_out.data_ptr(), r.ms_ptr, r.slice_len))
+            d2h = r.slice_len
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
     barrier()
@@ -244,18 +278,20 @@ def run_sharded_arm(args, rank, local_rank, world, ctx, part):
     ones = int((host_out[:d2h] <= 90).sum())
     chk = torch.tensor([float(d2h), float(ones)], dtype=torch.float64, device=dev)
     dist.all_reduce(chk, op=dist.ReduceOp.SUM)
-    assert int(chk[0]) == r.result.length and int(chk[1]) == r.n_kept, (chk.tolist(), r.result.length, r.n_kept)
+    assert int(chk[0]) == r.length and int(chk[1]) == r.n_kmers, (chk.tolist(), r.length, r.n_kmers)
     clocks = sampler.stop()
+    fast_runs, fallbacks = ctx.stat("fast_runs"), ctx.stat("fast_fallbacks")
 
     t = torch.tensor([dev_ms, e2e_s * 1000.0, float(launches)], dtype=torch.float64, device=dev)
     tmax = t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     tsum = t.clone()
     dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    ctx.group_close()
     if rank != 0:
         return
     dev_ms, e2e_ms, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
-    n_kmers = r.n_kept
+    n_kmers = r.n_kmers
     value = n_kmers * args.steps / (dev_ms / 1000.0)
     e2e_value = n_kmers * args.steps / (e2e_ms / 1000.0)
     peak, peak_src = measured_peak_gbs()
@@ -266,23 +302,40 @@ def run_sharded_arm(args, rank, local_rank, world, ctx, part):
                    "gbs": (v["bytes"] / (v["ms"] / 1000.0) / 1e9) if v["ms"] > 0 and v["bytes"] else None}
                for n, v in prof.items() if v["launches"]}
     item_bytes = 12
+    sent = r.n_occurrences / world * (world - 1) / world            # items a rank stores into OTHER ranks' heaps per job
+    s0 = kernels.get("ks_scatter0", {}).get("ms_per_step")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic", "config": workload_config(world),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": part_len * world, "d2h_bytes_per_step": int(r.result.length),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": part_len * world, "d2h_bytes_per_step": int(r.length),
                 "ms_per_step": e2e_ms / args.steps,
                 "timer": "host perf_counter around H2D + all-gather + sharded job + D2H of every rank's superstring slice, max over ranks"},
         "gpu_launches": launches, "clocks": clocks,
+        "parity_n": parity,
+        "parity_n_check": "md5 of the concatenated per-rank superstring slices == md5 of kc_compute_device of the same sequence on one GPU "
+                          "(rank 0), slices tile [0, length), same k-mer count; taken after the warm-up steps",
         "roofline": {"bound": "hbm", "kernel": dname + " (rank 0)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": None, "peak_source": peak_src, "share_of_step": d["ms"] / dev_ms},
         "cpu_baseline": None, "kernel_classes_rank0": kernels,
-        "exchange": {"items_sent_rank0_per_step": r.items_sent, "items_resolved_rank0_per_step": r.items_received,
-                     "nvlink_store_bytes_rank0_per_step": r.items_sent * item_bytes,
-                     "flag_reduce_bytes": int(ops.flags.numel() * 4)},
-        "result": {"distinct_kmers": int(n_kmers), "superstring_length": int(r.result.length), "nodes": int(r.result.n_nodes)},
+        "exchange": {"items_stored_to_peers_per_rank_per_step": int(sent), "nvlink_store_bytes_per_rank_per_step": int(sent * item_bytes),
+                     "nvlink_gbs_during_level0_rank0": (sent * item_bytes / (s0 / 1000.0) / 1e9) if s0 else None,
+                     "nvlink_peak_gbs_per_direction": 900.0,
+                     "collectives_on_the_data_path": 0, "fast_runs_rank0": fast_runs, "fast_fallbacks_rank0": fallbacks},
+        "result": {"distinct_kmers": int(n_kmers), "superstring_length": int(r.length), "nodes": int(r.n_nodes)},
     }
     print(json.dumps(line), flush=True)
+
+
+_SCRATCH = {}
+
+
+def pinned_scratch(n):
+    import torch
+    if _SCRATCH.get("n", 0) < n:
+        _SCRATCH["t"] = torch.empty(n, dtype=torch.uint8).pin_memory()
+        _SCRATCH["n"] = n
+    return _SCRATCH["t"]
 
 
 def main():
@@ -309,7 +362,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # stdout carries exactly one JSON line (NCCL prints its version at VERSION/INFO)
+        # stdout carries exactly one JSON line: whatever NCCL_DEBUG level the caller asked for goes to stderr
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     records, (seq, off, ln) = make_workload(rank)

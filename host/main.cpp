@@ -70,10 +70,39 @@ static int usage() {
     std::cerr << "  -S       - assume the input are simplitigs / matchtigs / unitigs" << std::endl;
     std::cerr << "  -M FILE  - also output the masked superstring with the mask maximizing the number of ones" << std::endl;
     std::cerr << "  -z INT   - keep only k-mers with at least this many occurrences [default: 1]" << std::endl;
-    std::cerr << "  -g INT   - CUDA device ordinal [default: 0]" << std::endl;
+    std::cerr << "  -g LIST  - CUDA device ordinal(s), e.g. 0 or 0,1,2,3 or 0-7 [default: 0]; several devices shard the k-mer set" << std::endl;
+    std::cerr << "             construction of `compute` (from FASTA, without -S / -M) by hash range over NVLink" << std::endl;
+    std::cerr << "  -V       - verify: the k-mer set the output represents must equal the k-mer set of the input (digest on the GPU)" << std::endl;
     std::cerr << "  -h       - print help" << std::endl;
     std::cerr << std::endl;
     return 1;
+}
+
+// "-g 0", "-g 0,1,2", "-g 0-7", "-g 0-3,6" -> device ordinals (an ordinal may repeat: the ranks then share that GPU)
+static bool parse_devices(const std::string &arg, std::vector<int> &out) {
+    out.clear();
+    size_t at = 0;
+    while (at <= arg.size()) {
+        const size_t comma = std::min(arg.find(',', at), arg.size());
+        const std::string part = arg.substr(at, comma - at);
+        if (part.empty()) return false;
+        const size_t dash = part.find('-');
+        try {
+            if (dash == std::string::npos) {
+                out.push_back(std::stoi(part));
+            } else {
+                const int a = std::stoi(part.substr(0, dash)), b = std::stoi(part.substr(dash + 1));
+                if (b < a) return false;
+                for (int d = a; d <= b; ++d) out.push_back(d);
+            }
+        } catch (std::exception &) {
+            return false;
+        }
+        at = comma + 1;
+    }
+    for (int d : out)
+        if (d < 0) return false;
+    return !out.empty() && out.size() <= 16;
 }
 
 // Whole file (plain or gzip, "-" = stdin) into memory; zlib detects the format as in src/parser.h:88-101.
@@ -108,12 +137,13 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
         argc--;
     }
     int k = 0, device = 0;
+    std::vector<int> devices{0};
     long min_frequency = 1;
     std::string out_path, mask_path, algorithm = "greedy";
-    bool complements = true, assume_simplitigs = false, d_set = false;
+    bool complements = true, assume_simplitigs = false, d_set = false, verify = false;
     int opt;
     try {
-        while ((opt = getopt(argc, argv, lower_bound ? "k:huxSz:g:" : "k:d:a:o:huxM:Sz:g:")) != -1) {  // src/main.cpp:234,391
+        while ((opt = getopt(argc, argv, lower_bound ? "k:huxSz:g:" : "k:d:a:o:huxM:Sz:g:V")) != -1) {  // src/main.cpp:234,391
             switch (opt) {
                 case 'o': out_path = optarg; break;
                 case 'k': k = std::stoi(optarg); break;
@@ -126,7 +156,14 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
                 case 'M': mask_path = optarg; break;
                 case 'S': assume_simplitigs = true; break;
                 case 'z': min_frequency = std::stol(optarg); break;
-                case 'g': device = std::stoi(optarg); break;
+                case 'g':
+                    if (!parse_devices(optarg, devices)) {
+                        std::cerr << "-g takes CUDA device ordinals, e.g. 0 or 0,1,2,3 or 0-7." << std::endl;
+                        return usage();
+                    }
+                    device = devices[0];
+                    break;
+                case 'V': verify = true; break;
                 case 'h': usage(); return 0;
                 default: return usage();
             }
@@ -171,12 +208,21 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
     if (!lower_bound) write_log("Started computation of a masked superstring from '" + path + "'.");
     else write_log("Started computation of a masked superstring length lower bound from '" + path + "'.");  // src/main.cpp:134
     const double t_start = now_ms();
-    // the CUDA context (~1 s) is created while the file is read and framed
+    // several devices: the k-mer set construction of the from-FASTA greedy is sharded over them; every other mode runs on the first
+    const bool multi = devices.size() > 1 && !lower_bound && algorithm == "greedy" && !assume_simplitigs && mask_path.empty();
+    if (devices.size() > 1 && !multi) write_log("Note: -S, -M, streaming and lowerbound run on one GPU; using device " + std::to_string(device) + ".");
+    // the CUDA context(s) (~1 s) are created while the file is read and framed
     kc_ctx *ctx = nullptr;
+    kc_group *group = nullptr;
     int rc_init = KC_OK;
     double t_init_done = 0;
     std::thread init_thread([&] {
-        rc_init = kc_init(device, nullptr, &ctx);
+        if (multi) {
+            rc_init = kc_init_multi((int) devices.size(), devices.data(), &group);
+            if (rc_init == KC_OK) ctx = kc_group_ctx(group, 0);
+        } else {
+            rc_init = kc_init(device, nullptr, &ctx);
+        }
         t_init_done = now_ms();
     });
     struct Joiner {
@@ -215,6 +261,7 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
     uint64_t bound = 0;
     if (algorithm == "streaming") {  // src/main.cpp:139-144: header, then Streaming / StreamingFiltered
         rc = kc_streaming(ctx, &p, &in, &out);
+        (void) verify;
         if (rc != KC_OK) {
             std::cerr << "kmercamel compute -a streaming failed: " << kc_strerror(rc) << ": " << kc_last_error(ctx) << std::endl;
             kc_destroy(ctx);
@@ -233,16 +280,17 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
         if (output.is_open()) output.close();
         finish_ok();
     }
-    rc = lower_bound ? kc_lower_bound(ctx, &p, &in, &bound, &out) : kc_compute(ctx, &p, &in, &out);
+    rc = lower_bound ? kc_lower_bound(ctx, &p, &in, &bound, &out) : (multi ? kc_group_compute(group, &p, &in, &out) : kc_compute(ctx, &p, &in, &out));
     const double t_compute = now_ms();
     if (rc == KC_ERR_EMPTY && !assume_simplitigs) {  // src/main.cpp:155-158
         std::cerr << "Path '" << path << "' contains no k-mers. Make sure that your file is a FASTA or gzipped FASTA." << std::endl;
-        kc_destroy(ctx);
+        if (!multi) kc_destroy(ctx);
         return usage();
     }
     if (rc != KC_OK) {
-        std::cerr << "kmercamel " << (lower_bound ? "lowerbound" : "compute") << " failed: " << kc_strerror(rc) << ": " << kc_last_error(ctx) << std::endl;
-        kc_destroy(ctx);
+        std::cerr << "kmercamel " << (lower_bound ? "lowerbound" : "compute") << " failed: " << kc_strerror(rc) << ": "
+                  << (multi ? kc_group_last_error(group) : kc_last_error(ctx)) << std::endl;
+        if (!multi) kc_destroy(ctx);
         return 1;
     }
     if (!assume_simplitigs)
@@ -261,6 +309,27 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
     std::snprintf(times, sizeof(times), "GPU stages [ms]: extract %.3f, count %.3f, path %.3f, emit %.3f, total %.3f; %llu kernels",
                   out.t.extract_ms, out.t.count_ms, out.t.path_ms, out.t.emit_ms, out.t.total_ms, (unsigned long long) out.n_launches);
     write_log(times);
+    if (multi) write_log("k-mer set construction sharded by hash range over " + std::to_string(devices.size()) + " GPUs.");
+    bool verified_ok = true;
+    if (verify) {  // what the reference's verify.py checks: the superstring represents exactly the k-mer set of the input
+        uint64_t d_in[4], d_out[4];
+        kc_input ms_in{out.ms, out.length, nullptr, nullptr, 0};
+        kc_params pv = p;
+        pv.min_frequency = 1;
+        int rv = kc_kmer_digest(ctx, &p, &in, 0, d_in);
+        if (rv == KC_OK) rv = kc_kmer_digest(ctx, &pv, &ms_in, 1, d_out);
+        if (rv != KC_OK) {
+            std::cerr << "verification could not run: " << kc_strerror(rv) << ": " << kc_last_error(ctx) << std::endl;
+            return 1;
+        }
+        verified_ok = d_in[0] == d_out[0] && d_in[1] == d_out[1] && d_in[2] == d_out[2] && d_in[0] == out.n_kmers;
+        char vb[256];
+        std::snprintf(vb, sizeof(vb), "Verification %s: input %llu k-mers (digest %016llx %016llx), output represents %llu (digest %016llx %016llx).",
+                      verified_ok ? "passed" : "FAILED", (unsigned long long) d_in[0], (unsigned long long) d_in[1], (unsigned long long) d_in[2],
+                      (unsigned long long) d_out[0], (unsigned long long) d_out[1], (unsigned long long) d_out[2]);
+        write_log(vb);
+    }
+    const double t_verify = now_ms();
 
     std::ofstream output, mask_output;
     std::ostream *of = &std::cout;
@@ -278,9 +347,14 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
         mask_output << std::endl;  // src/global.h:206-208
     }
     if (of == &output) output.flush();
-    std::snprintf(times, sizeof(times), "Host stages [ms]: read %.1f, frame %.1f, CUDA context %.1f (in the background; waited %.1f), compute incl. H2D/D2H and arena %.1f, write %.1f",
-                  t_read - t_start, t_frame - t_read, t_init_done - t_start, t_init - t_frame, t_compute - t_init, now_ms() - t_compute);
+    std::snprintf(times, sizeof(times), "Host stages [ms]: read %.1f, frame %.1f, CUDA context %.1f (in the background; waited %.1f), compute incl. H2D/D2H and arena %.1f, verify %.1f, write %.1f, total %.1f",
+                  t_read - t_start, t_frame - t_read, t_init_done - t_start, t_init - t_frame, t_compute - t_init, t_verify - t_compute, now_ms() - t_verify, now_ms() - t_start);
     write_log(times);
+    if (!verified_ok) {
+        std::cout.flush();
+        std::fflush(nullptr);
+        _exit(2);
+    }
     if (output.is_open()) output.close();
     if (mask_output.is_open()) mask_output.close();
     finish_ok();

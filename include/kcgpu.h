@@ -165,33 +165,46 @@ int kc_overlap_path(kc_ctx *ctx, const uint64_t *first, const uint64_t *last, ui
 int kc_frame_fasta(const uint8_t *data, uint64_t n, uint8_t **seq, uint64_t *n_bytes, uint64_t **rec_off,
                    uint64_t **rec_len, uint64_t *n_recs);
 
-/* ---- multi-GPU: hash-range sharded k-mer set construction ------------------------------------------------------------
- * The reference is single-process; this is the north star's "counting shards by hash range, all-to-all over NVLink,
- * greedy merge on one GPU".  The library does the per-GPU halves, the caller (kmercamel_b200/sharded.py, over
- * torch.distributed / NCCL) does the exchange.  All pointers are DEVICE pointers unless noted; the whole framed
- * sequence is resident on every GPU.  From-FASTA regime only (no -S, no -M).
+/* ---- multi-GPU: hash-range sharded k-mer set construction ----------------------------------------------------
+ * The reference is single-threaded; this is the north star's "k-mer counting shards by hash range across the GPUs of one box,
+ * the greedy merge on one GPU".  Every rank owns a heap in its HBM that all other ranks address directly (peer pointers over
+ * NVLink / NVSwitch); the level-0 partition pass stores each (k-mer, position) item straight into the heap of the GPU that owns
+ * the k-mer's hash range, and ranks synchronise through device-side signal words — no collective library and no host round trip
+ * on the data path (kmercamel_b200/csrc/group.cuh).  From-FASTA regime only (no -S, no -M); results are identical to kc_compute.
  *
- *   kc_shard_partition   k-mers of the windows ENDING in [pos_begin, pos_end) (multiples of kc_shard_granule(k), or
- *                        n_bytes), as scrambled words + global positions, grouped by the top 8 bits of the scrambled
- *                        word; digit_counts[256] (host) says how many fell into each group.  Owner of group g among
- *                        G ranks: g * G / 256, so the items of one owner are contiguous.
- *   kc_shard_resolve     all occurrences of this rank's groups (gathered by the caller) -> sets the bit of the FIRST
- *                        occurrence of every k-mer with >= min_frequency occurrences in flags_dev (a zeroed bit array
- *                        over all n_bytes positions, (n_bytes + 31) / 32 + 1 words); keys_dev / pos_dev are clobbered.
- *   kc_compute_from_flags  the flags of all ranks OR-ed together (their bits are disjoint, so a SUM reduce is an OR) ->
- *                        first-occurrence runs -> overlap levels -> superstring, as kc_compute_device. */
-uint64_t kc_shard_granule(int k);
-int kc_shard_partition(kc_ctx *ctx, const kc_params *p, const uint8_t *seq_dev, uint64_t n_bytes, uint64_t pos_begin, uint64_t pos_end,
-                       void *keys_dev_out, uint32_t *pos_dev_out, uint64_t *digit_counts, uint64_t *n_items);
-int kc_shard_resolve(kc_ctx *ctx, const kc_params *p, void *keys_dev, uint32_t *pos_dev, uint64_t n_items, uint32_t *flags_dev,
-                     uint64_t *n_kept);
-int kc_compute_from_flags(kc_ctx *ctx, const kc_params *p, const kc_input *in, const uint32_t *flags_dev, uint64_t n_kept, kc_output *out);
-/* Same, but only slice `slice_index` of `n_slices` of the superstring is written: out->ms holds bytes [*slice_begin, *slice_begin +
- * *slice_len) of it (boundaries are multiples of 16, the slices of indices 0..n_slices-1 tile the whole string), out->length is the
- * length of the WHOLE superstring.  With the flags all-reduced, every rank runs the (deterministic) greedy stage and emits and
- * copies back only its own slice, so the device-to-host copy of the result is spread over all the GPUs' links. */
-int kc_compute_from_flags_slice(kc_ctx *ctx, const kc_params *p, const kc_input *in, const uint32_t *flags_dev, uint64_t n_kept,
-                                uint32_t slice_index, uint32_t n_slices, kc_output *out, uint64_t *slice_begin, uint64_t *slice_len);
+ * (1) One process, one host thread per GPU — what §8(b) calls kc_init(n_gpus, device_ids):
+ *       kc_init_multi     contexts on the given devices (an ordinal may repeat: several ranks then share a GPU, which is how the
+ *                         single-GPU test box exercises the protocol), peer access enabled between them
+ *       kc_group_compute  as kc_compute with HOST buffers: every rank copies in 1 / n of the sequence over its own PCIe link and
+ *                         hands it to its peers over NVLink, all ranks build the k-mer set together, every rank repeats the
+ *                         (deterministic) greedy stage and emits + copies back its own slice of the superstring into one pinned
+ *                         buffer (valid until the next call on the group)
+ *       kc_group_ctx      the context of a rank, for kc_set_option / kc_get_stat / kc_profile_* (options must be set on every rank)
+ * (2) One process per GPU (torchrun; bench.py, tests): a context from kc_init becomes rank `rank` of `n_ranks`
+ *       kc_group_alloc    allocates the rank's heap for inputs of up to n_bytes_cap bytes at word width of k and returns its
+ *                         64-byte CUDA IPC handle; the caller all-gathers the handles (any transport: this is set-up, not data path)
+ *       kc_group_open     all_handles: n_ranks * 64 bytes in rank order
+ *       kc_group_compute_device   one job; in->seq = DEVICE pointer to the whole framed sequence, resident on this GPU.  Every rank
+ *                         must make the same call.  out->ms = DEVICE pointer to bytes [*slice_begin, *slice_begin + *slice_len) of
+ *                         the superstring (slices are 16-byte aligned and tile the string), out->length = its whole length.
+ *       kc_group_close    releases the heap (all ranks must have finished their last job)
+ *     kc_group_plan       host only, no GPU: plan[0] = fixed-slot path applies, [1], [2] = the rank's slice of window END positions,
+ *                         [3], [4] = its range of level-0 digits (hash range), [5] = level-0 digits, [6] = items per (digit, sender)
+ *                         sub-slot, [7] = heap bytes per rank. */
+typedef struct kc_group kc_group;
+int kc_init_multi(int n_gpus, const int *device_ids, kc_group **out);
+void kc_group_destroy(kc_group *g);
+int kc_group_size(const kc_group *g);
+kc_ctx *kc_group_ctx(kc_group *g, int rank);
+int kc_group_compute(kc_group *g, const kc_params *p, const kc_input *in, kc_output *out);
+const char *kc_group_last_error(const kc_group *g);
+
+uint64_t kc_shard_granule(int k);  /* window positions per level-0 tile: slices are multiples of it */
+int kc_group_alloc(kc_ctx *ctx, int n_ranks, int rank, int k, uint64_t n_bytes_cap, uint8_t *handle_out);
+int kc_group_open(kc_ctx *ctx, const uint8_t *all_handles);
+int kc_group_compute_device(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *out, uint64_t *slice_begin, uint64_t *slice_len);
+int kc_group_close(kc_ctx *ctx);
+int kc_group_plan(int n_ranks, int rank, int k, uint64_t n_bytes, uint64_t *plan);
 
 /* Per-kernel-class device timing for roofline reports.  Enable, run kc_compute*, then read the table:
  * names[i], milliseconds, launches, algorithmic bytes (read once + written once). */
@@ -199,23 +212,6 @@ int kc_profile_enable(kc_ctx *ctx, int on);
 int kc_profile_count(void);
 int kc_profile_get(kc_ctx *ctx, int i, const char **name, double *ms, uint64_t *launches, uint64_t *bytes);
 int kc_profile_reset(kc_ctx *ctx);
-
-/* Fused partition + exchange (the product multi-GPU path): the level-0 scatter pass stores every item straight into the
- * receive buffer of its owner GPU through peer pointers (CUDA IPC, NVLink), so the partition pass IS the all-to-all and
- * the owner finds complete, contiguous level-0 buckets.  Sequence of calls per rank:
- *   once:      kc_p2p_alloc (receive buffers of capacity_items items; returns two 64-byte IPC handles = 128 bytes)
- *              -> all-gather the handles -> kc_p2p_open (all_handles: n_ranks * 128 bytes, rank order)
- *   per job:   kc_p2p_hist (256 digit counts of the slice, host) -> all-gather the counts ->
- *              kc_p2p_scatter (all_counts[n_ranks][256], host) -> barrier across ranks ->
- *              kc_p2p_resolve (flags as kc_shard_resolve) -> reduce flags -> kc_compute_from_flags on rank 0.
- * A barrier is also needed before the NEXT kc_p2p_scatter (peers must be done resolving). */
-int kc_p2p_alloc(kc_ctx *ctx, int k, uint64_t capacity_items, uint8_t *handles_out);
-int kc_p2p_open(kc_ctx *ctx, int n_ranks, int rank, const uint8_t *all_handles);
-int kc_p2p_hist(kc_ctx *ctx, const kc_params *p, const uint8_t *seq_dev, uint64_t n_bytes, uint64_t pos_begin, uint64_t pos_end,
-                uint64_t *digit_counts);
-int kc_p2p_scatter(kc_ctx *ctx, const kc_params *p, const uint8_t *seq_dev, uint64_t n_bytes, uint64_t pos_begin, uint64_t pos_end,
-                   const uint64_t *all_counts);
-int kc_p2p_resolve(kc_ctx *ctx, const kc_params *p, const uint64_t *all_counts, uint32_t *flags_dev, uint64_t *n_kept, uint64_t *n_owned);
 
 /* CUDA kernels launched through this context since kc_init (every entry point adds its own). */
 uint64_t kc_total_launches(const kc_ctx *ctx);
@@ -226,18 +222,10 @@ uint64_t kc_total_launches(const kc_ctx *ctx);
  * "fast_leaf_target", "fast_sigmas", "fast_min_items": its plan parameters, exposed so that tests reach the
  * multi-level plan and the overflow fallback with small inputs; "fast_heuristics" (default 1): skip the attempt when
  * duplicates are expected (-z > 1, or the previous call on an input of similar size overflowed).
- * Kernel variants of that construction, kept selectable so that every measurement in profiles/ can be repeated
- * (profiles/variant_sweep.py; defaults = the fastest measured):
- *   "fast_resolve"      0 bucket-list resolve of the exact path, 1 two-barrier leaf resolve (set-the-winners flags),
- *                       2 the same with clear-the-losers flags, 3 / 4 / 5 one-barrier resolve with 2 / 3 / 4 staging buffers,
- *                       6 / 7 one-barrier resolve with a thread's items staged in registers (256 / 512 threads);
- *   "fast_tile_variant" level >= 1 scatter: 0 / 1 / 2 plain with full / half / three-quarter tiles, 3 / 4 next tile streaming
- *                       in through cp.async with full / half tiles, 5 as 3 with 512-thread CTAs;
- *   "fast_max_ctas"     upper bound of that scatter's grid (0 = 148 * 8);  "fast_split0": two threads per level-0 strip.
+ * "fast_max_ctas": upper bound of the level >= 1 scatter grid.
  * Results never depend on these options. */
 int kc_set_option(kc_ctx *ctx, const char *name, int value);
-/* Counters since kc_init: "fast_runs", "fast_fallbacks", "total_launches"; current value of the options "fast_resolve",
- * "fast_tile_variant", "fast_max_ctas". */
+/* Counters since kc_init: "fast_runs", "fast_fallbacks", "total_launches"; current value of the option "fast_max_ctas". */
 int kc_get_stat(const kc_ctx *ctx, const char *name, uint64_t *value);
 
 int kc_limbs_for_k(int k);

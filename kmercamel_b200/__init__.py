@@ -3,8 +3,8 @@
 The product is the C-ABI library csrc/libkcgpu.so (CUDA, sm_100a) plus the `kmercamel` CLI in host/.
 This package is only the ctypes binding used by tests and bench.py; it never falls back to a CPU path.
 """
-from .api import (Context, ComputeResult, KcError, frame_fasta, frame_fasta_file, limbs_for_k, lib_path,
+from .api import (Context, ComputeResult, Group, KcError, frame_fasta, frame_fasta_file, group_plan, limbs_for_k, lib_path,
                   load_library)
 
-__all__ = ["Context", "ComputeResult", "KcError", "frame_fasta", "frame_fasta_file", "limbs_for_k", "lib_path",
+__all__ = ["Context", "ComputeResult", "Group", "KcError", "frame_fasta", "frame_fasta_file", "group_plan", "limbs_for_k", "lib_path",
            "load_library"]

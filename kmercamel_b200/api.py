@@ -86,18 +86,20 @@ def load_library():
     L.kc_frame_fasta.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(u8p), u64p, C.POINTER(u64p), C.POINTER(u64p), u64p]
     L.kc_shard_granule.argtypes = [C.c_int]
     L.kc_shard_granule.restype = C.c_uint64
-    L.kc_shard_partition.argtypes = [C.c_void_p, C.POINTER(kc_params), C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
-                                     C.c_void_p, u64p, u64p]
-    L.kc_shard_resolve.argtypes = [C.c_void_p, C.POINTER(kc_params), C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, u64p]
-    L.kc_compute_from_flags.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.c_void_p, C.c_uint64,
-                                        C.POINTER(kc_output)]
-    L.kc_compute_from_flags_slice.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.c_void_p, C.c_uint64, C.c_uint32,
-                                              C.c_uint32, C.POINTER(kc_output), u64p, u64p]
-    L.kc_p2p_alloc.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]
-    L.kc_p2p_open.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
-    L.kc_p2p_hist.argtypes = [C.c_void_p, C.POINTER(kc_params), C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, u64p]
-    L.kc_p2p_scatter.argtypes = [C.c_void_p, C.POINTER(kc_params), C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, u64p]
-    L.kc_p2p_resolve.argtypes = [C.c_void_p, C.POINTER(kc_params), u64p, C.c_void_p, u64p, u64p]
+    L.kc_init_multi.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+    L.kc_group_destroy.argtypes = [C.c_void_p]
+    L.kc_group_destroy.restype = None
+    L.kc_group_size.argtypes = [C.c_void_p]
+    L.kc_group_ctx.argtypes = [C.c_void_p, C.c_int]
+    L.kc_group_ctx.restype = C.c_void_p
+    L.kc_group_compute.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.POINTER(kc_output)]
+    L.kc_group_last_error.argtypes = [C.c_void_p]
+    L.kc_group_last_error.restype = C.c_char_p
+    L.kc_group_alloc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p]
+    L.kc_group_open.argtypes = [C.c_void_p, C.c_void_p]
+    L.kc_group_compute_device.argtypes = [C.c_void_p, C.POINTER(kc_params), C.POINTER(kc_input), C.POINTER(kc_output), u64p, u64p]
+    L.kc_group_close.argtypes = [C.c_void_p]
+    L.kc_group_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, u64p]
     L.kc_total_launches.argtypes = [C.c_void_p]
     L.kc_total_launches.restype = C.c_uint64
     L.kc_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
@@ -118,8 +120,10 @@ def load_library():
     return L
 
 
-EXPORTED_SYMBOLS = ["kc_kmer_digest", "kc_partial_presort", "kc_init", "kc_destroy", "kc_compute", "kc_compute_device", "kc_lower_bound", "kc_copy_to_host", "kc_count_kmers", "kc_overlap_path",
-                    "kc_p2p_alloc", "kc_p2p_open", "kc_p2p_hist", "kc_p2p_scatter", "kc_p2p_resolve", "kc_total_launches", "kc_shard_granule", "kc_shard_partition", "kc_shard_resolve", "kc_compute_from_flags", "kc_compute_from_flags_slice",
+EXPORTED_SYMBOLS = ["kc_kmer_digest", "kc_partial_presort", "kc_init", "kc_destroy", "kc_compute", "kc_compute_device", "kc_lower_bound",
+                    "kc_copy_to_host", "kc_count_kmers", "kc_overlap_path", "kc_total_launches", "kc_shard_granule",
+                    "kc_init_multi", "kc_group_destroy", "kc_group_size", "kc_group_ctx", "kc_group_compute", "kc_group_last_error",
+                    "kc_group_alloc", "kc_group_open", "kc_group_compute_device", "kc_group_close", "kc_group_plan",
                     "kc_streaming", "kc_maskopt", "kc_split_ms", "kc_join_ms", "kc_ms_to_spss", "kc_spss_to_ms", "kc_fasta_first_header",
                     "kc_frame_fasta", "kc_set_option", "kc_get_stat", "kc_profile_enable", "kc_profile_count", "kc_profile_get", "kc_profile_reset",
                     "kc_limbs_for_k", "kc_free", "kc_strerror", "kc_last_error"]
@@ -380,71 +384,31 @@ class Context:
                                               ov.ctypes.data_as(u8p)))
         return ef, ov
 
-    # ---- multi-GPU halves (device pointers; the exchange is the caller's, see sharded.py) ---------------------------
-    def shard_partition(self, seq_ptr: int, n_bytes: int, pos_begin: int, pos_end: int, keys_out_ptr: int, pos_out_ptr: int, *, k,
-                        complements=True):
-        """-> (digit_counts[256] int64, n_items)"""
-        p = self._params(k, complements, 1, False, False)
-        counts = np.zeros(256, dtype=np.uint64)
-        n = C.c_uint64()
-        self._check(self._lib.kc_shard_partition(self._h, C.byref(p), C.c_void_p(seq_ptr), n_bytes, pos_begin, pos_end,
-                                                 C.c_void_p(keys_out_ptr or None), C.c_void_p(pos_out_ptr or None),
-                                                 counts.ctypes.data_as(u64p), C.byref(n)))
-        return counts.astype(np.int64), n.value
+    # ---- multi-GPU: this context as one rank of a group of processes (include/kcgpu.h "multi-GPU", form 2) ---------------
+    def group_alloc(self, n_ranks: int, rank: int, k: int, n_bytes_cap: int) -> np.ndarray:
+        """Allocate this rank's heap; -> its 64-byte CUDA IPC handle (to be all-gathered by the caller)."""
+        h = np.zeros(64, dtype=np.uint8)
+        self._check(self._lib.kc_group_alloc(self._h, n_ranks, rank, int(k), int(n_bytes_cap), h.ctypes.data))
+        return h
 
-    def shard_resolve(self, keys_ptr: int, pos_ptr: int, n_items: int, flags_ptr: int, *, k, complements=True, min_frequency=1) -> int:
+    def group_open(self, all_handles: np.ndarray):
+        all_handles = np.ascontiguousarray(all_handles, dtype=np.uint8)
+        self._check(self._lib.kc_group_open(self._h, all_handles.ctypes.data))
+
+    def group_compute_device(self, seq_ptr: int, n_bytes: int, *, k, complements=True, min_frequency=1) -> ComputeResult:
+        """One sharded job (every rank makes the same call); ms_ptr holds bytes [slice_begin, slice_begin + slice_len) of the
+        superstring on this rank's GPU, length is the whole superstring's."""
         p = self._params(k, complements, min_frequency, False, False)
-        kept = C.c_uint64()
-        self._check(self._lib.kc_shard_resolve(self._h, C.byref(p), C.c_void_p(keys_ptr or None), C.c_void_p(pos_ptr or None), n_items,
-                                               C.c_void_p(flags_ptr), C.byref(kept)))
-        return kept.value
-
-    def compute_from_flags(self, seq_ptr: int, n_bytes: int, flags_ptr: int, n_kept: int, *, k, complements=True, slice=None) -> ComputeResult:
-        """slice = (index, count): emit only that slice of the superstring (kc_compute_from_flags_slice)."""
-        p = self._params(k, complements, 1, False, False)
         inp = kc_input(seq_ptr, n_bytes, None, None, 0)
         out = kc_output()
-        if slice is None:
-            self._check(self._lib.kc_compute_from_flags(self._h, C.byref(p), C.byref(inp), C.c_void_p(flags_ptr), n_kept, C.byref(out)))
-            r = self._result(out, False)
-            r.slice_len = r.length
-            return r
         sb, sl = C.c_uint64(), C.c_uint64()
-        self._check(self._lib.kc_compute_from_flags_slice(self._h, C.byref(p), C.byref(inp), C.c_void_p(flags_ptr), n_kept, int(slice[0]),
-                                                          int(slice[1]), C.byref(out), C.byref(sb), C.byref(sl)))
+        self._check(self._lib.kc_group_compute_device(self._h, C.byref(p), C.byref(inp), C.byref(out), C.byref(sb), C.byref(sl)))
         r = self._result(out, False)
         r.slice_begin, r.slice_len = sb.value, sl.value
         return r
 
-    # ---- fused partition + exchange over peer memory (see include/kcgpu.h kc_p2p_*) ------------------------------------
-    def p2p_alloc(self, k: int, capacity_items: int) -> np.ndarray:
-        h = np.zeros(128, dtype=np.uint8)
-        self._check(self._lib.kc_p2p_alloc(self._h, k, capacity_items, h.ctypes.data))
-        return h
-
-    def p2p_open(self, n_ranks: int, rank: int, all_handles: np.ndarray):
-        all_handles = np.ascontiguousarray(all_handles, dtype=np.uint8)
-        assert all_handles.size == n_ranks * 128
-        self._check(self._lib.kc_p2p_open(self._h, n_ranks, rank, all_handles.ctypes.data))
-
-    def p2p_hist(self, seq_ptr: int, n_bytes: int, pos_begin: int, pos_end: int, *, k, complements=True) -> np.ndarray:
-        p = self._params(k, complements, 1, False, False)
-        counts = np.zeros(256, dtype=np.uint64)
-        self._check(self._lib.kc_p2p_hist(self._h, C.byref(p), C.c_void_p(seq_ptr), n_bytes, pos_begin, pos_end, counts.ctypes.data_as(u64p)))
-        return counts.astype(np.int64)
-
-    def p2p_scatter(self, seq_ptr: int, n_bytes: int, pos_begin: int, pos_end: int, all_counts: np.ndarray, *, k, complements=True):
-        p = self._params(k, complements, 1, False, False)
-        ac = np.ascontiguousarray(all_counts, dtype=np.uint64)
-        self._check(self._lib.kc_p2p_scatter(self._h, C.byref(p), C.c_void_p(seq_ptr), n_bytes, pos_begin, pos_end, ac.ctypes.data_as(u64p)))
-
-    def p2p_resolve(self, all_counts: np.ndarray, flags_ptr: int, *, k, complements=True, min_frequency=1):
-        """-> (kept distinct k-mers of this rank's hash range, items resolved)"""
-        p = self._params(k, complements, min_frequency, False, False)
-        ac = np.ascontiguousarray(all_counts, dtype=np.uint64)
-        kept, owned = C.c_uint64(), C.c_uint64()
-        self._check(self._lib.kc_p2p_resolve(self._h, C.byref(p), ac.ctypes.data_as(u64p), C.c_void_p(flags_ptr), C.byref(kept), C.byref(owned)))
-        return kept.value, owned.value
+    def group_close(self):
+        self._lib.kc_group_close(self._h)
 
     def total_launches(self) -> int:
         return int(self._lib.kc_total_launches(self._h))
@@ -471,3 +435,74 @@ class Context:
             self._lib.kc_profile_get(self._h, i, C.byref(name), C.byref(ms), C.byref(n), C.byref(b))
             out[name.value.decode()] = dict(ms=ms.value, launches=n.value, bytes=b.value)
         return out
+
+
+def group_plan(n_ranks: int, rank: int, k: int, n_bytes: int) -> dict:
+    """Host-only geometry of a sharded job (kc_group_plan): no GPU needed."""
+    pl = (C.c_uint64 * 8)()
+    rc = load_library().kc_group_plan(n_ranks, rank, int(k), int(n_bytes), pl)
+    if rc != 0:
+        raise KcError(rc)
+    return dict(fixed_slots=bool(pl[0]), pos_begin=int(pl[1]), pos_end=int(pl[2]), digit_begin=int(pl[3]), digit_end=int(pl[4]),
+                n_digits=int(pl[5]), cap_sub=int(pl[6]), heap_bytes=int(pl[7]))
+
+
+class _RankView(Context):
+    """A rank's context inside a Group: owned by the group, never destroyed on its own."""
+
+    def __init__(self, lib, handle):
+        self._lib = lib
+        self._h = C.c_void_p(handle)
+        self.stream_handle = None
+
+    def close(self):
+        self._h = C.c_void_p()
+
+
+class Group:
+    """Several GPUs driven from ONE process (kc_init_multi / kc_group_compute): what `kmercamel compute -g 0,1,...` uses.
+    A device ordinal may repeat — the ranks then share a GPU, which exercises the whole peer protocol on a one-GPU box."""
+
+    def __init__(self, device_ids):
+        self._lib = load_library()
+        self._g = C.c_void_p()
+        ids = (C.c_int * len(device_ids))(*[int(d) for d in device_ids])
+        rc = self._lib.kc_init_multi(len(device_ids), ids, C.byref(self._g))
+        if rc != 0:
+            raise KcError(rc, "kc_init_multi")
+        self.n = len(device_ids)
+
+    def rank(self, r: int) -> Context:
+        return _RankView(self._lib, self._lib.kc_group_ctx(self._g, r))
+
+    def set_option(self, name: str, value: int):
+        for r in range(self.n):
+            self.rank(r).set_option(name, value)
+
+    def stat(self, name: str):
+        return [self.rank(r).stat(name) for r in range(self.n)]
+
+    def compute(self, seq, *, k, complements=True, min_frequency=1, copy=True) -> ComputeResult:
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        p = Context._params(k, complements, min_frequency, False, False)
+        inp = kc_input(seq.ctypes.data, seq.size, None, None, 0)
+        out = kc_output()
+        rc = self._lib.kc_group_compute(self._g, C.byref(p), C.byref(inp), C.byref(out))
+        if rc != 0:
+            raise KcError(rc, self._lib.kc_group_last_error(self._g).decode())
+        t = out.t
+        times = dict(extract=t.extract_ms, count=t.count_ms, path=t.path_ms, emit=t.emit_ms, total=t.total_ms)
+        ms = C.string_at(out.ms, out.length) if copy else None
+        return ComputeResult(ms, None, out.length, out.n_kmers, out.n_occurrences, out.n_nodes, out.n_launches, out.n_simplitigs, times,
+                             out.ms or 0, 0, 0, out.length)
+
+    def close(self):
+        if self._g:
+            self._lib.kc_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

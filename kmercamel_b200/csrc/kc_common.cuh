@@ -41,6 +41,8 @@ struct KcError {
     } while (0)
 
 static const u32 KC_NONE = 0xFFFFFFFFu;
+static const int KC_MAX_PEERS = 16;    // GPUs of one group (multi-GPU construction, group.cuh)
+static const int KC_MAX_DEVICES = 64;
 
 KC_HD u64 kc_div_up(u64 a, u64 b) { return (a + b - 1) / b; }
 KC_HD u64 kc_align_up(u64 a, u64 b) { return (a + b - 1) / b * b; }
@@ -48,6 +50,31 @@ inline int kc_ceil_log2(u64 x) {
     int r = 0;
     while ((1ULL << r) < x) ++r;
     return r;
+}
+
+// Function attributes (the > 48 KB dynamic shared memory opt-in) and occupancy figures belong to a DEVICE, not to the process:
+// a call site keeps one static KcDevOnce and runs its set-up once per device.  The lock also covers two host threads that
+// drive the same device (virtual ranks of a group in the tests).
+#include <mutex>
+struct KcDevOnce {
+    std::mutex m;
+    bool done[KC_MAX_DEVICES] = {};
+    template <class F> int run(F f) {  // -> current device
+        int d = 0;
+        KC_CUDA(cudaGetDevice(&d));
+        if (d < 0 || d >= KC_MAX_DEVICES) KC_THROW(KC_ERR_ARG, "device ordinal out of range");
+        std::lock_guard<std::mutex> g(m);
+        if (!done[d]) {
+            f(d);
+            done[d] = true;
+        }
+        return d;
+    }
+};
+inline int kc_sm_count(int dev) {
+    static int n[KC_MAX_DEVICES] = {};
+    if (!n[dev]) KC_CUDA(cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev));
+    return n[dev];
 }
 
 // Bump allocator over one device (or, in the host-emulation test build, host) slab.  All temporaries of a

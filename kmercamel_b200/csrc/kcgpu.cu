@@ -5,6 +5,7 @@
 #include "emit.cuh"
 #include "engine.cuh"
 #include "exec.cuh"
+#include "group.cuh"
 #include "kmerset.cuh"
 #include "kmerset_fast.cuh"
 #include "kword.cuh"
@@ -14,8 +15,11 @@
 #include "stage1.cuh"
 
 #include <chrono>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
+#include <vector>
 
 static double kc_now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -25,8 +29,6 @@ static const bool kc_trace = std::getenv("KC_TRACE") != nullptr;
     do {                                                                                    \
         if (kc_trace) std::fprintf(stderr, "[kc_trace] %-28s %.3f ms\n", (label), kc_now_ms()); \
     } while (0)
-
-static const int KC_MAX_PEERS = 16;
 
 struct kc_ctx {
     int device = 0;
@@ -53,21 +55,7 @@ struct kc_ctx {
     bool fast_heuristics = true;  // skip the fixed-slot attempt when duplicates are expected (see run_stage1_runs)
     u64 fast_overflow_bytes = 0;  // input size of the last call whose fixed-slot attempt overflowed (0 = none)
     u64 total_launches = 0;  // kernels launched through this context since kc_init
-    // fused partition + exchange over peer memory (kc_p2p_*)
-    struct P2P {
-        int n_ranks = 0, rank = 0, limbs = 0;
-        u64 capacity = 0;                 // items per receive buffer
-        void *recv_k = nullptr;           // own receive buffers (cudaMalloc, exported through CUDA IPC)
-        u32 *recv_p = nullptr;
-        void *peer_k[KC_MAX_PEERS] = {};  // every rank's receive buffers as seen from this process
-        u32 *peer_p[KC_MAX_PEERS] = {};
-        bool opened[KC_MAX_PEERS] = {};
-        u16 *tile_hist = nullptr;         // kept between kc_p2p_hist and kc_p2p_scatter
-        size_t tile_hist_cap = 0;
-        void **dst_k = nullptr;           // device tables of 256 destination pointers
-        u32 **dst_p = nullptr;
-        u64 n_items = 0;                  // items of this rank's slice (from kc_p2p_hist)
-    } p2p;
+    KcGroup grp;             // multi-GPU: this context as one rank of a group (group.cuh)
     bool arena_limited = false;
     std::string last_error;
 };
@@ -269,9 +257,17 @@ u64 run_stage1_runs(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_para
     return n_kept;
 }
 
+// First-occurrence flags that were built outside run_pipeline (multi-GPU construction, group.cuh).
+struct ExtFlags {
+    const u32 *flags = nullptr;
+    u64 kept = 0, n_occ = 0;   // totals, when they are known on the host already (exact path)
+    u64 *cells4 = nullptr;     // fast path: device words {kept, 0, M, status}, read back together with the run count
+    bool aborted = false;      // out: the status word was set (a slot overflowed somewhere): nothing was done
+};
+
 template <int L>
-void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, DevResult &res, const u32 *ext_flags = nullptr,
-                  u64 ext_kept = 0, bool lower_bound = false, u32 slice_index = 0, u32 n_slices = 1) {
+void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, DevResult &res, ExtFlags *ext = nullptr,
+                  bool lower_bound = false, u32 slice_index = 0, u32 n_slices = 1) {
     const bool complements = p.complements != 0;
     KWord<L> *uniq = nullptr;
     u8 *cnt = nullptr;
@@ -287,17 +283,26 @@ void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params
     ns.rec_len = in.rec_len;
     u64 n_nodes = 0;
     const u64 *node_off = in.rec_off, *node_len = in.rec_len;
-    if (in.chunks && (p.assume_simplitigs || ext_flags)) in.chunks->wait_all(ex.stream);
+    if (in.chunks && (p.assume_simplitigs || ext)) in.chunks->wait_all(ex.stream);
     if (!p.assume_simplitigs) {
         RunNodes runs;
-        if (ext_flags) {  // sharded construction: the first-occurrence flags were reduced onto this GPU by the caller
-            KC_CUDA(cudaEventRecord(ctx->ev[0], ex.stream));
-            KC_CUDA(cudaEventRecord(ctx->ev[1], ex.stream));
+        if (ext && ext->cells4) {  // multi-GPU fast path: totals and status arrive with the run count, in ONE read-back
+            u64 hc[4];
+            runs = kc_runs_from_flags(ex, ext->flags, in.n_bytes, p.k, ext->cells4, hc, 4, &ext->aborted);
+            if (ext->aborted) {
+                ext->kept = hc[3];  // the status word, for the caller's diagnosis
+                return;
+            }
+            U = hc[2] ? hc[0] : 0;
+            n_occ = hc[2];
+            KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
+        } else if (ext) {          // multi-GPU exact path
             u64 *cells = ex.arena->alloc_top<u64>(2);
             ex.fill_bytes(cells, 0, 16);
             u64 host_cells[2];
-            runs = kc_runs_from_flags(ex, ext_flags, in.n_bytes, p.k, cells, host_cells);
-            U = runs.n_runs ? ext_kept : 0;
+            runs = kc_runs_from_flags(ex, ext->flags, in.n_bytes, p.k, cells, host_cells);
+            U = runs.n_runs ? ext->kept : 0;
+            n_occ = ext->n_occ;
             KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
         } else {
             U = run_stage1_runs<L>(ctx, ex, in, p, &runs, &uniq, &n_occ);
@@ -389,9 +394,9 @@ void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params
 }
 
 void dispatch_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, DevResult &res, bool lower_bound = false) {
-    if (p.k < 32) run_pipeline<1>(ctx, ex, in, p, res, nullptr, 0, lower_bound);
-    else if (p.k < 64) run_pipeline<2>(ctx, ex, in, p, res, nullptr, 0, lower_bound);
-    else run_pipeline<4>(ctx, ex, in, p, res, nullptr, 0, lower_bound);
+    if (p.k < 32) run_pipeline<1>(ctx, ex, in, p, res, nullptr, lower_bound);
+    else if (p.k < 64) run_pipeline<2>(ctx, ex, in, p, res, nullptr, lower_bound);
+    else run_pipeline<4>(ctx, ex, in, p, res, nullptr, lower_bound);
 }
 
 void fill_times(kc_ctx *ctx, kc_output *out) {
@@ -497,6 +502,124 @@ void overlap_only(kc_ctx *ctx, CudaExec &ex, const uint64_t *first, const uint64
     for (u32 i = 0; i < nv.N; ++i) edge_from[i] = ef[i] == KC_NONE ? -1 : (int64_t) ef[i];
 }
 
+// ---- multi-GPU: one context = one rank of a group (group.cuh) ---------------------------------------------------------------------
+void group_alloc_common(kc_ctx *ctx, int n_ranks, int rank, int k, uint64_t n_bytes_cap, bool with_seq) {
+    if (n_ranks < 1 || n_ranks > KC_MAX_PEERS || rank < 0 || rank >= n_ranks) KC_THROW(KC_ERR_ARG, "bad rank / group size");
+    if (k < 1 || k > 127) KC_THROW(KC_ERR_ARG, "k must be in 1..127");
+    if (n_bytes_cap >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 sequence bytes");
+    KcGroup &G = ctx->grp;
+    if (G.heap) KC_THROW(KC_ERR_ARG, "this context already belongs to a group");
+    KC_CUDA(cudaSetDevice(ctx->device));
+    G.n = n_ranks;
+    G.rank = rank;
+    G.lay = kc_grp_layout(n_bytes_cap, kc_limbs_for_k(k), n_ranks, with_seq, kc_shard_granule(k), ctx->fast);
+    KC_CUDA(cudaMalloc(reinterpret_cast<void **>(&G.heap), G.lay.total));
+    KC_CUDA(cudaMemset(G.heap, 0, G.lay.off_flags));  // sync words, cells, counts
+    KC_CUDA(cudaMalloc(reinterpret_cast<void **>(&G.cnt0), 256 * 4));
+    KC_CUDA(cudaMalloc(reinterpret_cast<void **>(&G.cells_local), 64));
+    KC_CUDA(cudaMalloc(reinterpret_cast<void **>(&G.dst_k), 256 * sizeof(void *)));
+    KC_CUDA(cudaMalloc(reinterpret_cast<void **>(&G.dst_p), 256 * sizeof(void *)));
+    KC_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&G.h_dst), 512 * sizeof(void *), cudaHostAllocDefault));
+    KC_CUDA(cudaDeviceSynchronize());
+    for (int r = 0; r < KC_MAX_PEERS; ++r) G.peer[r] = nullptr;
+    G.peer[rank] = G.heap;
+    G.seq = 0;
+    G.done_pending = false;
+    G.failed = false;
+    G.tab_n_bytes = ~0ull;
+    if (const char *e = std::getenv("KC_GROUP_TIMEOUT_MS")) G.timeout_ns = (u64) std::atoll(e) * 1000000ull;
+}
+
+void group_detach(kc_ctx *ctx) {
+    KcGroup &G = ctx->grp;
+    if (!G.heap) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < G.n && r < KC_MAX_PEERS; ++r)
+        if (G.ipc_opened[r]) {
+            cudaIpcCloseMemHandle(G.peer[r]);
+            G.ipc_opened[r] = false;
+        }
+    cudaFree(G.heap);
+    if (G.cnt0) cudaFree(G.cnt0);
+    if (G.cells_local) cudaFree(G.cells_local);
+    if (G.dst_k) cudaFree(G.dst_k);
+    if (G.dst_p) cudaFree(G.dst_p);
+    if (G.h_dst) cudaFreeHost(G.h_dst);
+    if (G.tile_hist) cudaFree(G.tile_hist);
+    G = KcGroup();
+    (void) cudaGetLastError();
+}
+
+// Arena of one rank for a job of n_bytes: the owner-side levels over its hash range (two ping-pong generations of fixed slots, or
+// the exact construction's buffers), the node-dependent part of the overlap stage and the emission scratch.
+size_t group_arena_need(u64 n_bytes, int n_ranks, int limbs, bool complements, bool pessimistic) {
+    const double owned = (double) n_bytes / n_ranks * 1.3 + (1u << 20);
+    const double stage1 = owned * (8.0 * limbs + 4.0 + 2.0) * 4.0;
+    const double c = complements ? 2.0 : 1.0;
+    const double nodes = pessimistic ? n_bytes * 0.85 : n_bytes / 64.0 + 1e6;
+    return (size_t) ((stage1 + c * nodes * (240.0 + 32.0 * limbs) + 3.0 * n_bytes) * 1.1) + (256u << 20);
+}
+
+// One job of this rank.  `in.seq` is the WHOLE framed sequence, resident on this GPU.  Every rank of the group must make the
+// same call (same input, same parameters, same options) at about the same time.
+template <int L> void group_compute_rank(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params &p, DevResult &res) {
+    KcGroup &G = ctx->grp;
+    const u64 nb = in.n_bytes;
+    KC_CUDA(cudaEventRecord(ctx->ev[0], ex.stream));
+    KC_CUDA(cudaEventRecord(ctx->ev[1], ex.stream));
+    if (G.done_pending) {  // every rank has finished the previous job: its heaps may be written again
+        u32 *ws = reinterpret_cast<u32 *>(ex.arena->alloc_top<u64>(1));
+        ex.fill_bytes(ws, 0, 8);
+        kc_grp_wait(G, ex, G.done_seq, ws);
+        G.done_pending = false;
+    }
+    auto finish = [&]() {
+        G.done_seq = ++G.seq;
+        kc_grp_signal(G, ex, G.done_seq);
+        G.done_pending = true;
+    };
+    const KsfGroupPlan gp = kc_ksf_group_plan(nb, G.n, KsCfg<L>::EX_TILE, ctx->fast);
+    const bool expect_duplicates = ctx->fast_heuristics && (p.min_frequency > 1 || (ctx->fast_overflow_bytes && nb >= ctx->fast_overflow_bytes / 2 && nb <= ctx->fast_overflow_bytes * 2));
+    if (gp.ok && !expect_duplicates && gp.recv_items() <= G.lay.recv_items) {
+        const size_t top_mark = ex.arena->top, mark = ex.arena->mark();
+        ExtFlags ext;
+        ext.flags = reinterpret_cast<const u32 *>(G.heap + G.lay.off_flags);
+        ext.cells4 = kc_grp_fast_flags<L>(G, ex, in.seq, nb, p.k, p.complements != 0, p.min_frequency, gp, ctx->fast);
+        run_pipeline<L>(ctx, ex, in, p, res, &ext, false, (u32) G.rank, (u32) G.n);
+        if (!ext.aborted) {
+            ++ctx->fast_runs;
+            finish();
+            return;
+        }
+        if (ext.kept & 2u) {
+            G.failed = true;
+            KC_THROW(KC_ERR_INTERNAL, "a rank of the group did not arrive (wait timed out)");
+        }
+        ++ctx->fast_fallbacks;  // a slot overflowed on some rank: every rank sees the same status word and falls back
+        ctx->fast_overflow_bytes = nb;
+        ex.arena->release(mark);
+        ex.arena->top = top_mark;
+    }
+    ExtFlags ext;
+    ext.flags = kc_grp_exact_flags<L>(G, ex, in.seq, nb, p.k, p.complements != 0, p.min_frequency, &ext.kept, &ext.n_occ);
+    run_pipeline<L>(ctx, ex, in, p, res, &ext, false, (u32) G.rank, (u32) G.n);
+    finish();
+}
+
+void group_check_job(kc_ctx *ctx, const kc_params *p, u64 n_bytes) {
+    check_params(p);
+    KcGroup &G = ctx->grp;
+    if (!G.attached()) KC_THROW(KC_ERR_ARG, "this context is not part of a group");
+    for (int r = 0; r < G.n; ++r)
+        if (!G.peer[r]) KC_THROW(KC_ERR_ARG, "the group's heaps have not been opened");
+    if (G.failed) KC_THROW(KC_ERR_INTERNAL, "the group lost its synchronisation in an earlier call; create a new one");
+    if (p->assume_simplitigs || p->want_maxone) KC_THROW(KC_ERR_ARG, "the multi-GPU construction supports neither -S nor -M");
+    if (kc_limbs_for_k(p->k) > G.lay.limbs) KC_THROW(KC_ERR_ARG, "the group heap was sized for a narrower k-mer word");
+    if (n_bytes > G.lay.n_bytes_cap) KC_THROW(KC_ERR_TOO_LARGE, "the input exceeds the capacity the group heap was sized for");
+}
+
+
 }  // namespace
 
 extern "C" {
@@ -525,10 +648,7 @@ int kc_init(int device, void *stream, kc_ctx **out) {
         for (int i = 0; i < 6; ++i) KC_CUDA(cudaEventCreate(&ctx->ev[i]));
         KC_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->pin_small), kc_ctx::KC_PIN_SMALL, cudaHostAllocDefault));
         if (const char *e = std::getenv("KC_FAST_SET")) ctx->fast.enabled = std::atoi(e) != 0;
-        if (const char *e = std::getenv("KC_FAST_RESOLVE")) ctx->fast.resolve = std::atoi(e);
-        if (const char *e = std::getenv("KC_FAST_TILE")) ctx->fast.tile_variant = std::atoi(e);
         if (const char *e = std::getenv("KC_FAST_MAX_CTAS")) ctx->fast.max_ctas = std::atoi(e);
-        if (const char *e = std::getenv("KC_FAST_SPLIT0")) ctx->fast.split0 = std::atoi(e) != 0;
     } catch (const KcError &e) {
         int code = e.code;
         kc_destroy(ctx);
@@ -545,16 +665,7 @@ void kc_destroy(kc_ctx *ctx) {
     if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
     if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
     if (ctx->pin_small) cudaFreeHost(ctx->pin_small);
-    for (int r = 0; r < ctx->p2p.n_ranks && r < KC_MAX_PEERS; ++r)
-        if (ctx->p2p.opened[r]) {
-            cudaIpcCloseMemHandle(ctx->p2p.peer_k[r]);
-            cudaIpcCloseMemHandle(ctx->p2p.peer_p[r]);
-        }
-    if (ctx->p2p.recv_k) cudaFree(ctx->p2p.recv_k);
-    if (ctx->p2p.recv_p) cudaFree(ctx->p2p.recv_p);
-    if (ctx->p2p.tile_hist) cudaFree(ctx->p2p.tile_hist);
-    if (ctx->p2p.dst_k) cudaFree(ctx->p2p.dst_k);
-    if (ctx->p2p.dst_p) cudaFree(ctx->p2p.dst_p);
+    group_detach(ctx);
     for (int i = 0; i < 6; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < kc_ctx::KC_H2D_CHUNKS; ++i)
@@ -951,95 +1062,61 @@ uint64_t kc_shard_granule(int k) {
     return limbs == 1 ? KsCfg<1>::EX_TILE : (limbs == 2 ? KsCfg<2>::EX_TILE : KsCfg<4>::EX_TILE);
 }
 
-int kc_shard_partition(kc_ctx *ctx, const kc_params *p, const uint8_t *seq_dev, uint64_t n_bytes, uint64_t pos_begin, uint64_t pos_end,
-                       void *keys_dev_out, uint32_t *pos_dev_out, uint64_t *digit_counts, uint64_t *n_items) {
-    if (!ctx || !seq_dev || !digit_counts || !n_items) return KC_ERR_ARG;
+int kc_group_alloc(kc_ctx *ctx, int n_ranks, int rank, int k, uint64_t n_bytes_cap, uint8_t *handle_out) {
+    if (!ctx || !handle_out) return KC_ERR_ARG;
     KC_API_BEGIN
-    check_params(p);
-    if (p->assume_simplitigs || p->want_maxone) KC_THROW(KC_ERR_ARG, "sharded construction supports neither -S nor -M");
-    if (n_bytes >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 sequence bytes");
-    if ((reinterpret_cast<uintptr_t>(seq_dev) & 15) != 0) KC_THROW(KC_ERR_ARG, "device sequence pointer must be 16-byte aligned");
-    if (pos_end > pos_begin && (!keys_dev_out || !pos_dev_out)) KC_THROW(KC_ERR_ARG, "output buffers missing");
-    KC_CUDA(cudaSetDevice(ctx->device));
-    const u64 span = pos_end > pos_begin ? pos_end - pos_begin : 0;
-    ensure_arena(ctx, (size_t) (span * 2 + (64u << 20)));  // control arrays and tile histograms only: the items go to the caller's buffers
-    ctx->arena.reset();
-    CudaExec ex{ctx->stream, &ctx->arena};
-    ex.prof = &ctx->prof;
-    ex.pinned = ctx->pin_small;
-    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
-    KsShard sh;
-    sh.pos_begin = pos_begin;
-    sh.pos_end = pos_end;
-    sh.keys = keys_dev_out;
-    sh.pos = pos_dev_out;
-    u64 m = 0;
-    const bool c = p->complements != 0;
-    if (p->k < 32) m = kc_kmerset_partition<1>(ex, seq_dev, n_bytes, p->k, c, &sh);
-    else if (p->k < 64) m = kc_kmerset_partition<2>(ex, seq_dev, n_bytes, p->k, c, &sh);
-    else m = kc_kmerset_partition<4>(ex, seq_dev, n_bytes, p->k, c, &sh);
-    for (int i = 0; i < 256; ++i) digit_counts[i] = sh.host_hist[i];
-    *n_items = m;
-    ctx->total_launches += ex.launches;
+    group_alloc_common(ctx, n_ranks, rank, k, n_bytes_cap, false);
+    cudaIpcMemHandle_t h;
+    KC_CUDA(cudaIpcGetMemHandle(&h, ctx->grp.heap));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::memcpy(handle_out, &h, 64);
     return KC_OK;
     KC_API_END(ctx)
 }
 
-int kc_shard_resolve(kc_ctx *ctx, const kc_params *p, void *keys_dev, uint32_t *pos_dev, uint64_t n_items, uint32_t *flags_dev,
-                     uint64_t *n_kept) {
-    if (!ctx || !n_kept || !flags_dev) return KC_ERR_ARG;
+int kc_group_open(kc_ctx *ctx, const uint8_t *all_handles) {
+    if (!ctx || !all_handles) return KC_ERR_ARG;
     KC_API_BEGIN
-    check_params(p);
-    *n_kept = 0;
-    if (n_items == 0) return KC_OK;
-    if (!keys_dev || !pos_dev) KC_THROW(KC_ERR_ARG, "item buffers missing");
+    KcGroup &G = ctx->grp;
+    if (!G.heap) KC_THROW(KC_ERR_ARG, "kc_group_alloc first");
     KC_CUDA(cudaSetDevice(ctx->device));
-    const int limbs = kc_limbs_for_k(p->k);
-    ensure_arena(ctx, (size_t) ((double) n_items * (8.0 * limbs + 4.0 + 2.0) * 1.1) + (128u << 20));
-    ctx->arena.reset();
-    CudaExec ex{ctx->stream, &ctx->arena};
-    ex.prof = &ctx->prof;
-    ex.pinned = ctx->pin_small;
-    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
-    KsShard sh;
-    sh.keys = keys_dev;
-    sh.pos = pos_dev;
-    sh.n_items = n_items;
-    if (limbs == 1) *n_kept = kc_kmerset_resolve<1>(ex, p->k, p->min_frequency, flags_dev, &sh);
-    else if (limbs == 2) *n_kept = kc_kmerset_resolve<2>(ex, p->k, p->min_frequency, flags_dev, &sh);
-    else *n_kept = kc_kmerset_resolve<4>(ex, p->k, p->min_frequency, flags_dev, &sh);
-    ctx->total_launches += ex.launches;
+    for (int r = 0; r < G.n; ++r) {
+        if (r == G.rank || G.peer[r]) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, all_handles + (size_t) r * 64, 64);
+        void *pp = nullptr;
+        KC_CUDA(cudaIpcOpenMemHandle(&pp, h, cudaIpcMemLazyEnablePeerAccess));
+        G.peer[r] = reinterpret_cast<char *>(pp);
+        G.ipc_opened[r] = true;
+    }
     return KC_OK;
     KC_API_END(ctx)
 }
 
-int kc_compute_from_flags(kc_ctx *ctx, const kc_params *p, const kc_input *in, const uint32_t *flags_dev, uint64_t n_kept, kc_output *out) {
-    return kc_compute_from_flags_slice(ctx, p, in, flags_dev, n_kept, 0, 1, out, nullptr, nullptr);
-}
-
-int kc_compute_from_flags_slice(kc_ctx *ctx, const kc_params *p, const kc_input *in, const uint32_t *flags_dev, uint64_t n_kept, uint32_t slice_index,
-                                uint32_t n_slices, kc_output *out, uint64_t *slice_begin, uint64_t *slice_len) {
-    if (!ctx || !in || !out || !flags_dev || n_slices == 0 || slice_index >= n_slices) return KC_ERR_ARG;
+int kc_group_compute_device(kc_ctx *ctx, const kc_params *p, const kc_input *in, kc_output *out, uint64_t *slice_begin, uint64_t *slice_len) {
+    if (!ctx || !in || !out) return KC_ERR_ARG;
     KC_API_BEGIN
-    check_params(p);
-    if (p->assume_simplitigs || p->want_maxone) KC_THROW(KC_ERR_ARG, "sharded construction supports neither -S nor -M");
-    if (in->n_bytes >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 sequence bytes on one GPU");
+    group_check_job(ctx, p, in->n_bytes);
+    if ((reinterpret_cast<uintptr_t>(in->seq) & 15) != 0) KC_THROW(KC_ERR_ARG, "device sequence pointer must be 16-byte aligned");
     KC_CUDA(cudaSetDevice(ctx->device));
     const int limbs = kc_limbs_for_k(p->k);
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;
     ex.pinned = ctx->pin_small;
     ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
-    DevInput di{in->seq, in->n_bytes, in->rec_off, in->rec_len, in->n_recs};
+    DevInput di{in->seq, in->n_bytes, nullptr, nullptr, 0};
     DevResult res;
-    // no stage 1 here: only the node-dependent part (+ the emission scratch) is needed
-    const double c = p->complements ? 2.0 : 1.0;
-    auto need = [&](double nodes) { return (size_t) ((c * nodes * (240.0 + 32.0 * limbs) + 3.0 * in->n_bytes) * 1.1) + (256u << 20); };
-    run_with_arena(ctx, need(in->n_bytes / 64.0 + 1e6), need(in->n_bytes * 0.85), [&] {
-        if (p->k < 32) run_pipeline<1>(ctx, ex, di, *p, res, flags_dev, n_kept, false, slice_index, n_slices);
-        else if (p->k < 64) run_pipeline<2>(ctx, ex, di, *p, res, flags_dev, n_kept, false, slice_index, n_slices);
-        else run_pipeline<4>(ctx, ex, di, *p, res, flags_dev, n_kept, false, slice_index, n_slices);
-    });
+    // no retry with a larger arena here: a rank that repeated its job alone would leave the group's sync numbers behind
+    ensure_arena(ctx, group_arena_need(in->n_bytes, ctx->grp.n, limbs, p->complements != 0, false));
+    ctx->arena.reset();
+    try {
+        if (limbs == 1) group_compute_rank<1>(ctx, ex, di, *p, res);
+        else if (limbs == 2) group_compute_rank<2>(ctx, ex, di, *p, res);
+        else group_compute_rank<4>(ctx, ex, di, *p, res);
+    } catch (const KcError &e) {
+        if (e.code != KC_ERR_EMPTY) ctx->grp.failed = true;  // "no k-mers" is found by every rank at the same point
+        throw;
+    }
     KC_CUDA(cudaStreamSynchronize(ctx->stream));
     if (slice_begin) *slice_begin = res.slice_begin;
     if (slice_len) *slice_len = res.slice_len;
@@ -1047,7 +1124,7 @@ int kc_compute_from_flags_slice(kc_ctx *ctx, const kc_params *p, const kc_input 
     out->ms_maxone = nullptr;
     out->length = res.length;
     out->n_kmers = res.n_kmers;
-    out->n_occurrences = 0;
+    out->n_occurrences = res.n_occ;
     out->n_nodes = res.n_nodes;
     out->n_simplitigs = res.n_simplitigs;
     out->n_launches = ex.launches;
@@ -1057,210 +1134,230 @@ int kc_compute_from_flags_slice(kc_ctx *ctx, const kc_params *p, const kc_input 
     KC_API_END(ctx)
 }
 
-// ---- fused partition + exchange over peer memory -------------------------------------------------------------------------
-int kc_p2p_alloc(kc_ctx *ctx, int k, uint64_t capacity_items, uint8_t *handles_out) {
-    if (!ctx || !handles_out || capacity_items == 0) return KC_ERR_ARG;
-    KC_API_BEGIN
-    if (k < 1 || k > 127) KC_THROW(KC_ERR_ARG, "k must be in 1..127");
-    KC_CUDA(cudaSetDevice(ctx->device));
-    kc_ctx::P2P &q = ctx->p2p;
-    if (q.recv_k || q.n_ranks) KC_THROW(KC_ERR_ARG, "peer buffers already allocated on this context");
-    q.limbs = kc_limbs_for_k(k);
-    q.capacity = capacity_items;
-    KC_CUDA(cudaMalloc(&q.recv_k, capacity_items * 8 * q.limbs));
-    KC_CUDA(cudaMalloc(&q.recv_p, capacity_items * 4));
-    KC_CUDA(cudaMalloc(&q.dst_k, 256 * sizeof(void *)));
-    KC_CUDA(cudaMalloc(&q.dst_p, 256 * sizeof(u32 *)));
-    cudaIpcMemHandle_t hk, hp;
-    KC_CUDA(cudaIpcGetMemHandle(&hk, q.recv_k));
-    KC_CUDA(cudaIpcGetMemHandle(&hp, q.recv_p));
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    std::memcpy(handles_out, &hk, 64);
-    std::memcpy(handles_out + 64, &hp, 64);
+int kc_group_close(kc_ctx *ctx) {
+    if (!ctx) return KC_ERR_ARG;
+    group_detach(ctx);
     return KC_OK;
-    KC_API_END(ctx)
 }
 
-int kc_p2p_open(kc_ctx *ctx, int n_ranks, int rank, const uint8_t *all_handles) {
-    if (!ctx || !all_handles) return KC_ERR_ARG;
-    KC_API_BEGIN
-    if (n_ranks < 1 || n_ranks > KC_MAX_PEERS || rank < 0 || rank >= n_ranks) KC_THROW(KC_ERR_ARG, "bad rank / world size");
-    kc_ctx::P2P &q = ctx->p2p;
-    if (!q.recv_k) KC_THROW(KC_ERR_ARG, "kc_p2p_alloc first");
-    KC_CUDA(cudaSetDevice(ctx->device));
-    for (int r = 0; r < n_ranks; ++r) {
-        if (r == rank) {
-            q.peer_k[r] = q.recv_k;
-            q.peer_p[r] = q.recv_p;
-            continue;
+int kc_group_plan(int n_ranks, int rank, int k, uint64_t n_bytes, uint64_t *plan) {
+    if (!plan || n_ranks < 1 || n_ranks > KC_MAX_PEERS || rank < 0 || rank >= n_ranks || k < 1 || k > 127) return KC_ERR_ARG;
+    const u64 tile = kc_shard_granule(k);
+    KsfTuning tune;
+    const KsfGroupPlan gp = kc_ksf_group_plan(n_bytes, n_ranks, tile, tune);
+    const GrpLayout lay = kc_grp_layout(n_bytes, kc_limbs_for_k(k), n_ranks, false, tile, tune);
+    const u64 tiles = kc_div_up(n_bytes, tile);
+    plan[0] = gp.ok ? 1 : 0;
+    plan[1] = std::min<u64>(n_bytes, tiles * (u64) rank / (u64) n_ranks * tile);
+    plan[2] = std::min<u64>(n_bytes, tiles * (u64) (rank + 1) / (u64) n_ranks * tile);
+    plan[3] = gp.ok ? gp.dig_begin(rank) : (u64) ((rank * 256 + n_ranks - 1) / n_ranks);
+    plan[4] = gp.ok ? gp.dig_begin(rank + 1) : (u64) (((rank + 1) * 256 + n_ranks - 1) / n_ranks);
+    plan[5] = gp.ok ? gp.n_digits : 256;
+    plan[6] = gp.cap_sub;
+    plan[7] = lay.total;
+    return KC_OK;
+}
+
+// ---- multi-GPU inside one process: SURVEY.md §8(b) `kc_init(n_gpus, device_ids)` ----------------------------------------------
+// One host thread per GPU for the duration of a call, peer access between the devices (no IPC handles), the same rank-level
+// code as the multi-process form above.  The host side of `kmercamel compute -g 0,1,...` (host/main.cpp).
+struct kc_group {
+    int n = 0;
+    kc_ctx *ctx[KC_MAX_PEERS] = {};
+    u8 *pin_out = nullptr;
+    size_t pin_out_cap = 0;
+    std::mutex out_mutex;
+    std::string last_error;
+};
+
+static void group_release_heaps(kc_group *g) {
+    for (int r = 0; r < g->n; ++r)
+        if (g->ctx[r]) {
+            cudaSetDevice(g->ctx[r]->device);
+            cudaStreamSynchronize(g->ctx[r]->stream);
         }
-        cudaIpcMemHandle_t hk, hp;
-        std::memcpy(&hk, all_handles + (size_t) r * 128, 64);
-        std::memcpy(&hp, all_handles + (size_t) r * 128 + 64, 64);
-        KC_CUDA(cudaIpcOpenMemHandle(&q.peer_k[r], hk, cudaIpcMemLazyEnablePeerAccess));
-        void *pp = nullptr;
-        KC_CUDA(cudaIpcOpenMemHandle(&pp, hp, cudaIpcMemLazyEnablePeerAccess));
-        q.peer_p[r] = reinterpret_cast<u32 *>(pp);
-        q.opened[r] = true;
-    }
-    q.n_ranks = n_ranks;
-    q.rank = rank;
-    return KC_OK;
-    KC_API_END(ctx)
+    for (int r = 0; r < g->n; ++r)
+        if (g->ctx[r]) group_detach(g->ctx[r]);
 }
 
-int kc_p2p_hist(kc_ctx *ctx, const kc_params *p, const uint8_t *seq_dev, uint64_t n_bytes, uint64_t pos_begin, uint64_t pos_end,
-                uint64_t *digit_counts) {
-    if (!ctx || !seq_dev || !digit_counts) return KC_ERR_ARG;
-    KC_API_BEGIN
-    check_params(p);
-    if (p->assume_simplitigs || p->want_maxone) KC_THROW(KC_ERR_ARG, "sharded construction supports neither -S nor -M");
-    if (n_bytes >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 sequence bytes");
-    if ((reinterpret_cast<uintptr_t>(seq_dev) & 15) != 0) KC_THROW(KC_ERR_ARG, "device sequence pointer must be 16-byte aligned");
-    kc_ctx::P2P &q = ctx->p2p;
-    if (!q.n_ranks || kc_limbs_for_k(p->k) != q.limbs) KC_THROW(KC_ERR_ARG, "peer buffers not set up for this word width");
-    KC_CUDA(cudaSetDevice(ctx->device));
-    const u64 span = pos_end > pos_begin ? pos_end - pos_begin : 0;
-    const size_t need = (size_t) (kc_div_up(span, kc_shard_granule(p->k)) + 1) * 256 * sizeof(u16);
-    if (q.tile_hist_cap < need) {
-        if (q.tile_hist) KC_CUDA(cudaFree(q.tile_hist));
-        q.tile_hist = nullptr;
-        q.tile_hist_cap = 0;
-        KC_CUDA(cudaMalloc(&q.tile_hist, need));
-        q.tile_hist_cap = need;
-    }
-    ensure_arena(ctx, 64u << 20);
-    ctx->arena.reset();
-    CudaExec ex{ctx->stream, &ctx->arena};
-    ex.prof = &ctx->prof;
-    ex.pinned = ctx->pin_small;
-    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
-    KsShard sh;
-    sh.pos_begin = pos_begin;
-    sh.pos_end = pos_end;
-    sh.tile_hist_keep = q.tile_hist;
-    const bool c = p->complements != 0;
-    if (q.limbs == 1) q.n_items = kc_kmerset_hist_only<1>(ex, seq_dev, n_bytes, p->k, c, &sh);
-    else if (q.limbs == 2) q.n_items = kc_kmerset_hist_only<2>(ex, seq_dev, n_bytes, p->k, c, &sh);
-    else q.n_items = kc_kmerset_hist_only<4>(ex, seq_dev, n_bytes, p->k, c, &sh);
-    for (int i = 0; i < 256; ++i) digit_counts[i] = sh.host_hist[i];
-    ctx->total_launches += ex.launches;
-    return KC_OK;
-    KC_API_END(ctx)
-}
-
-// all_counts[s * 256 + g] = items of digit g on rank s.  Layout of an owner's receive buffer: its digits ascending,
-// inside a digit the ranks ascending.
-static void p2p_layout(const kc_ctx::P2P &q, const uint64_t *all_counts, u64 *bucket_off /*[256]*/, u64 *bucket_size /*[256]*/, u64 *owned /*[n_ranks]*/) {
-    for (int r = 0; r < q.n_ranks; ++r) owned[r] = 0;
-    for (int g = 0; g < 256; ++g) {
-        const int o = g * q.n_ranks / 256;
-        u64 sz = 0;
-        for (int s = 0; s < q.n_ranks; ++s) sz += all_counts[(size_t) s * 256 + g];
-        bucket_off[g] = owned[o];
-        bucket_size[g] = sz;
-        owned[o] += sz;
-    }
-}
-
-int kc_p2p_scatter(kc_ctx *ctx, const kc_params *p, const uint8_t *seq_dev, uint64_t n_bytes, uint64_t pos_begin, uint64_t pos_end,
-                   const uint64_t *all_counts) {
-    if (!ctx || !seq_dev || !all_counts) return KC_ERR_ARG;
-    KC_API_BEGIN
-    check_params(p);
-    kc_ctx::P2P &q = ctx->p2p;
-    if (!q.n_ranks || kc_limbs_for_k(p->k) != q.limbs || !q.tile_hist) KC_THROW(KC_ERR_ARG, "kc_p2p_hist first");
-    KC_CUDA(cudaSetDevice(ctx->device));
-    u64 off[256], size[256], owned[KC_MAX_PEERS], cursor0[256];
-    p2p_layout(q, all_counts, off, size, owned);
-    for (int r = 0; r < q.n_ranks; ++r)
-        if (owned[r] > q.capacity) KC_THROW(KC_ERR_TOO_LARGE, "a rank's hash range exceeds the peer buffer capacity");
-    void *hk[256];
-    u32 *hp[256];
-    for (int g = 0; g < 256; ++g) {
-        const int o = g * q.n_ranks / 256;
-        u64 before = 0;
-        for (int s = 0; s < q.rank; ++s) before += all_counts[(size_t) s * 256 + g];
-        cursor0[g] = off[g] + before;
-        hk[g] = q.peer_k[o];
-        hp[g] = q.peer_p[o];
-    }
-    KC_CUDA(cudaMemcpyAsync(q.dst_k, hk, sizeof(hk), cudaMemcpyHostToDevice, ctx->stream));
-    KC_CUDA(cudaMemcpyAsync(q.dst_p, hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
-    ensure_arena(ctx, 64u << 20);
-    ctx->arena.reset();
-    CudaExec ex{ctx->stream, &ctx->arena};
-    ex.prof = &ctx->prof;
-    ex.pinned = ctx->pin_small;
-    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
-    KsShard sh;
-    sh.pos_begin = pos_begin;
-    sh.pos_end = pos_end;
-    sh.tile_hist_keep = q.tile_hist;
-    sh.cursor0 = cursor0;
-    sh.dst_k = q.dst_k;
-    sh.dst_p = q.dst_p;
-    const bool c = p->complements != 0;
-    if (q.limbs == 1) kc_kmerset_scatter_p2p<1>(ex, seq_dev, n_bytes, p->k, c, q.n_items, &sh);
-    else if (q.limbs == 2) kc_kmerset_scatter_p2p<2>(ex, seq_dev, n_bytes, p->k, c, q.n_items, &sh);
-    else kc_kmerset_scatter_p2p<4>(ex, seq_dev, n_bytes, p->k, c, q.n_items, &sh);
-    KC_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->total_launches += ex.launches;
-    return KC_OK;
-    KC_API_END(ctx)
-}
-
-int kc_p2p_resolve(kc_ctx *ctx, const kc_params *p, const uint64_t *all_counts, uint32_t *flags_dev, uint64_t *n_kept, uint64_t *n_owned) {
-    if (!ctx || !all_counts || !flags_dev || !n_kept) return KC_ERR_ARG;
-    KC_API_BEGIN
-    check_params(p);
-    kc_ctx::P2P &q = ctx->p2p;
-    if (!q.n_ranks || kc_limbs_for_k(p->k) != q.limbs) KC_THROW(KC_ERR_ARG, "peer buffers not set up for this word width");
-    KC_CUDA(cudaSetDevice(ctx->device));
-    u64 off[256], size[256], owned[KC_MAX_PEERS];
-    p2p_layout(q, all_counts, off, size, owned);
-    *n_kept = 0;
-    if (n_owned) *n_owned = owned[q.rank];
-    if (owned[q.rank] == 0) return KC_OK;
-    u64 my_off[256], my_size[256];
-    u32 n_pre = 0;
-    for (int g = 0; g < 256; ++g)
-        if (g * q.n_ranks / 256 == q.rank) {
-            my_off[n_pre] = off[g];
-            my_size[n_pre] = size[g];
-            ++n_pre;
+int kc_init_multi(int n_gpus, const int *device_ids, kc_group **out) {
+    if (!out || !device_ids || n_gpus < 1 || n_gpus > KC_MAX_PEERS) return KC_ERR_ARG;
+    *out = nullptr;
+    kc_group *g = new (std::nothrow) kc_group();
+    if (!g) return KC_ERR_OOM;
+    g->n = n_gpus;
+    int rc = KC_OK;
+    for (int r = 0; r < n_gpus && rc == KC_OK; ++r) rc = kc_init(device_ids[r], nullptr, &g->ctx[r]);
+    for (int a = 0; a < n_gpus && rc == KC_OK; ++a)
+        for (int b = 0; b < n_gpus && rc == KC_OK; ++b) {
+            const int da = device_ids[a], db = device_ids[b];
+            if (da == db) continue;
+            int can = 0;
+            if (cudaSetDevice(da) != cudaSuccess || cudaDeviceCanAccessPeer(&can, da, db) != cudaSuccess || !can) {
+                rc = KC_ERR_ARG;
+                break;
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) rc = KC_ERR_CUDA;
+            (void) cudaGetLastError();
         }
-    ensure_arena(ctx, (size_t) ((double) owned[q.rank] * (8.0 * q.limbs + 4.0 + 2.0) * 4.0) + (192u << 20));  // two ping-pong levels of fixed slots (leaf slots hold 1024 for a mean of 384..768)
-    ctx->arena.reset();
-    CudaExec ex{ctx->stream, &ctx->arena};
-    ex.prof = &ctx->prof;
-    ex.pinned = ctx->pin_small;
-    ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
-    KsShard sh;
-    sh.keys = q.recv_k;
-    sh.pos = q.recv_p;
-    sh.n_items = owned[q.rank];
-    sh.n_pre = n_pre;
-    sh.pre_off = my_off;
-    sh.pre_size = my_size;
-    // fixed-slot levels first (no counting passes); exact construction when the plan does not apply or a slot overflowed
-    u64 kept = 0;
-    bool fast = false;
-    if (q.limbs == 1) fast = kc_kmerset_resolve_fast<1>(ex, p->k, p->min_frequency, flags_dev, &sh, ctx->fast, &kept);
-    else if (q.limbs == 2) fast = kc_kmerset_resolve_fast<2>(ex, p->k, p->min_frequency, flags_dev, &sh, ctx->fast, &kept);
-    else fast = kc_kmerset_resolve_fast<4>(ex, p->k, p->min_frequency, flags_dev, &sh, ctx->fast, &kept);
-    if (fast) {
-        ++ctx->fast_runs;
-        *n_kept = kept;
-    } else {
-        ++ctx->fast_fallbacks;
-        if (q.limbs == 1) *n_kept = kc_kmerset_resolve<1>(ex, p->k, p->min_frequency, flags_dev, &sh);
-        else if (q.limbs == 2) *n_kept = kc_kmerset_resolve<2>(ex, p->k, p->min_frequency, flags_dev, &sh);
-        else *n_kept = kc_kmerset_resolve<4>(ex, p->k, p->min_frequency, flags_dev, &sh);
+    if (rc != KC_OK) {
+        kc_group_destroy(g);
+        return rc;
     }
-    ctx->total_launches += ex.launches;
+    *out = g;
     return KC_OK;
-    KC_API_END(ctx)
+}
+
+void kc_group_destroy(kc_group *g) {
+    if (!g) return;
+    group_release_heaps(g);
+    for (int r = 0; r < g->n; ++r)
+        if (g->ctx[r]) kc_destroy(g->ctx[r]);
+    if (g->pin_out) cudaFreeHost(g->pin_out);
+    delete g;
+}
+
+int kc_group_size(const kc_group *g) { return g ? g->n : 0; }
+kc_ctx *kc_group_ctx(kc_group *g, int rank) { return g && rank >= 0 && rank < g->n ? g->ctx[rank] : nullptr; }
+const char *kc_group_last_error(const kc_group *g) { return g ? g->last_error.c_str() : ""; }
+
+int kc_group_compute(kc_group *g, const kc_params *p, const kc_input *in, kc_output *out) {
+    if (!g || !p || !in || !out) return KC_ERR_ARG;
+    kc_ctx *c0 = g->ctx[0];
+    try {
+        check_params(p);
+        if (p->assume_simplitigs || p->want_maxone) KC_THROW(KC_ERR_ARG, "the multi-GPU construction supports neither -S nor -M");
+        if (in->n_bytes >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 sequence bytes");
+        const int limbs = kc_limbs_for_k(p->k);
+        // (re)build the heaps when the job does not fit the ones in place
+        const KcGroup &G0 = c0->grp;
+        if (!G0.attached() || in->n_bytes > G0.lay.n_bytes_cap || limbs > G0.lay.limbs || G0.failed) {
+            group_release_heaps(g);
+            const u64 cap = std::min<u64>(0xFFFFFFE0ULL, in->n_bytes + in->n_bytes / 16 + (1u << 20));
+            for (int r = 0; r < g->n; ++r) {
+                g->ctx[r]->fast = c0->fast;  // one plan for the whole group
+                g->ctx[r]->fast_heuristics = c0->fast_heuristics;
+                g->ctx[r]->fast_overflow_bytes = c0->fast_overflow_bytes;
+                group_alloc_common(g->ctx[r], g->n, r, limbs == 1 ? 31 : (limbs == 2 ? 63 : 127), cap, true);
+            }
+            for (int r = 0; r < g->n; ++r)
+                for (int s = 0; s < g->n; ++s) g->ctx[r]->grp.peer[s] = g->ctx[s]->grp.heap;
+        }
+        // every allocation happens BEFORE the first kernel of the job is queued anywhere: cudaMalloc / cudaFree wait for the whole
+        // device, which would include a peer rank's wait kernel when two ranks share a GPU (tests)
+        for (int r = 0; r < g->n; ++r) {
+            KC_CUDA(cudaSetDevice(g->ctx[r]->device));
+            ensure_arena(g->ctx[r], group_arena_need(in->n_bytes, g->n, limbs, p->complements != 0, false));
+        }
+    } catch (const KcError &e) {
+        set_error(c0, e);
+        g->last_error = c0->last_error;
+        return e.code;
+    }
+    struct RankOut {
+        int code = KC_OK;
+        std::string what;
+        DevResult res;
+        u64 launches = 0;
+        kc_output o;
+    } ro[KC_MAX_PEERS];
+    auto worker = [&](int r) {
+        kc_ctx *ctx = g->ctx[r];
+        RankOut &R = ro[r];
+        try {
+            KC_CUDA(cudaSetDevice(ctx->device));
+            KcGroup &G = ctx->grp;
+            ctx->arena.reset();
+            CudaExec ex{ctx->stream, &ctx->arena};
+            ex.prof = &ctx->prof;
+            ex.pinned = ctx->pin_small;
+            ex.pinned_cap = ctx->pin_small ? kc_ctx::KC_PIN_SMALL : 0;
+            // the sequence: this rank brings in its share over its own PCIe link and hands it to every peer over NVLink
+            u8 *seq = reinterpret_cast<u8 *>(G.heap + G.lay.off_seq);
+            const u64 nb = in->n_bytes;
+            const u64 b = (nb * (u64) r / (u64) g->n) & ~(u64) 255, e = r == g->n - 1 ? nb : ((nb * (u64) (r + 1) / (u64) g->n) & ~(u64) 255);
+            if (G.done_pending) {  // the peers may still read the previous job's sequence
+                u32 *ws = reinterpret_cast<u32 *>(ex.arena->alloc_top<u64>(1));
+                ex.fill_bytes(ws, 0, 8);
+                kc_grp_wait(G, ex, G.done_seq, ws);
+                G.done_pending = false;
+            }
+            if (e > b) {
+                KC_CUDA(cudaMemcpyAsync(seq + b, in->seq + b, e - b, cudaMemcpyHostToDevice, ctx->stream));
+                for (int s = 0; s < g->n; ++s)
+                    if (s != r) KC_CUDA(cudaMemcpyAsync(G.peer[s] + G.lay.off_seq + b, seq + b, e - b, cudaMemcpyDefault, ctx->stream));
+            }
+            u32 *ws = reinterpret_cast<u32 *>(ex.arena->alloc_top<u64>(1));
+            ex.fill_bytes(ws, 0, 8);
+            const u32 s0 = ++G.seq;
+            kc_grp_signal(G, ex, s0);
+            kc_grp_wait(G, ex, s0, ws);
+            DevInput di{seq, nb, nullptr, nullptr, 0};
+            const int limbs = kc_limbs_for_k(p->k);
+            if (limbs == 1) group_compute_rank<1>(ctx, ex, di, *p, R.res);
+            else if (limbs == 2) group_compute_rank<2>(ctx, ex, di, *p, R.res);
+            else group_compute_rank<4>(ctx, ex, di, *p, R.res);
+            {   // the first rank to get here sizes the common result buffer
+                std::lock_guard<std::mutex> lk(g->out_mutex);
+                const size_t need = (size_t) R.res.length + 64;
+                if (g->pin_out_cap < need) {
+                    if (g->pin_out) KC_CUDA(cudaFreeHost(g->pin_out));
+                    g->pin_out = nullptr;
+                    g->pin_out_cap = 0;
+                    KC_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&g->pin_out), need + need / 8, cudaHostAllocPortable));
+                    g->pin_out_cap = need + need / 8;
+                }
+            }
+            if (R.res.slice_len)
+                KC_CUDA(cudaMemcpyAsync(g->pin_out + R.res.slice_begin, R.res.ms, R.res.slice_len, cudaMemcpyDeviceToHost, ctx->stream));
+            KC_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (ex.read(ws) & 2u) KC_THROW(KC_ERR_INTERNAL, "a rank of the group did not arrive (wait timed out)");
+            R.launches = ex.launches;
+            fill_times(ctx, &R.o);
+            ctx->total_launches += ex.launches;
+        } catch (const KcError &e) {
+            R.code = e.code;
+            char buf[512];
+            std::snprintf(buf, sizeof(buf), "rank %d: %s (%s:%d)", r, e.what, e.file, e.line);
+            R.what = buf;
+            if (e.code != KC_ERR_EMPTY) ctx->grp.failed = true;
+        } catch (...) {
+            R.code = KC_ERR_INTERNAL;
+            R.what = "rank " + std::to_string(r) + ": unknown failure";
+            ctx->grp.failed = true;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int r = 1; r < g->n; ++r) th.emplace_back(worker, r);
+    worker(0);
+    for (auto &t : th) t.join();
+    for (int r = 0; r < g->n; ++r)
+        if (ro[r].code != KC_OK) {
+            if (ro[r].code != KC_ERR_EMPTY)
+                for (int s = 0; s < g->n; ++s) g->ctx[s]->grp.failed = true;
+            g->last_error = ro[r].what;
+            c0->last_error = ro[r].what;
+            return ro[r].code;
+        }
+    for (int r = 1; r < g->n; ++r)
+        if (ro[r].res.length != ro[0].res.length || ro[r].res.n_kmers != ro[0].res.n_kmers) {
+            g->last_error = "the ranks disagree on the result";
+            return KC_ERR_INTERNAL;
+        }
+    std::memset(out, 0, sizeof(*out));
+    out->ms = g->pin_out;
+    out->length = ro[0].res.length;
+    out->n_kmers = ro[0].res.n_kmers;
+    out->n_occurrences = ro[0].res.n_occ;
+    out->n_nodes = ro[0].res.n_nodes;
+    out->n_simplitigs = ro[0].res.n_simplitigs;
+    out->t = ro[0].o.t;
+    for (int r = 0; r < g->n; ++r) {
+        out->n_launches += ro[r].launches;
+        if (ro[r].o.t.total_ms > out->t.total_ms) out->t = ro[r].o.t;  // the slowest rank's stage times
+    }
+    return KC_OK;
 }
 
 uint64_t kc_total_launches(const kc_ctx *ctx) { return ctx ? ctx->total_launches : 0; }
@@ -1270,8 +1367,6 @@ int kc_get_stat(const kc_ctx *ctx, const char *name, uint64_t *value) {
     if (std::strcmp(name, "fast_runs") == 0) *value = ctx->fast_runs;
     else if (std::strcmp(name, "fast_fallbacks") == 0) *value = ctx->fast_fallbacks;
     else if (std::strcmp(name, "total_launches") == 0) *value = ctx->total_launches;
-    else if (std::strcmp(name, "fast_resolve") == 0) *value = (uint64_t) ctx->fast.resolve;
-    else if (std::strcmp(name, "fast_tile_variant") == 0) *value = (uint64_t) ctx->fast.tile_variant;
     else if (std::strcmp(name, "fast_max_ctas") == 0) *value = (uint64_t) ctx->fast.max_ctas;
     else return KC_ERR_ARG;
     return KC_OK;
@@ -1301,25 +1396,13 @@ int kc_set_option(kc_ctx *ctx, const char *name, int value) {
         ctx->fast.sigmas = (double) value;
         return KC_OK;
     }
-    if (std::strcmp(name, "fast_resolve") == 0 && value >= 0 && value <= 8) {
-        ctx->fast.resolve = value;
-        return KC_OK;
-    }
     if (std::strcmp(name, "fast_heuristics") == 0 && (value == 0 || value == 1)) {
         ctx->fast_heuristics = value != 0;
         ctx->fast_overflow_bytes = 0;
         return KC_OK;
     }
-    if (std::strcmp(name, "fast_tile_variant") == 0 && value >= 0 && value <= 5) {
-        ctx->fast.tile_variant = value;
-        return KC_OK;
-    }
     if (std::strcmp(name, "fast_max_ctas") == 0 && value >= 0 && value <= (1 << 20)) {
         ctx->fast.max_ctas = value;
-        return KC_OK;
-    }
-    if (std::strcmp(name, "fast_split0") == 0 && (value == 0 || value == 1)) {
-        ctx->fast.split0 = value;
         return KC_OK;
     }
     if (std::strcmp(name, "fast_min_items") == 0 && value >= 0) {

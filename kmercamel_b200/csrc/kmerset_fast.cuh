@@ -13,6 +13,15 @@
 //   * two host read-backs (bucket lists / tile counts) and six scan / bookkeeping launches.
 // Algorithmic HBM bytes per k-mer (L = 1): 1 + 12 (level 0) + 12 + 12 (level 1) + 12 (resolve) = 49 instead of 58.
 //
+// Flags are "clear the losers": level 0 writes the bit of every valid window (one coalesced word per strip), and every
+// atomicMin that folds a duplicate in the leaf resolve clears exactly one bit — the larger of the two positions it compared.
+// A genome has ~0 duplicates, so the resolve writes almost nothing.
+//
+// Multi-GPU (group.cuh): the same kernels with P2P = true.  Level 0 runs over the rank's slice of the input and stores every
+// item straight into the (digit, sender) sub-slot of the digit's OWNER GPU through peer pointers (NVLink), and the valid-window
+// words into every rank's flag array; the owner's level 1 reads the sub-slots of all senders as parents of one bucket, and
+// the resolve clears losers in every rank's flags.
+//
 // Inputs that break the assumption (30x read sets: every k-mer ~30 times, so sigma grows by sqrt(30); low-complexity
 // sequence) overflow a slot.  Overflow is detected on the device (items beyond the slot are dropped, a status word is
 // set) and reported with the same read-back that returns the counts; the caller then discards the flags and runs the
@@ -36,15 +45,40 @@ struct InputChunks {
     }
 };
 
+// The first-occurrence bit arrays a loser is cleared in / the valid-window words are written to: this GPU's own array, or
+// the arrays of every rank of the group (peer pointers).
+struct KsfFlagPeers {
+    u32 *f[KC_MAX_PEERS];
+    int n;
+};
+inline KsfFlagPeers kc_ksf_own_flags(u32 *flags) {
+    KsfFlagPeers fp;
+    for (int i = 0; i < KC_MAX_PEERS; ++i) fp.f[i] = nullptr;
+    fp.f[0] = flags;
+    fp.n = 1;
+    return fp;
+}
+
 #ifdef __CUDACC__
+
+KC_D void kc_flag_clear_all(const KsfFlagPeers &fp, u32 pos) {
+    const u32 m = ~(1u << (pos & 31));
+    for (int r = 0; r < fp.n; ++r) atomicAnd(&fp.f[r][pos >> 5], m);
+}
 
 // status[0] = 1: some slot overflowed (the flags are incomplete and must be discarded)
 // ---- level 0: sequence -> fixed-slot buckets, one compute pass ----------------------------------------------------------
-template <int L>
+// P2P = false: bucket i is the slot keys[i * cap0 ..), the valid-window word goes to vf.f[0] (only words with a window: the
+//              array arrives zeroed).
+// P2P = true : bucket i is the sub-slot dst_k[i] / dst_p[i] (cap0 items, somewhere in the heap of the digit's owner), the
+//              valid-window word of EVERY strip goes to all vf.n arrays (they do not arrive zeroed).
+template <int L, bool P2P>
 __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int complements,
                                                                                 int shift, int bits, u32 *bucket_cnt, u32 cap0,
                                                                                 KWord<L> *__restrict__ keys, u32 *__restrict__ pos, u32 *status, u32 tile0,
-                                                                                u32 *__restrict__ valid_flags = nullptr, u32 n_flag_words = 0) {
+                                                                                KsfFlagPeers vf, u32 n_flag_words,
+                                                                                KWord<L> *const *__restrict__ dst_k = nullptr,
+                                                                                u32 *const *__restrict__ dst_p = nullptr) {
     constexpr int T = KsCfg<L>::EX_THREADS;
     constexpr int LOG_T = T == 256 ? 8 : (T == 128 ? 7 : 6);
     constexpr int R = 256 / T;
@@ -58,6 +92,8 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(c
     __shared__ u32 cnt[256];
     __shared__ u32 loff[256];
     __shared__ u64 dbase[256];  // slot index of the digit's first item of this tile, minus its staged position: at = dbase + q
+                                // (P2P: the address of the key with staged position 0, pbase the same for the positions)
+    __shared__ u64 pbase[P2P ? 256 : 1];
     __shared__ u32 qlim[256];   // staged positions below this still fit into the digit's slot
     __shared__ u32 sw[T / 32];
     const i64 block_pos0 = (i64) (tile0 + blockIdx.x) * TILE;
@@ -68,9 +104,14 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(c
     __syncthreads();
     const int widx = KC_EX_HALO + threadIdx.x;
     const u32 em = kc_strip_emit_mask(vm, widx, k);
-    if (valid_flags) {  // clear-the-losers flags: every window starts as "first occurrence" (bit p & 31 of word p >> 5 = window END p)
+    {   // clear-the-losers flags: every window starts as "first occurrence" (bit p & 31 of word p >> 5 = window END p)
         const u64 w = (u64) (block_pos0 >> 5) + threadIdx.x;
-        if (em && w < n_flag_words) valid_flags[w] = __brev(em);
+        if (P2P) {
+            if (w < n_flag_words)
+                for (int r = 0; r < vf.n; ++r) vf.f[r][w] = __brev(em);
+        } else if (em && w < n_flag_words) {
+            vf.f[0][w] = __brev(em);
+        }
     }
     kc_strip_windows<L>(pk, widx, em, k, complements, [&](int j, const KWord<L> &c0) {
         const KWord<L> c = kmer_scramble(c0);
@@ -95,7 +136,13 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(c
             u32 gb = 0;
             if (v[r]) gb = atomicAdd(&bucket_cnt[i], v[r]);  // reserve the tile's place inside the slot of bucket i
             const u32 room = gb < cap0 ? cap0 - gb : 0u;
-            dbase[i] = (u64) i * cap0 + gb - p;
+            if (P2P) {
+                const i64 d = (i64) gb - (i64) p;
+                dbase[i] = (u64) (reinterpret_cast<i64>(dst_k[i]) + d * (i64) sizeof(KWord<L>));
+                pbase[i] = (u64) (reinterpret_cast<i64>(dst_p[i]) + d * 4);
+            } else {
+                dbase[i] = (u64) i * cap0 + gb - p;
+            }
             qlim[i] = p + (v[r] < room ? v[r] : room);
             p += v[r];
         }
@@ -130,109 +177,15 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(c
         const KWord<L> v = stash[slot];
         const u32 dg = v.digit_top(shift, bits);
         if (q < qlim[dg]) {
-            const u64 at = dbase[dg] + q;
-            keys[at] = v;
-            pos[at] = (u32) block_pos0 + (slot & (T - 1)) * KC_EX_STRIP + (slot >> LOG_T);
-        } else {
-            over = true;
-        }
-    }
-    if (over) status[0] = 1;
-}
-
-// L = 1 with TWO threads per 32-base strip: thread t handles the windows ending at bases [16 h, 16 h + 16) of strip
-// t & 255, h = t >> 8.  Same tile, same shared memory, same output as kc_ksf_scatter0_kernel<1>, but 16 instead of 8 warps
-// per CTA: the kernel is limited to 2 CTAs per SM by its 96 KB stash, and ncu showed it waiting on shared-memory
-// round trips (short scoreboard) at 24 % occupancy.
-__global__ void __launch_bounds__(512) kc_ksf_scatter0_split_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int complements, int shift, int bits,
-                                                                    u32 *bucket_cnt, u32 cap0, KWord<1> *__restrict__ keys, u32 *__restrict__ pos,
-                                                                    u32 *status, u32 tile0) {
-    constexpr int S = 256;   // strips per tile
-    constexpr int T = 512;
-    constexpr int TILE = KsCfg<1>::EX_TILE;
-    extern __shared__ __align__(16) unsigned char kc_smem_raw[];
-    u64 *stash = reinterpret_cast<u64 *>(kc_smem_raw);  // slot j * S + strip = window j of the strip (conflict-free)
-    u16 *rk = reinterpret_cast<u16 *>(stash + TILE);
-    u16 *perm = rk + TILE;
-    __shared__ u64 pk[KC_EX_HALO + S];
-    __shared__ u32 vm[KC_EX_HALO + S];
-    __shared__ u32 cnt[256];
-    __shared__ u32 loff[256];
-    __shared__ u32 gbase[256];
-    __shared__ u32 sw[T / 32];
-    const i64 block_pos0 = (i64) (tile0 + blockIdx.x) * TILE;
-    if (threadIdx.x < S) {
-        kc_tile_load<S>(seq, n_bytes, block_pos0, pk, vm);
-        cnt[threadIdx.x] = 0;
-    }
-    const u32 strip = threadIdx.x & (S - 1);
-    const int j0 = (int) (threadIdx.x >> 8) * 16;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) rk[(u32) (j0 + j) * S + strip] = 0xFFFFu;
-    __syncthreads();
-    const int widx = KC_EX_HALO + (int) strip;
-    const u32 em = kc_strip_emit_mask(vm, widx, k);
-    if ((em >> (16 - j0)) & 0xFFFFu) {  // bit 31 - j for base j: the half's 16 bits
-        const u64 mine = pk[widx], prev = pk[widx - 1];
-        const u64 mask = (1ULL << (2 * k)) - 1;
-        const int top = 2 * (k - 1);
-        // the k-1 bases before base j0 of the strip: the low end of (prev : mine) cut after base j0 - 1
-        const u64 before = j0 ? ((prev << 32) | (mine >> 32)) : prev;
-        KWord<1> pw;
-        pw.w[0] = before & ((1ULL << top) - 1);
-        u64 rcs = k > 1 ? kmer_reverse_complement(pw, k - 1).w[0] : 0;
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-            const int j = j0 + jj;
-            const int sh = 2 * (31 - j);
-            u64 fwd = mine >> sh;
-            if (j < 31) fwd |= prev << (2 * (j + 1));
-            fwd &= mask;
-            const u64 c = (mine >> sh) & 3;
-            const u64 rcf = rcs | ((3 ^ c) << top);
-            rcs = rcf >> 2;
-            if ((em >> (31 - j)) & 1) {
-                KWord<1> canon;
-                canon.w[0] = (!complements || fwd < rcf) ? fwd : rcf;
-                const KWord<1> cs = kmer_scramble(canon);
-                const u32 slot = (u32) j * S + strip;
-                stash[slot] = cs.w[0];
-                rk[slot] = (u16) atomicAdd(&cnt[cs.digit_top(shift, bits)], 1u);
+            const u32 pv = (u32) block_pos0 + (slot & (T - 1)) * KC_EX_STRIP + (slot >> LOG_T);
+            if (P2P) {
+                reinterpret_cast<KWord<L> *>(dbase[dg])[q] = v;
+                reinterpret_cast<u32 *>(pbase[dg])[q] = pv;
+            } else {
+                const u64 at = dbase[dg] + q;
+                keys[at] = v;
+                pos[at] = pv;
             }
-        }
-    }
-    __syncthreads();
-    u32 total;
-    {
-        const u32 c = threadIdx.x < 256 ? cnt[threadIdx.x] : 0u;
-        const u32 p = kc_block_exclusive_scan<T>(c, &total, sw);
-        if (threadIdx.x < 256) {
-            loff[threadIdx.x] = p;
-            if (c) gbase[threadIdx.x] = atomicAdd(&bucket_cnt[threadIdx.x], c);
-        }
-    }
-    __syncthreads();
-    if (total == 0) return;
-    for (u32 slot = threadIdx.x; slot < (u32) TILE; slot += T) {
-        const u32 r = rk[slot];
-        if (r != 0xFFFFu) {
-            KWord<1> v;
-            v.w[0] = stash[slot];
-            perm[loff[v.digit_top(shift, bits)] + r] = (u16) slot;
-        }
-    }
-    __syncthreads();
-    bool over = false;
-    for (u32 q = threadIdx.x; q < total; q += T) {
-        const u32 slot = perm[q];
-        KWord<1> v;
-        v.w[0] = stash[slot];
-        const u32 dg = v.digit_top(shift, bits);
-        const u32 idx = gbase[dg] + (q - loff[dg]);
-        if (idx < cap0) {
-            const u64 at = (u64) dg * cap0 + idx;
-            keys[at] = v;
-            pos[at] = (u32) ((u64) block_pos0 + (slot & (S - 1)) * KC_EX_STRIP + (slot >> 8));
         } else {
             over = true;
         }
@@ -260,106 +213,6 @@ __global__ void __launch_bounds__(256) kc_ksf_prep_kernel(const u32 *cnt, u32 nP
     tile_count[p] = (c + tile - 1) / tile;
 }
 
-// ---- levels >= 1: fixed-slot parents -> fixed-slot children (kc_kv_scatter_kernel without the counting pass) ---------------
-template <int L, int TILE, int MINB>
-__global__ void __launch_bounds__(256, MINB) kc_ksf_scatter_kernel(const KWord<L> *__restrict__ ksrc, const u32 *__restrict__ psrc, KWord<L> *__restrict__ kdst,
-                                                             u32 *__restrict__ pdst, const u32 *__restrict__ P_size, const u32 *__restrict__ tile_prefix,
-                                                             u32 nP, u64 capP, u32 tiles_per_cta, int shift, int bits, u32 *C_cnt, u32 capC, u32 *status,
-                                                             const u64 *__restrict__ P_off = nullptr) {
-    constexpr int ITEMS = TILE / 256;
-    extern __shared__ __align__(16) unsigned char kc_smem_raw[];
-    KWord<L> *stage_k = reinterpret_cast<KWord<L> *>(kc_smem_raw);
-    u32 *stage_p = reinterpret_cast<u32 *>(stage_k + TILE);
-    u16 *rk = reinterpret_cast<u16 *>(stage_p + TILE);
-    __shared__ u32 cnt[256];
-    __shared__ u32 loff[256];
-    __shared__ u32 gbase[256];
-    __shared__ u32 sw[8];
-    const u32 n_tiles = tile_prefix[nP];
-    const u32 t0 = blockIdx.x * tiles_per_cta;
-    const u32 t1 = min(n_tiles, t0 + tiles_per_cta);
-    if (t0 >= t1) return;
-    u32 b = kc_upper_bound_u32(tile_prefix, nP + 1, t0) - 1;
-    cnt[threadIdx.x] = 0;
-    bool over = false;
-    __syncthreads();
-    for (u32 t = t0; t < t1; ++t) {
-        while (t >= tile_prefix[b + 1]) ++b;
-        const u64 pbase = P_off ? P_off[b] : (u64) b * capP;  // P_off: parents laid out back to back (multi-GPU receive buffer)
-        const KWord<L> *src = ksrc + pbase;
-        const u32 *ps = psrc + pbase;
-        const u32 start = (t - tile_prefix[b]) * TILE;
-        const u32 n_here = min((u32) TILE, P_size[b] - start);
-        KWord<L> item[ITEMS];
-        u32 pay[ITEMS];
-#pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const u32 i = threadIdx.x + j * 256;
-            if (i < n_here) item[j] = src[start + i];
-        }
-#pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const u32 i = threadIdx.x + j * 256;
-            if (i < n_here) pay[j] = ps[start + i];
-        }
-#pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const u32 i = threadIdx.x + j * 256;
-            if (i < n_here) rk[i] = (u16) atomicAdd(&cnt[item[j].digit_top(shift, bits)], 1u);
-        }
-        __syncthreads();
-        const u32 c = cnt[threadIdx.x];
-        u32 total;
-        const u32 p = kc_block_exclusive_scan<256>(c, &total, sw);
-        loff[threadIdx.x] = p;
-        if (c) gbase[threadIdx.x] = atomicAdd(&C_cnt[((u64) b << bits) + threadIdx.x], c);
-        cnt[threadIdx.x] = 0;
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const u32 i = threadIdx.x + j * 256;
-            if (i < n_here) {
-                const u32 q = loff[item[j].digit_top(shift, bits)] + rk[i];
-                stage_k[q] = item[j];
-                stage_p[q] = pay[j];
-            }
-        }
-        __syncthreads();
-        for (u32 q = threadIdx.x; q < n_here; q += 256) {
-            const KWord<L> v = stage_k[q];
-            const u32 dg = v.digit_top(shift, bits);
-            const u32 idx = gbase[dg] + (q - loff[dg]);
-            if (idx < capC) {
-                const u64 at = (((u64) b << bits) + dg) * capC + idx;
-                kdst[at] = v;
-                pdst[at] = stage_p[q];
-            } else {
-                over = true;
-            }
-        }
-        __syncthreads();
-    }
-    if (over) status[0] = 1;
-}
-
-// Leaf slots -> the bucket list kc_ks_resolve_hash_kernel walks.
-__global__ void __launch_bounds__(256) kc_ksf_leaf_kernel(const u32 *cnt, u64 n_leaf, u32 cap, u8 parity, SortBucket *small, u32 *status) {
-    const u64 c = (u64) blockIdx.x * 256 + threadIdx.x;
-    if (c >= n_leaf) return;
-    u32 s = cnt[c];
-    if (s > cap) {
-        status[0] = 1;
-        s = cap;
-    }
-    SortBucket d;
-    d.off = c * cap;
-    d.size = s;
-    d.rem = 0;
-    d.parity = parity;
-    d.bits = 0;
-    small[c] = d;
-}
-
 // ---- leaf resolve: exact dedup of one fixed slot through shared-memory tables, two barriers per bucket ------------------------
 // Persistent CTAs walk the leaf slots with stride gridDim.x.  The slot of bucket n + 1 streams into the second staging
 // buffer with cp.async while bucket n is resolved, so no thread ever waits on HBM between the barriers.
@@ -380,15 +233,13 @@ KC_D void kc_cp_async16(void *smem_dst, const void *gmem_src) {
 KC_D void kc_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 KC_D void kc_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-KC_D void kc_flag_clear(u32 *flags, u32 pos) { atomicAnd(&flags[pos >> 5], ~(1u << (pos & 31))); }
 
-// CLEAR = false: `flags` arrives zeroed and every kept k-mer sets the bit of its smallest position (M scattered REDs).
-// CLEAR = true : `flags` arrives with the bit of every valid window set (written by level 0, one coalesced word per strip);
-//                every atomicMin that folds a duplicate knocks out exactly one position — the larger of the two it compared —
-//                so only the DUPLICATES cost a scattered RED (a genome: ~0 of them) and the kept bits are never touched.
-template <int L, bool COUNTED, bool CLEAR = false>
+// The flags arrive with the bit of every valid window set (written by level 0); every atomicMin that folds a duplicate knocks
+// out exactly one position — the larger of the two it compared — so only the DUPLICATES cost a scattered RED and the kept
+// bits are never touched.  This kernel serves -z Z > 1 (COUNTED); -z 1 takes kc_ksf_resolve2_kernel.
+template <int L, bool COUNTED>
 __global__ void __launch_bounds__(256) kc_ksf_resolve_kernel(const KWord<L> *__restrict__ keys, const u32 *__restrict__ pos, const u32 *__restrict__ cnt,
-                                                             u32 n_leaf, u32 *flags, u32 min_count, kc_ull *n_unique, u32 *status) {
+                                                             u32 n_leaf, KsfFlagPeers fl, u32 min_count, kc_ull *n_unique, u32 *status) {
     constexpr u32 CAP = KSF_LEAF_CAP;
     constexpr u32 T1N = 2 * CAP, T2N = CAP;
     constexpr int KPC = 16 / (int) sizeof(KWord<L>) > 0 ? 16 / (int) sizeof(KWord<L>) : 1;  // keys per 16-byte chunk (L = 1: 2)
@@ -478,7 +329,7 @@ __global__ void __launch_bounds__(256) kc_ksf_resolve_kernel(const KWord<L> *__r
                     } else if (sk[o] == key) {
                         const u32 mine = sp[i];
                         const u32 was = atomicMin(&sp[o], mine);
-                        if (CLEAR) kc_flag_clear(flags, was > mine ? was : mine);
+                        kc_flag_clear_all(fl, was > mine ? was : mine);
                         if (COUNTED) atomicAdd(&occ[o], 1u);
                     } else {
                         u32 s = (u32) (h >> 43) & (T2N - 1);
@@ -491,7 +342,7 @@ __global__ void __launch_bounds__(256) kc_ksf_resolve_kernel(const KWord<L> *__r
                             if (sk[old] == key) {
                                 const u32 mine = sp[i];
                                 const u32 was = atomicMin(&sp[old], mine);
-                                if (CLEAR) kc_flag_clear(flags, was > mine ? was : mine);
+                                kc_flag_clear_all(fl, was > mine ? was : mine);
                                 if (COUNTED) atomicAdd(&occ[old], 1u);
                                 break;
                             }
@@ -511,10 +362,9 @@ __global__ void __launch_bounds__(256) kc_ksf_resolve_kernel(const KWord<L> *__r
                     const u32 i = q * KPC + e;
                     if (!((rep >> (m * KPC + e)) & 1u)) continue;
                     if (!COUNTED || occ[i] >= min_count) {
-                        if (!CLEAR) kc_flag_set(flags, sp[i]);
                         ++kept;
-                    } else if (CLEAR) {
-                        kc_flag_clear(flags, sp[i]);  // too few occurrences: the surviving (smallest) position goes as well
+                    } else {
+                        kc_flag_clear_all(fl, sp[i]);  // too few occurrences: the surviving (smallest) position goes as well
                     }
                 }
             }
@@ -529,145 +379,7 @@ __global__ void __launch_bounds__(256) kc_ksf_resolve_kernel(const KWord<L> *__r
     if ((threadIdx.x & 31) == 0 && kept) atomicAdd(n_unique, (kc_ull) kept);
 }
 
-// ---- leaf resolve, one barrier per leaf (-z 1, clear-the-losers flags) ---------------------------------------------------------
-// With clear-the-losers flags phase C of kc_ksf_resolve_kernel has nothing left to write, so the barrier in front of it only
-// protects the tables from the next leaf's phase A.  Two sets of tables (T1 as u16 indices, T2 as u32 for the CAS) alternate
-// instead: leaf n + 1 fills the set that leaf n - 1 used, and every thread is past leaf n - 1 once it has crossed the barrier
-// of leaf n.
-// STAGES staging buffers form a ring: while leaf n is resolved, leaves n + 1 .. n + STAGES - 1 are in flight (cp.async groups,
-// one per leaf).  With two stages the kernel ran at 2.5 TB/s = exactly the bytes in flight (5 CTAs x 9 KB per SM) over the
-// ~2.7 us a leaf took, i.e. it was bound by DRAM latency through Little's law, not by its instructions.
-// Shared memory per CTA (L = 1): STAGES x 12 KB + 16 KB of tables.
 template <int N> KC_D void kc_cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-template <int L, int STAGES>
-__global__ void __launch_bounds__(256) kc_ksf_resolve1_kernel(const KWord<L> *__restrict__ keys, const u32 *__restrict__ pos, const u32 *__restrict__ cnt,
-                                                              u32 n_leaf, u32 *flags, kc_ull *n_unique, u32 *status) {
-    constexpr u32 CAP = KSF_LEAF_CAP;
-    constexpr u32 T1N = 2 * CAP, T2N = CAP;
-    constexpr int KPC = 16 / (int) sizeof(KWord<L>) > 0 ? 16 / (int) sizeof(KWord<L>) : 1;
-    constexpr int CPK = (int) sizeof(KWord<L>) / 16 > 0 ? (int) sizeof(KWord<L>) / 16 : 1;
-    extern __shared__ __align__(16) unsigned char kc_smem_raw[];
-    KWord<L> *sk0 = reinterpret_cast<KWord<L> *>(kc_smem_raw);
-    u32 *sp0 = reinterpret_cast<u32 *>(sk0 + STAGES * CAP);
-    u32 *T2a = sp0 + STAGES * CAP;                             // [2][T2N]
-    u16 *T1a = reinterpret_cast<u16 *>(T2a + 2 * T2N);         // [2][T1N]
-    const u64 stride = gridDim.x;
-    u64 c = blockIdx.x;
-    if (c >= n_leaf) return;
-    auto leaf_size = [&](u64 leaf) -> u32 {
-        if (leaf >= n_leaf) return 0u;
-        u32 sz = cnt[leaf];
-        if (sz > CAP) {
-            sz = CAP;
-            if (threadIdx.x == 0) status[0] = 1;
-        }
-        return sz;
-    };
-    // one cp.async group per leaf, empty when the CTA has run out of leaves (keeps the group count uniform)
-    auto fetch = [&](u64 bucket, u32 size, int buf) {
-        if (bucket < n_leaf) {
-            const char *gk = reinterpret_cast<const char *>(keys + bucket * CAP);
-            const char *gp = reinterpret_cast<const char *>(pos + bucket * CAP);
-            char *dk = reinterpret_cast<char *>(sk0 + (u32) buf * CAP);
-            char *dp = reinterpret_cast<char *>(sp0 + (u32) buf * CAP);
-            // a thread copies whole units (L = 1: a pair of keys, otherwise one key), so the keys it hashes in phase A are the
-            // ones it fetched itself
-            const u32 n_units = (size + KPC - 1) / KPC, pchunks = (size * 4 + 15) / 16;
-            for (u32 u = threadIdx.x; u < n_units; u += 256) {
-#pragma unroll
-                for (int cc = 0; cc < CPK; ++cc) kc_cp_async16(dk + 16 * (u * CPK + cc), gk + 16 * (u * CPK + cc));
-            }
-            for (u32 q = threadIdx.x; q < pchunks; q += 256) kc_cp_async16(dp + 16 * q, gp + 16 * q);
-        }
-        kc_cp_async_commit();
-    };
-    u32 sz[STAGES];  // sz[i] = size of leaf c + i * stride
-#pragma unroll
-    for (int i = 0; i < STAGES - 1; ++i) {
-        sz[i] = leaf_size(c + (u64) i * stride);
-        fetch(c + (u64) i * stride, sz[i], i);
-    }
-    int buf = 0, par = 0;
-    u32 kept = 0;
-    while (true) {
-        const u64 c_far = c + (u64) (STAGES - 1) * stride;
-        sz[STAGES - 1] = leaf_size(c_far);
-        const u32 size = sz[0];
-        KWord<L> *sk = sk0 + (u32) buf * CAP;
-        u32 *sp = sp0 + (u32) buf * CAP;
-        u32 *T2 = T2a + (u32) par * T2N;
-        u16 *T1 = T1a + (u32) par * T1N;
-        kc_cp_async_wait_group<STAGES - 2>();  // the thread's own chunks of leaf c have landed
-        const u32 n_chunk_items = (size + KPC - 1) / KPC;
-        reinterpret_cast<uint4 *>(T2)[threadIdx.x] = make_uint4(KC_NONE, KC_NONE, KC_NONE, KC_NONE);  // T2N = 256 x 4 slots
-        // A: some item of every key group wins the group's T1 slot (plain 16-bit stores)
-        for (u32 q = threadIdx.x; q < n_chunk_items; q += 256) {
-#pragma unroll
-            for (int e = 0; e < KPC; ++e) {
-                const u32 i = q * KPC + e;
-                if (i < size) {
-                    u64 h = 0;
-#pragma unroll
-                    for (int w = 0; w < L; ++w) h = (h ^ sk[i].w[w]) * 0xD6E8FEB86659FD93ULL;
-                    T1[h >> 53] = (u16) i;
-                }
-            }
-        }
-        __syncthreads();
-        {   // every thread is past phase B of the leaf that used the ring slot behind the newest one
-            int far = buf + STAGES - 1;
-            if (far >= STAGES) far -= STAGES;
-            fetch(c_far, sz[STAGES - 1], far);
-        }
-        // B: winners represent their key; a duplicate folds its position and clears the larger of the two
-        for (u32 q = threadIdx.x; q < n_chunk_items; q += 256) {
-#pragma unroll
-            for (int e = 0; e < KPC; ++e) {
-                const u32 i = q * KPC + e;
-                if (i >= size) continue;
-                const KWord<L> key = sk[i];
-                u64 h = 0;
-#pragma unroll
-                for (int w = 0; w < L; ++w) h = (h ^ key.w[w]) * 0xD6E8FEB86659FD93ULL;
-                const u32 o = T1[h >> 53];
-                if (o == i) {
-                    ++kept;
-                } else if (sk[o] == key) {
-                    const u32 mine = sp[i];
-                    const u32 was = atomicMin(&sp[o], mine);
-                    kc_flag_clear(flags, was > mine ? was : mine);
-                } else {
-                    u32 s = (u32) (h >> 43) & (T2N - 1);
-                    while (true) {
-                        const u32 old = atomicCAS(&T2[s], KC_NONE, i);
-                        if (old == KC_NONE) {
-                            ++kept;
-                            break;
-                        }
-                        if (sk[old] == key) {
-                            const u32 mine = sp[i];
-                            const u32 was = atomicMin(&sp[old], mine);
-                            kc_flag_clear(flags, was > mine ? was : mine);
-                            break;
-                        }
-                        s = (s + 1) & (T2N - 1);
-                    }
-                }
-            }
-        }
-        if (c + stride >= n_leaf) break;
-        c += stride;
-#pragma unroll
-        for (int i = 0; i < STAGES - 1; ++i) sz[i] = sz[i + 1];
-        buf = buf + 1 == STAGES ? 0 : buf + 1;
-        par ^= 1;
-    }
-    kc_cp_async_wait_group<0>();  // only empty groups are left
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) kept += __shfl_down_sync(0xFFFFFFFFu, kept, o);
-    if ((threadIdx.x & 31) == 0 && kept) atomicAdd(n_unique, (kc_ull) kept);
-}
 
 // ---- one-barrier leaf resolve with the thread's items staged in registers ------------------------------------------------------
 // The stage sweep of kc_ksf_resolve1_kernel (profiles/r01h_variant_sweep2.json) showed its time going with 1 / (CTAs per SM):
@@ -685,7 +397,7 @@ KC_D void kc_cp_async8(void *smem_dst, const void *gmem_src) {
 
 template <int L, int THREADS, bool BAL = false>
 __global__ void __launch_bounds__(THREADS) kc_ksf_resolve2_kernel(const KWord<L> *__restrict__ keys, const u32 *__restrict__ pos, const u32 *__restrict__ cnt,
-                                                                  u32 n_leaf, u32 *flags, kc_ull *n_unique, u32 *status) {
+                                                                  u32 n_leaf, KsfFlagPeers fl, kc_ull *n_unique, u32 *status) {
     constexpr u32 CAP = KSF_LEAF_CAP;
     constexpr u32 T1N = 2 * CAP, T2N = CAP;
     constexpr int KPC = (BAL && L == 1) ? 1 : (16 / (int) sizeof(KWord<L>) > 0 ? 16 / (int) sizeof(KWord<L>) : 1);
@@ -789,7 +501,7 @@ __global__ void __launch_bounds__(THREADS) kc_ksf_resolve2_kernel(const KWord<L>
             } else if (sk[o[m]] == key[m]) {
                 const u32 mine = sp[i];
                 const u32 was = atomicMin(&sp[o[m]], mine);
-                kc_flag_clear(flags, was > mine ? was : mine);
+                kc_flag_clear_all(fl, was > mine ? was : mine);
             } else {
                 u32 s = h2[m];
                 while (true) {
@@ -801,7 +513,7 @@ __global__ void __launch_bounds__(THREADS) kc_ksf_resolve2_kernel(const KWord<L>
                     if (sk[old] == key[m]) {
                         const u32 mine = sp[i];
                         const u32 was = atomicMin(&sp[old], mine);
-                        kc_flag_clear(flags, was > mine ? was : mine);
+                        kc_flag_clear_all(fl, was > mine ? was : mine);
                         break;
                     }
                     s = (s + 1) & (T2N - 1);
@@ -836,7 +548,8 @@ __global__ void __launch_bounds__(THREADS) kc_ksf_resolve2_kernel(const KWord<L>
 template <int L, int TILE, int MINB, int THREADS = 256>
 __global__ void __launch_bounds__(THREADS, MINB) kc_ksf_scatter_pf_kernel(const KWord<L> *__restrict__ ksrc, const u32 *__restrict__ psrc, KWord<L> *__restrict__ kdst,
                                                                 u32 *__restrict__ pdst, const u32 *__restrict__ P_size, const u32 *__restrict__ tile_prefix,
-                                                                u32 nP, u64 capP, u32 tiles_per_cta, int shift, int bits, u32 *C_cnt, u32 capC, u32 *status) {
+                                                                u32 nP, u64 capP, u32 tiles_per_cta, int shift, int bits, u32 *C_cnt, u32 capC, u32 *status,
+                                                                u32 pdiv = 1) {
     constexpr int ITEMS = TILE / THREADS;
     extern __shared__ __align__(16) unsigned char kc_smem_raw[];
     KWord<L> *in_k = reinterpret_cast<KWord<L> *>(kc_smem_raw);
@@ -916,9 +629,10 @@ __global__ void __launch_bounds__(THREADS, MINB) kc_ksf_scatter_pf_kernel(const 
         if (threadIdx.x < 256) {
             loff[threadIdx.x] = p;
             u32 gb = 0;
-            if (c) gb = atomicAdd(&C_cnt[((u64) b << bits) + threadIdx.x], c);
+            const u64 child = ((u64) (b / pdiv) << bits) + threadIdx.x;  // pdiv parents (one per sender) share a bucket's children
+            if (c) gb = atomicAdd(&C_cnt[child], c);
             const u32 room = gb < capC ? capC - gb : 0u;
-            dbase[threadIdx.x] = (((u64) b << bits) + threadIdx.x) * capC + gb - p;
+            dbase[threadIdx.x] = child * capC + gb - p;
             qlim[threadIdx.x] = p + (c < room ? c : room);
             cnt[threadIdx.x] = 0;
         }
@@ -960,6 +674,81 @@ __global__ void __launch_bounds__(THREADS, MINB) kc_ksf_scatter_pf_kernel(const 
     if (over) status[0] = 1;
 }
 
+// ---- host side -----------------------------------------------------------------------------------------------------------------
+template <int L> struct KsfKernels {  // the kernel instances this construction launches, their shared memory, the per-device opt-in
+    typedef KsCfg<L> Cfg;
+    static constexpr int TILE1 = Cfg::TILE;
+    static constexpr int THREADS1 = 512;
+    static int smem0() { return Cfg::EX_TILE * ((int) sizeof(KWord<L>) + 4); }
+    static int smem1() { return TILE1 * (2 * ((int) sizeof(KWord<L>) + 4) + 2); }
+    static int smem_r(bool counted) {
+        return counted ? (int) KSF_LEAF_CAP * (16 * L + 24) : (int) KSF_LEAF_CAP * (2 * (8 * L + 4) + 16);
+    }
+    struct Dev {
+        int n_sm = 0, occ_r[2] = {0, 0};
+    };
+    static const Dev &prepare() {
+        static KcDevOnce once;
+        static Dev dev[KC_MAX_DEVICES];
+        const int d = once.run([&](int dv) {
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter0_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem0()));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter0_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem0()));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_pf_kernel<L, TILE1, 2, THREADS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1()));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve2_kernel<L, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r(false)));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r(true)));
+            dev[dv].n_sm = kc_sm_count(dv);
+            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev[dv].occ_r[0], kc_ksf_resolve2_kernel<L, 256>, 256, smem_r(false)));
+            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev[dv].occ_r[1], kc_ksf_resolve_kernel<L, true>, 256, smem_r(true)));
+        });
+        return dev[d];
+    }
+};
+
+// One level >= 1: the nP parent slots (capP items each, fill counts cnt_par) -> children of capC items (counters cnt_next).
+// pdiv > 1: pdiv consecutive parents are the per-sender sub-slots of ONE bucket and share its children (multi-GPU level 1).
+template <int L>
+void kc_ksf_level(CudaExec &ex, const KWord<L> *ksrc, const u32 *psrc, KWord<L> *kdst, u32 *pdst, const u32 *cnt_par, u32 nP, u64 capP, u32 *cnt_next,
+                  u64 capC, int shift, int bits, u64 items_ub, u32 *status, kc_ull *m_cell, const KsfTuning &tune, u32 pdiv = 1) {
+    typedef KsfKernels<L> KK;
+    cudaStream_t st = ex.stream;
+    const size_t mark = ex.arena->mark();
+    u32 *P_size = ex.alloc<u32>(nP);
+    u32 *tile_prefix = ex.alloc<u32>((u64) nP + 1);
+    kc_ksf_prep_kernel<<<(unsigned) kc_div_up((u64) nP + 1, 256), 256, 0, st>>>(cnt_par, nP, (u32) capP, (u32) KK::TILE1, P_size, tile_prefix, status, m_cell);
+    ++ex.launches;
+    ex.exclusive_scan_nosync(tile_prefix, tile_prefix, (u64) nP + 1);
+    const u32 max_ctas = tune.max_ctas > 0 ? (u32) tune.max_ctas : 148 * 16;
+    const u64 tiles_ub = items_ub / KK::TILE1 + nP + 1;
+    const u32 tiles_per_cta = (u32) kc_div_up(tiles_ub, max_ctas);
+    const u32 ctas = (u32) kc_div_up(tiles_ub, tiles_per_cta);
+    {
+        CudaExec::Scope sc(ex, KP_SORT_SCATTER, 2 * items_ub * (sizeof(KWord<L>) + 4));
+        kc_ksf_scatter_pf_kernel<L, KK::TILE1, 2, KK::THREADS1><<<ctas, KK::THREADS1, KK::smem1(), st>>>(ksrc, psrc, kdst, pdst, P_size, tile_prefix, nP, capP,
+                                                                                                      tiles_per_cta, shift, bits, cnt_next, (u32) capC,
+                                                                                                      status, pdiv);
+        ++ex.launches;
+        KC_CUDA(cudaGetLastError());
+    }
+    ex.arena->release(mark);  // stream order keeps P_size / tile_prefix alive until the scatter has run
+}
+
+// Leaf slots (KSF_LEAF_CAP items each) -> losers cleared in fl, *n_unique += kept k-mers.
+template <int L>
+void kc_ksf_resolve(CudaExec &ex, const KWord<L> *keys, const u32 *pos, const u32 *cnt, u64 n_leaf, const KsfFlagPeers &fl, int min_freq, kc_ull *n_unique,
+                    u32 *status, u64 items_ub) {
+    typedef KsfKernels<L> KK;
+    if (n_leaf >= 0xFFFFFFFFULL) KC_THROW(KC_ERR_TOO_LARGE, "too many leaf buckets");
+    const typename KK::Dev &dv = KK::prepare();
+    const bool counted = min_freq > 1;
+    const u32 fit = (u32) (dv.n_sm * (dv.occ_r[counted] > 0 ? dv.occ_r[counted] : 1));
+    const u32 grid = (u32) n_leaf < fit ? (u32) n_leaf : fit;
+    CudaExec::Scope sc(ex, KP_KS_RESOLVE, items_ub * (sizeof(KWord<L>) + 4));
+    if (counted) kc_ksf_resolve_kernel<L, true><<<grid, 256, KK::smem_r(true), ex.stream>>>(keys, pos, cnt, (u32) n_leaf, fl, (u32) min_freq, n_unique, status);
+    else kc_ksf_resolve2_kernel<L, 256><<<grid, 256, KK::smem_r(false), ex.stream>>>(keys, pos, cnt, (u32) n_leaf, fl, n_unique, status);
+    ++ex.launches;
+    KC_CUDA(cudaGetLastError());
+}
+
 // Launches the whole construction on ex.stream and returns without synchronising.
 //   cells[0] += distinct k-mers with >= min_freq occurrences, cells[2] = M (k-mer windows), low word of cells[3] = overflow status;
 //   flags: zeroed bit array over the n_bytes positions (see kc_kmerset_build).
@@ -968,9 +757,11 @@ template <int L>
 bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, int min_freq, u32 *flags, u64 *cells,
                            const KsfTuning &tune, KsfPlan *plan_out = nullptr, InputChunks *chunks = nullptr) {
     typedef KsCfg<L> Cfg;
+    typedef KsfKernels<L> KK;
     const KsfPlan pl = kc_ksf_plan(n_bytes, tune);
     if (plan_out) *plan_out = pl;
     if (!pl.ok) return false;
+    KK::prepare();
     cudaStream_t st = ex.stream;
     const size_t base_mark = ex.arena->mark();
     const u64 item_bytes = sizeof(KWord<L>) + 4;
@@ -986,43 +777,7 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
     ex.fill_bytes(cnt_all, 0, n_cnt * 4);
     u32 *status = reinterpret_cast<u32 *>(cells + 3);
     kc_ull *m_cell = reinterpret_cast<kc_ull *>(cells + 2);
-
-    const int smem0 = Cfg::EX_TILE * ((int) sizeof(KWord<L>) + 4);
-    const int tv = tune.tile_variant;
-    const int tile1 = (tv == 1 || tv == 4) ? Cfg::TILE / 2 : (tv == 2 ? Cfg::TILE * 3 / 4 : Cfg::TILE);
-    const bool pf = tv >= 3;  // input tile double-buffered in shared memory
-    const int smem1 = tile1 * ((pf ? 2 : 1) * ((int) sizeof(KWord<L>) + 4) + 2);
-    const bool clear_flags = tune.resolve >= 2;  // level 0 writes the valid-window bits, the resolve clears the losers
-    const bool counted = min_freq > 1;
-    constexpr int CA = KSF_LEAF_CAP;
-    const int per_item = (int) sizeof(KWord<L>) + 12 + 4;
-    const int smem_r = CA * (per_item + (counted ? 4 : 0));
-    static bool attr_done = false;
-    static int occ_r[2] = {0, 0}, n_sm = 0;
-    if (!attr_done) {
-        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter0_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem0));
-        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_kernel<L, Cfg::TILE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::TILE * ((int) sizeof(KWord<L>) + 4 + 2)));
-        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_kernel<L, Cfg::TILE / 2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::TILE / 2 * ((int) sizeof(KWord<L>) + 4 + 2)));
-        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_kernel<L, Cfg::TILE * 3 / 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::TILE * 3 / 4 * ((int) sizeof(KWord<L>) + 4 + 2)));
-        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter0_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KsCfg<1>::EX_TILE * 12));
-        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_pf_kernel<L, Cfg::TILE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::TILE * (2 * ((int) sizeof(KWord<L>) + 4) + 2)));
-        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_pf_kernel<L, Cfg::TILE, 2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::TILE * (2 * ((int) sizeof(KWord<L>) + 4) + 2)));
-        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_pf_kernel<L, Cfg::TILE / 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg::TILE / 2 * (2 * ((int) sizeof(KWord<L>) + 4) + 2)));
-        KC_CUDA(cudaFuncSetAttribute(kc_ks_resolve_hash_kernel<L, CA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CA * per_item));
-        KC_CUDA(cudaFuncSetAttribute(kc_ks_resolve_hash_kernel<L, CA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CA * (per_item + 4)));
-        int dev = 0;
-        KC_CUDA(cudaGetDevice(&dev));
-        KC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r[0], kc_ks_resolve_hash_kernel<L, CA, false>, 256, CA * per_item));
-        KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r[1], kc_ks_resolve_hash_kernel<L, CA, true>, 256, CA * (per_item + 4)));
-        attr_done = true;
-    }
+    const KsfFlagPeers fl = kc_ksf_own_flags(flags);
 
     // ---- level 0 ----
     u32 *cnt_cur = cnt_all;
@@ -1041,213 +796,73 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
             if (t1 <= t0) continue;
             const u64 part_bytes = std::min<u64>(n_bytes, (u64) t1 * Cfg::EX_TILE) - (u64) t0 * Cfg::EX_TILE;
             CudaExec::Scope sc(ex, KP_KS_SCATTER0, part_bytes + part_bytes * item_bytes);
-            bool split = false;
-            if constexpr (L == 1) {
-                if (tune.split0 && !clear_flags) {
-                    split = true;
-                    kc_ksf_scatter0_split_kernel<<<t1 - t0, 512, smem0, st>>>(seq, n_bytes, k, complements ? 1 : 0, 64 * L - pl.cum[0], pl.bits[0], cnt_cur,
-                                                                              (u32) pl.cap[0], kb[0], pb[0], status, t0);
-                }
-            }
-            if (!split)
-                kc_ksf_scatter0_kernel<L><<<t1 - t0, Cfg::EX_THREADS, smem0, st>>>(seq, n_bytes, k, complements ? 1 : 0, 64 * L - pl.cum[0], pl.bits[0], cnt_cur,
-                                                                                 (u32) pl.cap[0], kb[0], pb[0], status, t0, clear_flags ? flags : nullptr,
-                                                                                 (u32) (kc_div_up(n_bytes, (u64) 32) + 1));  // = kc_runs_flag_words(n_bytes)
+            kc_ksf_scatter0_kernel<L, false><<<t1 - t0, Cfg::EX_THREADS, KK::smem0(), st>>>(seq, n_bytes, k, complements ? 1 : 0, 64 * L - pl.cum[0], pl.bits[0],
+                                                                                         cnt_cur, (u32) pl.cap[0], kb[0], pb[0], status, t0, fl,
+                                                                                         (u32) (kc_div_up(n_bytes, (u64) 32) + 1));  // = kc_runs_flag_words(n_bytes)
             ++ex.launches;
             KC_CUDA(cudaGetLastError());
         }
         if (chunks) chunks->waited = true;
     }
     // ---- levels >= 1 ----
-    const u32 max_ctas = tune.max_ctas > 0 ? (u32) tune.max_ctas : 148 * 8;
     for (int lv = 1; lv < pl.n_levels; ++lv) {
         const u32 nP = (u32) (1ULL << pl.cum[lv - 1]);
-        const size_t mark = ex.arena->mark();
-        u32 *P_size = ex.alloc<u32>(nP);
-        u32 *tile_prefix = ex.alloc<u32>((u64) nP + 1);
-        kc_ksf_prep_kernel<<<(unsigned) kc_div_up((u64) nP + 1, 256), 256, 0, st>>>(cnt_cur, nP, (u32) pl.cap[lv - 1], (u32) tile1, P_size, tile_prefix,
-                                                                                  status, lv == 1 ? m_cell : nullptr);
-        ++ex.launches;
-        ex.exclusive_scan_nosync(tile_prefix, tile_prefix, (u64) nP + 1);
         u32 *cnt_next = cnt_cur + nP;
-        const u64 tiles_ub = n_bytes / tile1 + nP + 1;
-        const u32 tiles_per_cta = (u32) kc_div_up(tiles_ub, max_ctas);
-        const u32 ctas = (u32) kc_div_up(tiles_ub, tiles_per_cta);
-        {
-            CudaExec::Scope sc(ex, KP_SORT_SCATTER, 2 * n_bytes * item_bytes);
-            if (tv == 3) kc_ksf_scatter_pf_kernel<L, Cfg::TILE, 2><<<ctas, 256, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
-                                                               pl.cap[lv - 1], tiles_per_cta, 64 * L - pl.cum[lv], pl.bits[lv], cnt_next, (u32) pl.cap[lv],
-                                                               status);
-            else if (tv == 5) kc_ksf_scatter_pf_kernel<L, Cfg::TILE, 2, 512><<<ctas, 512, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
-                                                               pl.cap[lv - 1], tiles_per_cta, 64 * L - pl.cum[lv], pl.bits[lv], cnt_next, (u32) pl.cap[lv],
-                                                               status);
-            else if (tv == 4) kc_ksf_scatter_pf_kernel<L, Cfg::TILE / 2, 4><<<ctas, 256, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
-                                                               pl.cap[lv - 1], tiles_per_cta, 64 * L - pl.cum[lv], pl.bits[lv], cnt_next, (u32) pl.cap[lv],
-                                                               status);
-            else if (tv == 1) kc_ksf_scatter_kernel<L, Cfg::TILE / 2, 5><<<ctas, 256, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
-                                                               pl.cap[lv - 1], tiles_per_cta, 64 * L - pl.cum[lv], pl.bits[lv], cnt_next, (u32) pl.cap[lv],
-                                                               status);
-            else if (tv == 2) kc_ksf_scatter_kernel<L, Cfg::TILE * 3 / 4, 4><<<ctas, 256, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
-                                                               pl.cap[lv - 1], tiles_per_cta, 64 * L - pl.cum[lv], pl.bits[lv], cnt_next, (u32) pl.cap[lv],
-                                                               status);
-            else kc_ksf_scatter_kernel<L, Cfg::TILE, 3><<<ctas, 256, smem1, st>>>(kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP,
-                                                               pl.cap[lv - 1], tiles_per_cta, 64 * L - pl.cum[lv], pl.bits[lv], cnt_next, (u32) pl.cap[lv],
-                                                               status);
-            ++ex.launches;
-            KC_CUDA(cudaGetLastError());
-        }
+        kc_ksf_level<L>(ex, kb[(lv - 1) & 1], pb[(lv - 1) & 1], kb[lv & 1], pb[lv & 1], cnt_cur, nP, pl.cap[lv - 1], cnt_next, pl.cap[lv], 64 * L - pl.cum[lv],
+                        pl.bits[lv], n_bytes, status, lv == 1 ? m_cell : nullptr, tune);
         cnt_cur = cnt_next;
-        ex.arena->release(mark);  // stream order keeps P_size / tile_prefix alive until the scatter has run
     }
     // ---- leaves -> hash resolve ----
     const int last = pl.n_levels - 1;
-    if (pl.n_leaf >= 0xFFFFFFFFULL) KC_THROW(KC_ERR_TOO_LARGE, "too many leaf buckets");
-    const u32 n_small = (u32) pl.n_leaf;
-    kc_ull *n_unique = reinterpret_cast<kc_ull *>(cells);
     if (pl.n_levels == 1) {  // M has not been added up by a prep kernel
         const u32 *cc = cnt_cur;
-        const u64 nl = pl.n_leaf;
-        ex.for_each(nl, [=] __device__(u64 i) {
+        ex.for_each(pl.n_leaf, [=] __device__(u64 i) {
             const u32 c = cc[i] < KSF_LEAF_CAP ? cc[i] : KSF_LEAF_CAP;
             if (c) atomicAdd(m_cell, (kc_ull) c);
         });
     }
-    if (tune.resolve >= 6 && !counted) {
-        const int smem4 = (int) KSF_LEAF_CAP * (2 * (8 * L + 4) + 16);
-        static bool attr4_done = false;
-        static int occ4[2] = {0, 0};
-        if (!attr4_done) {
-            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve2_kernel<L, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve2_kernel<L, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve2_kernel<L, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4[0], kc_ksf_resolve2_kernel<L, 256>, 256, smem4));
-            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4[1], kc_ksf_resolve2_kernel<L, 512>, 512, smem4));
-            attr4_done = true;
-        }
-        const int wide = tune.resolve == 7 ? 1 : 0;
-        const u32 fit = (u32) (n_sm * (occ4[wide] > 0 ? occ4[wide] : 1));
-        const u32 grid = n_small < fit ? n_small : fit;
-        CudaExec::Scope sc(ex, KP_KS_RESOLVE, n_bytes * item_bytes);
-        if (tune.resolve == 8) kc_ksf_resolve2_kernel<L, 256, true><<<grid, 256, smem4, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, n_unique, status);
-        else if (wide) kc_ksf_resolve2_kernel<L, 512><<<grid, 512, smem4, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, n_unique, status);
-        else kc_ksf_resolve2_kernel<L, 256><<<grid, 256, smem4, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, n_unique, status);
-        ++ex.launches;
-        KC_CUDA(cudaGetLastError());
-    } else if (tune.resolve >= 3 && !counted) {
-        const int stages = tune.resolve == 3 ? 2 : (tune.resolve == 4 ? 3 : 4);
-        // per ring stage: keys + positions of one leaf; tables: T2 x2 (u32), T1 x2 (two u16 slots per item)
-        const int smem3 = (int) KSF_LEAF_CAP * (stages * (8 * L + 4) + 8 + 8);
-        static bool attr3_done = false;
-        static int occ3[3] = {0, 0, 0};
-        if (!attr3_done) {
-            const int per = 8 * L + 4;
-            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve1_kernel<L, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (2 * per + 16)));
-            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve1_kernel<L, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (3 * per + 16)));
-            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve1_kernel<L, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (4 * per + 16)));
-            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3[0], kc_ksf_resolve1_kernel<L, 2>, 256, (int) KSF_LEAF_CAP * (2 * per + 16)));
-            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3[1], kc_ksf_resolve1_kernel<L, 3>, 256, (int) KSF_LEAF_CAP * (3 * per + 16)));
-            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3[2], kc_ksf_resolve1_kernel<L, 4>, 256, (int) KSF_LEAF_CAP * (4 * per + 16)));
-            attr3_done = true;
-        }
-        const int occ = occ3[stages - 2];
-        const u32 fit = (u32) (n_sm * (occ > 0 ? occ : 1));
-        const u32 grid = n_small < fit ? n_small : fit;
-        CudaExec::Scope sc(ex, KP_KS_RESOLVE, n_bytes * item_bytes);
-        if (stages == 2) kc_ksf_resolve1_kernel<L, 2><<<grid, 256, smem3, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, n_unique, status);
-        else if (stages == 3) kc_ksf_resolve1_kernel<L, 3><<<grid, 256, smem3, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, n_unique, status);
-        else kc_ksf_resolve1_kernel<L, 4><<<grid, 256, smem3, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, n_unique, status);
-        ++ex.launches;
-        KC_CUDA(cudaGetLastError());
-    } else if (tune.resolve >= 1) {
-        const int smem2 = (int) KSF_LEAF_CAP * (16 * L + 20 + (counted ? 4 : 0));
-        static bool attr2_done = false;
-        static int occ2[2] = {0, 0};
-        if (!attr2_done) {
-            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (16 * L + 20)));
-            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (16 * L + 24)));
-            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (16 * L + 20)));
-            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (16 * L + 24)));
-            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2[0], kc_ksf_resolve_kernel<L, false>, 256, (int) KSF_LEAF_CAP * (16 * L + 20)));
-            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2[1], kc_ksf_resolve_kernel<L, true>, 256, (int) KSF_LEAF_CAP * (16 * L + 24)));
-            attr2_done = true;
-        }
-        const u32 fit = (u32) (n_sm * (occ2[counted] > 0 ? occ2[counted] : 1));
-        const u32 grid = n_small < fit ? n_small : fit;
-        CudaExec::Scope sc(ex, KP_KS_RESOLVE, n_bytes * item_bytes);
-        if (counted && clear_flags)
-            kc_ksf_resolve_kernel<L, true, true><<<grid, 256, smem2, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, (u32) min_freq, n_unique, status);
-        else if (counted)
-            kc_ksf_resolve_kernel<L, true><<<grid, 256, smem2, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, (u32) min_freq, n_unique, status);
-        else if (clear_flags)
-            kc_ksf_resolve_kernel<L, false, true><<<grid, 256, smem2, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, (u32) min_freq, n_unique, status);
-        else
-            kc_ksf_resolve_kernel<L, false><<<grid, 256, smem2, st>>>(kb[last & 1], pb[last & 1], cnt_cur, n_small, flags, (u32) min_freq, n_unique, status);
-        ++ex.launches;
-        KC_CUDA(cudaGetLastError());
-    } else {
-        SortBucket *small = ex.alloc<SortBucket>(pl.n_leaf);
-        kc_ksf_leaf_kernel<<<(unsigned) kc_div_up(pl.n_leaf, 256), 256, 0, st>>>(cnt_cur, pl.n_leaf, KSF_LEAF_CAP, (u8) (last & 1), small, status);
-        ++ex.launches;
-        const u32 fit = (u32) (n_sm * (occ_r[counted] > 0 ? occ_r[counted] : 1));
-        const u32 grid = n_small < fit ? n_small : fit;
-        CudaExec::Scope sc(ex, KP_KS_RESOLVE, n_bytes * item_bytes);
-        if (counted)
-            kc_ks_resolve_hash_kernel<L, CA, true><<<grid, 256, smem_r, st>>>(kb[0], kb[1], pb[0], pb[1], small, n_small, 0u, (u32) CA, flags,
-                                                                              (u32) min_freq, n_unique);
-        else
-            kc_ks_resolve_hash_kernel<L, CA, false><<<grid, 256, smem_r, st>>>(kb[0], kb[1], pb[0], pb[1], small, n_small, 0u, (u32) CA, flags,
-                                                                               (u32) min_freq, n_unique);
-        ++ex.launches;
-        KC_CUDA(cudaGetLastError());
-    }
+    kc_ksf_resolve<L>(ex, kb[last & 1], pb[last & 1], cnt_cur, pl.n_leaf, fl, min_freq, reinterpret_cast<kc_ull *>(cells), status, n_bytes);
     ex.arena->release(base_mark);
     return true;
 }
 
-// Multi-GPU owner side (kc_p2p_resolve): the rank's level-0 buckets arrive complete and back to back in the receive buffer
-// (sh->pre_off / pre_size).  The same fixed-slot levels + leaf resolve as above take over from there, instead of the
-// histogram-based levels of kmerset.cuh: no counting passes and no host read-backs between the kernels.  Returns false —
-// with NOTHING written to `flags` — when the plan does not apply or a slot overflowed (checked on the device before the
-// resolve is launched); the caller then runs the exact construction.
+// Level 0 of rank `rank` over its tile slice: items into the owners' sub-slots (dst tables), valid-window words into every
+// rank's flags, fill counts into cnt0[n_digits] (this rank's own counters, zeroed here).
 template <int L>
-bool kc_kmerset_resolve_fast(CudaExec &ex, int k, int min_freq, u32 *flags, const KsShard *sh, const KsfTuning &tune, u64 *n_kept_out) {
+void kc_ksf_group_scatter0(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, const KsfGroupPlan &g, int rank, u32 *cnt0, u32 *status,
+                           KWord<L> *const *dst_k, u32 *const *dst_p, const KsfFlagPeers &all_flags) {
     typedef KsCfg<L> Cfg;
-    (void) k;
-    const u32 nP0 = sh->n_pre;
-    const u64 total = sh->n_items;
-    if (!tune.enabled || nP0 == 0 || total < tune.min_items) return false;
-    u64 max0 = 0;
-    for (u32 i = 0; i < nP0; ++i) max0 = sh->pre_size[i] > max0 ? sh->pre_size[i] : max0;
-    if (max0 >= 0xFFFFFFF0ULL) return false;
-    int sub_bits = 0;
-    while (sub_bits < 32 && (max0 >> sub_bits) > tune.leaf_target) ++sub_bits;
-    if (sub_bits == 0) return false;
-    const int levels = (sub_bits + 7) / 8;
-    if (levels > KSF_MAX_LEVELS - 1) return false;
-    int bits[KSF_MAX_LEVELS], cum[KSF_MAX_LEVELS];
-    u64 cap[KSF_MAX_LEVELS], slots[2] = {1, 1};
-    int c = 0;
-    for (int i = 0; i < levels; ++i) {
-        bits[i] = sub_bits / levels + (i < sub_bits % levels ? 1 : 0);
-        c += bits[i];
-        cum[i] = c;
-        const double mean = (double) max0 / (double) (1ULL << c);
-        u64 cp = (u64) std::ceil(mean + tune.sigmas * std::sqrt(mean) + (tune.sigmas > 0 ? 0.02 * mean + 64.0 : 0.0));
-        cp = (cp + 31) / 32 * 32;
-        if (i == levels - 1) cp = KSF_LEAF_CAP;
-        cap[i] = cp;
-        const u64 need = ((u64) nP0 << c) * cp;
-        if (need > slots[i & 1]) slots[i & 1] = need;
-    }
-    const u64 n_leaf = (u64) nP0 << cum[levels - 1];
-    if (n_leaf >= 0xFFFFFFFFULL) return false;
-    cudaStream_t st = ex.stream;
+    typedef KsfKernels<L> KK;
+    KK::prepare();
+    ex.fill_bytes(cnt0, 0, (size_t) g.n_digits * 4);
+    const u32 t0 = g.tile_begin(rank), t1 = g.tile_begin(rank + 1);
+    if (t1 <= t0) return;
+    const u64 part_bytes = std::min<u64>(n_bytes, (u64) t1 * Cfg::EX_TILE) - (u64) t0 * Cfg::EX_TILE;
+    CudaExec::Scope sc(ex, KP_KS_SCATTER0, part_bytes + part_bytes * (sizeof(KWord<L>) + 4));
+    kc_ksf_scatter0_kernel<L, true><<<t1 - t0, Cfg::EX_THREADS, KK::smem0(), ex.stream>>>(seq, n_bytes, k, complements ? 1 : 0, 64 * L - g.pl.cum[0], g.pl.bits[0], cnt0,
+                                                                                       (u32) g.cap_sub, nullptr, nullptr, status, t0, all_flags,
+                                                                                       (u32) kc_div_up(n_bytes, (u64) 32), dst_k, dst_p);
+    ++ex.launches;
+    KC_CUDA(cudaGetLastError());
+}
+
+// Owner side: the sub-slots of this rank's digits (recv_k / recv_p: [digit - dig_begin][sender] x cap_sub items, fill counts
+// sub_cnt in the same order, already clamped to cap_sub) -> levels 1.. -> leaf resolve, losers cleared in every rank's flags.
+// cells: {kept (+=), -, M of this rank's digits (+=), status (low word)}.
+template <int L>
+void kc_ksf_group_resolve(CudaExec &ex, int min_freq, const KsfGroupPlan &g, int rank, const KWord<L> *recv_k, const u32 *recv_p, const u32 *sub_cnt,
+                          const KsfFlagPeers &all_flags, u64 *cells, const KsfTuning &tune) {
+    const KsfPlan &pl = g.pl;
+    const u32 dig_n = g.dig_begin(rank + 1) - g.dig_begin(rank);
+    if (dig_n == 0) return;
     const size_t base_mark = ex.arena->mark();
-    u64 n_cnt = 0;
-    for (int i = 0; i < levels; ++i) n_cnt += (u64) nP0 << cum[i];
-    {   // the slots must fit what is left of the arena (the caller falls back to the exact construction otherwise)
-        const u64 need = (slots[0] + slots[1]) * (sizeof(KWord<L>) + 4) + n_cnt * 4 + ((u64) nP0 << cum[levels - 1]) * 8 + (1u << 20);
-        if (ex.arena->off + need > ex.arena->top) return false;
+    u32 *status = reinterpret_cast<u32 *>(cells + 3);
+    kc_ull *m_cell = reinterpret_cast<kc_ull *>(cells + 2);
+    u64 slots[2] = {1, 1}, n_cnt = 0;
+    for (int lv = 1; lv < pl.n_levels; ++lv) {
+        const u64 nb = (u64) dig_n << (pl.cum[lv] - pl.cum[0]);
+        slots[lv & 1] = std::max<u64>(slots[lv & 1], nb * pl.cap[lv]);
+        n_cnt += nb;
     }
     KWord<L> *kb[2];
     u32 *pb[2];
@@ -1257,92 +872,23 @@ bool kc_kmerset_resolve_fast(CudaExec &ex, int k, int min_freq, u32 *flags, cons
     }
     u32 *cnt_all = ex.alloc<u32>(n_cnt);
     ex.fill_bytes(cnt_all, 0, n_cnt * 4);
-    u64 *d_off = ex.alloc<u64>(nP0);
-    u32 *d_size = ex.alloc<u32>(nP0);
-    u64 *cells = ex.alloc<u64>(2);  // [0] kept, [1] low word = overflow status
-    ex.fill_bytes(cells, 0, 16);
-    u32 *status = reinterpret_cast<u32 *>(cells + 1);
-    kc_ull *n_unique = reinterpret_cast<kc_ull *>(cells);
-    {
-        std::vector<u32> hs(nP0);
-        for (u32 i = 0; i < nP0; ++i) hs[i] = (u32) sh->pre_size[i];
-        KC_CUDA(cudaMemcpyAsync(d_off, sh->pre_off, (size_t) nP0 * 8, cudaMemcpyHostToDevice, st));
-        KC_CUDA(cudaMemcpyAsync(d_size, hs.data(), (size_t) nP0 * 4, cudaMemcpyHostToDevice, st));
-        KC_CUDA(cudaStreamSynchronize(st));  // hs goes out of scope
-    }
-    const int tile1 = Cfg::TILE;
-    const int smem1 = tile1 * ((int) sizeof(KWord<L>) + 4 + 2);
-    static bool attr_done = false;
-    if (!attr_done) {
-        KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_kernel<L, Cfg::TILE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-        KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (16 * L + 20)));
-        KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) KSF_LEAF_CAP * (16 * L + 24)));
-        attr_done = true;
-    }
-    const u64 item_bytes = sizeof(KWord<L>) + 4;
-    const u32 max_ctas = 148 * 8;
-    const KWord<L> *ksrc = reinterpret_cast<const KWord<L> *>(sh->keys);
-    const u32 *psrc = sh->pos;
-    const u32 *cnt_par = d_size;
+    const u64 items_ub = (u64) dig_n * (u64) g.n_ranks * g.cap_sub;
+    const KWord<L> *ksrc = recv_k;
+    const u32 *psrc = recv_p;
+    const u32 *cnt_par = sub_cnt;
     u32 *cnt_cur = cnt_all;
-    for (int lv = 0; lv < levels; ++lv) {
-        const u32 nP = lv == 0 ? nP0 : (u32) ((u64) nP0 << cum[lv - 1]);
-        const size_t mark = ex.arena->mark();
-        u32 *P_size = ex.alloc<u32>(nP);
-        u32 *tile_prefix = ex.alloc<u32>((u64) nP + 1);
-        const u32 capP = lv == 0 ? 0xFFFFFFFFu : (u32) cap[lv - 1];
-        kc_ksf_prep_kernel<<<(unsigned) kc_div_up((u64) nP + 1, 256), 256, 0, st>>>(cnt_par, nP, capP, (u32) tile1, P_size, tile_prefix, status, nullptr);
-        ++ex.launches;
-        ex.exclusive_scan_nosync(tile_prefix, tile_prefix, (u64) nP + 1);
-        const u64 tiles_ub = total / tile1 + nP + 1;
-        const u32 tiles_per_cta = (u32) kc_div_up(tiles_ub, max_ctas);
-        const u32 ctas = (u32) kc_div_up(tiles_ub, tiles_per_cta);
-        {
-            CudaExec::Scope sc(ex, KP_SORT_SCATTER, 2 * total * item_bytes);
-            kc_ksf_scatter_kernel<L, Cfg::TILE, 3><<<ctas, 256, smem1, st>>>(ksrc, psrc, kb[lv & 1], pb[lv & 1], P_size, tile_prefix, nP, (u64) capP, tiles_per_cta,
-                                                                             64 * L - Cfg::D0 - cum[lv], bits[lv], cnt_cur, (u32) cap[lv], status,
-                                                                             lv == 0 ? d_off : nullptr);
-            ++ex.launches;
-            KC_CUDA(cudaGetLastError());
-        }
+    for (int lv = 1; lv < pl.n_levels; ++lv) {
+        const u32 nP = lv == 1 ? dig_n * (u32) g.n_ranks : (u32) ((u64) dig_n << (pl.cum[lv - 1] - pl.cum[0]));
+        kc_ksf_level<L>(ex, ksrc, psrc, kb[lv & 1], pb[lv & 1], cnt_par, nP, lv == 1 ? g.cap_sub : pl.cap[lv - 1], cnt_cur, pl.cap[lv], 64 * L - pl.cum[lv], pl.bits[lv],
+                        items_ub, status, lv == 1 ? m_cell : nullptr, tune, lv == 1 ? (u32) g.n_ranks : 1u);
         ksrc = kb[lv & 1];
         psrc = pb[lv & 1];
         cnt_par = cnt_cur;
-        cnt_cur += (u64) nP0 << cum[lv];
-        ex.arena->release(mark);
+        cnt_cur += (u64) dig_n << (pl.cum[lv] - pl.cum[0]);
     }
-    {   // no leaf may exceed the resolve capacity: decided BEFORE a single flag bit is written
-        const u32 *cc = cnt_par;
-        ex.for_each(n_leaf, [=] __device__(u64 i) {
-            if (cc[i] > KSF_LEAF_CAP) status[0] = 1;
-        });
-    }
-    if (ex.read(status)) {
-        ex.arena->release(base_mark);
-        return false;
-    }
-    const bool counted = min_freq > 1;
-    const int smem2 = (int) KSF_LEAF_CAP * (16 * L + 20 + (counted ? 4 : 0));
-    int occ = 0, n_sm = 0, dev = 0;
-    KC_CUDA(cudaGetDevice(&dev));
-    KC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    if (counted) KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kc_ksf_resolve_kernel<L, true>, 256, smem2));
-    else KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kc_ksf_resolve_kernel<L, false>, 256, smem2));
-    const u32 fit = (u32) (n_sm * (occ > 0 ? occ : 1));
-    const u32 grid = (u32) n_leaf < fit ? (u32) n_leaf : fit;
-    {
-        CudaExec::Scope sc(ex, KP_KS_RESOLVE, total * item_bytes);
-        const int last = levels - 1;
-        if (counted)
-            kc_ksf_resolve_kernel<L, true><<<grid, 256, smem2, st>>>(kb[last & 1], pb[last & 1], cnt_par, (u32) n_leaf, flags, (u32) min_freq, n_unique, status);
-        else
-            kc_ksf_resolve_kernel<L, false><<<grid, 256, smem2, st>>>(kb[last & 1], pb[last & 1], cnt_par, (u32) n_leaf, flags, (u32) min_freq, n_unique, status);
-        ++ex.launches;
-        KC_CUDA(cudaGetLastError());
-    }
-    *n_kept_out = ex.read(cells);
+    const u64 n_leaf = (u64) dig_n << (pl.cum[pl.n_levels - 1] - pl.cum[0]);
+    kc_ksf_resolve<L>(ex, ksrc, psrc, cnt_par, n_leaf, all_flags, min_freq, reinterpret_cast<kc_ull *>(cells), status, items_ub);
     ex.arena->release(base_mark);
-    return true;
 }
 
 #endif  // __CUDACC__

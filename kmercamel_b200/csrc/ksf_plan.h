@@ -10,7 +10,7 @@
 #include <cmath>
 #include <cstdint>
 
-static const uint32_t KSF_LEAF_CAP = 1024;  // capacity of kc_ks_resolve_hash_kernel<L, 1024, *>
+static const uint32_t KSF_LEAF_CAP = 1024;  // capacity of the shared-memory leaf resolve (kc_ksf_resolve*_kernel)
 static const int KSF_MAX_LEVELS = 4;
 
 struct KsfTuning {
@@ -18,17 +18,7 @@ struct KsfTuning {
     uint32_t leaf_target = 768;   // mean leaf size aimed at (the leaf slot holds KSF_LEAF_CAP)
     double sigmas = 8.0;     // slot = mean + sigmas * sqrt(mean) (+ 2 %) items; 0 forces overflows (tests)
     uint64_t min_items = 1u << 16;  // smaller inputs take the exact path (nothing to gain)
-    int resolve = 6;         // 1 = kc_ksf_resolve_kernel (cp.async, two barriers), 0 = kc_ks_resolve_hash_kernel over a bucket list,
-                             // 2 = as 1 with clear-the-losers flags (level 0 writes the valid-window bits, a duplicate clears one),
-                             // 3 = kc_ksf_resolve1_kernel: clear-the-losers + double-buffered tables, ONE barrier per leaf (-z 1 only),
-                             // 4 / 5 = the same with 3 / 4 staging buffers in the ring (two / three leaves in flight per CTA),
-                             // 6 / 7 = kc_ksf_resolve2_kernel: as 3 with a thread's items staged in registers, 256 / 512 threads,
-                             // 8 = as 6 with 8-byte copy units (every thread the same number of items) and the leaf size loaded a leaf ahead
-    int tile_variant = 5;    // level >= 1 scatter: 0 = KsCfg<L>::TILE items per tile, 3 CTAs/SM; 1 = half tiles, 5 CTAs/SM; 2 = 3/4 tiles, 4 CTAs/SM;
-                             // 3 / 4 = kc_ksf_scatter_pf_kernel (next tile streams in with cp.async) with full / half tiles,
-                             // 5 = full tiles and 512-thread CTAs (2 per SM: 32 instead of 16 warps)
-    int max_ctas = 148 * 16; // level >= 1 scatter grid: at most this many CTAs, each walking a run of consecutive tiles (0 = 148 * 8)
-    int split0 = 0;          // level 0 (L = 1): two threads per 32-base strip (512-thread CTAs); measured slower (0.327 vs 0.315 ms), kept as an option
+    int max_ctas = 148 * 16; // level >= 1 scatter grid: at most this many CTAs, each walking a run of consecutive tiles
 };
 
 struct KsfPlan {
@@ -66,5 +56,50 @@ inline KsfPlan kc_ksf_plan(uint64_t m_upper, const KsfTuning &t) {
     p.n_leaf = 1ULL << cum;
     p.ok = true;
     return p;
+}
+
+// ---- multi-GPU (group.cuh): hash-range sharding of the same construction ---------------------------------------------------
+// Level 0 runs on every rank over its slice of the level-0 tiles; level-0 digit d belongs to rank owner(d) = d * n_ranks /
+// n_digits (contiguous digit ranges), and the items a sender produces for d go into the sub-slot (d, sender) of the owner's
+// receive buffer: cap_sub items, planned like every other slot from the slice size alone.  From level 1 on the owner works
+// alone, with the plan of the WHOLE input (its buckets hold the items of all senders).
+static const int KSF_MAX_RANKS = 16;
+inline uint64_t ksf_div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// Geometry of one job, the same on every rank (computed from n_bytes, the tuning and the group size alone).
+struct KsfGroupPlan {
+    bool ok = false;
+    KsfPlan pl;
+    int n_ranks = 1;
+    uint32_t n_digits = 0;      // level-0 buckets = 1 << pl.bits[0]
+    uint32_t tiles = 0;         // level-0 tiles of the whole input
+    uint64_t cap_sub = 0;       // items per (digit, sender) sub-slot
+    uint32_t dig_max = 0;       // most digits any rank owns
+    uint32_t tile_begin(int r) const { return (uint32_t) ((uint64_t) tiles * (uint64_t) r / (uint64_t) n_ranks); }
+    uint32_t dig_begin(int r) const { return (uint32_t) (((uint64_t) r * n_digits + (uint64_t) n_ranks - 1) / (uint64_t) n_ranks); }  // owner(d) = d * n_ranks / n_digits
+    uint32_t owner(uint32_t d) const { return (uint32_t) ((uint64_t) d * (uint64_t) n_ranks / n_digits); }
+    uint64_t recv_items() const { return (uint64_t) dig_max * (uint64_t) n_ranks * cap_sub; }  // receive slots every rank must provide
+};
+
+inline KsfGroupPlan kc_ksf_group_plan(uint64_t n_bytes, int n_ranks, uint64_t ex_tile, const KsfTuning &tune) {
+    KsfGroupPlan g;
+    g.pl = kc_ksf_plan(n_bytes, tune);
+    g.n_ranks = n_ranks;
+    if (!g.pl.ok || g.pl.n_levels < 2 || n_ranks < 1 || n_ranks > KSF_MAX_RANKS) return g;  // one level: the leaves would be split by sender
+    g.n_digits = 1u << g.pl.bits[0];
+    if (g.n_digits < (uint32_t) n_ranks) return g;
+    g.tiles = (uint32_t) ksf_div_up(n_bytes, ex_tile);
+    const uint64_t slice_tiles = ksf_div_up((uint64_t) g.tiles, (uint64_t) n_ranks);
+    const double mean = (double) (slice_tiles * ex_tile) / (double) g.n_digits;
+    uint64_t cap = (uint64_t) std::ceil(mean + tune.sigmas * std::sqrt(mean) + (tune.sigmas > 0 ? 0.02 * mean + 64.0 : 0.0));
+    cap = (cap + 31) / 32 * 32;
+    if (cap >= 0xFFFFFFFFULL) return g;
+    g.cap_sub = cap;
+    for (int r = 0; r < n_ranks; ++r) {
+        const uint32_t n = g.dig_begin(r + 1) - g.dig_begin(r);
+        g.dig_max = n > g.dig_max ? n : g.dig_max;
+    }
+    g.ok = true;
+    return g;
 }
 

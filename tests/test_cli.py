@@ -142,3 +142,33 @@ def test_cli_streaming_and_maskopt(gm, tmp_path):
     empty.write_text(">r\nACG\n")
     p = run(["compute", "-k", "5", str(empty)])
     assert p.returncode == 1 and "contains no k-mers" in p.stderr.decode()  # src/main.cpp:155-158
+
+
+@pytest.mark.gpu
+def test_cli_several_gpus_and_verify(tmp_path):
+    """`compute -g a,b,...` (one process, one host thread per rank; ranks may share a GPU): byte-identical to `-g 0`, the
+    reference's log lines, and -V (the verify.py check as a device-side digest) passes."""
+    import torch
+    from kmercamel_b200 import synth
+    n = torch.cuda.device_count()
+    recs = synth.human_like_genome(3_000_000, 77)
+    fa = tmp_path / "g.fa"
+    fa.write_bytes(synth.fasta_bytes(recs))
+    one = run(["compute", "-k", "31", "-V", str(fa)])
+    assert one.returncode == 0, one.stderr.decode()
+    assert "Verification passed" in one.stderr.decode() and "simplitigs)." in one.stderr.decode()
+    for ranks in (2, 4):
+        devs = ",".join(str(r % n) for r in range(ranks))
+        p = run(["compute", "-k", "31", "-V", "-g", devs, str(fa)])
+        assert p.returncode == 0, p.stderr.decode()
+        assert p.stdout == one.stdout
+        err = p.stderr.decode()
+        assert "Verification passed" in err and "sharded by hash range over %d GPUs" % ranks in err
+    p = run(["compute", "-k", "31", "-g", "0-1x", str(fa)])
+    assert p.returncode == 1 and "-g takes CUDA device ordinals" in p.stderr.decode()
+    # -S on several devices runs on the first one (with a note) and gives the single-GPU answer
+    sim = tmp_path / "s.fa"
+    sim.write_bytes(synth.fasta_bytes([r[:5000] for r in recs[:6]]))
+    a = run(["compute", "-k", "31", "-S", str(sim)])
+    b = run(["compute", "-k", "31", "-S", "-g", "0,0", str(sim)])
+    assert a.returncode == 0 and b.returncode == 0 and a.stdout == b.stdout and "run on one GPU" in b.stderr.decode()

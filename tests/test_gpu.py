@@ -300,7 +300,7 @@ def test_fast_set_matches_exact(ctx, k, compl, z):
     recs.append(np.frombuffer(b"ACGTNNNNNACGT" * 50, dtype=np.uint8).copy())  # N breaks, low complexity
     recs += list(synth.reads_from_genome(20000, 4.0, 150, 0.01, seed=k))
     seq, off, ln = synth.frame_records(recs)
-    default_variant = (ctx.stat("fast_resolve"), ctx.stat("fast_tile_variant"), ctx.stat("fast_max_ctas"))
+    default_ctas = ctx.stat("fast_max_ctas")
     try:
         _fast_options(ctx, fast_set=0)
         want = ctx.compute(seq, k=k, complements=compl, min_frequency=z)
@@ -310,24 +310,17 @@ def test_fast_set_matches_exact(ctx, k, compl, z):
             got = ctx.compute(seq, k=k, complements=compl, min_frequency=z)
             assert ctx.stat("fast_runs") == runs0 + 1 and ctx.stat("fast_fallbacks") == fb0, leaf_target
             assert got.n_kmers == want.n_kmers and got.ms == want.ms, leaf_target
-        # every kernel variant of the construction (kc_set_option fast_resolve / fast_tile_variant / fast_max_ctas) gives the same
-        # flags: bucket-list resolve (0), two-barrier resolve with set-the-winners (1) / clear-the-losers (2) flags, one-barrier
-        # resolve with 2 / 3 / 4 staging buffers (3 / 4 / 5) and with register-staged items (6 / 7 / 8); plain (0 - 2) and
-        # prefetching (3 - 5) level >= 1 scatter, over different grid sizes
+        # the grid size of the level >= 1 scatter (CTAs walk runs of consecutive tiles) never changes the result
         for leaf_target in (768, 16):
             _fast_options(ctx, fast_min_items=0, fast_leaf_target=leaf_target)
-            for resolve, tile, max_ctas in ((0, 0, 0), (1, 1, 0), (2, 2, 0), (3, 3, 0), (4, 4, 296), (5, 5, 4096), (6, 3, 0), (7, 0, 0), (8, 5, 0), (1, 3, 0)):
-                ctx.set_option("fast_resolve", resolve)
-                ctx.set_option("fast_tile_variant", tile)
+            for max_ctas in (1, 296, 4096, 1 << 20):
                 ctx.set_option("fast_max_ctas", max_ctas)
                 runs0, fb0 = ctx.stat("fast_runs"), ctx.stat("fast_fallbacks")
                 got = ctx.compute(seq, k=k, complements=compl, min_frequency=z)
-                assert ctx.stat("fast_runs") == runs0 + 1 and ctx.stat("fast_fallbacks") == fb0, (leaf_target, resolve, tile)
-                assert got.n_kmers == want.n_kmers and got.ms == want.ms, (leaf_target, resolve, tile)
+                assert ctx.stat("fast_runs") == runs0 + 1 and ctx.stat("fast_fallbacks") == fb0, (leaf_target, max_ctas)
+                assert got.n_kmers == want.n_kmers and got.ms == want.ms, (leaf_target, max_ctas)
     finally:
-        ctx.set_option("fast_resolve", default_variant[0])
-        ctx.set_option("fast_tile_variant", default_variant[1])
-        ctx.set_option("fast_max_ctas", default_variant[2])
+        ctx.set_option("fast_max_ctas", default_ctas)
         _fast_options(ctx)
     want_k, want_v = orc.count_kmers(seq, off, ln, k, compl)
     want_k = want_k[want_v.astype(int) + 1 >= z]

@@ -33,9 +33,9 @@ def test_partial_presort_random_vs_oracle(ctx, k, n):
     rng = np.random.default_rng(k * 1000 + 1)
     L = orc.limbs_for_k(k)
     kmers = rng.integers(0, 1 << 63, size=(n, L), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, L), dtype=np.uint64)
-    top_bits = 2 * k - 64 * (L - 1)                      # valid bits of the top limb
-    if top_bits < 64:
-        kmers[:, L - 1] &= np.uint64((1 << top_bits) - 1)
+    for limb in range(L):                                # keep the low 2k bits of the word
+        bits = min(64, max(0, 2 * k - 64 * limb))
+        kmers[:, limb] &= np.uint64((1 << bits) - 1)
     kmers[: n // 3] = kmers[n // 3: 2 * (n // 3)]        # equal digits and equal words: stability matters
     got = ctx.partial_presort(kmers, k=k)
     assert np.array_equal(got, orc.partial_presort(kmers, k))

@@ -1,11 +1,21 @@
-"""Host-side logic of the hash-range sharded path (kmercamel_b200/sharded.py).
+"""The multi-GPU construction (kmercamel_b200/csrc/group.cuh behind kc_group_* / kc_init_multi).
 
-CPU part (`-m "not gpu"`): the orchestration runs with world_size 2 over gloo, with a numpy stand-in for the two GPU
-halves (partition / resolve), and must produce exactly the first-occurrence flags of a single-process computation.
-GPU part (`-m gpu`): world_size 1 through the real library halves must reproduce kc_compute byte for byte.
+CPU part (`-m "not gpu"`):
+  * the job geometry every rank derives on its own (kc_group_plan, host-only) tiles the input and partitions the hash space;
+  * world_size 2 over gloo: each rank extracts the k-mers of ITS slice, routes every item to the owner of its hash range as the
+    plan says (numpy stand-in for the kernels, gloo all-to-all for the NVLink stores), resolves its range, and the OR of the
+    ranks' first-occurrence bits must be exactly the bits of a single-process computation — the sharding itself is right;
+  * the handle all-gather of sharded.attach.
+GPU part (`-m gpu`): the real kernels and the real peer protocol.  Several ranks on ONE device (a device ordinal may repeat in
+kc_init_multi) exercise every peer store, signal and wait of the N-GPU path on the one-GPU box the driver tests on, and two
+PROCESSES sharing the GPU exercise the CUDA-IPC form that bench.py uses under torchrun; with >= 2 GPUs visible the same tests
+spread the ranks over distinct devices.  The result must be byte-identical to kc_compute on one GPU.
 """
+import json
 import os
 import socket
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -13,6 +23,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+import kmercamel_b200 as kb
 from kmercamel_b200 import sharded, synth
 
 MULT = np.uint64(0x9E3779B97F4A7C15)
@@ -59,63 +70,6 @@ def first_occurrence_flags(seq, k, complements, min_frequency):
     return words, int(keep.sum())
 
 
-class CpuStandInOps:
-    """numpy stand-in for GpuOps: same interface, same data layout (items grouped by level-0 digit)."""
-
-    def __init__(self, seq: np.ndarray):
-        self.seq = seq
-        self.n_bytes = len(seq)
-        self.flags = torch.zeros((self.n_bytes + 31) // 32 + 1, dtype=torch.int32)
-
-    def granule(self, k):
-        return 64
-
-    def partition(self, b, e, *, k, complements):
-        keys, pos = window_kmers(self.seq, k, complements)
-        sel = (pos >= b) & (pos < e)
-        keys, pos = keys[sel], pos[sel]
-        digit = ((keys * MULT) >> np.uint64(56)).astype(np.int64)
-        order = np.argsort(digit, kind="stable")
-        self._send_k = torch.from_numpy(keys[order].astype(np.int64))
-        self._send_p = torch.from_numpy(pos[order].astype(np.int32))
-        return np.bincount(digit, minlength=256).astype(np.int64), len(keys)
-
-    def exchange_items(self, comm, send, recv):
-        n_recv = int(recv.sum())
-        keys = torch.empty(n_recv, dtype=torch.int64)
-        pos = torch.empty(n_recv, dtype=torch.int32)
-        comm.all_to_all(keys, self._send_k, recv, send, 1)
-        comm.all_to_all(pos, self._send_p, recv, send, 1)
-        return keys, pos
-
-    def resolve(self, keys, pos, n, *, k, complements, min_frequency):
-        self.flags.zero_()
-        ks = keys.numpy()[:n].astype(np.uint64)
-        ps = pos.numpy()[:n].astype(np.int64)
-        if n == 0:
-            return 0
-        order = np.lexsort((ps, ks))
-        ks, ps = ks[order], ps[order]
-        head = np.concatenate([[True], ks[1:] != ks[:-1]])
-        starts = np.flatnonzero(head)
-        counts = np.diff(np.concatenate([starts, [n]]))
-        keep = counts >= min_frequency
-        first = ps[starts[keep]]
-        words = np.zeros(self.flags.numel(), dtype=np.uint32)
-        np.bitwise_or.at(words, first >> 5, (np.uint32(1) << (first & 31).astype(np.uint32)))
-        self.flags.copy_(torch.from_numpy(words.view(np.int32)))
-        return int(keep.sum())
-
-    def reduce_flags(self, comm, all_ranks: bool = False):
-        if all_ranks:
-            comm.all_reduce_sum(self.flags)
-        else:
-            comm.reduce_sum(self.flags, 0)
-
-    def finish(self, n_kept, *, k, complements, slice=None):
-        return self.flags.numpy().view(np.uint32).copy()
-
-
 def make_input(seed):
     recs = synth.random_genome_records(3, 700, seed)
     recs.append(recs[0][100:400].copy())          # duplicated region
@@ -125,31 +79,87 @@ def make_input(seed):
     return seq
 
 
-def _worker(rank, world, port, k, complements, z, seed, out):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        seq = make_input(seed)
-        ops = CpuStandInOps(seq)
-        comm = sharded.TorchComm(torch.device("cpu"))
-        r = sharded.sharded_compute(ops, comm, len(seq), k=k, complements=complements, min_frequency=z)
-        if rank == 0:
-            want, want_kept = first_occurrence_flags(seq, k, complements, z)
-            keys, _ = window_kmers(seq, k, complements)
-            out.put((bool(np.array_equal(r.result, want)), r.n_kept == want_kept, r.n_occurrences == len(keys), r.items_sent, r.items_received))
-    finally:
-        dist.destroy_process_group()
-
-
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
 
 
+
+# ---- CPU: geometry -------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 5, 8, 16])
+def test_group_plan_invariants(world):
+    for k in (15, 31, 63, 127):
+        for n_bytes in (0, 1000, 70_000, 8192 * 5 + 3, 3_000_001, 50_000_050, 400_000_400, 3_100_000_024):
+            plans = sharded.check_plans(world, k, n_bytes)
+            g = int(kb.load_library().kc_shard_granule(k))
+            assert all(p["pos_begin"] % g == 0 and (p["pos_end"] % g == 0 or p["pos_end"] == n_bytes) for p in plans)
+            if plans[0]["fixed_slots"]:
+                # a sub-slot holds the expected share of a slice with room to spare, and stays 128-byte aligned for the positions
+                slice_max = max(p["pos_end"] - p["pos_begin"] for p in plans)
+                assert plans[0]["cap_sub"] % 32 == 0 and plans[0]["cap_sub"] > slice_max / plans[0]["n_digits"]
+                assert all(p["digit_end"] > p["digit_begin"] for p in plans)
+    assert not sharded.group_plan(2, 0, 31, 50_000)["fixed_slots"]       # too small: the exact construction
+    assert sharded.group_plan(8, 3, 31, 400_000_400)["fixed_slots"]
+
+
+# ---- CPU: the sharding is a correct decomposition (world 2 over gloo, numpy stand-in for the kernels) -------------------
+def _sharded_flags_cpu(rank, world, seq, k, complements, z):
+    plan = sharded.group_plan(world, rank, k, len(seq))
+    plans = [sharded.group_plan(world, r, k, len(seq)) for r in range(world)]
+    keys, pos = window_kmers(seq, k, complements)
+    mine = (pos >= plan["pos_begin"]) & (pos < plan["pos_end"])
+    keys, pos = keys[mine], pos[mine]
+    bits = int(plan["n_digits"]).bit_length() - 1
+    digit = ((keys * MULT) >> np.uint64(64 - bits)).astype(np.int64)       # level-0 digit of the scrambled word
+    owner = np.searchsorted(np.array([p["digit_end"] for p in plans]), digit, side="right")
+    order = np.argsort(owner, kind="stable")
+    send = np.bincount(owner, minlength=world).astype(np.int64)
+    s = torch.from_numpy(send)
+    r = torch.empty_like(s)
+    dist.all_to_all_single(r, s)
+    recv = r.numpy()
+    rk = torch.empty(int(recv.sum()), dtype=torch.int64)
+    rp = torch.empty(int(recv.sum()), dtype=torch.int64)
+    dist.all_to_all_single(rk, torch.from_numpy(keys[order].astype(np.int64)), recv.tolist(), send.tolist())
+    dist.all_to_all_single(rp, torch.from_numpy(pos[order].astype(np.int64)), recv.tolist(), send.tolist())
+    ks, ps = rk.numpy().astype(np.uint64), rp.numpy()
+    words = np.zeros((len(seq) + 31) // 32 + 1, dtype=np.uint32)
+    kept = 0
+    if len(ks):
+        o = np.lexsort((ps, ks))
+        ks, ps = ks[o], ps[o]
+        starts = np.flatnonzero(np.concatenate([[True], ks[1:] != ks[:-1]]))
+        counts = np.diff(np.concatenate([starts, [len(ks)]]))
+        keep = counts >= z
+        first = ps[starts[keep]]
+        np.bitwise_or.at(words, first >> 5, (np.uint32(1) << (first & 31).astype(np.uint32)))
+        kept = int(keep.sum())
+    t = torch.from_numpy(words.view(np.int32).copy())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)                               # disjoint bits: SUM == OR
+    tot = torch.tensor([kept, int(send.sum()) - int(send[rank])], dtype=torch.int64)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    return t.numpy().view(np.uint32), int(tot[0]), int(tot[1])
+
+
+def _worker(rank, world, port, k, complements, z, seed, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        seq = make_input(seed)
+        seq = np.concatenate([seq] + [synth.frame_records(synth.random_genome_records(2, 40_000, seed + 1))[0]])
+        handles = sharded.gather_handles(np.full(64, rank + 1, dtype=np.uint8), world)      # the set-up plumbing of sharded.attach
+        flags, kept, moved = _sharded_flags_cpu(rank, world, seq, k, complements, z)
+        if rank == 0:
+            want, want_kept = first_occurrence_flags(seq, k, complements, z)
+            out.put((bool(np.array_equal(flags, want)), kept == want_kept, moved, handles.tolist() == [1] * 64 + [2] * 64))
+    finally:
+        dist.destroy_process_group()
+
+
 @pytest.mark.parametrize("k,complements,z", [(11, True, 1), (21, False, 1), (15, True, 2), (31, True, 3)])
-def test_sharded_two_ranks_gloo(k, complements, z):
+def test_sharding_two_ranks_gloo(k, complements, z):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
@@ -159,138 +169,86 @@ def test_sharded_two_ranks_gloo(k, complements, z):
     for p in procs:
         p.join(180)
         assert p.exitcode == 0
-    flags_ok, kept_ok, occ_ok, sent, received = out.get(timeout=10)
-    assert flags_ok and kept_ok and occ_ok
-    assert sent > 0 and received > 0          # the exchange really moved items between the two ranks
+    flags_ok, kept_ok, moved, handles_ok = out.get(timeout=10)
+    assert flags_ok and kept_ok and handles_ok
+    assert moved > 0                          # the exchange really moved items between the two ranks
 
 
-def test_plan_slices_and_owners():
-    for n_bytes, world, g in [(50_000_050, 8, 8192), (1000, 4, 8192), (8192 * 5 + 3, 3, 8192), (0, 2, 64), (777, 1, 64)]:
-        sl = sharded.plan_slices(n_bytes, world, g)
-        assert len(sl) == world and sl[0][0] == 0 and sl[-1][1] == n_bytes
-        for (b, e), (b2, _) in zip(sl, sl[1:]):
-            assert e == b2 and b <= e
-        assert all(b % g == 0 for b, _ in sl) and all(e % g == 0 or e == n_bytes for _, e in sl)
-    for world in (1, 2, 3, 4, 8):
-        owners = [sharded.owner_of_digit(d, world) for d in range(256)]
-        assert owners == sorted(owners) and set(owners) == set(range(world))
-        counts = np.arange(256)
-        oc = sharded.owner_counts(counts, world)
-        assert oc.sum() == counts.sum() and all(oc[r] == sum(d for d in range(256) if owners[d] == r) for r in range(world))
+# ---- GPU: several ranks in one process ----------------------------------------------------------------------------------------
+def _devices(n_ranks):
+    n = torch.cuda.device_count()
+    return [r % n for r in range(n_ranks)]
 
 
-def test_single_rank_stand_in_matches_flags():
-    seq = make_input(3)
-    ops = CpuStandInOps(seq)
-    comm = sharded.TorchComm(torch.device("cpu"))
-    r = sharded.sharded_compute(ops, comm, len(seq), k=13, complements=True, min_frequency=1)
-    want, kept = first_occurrence_flags(seq, 13, True, 1)
-    assert np.array_equal(r.result, want) and r.n_kept == kept
+def _inputs():
+    g = synth.frame_records(synth.random_genome_records(5, 600_000, 41))[0]
+    rep = synth.frame_records(synth.human_like_genome(2_000_000, 43))[0]
+    reads = synth.frame_reads(synth.reads_chunks(60_000, 12.0, 150, 0.01, 44, chunk_reads=2000), 150)
+    return {"genome": g, "repeats": rep, "reads": reads, "twice": np.concatenate([g, g[: len(g) // 2]])}
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k,complements,z", [(31, True, 1), (31, True, 2), (63, False, 1), (127, True, 1), (9, True, 1)])
-def test_sharded_world1_matches_kc_compute(ctx, k, complements, z):
-    recs = synth.random_genome_records(6, 40_000, 5)
-    recs.append(recs[1][5000:9000].copy())
-    reads = synth.reads_from_genome(20_000, 8.0, 150, 0.01, seed=k)
-    seq, _, _ = synth.frame_records(recs + list(reads))
-    want = ctx.compute(seq, k=k, complements=complements, min_frequency=z)
-    d = torch.from_numpy(seq).cuda()
-    torch.cuda.synchronize()
-    ops = sharded.GpuOps(ctx, d)
-    comm = sharded.TorchComm(d.device)
-    r = sharded.sharded_compute(ops, comm, d.numel(), k=k, complements=complements, min_frequency=z)
-    assert r.n_kept == want.n_kmers and r.result.length == want.length
-    assert ctx.copy_to_host(r.result.ms_ptr, r.result.length) == want.ms
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("stream_mode", ["private", "torch"])
-def test_sharded_p2p_world1_matches_kc_compute(stream_mode):
-    """The fused partition + exchange path with a single rank (its own buffers stand in for the peers'), on a private
-    library stream and on torch's current stream (then no host synchronisation separates torch's work from the kernels)."""
-    import kmercamel_b200 as kb
-    c = kb.Context(0, None if stream_mode == "private" else torch.cuda.current_stream().cuda_stream)
+@pytest.mark.parametrize("n_ranks", [1, 2, 3, 4, 8])
+def test_group_in_process_matches_single_gpu(ctx, n_ranks):
+    inputs = _inputs()
+    grp = kb.Group(_devices(n_ranks))
     try:
-        recs = synth.random_genome_records(6, 40_000, 11)
-        recs.append(recs[2][100:3000].copy())
-        seq, _, _ = synth.frame_records(recs)
-        d = torch.from_numpy(seq).cuda()
-        ops = sharded.GpuOps(c, d)
-        comm = sharded.TorchComm(d.device)
-        ops.setup_p2p(comm, 31)
-        for z in (1, 2):
-            want = c.compute(seq, k=31, min_frequency=z)
-            r = sharded.sharded_compute_p2p(ops, comm, d.numel(), k=31, min_frequency=z)
-            assert r.n_kept == want.n_kmers and r.result.length == want.length
-            assert c.copy_to_host(r.result.ms_ptr, r.result.length) == want.ms
+        for name, k, compl, z in [("genome", 31, True, 1), ("repeats", 31, True, 1), ("twice", 31, False, 1), ("genome", 63, True, 1),
+                                  ("repeats", 127, False, 1), ("reads", 31, True, 2), ("reads", 21, True, 1), ("genome", 31, True, 1)]:
+            seq = inputs[name]
+            want = ctx.compute(seq, k=k, complements=compl, min_frequency=z)
+            got = grp.compute(seq, k=k, complements=compl, min_frequency=z)
+            assert (got.n_kmers, got.length, got.n_nodes) == (want.n_kmers, want.length, want.n_nodes), (name, k, z)
+            assert got.ms == want.ms, (name, k, z)
+        runs = grp.stat("fast_runs")
+        assert min(runs) >= 4 and len(set(runs)) == 1          # the genomes took the fixed-slot path on every rank
     finally:
-        c.close()
+        grp.close()
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k,n_slices", [(31, 3), (63, 8), (15, 2)])
-def test_sliced_emission_tiles_the_superstring(k, n_slices):
-    """kc_compute_from_flags_slice: the slices of indices 0..n-1 (what the ranks of a multi-GPU job emit) concatenate to exactly
-    the superstring of the unsliced call, for long runs (chunked 16-byte emission) and for thousands of short ones."""
-    import kmercamel_b200 as kb
-    c = kb.Context(0, torch.cuda.current_stream().cuda_stream)
+def test_group_overflow_falls_back_on_every_rank(ctx):
+    """Slots planned without slack overflow; every rank sees the status word and all switch to the exact construction together."""
+    seq = _inputs()["repeats"]
+    want = ctx.compute(seq, k=31)
+    grp = kb.Group(_devices(3))
     try:
-        recs = synth.random_genome_records(3, 200_000, 31) + list(synth.reads_from_genome(30_000, 6.0, 150, 0.01, seed=k))
-        seq, _, _ = synth.frame_records(recs)
-        d = torch.from_numpy(seq).cuda()
-        ops = sharded.GpuOps(c, d)
-        comm = sharded.TorchComm(d.device)
-        ops.setup_p2p(comm, k)
-        whole = sharded.sharded_compute_p2p(ops, comm, d.numel(), k=k)
-        want = c.copy_to_host(whole.result.ms_ptr, whole.result.length)
-        assert want == kb.Context(0).compute(seq, k=k).ms
-        parts, at = [], 0
-        for i in range(n_slices):
-            r = c.compute_from_flags(d.data_ptr(), d.numel(), ops.flags.data_ptr(), whole.n_kept, k=k, slice=(i, n_slices))
-            assert r.length == len(want) and r.slice_begin == at and (r.slice_begin % 16 == 0)
-            parts.append(c.copy_to_host(r.ms_ptr, r.slice_len))
-            at += r.slice_len
-        assert at == len(want) and b"".join(parts) == want
-        sliced = sharded.sharded_compute_p2p(ops, comm, d.numel(), k=k, slice_output=True)     # world 1: one slice = everything
-        assert (sliced.result.slice_begin, sliced.result.slice_len) == (0, len(want))
-        assert c.copy_to_host(sliced.result.ms_ptr, sliced.result.slice_len) == want
+        grp.set_option("fast_sigmas", 0)
+        grp.set_option("fast_heuristics", 0)
+        for _ in range(2):
+            got = grp.compute(seq, k=31)
+            assert got.ms == want.ms
+        assert min(grp.stat("fast_fallbacks")) >= 2
+        grp.set_option("fast_sigmas", 8)
+        assert grp.compute(seq, k=31).ms == want.ms and min(grp.stat("fast_runs")) >= 1
     finally:
-        c.close()
+        grp.close()
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k,z", [(31, 1), (31, 2), (47, 1), (100, 2)])
-def test_sharded_p2p_fixed_slot_resolve_with_duplicates(k, z):
-    """Owner-side fixed-slot levels (kc_kmerset_resolve_fast) on inputs where every k-mer occurs twice or three times, with the
-    data set changing between jobs (stale receive-buffer contents must never leak into a result)."""
-    import kmercamel_b200 as kb
-    c = kb.Context(0, torch.cuda.current_stream().cuda_stream)
-    one = kb.Context(0)
+def test_group_small_and_empty_inputs(ctx):
+    grp = kb.Group(_devices(2))
     try:
-        comm = sharded.TorchComm(torch.device("cuda", 0))
-        a = synth.frame_records(synth.random_genome_records(4, 500_000, 21))[0]
-        b = synth.frame_records(synth.random_genome_records(4, 500_000, 22))[0]
-        first = True
-        for parts in ((a, b), (b, b), (a, a[:700_000], b, a), (a, b)):
-            seq = np.concatenate(parts)
-            d = torch.from_numpy(seq).cuda()
-            ops = sharded.GpuOps(c, d)
-            if first:
-                ops.setup_p2p(comm, k, slack=2.0)
-                first = False
-            try:
-                want = one.compute(seq, k=k, min_frequency=z)
-            except kb.api.KcError as e:      # all k-mers distinct and z = 2: nothing is kept
-                assert e.code == -4
-                with pytest.raises(kb.api.KcError):
-                    sharded.sharded_compute_p2p(ops, comm, d.numel(), k=k, min_frequency=z)
-                continue
-            r = sharded.sharded_compute_p2p(ops, comm, d.numel(), k=k, min_frequency=z)
-            assert r.n_kept == want.n_kmers and r.result.length == want.length
-            assert c.copy_to_host(r.result.ms_ptr, r.result.length) == want.ms
-        assert c.stat("fast_runs") >= 3
+        small = synth.frame_records(synth.random_genome_records(3, 5_000, 3))[0]
+        assert grp.compute(small, k=31).ms == ctx.compute(small, k=31).ms            # below the fixed-slot plan: exact path
+        with pytest.raises(kb.KcError) as e:
+            grp.compute(np.frombuffer(b"ACGT\nNNNN\n", dtype=np.uint8), k=31)
+        assert e.value.code == -4                                                     # no k-mers: KC_ERR_EMPTY on the group too
+        assert grp.compute(small, k=15).ms == ctx.compute(small, k=15).ms            # and the group is still usable
+        with pytest.raises(kb.KcError):
+            grp.compute(small, k=31, min_frequency=300)
     finally:
-        c.close()
-        one.close()
+        grp.close()
+
+
+# ---- GPU: one process per rank (CUDA IPC heaps), launched as the driver launches bench.py ------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_group_torchrun_processes_match_single_gpu(tmp_path, world):
+    out = tmp_path / "result.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(os.path.dirname(__file__), "sharded_worker.py"), str(out)]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    res = json.load(open(out))
+    assert res["world"] == world and res["cases"] >= 5 and res["all_identical"], res
