@@ -354,12 +354,11 @@ template <class Exec, int L> struct Engine {
             a.strict = strict;
             a.out = ex.template alloc<u32>(8 + 128 + 8);
             ex.fill_bytes(a.out, 0, (8 + 128 + 8) * 4);
-            static bool attr_done = false;
-            if (!attr_done) {
+            static KcDevOnce once;  // function attributes are per device
+            once.run([&](int) {
                 KC_CUDA(cudaFuncSetAttribute(kc_small_engine_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int) SmallCfg<L>::SMEM));
-                attr_done = true;
-            }
+            });
             {
                 typename Exec::Scope sc(ex, KP_SMALL_ENGINE, 0);
                 // (measured: one warp instead of 256 threads makes the kernel 1.7x slower on configs[1] — the levels are

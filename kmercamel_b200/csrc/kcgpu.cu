@@ -894,7 +894,9 @@ int kc_maskopt(kc_ctx *ctx, const uint8_t *ms, uint64_t n, int k, int complement
     if (n + 1 >= 0xFFFFFFF0ULL) KC_THROW(KC_ERR_TOO_LARGE, "more than 2^32 sequence bytes on one GPU");
     KC_CUDA(cudaSetDevice(ctx->device));
     const int limbs = kc_limbs_for_k(k);
-    ensure_arena(ctx, estimate_arena(n + 1, 0, limbs, false, true) + 2 * n);
+    // min-one keeps the sorted key set of the first construction (n * (8 limbs + 1) bytes) at the arena bottom while a second,
+    // flags-only construction runs above it
+    ensure_arena(ctx, estimate_arena(n + 1, 0, limbs, false, true) + 2 * n + (minimize ? (size_t) n * (8 * limbs + 1) + n / 4 : 0));
     ctx->arena.reset();
     CudaExec ex{ctx->stream, &ctx->arena};
     ex.prof = &ctx->prof;

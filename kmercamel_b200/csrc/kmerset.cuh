@@ -962,16 +962,15 @@ KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k
     ex.fill_bytes(hist, 0, 256 * 4);
 
     constexpr bool SCRAMBLE = PAY && !KEYS;  // FLAGS-only: bucket by a bijective hash of the k-mer (see kmer_scramble)
-    static bool attr_done = false;
+    static KcDevOnce attr_once;  // function attributes are per device
     const int scatter0_smem = Cfg::EX_TILE * ((int) sizeof(KWord<L>) + (PAY ? 2 : 0));
     const int scatter_smem = Cfg::TILE * ((int) sizeof(KWord<L>) + (PAY ? 4 : 0) + 2);
     const int resolve_smem = Cfg::CAP * ((int) sizeof(KWord<L>) + (PAY ? 4 : 0) + 2);
-    if (!attr_done) {
+    attr_once.run([&](int) {
         KC_CUDA(cudaFuncSetAttribute(kc_ks_scatter0_kernel<L, PAY, SCRAMBLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter0_smem));
         KC_CUDA(cudaFuncSetAttribute(kc_kv_scatter_kernel<L, PAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_smem));
         KC_CUDA(cudaFuncSetAttribute(kc_ks_resolve_kernel<L, PAY, KEYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, resolve_smem));
-        attr_done = true;
-    }
+    });
 
     // ---- level 0 ----
     const int key_bits = SCRAMBLE ? 64 * L : 2 * k;
@@ -1148,25 +1147,21 @@ KmerSet<L> kc_kmerset_build_impl(CudaExec &ex, const u8 *seq, u64 n_bytes, int k
             const int per_item = (int) sizeof(KWord<L>) + 12 + 4;  // key + three table slots + position (+ count)
             const int smem_a = CA * (per_item + (counted ? 4 : 0));
             const int smem_b = Cfg::CAP * (per_item + (counted ? 4 : 0));
-            static bool hash_attr_done = false;
-            if (!hash_attr_done) {
+            // function attributes and occupancy are per device; persistent kernels: exactly as many CTAs as fit on the device
+            static KcDevOnce hash_once;
+            static int occ_tab[KC_MAX_DEVICES][4];
+            const int dev_id = hash_once.run([&](int dv) {
                 KC_CUDA(cudaFuncSetAttribute(kc_ks_resolve_hash_kernel<L, CA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CA * per_item));
                 KC_CUDA(cudaFuncSetAttribute(kc_ks_resolve_hash_kernel<L, CA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CA * (per_item + 4)));
                 KC_CUDA(cudaFuncSetAttribute(kc_ks_resolve_hash_kernel<L, Cfg::CAP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::CAP * per_item));
                 KC_CUDA(cudaFuncSetAttribute(kc_ks_resolve_hash_kernel<L, Cfg::CAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::CAP * (per_item + 4)));
-                hash_attr_done = true;
-            }
-            // persistent kernels: exactly as many CTAs as fit on the device
-            static int occ_a[2] = {0, 0}, occ_b[2] = {0, 0}, n_sm = 0;
-            if (!n_sm) {
-                int dev = 0;
-                KC_CUDA(cudaGetDevice(&dev));
-                KC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-                KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a[0], kc_ks_resolve_hash_kernel<L, CA, false>, 256, CA * per_item));
-                KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a[1], kc_ks_resolve_hash_kernel<L, CA, true>, 256, CA * (per_item + 4)));
-                KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b[0], kc_ks_resolve_hash_kernel<L, Cfg::CAP, false>, 256, Cfg::CAP * per_item));
-                KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b[1], kc_ks_resolve_hash_kernel<L, Cfg::CAP, true>, 256, Cfg::CAP * (per_item + 4)));
-            }
+                KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tab[dv][0], kc_ks_resolve_hash_kernel<L, CA, false>, 256, CA * per_item));
+                KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tab[dv][1], kc_ks_resolve_hash_kernel<L, CA, true>, 256, CA * (per_item + 4)));
+                KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tab[dv][2], kc_ks_resolve_hash_kernel<L, Cfg::CAP, false>, 256, Cfg::CAP * per_item));
+                KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tab[dv][3], kc_ks_resolve_hash_kernel<L, Cfg::CAP, true>, 256, Cfg::CAP * (per_item + 4)));
+            });
+            const int n_sm = kc_sm_count(dev_id);
+            const int *occ_a = &occ_tab[dev_id][0], *occ_b = &occ_tab[dev_id][2];
             const u32 fit_a = (u32) (n_sm * (occ_a[counted] > 0 ? occ_a[counted] : 1)), fit_b = (u32) (n_sm * (occ_b[counted] > 0 ? occ_b[counted] : 1));
             const u32 grid_a = n_small < fit_a ? n_small : fit_a;
             const u32 grid_b = n_small < fit_b ? n_small : fit_b;
@@ -1268,11 +1263,8 @@ template <int L> void kc_kmerset_scatter_p2p(CudaExec &ex, const u8 *seq, u64 n_
     u64 *cursor = ex.alloc<u64>(256);
     KC_CUDA(cudaMemcpyAsync(cursor, sh->cursor0, 256 * 8, cudaMemcpyHostToDevice, ex.stream));
     const int smem = Cfg::EX_TILE * ((int) sizeof(KWord<L>) + 2);
-    static bool attr_done = false;
-    if (!attr_done) {
-        KC_CUDA(cudaFuncSetAttribute(kc_ks_scatter0_kernel<L, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
-    }
+    static KcDevOnce attr_once;
+    attr_once.run([&](int) { KC_CUDA(cudaFuncSetAttribute(kc_ks_scatter0_kernel<L, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); });
     const u32 blocks = (u32) kc_div_up(sh->pos_end - sh->pos_begin, (u64) Cfg::EX_TILE);
     {
         CudaExec::Scope sc(ex, KP_KS_SCATTER0, (sh->pos_end - sh->pos_begin) + n_items * (sizeof(KWord<L>) + 4));

@@ -432,14 +432,13 @@ void kc_sort_impl(CudaExec &ex, KWord<L> *buf0, KWord<L> *buf1, u64 n, int key_b
     u32 *ctr = ex.alloc<u32>(4);
     ex.fill_bytes(ctr, 0, 16);
 
-    static bool attr_done = false;
+    static KcDevOnce attr_once;  // function attributes are per device
     const int local_smem = Cfg::CAP * (int) sizeof(KWord<L>) + Cfg::CAP * 2;
     const int scatter_smem = Cfg::TILE * (int) sizeof(KWord<L>);
-    if (!attr_done) {
+    attr_once.run([&](int) {
         KC_CUDA(cudaFuncSetAttribute(kc_sort_local_kernel<L, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, local_smem));
         KC_CUDA(cudaFuncSetAttribute(kc_sort_scatter_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, scatter_smem));
-        attr_done = true;
-    }
+    });
 
     SortBucket root;
     root.off = 0;

@@ -205,11 +205,8 @@ u64 kc_extract_kmers(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool compl
     ex.fill_bytes(counter, 0, 8);
     u64 blocks = kc_div_up(n_bytes, (u64) KC_EX_THREADS * KC_EX_STRIP);
     const int smem = (L == 1 && !WITH_POS) ? 8 * 32 * KC_EX_STRIP * 8 : 0;
-    static bool attr_done = false;
-    if (!attr_done && smem) {
-        KC_CUDA(cudaFuncSetAttribute(kc_extract_kernel<L, WITH_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
-    }
+    static KcDevOnce attr_once;  // function attributes are per device
+    if (smem) attr_once.run([&](int) { KC_CUDA(cudaFuncSetAttribute(kc_extract_kernel<L, WITH_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); });
     {
         // algorithmic bytes: the input once; the M item bytes written are added below once M is known
         CudaExec::Scope sc(ex, KP_EXTRACT, n_bytes);
