@@ -85,7 +85,7 @@ static bool parse_devices(const std::string &arg, std::vector<int> &out) {
     while (at <= arg.size()) {
         const size_t comma = std::min(arg.find(',', at), arg.size());
         const std::string part = arg.substr(at, comma - at);
-        if (part.empty()) return false;
+        if (part.empty() || part.find_first_not_of("0123456789-") != std::string::npos) return false;
         const size_t dash = part.find('-');
         try {
             if (dash == std::string::npos) {
@@ -251,7 +251,8 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
     rc = rc_init;
     const double t_init = now_ms();
     if (rc != KC_OK) {
-        std::cerr << "cannot initialise CUDA device " << device << ": " << kc_strerror(rc) << " (this build has no CPU path)" << std::endl;
+        std::cerr << "cannot initialise CUDA device " << device << (multi ? " (and the other devices of -g; all need peer access to each other)" : "") << ": "
+                  << kc_strerror(rc) << " (this build has no CPU path)" << std::endl;
         return 1;
     }
     kc_params p{k, complements ? 1 : 0, (int) min_frequency, assume_simplitigs ? 1 : 0, mask_path.empty() ? 0 : 1};
@@ -431,7 +432,8 @@ static int camel_optimize(int argc, char **argv) {
     kc_ctx *ctx = nullptr;
     int rc = kc_init(device, nullptr, &ctx);
     if (rc != KC_OK) {
-        std::cerr << "cannot initialise CUDA device " << device << ": " << kc_strerror(rc) << " (this build has no CPU path)" << std::endl;
+        std::cerr << "cannot initialise CUDA device " << device << (multi ? " (and the other devices of -g; all need peer access to each other)" : "") << ": "
+                  << kc_strerror(rc) << " (this build has no CPU path)" << std::endl;
         return 1;
     }
     const uint64_t len = n_recs ? rec_len[0] : 0;  // ReadMaskedSuperstring: the first record (src/parser.h:145-150)

@@ -70,8 +70,42 @@ struct GrpDev {  // the group as a kernel sees it (by-value kernel parameter)
     u32 off_sig, off_cells, off_cnt;
 };
 
+// Ranks that live in ONE process (kc_init_multi) do not spin on the device: a wait is "every rank has queued its signal (host
+// barrier between the rank threads), then my stream waits for the events the others recorded behind theirs".  Nothing busy-
+// waits on a GPU, so ranks may share a device (tests on a one-GPU box; a spinning kernel there would starve the very rank it
+// waits for whenever that rank's host thread needs the device to go idle — lazy module loading, cudaMalloc).  The host threads
+// still never wait for a GPU, only for each other.
+#include <condition_variable>
+struct GrpHostSync {
+    std::mutex m;
+    std::condition_variable cv;
+    int n = 0, arrived = 0;
+    u64 generation = 0;
+    bool aborted = false;
+    cudaEvent_t ev[KC_MAX_PEERS][2] = {};
+    bool arrive_and_wait() {  // false: some rank left the job (abort())
+        std::unique_lock<std::mutex> lk(m);
+        if (aborted) return false;
+        const u64 gen = generation;
+        if (++arrived == n) {
+            arrived = 0;
+            ++generation;
+            cv.notify_all();
+            return true;
+        }
+        cv.wait(lk, [&] { return generation != gen || aborted; });
+        return !aborted;
+    }
+    void abort() {
+        std::lock_guard<std::mutex> lk(m);
+        aborted = true;
+        cv.notify_all();
+    }
+};
+
 struct KcGroup {
     int n = 0, rank = 0;
+    GrpHostSync *hs = nullptr;            // != nullptr: in-process group (events + host barrier instead of the wait kernel)
     GrpLayout lay;
     char *heap = nullptr;                 // own heap (cudaMalloc by the library)
     char *peer[KC_MAX_PEERS] = {};        // every rank's heap as mapped here (peer[rank] = heap)
@@ -168,8 +202,20 @@ inline void kc_grp_signal(KcGroup &G, CudaExec &ex, u32 seq, const u32 *cnt0 = n
     kc_grp_signal_kernel<<<1, 256, 0, ex.stream>>>(G.dev(), seq, cnt0, n_digits, cap, cells);
     ++ex.launches;
     KC_CUDA(cudaGetLastError());
+    if (G.hs) KC_CUDA(cudaEventRecord(G.hs->ev[G.rank][seq & 1], ex.stream));
 }
+// Signals and waits strictly alternate on every rank (signal s, wait s, signal s + 1, ...), which is what lets two events per
+// rank do: nobody re-records event s & 1 before every rank has queued its wait on it (it passed the barrier of wait s + 1).
 inline void kc_grp_wait(KcGroup &G, CudaExec &ex, u32 seq, u32 *status) {
+    if (G.hs) {
+        if (!G.hs->arrive_and_wait()) {
+            G.failed = true;
+            KC_THROW(KC_ERR_INTERNAL, "another rank of the group failed");
+        }
+        for (int s = 0; s < G.n; ++s)
+            if (s != G.rank) KC_CUDA(cudaStreamWaitEvent(ex.stream, G.hs->ev[s][seq & 1], 0));
+        return;
+    }
     kc_grp_wait_kernel<<<1, 32, 0, ex.stream>>>(G.dev(), seq, status, G.timeout_ns);
     ++ex.launches;
     KC_CUDA(cudaGetLastError());

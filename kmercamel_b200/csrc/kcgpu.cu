@@ -1166,6 +1166,7 @@ int kc_group_plan(int n_ranks, int rank, int k, uint64_t n_bytes, uint64_t *plan
 struct kc_group {
     int n = 0;
     kc_ctx *ctx[KC_MAX_PEERS] = {};
+    GrpHostSync hs;
     u8 *pin_out = nullptr;
     size_t pin_out_cap = 0;
     std::mutex out_mutex;
@@ -1203,6 +1204,12 @@ int kc_init_multi(int n_gpus, const int *device_ids, kc_group **out) {
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) rc = KC_ERR_CUDA;
             (void) cudaGetLastError();
         }
+    g->hs.n = n_gpus;
+    for (int r = 0; r < n_gpus && rc == KC_OK; ++r) {
+        if (cudaSetDevice(device_ids[r]) != cudaSuccess) rc = KC_ERR_CUDA;
+        for (int i = 0; i < 2 && rc == KC_OK; ++i)
+            if (cudaEventCreateWithFlags(&g->hs.ev[r][i], cudaEventDisableTiming) != cudaSuccess) rc = KC_ERR_CUDA;
+    }
     if (rc != KC_OK) {
         kc_group_destroy(g);
         return rc;
@@ -1216,6 +1223,9 @@ void kc_group_destroy(kc_group *g) {
     group_release_heaps(g);
     for (int r = 0; r < g->n; ++r)
         if (g->ctx[r]) kc_destroy(g->ctx[r]);
+    for (int r = 0; r < g->n; ++r)
+        for (int i = 0; i < 2; ++i)
+            if (g->hs.ev[r][i]) cudaEventDestroy(g->hs.ev[r][i]);
     if (g->pin_out) cudaFreeHost(g->pin_out);
     delete g;
 }
@@ -1243,8 +1253,15 @@ int kc_group_compute(kc_group *g, const kc_params *p, const kc_input *in, kc_out
                 g->ctx[r]->fast_overflow_bytes = c0->fast_overflow_bytes;
                 group_alloc_common(g->ctx[r], g->n, r, limbs == 1 ? 31 : (limbs == 2 ? 63 : 127), cap, true);
             }
-            for (int r = 0; r < g->n; ++r)
+            for (int r = 0; r < g->n; ++r) {
                 for (int s = 0; s < g->n; ++s) g->ctx[r]->grp.peer[s] = g->ctx[s]->grp.heap;
+                g->ctx[r]->grp.hs = &g->hs;
+            }
+        }
+        {   // a failed call may have left the barrier half way
+            std::lock_guard<std::mutex> lk(g->hs.m);
+            g->hs.arrived = 0;
+            g->hs.aborted = false;
         }
         // every allocation happens BEFORE the first kernel of the job is queued anywhere: cudaMalloc / cudaFree wait for the whole
         // device, which would include a peer rank's wait kernel when two ranks share a GPU (tests)
@@ -1323,11 +1340,15 @@ int kc_group_compute(kc_group *g, const kc_params *p, const kc_input *in, kc_out
             char buf[512];
             std::snprintf(buf, sizeof(buf), "rank %d: %s (%s:%d)", r, e.what, e.file, e.line);
             R.what = buf;
-            if (e.code != KC_ERR_EMPTY) ctx->grp.failed = true;
+            if (e.code != KC_ERR_EMPTY) {  // "no k-mers" is found by every rank at the same point; anything else strands the others
+                ctx->grp.failed = true;
+                g->hs.abort();
+            }
         } catch (...) {
             R.code = KC_ERR_INTERNAL;
             R.what = "rank " + std::to_string(r) + ": unknown failure";
             ctx->grp.failed = true;
+            g->hs.abort();
         }
     };
     std::vector<std::thread> th;
