@@ -432,8 +432,7 @@ static int camel_optimize(int argc, char **argv) {
     kc_ctx *ctx = nullptr;
     int rc = kc_init(device, nullptr, &ctx);
     if (rc != KC_OK) {
-        std::cerr << "cannot initialise CUDA device " << device << (multi ? " (and the other devices of -g; all need peer access to each other)" : "") << ": "
-                  << kc_strerror(rc) << " (this build has no CPU path)" << std::endl;
+        std::cerr << "cannot initialise CUDA device " << device << ": " << kc_strerror(rc) << " (this build has no CPU path)" << std::endl;
         return 1;
     }
     const uint64_t len = n_recs ? rec_len[0] : 0;  // ReadMaskedSuperstring: the first record (src/parser.h:145-150)

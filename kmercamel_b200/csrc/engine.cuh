@@ -237,7 +237,8 @@ template <class Exec, int L> struct Engine {
     PathState st;
     bool strict;
     bool lower_bound;
-    bool use_small = true;  // hand the tail of the level loop to the single-CTA kernel (small_engine.cuh)
+    bool use_small = true;      // hand the tail of the level loop to the single-CTA kernel (small_engine.cuh)
+    int small_threads_opt = 0;  // 0 = by size; 256 / 512 (option "small_threads")
     EngineStats stats;
 
     // live end lists (ascending node id); nullptr = identity 0..N-1
@@ -363,7 +364,8 @@ template <class Exec, int L> struct Engine {
                 typename Exec::Scope sc(ex, KP_SMALL_ENGINE, 0);
                 // (measured: one warp instead of 256 threads makes the kernel 1.7x slower on configs[1] — the levels are
                 // bound by the work per phase, not by the block barriers)
-                const unsigned small_threads = 256u;
+                // 512 threads once the tuple phases (level mask, bitonic sort) have more than two items per thread to share out
+                const unsigned small_threads = small_threads_opt ? (unsigned) small_threads_opt : (n_s + n_p > 512 ? 512u : 256u);
                 kc_small_engine_kernel<L><<<1, small_threads, SmallCfg<L>::SMEM, ex.stream>>>(a);
             }
             ++ex.launches;

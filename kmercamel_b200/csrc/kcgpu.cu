@@ -49,6 +49,7 @@ struct kc_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_ev[KC_H2D_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
     bool small_engine = true;
+    int small_threads = 0;   // 0 = chosen by the number of free ends (option "small_threads": 256 or 512)
     bool sparse_switch = true;  // src/main.cpp:175 (option "sparse_switch" = 0 keeps the runs as nodes whatever their number)
     KsfTuning fast;          // histogram-free set construction (kmerset_fast.cuh); KC_FAST_* environment knobs for tests
     u64 fast_runs = 0, fast_fallbacks = 0;
@@ -347,6 +348,7 @@ void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params
     KC_TRACE_POINT("pipeline: nodes ready");
     Engine<CudaExec, L> eng(ex, nv, /*strict=*/p.assume_simplitigs != 0, lower_bound);
     eng.use_small = ctx->small_engine;
+    eng.small_threads_opt = ctx->small_threads;
     eng.init_state();
     eng.run();
     KC_TRACE_POINT("pipeline: engine done");
@@ -492,6 +494,7 @@ void overlap_only(kc_ctx *ctx, CudaExec &ex, const uint64_t *first, const uint64
     nv.complements = complements;
     Engine<CudaExec, L> eng(ex, nv, strict, lower_bound);
     eng.use_small = ctx->small_engine;
+    eng.small_threads_opt = ctx->small_threads;
     eng.init_state();
     eng.run();
     eng.check_small();
@@ -649,6 +652,8 @@ int kc_init(int device, void *stream, kc_ctx **out) {
         KC_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->pin_small), kc_ctx::KC_PIN_SMALL, cudaHostAllocDefault));
         if (const char *e = std::getenv("KC_FAST_SET")) ctx->fast.enabled = std::atoi(e) != 0;
         if (const char *e = std::getenv("KC_FAST_MAX_CTAS")) ctx->fast.max_ctas = std::atoi(e);
+        if (const char *e = std::getenv("KC_FAST_TMA")) ctx->fast.tma = std::atoi(e) != 0;
+        if (const char *e = std::getenv("KC_SMALL_THREADS")) ctx->small_threads = std::atoi(e);
     } catch (const KcError &e) {
         int code = e.code;
         kc_destroy(ctx);
@@ -1401,6 +1406,10 @@ int kc_set_option(kc_ctx *ctx, const char *name, int value) {
         ctx->sparse_switch = value != 0;
         return KC_OK;
     }
+    if (std::strcmp(name, "small_threads") == 0 && (value == 0 || value == 256 || value == 512)) {
+        ctx->small_threads = value;
+        return KC_OK;
+    }
     if (std::strcmp(name, "small_engine") == 0) {
         ctx->small_engine = value != 0;
         return KC_OK;
@@ -1417,6 +1426,10 @@ int kc_set_option(kc_ctx *ctx, const char *name, int value) {
     }
     if (std::strcmp(name, "fast_sigmas") == 0 && value >= 0) {
         ctx->fast.sigmas = (double) value;
+        return KC_OK;
+    }
+    if (std::strcmp(name, "fast_tma") == 0 && (value == 0 || value == 1)) {
+        ctx->fast.tma = value != 0;
         return KC_OK;
     }
     if (std::strcmp(name, "fast_heuristics") == 0 && (value == 0 || value == 1)) {

@@ -61,9 +61,15 @@ inline KsfFlagPeers kc_ksf_own_flags(u32 *flags) {
 
 #ifdef __CUDACC__
 
-KC_D void kc_flag_clear_all(const KsfFlagPeers &fp, u32 pos) {
+// MULTI = false is the single-GPU instance: one RED on the GPU's own array, nothing else in the instruction stream (the loop over
+// the ranks cost the leaf resolve 9 % on one GPU although it almost never runs).
+template <bool MULTI> KC_D void kc_flag_clear_all(const KsfFlagPeers &fp, u32 pos) {
     const u32 m = ~(1u << (pos & 31));
-    for (int r = 0; r < fp.n; ++r) atomicAnd(&fp.f[r][pos >> 5], m);
+    if (MULTI) {
+        for (int r = 0; r < fp.n; ++r) atomicAnd(&fp.f[r][pos >> 5], m);
+    } else {
+        atomicAnd(&fp.f[0][pos >> 5], m);
+    }
 }
 
 // status[0] = 1: some slot overflowed (the flags are incomplete and must be discarded)
@@ -231,13 +237,44 @@ KC_D void kc_cp_async16(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
 }
 KC_D void kc_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+
+// ---- 1-D bulk copies (TMA) completing on an mbarrier: one elected thread arms the barrier with the byte count and issues the
+// copy; the copy engine streams the bytes into shared memory without any thread issuing per-chunk loads, and every thread that
+// needs the data waits on the barrier's phase.  Addresses and sizes are multiples of 16 bytes (slots are 128-byte aligned,
+// ksf_plan.h).  SASS: UBLKCP (the copy) and SYNCS (mbarrier arrive / try_wait).
+KC_D u32 kc_smem_u32(const void *p) { return (u32) __cvta_generic_to_shared(p); }
+KC_D void kc_mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(kc_smem_u32(bar)), "r"(count) : "memory");
+}
+KC_D void kc_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+KC_D void kc_mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(kc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+KC_D void kc_bulk_g2s(void *smem_dst, const void *gmem_src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(kc_smem_u32(smem_dst)), "l"(gmem_src),
+                 "r"(bytes), "r"(kc_smem_u32(bar))
+                 : "memory");
+}
+KC_D void kc_mbar_wait(u64 *bar, u32 parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "KC_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra KC_DONE;\n\t"
+        "bra KC_WAIT;\n\t"
+        "KC_DONE:\n\t"
+        "}" ::"r"(kc_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 KC_D void kc_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 
 // The flags arrive with the bit of every valid window set (written by level 0); every atomicMin that folds a duplicate knocks
 // out exactly one position — the larger of the two it compared — so only the DUPLICATES cost a scattered RED and the kept
 // bits are never touched.  This kernel serves -z Z > 1 (COUNTED); -z 1 takes kc_ksf_resolve2_kernel.
-template <int L, bool COUNTED>
+template <int L, bool COUNTED, bool MULTI>
 __global__ void __launch_bounds__(256) kc_ksf_resolve_kernel(const KWord<L> *__restrict__ keys, const u32 *__restrict__ pos, const u32 *__restrict__ cnt,
                                                              u32 n_leaf, KsfFlagPeers fl, u32 min_count, kc_ull *n_unique, u32 *status) {
     constexpr u32 CAP = KSF_LEAF_CAP;
@@ -329,7 +366,7 @@ __global__ void __launch_bounds__(256) kc_ksf_resolve_kernel(const KWord<L> *__r
                     } else if (sk[o] == key) {
                         const u32 mine = sp[i];
                         const u32 was = atomicMin(&sp[o], mine);
-                        kc_flag_clear_all(fl, was > mine ? was : mine);
+                        kc_flag_clear_all<MULTI>(fl, was > mine ? was : mine);
                         if (COUNTED) atomicAdd(&occ[o], 1u);
                     } else {
                         u32 s = (u32) (h >> 43) & (T2N - 1);
@@ -342,7 +379,7 @@ __global__ void __launch_bounds__(256) kc_ksf_resolve_kernel(const KWord<L> *__r
                             if (sk[old] == key) {
                                 const u32 mine = sp[i];
                                 const u32 was = atomicMin(&sp[old], mine);
-                                kc_flag_clear_all(fl, was > mine ? was : mine);
+                                kc_flag_clear_all<MULTI>(fl, was > mine ? was : mine);
                                 if (COUNTED) atomicAdd(&occ[old], 1u);
                                 break;
                             }
@@ -364,7 +401,7 @@ __global__ void __launch_bounds__(256) kc_ksf_resolve_kernel(const KWord<L> *__r
                     if (!COUNTED || occ[i] >= min_count) {
                         ++kept;
                     } else {
-                        kc_flag_clear_all(fl, sp[i]);  // too few occurrences: the surviving (smallest) position goes as well
+                        kc_flag_clear_all<MULTI>(fl, sp[i]);  // too few occurrences: the surviving (smallest) position goes as well
                     }
                 }
             }
@@ -395,12 +432,15 @@ KC_D void kc_cp_async8(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
 }
 
-template <int L, int THREADS, bool BAL = false>
+// TMA = true: the leaf arrives by two bulk copies (keys, positions) that one thread issues and that complete on an mbarrier, instead
+// of every thread issuing its own cp.async chunks and waiting for its own group; the items are then dealt out to the threads
+// round-robin (any thread may read any item once the barrier's phase has flipped).
+template <int L, int THREADS, bool MULTI, bool TMA, bool BAL = false>
 __global__ void __launch_bounds__(THREADS) kc_ksf_resolve2_kernel(const KWord<L> *__restrict__ keys, const u32 *__restrict__ pos, const u32 *__restrict__ cnt,
                                                                   u32 n_leaf, KsfFlagPeers fl, kc_ull *n_unique, u32 *status) {
     constexpr u32 CAP = KSF_LEAF_CAP;
     constexpr u32 T1N = 2 * CAP, T2N = CAP;
-    constexpr int KPC = (BAL && L == 1) ? 1 : (16 / (int) sizeof(KWord<L>) > 0 ? 16 / (int) sizeof(KWord<L>) : 1);
+    constexpr int KPC = (TMA || (BAL && L == 1)) ? 1 : (16 / (int) sizeof(KWord<L>) > 0 ? 16 / (int) sizeof(KWord<L>) : 1);
     constexpr int CPK = (int) sizeof(KWord<L>) / 16 > 0 ? (int) sizeof(KWord<L>) / 16 : 1;
     constexpr int UNITS = (int) CAP / KPC / THREADS;  // copy units (and hash rounds) per thread
     constexpr int NI = UNITS * KPC;                   // items per thread
@@ -410,9 +450,19 @@ __global__ void __launch_bounds__(THREADS) kc_ksf_resolve2_kernel(const KWord<L>
     u32 *sp0 = reinterpret_cast<u32 *>(sk0 + 2 * CAP);
     u32 *T2a = sp0 + 2 * CAP;                                  // [2][T2N]
     u16 *T1a = reinterpret_cast<u16 *>(T2a + 2 * T2N);         // [2][T1N]
+    __shared__ __align__(8) u64 full[2];  // TMA: "leaf in staging buffer b has landed"
     const u64 stride = gridDim.x;
     u64 c = blockIdx.x;
     if (c >= n_leaf) return;
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            kc_mbar_init(&full[0], 1);
+            kc_mbar_init(&full[1], 1);
+            kc_mbar_fence_init();
+        }
+        __syncthreads();
+    }
+    u32 full_phase = 0;  // bit b: parity to wait for on full[b]
     auto leaf_size = [&](u64 leaf) -> u32 {
         if (leaf >= n_leaf) return 0u;
         u32 sz = cnt[leaf];
@@ -423,6 +473,15 @@ __global__ void __launch_bounds__(THREADS) kc_ksf_resolve2_kernel(const KWord<L>
         return sz;
     };
     auto fetch = [&](u64 bucket, u32 size, int buf) {
+        if constexpr (TMA) {
+            if (bucket < n_leaf && threadIdx.x == 0) {
+                const u32 kb = (size * (u32) sizeof(KWord<L>) + 15u) & ~15u, pb = (size * 4u + 15u) & ~15u;
+                kc_mbar_expect_tx(&full[buf], kb + pb);
+                if (kb) kc_bulk_g2s(sk0 + (u32) buf * CAP, keys + bucket * CAP, kb, &full[buf]);
+                if (pb) kc_bulk_g2s(sp0 + (u32) buf * CAP, pos + bucket * CAP, pb, &full[buf]);
+            }
+            return;
+        }
         if (bucket < n_leaf) {
             const char *gk = reinterpret_cast<const char *>(keys + bucket * CAP);
             const char *gp = reinterpret_cast<const char *>(pos + bucket * CAP);
@@ -460,7 +519,12 @@ __global__ void __launch_bounds__(THREADS) kc_ksf_resolve2_kernel(const KWord<L>
         u32 *sp = sp0 + (u32) buf * CAP;
         u32 *T2 = T2a + (u32) buf * T2N;
         u16 *T1 = T1a + (u32) buf * T1N;
-        kc_cp_async_wait_group<0>();  // the thread's own key units of leaf c have landed
+        if (TMA) {
+            kc_mbar_wait(&full[buf], (full_phase >> buf) & 1u);  // leaf c has landed (all of it, for every thread)
+            full_phase ^= 1u << buf;
+        } else {
+            kc_cp_async_wait_group<0>();  // the thread's own key units of leaf c have landed
+        }
         if (threadIdx.x < 256) reinterpret_cast<uint4 *>(T2)[threadIdx.x] = make_uint4(KC_NONE, KC_NONE, KC_NONE, KC_NONE);  // T2N = 256 x 4 slots
         // A: all keys, then all hashes, then all table stores
         KWord<L> key[NI];
@@ -501,7 +565,7 @@ __global__ void __launch_bounds__(THREADS) kc_ksf_resolve2_kernel(const KWord<L>
             } else if (sk[o[m]] == key[m]) {
                 const u32 mine = sp[i];
                 const u32 was = atomicMin(&sp[o[m]], mine);
-                kc_flag_clear_all(fl, was > mine ? was : mine);
+                kc_flag_clear_all<MULTI>(fl, was > mine ? was : mine);
             } else {
                 u32 s = h2[m];
                 while (true) {
@@ -513,7 +577,7 @@ __global__ void __launch_bounds__(THREADS) kc_ksf_resolve2_kernel(const KWord<L>
                     if (sk[old] == key[m]) {
                         const u32 mine = sp[i];
                         const u32 was = atomicMin(&sp[old], mine);
-                        kc_flag_clear_all(fl, was > mine ? was : mine);
+                        kc_flag_clear_all<MULTI>(fl, was > mine ? was : mine);
                         break;
                     }
                     s = (s + 1) & (T2N - 1);
@@ -534,7 +598,7 @@ __global__ void __launch_bounds__(THREADS) kc_ksf_resolve2_kernel(const KWord<L>
         }
         buf ^= 1;
     }
-    kc_cp_async_wait_group<0>();
+    if (!TMA) kc_cp_async_wait_group<0>();
 #pragma unroll
     for (int o2 = 16; o2 > 0; o2 >>= 1) kept += __shfl_down_sync(0xFFFFFFFFu, kept, o2);
     if ((threadIdx.x & 31) == 0 && kept) atomicAdd(n_unique, (kc_ull) kept);
@@ -545,7 +609,7 @@ __global__ void __launch_bounds__(THREADS) kc_ksf_resolve2_kernel(const KWord<L>
 // tile after the current one streams into a shared-memory input buffer with cp.async while the current tile is ranked,
 // staged and written out: a thread takes its items out of the input buffer into registers, and the barrier that ends the
 // ranking phase frees the buffer for the next copy.  Tiles are contiguous in their parent slot, slots are 128-byte aligned.
-template <int L, int TILE, int MINB, int THREADS = 256>
+template <int L, int TILE, int MINB, int THREADS, bool TMA>
 __global__ void __launch_bounds__(THREADS, MINB) kc_ksf_scatter_pf_kernel(const KWord<L> *__restrict__ ksrc, const u32 *__restrict__ psrc, KWord<L> *__restrict__ kdst,
                                                                 u32 *__restrict__ pdst, const u32 *__restrict__ P_size, const u32 *__restrict__ tile_prefix,
                                                                 u32 nP, u64 capP, u32 tiles_per_cta, int shift, int bits, u32 *C_cnt, u32 capC, u32 *status,
@@ -562,12 +626,21 @@ __global__ void __launch_bounds__(THREADS, MINB) kc_ksf_scatter_pf_kernel(const 
     __shared__ u64 dbase[256];  // slot index of the digit's first item of this tile, minus its staged position: at = dbase + q
     __shared__ u32 qlim[256];   // staged positions below this still fit into the child's slot
     __shared__ u32 sw[THREADS / 32];
+    __shared__ __align__(8) u64 full;  // TMA: "the tile in the input buffer has landed"
     const u32 n_tiles = tile_prefix[nP];
     const u32 t0 = blockIdx.x * tiles_per_cta;
     const u32 t1 = min(n_tiles, t0 + tiles_per_cta);
     if (t0 >= t1) return;
     u32 b = kc_upper_bound_u32(tile_prefix, nP + 1, t0) - 1;
     if (threadIdx.x < 256) cnt[threadIdx.x] = 0;
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            kc_mbar_init(&full, 1);
+            kc_mbar_fence_init();
+        }
+        __syncthreads();
+    }
+    u32 full_phase = 0;
     bool over = false;
     // tile t of the CTA -> (parent bucket, first item inside the source arrays, items)
     auto describe = [&](u32 t, u32 &bb, u64 &first, u32 &n_here) {
@@ -577,6 +650,15 @@ __global__ void __launch_bounds__(THREADS, MINB) kc_ksf_scatter_pf_kernel(const 
         first = (u64) bb * capP + start;
     };
     auto prefetch = [&](u64 first, u32 n_here) {
+        if constexpr (TMA) {  // two bulk copies issued by one thread; tiles start on 128-byte boundaries of their slot
+            if (threadIdx.x == 0) {
+                const u32 kb = (n_here * (u32) sizeof(KWord<L>) + 15u) & ~15u, pb = (n_here * 4u + 15u) & ~15u;
+                kc_mbar_expect_tx(&full, kb + pb);
+                if (kb) kc_bulk_g2s(in_k, ksrc + first, kb, &full);
+                if (pb) kc_bulk_g2s(in_p, psrc + first, pb, &full);
+            }
+            return;
+        }
         const char *gk = reinterpret_cast<const char *>(ksrc + first);
         const char *gp = reinterpret_cast<const char *>(psrc + first);
         const u32 kch = (n_here * (u32) sizeof(KWord<L>) + 15) / 16, pch = (n_here * 4 + 15) / 16;
@@ -589,7 +671,12 @@ __global__ void __launch_bounds__(THREADS, MINB) kc_ksf_scatter_pf_kernel(const 
     describe(t0, b, first, n_here);
     prefetch(first, n_here);
     for (u32 t = t0; t < t1; ++t) {
-        kc_cp_async_wait_all();
+        if (TMA) {
+            kc_mbar_wait(&full, full_phase);
+            full_phase ^= 1u;
+        } else {
+            kc_cp_async_wait_all();
+        }
         __syncthreads();  // tile t is complete in the input buffer; the write-out of tile t - 1 has left the staging buffers
         KWord<L> item[ITEMS];
         u32 pay[ITEMS];
@@ -693,12 +780,16 @@ template <int L> struct KsfKernels {  // the kernel instances this construction 
         const int d = once.run([&](int dv) {
             KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter0_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem0()));
             KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter0_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem0()));
-            KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_pf_kernel<L, TILE1, 2, THREADS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1()));
-            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve2_kernel<L, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r(false)));
-            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r(true)));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_pf_kernel<L, TILE1, 2, THREADS1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1()));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_scatter_pf_kernel<L, TILE1, 2, THREADS1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1()));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve2_kernel<L, 256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r(false)));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve2_kernel<L, 256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r(false)));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve2_kernel<L, 256, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r(false)));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r(true)));
+            KC_CUDA(cudaFuncSetAttribute(kc_ksf_resolve_kernel<L, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r(true)));
             dev[dv].n_sm = kc_sm_count(dv);
-            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev[dv].occ_r[0], kc_ksf_resolve2_kernel<L, 256>, 256, smem_r(false)));
-            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev[dv].occ_r[1], kc_ksf_resolve_kernel<L, true>, 256, smem_r(true)));
+            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev[dv].occ_r[0], kc_ksf_resolve2_kernel<L, 256, false, true>, 256, smem_r(false)));
+            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev[dv].occ_r[1], kc_ksf_resolve_kernel<L, true, false>, 256, smem_r(true)));
         });
         return dev[d];
     }
@@ -723,9 +814,14 @@ void kc_ksf_level(CudaExec &ex, const KWord<L> *ksrc, const u32 *psrc, KWord<L> 
     const u32 ctas = (u32) kc_div_up(tiles_ub, tiles_per_cta);
     {
         CudaExec::Scope sc(ex, KP_SORT_SCATTER, 2 * items_ub * (sizeof(KWord<L>) + 4));
-        kc_ksf_scatter_pf_kernel<L, KK::TILE1, 2, KK::THREADS1><<<ctas, KK::THREADS1, KK::smem1(), st>>>(ksrc, psrc, kdst, pdst, P_size, tile_prefix, nP, capP,
-                                                                                                      tiles_per_cta, shift, bits, cnt_next, (u32) capC,
-                                                                                                      status, pdiv);
+        if (tune.tma)
+            kc_ksf_scatter_pf_kernel<L, KK::TILE1, 2, KK::THREADS1, true><<<ctas, KK::THREADS1, KK::smem1(), st>>>(ksrc, psrc, kdst, pdst, P_size, tile_prefix, nP, capP,
+                                                                                                                tiles_per_cta, shift, bits, cnt_next, (u32) capC,
+                                                                                                                status, pdiv);
+        else
+            kc_ksf_scatter_pf_kernel<L, KK::TILE1, 2, KK::THREADS1, false><<<ctas, KK::THREADS1, KK::smem1(), st>>>(ksrc, psrc, kdst, pdst, P_size, tile_prefix, nP, capP,
+                                                                                                                 tiles_per_cta, shift, bits, cnt_next, (u32) capC,
+                                                                                                                 status, pdiv);
         ++ex.launches;
         KC_CUDA(cudaGetLastError());
     }
@@ -735,7 +831,7 @@ void kc_ksf_level(CudaExec &ex, const KWord<L> *ksrc, const u32 *psrc, KWord<L> 
 // Leaf slots (KSF_LEAF_CAP items each) -> losers cleared in fl, *n_unique += kept k-mers.
 template <int L>
 void kc_ksf_resolve(CudaExec &ex, const KWord<L> *keys, const u32 *pos, const u32 *cnt, u64 n_leaf, const KsfFlagPeers &fl, int min_freq, kc_ull *n_unique,
-                    u32 *status, u64 items_ub) {
+                    u32 *status, u64 items_ub, bool tma = true) {
     typedef KsfKernels<L> KK;
     if (n_leaf >= 0xFFFFFFFFULL) KC_THROW(KC_ERR_TOO_LARGE, "too many leaf buckets");
     const typename KK::Dev &dv = KK::prepare();
@@ -743,8 +839,12 @@ void kc_ksf_resolve(CudaExec &ex, const KWord<L> *keys, const u32 *pos, const u3
     const u32 fit = (u32) (dv.n_sm * (dv.occ_r[counted] > 0 ? dv.occ_r[counted] : 1));
     const u32 grid = (u32) n_leaf < fit ? (u32) n_leaf : fit;
     CudaExec::Scope sc(ex, KP_KS_RESOLVE, items_ub * (sizeof(KWord<L>) + 4));
-    if (counted) kc_ksf_resolve_kernel<L, true><<<grid, 256, KK::smem_r(true), ex.stream>>>(keys, pos, cnt, (u32) n_leaf, fl, (u32) min_freq, n_unique, status);
-    else kc_ksf_resolve2_kernel<L, 256><<<grid, 256, KK::smem_r(false), ex.stream>>>(keys, pos, cnt, (u32) n_leaf, fl, n_unique, status);
+    const bool multi = fl.n > 1;
+    if (counted && multi) kc_ksf_resolve_kernel<L, true, true><<<grid, 256, KK::smem_r(true), ex.stream>>>(keys, pos, cnt, (u32) n_leaf, fl, (u32) min_freq, n_unique, status);
+    else if (counted) kc_ksf_resolve_kernel<L, true, false><<<grid, 256, KK::smem_r(true), ex.stream>>>(keys, pos, cnt, (u32) n_leaf, fl, (u32) min_freq, n_unique, status);
+    else if (multi) kc_ksf_resolve2_kernel<L, 256, true, true><<<grid, 256, KK::smem_r(false), ex.stream>>>(keys, pos, cnt, (u32) n_leaf, fl, n_unique, status);
+    else if (tma) kc_ksf_resolve2_kernel<L, 256, false, true><<<grid, 256, KK::smem_r(false), ex.stream>>>(keys, pos, cnt, (u32) n_leaf, fl, n_unique, status);
+    else kc_ksf_resolve2_kernel<L, 256, false, false><<<grid, 256, KK::smem_r(false), ex.stream>>>(keys, pos, cnt, (u32) n_leaf, fl, n_unique, status);
     ++ex.launches;
     KC_CUDA(cudaGetLastError());
 }
@@ -821,7 +921,7 @@ bool kc_kmerset_build_fast(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool
             if (c) atomicAdd(m_cell, (kc_ull) c);
         });
     }
-    kc_ksf_resolve<L>(ex, kb[last & 1], pb[last & 1], cnt_cur, pl.n_leaf, fl, min_freq, reinterpret_cast<kc_ull *>(cells), status, n_bytes);
+    kc_ksf_resolve<L>(ex, kb[last & 1], pb[last & 1], cnt_cur, pl.n_leaf, fl, min_freq, reinterpret_cast<kc_ull *>(cells), status, n_bytes, tune.tma);
     ex.arena->release(base_mark);
     return true;
 }

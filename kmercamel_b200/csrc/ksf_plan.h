@@ -18,6 +18,7 @@ struct KsfTuning {
     uint32_t leaf_target = 768;   // mean leaf size aimed at (the leaf slot holds KSF_LEAF_CAP)
     double sigmas = 8.0;     // slot = mean + sigmas * sqrt(mean) (+ 2 %) items; 0 forces overflows (tests)
     uint64_t min_items = 1u << 16;  // smaller inputs take the exact path (nothing to gain)
+    bool tma = true;         // tiles / leaves stream in through 1-D bulk copies (TMA) + mbarrier; false: per-thread cp.async (kept for A/B timing)
     int max_ctas = 148 * 16; // level >= 1 scatter grid: at most this many CTAs, each walking a run of consecutive tiles
 };
 

@@ -32,7 +32,7 @@ template <int L> struct SmallEngineArgs {
     u32 *out;  // [0] error, [1] levels run, [2] groups, [3] edges, [4] ban rounds, [5] bans, [8 + d] clocks spent in level d (KC_TRACE)
 };
 
-template <int L> __global__ void __launch_bounds__(256) kc_small_engine_kernel(SmallEngineArgs<L> a) {
+template <int L> __global__ void __launch_bounds__(512) kc_small_engine_kernel(SmallEngineArgs<L> a) {
     typedef KWord<L + 1> TW;
     constexpr u32 TCAP = SmallCfg<L>::T, HCAP = SmallCfg<L>::H;
     extern __shared__ __align__(16) unsigned char kc_smem_raw[];
