@@ -281,8 +281,11 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
                 u64 cnt = q.length(v) - (s.edge_from[v] != KC_NONE ? (u64) s.ovl[v] : 0);
                 if (cnt > KC_EMIT_SHORT) {
                     u64 off = total - da[v];
-                    u64 span = off + cnt - (off & ~(u64) 15);  // bytes from the aligned start to the end
-                    c = (u32) ((span + KC_EMIT_CHUNK - 1) / KC_EMIT_CHUNK);
+                    // the node's chunks start at its 16-byte aligned first byte; only those that meet the slice [s_begin, s_end) of this
+                    // rank are enumerated (a rank of an 8-GPU job used to walk all chunks of the whole superstring: 0.26 ms instead of 0.06)
+                    const u64 a0 = off & ~(u64) 15, a1 = off + cnt;
+                    const u64 lo = a0 > s_begin ? a0 : s_begin, hi = a1 < s_end ? a1 : s_end;
+                    if (lo < hi) c = (u32) ((hi - a0 + KC_EMIT_CHUNK - 1) / KC_EMIT_CHUNK - (lo - a0) / KC_EMIT_CHUNK);
                 }
             }
             chunks[vv] = c;
@@ -296,7 +299,7 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
             if (N <= 65536) {
                 bounded = true;
                 ex.exclusive_scan_nosync(chunks, chunks, N + 1);
-                n_chunks = (u32) (total / KC_EMIT_CHUNK + 2 * N + 1);
+                n_chunks = (u32) ((s_end - s_begin) / KC_EMIT_CHUNK + 2 * N + 1);
             }
         }
 #endif
@@ -329,7 +332,9 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
             u64 n_upper = len - k + 1;
             u64 off = total - da[v];
             // output bytes [a0, a0 + 16) of this item, clipped to the node's [off, off + cnt)
-            u64 a0 = (off & ~(u64) 15) + (u64) (chunk - chunks[v]) * KC_EMIT_CHUNK + (u64) lane * 16;
+            const u64 n0 = off & ~(u64) 15;                                             // first chunk of the node that meets the slice
+            const u64 skip = n0 < s_begin ? (s_begin - n0) / KC_EMIT_CHUNK : 0;
+            u64 a0 = n0 + ((u64) (chunk - chunks[v]) + skip) * KC_EMIT_CHUNK + (u64) lane * 16;
             u64 b0 = a0 < off ? off : a0;
             u64 b1 = a0 + 16 < off + cnt ? a0 + 16 : off + cnt;
             if (b0 < s_begin) b0 = s_begin;  // slice boundaries are multiples of 16: an item is inside or outside as a whole

@@ -132,10 +132,12 @@ template <int L> struct SimulatePairFn {
         return false;
     }
     KC_HD bool owns_suffix(u32 v, const KWord<L> &ka, const KWord<L> &kb) const {
+        if (c.d == 0) return true;  // one group holds every end
         KWord<L> s = kmer_suffix(c.nv.last_kmer(v), c.d);
         return s == ka || s == kb;
     }
     KC_HD bool owns_prefix(u32 v, const KWord<L> &ka, const KWord<L> &kb) const {
+        if (c.d == 0) return true;
         KWord<L> p = kmer_prefix(c.nv.first_kmer(v), c.nv.k, c.d);
         return p == ka || p == kb;
     }

@@ -1195,7 +1195,14 @@ int kc_init_multi(int n_gpus, const int *device_ids, kc_group **out) {
     if (!g) return KC_ERR_OOM;
     g->n = n_gpus;
     int rc = KC_OK;
-    for (int r = 0; r < n_gpus && rc == KC_OK; ++r) rc = kc_init(device_ids[r], nullptr, &g->ctx[r]);
+    {   // one thread per rank: creating a primary context costs ~1 s per GPU and the devices do not wait for each other
+        int rcs[KC_MAX_PEERS];
+        std::vector<std::thread> th;
+        for (int r = 0; r < n_gpus; ++r) th.emplace_back([&, r] { rcs[r] = kc_init(device_ids[r], nullptr, &g->ctx[r]); });
+        for (auto &t : th) t.join();
+        for (int r = 0; r < n_gpus; ++r)
+            if (rcs[r] != KC_OK && rc == KC_OK) rc = rcs[r];
+    }
     for (int a = 0; a < n_gpus && rc == KC_OK; ++a)
         for (int b = 0; b < n_gpus && rc == KC_OK; ++b) {
             const int da = device_ids[a], db = device_ids[b];
@@ -1270,9 +1277,23 @@ int kc_group_compute(kc_group *g, const kc_params *p, const kc_input *in, kc_out
         }
         // every allocation happens BEFORE the first kernel of the job is queued anywhere: cudaMalloc / cudaFree wait for the whole
         // device, which would include a peer rank's wait kernel when two ranks share a GPU (tests)
-        for (int r = 0; r < g->n; ++r) {
-            KC_CUDA(cudaSetDevice(g->ctx[r]->device));
-            ensure_arena(g->ctx[r], group_arena_need(in->n_bytes, g->n, limbs, p->complements != 0, false));
+        {   // (one thread per rank: cudaMalloc of tens of GB takes ~0.1 s per device)
+            KcError errs[KC_MAX_PEERS];
+            bool bad[KC_MAX_PEERS] = {};
+            std::vector<std::thread> th;
+            for (int r = 0; r < g->n; ++r)
+                th.emplace_back([&, r] {
+                    try {
+                        KC_CUDA(cudaSetDevice(g->ctx[r]->device));
+                        ensure_arena(g->ctx[r], group_arena_need(in->n_bytes, g->n, limbs, p->complements != 0, false));
+                    } catch (const KcError &e) {
+                        errs[r] = e;
+                        bad[r] = true;
+                    }
+                });
+            for (auto &t : th) t.join();
+            for (int r = 0; r < g->n; ++r)
+                if (bad[r]) throw errs[r];
         }
     } catch (const KcError &e) {
         set_error(c0, e);

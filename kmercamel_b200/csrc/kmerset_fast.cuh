@@ -177,23 +177,41 @@ __global__ void __launch_bounds__(KsCfg<L>::EX_THREADS) kc_ksf_scatter0_kernel(c
     }
     __syncthreads();
     bool over = false;
+    if constexpr (P2P) {
+        // Most of these stores cross NVLink, where a partially written 128-byte line travels as several small packets.  A warp
+        // therefore takes whole digit runs and lines its lanes up with the DESTINATION: lane l writes the items whose index in the
+        // owner's sub-slot is l mod 32, so that every warp-wide store covers one aligned 256-byte block of keys (128 bytes of
+        // positions) and only the two ends of a run are partial lines.
+        const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const u32 n_dig = 1u << bits;
+        for (u32 dg = warp; dg < n_dig; dg += T / 32) {
+            const u32 q0 = loff[dg], n_all = cnt[dg], n_ok = qlim[dg] - q0;
+            if (n_ok < n_all) over = true;
+            if (n_ok == 0) continue;
+            KWord<L> *kd = reinterpret_cast<KWord<L> *>(dbase[dg]);
+            u32 *pd = reinterpret_cast<u32 *>(pbase[dg]);
+            const u32 mis = (u32) ((dbase[dg] / sizeof(KWord<L>) + q0) & 31u);
+            for (i64 i = (i64) lane - (i64) mis; i < (i64) n_ok; i += 32) {
+                if (i < 0) continue;
+                const u32 q = q0 + (u32) i;
+                const u32 slot = perm[q];
+                kd[q] = stash[slot];
+                pd[q] = (u32) block_pos0 + (slot & (T - 1)) * KC_EX_STRIP + (slot >> LOG_T);
+            }
+        }
+    } else {
 #pragma unroll 4
-    for (u32 q = threadIdx.x; q < total; q += T) {
-        const u32 slot = perm[q];
-        const KWord<L> v = stash[slot];
-        const u32 dg = v.digit_top(shift, bits);
-        if (q < qlim[dg]) {
-            const u32 pv = (u32) block_pos0 + (slot & (T - 1)) * KC_EX_STRIP + (slot >> LOG_T);
-            if (P2P) {
-                reinterpret_cast<KWord<L> *>(dbase[dg])[q] = v;
-                reinterpret_cast<u32 *>(pbase[dg])[q] = pv;
-            } else {
+        for (u32 q = threadIdx.x; q < total; q += T) {
+            const u32 slot = perm[q];
+            const KWord<L> v = stash[slot];
+            const u32 dg = v.digit_top(shift, bits);
+            if (q < qlim[dg]) {
                 const u64 at = dbase[dg] + q;
                 keys[at] = v;
-                pos[at] = pv;
+                pos[at] = (u32) block_pos0 + (slot & (T - 1)) * KC_EX_STRIP + (slot >> LOG_T);
+            } else {
+                over = true;
             }
-        } else {
-            over = true;
         }
     }
     if (over) status[0] = 1;

@@ -14,7 +14,10 @@ template <int L> struct SmallCfg {
     static constexpr u32 H = T / 2;
     static constexpr u32 NS = 1024;  // up to this many virtual nodes the whole path state lives in shared memory
     static constexpr u32 RANK_SORT = 384;      // up to this many tuples: rank sort (no barriers) instead of the bitonic network
-    static constexpr size_t SMEM = (size_t) T * sizeof(KWord<L + 1>) + (size_t) H * (4 * 6 + 8 * 2) + (size_t) NS * (8 + 4 * 7 + 3);
+    // Staging the first / last k-mers of the nodes in shared memory next to the path state was tried and made the kernel slower:
+    static constexpr bool STAGE_KMERS = false;  // measured on B200: 0.159 -> 0.179 ms at 100 free ends, 0.22 -> 0.25 at 200 (the k-mers were L1 hits already)
+    static constexpr size_t SMEM = (size_t) T * sizeof(KWord<L + 1>) + (size_t) H * (4 * 6 + 8 * 2) + (size_t) NS * (8 + 4 * 7 + 3) +
+                                   (STAGE_KMERS ? (size_t) NS * 2 * sizeof(KWord<L>) + 16 : 0);
 };
 
 template <int L> struct SmallEngineArgs {
@@ -48,7 +51,7 @@ template <int L> __global__ void __launch_bounds__(512) kc_small_engine_kernel(S
     __shared__ kc_ull s_min;
     const u32 tid = threadIdx.x;
     const u32 NT = blockDim.x;  // 256, or one warp for tiny problems (block barriers then cost next to nothing)
-    const NodeView<L> v = a.nv;
+    NodeView<L> v = a.nv;
     PathState s = a.st;
     u32 *head_w = a.head_w, *tail_w = a.tail_w, *slot_of = a.slot_of;
     u64 *stamp = a.stamp;
@@ -81,6 +84,15 @@ template <int L> __global__ void __launch_bounds__(512) kc_small_engine_kernel(S
         s.ovl = l8;
         prim = l8 + NS;
         ban_flag = l8 + 2 * NS;
+        if constexpr (SmallCfg<L>::STAGE_KMERS) {
+            KWord<L> *lk = reinterpret_cast<KWord<L> *>((reinterpret_cast<uintptr_t>(l8 + 3 * NS) + 15) & ~(uintptr_t) 15);
+            for (u32 i = tid; i < v.n; i += NT) {
+                lk[i] = a.nv.first[i];
+                lk[NS + i] = a.nv.last[i];
+            }
+            v.first = lk;
+            v.last = lk + NS;
+        }
         __syncthreads();
     }
     u32 n_s = a.n_s, n_p = a.n_p;
