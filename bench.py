@@ -153,11 +153,17 @@ def run_reference_arm(args, rank, world):
     value = n_k * len(secs) / sum(secs)
     sample = f"first {n_sample} of the {N_RECORDS} records ({n_sample * RECORD_LEN / 1e6:.0f} Mbp, {n_k} distinct k-mers) per step; " \
              f"wall clock of `kmercamel compute -k 31` incl. file read and output write"
+    ref_cfg = workload_config(world)
+    ref_cfg["workload"] += (f" -- REFERENCE ARM SAMPLE: the first {n_sample} of the {N_RECORDS} records ({n_sample} Mbp) per step, the whole `kmercamel compute` "
+                            "process incl. file read and output write.  The reference's hash tables slow down with the set size (BASELINE.md: 1.82 M k-mers/s at "
+                            "10 Mbp, 1.23 M/s at 50 Mbp), so this sampled rate OVER-states what it reaches on the full 50 Mbp workload: ratios against it are "
+                            "conservative.  Like-for-like wall clocks (both CLIs, same file, same box) are in profiles/ (r02_cli_wallclock.json, r02_northstar/)")
+    ref_cfg["reference_sample_records"] = n_sample
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": workload_config(world),
+        "config": ref_cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cores_available": os.cpu_count(),
@@ -451,6 +457,23 @@ def main():
                     "launches_per_step": d["launches"] / args.steps, "ms_per_launch": d["ms"] / max(d["launches"], 1),
                     "algorithmic_bytes_per_launch": d["bytes"] / max(d["launches"], 1),
                     "share_of_step": d["ms"] / dev_ms}
+        # SURVEY.md §8(d) accounting next to the per-pass one: the k-mer set stage (pack + emit_canonical + sort / dedup / count) is charged
+        # F + B/4 + B/8  +  B/4 + B/8 + M W  +  M W + U (W + 1) bytes — every radix pass together as ONE read + ONE write — over the time of
+        # the three kernels that do that work here (level-0 partition, level-1 partition, leaf resolve); and the whole step is charged
+        # SURVEY's ~60 B per distinct k-mer.  The per-kernel fractions by measured DRAM bytes come from the ncu capture (profiles/traffic.json).
+        B, M, U, W = float(seq.size), float(res.n_occurrences), float(n_kmers), 8.0
+        set_ms = sum(prof[c]["ms"] for c in ("ks_scatter0", "sort_scatter", "ks_resolve") if c in prof) / args.steps
+        bytes_8d = (B + B / 4 + B / 8) + (B / 4 + B / 8 + M * W) + (M * W + U * (W + 1))
+        roofline["stage_8d"] = {"stage": "k-mer set (pack + emit_canonical + sort/dedup/count of SURVEY 8d = ks_scatter0 + sort_scatter + ks_resolve here)",
+                                "algorithmic_bytes": bytes_8d, "ms": set_ms, "achieved": bytes_8d / (set_ms / 1000.0) / 1e9 if set_ms else None,
+                                "frac": bytes_8d / (set_ms / 1000.0) / 1e9 / peak if set_ms else None}
+        roofline["step_8d"] = {"algorithmic_bytes": 60.0 * U, "ms": dev_ms / args.steps, "frac": 60.0 * U / (dev_ms / args.steps / 1000.0) / 1e9 / peak}
+        try:
+            tj = json.load(open(tpath))
+            roofline["frac_by_dram_bytes"] = {c: (tj[c] / (prof[c]["ms"] / max(prof[c]["launches"], 1) / 1000.0) / 1e9 / peak)
+                                              for c in ("ks_scatter0", "sort_scatter", "ks_resolve") if c in tj and c in prof and prof[c]["ms"] > 0}
+        except Exception:
+            pass
         kernels = {n: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                        "gbs": (v["bytes"] / (v["ms"] / 1000.0) / 1e9) if v["ms"] > 0 and v["bytes"] else None}
                    for n, v in prof.items() if v["launches"]}

@@ -107,6 +107,28 @@ static bool parse_devices(const std::string &arg, std::vector<int> &out) {
     return !out.empty() && out.size() <= 16;
 }
 
+// CUDA initialisation enumerates every GPU of the box (5 s on an 8-GPU node for a job that uses one of them).  Unless the caller
+// already restricts the visible devices, expose only the ones named by -g and renumber them 0, 1, ...; must run before the first
+// CUDA call of the process.
+static void restrict_visible_devices(std::vector<int> &devices) {
+    if (std::getenv("CUDA_VISIBLE_DEVICES")) return;
+    std::vector<int> uniq;
+    for (int d : devices) {
+        bool seen = false;
+        for (int u : uniq) seen = seen || u == d;
+        if (!seen) uniq.push_back(d);
+    }
+    std::string list;
+    for (size_t i = 0; i < uniq.size(); ++i) list += (i ? "," : "") + std::to_string(uniq[i]);
+    if (setenv("CUDA_VISIBLE_DEVICES", list.c_str(), 0) != 0) return;
+    for (int &d : devices)
+        for (size_t i = 0; i < uniq.size(); ++i)
+            if (uniq[i] == d) {
+                d = (int) i;
+                break;
+            }
+}
+
 // Whole file (plain or gzip, "-" = stdin) into memory; zlib detects the format as in src/parser.h:88-101.  A regular file that
 // does not start with the gzip magic is read with plain read() calls into a buffer of its size (gzread passes such a file
 // through at ~0.8 GB/s and the doubling vector touches every page twice: 4 s for the 3.1 GB of the human-scale input).
@@ -243,9 +265,12 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
     if (!lower_bound) write_log("Started computation of a masked superstring from '" + path + "'.");
     else write_log("Started computation of a masked superstring length lower bound from '" + path + "'.");  // src/main.cpp:134
     const double t_start = now_ms();
+    const int device_asked = device;
+    restrict_visible_devices(devices);
+    device = devices[0];
     // several devices: the k-mer set construction of the from-FASTA greedy is sharded over them; every other mode runs on the first
     const bool multi = devices.size() > 1 && !lower_bound && algorithm == "greedy" && !assume_simplitigs && mask_path.empty();
-    if (devices.size() > 1 && !multi) write_log("Note: -S, -M, streaming and lowerbound run on one GPU; using device " + std::to_string(device) + ".");
+    if (devices.size() > 1 && !multi) write_log("Note: -S, -M, streaming and lowerbound run on one GPU; using device " + std::to_string(device_asked) + ".");
     // the CUDA context(s) (~1 s) are created while the file is read and framed
     kc_ctx *ctx = nullptr;
     kc_group *group = nullptr;
@@ -286,7 +311,7 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
     rc = rc_init;
     const double t_init = now_ms();
     if (rc != KC_OK) {
-        std::cerr << "cannot initialise CUDA device " << device << (multi ? " (and the other devices of -g; all need peer access to each other)" : "") << ": "
+        std::cerr << "cannot initialise CUDA device " << device_asked << (multi ? " (and the other devices of -g; all need peer access to each other)" : "") << ": "
                   << kc_strerror(rc) << " (this build has no CPU path)" << std::endl;
         return 1;
     }
@@ -465,6 +490,11 @@ static int camel_optimize(int argc, char **argv) {
     uint64_t span[5] = {0, 0, 0, 0, 0};
     kc_fasta_first_header(data.data(), data.size(), span);
     kc_ctx *ctx = nullptr;
+    {
+        std::vector<int> dv{device};
+        restrict_visible_devices(dv);
+        device = dv[0];
+    }
     int rc = kc_init(device, nullptr, &ctx);
     if (rc != KC_OK) {
         std::cerr << "cannot initialise CUDA device " << device << ": " << kc_strerror(rc) << " (this build has no CPU path)" << std::endl;
