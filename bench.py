@@ -330,9 +330,11 @@ def run_sharded_arm(args, rank, local_rank, world, ctx, part):
                      "collectives_on_the_data_path": 0, "fast_runs_rank0": fast_runs, "fast_fallbacks_rank0": fallbacks},
         "result": {"distinct_kmers": int(n_kmers), "superstring_length": int(r.length), "nodes": int(r.n_nodes)},
     }
-    print(json.dumps(line), flush=True)
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
 
 
+_REAL_STDOUT = sys.stdout
 _SCRATCH = {}
 
 
@@ -368,9 +370,12 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: whatever NCCL_DEBUG level the caller asked for goes to stderr
-        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
-            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        # stdout carries exactly one JSON line.  NCCL writes its version banner (and, with NCCL_DEBUG=INFO, its whole log) to file
+        # descriptor 1 from C: point fd 1 at stderr for the lifetime of the process and keep the real stdout for the final line.
+        global _REAL_STDOUT
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     records, (seq, off, ln) = make_workload(rank)

@@ -1,0 +1,20 @@
+#!/bin/bash
+# 8 x B200, second call: configs[3] (reads) at 1/2/4/8 GPUs, the bench lines at 2/4/8 with the final kernels
+mkdir -p gpurun_out
+export KC_GROUP_TIMEOUT_MS=60000
+timeout 900 python profiles/run_reads_scaling.py > gpurun_out/reads_scaling.log 2> gpurun_out/reads_scaling.err; echo "reads rc=$?"; tail -5 gpurun_out/reads_scaling.err | cut -c1-600
+for N in 8 4 2; do
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2952$N bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; echo "bench$N rc=$?"
+done
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err; echo "bench1 rc=$?"
+python - <<'PY'
+import json
+for n in (1,2,4,8):
+    f=f"gpurun_out/bench_{n}gpu.json"
+    try:
+        lines=[l for l in open(f).read().strip().splitlines() if l.startswith("{")]
+        d=json.loads(lines[-1])
+        print(f, "stdout lines:", len(open(f).read().strip().splitlines()), d["n_gpus"], round(d["ms_per_step"],3), "ms", round(d["value"]/1e9,2), "G/s e2e", round(d["e2e"]["ms_per_step"],3), d.get("parity_n"))
+        for k,v in (d.get("kernel_classes") or d.get("kernel_classes_rank0")).items(): print("   ",k, round(v["ms_per_step"],3), v["launches_per_step"])
+    except Exception as e: print(f, "ERR", e)
+PY
