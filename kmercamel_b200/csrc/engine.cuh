@@ -226,6 +226,63 @@ template <int L> struct SimulatePairFn {
     }
 };
 
+// ---- pointer doubling in ONE cooperative kernel ---------------------------------------------------------------------------
+// The validation of a level contracts this level's edges by pointer doubling: ceil(log2(ne)) + 1 rounds, each a pass over the ne
+// slots that must see the previous round complete.  As separate launches that was 444 of the 1263 launches of a 126 k-node input
+// (profiles/r02e_path_stage_310M.json), each ~7 us for microseconds of work.  Here the rounds are iterations of one persistent
+// grid separated by grid-wide barriers, and the loop ends as soon as a round found nothing left to jump over (chains made of this
+// level's edges are short: a handful of rounds instead of 17); slots on a cycle never resolve and keep the loop going for the full
+// count, exactly as before.  Results always end in the `a` arrays.
+#ifdef __CUDACC__
+#include <cooperative_groups.h>
+__global__ void __launch_bounds__(256) kc_doubling_kernel(u32 *jump_a, u32 *jump_b, u32 *fin_a, u32 *fin_b, u64 *max_a, u64 *max_b, u32 ne, int rounds,
+                                                          u32 *active /*[3], zeroed*/) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    u32 *ja = jump_a, *jb = jump_b, *fa = fin_a, *fb = fin_b;
+    u64 *ma = max_a, *mb = max_b;
+    const u32 stride = gridDim.x * blockDim.x;
+    int it = 0;
+    for (; it < rounds; ++it) {
+        bool any = false;
+        for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < ne; r += stride) {
+            const u32 j = ja[r];
+            if (j == KC_NONE) {
+                jb[r] = KC_NONE;
+                fb[r] = fa[r];
+                mb[r] = ma[r];
+            } else {
+                any = true;
+                jb[r] = ja[j];
+                fb[r] = fa[j];
+                const u64 m1 = ma[r], m2 = ma[j];
+                mb[r] = m1 > m2 ? m1 : m2;
+            }
+        }
+        if (__syncthreads_or(any) && threadIdx.x == 0) atomicOr(&active[it % 3], 1u);
+        // the flag of the NEXT round: last read after the barrier of round it - 2, which every thread has left (all passed the barrier of
+        // round it - 1); with only two flags a slow thread could still be reading the one being cleared
+        if (blockIdx.x == 0 && threadIdx.x == 0) active[(it + 1) % 3] = 0;
+        grid.sync();
+        u32 *t = ja; ja = jb; jb = t;
+        t = fa; fa = fb; fb = t;
+        u64 *m = ma; ma = mb; mb = m;
+        const u32 more = *reinterpret_cast<volatile u32 *>(&active[it % 3]);
+        if (!more) {  // every slot was resolved BEFORE this round: it only copied a -> b
+            ++it;
+            break;
+        }
+    }
+    if (ja != jump_a) {  // an odd number of rounds: bring the results home
+        grid.sync();
+        for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < ne; r += stride) {
+            jump_a[r] = ja[r];
+            fin_a[r] = fa[r];
+            max_a[r] = ma[r];
+        }
+    }
+}
+#endif
+
 #include "small_engine.cuh"
 
 // ---- engine -------------------------------------------------------------------------------------------
@@ -245,6 +302,8 @@ template <class Exec, int L> struct Engine {
 
     // live end lists (ascending node id); nullptr = identity 0..N-1
     u32 *live_s = nullptr, *live_p = nullptr;
+    u32 *list_buf[4] = {nullptr, nullptr, nullptr, nullptr};  // live_s generations 0 / 1, live_p generations 0 / 1
+    int list_gen = 0;
     u64 n_s = 0, n_p = 0;
     u32 *head_w, *tail_w, *slot_of;
     u64 *stamp;
@@ -499,17 +558,15 @@ template <class Exec, int L> struct Engine {
             ex.fill_bytes(ban_ctr, 0, 16);
         }
         ex.arena->release(mark);
-        // 8. shrink the live lists: count, allocate exactly, then compact (the lists only ever shrink, so the
-        //    arena grows by a geometric tail after the first level)
-        {
+        // 8. shrink the live lists.  Only a level that accepted edges changes them; the lists only ever shrink, so the new ones are
+        //    compacted straight into buffers of the old size (one compaction per list instead of count + allocate + compact)
+        if (n_edges) {
             const u32 *src_s = live_s, *src_p = live_p;
-            u64 cnt_s = ex.compact_if(
-                ns, [=] KC_HD_LAMBDA(u64 i) { return s.edge_from[src_s ? src_s[i] : (u32) i] == KC_NONE; },
-                [=] KC_HD_LAMBDA(u64, u32) {});
-            u64 cnt_p = ex.compact_if(
-                np, [=] KC_HD_LAMBDA(u64 i) { return s.edge_to[src_p ? src_p[i] : (u32) i] == KC_NONE; },
-                [=] KC_HD_LAMBDA(u64, u32) {});
-            u32 *dst_s = ex.template alloc<u32>(cnt_s), *dst_p = ex.template alloc<u32>(cnt_p);
+            if (!list_buf[0]) {  // two generations of each list, allocated once: the next generation goes where the one before last was
+                for (int i = 0; i < 4; ++i) list_buf[i] = ex.template alloc<u32>(i < 2 ? ns : np);
+            }
+            u32 *dst_s = list_buf[list_gen], *dst_p = list_buf[2 + list_gen];
+            list_gen ^= 1;
             n_s = ex.compact_if(
                 ns, [=] KC_HD_LAMBDA(u64 i) { return s.edge_from[src_s ? src_s[i] : (u32) i] == KC_NONE; },
                 [=] KC_HD_LAMBDA(u64 i, u32 r) { dst_s[r] = src_s ? src_s[i] : (u32) i; });
@@ -520,6 +577,30 @@ template <class Exec, int L> struct Engine {
             live_p = dst_p;
         }
     }
+
+#ifdef __CUDACC__
+    // All rounds of the doubling in one cooperative launch (kc_doubling_kernel); false = not available, the caller loops over launches.
+    bool doubling_fused(u32 *jump_a, u32 *jump_b, u32 *fin_a, u32 *fin_b, u64 *max_a, u64 *max_b, u32 ne, int rounds) {
+        static KcDevOnce once;
+        static int max_blocks[KC_MAX_DEVICES];
+        const int dev = once.run([&](int dv) {
+            int coop = 0, per_sm = 0;
+            KC_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dv));
+            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kc_doubling_kernel, 256, 0));
+            max_blocks[dv] = coop ? per_sm * kc_sm_count(dv) : 0;
+        });
+        if (max_blocks[dev] <= 0) return false;
+        u32 *active = ex.template alloc<u32>(4);
+        ex.fill_bytes(active, 0, 16);
+        u32 blocks = (u32) kc_div_up((u64) ne, 256);
+        if (blocks > (u32) max_blocks[dev]) blocks = (u32) max_blocks[dev];
+        void *args[] = {&jump_a, &jump_b, &fin_a, &fin_b, &max_a, &max_b, &ne, &rounds, &active};
+        typename Exec::Scope sc(ex, KP_DOUBLING, (u64) ne * 32 * 4);
+        KC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kc_doubling_kernel), dim3(blocks), dim3(256), args, 0, ex.stream));
+        ++ex.launches;
+        return true;
+    }
+#endif
 
     // Pointer doubling over this level's edges with chains contracted.  Returns true when the edge set is
     // acyclic (and the chain ends have been updated); false after appending bans for the cycle closers.
@@ -541,7 +622,11 @@ template <class Exec, int L> struct Engine {
             max_a[r] = stp[x];
         }, KP_DOUBLING, (u64) ne * 36);
         int rounds = kc_ceil_log2(ne) + 1;
-        for (int it = 0; it < rounds; ++it) {
+        bool fused = false;
+#ifdef __CUDACC__
+        if constexpr (Exec::is_device) fused = doubling_fused(jump_a, jump_b, fin_a, fin_b, max_a, max_b, ne, rounds);
+#endif
+        for (int it = 0; it < rounds && !fused; ++it) {
             const u32 *ja = jump_a, *fa = fin_a;
             const u64 *ma = max_a;
             u32 *jb = jump_b, *fb = fin_b;
