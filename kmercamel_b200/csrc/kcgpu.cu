@@ -8,6 +8,7 @@
 #include "group.cuh"
 #include "kmerset.cuh"
 #include "kmerset_fast.cuh"
+#include "kmerset_sig.cuh"
 #include "kword.cuh"
 #include "masks.cuh"
 #include "runs.cuh"
@@ -53,6 +54,9 @@ struct kc_ctx {
     bool sparse_switch = true;  // src/main.cpp:175 (option "sparse_switch" = 0 keeps the runs as nodes whatever their number)
     KsfTuning fast;          // histogram-free set construction (kmerset_fast.cuh); KC_FAST_* environment knobs for tests
     u64 fast_runs = 0, fast_fallbacks = 0;
+    SigTuning sig;           // signature-bucket set construction (kmerset_sig.cuh), tried first in the FLAGS regime
+    u64 sig_runs = 0, sig_fallbacks = 0;
+    u64 sig_overflow_bytes = 0;   // input size of the last call whose signature buckets overflowed (0 = none)
     bool fast_heuristics = true;  // skip the fixed-slot attempt when duplicates are expected (see run_stage1_runs)
     u64 fast_overflow_bytes = 0;  // input size of the last call whose fixed-slot attempt overflowed (0 = none)
     u64 total_launches = 0;  // kernels launched through this context since kc_init
@@ -208,6 +212,29 @@ u64 run_stage1_runs(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_para
     // the leaf slots overflow and the attempt is wasted — configs[3] at full size lost 70 ms to it), and so does an
     // overflow in the previous call of this context on an input of similar size.
     const bool expect_duplicates = ctx->fast_heuristics && (p.min_frequency > 1 || (ctx->fast_overflow_bytes && nb >= ctx->fast_overflow_bytes / 2 && nb <= ctx->fast_overflow_bytes * 2));
+    // Signature buckets first (kmerset_sig.cuh): records of ~7 windows instead of 12-byte items.  Read sets with coverage overflow
+    // its buckets (every run of windows comes c times: sigma grows by sqrt(c)) and are remembered like a fixed-slot overflow.
+    const bool sig_overflowed = ctx->fast_heuristics && ctx->sig_overflow_bytes && nb >= ctx->sig_overflow_bytes / 2 && nb <= ctx->sig_overflow_bytes * 2;
+    if (!p.want_maxone && p.min_frequency == 1 && !sig_overflowed) {
+        u64 *cells4 = ex.arena->alloc_top<u64>(4);  // {kept, runs, M, overflow status}
+        ex.fill_bytes(cells4, 0, 32);
+        if (kc_kmerset_build_sig<L>(ex, in.seq, nb, p.k, p.complements != 0, flags, cells4, ctx->sig, in.chunks)) {
+            KC_TRACE_POINT("stage1: signature set launched");
+            u64 hc[4];
+            bool aborted = false;
+            *runs = kc_runs_from_flags(ex, flags, nb, p.k, cells4, hc, 4, &aborted);
+            if (!aborted) {
+                ++ctx->sig_runs;
+                *n_occ = hc[2];
+                *set_out = nullptr;
+                KC_CUDA(cudaEventRecord(ctx->ev[2], ex.stream));
+                return hc[2] ? hc[0] : 0;
+            }
+            ++ctx->sig_fallbacks;  // a bucket overflowed: discard the flags, fall through to the other constructions
+            ctx->sig_overflow_bytes = nb;
+            ex.fill_bytes(flags, 0, fwords * 4);
+        }
+    }
     if (!p.want_maxone && !expect_duplicates) {
         KsfPlan plan;
         u64 *cells4 = ex.arena->alloc_top<u64>(4);  // {kept, runs, M, overflow status}
@@ -651,6 +678,7 @@ int kc_init(int device, void *stream, kc_ctx **out) {
         for (int i = 0; i < 6; ++i) KC_CUDA(cudaEventCreate(&ctx->ev[i]));
         KC_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ctx->pin_small), kc_ctx::KC_PIN_SMALL, cudaHostAllocDefault));
         if (const char *e = std::getenv("KC_FAST_SET")) ctx->fast.enabled = std::atoi(e) != 0;
+        if (const char *e = std::getenv("KC_SIG_SET")) ctx->sig.enabled = std::atoi(e) != 0;
         if (const char *e = std::getenv("KC_FAST_MAX_CTAS")) ctx->fast.max_ctas = std::atoi(e);
         if (const char *e = std::getenv("KC_FAST_TMA")) ctx->fast.tma = std::atoi(e) != 0;
         if (const char *e = std::getenv("KC_SMALL_THREADS")) ctx->small_threads = std::atoi(e);
@@ -1415,6 +1443,8 @@ int kc_get_stat(const kc_ctx *ctx, const char *name, uint64_t *value) {
     if (!ctx || !name || !value) return KC_ERR_ARG;
     if (std::strcmp(name, "fast_runs") == 0) *value = ctx->fast_runs;
     else if (std::strcmp(name, "fast_fallbacks") == 0) *value = ctx->fast_fallbacks;
+    else if (std::strcmp(name, "sig_runs") == 0) *value = ctx->sig_runs;
+    else if (std::strcmp(name, "sig_fallbacks") == 0) *value = ctx->sig_fallbacks;
     else if (std::strcmp(name, "total_launches") == 0) *value = ctx->total_launches;
     else if (std::strcmp(name, "fast_max_ctas") == 0) *value = (uint64_t) ctx->fast.max_ctas;
     else return KC_ERR_ARG;
@@ -1456,6 +1486,7 @@ int kc_set_option(kc_ctx *ctx, const char *name, int value) {
     if (std::strcmp(name, "fast_heuristics") == 0 && (value == 0 || value == 1)) {
         ctx->fast_heuristics = value != 0;
         ctx->fast_overflow_bytes = 0;
+        ctx->sig_overflow_bytes = 0;
         return KC_OK;
     }
     if (std::strcmp(name, "fast_max_ctas") == 0 && value >= 0 && value <= (1 << 20)) {
@@ -1464,6 +1495,19 @@ int kc_set_option(kc_ctx *ctx, const char *name, int value) {
     }
     if (std::strcmp(name, "fast_min_items") == 0 && value >= 0) {
         ctx->fast.min_items = (u64) value;
+        return KC_OK;
+    }
+    // signature-bucket set construction (kmerset_sig.cuh)
+    if (std::strcmp(name, "sig_set") == 0) {
+        ctx->sig.enabled = value != 0;
+        return KC_OK;
+    }
+    if (std::strcmp(name, "sig_load_pct") == 0 && value >= 0 && value <= 400) {  // > 100 forces overflows (tests)
+        ctx->sig.load_pct = (u32) value;
+        return KC_OK;
+    }
+    if (std::strcmp(name, "sig_min_items") == 0 && value >= 0) {
+        ctx->sig.min_items = (u64) value;
         return KC_OK;
     }
     return KC_ERR_ARG;

@@ -287,7 +287,9 @@ def test_small_engine_and_host_levels_agree(ctx, golden, simplitigs_bytes):
 
 # ---- histogram-free set construction (kmerset_fast.cuh) must agree with the exact one -----------------------------
 def _fast_options(ctx, **kw):
-    defaults = dict(fast_set=1, fast_leaf_target=768, fast_sigmas=8, fast_min_items=1 << 16, fast_heuristics=0)
+    # any explicit option switches the signature-bucket construction (kmerset_sig.cuh, tried first by default) off, so that these
+    # tests reach the fixed-slot / exact constructions; a bare call restores the defaults
+    defaults = dict(fast_set=1, fast_leaf_target=768, fast_sigmas=8, fast_min_items=1 << 16, fast_heuristics=0, sig_set=0 if kw else 1)
     defaults.update(kw)
     for name, value in defaults.items():
         ctx.set_option(name, value)
@@ -373,6 +375,7 @@ def test_fast_set_heuristics(ctx):
     seq, off, ln = synth.frame_records(list(reads))
     try:
         _fast_options(ctx, fast_min_items=0, fast_heuristics=1)
+        ctx.set_option("sig_set", 0)   # fast_heuristics resets the memory of both constructions
         runs0, fb0 = ctx.stat("fast_runs"), ctx.stat("fast_fallbacks")
         a = ctx.compute(seq, k=31, min_frequency=2)
         assert (ctx.stat("fast_runs"), ctx.stat("fast_fallbacks")) == (runs0, fb0)          # not even tried
@@ -394,7 +397,11 @@ def test_fast_set_config2_full_size(ctx):
     recs = synth.random_genome_records(50, 1_000_000, 12345)
     seq, off, ln = synth.frame_records(recs)
     runs0, fb0 = ctx.stat("fast_runs"), ctx.stat("fast_fallbacks")
-    r = ctx.compute(seq, k=31)
+    ctx.set_option("sig_set", 0)
+    try:
+        r = ctx.compute(seq, k=31)
+    finally:
+        ctx.set_option("sig_set", 1)
     assert ctx.stat("fast_runs") == runs0 + 1 and ctx.stat("fast_fallbacks") == fb0
     assert r.n_kmers == 49_998_500 and abs(r.length - 49_999_860) <= 0.001 * 49_999_860
     got, n_on = orc.ms_kmers(r.ms, 31, True)
