@@ -1,60 +1,56 @@
 // K-mer set construction by SIGNATURE buckets (super-k-mers) for the FLAGS regime: the same result as kmerset_fast.cuh /
 // kmerset.cuh — bit p of the flag array set iff the k-mer of the window ending at p occurs there for the first time
-// (reference src/parser.h:22-141 AddKMers / ReadKMers + khash) — with ~5 x less HBM traffic and two kernels instead of three.
+// (reference src/parser.h:22-141 AddKMers / ReadKMers + khash) — with ~10 x less HBM traffic and two kernels instead of three.
 //
 // The partition passes of kmerset_fast.cuh move every k-mer occurrence as a 12-byte (key, position) item: 1 + 12 (level 0)
 // + 12 + 12 (level 1) + 12 (leaf resolve) = 49 bytes per k-mer, and their cost is the shared-memory ranking of those items.
-// Here the unit that travels is a RECORD: a run of consecutive windows of one 32-position strip whose k-mers share a
-// signature, 8 bytes for ~7 windows.  The k-mers themselves are re-created from the sequence (which stays in HBM anyway: the
-// emission reads it again) inside the CTA that resolves the bucket.
+// Here the unit that travels is a RECORD: up to 8 consecutive windows of one 32-position strip whose k-mers share a
+// signature, 8 bytes for ~5 windows.  The k-mers themselves are re-created from the 2-bit packed sequence (0.25 bytes per
+// base, written by the scan) inside the CTA that resolves the bucket.
 //
 //   signature of a k-mer  = the smallest hash among the canonical M-mers at its W = 16 CENTRAL M-mer positions
 //                           (M = 16 / 15 for k >= 30, 12 / 11 for 26 <= k < 30; chosen so that k - M - (W - 1) is even:
 //                           the central range is then mirror-symmetric, a k-mer and its reverse complement see the same
 //                           set of canonical M-mers, and every occurrence of a canonical k-mer gets the same signature);
-//   bucket                = floor(n_buckets * (1 - (1 - s)^14)), s = signature / 2^32.  The minimum of W uniform hashes has
+//   bucket                = floor(n_buckets * (1 - (1 - s)^13)), s = signature / 2^32.  The minimum of W uniform hashes has
 //                           distribution 1 - (1 - s)^W; exponent W would spread the WINDOWS evenly over the buckets, but a large
-//                           signature changes hands after ~2 windows where a small one lasts for ~16, so the last buckets would
-//                           hold four times the RECORDS of the first ones.  Exponent 14 gives the first buckets 14 % more windows
-//                           and the last ones fewer, which evens out the records (simulation: windows max / mean 1.43, records
-//                           max / mean 1.6 over 3.5 k buckets instead of 1.3 and 3.0);
-//   kc_sig_scan_kernel    sequence -> 2-bit codes (as level 0 of the other constructions) -> 47 M-mer hashes per strip by static
-//                           funnel shifts of the strip's 128-bit code window and of its reverse complement -> sliding minimum by
-//                           doubling (2, 4, 8, 16) in registers -> bucket per window -> one record per run: ONE 64-bit
-//                           atomicAdd on the bucket's cursor reserves the record slot (low word) and the item range (high word),
-//                           one 8-byte store writes {position, length, first item}.  Also writes the valid-window bits
-//                           ("clear the losers" flags, kmerset_fast.cuh).
-//   kc_sig_resolve_kernel persistent CTAs, one bucket at a time (<= CAP windows): a thread per record decodes the record's
-//                           strip (+ L strips to the left) into shared memory; a thread per window funnel-shifts its k-mer out of
-//                           those words, takes the canonical form and resolves it in the shared-memory tables of
-//                           kc_ksf_resolve2_kernel (plain-store table T1, one barrier, CAS fallback T2); every folded duplicate
-//                           clears the bit of the larger position.
+//                           signature changes hands after ~2 windows where a small one lasts for 16, so the last buckets would
+//                           hold twice the RECORDS of the first ones — and the capacity of a bucket is counted in records.
+//                           Exponent 13 evens the records out (simulation over 16 M windows: octile means within 6 %);
+//   kc_sig_scan_kernel    sequence -> 2-bit codes (as level 0 of the other constructions; the code words also go to HBM) -> 47
+//                           M-mer hashes per strip by static funnel shifts of the strip's 128-bit code window and of its reverse
+//                           complement -> sliding minimum by doubling (2, 4, 8, 16) in registers -> runs of equal signature, cut
+//                           into records of <= 8 windows: one atomicAdd on the bucket's counter reserves the record slot, one
+//                           8-byte store writes {position, length}.  Also writes the valid-window bits ("clear the losers"
+//                           flags, kmerset_fast.cuh).
+//   kc_sig_resolve_kernel persistent CTAs, one bucket (<= 256 records) at a time, ONE THREAD PER RECORD: two 8-byte loads fetch
+//                           the record's code words (one bucket ahead, into registers), the first k-mer is a funnel shift, the
+//                           next ones roll (forward and reverse complement, src/parser.h:39-40); item t of record r lives in
+//                           slot t * 256 + r of the shared-memory arrays (conflict-free, no prefix sums), and the tables of
+//                           kc_ksf_resolve2_kernel resolve them: plain-store table T1, one barrier, CAS fallback T2; every folded
+//                           duplicate clears the bit of the larger position.  (Handing the windows of a warp's records out one
+//                           per lane — dense lanes, direct funnel extraction — was measured: more instructions per window.)
 //
-// Algorithmic HBM bytes per k-mer (L = 1): 1 (sequence) + ~1.2 (record written) + ~1.2 (record read) + ~9.6 (the two 32-byte
-// sectors a record's strip is re-read as, ~6.7 windows per record) = ~13 instead of 49.
+// HBM bytes per k-mer (L = 1): 1 (sequence) + 0.25 (code words written) + 1.6 (record written) + 1.6 (record read) + ~3 (code
+// words re-read, 16 bytes per record) = ~7.5 instead of 49.
 //
-// A bucket that exceeds its capacity (records or windows: heavily repeated sequence) sets the status word; the caller
+// A bucket that exceeds its capacity (heavily repeated sequence, read sets with coverage) sets the status word; the caller
 // discards the flags and uses the other constructions, exactly like an overflow in kmerset_fast.cuh.
 #pragma once
 #include "kmerset_fast.cuh"
 
 struct SigTuning {
     bool enabled = true;
-    uint32_t load_pct = 0;             // mean windows per bucket, in percent of the bucket capacity; 0 = 50 / 44 / 39 for L = 1 / 2 / 4
-                                       // (the first buckets get 14 % more, sigma ~ 4.2 sqrt(mean) because windows arrive in runs: the
-                                       // mean + 5.5 sigma that the largest of 10^6 buckets reaches stays below the capacity)
+    uint32_t load_pct = 55;            // mean records per bucket, in percent of the bucket capacity: 141 of 256.  Records arrive in
+                                       // clumps (sigma ~ 1.5 sqrt(mean) ~ 18), the first buckets get ~6 % more: mean + 6 sigma = 256
     uint64_t min_items = 1u << 16;     // smaller inputs: nothing to gain
 };
 
-template <int L> struct SigCfg {
-    static constexpr u32 CAP = L == 1 ? 4096 : (L == 2 ? 2048 : 1024);  // windows (items) per bucket
-    static constexpr u32 REC_CAP = CAP / 4;                              // records per bucket
-    static constexpr int THREADS = L == 1 ? 512 : 256;
-    static constexpr int NW = L + 1;                                     // 32-base words a window can reach into
-    static constexpr int MIN_CTAS = L == 1 ? 2 : 3;                      // resident CTAs per SM the shared memory allows
-};
-
 static const int KC_SIG_W = 16;
+static const int KC_SIG_PIECE = 8;          // windows per record at most
+static const u32 KC_SIG_REC_CAP = 256;      // records per bucket = threads of the resolving CTA
+static const u32 KC_SIG_SLOTS = KC_SIG_PIECE * KC_SIG_REC_CAP;  // item t of record r lives in slot t * REC_CAP + r
+static const double KC_SIG_WINDOWS_PER_RECORD = 5.16;          // random sequence, runs cut by the 32-window strips and into pieces of 8
 
 struct SigPlan {
     bool ok = false;
@@ -63,7 +59,7 @@ struct SigPlan {
     u32 n_buckets = 0;
 };
 
-inline SigPlan kc_sig_plan(u64 n_bytes, int k, u32 cap, const SigTuning &t) {
+inline SigPlan kc_sig_plan(u64 n_bytes, int k, const SigTuning &t) {
     SigPlan p;
     if (!t.enabled || n_bytes < t.min_items || n_bytes >= 0xFFFFFFFFULL) return p;
     static const int ms[4] = {16, 15, 12, 11};
@@ -75,22 +71,15 @@ inline SigPlan kc_sig_plan(u64 n_bytes, int k, u32 cap, const SigTuning &t) {
         }
     }
     if (!p.m) return p;
-    const u64 pct = t.load_pct ? t.load_pct : (cap >= 4096 ? 50 : (cap >= 2048 ? 44 : 39));
-    const u64 mean = (u64) cap * pct / 100;
-    const u64 nb = kc_div_up(n_bytes, mean ? mean : 1);
-    if (nb >= (1u << 26)) return p;  // a record keeps its bucket's item base in 26 bits... and the scan its bucket in 27
+    const double mean_windows = KC_SIG_REC_CAP * (t.load_pct / 100.0) * KC_SIG_WINDOWS_PER_RECORD;
+    const u64 nb = (u64) ((double) n_bytes / (mean_windows > 1.0 ? mean_windows : 1.0)) + 1;
+    if (nb >= (1u << 27)) return p;
     p.n_buckets = (u32) (nb < 64 ? 64 : nb);
     p.ok = true;
     return p;
 }
 
 #ifdef __CUDACC__
-
-// 4 ASCII bytes (byte 0 = first base) -> 8 bits of codes, first base in the top 2 bits (kc_pack4 without the validity bits).
-KC_D u32 kc_codes4(u32 w) {
-    const u32 c = ((w >> 1) ^ (w >> 2)) & 0x03030303u;
-    return (c * 0x40100401u) >> 24;
-}
 
 // Reverse complement of 16 bases held in one 32-bit word.
 KC_D u32 kc_revcomp16(u32 w) {
@@ -127,23 +116,41 @@ template <int M> struct SigHashLoop<M, 32 + KC_SIG_W - 1> {
     KC_D static void run(const u32 (&)[4], const u32 (&)[4], u32 *) {}
 };
 
-// A record: bits 0..31 END position of its first window, 32..36 windows - 1, 38..63 index of its first item inside the bucket.
-KC_HD u64 kc_sig_record(u32 pos, u32 len, u32 item_base) { return (u64) pos | ((u64) (len - 1) << 32) | ((u64) item_base << 38); }
+// signature -> bucket (see the header): floor(n_buckets * (1 - (1 - s)^13))
+KC_D u32 kc_sig_bucket(u32 sig, u32 n_buckets) {
+    const u32 u1 = ~sig;
+    const u32 u2 = __umulhi(u1, u1), u4 = __umulhi(u2, u2), u8 = __umulhi(u4, u4);
+    const u32 u13 = __umulhi(__umulhi(u8, u4), u1);
+    return __umulhi(~u13, n_buckets);
+}
 
+// A record: bits 0..31 END position of its first window, 32..34 windows - 1.
+KC_HD u64 kc_sig_record(u32 pos, u32 len) { return (u64) pos | ((u64) (len - 1) << 32); }
+
+// packed[s] = the 2-bit codes of bases 32 s .. 32 s + 31 (first base in the top bits); every strip of every tile is written.
 template <int M>
-__global__ void __launch_bounds__(256) kc_sig_scan_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int a, u32 n_buckets, u32 rec_cap, u32 item_cap,
-                                                          kc_ull *cursor, u64 *__restrict__ recs, u32 *__restrict__ flags, u32 n_flag_words, u32 tile0,
-                                                          kc_ull *m_cell, u32 *status, const u32 *__restrict__ win_mask) {
+__global__ void __launch_bounds__(256) kc_sig_scan_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int a, u32 n_buckets, u32 *cursor,
+                                                          u64 *__restrict__ recs, u64 *__restrict__ packed, u32 *__restrict__ flags, u32 n_flag_words,
+                                                          u32 tile0, kc_ull *m_cell, u32 *status, const u32 *__restrict__ win_mask) {
     constexpr int T = 256;
     constexpr int NH = 32 + KC_SIG_W - 1;  // M-mer hashes a strip needs
     __shared__ u64 pk[KC_EX_HALO + T];
     __shared__ u32 vm[KC_EX_HALO + T];
-    __shared__ u32 starts[KC_EX_STRIP * T];  // (bucket << 5 | first window) of the thread's c-th record at [c * T + thread]
+    __shared__ u32 ssig[KC_EX_STRIP * T];  // signature of the window ending at strip base j of thread t at [j * T + t]
     const i64 block_pos0 = (i64) (tile0 + blockIdx.x) * (T * KC_EX_STRIP);
     kc_tile_load<T>(seq, n_bytes, block_pos0, pk, vm);
     __syncthreads();
     const int widx = KC_EX_HALO + threadIdx.x;
-    const u32 em = kc_strip_emit_mask(vm, widx, k) & kc_strip_window_filter(win_mask, block_pos0);
+    packed[(u64) (block_pos0 >> 5) + threadIdx.x] = pk[widx];
+    u32 em;
+    {   // genomes: every base of the strip and of the k - 1 before it is a nucleotide (warp-uniform most of the time)
+        const int need = (k - 1 + 31) >> 5;  // words to the left that a window of the strip can reach into
+        bool all = vm[widx] == 0xFFFFFFFFu;
+#pragma unroll
+        for (int w = 1; w <= KC_EX_HALO; ++w) all = all && (w > need || vm[widx - w] == 0xFFFFFFFFu);
+        em = all ? 0xFFFFFFFFu : kc_strip_emit_mask(vm, widx, k);
+    }
+    em &= kc_strip_window_filter(win_mask, block_pos0);
     {   // clear-the-losers flags: every window starts as "first occurrence" (bit p & 31 of word p >> 5 = window END p)
         const u64 w = (u64) (block_pos0 >> 5) + threadIdx.x;
         if (em && w < n_flag_words) flags[w] = __brev(em);
@@ -175,180 +182,219 @@ __global__ void __launch_bounds__(256) kc_sig_scan_kernel(const u8 *__restrict__
     for (int i = 0; i < NH - 7; ++i) H[i] = min(H[i], H[i + 4]);
 #pragma unroll
     for (int i = 0; i < NH - 15; ++i) H[i] = min(H[i], H[i + 8]);
-    const u32 emr = __brev(em);  // bit j = window ending at strip base j
-    u32 n_rec = 0, prev_b = 0;
+    u32 neq = 1u;  // bit j: the signature changes at window j
 #pragma unroll
     for (int j = 0; j < KC_EX_STRIP; ++j) {
-        const u32 u1 = ~H[j];
-        const u32 u2 = __umulhi(u1, u1), u4 = __umulhi(u2, u2), u8 = __umulhi(u4, u4);
-        const u32 u = __umulhi(__umulhi(u8, u4), u2);  // (1 - s)^14
-        const u32 b = __umulhi(~u, n_buckets);
-        const bool valid = (emr >> j) & 1u;
-        const bool first = valid && (j == 0 || !((emr >> (j - 1)) & 1u) || b != prev_b);
-        if (first) {
-            starts[n_rec * T + threadIdx.x] = (b << 5) | (u32) j;
-            ++n_rec;
-        }
-        prev_b = b;
+        ssig[j * T + threadIdx.x] = H[j];
+        if (j) neq |= (H[j] != H[j - 1] ? 1u : 0u) << j;
     }
-    // stops: a record ends where the next one starts or where the valid windows end
-    u32 bnd = 0;
-    for (u32 c = 0; c < n_rec; ++c) bnd |= 1u << (starts[c * T + threadIdx.x] & 31u);
-    const u32 stops = bnd | ~emr;
+    const u32 emr = __brev(em);                          // bit j = window ending at strip base j
+    u32 run_starts = emr & (neq | ~(emr << 1));          // a run: valid windows of one signature
+    const u32 stops = run_starts | ~emr;
     const u32 pos0 = (u32) block_pos0 + threadIdx.x * KC_EX_STRIP;
     bool over = false;
-    for (u32 c = 0; c < n_rec; ++c) {
-        const u32 e = starts[c * T + threadIdx.x];
-        const u32 j = e & 31u, b = e >> 5;
+    while (run_starts) {
+        u32 j = (u32) __ffs(run_starts) - 1u;
+        run_starts &= run_starts - 1u;
         const u32 rest = j < 31 ? stops & (0xFFFFFFFFu << (j + 1)) : 0u;
-        const u32 len = (rest ? (u32) __ffs(rest) - 1u : 32u) - j;
-        const kc_ull old = atomicAdd(&cursor[b], ((kc_ull) len << 32) | 1ULL);
-        const u32 slot = (u32) old, ib = (u32) (old >> 32);
-        if (slot < rec_cap && ib + len <= item_cap) recs[(u64) b * rec_cap + slot] = kc_sig_record(pos0 + j, len, ib);
-        else over = true;
+        u32 len = (rest ? (u32) __ffs(rest) - 1u : 32u) - j;
+        const u32 b = kc_sig_bucket(ssig[j * T + threadIdx.x], n_buckets);
+        while (len) {  // pieces of <= 8 windows
+            const u32 l = len < (u32) KC_SIG_PIECE ? len : (u32) KC_SIG_PIECE;
+            const u32 slot = atomicAdd(&cursor[b], 1u);
+            if (slot < KC_SIG_REC_CAP) recs[(u64) b * KC_SIG_REC_CAP + slot] = kc_sig_record(pos0 + j, l);
+            else over = true;
+            j += l;
+            len -= l;
+        }
     }
     if (over) status[0] = 1;
 }
 
+template <int L> struct SigCfg {
+    static constexpr int THREADS = (int) KC_SIG_REC_CAP;
+    static constexpr int NW = L + 1;                                     // 32-base code words a window can reach into
+    static constexpr u32 T1N = 2 * KC_SIG_SLOTS, T2N = KC_SIG_SLOTS / 2;  // T2 takes the ~16 % of the items that meet another key in T1
+    static constexpr int T1_BITS = 12;
+    static constexpr int MIN_CTAS = L == 1 ? 5 : (L == 2 ? 3 : 2);      // resident CTAs per SM the shared memory allows
+    static int smem() { return (int) (KC_SIG_SLOTS * (sizeof(KWord<L>) + 4) + T1N * 2 + T2N * 4); }
+};
+
+// Reverse the 32 two-bit symbols of a limb through the bit-reversal instruction (kc_reverse_symbols64 of kword.cuh walks a
+// five-step swap network: ~4 x the instructions).
+KC_D u64 kc_reverse_symbols64_brev(u64 w) {
+    const u64 b = __brevll(w);  // symbols reversed, the two bits of every symbol swapped
+    return ((b >> 1) & 0x5555555555555555ULL) | ((b & 0x5555555555555555ULL) << 1);
+}
+
+// The code words a record's windows can reach into: word NW - 1 = the strip of the record, the others to its left.
+template <int NW> KC_D void kc_sig_load_words(const u64 *__restrict__ packed, u64 rec, bool have, u64 (&w)[NW]) {
+    const u32 strip = (u32) rec >> 5;
+#pragma unroll
+    for (int wi = 0; wi < NW; ++wi) w[wi] = have && strip >= (u32) (NW - 1 - wi) ? __ldg(&packed[strip - (u32) (NW - 1 - wi)]) : 0ULL;
+}
+
+// One bucket at a time, ONE THREAD PER RECORD: item t of record r lives in slot t * 256 + r of the shared-memory arrays
+// (conflict-free, no prefix sums).  The first k-mer of a record is a funnel shift of its code words, the next ones roll: forward
+// word left by one base, reverse complement right by one base (src/parser.h:39-40; L = 1 keeps the reverse complement
+// left-aligned, so that every shift of the roll is static).  The record of bucket n + 2 and the code words of bucket n + 1 are
+// in flight (registers) while bucket n is resolved: no thread waits for HBM between the barriers.
 template <int L, bool MULTI>
-__global__ void __launch_bounds__(SigCfg<L>::THREADS, SigCfg<L>::MIN_CTAS) kc_sig_resolve_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int complements,
-                                                                             const kc_ull *__restrict__ cursor, const u64 *__restrict__ recs, u32 n_buckets,
-                                                                             KsfFlagPeers fl, kc_ull *n_unique, u32 *status) {
+__global__ void __launch_bounds__(SigCfg<L>::THREADS, SigCfg<L>::MIN_CTAS) kc_sig_resolve_kernel(const u64 *__restrict__ packed, int k, int complements,
+                                                                                                const u32 *__restrict__ cursor, const u64 *__restrict__ recs,
+                                                                                                u32 n_buckets, KsfFlagPeers fl, kc_ull *n_unique, u32 *status) {
     typedef SigCfg<L> Cfg;
-    constexpr u32 CAP = Cfg::CAP, REC_CAP = Cfg::REC_CAP;
-    constexpr int T = Cfg::THREADS, NW = Cfg::NW;
-    constexpr int NI = (int) CAP / T;
-    constexpr u32 T1N = 2 * CAP, T2N = CAP;
-    constexpr int T1_BITS = CAP == 4096 ? 13 : (CAP == 2048 ? 12 : 11);
-    static_assert((1u << T1_BITS) == T1N, "T1 size");
-    static_assert(NI % 4 == 0 && NI * T == (int) CAP, "a thread clears NI slots of T2 with 16-byte stores");
+    constexpr u32 RC = KC_SIG_REC_CAP, T2N = Cfg::T2N;
+    constexpr int NW = Cfg::NW, P = KC_SIG_PIECE;
+    static_assert((1u << Cfg::T1_BITS) == Cfg::T1N, "T1 size");
     extern __shared__ __align__(16) unsigned char kc_smem_raw[];
-    KWord<L> *sk = reinterpret_cast<KWord<L> *>(kc_smem_raw);  // [CAP] canonical k-mer of item i
-    u64 *swords = reinterpret_cast<u64 *>(sk + CAP);            // [NW][REC_CAP] code words of record r: word NW - 1 = its own strip
-    u32 *sp = reinterpret_cast<u32 *>(swords + NW * REC_CAP);   // [CAP] window END position of item i (the smallest one of its key, once folded)
-    u32 *T2 = sp + CAP;                                         // [T2N]
-    u32 *recinfo = T2 + T2N;                                    // [REC_CAP] position of the record's first window - its first item
-    u16 *T1 = reinterpret_cast<u16 *>(recinfo + REC_CAP);       // [T1N]
-    u16 *map = T1 + T1N;                                        // [CAP] item -> record
+    KWord<L> *sk = reinterpret_cast<KWord<L> *>(kc_smem_raw);  // [SLOTS] canonical k-mer of the item in slot t * RC + r
+    u32 *sp = reinterpret_cast<u32 *>(sk + KC_SIG_SLOTS);       // [SLOTS] its window END position (the smallest one of its key, once folded)
+    u32 *T2 = sp + KC_SIG_SLOTS;                                // [T2N]
+    u16 *T1 = reinterpret_cast<u16 *>(T2 + T2N);                // [T1N]
     const KWord<L> kmask = KWord<L>::low_mask(2 * k);
+    const int top = 2 * (k - 1);
+    const int top_limb = top >> 6, top_off = top & 63;
+    const int lsh = 64 * L - 2 * k;  // left-aligned <-> right-aligned
     u32 kept = 0;
-    for (u32 b = blockIdx.x; b < n_buckets; b += gridDim.x) {
-        const u64 cur = cursor[b];
-        const u32 n_rec = (u32) cur, n_items = (u32) (cur >> 32);
-        if (n_items == 0) continue;
-        if (n_rec > REC_CAP || n_items > CAP) {  // the scan has set the status word already
-            if (threadIdx.x == 0) status[0] = 1;
-            continue;
-        }
-        // P0: a thread per record
-        for (u32 r = threadIdx.x; r < n_rec; r += T) {
-            const u64 rec = recs[(u64) b * REC_CAP + r];
-            const u32 pos = (u32) rec, len = ((u32) (rec >> 32) & 31u) + 1u, ib = (u32) (rec >> 38);
-            const i64 s0 = (i64) (pos & ~31u);
+    const u32 stride = gridDim.x;
+    u32 b = blockIdx.x;
+    auto n_rec_of = [&](u32 bb) -> u32 { return bb < n_buckets ? cursor[bb] : 0u; };
+    auto rec_of = [&](u32 bb) -> u64 { return bb < n_buckets ? recs[(u64) bb * RC + threadIdx.x] : 0ULL; };
+    u32 nr0 = n_rec_of(b), nr1 = n_rec_of(b + stride);
+    u64 rec0 = rec_of(b), rec1 = rec_of(b + stride);
+    u64 w0[NW], w1[NW];
+    kc_sig_load_words<NW>(packed, rec0, threadIdx.x < nr0 && nr0 <= RC, w0);
+    for (; b < n_buckets; b += stride) {
+        const u32 nr2 = n_rec_of(b + 2 * stride);
+        const u64 rec2 = rec_of(b + 2 * stride);
+        kc_sig_load_words<NW>(packed, rec1, threadIdx.x < nr1 && nr1 <= RC, w1);
+        const u32 n_rec = nr0;
+        const bool skip = n_rec == 0 || n_rec > RC;  // uniform over the CTA
+        if (n_rec > RC && threadIdx.x == 0) status[0] = 1;  // the scan has set the status word already
+        if (!skip) {
+            {
+                uint4 *t2v = reinterpret_cast<uint4 *>(T2) + threadIdx.x * (T2N / 4 / Cfg::THREADS);
 #pragma unroll
-            for (int wi = 0; wi < NW; ++wi) {
-                const i64 p = s0 - 32 * (NW - 1 - wi);
-                u64 codes = 0;
-                if (p >= 0 && (u64) p + 32 <= n_bytes) {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(seq + p);
-                    const uint4 a4 = __ldg(src), b4 = __ldg(src + 1);
-                    const u32 w[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
+                for (u32 q = 0; q < T2N / 4 / Cfg::THREADS; ++q) t2v[q] = make_uint4(KC_NONE, KC_NONE, KC_NONE, KC_NONE);
+            }
+            // P1: the thread's record -> its k-mers, canonical, into the tables
+            const bool have = threadIdx.x < n_rec;
+            const u32 pos = (u32) rec0, len = have ? ((u32) (rec0 >> 32) & 7u) + 1u : 0u;
+            u32 h1[P];
+            if (have) {
+                const int sh = 2 * (31 - (int) (pos & 31u));
+                const u64 mine = w0[NW - 1];
+                const u64 ms = sh ? mine << (64 - sh) : 0ULL;  // the bases behind the first window, left-aligned
+                if constexpr (L == 1) {
+                    u64 f = (sh ? (mine >> sh) | (w0[0] << (64 - sh)) : mine) & kmask.w[0];
+                    const u64 tmask = kmask.w[0] << lsh;
+                    u64 ral = ~kc_reverse_symbols64_brev(f) & tmask;  // reverse complement, left-aligned
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) codes = (codes << 8) | kc_codes4(w[j]);
-                } else if (p + 32 > 0 && (u64) (p < 0 ? 0 : p) < n_bytes) {
-                    for (int j = 0; j < 32; ++j) {
-                        const i64 q = p + j;
-                        u32 code = 0;
-                        if (q >= 0 && (u64) q < n_bytes) code = kc_nucleotide_code(seq[q]) & 3u;
-                        codes = (codes << 2) | code;
+                    for (int t = 0; t < P; ++t) {
+                        if ((u32) t < len) {
+                            if (t) {
+                                const u64 c = (ms >> (64 - 2 * t)) & 3ULL;
+                                f = ((f << 2) | c) & kmask.w[0];
+                                ral = ((ral >> 2) | ((3ULL ^ c) << 62)) & tmask;
+                            }
+                            const u64 r = ral >> lsh;
+                            const u64 canon = (!complements || f < r) ? f : r;
+                            const u32 slot = (u32) t * RC + threadIdx.x;
+                            sk[slot].w[0] = canon;
+                            sp[slot] = pos + (u32) t;
+                            const u64 h = canon * 0xD6E8FEB86659FD93ULL;
+                            h1[t] = (u32) (h >> (64 - Cfg::T1_BITS));
+                            T1[h1[t]] = (u16) slot;
+                        }
+                    }
+                } else {
+                    KWord<L> f;
+#pragma unroll
+                    for (int l = 0; l < L; ++l) f.w[l] = sh ? (w0[NW - 1 - l] >> sh) | (w0[NW - 2 - l] << (64 - sh)) : w0[NW - 1 - l];
+                    f = f & kmask;
+                    KWord<L> r;
+#pragma unroll
+                    for (int i = 0; i < L; ++i) r.w[i] = ~kc_reverse_symbols64_brev(f.w[L - 1 - i]);
+                    r = r.shr(lsh);
+#pragma unroll
+                    for (int t = 0; t < P; ++t) {
+                        if ((u32) t < len) {
+                            if (t) {  // roll both strands by one base
+                                const u64 c = (ms >> (64 - 2 * t)) & 3ULL;
+                                f = f.shl(2);
+                                f.w[0] |= c;
+                                f = f & kmask;
+                                r = r.shr(2);
+#pragma unroll
+                                for (int i = 0; i < L; ++i)
+                                    if (i == top_limb) r.w[i] |= (3ULL ^ c) << top_off;
+                            }
+                            const KWord<L> canon = (!complements || f < r) ? f : r;
+                            const u32 slot = (u32) t * RC + threadIdx.x;
+                            sk[slot] = canon;
+                            sp[slot] = pos + (u32) t;
+                            u64 h = 0;
+#pragma unroll
+                            for (int q = 0; q < L; ++q) h = (h ^ canon.w[q]) * 0xD6E8FEB86659FD93ULL;
+                            h1[t] = (u32) (h >> (64 - Cfg::T1_BITS));
+                            T1[h1[t]] = (u16) slot;
+                        }
                     }
                 }
-                swords[wi * REC_CAP + r] = codes;
             }
-            recinfo[r] = pos - ib;
-            for (u32 t = 0; t < len; ++t) map[ib + t] = (u16) r;
-        }
-        __syncthreads();
-        // P1: a thread per window: k-mer out of the record's words, canonical, into the tables
-        {
-            uint4 *t2v = reinterpret_cast<uint4 *>(T2) + threadIdx.x * (NI / 4);
+            __syncthreads();
+            // P2: the winner of a T1 slot represents its key; equal key = duplicate (fold the positions, clear the larger one's bit);
+            //     different key -> T2 with CAS + linear probing
 #pragma unroll
-            for (int q = 0; q < NI / 4; ++q) t2v[q] = make_uint4(KC_NONE, KC_NONE, KC_NONE, KC_NONE);
-        }
-        KWord<L> key[NI];
-        u32 h1[NI], h2[NI];
-#pragma unroll
-        for (int m = 0; m < NI; ++m) {
-            const u32 i = threadIdx.x + (u32) m * T;
-            if (i < n_items) {
-                const u32 r = map[i];
-                const u32 p = recinfo[r] + i;
-                const int sh = 2 * (31 - (int) (p & 31u));
-                KWord<L> f;
-#pragma unroll
-                for (int l = 0; l < L; ++l) {
-                    const u64 lo = swords[(NW - 1 - l) * REC_CAP + r], hi = swords[(NW - 2 - l) * REC_CAP + r];
-                    f.w[l] = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
-                }
-                f = f & kmask;
-                if (complements) {
-                    const KWord<L> rc = kmer_reverse_complement(f, k);
-                    if (rc < f) f = rc;
-                }
-                key[m] = f;
-                sk[i] = f;
-                sp[i] = p;
-                u64 h = 0;
-#pragma unroll
-                for (int w = 0; w < L; ++w) h = (h ^ f.w[w]) * 0xD6E8FEB86659FD93ULL;
-                h1[m] = (u32) (h >> (64 - T1_BITS));
-                h2[m] = (u32) (h >> (64 - 2 * T1_BITS)) & (T2N - 1);
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < NI; ++m) {
-            const u32 i = threadIdx.x + (u32) m * T;
-            if (i < n_items) T1[h1[m]] = (u16) i;
-        }
-        __syncthreads();
-        // P2: the winner of a T1 slot represents its key; equal key = duplicate (fold the positions, clear the larger one's bit);
-        //     different key -> T2 with CAS + linear probing
-        u32 o[NI];
-#pragma unroll
-        for (int m = 0; m < NI; ++m) {
-            const u32 i = threadIdx.x + (u32) m * T;
-            o[m] = i < n_items ? (u32) T1[h1[m]] : i;
-        }
-#pragma unroll
-        for (int m = 0; m < NI; ++m) {
-            const u32 i = threadIdx.x + (u32) m * T;
-            if (i >= n_items) continue;
-            if (o[m] == i) {
-                ++kept;
-            } else if (sk[o[m]] == key[m]) {
-                const u32 mine = sp[i];
-                const u32 was = atomicMin(&sp[o[m]], mine);
-                kc_flag_clear_all<MULTI>(fl, was > mine ? was : mine);
-            } else {
-                u32 s = h2[m];
-                while (true) {
-                    const u32 old = atomicCAS(&T2[s], KC_NONE, i);
-                    if (old == KC_NONE) {
+            for (int t = 0; t < P; ++t) {
+                if ((u32) t < len) {
+                    const u32 slot = (u32) t * RC + threadIdx.x;
+                    const u32 o = T1[h1[t]];
+                    if (o == slot) {
                         ++kept;
-                        break;
+                    } else {
+                        const KWord<L> key = sk[slot];
+                        if (sk[o] == key) {
+                            const u32 mine_p = sp[slot];
+                            const u32 was = atomicMin(&sp[o], mine_p);
+                            kc_flag_clear_all<MULTI>(fl, was > mine_p ? was : mine_p);
+                        } else {
+                            u64 h = 0;
+#pragma unroll
+                            for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0xD6E8FEB86659FD93ULL;
+                            u32 s = (u32) (h >> (64 - 2 * Cfg::T1_BITS)) & (T2N - 1);
+#pragma unroll 1
+                            for (u32 probes = 0;; ++probes) {
+                                if (probes == T2N) {  // T2 is full (never seen: it would take > 1024 T1 collisions in one bucket)
+                                    status[0] = 1;
+                                    break;
+                                }
+                                const u32 old = atomicCAS(&T2[s], KC_NONE, slot);
+                                if (old == KC_NONE) {
+                                    ++kept;
+                                    break;
+                                }
+                                if (sk[old] == key) {
+                                    const u32 mine_p = sp[slot];
+                                    const u32 was = atomicMin(&sp[old], mine_p);
+                                    kc_flag_clear_all<MULTI>(fl, was > mine_p ? was : mine_p);
+                                    break;
+                                }
+                                s = (s + 1) & (T2N - 1);
+                            }
+                        }
                     }
-                    if (sk[old] == key[m]) {
-                        const u32 mine = sp[i];
-                        const u32 was = atomicMin(&sp[old], mine);
-                        kc_flag_clear_all<MULTI>(fl, was > mine ? was : mine);
-                        break;
-                    }
-                    s = (s + 1) & (T2N - 1);
                 }
             }
+            __syncthreads();  // the next bucket's P1 overwrites sk / sp / T1 / T2
         }
-        // no barrier here: P0 of the next bucket writes swords / recinfo / map only, which P2 does not read, and its barrier
-        // keeps P1 (sk, sp, T1, T2) behind every thread's P2
+        nr0 = nr1;
+        nr1 = nr2;
+        rec0 = rec1;
+        rec1 = rec2;
+#pragma unroll
+        for (int wi = 0; wi < NW; ++wi) w0[wi] = w1[wi];
     }
 #pragma unroll
     for (int o2 = 16; o2 > 0; o2 >>= 1) kept += __shfl_down_sync(0xFFFFFFFFu, kept, o2);
@@ -357,9 +403,6 @@ __global__ void __launch_bounds__(SigCfg<L>::THREADS, SigCfg<L>::MIN_CTAS) kc_si
 
 template <int L> struct SigKernels {
     typedef SigCfg<L> Cfg;
-    static int smem_r() {
-        return (int) (Cfg::CAP * (sizeof(KWord<L>) + 4 + 4 + 2 * 2 + 2) + Cfg::REC_CAP * (Cfg::NW * 8 + 4));
-    }
     struct Dev {
         int n_sm = 0, occ = 0;
     };
@@ -367,22 +410,22 @@ template <int L> struct SigKernels {
         static KcDevOnce once;
         static Dev dev[KC_MAX_DEVICES];
         const int d = once.run([&](int dv) {
-            KC_CUDA(cudaFuncSetAttribute(kc_sig_resolve_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r()));
-            KC_CUDA(cudaFuncSetAttribute(kc_sig_resolve_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r()));
+            KC_CUDA(cudaFuncSetAttribute(kc_sig_resolve_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem()));
+            KC_CUDA(cudaFuncSetAttribute(kc_sig_resolve_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem()));
             dev[dv].n_sm = kc_sm_count(dv);
-            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev[dv].occ, kc_sig_resolve_kernel<L, false>, Cfg::THREADS, smem_r()));
+            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev[dv].occ, kc_sig_resolve_kernel<L, false>, Cfg::THREADS, Cfg::smem()));
         });
         return dev[d];
     }
 };
 
-inline void kc_sig_scan_launch(int m, u32 blocks, cudaStream_t st, const u8 *seq, u64 n_bytes, int k, int a, u32 n_buckets, u32 rec_cap, u32 item_cap,
-                               kc_ull *cursor, u64 *recs, u32 *flags, u32 n_flag_words, u32 tile0, kc_ull *m_cell, u32 *status, const u32 *win_mask) {
+inline void kc_sig_scan_launch(int m, u32 blocks, cudaStream_t st, const u8 *seq, u64 n_bytes, int k, int a, u32 n_buckets, u32 *cursor, u64 *recs, u64 *packed,
+                               u32 *flags, u32 n_flag_words, u32 tile0, kc_ull *m_cell, u32 *status, const u32 *win_mask) {
     switch (m) {
-    case 16: kc_sig_scan_kernel<16><<<blocks, 256, 0, st>>>(seq, n_bytes, k, a, n_buckets, rec_cap, item_cap, cursor, recs, flags, n_flag_words, tile0, m_cell, status, win_mask); break;
-    case 15: kc_sig_scan_kernel<15><<<blocks, 256, 0, st>>>(seq, n_bytes, k, a, n_buckets, rec_cap, item_cap, cursor, recs, flags, n_flag_words, tile0, m_cell, status, win_mask); break;
-    case 12: kc_sig_scan_kernel<12><<<blocks, 256, 0, st>>>(seq, n_bytes, k, a, n_buckets, rec_cap, item_cap, cursor, recs, flags, n_flag_words, tile0, m_cell, status, win_mask); break;
-    default: kc_sig_scan_kernel<11><<<blocks, 256, 0, st>>>(seq, n_bytes, k, a, n_buckets, rec_cap, item_cap, cursor, recs, flags, n_flag_words, tile0, m_cell, status, win_mask); break;
+    case 16: kc_sig_scan_kernel<16><<<blocks, 256, 0, st>>>(seq, n_bytes, k, a, n_buckets, cursor, recs, packed, flags, n_flag_words, tile0, m_cell, status, win_mask); break;
+    case 15: kc_sig_scan_kernel<15><<<blocks, 256, 0, st>>>(seq, n_bytes, k, a, n_buckets, cursor, recs, packed, flags, n_flag_words, tile0, m_cell, status, win_mask); break;
+    case 12: kc_sig_scan_kernel<12><<<blocks, 256, 0, st>>>(seq, n_bytes, k, a, n_buckets, cursor, recs, packed, flags, n_flag_words, tile0, m_cell, status, win_mask); break;
+    default: kc_sig_scan_kernel<11><<<blocks, 256, 0, st>>>(seq, n_bytes, k, a, n_buckets, cursor, recs, packed, flags, n_flag_words, tile0, m_cell, status, win_mask); break;
     }
     KC_CUDA(cudaGetLastError());
 }
@@ -395,20 +438,21 @@ bool kc_kmerset_build_sig(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool 
                           InputChunks *chunks = nullptr, const u32 *win_mask = nullptr, SigPlan *plan_out = nullptr) {
     typedef SigCfg<L> Cfg;
     typedef SigKernels<L> KK;
-    const SigPlan pl = kc_sig_plan(n_bytes, k, Cfg::CAP, tune);
+    const SigPlan pl = kc_sig_plan(n_bytes, k, tune);
     if (plan_out) *plan_out = pl;
     if (!pl.ok) return false;
     const typename KK::Dev &dv = KK::prepare();
     cudaStream_t st = ex.stream;
     const size_t base_mark = ex.arena->mark();
-    u64 *recs = ex.alloc<u64>((u64) pl.n_buckets * Cfg::REC_CAP);
-    kc_ull *cursor = reinterpret_cast<kc_ull *>(ex.alloc<u64>(pl.n_buckets));
-    ex.fill_bytes(cursor, 0, (size_t) pl.n_buckets * 8);
+    constexpr u64 TILE = 256 * KC_EX_STRIP;
+    const u32 blocks = (u32) kc_div_up(n_bytes, TILE);
+    u64 *recs = ex.alloc<u64>((u64) pl.n_buckets * KC_SIG_REC_CAP);
+    u64 *packed = ex.alloc<u64>((u64) blocks * 256);
+    u32 *cursor = ex.alloc<u32>(pl.n_buckets);
+    ex.fill_bytes(cursor, 0, (size_t) pl.n_buckets * 4);
     u32 *status = reinterpret_cast<u32 *>(cells + 3);
     kc_ull *m_cell = reinterpret_cast<kc_ull *>(cells + 2);
-    constexpr u64 TILE = 256 * KC_EX_STRIP;
     {
-        const u32 blocks = (u32) kc_div_up(n_bytes, TILE);
         const int n_parts = chunks && chunks->n > 1 && !chunks->waited ? chunks->n : 1;
         if (chunks && n_parts == 1) chunks->wait_all(st);
         for (int c = 0; c < n_parts; ++c) {
@@ -420,9 +464,10 @@ bool kc_kmerset_build_sig(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool 
             }
             if (t1 <= t0) continue;
             const u64 part_bytes = std::min<u64>(n_bytes, (u64) t1 * TILE) - (u64) t0 * TILE;
-            CudaExec::Scope sc(ex, KP_KS_SCATTER0, part_bytes + part_bytes / 5);
-            kc_sig_scan_launch(pl.m, t1 - t0, st, seq, n_bytes, k, pl.a, pl.n_buckets, Cfg::REC_CAP, Cfg::CAP, cursor, recs, flags,
-                               (u32) (kc_div_up(n_bytes, (u64) 32) + 1), t0, m_cell, status, win_mask);
+            // sequence read, code words + flag words + records written
+            CudaExec::Scope sc(ex, KP_KS_SCATTER0, part_bytes + part_bytes / 4 + part_bytes / 8 + (u64) (part_bytes * 8 / KC_SIG_WINDOWS_PER_RECORD));
+            kc_sig_scan_launch(pl.m, t1 - t0, st, seq, n_bytes, k, pl.a, pl.n_buckets, cursor, recs, packed, flags, (u32) (kc_div_up(n_bytes, (u64) 32) + 1), t0,
+                               m_cell, status, win_mask);
             ++ex.launches;
         }
         if (chunks) chunks->waited = true;
@@ -430,9 +475,10 @@ bool kc_kmerset_build_sig(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool 
     {
         const u32 fit = (u32) (dv.n_sm * (dv.occ > 0 ? dv.occ : 1));
         const u32 grid = pl.n_buckets < fit ? pl.n_buckets : fit;
-        CudaExec::Scope sc(ex, KP_KS_RESOLVE, n_bytes / 5 + n_bytes * 10);
-        kc_sig_resolve_kernel<L, false><<<grid, Cfg::THREADS, KK::smem_r(), st>>>(seq, n_bytes, k, complements ? 1 : 0, cursor, recs, pl.n_buckets,
-                                                                                  kc_ksf_own_flags(flags), reinterpret_cast<kc_ull *>(cells), status);
+        // records read, two code words per record
+        CudaExec::Scope sc(ex, KP_KS_RESOLVE, (u64) (n_bytes * (8 + 8 * Cfg::NW) / KC_SIG_WINDOWS_PER_RECORD));
+        kc_sig_resolve_kernel<L, false><<<grid, Cfg::THREADS, Cfg::smem(), st>>>(packed, k, complements ? 1 : 0, cursor, recs, pl.n_buckets, kc_ksf_own_flags(flags),
+                                                                               reinterpret_cast<kc_ull *>(cells), status);
         ++ex.launches;
         KC_CUDA(cudaGetLastError());
     }
