@@ -26,13 +26,14 @@
 //     ranks' bits read over NVLink.
 #pragma once
 #include "kmerset_fast.cuh"
+#include "kmerset_sig.cuh"
 #include "runs.cuh"
 
 struct GrpLayout {
     u64 n_bytes_cap = 0;
     int limbs = 0, n_ranks = 0;
     u64 recv_items = 0, flag_words = 0;
-    size_t off_sig = 0, off_cells = 0, off_cnt = 0, off_flags = 0, off_flags2 = 0, off_recv_k = 0, off_recv_p = 0, off_seq = 0, total = 0;
+    size_t off_sig = 0, off_cells = 0, off_cnt = 0, off_flags = 0, off_flags2 = 0, off_recv_k = 0, off_recv_p = 0, off_packed = 0, off_seq = 0, total = 0;
 };
 
 // Heap of a rank for jobs of up to n_bytes_cap sequence bytes (identical on every rank).
@@ -59,6 +60,7 @@ inline GrpLayout kc_grp_layout(u64 n_bytes_cap, int limbs, int n_ranks, bool wit
     y.off_flags2 = take(y.flag_words * 4);
     y.off_recv_k = take(y.recv_items * 8 * (u64) limbs);
     y.off_recv_p = take(y.recv_items * 4);
+    y.off_packed = take(n_bytes_cap / 4 + 4096);  // 2-bit code words of the whole sequence (signature construction, kmerset_sig.cuh)
     y.off_seq = take(with_seq ? n_bytes_cap + 256 : 0);
     y.total = o;
     return y;
@@ -291,6 +293,59 @@ u64 *kc_grp_fast_flags(KcGroup &G, CudaExec &ex, const u8 *seq, u64 n_bytes, int
     }
     kc_ksf_group_resolve<L>(ex, min_freq, gp, G.rank, reinterpret_cast<const KWord<L> *>(G.heap + G.lay.off_recv_k),
                             reinterpret_cast<const u32 *>(G.heap + G.lay.off_recv_p), sub_cnt, G.all_flags(G.lay.off_flags), G.cells_local, tune);
+    ex.arena->release(mark);
+    const u32 sb = ++G.seq;
+    kc_grp_signal(G, ex, sb, nullptr, 0, 0, G.cells_local);
+    kc_grp_wait(G, ex, sb, wait_status);
+    kc_grp_sum_cells(G, ex, cells4, wait_status);
+    return cells4;
+}
+
+// ---- signature buckets (kmerset_sig.cuh) ---------------------------------------------------------------------------------------------
+// What travels is a RECORD (8 bytes for ~5 windows) instead of a 12-byte item per window, so the exchange over NVLink shrinks
+// ~7 x and the owner needs no further partition level: the bucket a record lands in is already the unit the resolve works on.
+//   scan      rank r scans its slice of the tiles: record -> sub-slot (bucket / n, r) of the bucket's owner (bucket % n), reserved
+//             with a LOCAL counter; code words + valid-window words of the slice -> every rank; then the fill counts -> the owners
+//   signal A / wait A
+//   resolve   the owner walks its buckets (the sub-slots of all senders back to back), clears a duplicate's bit in EVERY rank's flags
+//   signal B  (kept, M, overflow status) -> every rank / wait B
+// The receive array lives in the key receive region of the heap, the fill counts in the position receive region.
+// Returns nullptr when the plan does not apply to this job (too small, k < 26, heap regions too small).
+template <int L>
+u64 *kc_grp_sig_flags(KcGroup &G, CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, const SigTuning &tune) {
+    const SigPlan pl = kc_sig_plan(n_bytes, k, tune);
+    if (!pl.ok || G.n < 1 || pl.n_buckets >= (1u << 28)) return nullptr;
+    const u32 sub_cap = kc_sig_sub_cap(tune, G.n);
+    const u32 own_max = kc_sig_owned_buckets(pl.n_buckets, G.n, 0);
+    if ((u64) own_max * (u64) G.n * sub_cap * 8 > G.lay.recv_items * 8 * (u64) G.lay.limbs) return nullptr;
+    if ((u64) own_max * (u64) G.n * 4 > G.lay.recv_items * 4) return nullptr;
+    u32 *flags = reinterpret_cast<u32 *>(G.heap + G.lay.off_flags);
+    const u64 body_words = kc_div_up(n_bytes, (u64) 32);
+    ex.fill_bytes(flags + body_words, 0, 8);  // the padding words nobody writes (kc_runs_load reads one past the end)
+    SigPeers sp;
+    for (int i = 0; i < KC_MAX_PEERS; ++i) {
+        sp.recs[i] = i < G.n ? reinterpret_cast<u64 *>(G.peer[i] + G.lay.off_recv_k) : nullptr;
+        sp.packed[i] = i < G.n ? reinterpret_cast<u64 *>(G.peer[i] + G.lay.off_packed) : nullptr;
+        sp.flags[i] = i < G.n ? reinterpret_cast<u32 *>(G.peer[i] + G.lay.off_flags) : nullptr;
+        sp.cnt[i] = i < G.n ? reinterpret_cast<u32 *>(G.peer[i] + G.lay.off_recv_p) : nullptr;
+    }
+    sp.n = G.n;
+    sp.rank = G.rank;
+    sp.magic = (u32) (0x100000000ULL / (u64) G.n) + 1u;
+    sp.sub_cap = sub_cap;
+    u64 *cells4 = ex.arena->alloc_top<u64>(4);
+    u32 *wait_status = reinterpret_cast<u32 *>(ex.arena->alloc_top<u64>(1));
+    ex.fill_bytes(G.cells_local, 0, 32);
+    ex.fill_bytes(wait_status, 0, 8);
+    const size_t mark = ex.arena->mark();
+    u32 *cursor = ex.alloc<u32>(pl.n_buckets);
+    kc_sig_group_scan(ex, seq, n_bytes, k, pl, sp, cursor, G.cells_local);
+    const u32 sa = ++G.seq;
+    kc_grp_signal(G, ex, sa);
+    kc_grp_wait(G, ex, sa, wait_status);
+    kc_sig_group_resolve<L>(ex, reinterpret_cast<const u64 *>(G.heap + G.lay.off_packed), k, complements, kc_sig_owned_buckets(pl.n_buckets, G.n, G.rank),
+                            reinterpret_cast<const u32 *>(G.heap + G.lay.off_recv_p), reinterpret_cast<const u64 *>(G.heap + G.lay.off_recv_k), G.n, sub_cap,
+                            G.all_flags(G.lay.off_flags), G.cells_local, n_bytes);
     ex.arena->release(mark);
     const u32 sb = ++G.seq;
     kc_grp_signal(G, ex, sb, nullptr, 0, 0, G.cells_local);

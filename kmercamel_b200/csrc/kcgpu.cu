@@ -609,6 +609,30 @@ template <int L> void group_compute_rank(kc_ctx *ctx, CudaExec &ex, const DevInp
         kc_grp_signal(G, ex, G.done_seq);
         G.done_pending = true;
     };
+    // signature buckets first (kmerset_sig.cuh): every rank takes the same decision from values it sees identically
+    const bool sig_overflowed = ctx->fast_heuristics && ctx->sig_overflow_bytes && nb >= ctx->sig_overflow_bytes / 2 && nb <= ctx->sig_overflow_bytes * 2;
+    if (p.min_frequency == 1 && !sig_overflowed) {
+        const size_t top_mark = ex.arena->top, mark = ex.arena->mark();
+        ExtFlags ext;
+        ext.flags = reinterpret_cast<const u32 *>(G.heap + G.lay.off_flags);
+        ext.cells4 = kc_grp_sig_flags<L>(G, ex, in.seq, nb, p.k, p.complements != 0, ctx->sig);
+        if (ext.cells4) {
+            run_pipeline<L>(ctx, ex, in, p, res, &ext, false, (u32) G.rank, (u32) G.n);
+            if (!ext.aborted) {
+                ++ctx->sig_runs;
+                finish();
+                return;
+            }
+            if (ext.kept & 2u) {
+                G.failed = true;
+                KC_THROW(KC_ERR_INTERNAL, "a rank of the group did not arrive (wait timed out)");
+            }
+            ++ctx->sig_fallbacks;  // a bucket overflowed on some rank: every rank sees the same status word and falls back
+            ctx->sig_overflow_bytes = nb;
+        }
+        ex.arena->release(mark);
+        ex.arena->top = top_mark;
+    }
     const KsfGroupPlan gp = kc_ksf_group_plan(nb, G.n, KsCfg<L>::EX_TILE, ctx->fast);
     const bool expect_duplicates = ctx->fast_heuristics && (p.min_frequency > 1 || (ctx->fast_overflow_bytes && nb >= ctx->fast_overflow_bytes / 2 && nb <= ctx->fast_overflow_bytes * 2));
     if (gp.ok && !expect_duplicates && gp.recv_items() <= G.lay.recv_items) {

@@ -127,21 +127,39 @@ KC_D u32 kc_sig_bucket(u32 sig, u32 n_buckets) {
 // A record: bits 0..31 END position of its first window, 32..34 windows - 1.
 KC_HD u64 kc_sig_record(u32 pos, u32 len) { return (u64) pos | ((u64) (len - 1) << 32); }
 
+// Multi-GPU (group.cuh): bucket b belongs to rank b % n; rank r's records for it go into the sub-slot (b / n, r) of the owner's
+// receive array (sub_cap records, reserved with a LOCAL counter: no remote atomics), the code words and the valid-window words of
+// the rank's slice go to every rank.
+struct SigPeers {
+    u64 *recs[KC_MAX_PEERS];     // receive array of rank o: [bucket / n][sender][sub_cap]
+    u64 *packed[KC_MAX_PEERS];   // code words of the whole sequence, one copy per rank
+    u32 *flags[KC_MAX_PEERS];    // first-occurrence bits, one copy per rank
+    u32 *cnt[KC_MAX_PEERS];      // fill counts of the sub-slots of rank o: [bucket / n][sender]
+    int n, rank;
+    u32 magic;                   // floor(2^32 / n) + 1: b / n = umulhi(b, magic) for b < 2^28
+    u32 sub_cap;
+};
+
 // packed[s] = the 2-bit codes of bases 32 s .. 32 s + 31 (first base in the top bits); every strip of every tile is written.
-template <int M>
+template <int M, bool P2P>
 __global__ void __launch_bounds__(256) kc_sig_scan_kernel(const u8 *__restrict__ seq, u64 n_bytes, int k, int a, u32 n_buckets, u32 *cursor,
                                                           u64 *__restrict__ recs, u64 *__restrict__ packed, u32 *__restrict__ flags, u32 n_flag_words,
-                                                          u32 tile0, kc_ull *m_cell, u32 *status, const u32 *__restrict__ win_mask) {
+                                                          u32 tile0, kc_ull *m_cell, u32 *status, const u32 *__restrict__ win_mask, const SigPeers sp) {
     constexpr int T = 256;
     constexpr int NH = 32 + KC_SIG_W - 1;  // M-mer hashes a strip needs
     __shared__ u64 pk[KC_EX_HALO + T];
     __shared__ u32 vm[KC_EX_HALO + T];
-    __shared__ u32 ssig[KC_EX_STRIP * T];  // signature of the window ending at strip base j of thread t at [j * T + t]
+    __shared__ u32 ssig[KC_EX_STRIP * T];  // signature of the window ending at strip base j of thread t at [j * T + t]; later of its piece c
+    __shared__ u8 plist[KC_EX_STRIP * T];  // piece c of thread t at [c * T + t]: first window << 3 | windows - 1
     const i64 block_pos0 = (i64) (tile0 + blockIdx.x) * (T * KC_EX_STRIP);
     kc_tile_load<T>(seq, n_bytes, block_pos0, pk, vm);
     __syncthreads();
     const int widx = KC_EX_HALO + threadIdx.x;
-    packed[(u64) (block_pos0 >> 5) + threadIdx.x] = pk[widx];
+    if (P2P) {
+        for (int r = 0; r < sp.n; ++r) sp.packed[r][(u64) (block_pos0 >> 5) + threadIdx.x] = pk[widx];
+    } else {
+        packed[(u64) (block_pos0 >> 5) + threadIdx.x] = pk[widx];
+    }
     u32 em;
     {   // genomes: every base of the strip and of the k - 1 before it is a nucleotide (warp-uniform most of the time)
         const int need = (k - 1 + 31) >> 5;  // words to the left that a window of the strip can reach into
@@ -153,7 +171,12 @@ __global__ void __launch_bounds__(256) kc_sig_scan_kernel(const u8 *__restrict__
     em &= kc_strip_window_filter(win_mask, block_pos0);
     {   // clear-the-losers flags: every window starts as "first occurrence" (bit p & 31 of word p >> 5 = window END p)
         const u64 w = (u64) (block_pos0 >> 5) + threadIdx.x;
-        if (em && w < n_flag_words) flags[w] = __brev(em);
+        if (P2P) {  // the arrays of a group do not arrive zeroed: every word of the slice is written
+            if (w < n_flag_words)
+                for (int r = 0; r < sp.n; ++r) sp.flags[r][w] = __brev(em);
+        } else if (em && w < n_flag_words) {
+            flags[w] = __brev(em);
+        }
     }
     {
         u32 c = __popc(em);
@@ -191,24 +214,64 @@ __global__ void __launch_bounds__(256) kc_sig_scan_kernel(const u8 *__restrict__
     const u32 emr = __brev(em);                          // bit j = window ending at strip base j
     u32 run_starts = emr & (neq | ~(emr << 1));          // a run: valid windows of one signature
     const u32 stops = run_starts | ~emr;
-    const u32 pos0 = (u32) block_pos0 + threadIdx.x * KC_EX_STRIP;
-    bool over = false;
+    // the pieces (<= 8 windows) of the runs, listed first ...
+    u32 n_pieces = 0;
     while (run_starts) {
         u32 j = (u32) __ffs(run_starts) - 1u;
         run_starts &= run_starts - 1u;
         const u32 rest = j < 31 ? stops & (0xFFFFFFFFu << (j + 1)) : 0u;
         u32 len = (rest ? (u32) __ffs(rest) - 1u : 32u) - j;
-        const u32 b = kc_sig_bucket(ssig[j * T + threadIdx.x], n_buckets);
-        while (len) {  // pieces of <= 8 windows
+        const u32 sig = ssig[j * T + threadIdx.x];
+        while (len) {
             const u32 l = len < (u32) KC_SIG_PIECE ? len : (u32) KC_SIG_PIECE;
-            const u32 slot = atomicAdd(&cursor[b], 1u);
-            if (slot < KC_SIG_REC_CAP) recs[(u64) b * KC_SIG_REC_CAP + slot] = kc_sig_record(pos0 + j, l);
-            else over = true;
+            plist[n_pieces * T + threadIdx.x] = (u8) ((j << 3) | (l - 1u));
+            if (n_pieces != j) ssig[n_pieces * T + threadIdx.x] = sig;  // piece c <= its first window j: entries below c are never read again
+            ++n_pieces;
             j += l;
             len -= l;
         }
     }
+    // ... so that the atomics of eight pieces are in flight together (one at a time, the thread waited ~0.7 us for each slot:
+    // 51 % of the kernel's stall samples)
+    const u32 pos0 = (u32) block_pos0 + threadIdx.x * KC_EX_STRIP;
+    bool over = false;
+    for (u32 c0 = 0; c0 < n_pieces; c0 += 8) {
+        u32 bk[8], slot[8], e[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (c0 + u < n_pieces) {
+                e[u] = plist[(c0 + u) * T + threadIdx.x];
+                bk[u] = kc_sig_bucket(ssig[(c0 + u) * T + threadIdx.x], n_buckets);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (c0 + u < n_pieces) slot[u] = atomicAdd(&cursor[bk[u]], 1u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (c0 + u < n_pieces) {
+                const u64 rec = kc_sig_record(pos0 + (e[u] >> 3), (e[u] & 7u) + 1u);
+                if (P2P) {
+                    const u32 lb = __umulhi(bk[u], sp.magic), o = bk[u] - lb * (u32) sp.n;
+                    if (slot[u] < sp.sub_cap) sp.recs[o][((u64) lb * (u32) sp.n + (u32) sp.rank) * sp.sub_cap + slot[u]] = rec;
+                    else over = true;
+                } else {
+                    if (slot[u] < KC_SIG_REC_CAP) recs[(u64) bk[u] * KC_SIG_REC_CAP + slot[u]] = rec;
+                    else over = true;
+                }
+            }
+        }
+    }
     if (over) status[0] = 1;
+}
+
+// After the scan of a group rank: the fill count of every sub-slot it wrote -> the owner (clamped: the scan dropped the rest).
+__global__ void __launch_bounds__(256) kc_sig_counts_kernel(const u32 *__restrict__ cursor, u32 n_buckets, const SigPeers sp) {
+    const u32 b = blockIdx.x * 256 + threadIdx.x;
+    if (b >= n_buckets) return;
+    const u32 lb = __umulhi(b, sp.magic), o = b - lb * (u32) sp.n;
+    const u32 c = cursor[b];
+    sp.cnt[o][(u64) lb * (u32) sp.n + (u32) sp.rank] = c < sp.sub_cap ? c : sp.sub_cap;
 }
 
 template <int L> struct SigCfg {
@@ -242,7 +305,10 @@ template <int NW> KC_D void kc_sig_load_words(const u64 *__restrict__ packed, u6
 template <int L, bool MULTI>
 __global__ void __launch_bounds__(SigCfg<L>::THREADS, SigCfg<L>::MIN_CTAS) kc_sig_resolve_kernel(const u64 *__restrict__ packed, int k, int complements,
                                                                                                 const u32 *__restrict__ cursor, const u64 *__restrict__ recs,
-                                                                                                u32 n_buckets, KsfFlagPeers fl, kc_ull *n_unique, u32 *status) {
+                                                                                                u32 n_buckets, KsfFlagPeers fl, kc_ull *n_unique, u32 *status,
+                                                                                                u32 n_senders, u32 sub_cap) {
+    // MULTI: `cursor` = the fill counts [bucket][sender] of this rank's buckets, `recs` = its receive array [bucket][sender][sub_cap];
+    //        the records of a bucket are its senders' sub-slots back to back (thread i takes the i-th of them)
     typedef SigCfg<L> Cfg;
     constexpr u32 RC = KC_SIG_REC_CAP, T2N = Cfg::T2N;
     constexpr int NW = Cfg::NW, P = KC_SIG_PIECE;
@@ -256,18 +322,42 @@ __global__ void __launch_bounds__(SigCfg<L>::THREADS, SigCfg<L>::MIN_CTAS) kc_si
     const int top = 2 * (k - 1);
     const int top_limb = top >> 6, top_off = top & 63;
     const int lsh = 64 * L - 2 * k;  // left-aligned <-> right-aligned
+    const bool uni = complements == 0;
     u32 kept = 0;
     const u32 stride = gridDim.x;
     u32 b = blockIdx.x;
-    auto n_rec_of = [&](u32 bb) -> u32 { return bb < n_buckets ? cursor[bb] : 0u; };
-    auto rec_of = [&](u32 bb) -> u64 { return bb < n_buckets ? recs[(u64) bb * RC + threadIdx.x] : 0ULL; };
-    u32 nr0 = n_rec_of(b), nr1 = n_rec_of(b + stride);
-    u64 rec0 = rec_of(b), rec1 = rec_of(b + stride);
+    auto fetch = [&](u32 bb, u32 &nr, u64 &rec) {
+        nr = 0;
+        rec = 0;
+        if (bb >= n_buckets) return;
+        if constexpr (MULTI) {
+            const u32 *c = cursor + (u64) bb * n_senders;
+            u32 pre = 0, snd = n_senders, idx = 0;
+            for (u32 sd = 0; sd < n_senders; ++sd) {
+                const u32 cs = c[sd];
+                if (threadIdx.x >= pre && threadIdx.x < pre + cs) {
+                    snd = sd;
+                    idx = threadIdx.x - pre;
+                }
+                pre += cs;
+            }
+            nr = pre;
+            if (snd < n_senders) rec = recs[((u64) bb * n_senders + snd) * sub_cap + idx];
+        } else {
+            nr = cursor[bb];
+            rec = recs[(u64) bb * RC + threadIdx.x];
+        }
+    };
+    u32 nr0, nr1;
+    u64 rec0, rec1;
+    fetch(b, nr0, rec0);
+    fetch(b + stride, nr1, rec1);
     u64 w0[NW], w1[NW];
     kc_sig_load_words<NW>(packed, rec0, threadIdx.x < nr0 && nr0 <= RC, w0);
     for (; b < n_buckets; b += stride) {
-        const u32 nr2 = n_rec_of(b + 2 * stride);
-        const u64 rec2 = rec_of(b + 2 * stride);
+        u32 nr2;
+        u64 rec2;
+        fetch(b + 2 * stride, nr2, rec2);
         kc_sig_load_words<NW>(packed, rec1, threadIdx.x < nr1 && nr1 <= RC, w1);
         const u32 n_rec = nr0;
         const bool skip = n_rec == 0 || n_rec > RC;  // uniform over the CTA
@@ -299,7 +389,8 @@ __global__ void __launch_bounds__(SigCfg<L>::THREADS, SigCfg<L>::MIN_CTAS) kc_si
                                 ral = ((ral >> 2) | ((3ULL ^ c) << 62)) & tmask;
                             }
                             const u64 r = ral >> lsh;
-                            const u64 canon = (!complements || f < r) ? f : r;
+                            const bool take_f = uni | (f < r);
+                            const u64 canon = take_f ? f : r;
                             const u32 slot = (u32) t * RC + threadIdx.x;
                             sk[slot].w[0] = canon;
                             sp[slot] = pos + (u32) t;
@@ -344,46 +435,52 @@ __global__ void __launch_bounds__(SigCfg<L>::THREADS, SigCfg<L>::MIN_CTAS) kc_si
                 }
             }
             __syncthreads();
-            // P2: the winner of a T1 slot represents its key; equal key = duplicate (fold the positions, clear the larger one's bit);
-            //     different key -> T2 with CAS + linear probing
+            // P2: the winner of a T1 slot represents its key (~92 % of the items: done).  The others are listed in a bit mask and
+            //     handled in a loop of their own (a thread has ~0.4 of them; inside the unrolled pass over t every warp paid the
+            //     slow path eight times): equal key = duplicate (fold the positions, clear the larger one's bit); different key ->
+            //     T2 with CAS + linear probing
+            u32 slow = 0;
 #pragma unroll
             for (int t = 0; t < P; ++t) {
                 if ((u32) t < len) {
-                    const u32 slot = (u32) t * RC + threadIdx.x;
                     const u32 o = T1[h1[t]];
-                    if (o == slot) {
-                        ++kept;
-                    } else {
-                        const KWord<L> key = sk[slot];
-                        if (sk[o] == key) {
-                            const u32 mine_p = sp[slot];
-                            const u32 was = atomicMin(&sp[o], mine_p);
-                            kc_flag_clear_all<MULTI>(fl, was > mine_p ? was : mine_p);
-                        } else {
-                            u64 h = 0;
+                    if (o == (u32) t * RC + threadIdx.x) ++kept;
+                    else slow |= 1u << t;
+                }
+            }
+            while (slow) {
+                const u32 t = (u32) __ffs(slow) - 1u;
+                slow &= slow - 1u;
+                const u32 slot = t * RC + threadIdx.x;
+                const KWord<L> key = sk[slot];
+                u64 h = 0;
 #pragma unroll
-                            for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0xD6E8FEB86659FD93ULL;
-                            u32 s = (u32) (h >> (64 - 2 * Cfg::T1_BITS)) & (T2N - 1);
+                for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0xD6E8FEB86659FD93ULL;
+                const u32 o = T1[(u32) (h >> (64 - Cfg::T1_BITS))];
+                if (sk[o] == key) {
+                    const u32 mine_p = sp[slot];
+                    const u32 was = atomicMin(&sp[o], mine_p);
+                    kc_flag_clear_all<MULTI>(fl, was > mine_p ? was : mine_p);
+                } else {
+                    u32 s2 = (u32) (h >> (64 - 2 * Cfg::T1_BITS)) & (T2N - 1);
 #pragma unroll 1
-                            for (u32 probes = 0;; ++probes) {
-                                if (probes == T2N) {  // T2 is full (never seen: it would take > 1024 T1 collisions in one bucket)
-                                    status[0] = 1;
-                                    break;
-                                }
-                                const u32 old = atomicCAS(&T2[s], KC_NONE, slot);
-                                if (old == KC_NONE) {
-                                    ++kept;
-                                    break;
-                                }
-                                if (sk[old] == key) {
-                                    const u32 mine_p = sp[slot];
-                                    const u32 was = atomicMin(&sp[old], mine_p);
-                                    kc_flag_clear_all<MULTI>(fl, was > mine_p ? was : mine_p);
-                                    break;
-                                }
-                                s = (s + 1) & (T2N - 1);
-                            }
+                    for (u32 probes = 0;; ++probes) {
+                        if (probes == T2N) {  // T2 is full (never seen: it would take > 1024 T1 collisions in one bucket)
+                            status[0] = 1;
+                            break;
                         }
+                        const u32 old = atomicCAS(&T2[s2], KC_NONE, slot);
+                        if (old == KC_NONE) {
+                            ++kept;
+                            break;
+                        }
+                        if (sk[old] == key) {
+                            const u32 mine_p = sp[slot];
+                            const u32 was = atomicMin(&sp[old], mine_p);
+                            kc_flag_clear_all<MULTI>(fl, was > mine_p ? was : mine_p);
+                            break;
+                        }
+                        s2 = (s2 + 1) & (T2N - 1);
                     }
                 }
             }
@@ -419,13 +516,14 @@ template <int L> struct SigKernels {
     }
 };
 
+template <bool P2P>
 inline void kc_sig_scan_launch(int m, u32 blocks, cudaStream_t st, const u8 *seq, u64 n_bytes, int k, int a, u32 n_buckets, u32 *cursor, u64 *recs, u64 *packed,
-                               u32 *flags, u32 n_flag_words, u32 tile0, kc_ull *m_cell, u32 *status, const u32 *win_mask) {
+                               u32 *flags, u32 n_flag_words, u32 tile0, kc_ull *m_cell, u32 *status, const u32 *win_mask, const SigPeers &sp) {
     switch (m) {
-    case 16: kc_sig_scan_kernel<16><<<blocks, 256, 0, st>>>(seq, n_bytes, k, a, n_buckets, cursor, recs, packed, flags, n_flag_words, tile0, m_cell, status, win_mask); break;
-    case 15: kc_sig_scan_kernel<15><<<blocks, 256, 0, st>>>(seq, n_bytes, k, a, n_buckets, cursor, recs, packed, flags, n_flag_words, tile0, m_cell, status, win_mask); break;
-    case 12: kc_sig_scan_kernel<12><<<blocks, 256, 0, st>>>(seq, n_bytes, k, a, n_buckets, cursor, recs, packed, flags, n_flag_words, tile0, m_cell, status, win_mask); break;
-    default: kc_sig_scan_kernel<11><<<blocks, 256, 0, st>>>(seq, n_bytes, k, a, n_buckets, cursor, recs, packed, flags, n_flag_words, tile0, m_cell, status, win_mask); break;
+    case 16: kc_sig_scan_kernel<16, P2P><<<blocks, 256, 0, st>>>(seq, n_bytes, k, a, n_buckets, cursor, recs, packed, flags, n_flag_words, tile0, m_cell, status, win_mask, sp); break;
+    case 15: kc_sig_scan_kernel<15, P2P><<<blocks, 256, 0, st>>>(seq, n_bytes, k, a, n_buckets, cursor, recs, packed, flags, n_flag_words, tile0, m_cell, status, win_mask, sp); break;
+    case 12: kc_sig_scan_kernel<12, P2P><<<blocks, 256, 0, st>>>(seq, n_bytes, k, a, n_buckets, cursor, recs, packed, flags, n_flag_words, tile0, m_cell, status, win_mask, sp); break;
+    default: kc_sig_scan_kernel<11, P2P><<<blocks, 256, 0, st>>>(seq, n_bytes, k, a, n_buckets, cursor, recs, packed, flags, n_flag_words, tile0, m_cell, status, win_mask, sp); break;
     }
     KC_CUDA(cudaGetLastError());
 }
@@ -466,8 +564,8 @@ bool kc_kmerset_build_sig(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool 
             const u64 part_bytes = std::min<u64>(n_bytes, (u64) t1 * TILE) - (u64) t0 * TILE;
             // sequence read, code words + flag words + records written
             CudaExec::Scope sc(ex, KP_KS_SCATTER0, part_bytes + part_bytes / 4 + part_bytes / 8 + (u64) (part_bytes * 8 / KC_SIG_WINDOWS_PER_RECORD));
-            kc_sig_scan_launch(pl.m, t1 - t0, st, seq, n_bytes, k, pl.a, pl.n_buckets, cursor, recs, packed, flags, (u32) (kc_div_up(n_bytes, (u64) 32) + 1), t0,
-                               m_cell, status, win_mask);
+            kc_sig_scan_launch<false>(pl.m, t1 - t0, st, seq, n_bytes, k, pl.a, pl.n_buckets, cursor, recs, packed, flags, (u32) (kc_div_up(n_bytes, (u64) 32) + 1),
+                                      t0, m_cell, status, win_mask, SigPeers());
             ++ex.launches;
         }
         if (chunks) chunks->waited = true;
@@ -478,12 +576,60 @@ bool kc_kmerset_build_sig(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool 
         // records read, two code words per record
         CudaExec::Scope sc(ex, KP_KS_RESOLVE, (u64) (n_bytes * (8 + 8 * Cfg::NW) / KC_SIG_WINDOWS_PER_RECORD));
         kc_sig_resolve_kernel<L, false><<<grid, Cfg::THREADS, Cfg::smem(), st>>>(packed, k, complements ? 1 : 0, cursor, recs, pl.n_buckets, kc_ksf_own_flags(flags),
-                                                                               reinterpret_cast<kc_ull *>(cells), status);
+                                                                               reinterpret_cast<kc_ull *>(cells), status, 1u, KC_SIG_REC_CAP);
         ++ex.launches;
         KC_CUDA(cudaGetLastError());
     }
     ex.arena->release(base_mark);
     return true;
+}
+
+// ---- multi-GPU (group.cuh) -----------------------------------------------------------------------------------------------------
+// Records a (bucket, sender) sub-slot must hold: the bucket's mean share + 6 sigma (records arrive in clumps: sigma ~ 1.5 sqrt(mean)).
+inline u32 kc_sig_sub_cap(const SigTuning &t, int n_ranks) {
+    const double mean = KC_SIG_REC_CAP * (t.load_pct / 100.0) / n_ranks;
+    u32 cap = (u32) (mean * 1.06 + 6.0 * 1.5 * std::sqrt(mean) + 8.0);
+    cap = (cap + 31) / 32 * 32;
+    return cap < KC_SIG_REC_CAP ? cap : KC_SIG_REC_CAP;
+}
+inline u32 kc_sig_owned_buckets(u32 n_buckets, int n_ranks, int rank) { return (n_buckets + (u32) n_ranks - 1u - (u32) rank) / (u32) n_ranks; }
+
+// The scan of this rank's slice of the tiles: records into the owners' sub-slots, code words and valid-window words to every rank,
+// then the fill counts of its sub-slots to the owners.  cells: {-, -, M of the slice (+=), status (low word)}.
+inline void kc_sig_group_scan(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, const SigPlan &pl, const SigPeers &sp, u32 *cursor /* [n_buckets] */, u64 *cells) {
+    constexpr u64 TILE = 256 * KC_EX_STRIP;
+    const u32 tiles = (u32) kc_div_up(n_bytes, TILE);
+    const u32 t0 = (u32) ((u64) tiles * (u32) sp.rank / (u32) sp.n), t1 = (u32) ((u64) tiles * ((u32) sp.rank + 1) / (u32) sp.n);
+    ex.fill_bytes(cursor, 0, (size_t) pl.n_buckets * 4);
+    if (t1 > t0) {
+        const u64 part_bytes = std::min<u64>(n_bytes, (u64) t1 * TILE) - (u64) t0 * TILE;
+        CudaExec::Scope sc(ex, KP_KS_SCATTER0, part_bytes + (part_bytes / 4 + part_bytes / 8) * (u64) sp.n + (u64) (part_bytes * 8 / KC_SIG_WINDOWS_PER_RECORD));
+        kc_sig_scan_launch<true>(pl.m, t1 - t0, ex.stream, seq, n_bytes, k, pl.a, pl.n_buckets, cursor, nullptr, nullptr, nullptr, (u32) kc_div_up(n_bytes, (u64) 32), t0,
+                                 reinterpret_cast<kc_ull *>(cells + 2), reinterpret_cast<u32 *>(cells + 3), nullptr, sp);
+        ++ex.launches;
+    }
+    kc_sig_counts_kernel<<<(unsigned) kc_div_up((u64) pl.n_buckets, 256), 256, 0, ex.stream>>>(cursor, pl.n_buckets, sp);
+    ++ex.launches;
+    KC_CUDA(cudaGetLastError());
+}
+
+// Owner side: the buckets of this rank (receive array + fill counts in its own heap, code words of the whole sequence) -> losers
+// cleared in every rank's flags.  cells: {kept (+=), -, -, status (low word)}.
+template <int L>
+void kc_sig_group_resolve(CudaExec &ex, const u64 *packed, int k, bool complements, u32 n_owned, const u32 *sub_cnt, const u64 *recv, int n_ranks, u32 sub_cap,
+                          const KsfFlagPeers &all_flags, u64 *cells, u64 n_bytes) {
+    typedef SigCfg<L> Cfg;
+    typedef SigKernels<L> KK;
+    if (n_owned == 0) return;
+    const typename KK::Dev &dv = KK::prepare();
+    const u32 fit = (u32) (dv.n_sm * (dv.occ > 0 ? dv.occ : 1));
+    const u32 grid = n_owned < fit ? n_owned : fit;
+    CudaExec::Scope sc(ex, KP_KS_RESOLVE, (u64) (n_bytes / n_ranks * (8 + 8 * Cfg::NW) / KC_SIG_WINDOWS_PER_RECORD));
+    kc_sig_resolve_kernel<L, true><<<grid, Cfg::THREADS, Cfg::smem(), ex.stream>>>(packed, k, complements ? 1 : 0, sub_cnt, recv, n_owned, all_flags,
+                                                                                 reinterpret_cast<kc_ull *>(cells), reinterpret_cast<u32 *>(cells + 3), (u32) n_ranks,
+                                                                                 sub_cap);
+    ++ex.launches;
+    KC_CUDA(cudaGetLastError());
 }
 
 #endif  // __CUDACC__
