@@ -304,8 +304,9 @@ u64 *kc_grp_fast_flags(KcGroup &G, CudaExec &ex, const u8 *seq, u64 n_bytes, int
 // ---- signature buckets (kmerset_sig.cuh) ---------------------------------------------------------------------------------------------
 // What travels is a RECORD (8 bytes for ~5 windows) instead of a 12-byte item per window, so the exchange over NVLink shrinks
 // ~7 x and the owner needs no further partition level: the bucket a record lands in is already the unit the resolve works on.
-//   scan      rank r scans its slice of the tiles: record -> sub-slot (bucket / n, r) of the bucket's owner (bucket % n), reserved
-//             with a LOCAL counter; code words + valid-window words of the slice -> every rank; then the fill counts -> the owners
+//   scan      rank r scans its slice of the tiles: record -> its own staging copy of the sub-slot (bucket / n, r) of the bucket's
+//             owner (bucket % n), reserved with a LOCAL counter; code words + valid-window words of the slice -> every rank
+//   ship      every staged sub-slot -> the owner's receive array as ONE contiguous run (a warp each), the fill count with it
 //   signal A / wait A
 //   resolve   the owner walks its buckets (the sub-slots of all senders back to back), clears a duplicate's bit in EVERY rank's flags
 //   signal B  (kept, M, overflow status) -> every rank / wait B
@@ -339,7 +340,8 @@ u64 *kc_grp_sig_flags(KcGroup &G, CudaExec &ex, const u8 *seq, u64 n_bytes, int 
     ex.fill_bytes(wait_status, 0, 8);
     const size_t mark = ex.arena->mark();
     u32 *cursor = ex.alloc<u32>(pl.n_buckets);
-    kc_sig_group_scan(ex, seq, n_bytes, k, pl, sp, cursor, G.cells_local);
+    u64 *staged = ex.alloc<u64>((u64) pl.n_buckets * sub_cap);
+    kc_sig_group_scan(ex, seq, n_bytes, k, pl, sp, cursor, staged, G.cells_local);
     const u32 sa = ++G.seq;
     kc_grp_signal(G, ex, sa);
     kc_grp_wait(G, ex, sa, wait_status);

@@ -200,8 +200,15 @@ def test_group_in_process_matches_single_gpu(ctx, n_ranks):
             got = grp.compute(seq, k=k, complements=compl, min_frequency=z)
             assert (got.n_kmers, got.length, got.n_nodes) == (want.n_kmers, want.length, want.n_nodes), (name, k, z)
             assert got.ms == want.ms, (name, k, z)
-        runs = grp.stat("fast_runs")
-        assert min(runs) >= 4 and len(set(runs)) == 1          # the genomes took the fixed-slot path on every rank
+        runs, sig = grp.stat("fast_runs"), grp.stat("sig_runs")
+        assert min(sig) >= 5 and len(set(sig)) == 1            # k >= 26 without -z: signature buckets on every rank
+        assert len(set(runs)) == 1 and min(grp.stat("sig_fallbacks")) == 0
+        # the same jobs through the fixed-slot construction
+        grp.set_option("sig_set", 0)
+        for name, k, compl, z in [("genome", 31, True, 1), ("repeats", 127, False, 1)]:
+            seq = inputs[name]
+            assert grp.compute(seq, k=k, complements=compl, min_frequency=z).ms == ctx.compute(seq, k=k, complements=compl, min_frequency=z).ms
+        assert min(grp.stat("fast_runs")) >= min(runs) + 2
     finally:
         grp.close()
 
@@ -213,12 +220,16 @@ def test_group_overflow_falls_back_on_every_rank(ctx):
     want = ctx.compute(seq, k=31)
     grp = kb.Group(_devices(3))
     try:
-        grp.set_option("fast_sigmas", 0)
         grp.set_option("fast_heuristics", 0)
+        grp.set_option("sig_load_pct", 400)        # signature buckets at four times their capacity: every rank falls back together
+        grp.set_option("fast_sigmas", 0)           # ... to fixed slots without slack, which overflow as well
         for _ in range(2):
             got = grp.compute(seq, k=31)
             assert got.ms == want.ms
-        assert min(grp.stat("fast_fallbacks")) >= 2
+        assert min(grp.stat("sig_fallbacks")) >= 2 and min(grp.stat("fast_fallbacks")) >= 2
+        grp.set_option("sig_load_pct", 0)
+        assert grp.compute(seq, k=31).ms == want.ms and min(grp.stat("sig_runs")) >= 1
+        grp.set_option("sig_set", 0)
         grp.set_option("fast_sigmas", 8)
         assert grp.compute(seq, k=31).ms == want.ms and min(grp.stat("fast_runs")) >= 1
     finally:
