@@ -304,22 +304,24 @@ u64 *kc_grp_fast_flags(KcGroup &G, CudaExec &ex, const u8 *seq, u64 n_bytes, int
 // ---- signature buckets (kmerset_sig.cuh) ---------------------------------------------------------------------------------------------
 // What travels is a RECORD (8 bytes for ~5 windows) instead of a 12-byte item per window, so the exchange over NVLink shrinks
 // ~7 x and the owner needs no further partition level: the bucket a record lands in is already the unit the resolve works on.
-//   scan      rank r scans its slice of the tiles: record -> its own staging copy of the sub-slot (bucket / n, r) of the bucket's
-//             owner (bucket % n), reserved with a LOCAL counter; code words + valid-window words of the slice -> every rank
-//   ship      every staged sub-slot -> the owner's receive array as ONE contiguous run (a warp each), the fill count with it
+//   scan      rank r scans its slice of the tiles: records staged per bucket in its own HBM (slots reserved with a LOCAL counter);
+//             code words + valid-window words of the slice -> every rank
+//   ship      the staged records, compacted into one dense stream per owner (bucket % n), -> the owner's receive array, and the
+//             offsets of the owner's buckets inside the stream -> its offset table: few, long, coalesced NVLink writes
 //   signal A / wait A
 //   resolve   the owner walks its buckets (the sub-slots of all senders back to back), clears a duplicate's bit in EVERY rank's flags
 //   signal B  (kept, M, overflow status) -> every rank / wait B
-// The receive array lives in the key receive region of the heap, the fill counts in the position receive region.
+// The receive array (one stream per sender) lives in the key receive region of the heap, the offset tables in the position receive region.
 // Returns nullptr when the plan does not apply to this job (too small, k < 26, heap regions too small).
 template <int L>
 u64 *kc_grp_sig_flags(KcGroup &G, CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, const SigTuning &tune) {
     const SigPlan pl = kc_sig_plan(n_bytes, k, tune);
     if (!pl.ok || G.n < 1 || pl.n_buckets >= (1u << 28)) return nullptr;
     const u32 sub_cap = kc_sig_sub_cap(tune, G.n);
-    const u32 own_max = kc_sig_owned_buckets(pl.n_buckets, G.n, 0);
-    if ((u64) own_max * (u64) G.n * sub_cap * 8 > G.lay.recv_items * 8 * (u64) G.lay.limbs) return nullptr;
-    if ((u64) own_max * (u64) G.n * 4 > G.lay.recv_items * 4) return nullptr;
+    const u32 nbr = kc_sig_owned_buckets(pl.n_buckets, G.n, 0);
+    const u32 region_cap = kc_sig_region_cap(n_bytes, G.n);
+    if ((u64) G.n * region_cap * 8 > G.lay.recv_items * 8 * (u64) G.lay.limbs) return nullptr;
+    if ((u64) G.n * ((u64) nbr + 1) * 4 > G.lay.recv_items * 4) return nullptr;
     u32 *flags = reinterpret_cast<u32 *>(G.heap + G.lay.off_flags);
     const u64 body_words = kc_div_up(n_bytes, (u64) 32);
     ex.fill_bytes(flags + body_words, 0, 8);  // the padding words nobody writes (kc_runs_load reads one past the end)
@@ -339,14 +341,12 @@ u64 *kc_grp_sig_flags(KcGroup &G, CudaExec &ex, const u8 *seq, u64 n_bytes, int 
     ex.fill_bytes(G.cells_local, 0, 32);
     ex.fill_bytes(wait_status, 0, 8);
     const size_t mark = ex.arena->mark();
-    u32 *cursor = ex.alloc<u32>(pl.n_buckets);
-    u64 *staged = ex.alloc<u64>((u64) pl.n_buckets * sub_cap);
-    kc_sig_group_scan(ex, seq, n_bytes, k, pl, sp, cursor, staged, G.cells_local);
+    kc_sig_group_scan(ex, seq, n_bytes, k, pl, sp, region_cap, G.cells_local);
     const u32 sa = ++G.seq;
     kc_grp_signal(G, ex, sa);
     kc_grp_wait(G, ex, sa, wait_status);
     kc_sig_group_resolve<L>(ex, reinterpret_cast<const u64 *>(G.heap + G.lay.off_packed), k, complements, kc_sig_owned_buckets(pl.n_buckets, G.n, G.rank),
-                            reinterpret_cast<const u32 *>(G.heap + G.lay.off_recv_p), reinterpret_cast<const u64 *>(G.heap + G.lay.off_recv_k), G.n, sub_cap,
+                            reinterpret_cast<const u32 *>(G.heap + G.lay.off_recv_p), nbr + 1, reinterpret_cast<const u64 *>(G.heap + G.lay.off_recv_k), G.n, region_cap,
                             G.all_flags(G.lay.off_flags), G.cells_local, n_bytes);
     ex.arena->release(mark);
     const u32 sb = ++G.seq;

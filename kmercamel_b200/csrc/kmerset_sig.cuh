@@ -264,21 +264,63 @@ __global__ void __launch_bounds__(256) kc_sig_scan_kernel(const u8 *__restrict__
     if (over) status[0] = 1;
 }
 
-// After the scan of a group rank: every sub-slot it filled (staged in its own HBM) -> the owner's receive array, one warp per
-// sub-slot, and the fill count with it (clamped: the scan dropped the rest).  A record written straight from the scan crossed
-// NVLink as an 8-byte store of its own — 4.9 M small packets per rank at two GPUs, 0.57 ms for 39 MB; from here a sub-slot
-// travels as one contiguous run.
-__global__ void __launch_bounds__(256) kc_sig_ship_kernel(const u32 *__restrict__ cursor, const u64 *__restrict__ staged, u32 n_buckets, const SigPeers sp) {
-    const u32 b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+// After the scan of a group rank, its records (staged per bucket in its own HBM) travel to the owners as DENSE STREAMS: one
+// stream per owner, the owner's buckets in ascending order, plus the offsets of the buckets inside the stream.
+//   kc_sig_om_counts_kernel   fill count of bucket lb * n + o at index o * nbr + lb ("owner-major"; nbr = buckets a rank owns at most)
+//   exclusive scan             -> offsets into one dense array (all owners back to back)
+//   kc_sig_compact_kernel     a warp per bucket: staged records -> their place in the dense array (local)
+//   kc_sig_ship_kernel        owner o's part of the dense array -> region `rank` of o's receive array, and the nbr + 1 offsets
+//                             relative to its start -> o's offset table, both as long coalesced runs
+// Measured before: every record as an 8-byte store of its own across NVLink, 0.57 ms for 39 MB at two GPUs; one run per
+// (bucket, sender) sub-slot, 0.65 ms at eight GPUs (1.6 M small packets per rank).  NVLink wants few, large writes.
+__global__ void __launch_bounds__(256) kc_sig_om_counts_kernel(const u32 *__restrict__ cursor, u32 n_buckets, u32 nbr, u32 n_ranks, u32 sub_cap, u32 *cnt_om) {
+    const u32 i = blockIdx.x * 256 + threadIdx.x;
+    if (i > n_ranks * nbr) return;
+    u32 c = 0;
+    if (i < n_ranks * nbr) {
+        const u32 o = i / nbr, lb = i - o * nbr;
+        const u64 b = (u64) lb * n_ranks + o;
+        if (b < n_buckets) {
+            c = cursor[b];
+            c = c < sub_cap ? c : sub_cap;
+        }
+    }
+    cnt_om[i] = c;  // entry n_ranks * nbr = 0: the scan leaves the total there
+}
+
+__global__ void __launch_bounds__(256) kc_sig_compact_kernel(const u32 *__restrict__ cursor, const u64 *__restrict__ staged, const u32 *__restrict__ off_om,
+                                                             u32 n_buckets, u32 nbr, u32 n_ranks, u32 sub_cap, u64 *__restrict__ dense, u64 dense_cap, u32 *status) {
+    const u32 i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    if (i >= n_ranks * nbr) return;
+    const u32 o = i / nbr, lb = i - o * nbr;
+    const u64 b = (u64) lb * n_ranks + o;
     if (b >= n_buckets) return;
-    const u32 lb = sp.n == 1 ? b : __umulhi(b, sp.magic), o = b - lb * (u32) sp.n;
     u32 c = cursor[b];
-    c = c < sp.sub_cap ? c : sp.sub_cap;
-    const u64 sub = (u64) lb * (u32) sp.n + (u32) sp.rank;
-    const u64 *src = staged + (u64) b * sp.sub_cap;
-    u64 *dst = sp.recs[o] + sub * sp.sub_cap;
-    for (u32 i = lane; i < c; i += 32) dst[i] = src[i];
-    if (lane == 0) sp.cnt[o][sub] = c;
+    c = c < sub_cap ? c : sub_cap;
+    const u64 *src = staged + b * sub_cap;
+    const u32 at = off_om[i];
+    if ((u64) at + c > dense_cap) {  // far more records than windows / 5 (the caller falls back)
+        if (lane == 0) status[0] = 1;
+        return;
+    }
+    u64 *dst = dense + at;
+    for (u32 j = lane; j < c; j += 32) dst[j] = src[j];
+}
+
+// grid = (chunks, n_ranks): block (c, o) copies every gridDim.x-th 256-record piece of owner o's stream
+__global__ void __launch_bounds__(256) kc_sig_ship_kernel(const u64 *__restrict__ dense, const u32 *__restrict__ off_om, u32 nbr, u32 region_cap, u32 *status,
+                                                          const SigPeers sp) {
+    const u32 o = blockIdx.y;
+    const u32 base = off_om[o * nbr], len = off_om[(o + 1) * nbr] - base;
+    u32 *od = sp.cnt[o] + (u64) (u32) sp.rank * (nbr + 1);
+    if (len > region_cap || status[0]) {  // the owner must still find a valid table: all buckets empty (the status word makes every rank fall back)
+        if (threadIdx.x == 0 && blockIdx.x == 0) status[0] = 1;
+        for (u32 j = blockIdx.x * 256 + threadIdx.x; j <= nbr; j += gridDim.x * 256) od[j] = 0;
+        return;
+    }
+    u64 *dst = sp.recs[o] + (u64) (u32) sp.rank * region_cap;
+    for (u32 j = blockIdx.x * 256 + threadIdx.x; j < len; j += gridDim.x * 256) dst[j] = dense[base + j];
+    for (u32 j = blockIdx.x * 256 + threadIdx.x; j <= nbr; j += gridDim.x * 256) od[j] = off_om[o * nbr + j] - base;
 }
 
 template <int L> struct SigCfg {
@@ -313,9 +355,10 @@ template <int L, bool MULTI>
 __global__ void __launch_bounds__(SigCfg<L>::THREADS, SigCfg<L>::MIN_CTAS) kc_sig_resolve_kernel(const u64 *__restrict__ packed, int k, int complements,
                                                                                                 const u32 *__restrict__ cursor, const u64 *__restrict__ recs,
                                                                                                 u32 n_buckets, KsfFlagPeers fl, kc_ull *n_unique, u32 *status,
-                                                                                                u32 n_senders, u32 sub_cap) {
-    // MULTI: `cursor` = the fill counts [bucket][sender] of this rank's buckets, `recs` = its receive array [bucket][sender][sub_cap];
-    //        the records of a bucket are its senders' sub-slots back to back (thread i takes the i-th of them)
+                                                                                                u32 n_senders, u32 sub_cap, u32 off_stride) {
+    // MULTI: `recs` = this rank's receive array: one dense stream per sender (sub_cap records each), `cursor` = the offsets of this
+    //        rank's buckets inside every stream ([sender][off_stride]); the records of a bucket are its pieces of all streams back to
+    //        back (thread i takes the i-th of them)
     typedef SigCfg<L> Cfg;
     constexpr u32 RC = KC_SIG_REC_CAP, T2N = Cfg::T2N;
     constexpr int NW = Cfg::NW, P = KC_SIG_PIECE;
@@ -338,18 +381,16 @@ __global__ void __launch_bounds__(SigCfg<L>::THREADS, SigCfg<L>::MIN_CTAS) kc_si
         rec = 0;
         if (bb >= n_buckets) return;
         if constexpr (MULTI) {
-            const u32 *c = cursor + (u64) bb * n_senders;
-            u32 pre = 0, snd = n_senders, idx = 0;
+            u32 pre = 0;
+            u64 at = ~0ULL;
             for (u32 sd = 0; sd < n_senders; ++sd) {
-                const u32 cs = c[sd];
-                if (threadIdx.x >= pre && threadIdx.x < pre + cs) {
-                    snd = sd;
-                    idx = threadIdx.x - pre;
-                }
+                const u32 *of = cursor + (u64) sd * off_stride + bb;
+                const u32 o0 = of[0], cs = of[1] - o0;
+                if (threadIdx.x >= pre && threadIdx.x < pre + cs) at = (u64) sd * sub_cap + o0 + (threadIdx.x - pre);
                 pre += cs;
             }
             nr = pre;
-            if (snd < n_senders) rec = recs[((u64) bb * n_senders + snd) * sub_cap + idx];
+            if (at != ~0ULL) rec = recs[at];
         } else {
             nr = cursor[bb];
             rec = recs[(u64) bb * RC + threadIdx.x];
@@ -583,7 +624,7 @@ bool kc_kmerset_build_sig(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool 
         // records read, two code words per record
         CudaExec::Scope sc(ex, KP_KS_RESOLVE, (u64) (n_bytes * (8 + 8 * Cfg::NW) / KC_SIG_WINDOWS_PER_RECORD));
         kc_sig_resolve_kernel<L, false><<<grid, Cfg::THREADS, Cfg::smem(), st>>>(packed, k, complements ? 1 : 0, cursor, recs, pl.n_buckets, kc_ksf_own_flags(flags),
-                                                                               reinterpret_cast<kc_ull *>(cells), status, 1u, KC_SIG_REC_CAP);
+                                                                               reinterpret_cast<kc_ull *>(cells), status, 1u, KC_SIG_REC_CAP, 0u);
         ++ex.launches;
         KC_CUDA(cudaGetLastError());
     }
@@ -601,34 +642,54 @@ inline u32 kc_sig_sub_cap(const SigTuning &t, int n_ranks) {
 }
 inline u32 kc_sig_owned_buckets(u32 n_buckets, int n_ranks, int rank) { return (n_buckets + (u32) n_ranks - 1u - (u32) rank) / (u32) n_ranks; }
 
-// The scan of this rank's slice of the tiles: records into the owners' sub-slots, code words and valid-window words to every rank,
-// then the fill counts of its sub-slots to the owners.  cells: {-, -, M of the slice (+=), status (low word)}.
-inline void kc_sig_group_scan(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, const SigPlan &pl, const SigPeers &sp, u32 *cursor /* [n_buckets] */,
-                              u64 *staged /* [n_buckets][sub_cap] */, u64 *cells) {
+// Records one (sender, owner) stream must hold: the pair's share of the slice's records + 15 % + slack.
+inline u32 kc_sig_region_cap(u64 n_bytes, int n_ranks) {
+    const double per_pair = (double) n_bytes / n_ranks / KC_SIG_WINDOWS_PER_RECORD / n_ranks;
+    return (u32) (((u64) (per_pair * 1.15) + 8192 + 31) / 32 * 32);
+}
+
+// The scan of this rank's slice of the tiles (records staged per bucket, code words and valid-window words to every rank), then the
+// staged records as dense streams to the owners.  cells: {-, -, M of the slice (+=), status (low word)}.
+inline void kc_sig_group_scan(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, const SigPlan &pl, const SigPeers &sp, u32 region_cap, u64 *cells) {
     constexpr u64 TILE = 256 * KC_EX_STRIP;
     const u32 tiles = (u32) kc_div_up(n_bytes, TILE);
     const u32 t0 = (u32) ((u64) tiles * (u32) sp.rank / (u32) sp.n), t1 = (u32) ((u64) tiles * ((u32) sp.rank + 1) / (u32) sp.n);
+    const u32 nbr = kc_sig_owned_buckets(pl.n_buckets, sp.n, 0), n_om = (u32) sp.n * nbr;
+    u32 *cursor = ex.alloc<u32>(pl.n_buckets);
+    u64 *staged = ex.alloc<u64>((u64) pl.n_buckets * sp.sub_cap);
+    u32 *off_om = ex.alloc<u32>((u64) n_om + 1);
+    u32 *status = reinterpret_cast<u32 *>(cells + 3);
     ex.fill_bytes(cursor, 0, (size_t) pl.n_buckets * 4);
+    u64 slice_bytes = 0;
     if (t1 > t0) {
-        const u64 part_bytes = std::min<u64>(n_bytes, (u64) t1 * TILE) - (u64) t0 * TILE;
-        CudaExec::Scope sc(ex, KP_KS_SCATTER0, part_bytes + (part_bytes / 4 + part_bytes / 8) * (u64) sp.n + (u64) (part_bytes * 8 / KC_SIG_WINDOWS_PER_RECORD));
+        slice_bytes = std::min<u64>(n_bytes, (u64) t1 * TILE) - (u64) t0 * TILE;
+        CudaExec::Scope sc(ex, KP_KS_SCATTER0, slice_bytes + (slice_bytes / 4 + slice_bytes / 8) * (u64) sp.n + (u64) (slice_bytes * 8 / KC_SIG_WINDOWS_PER_RECORD));
         kc_sig_scan_launch<true>(pl.m, t1 - t0, ex.stream, seq, n_bytes, k, pl.a, pl.n_buckets, cursor, staged, nullptr, nullptr, (u32) kc_div_up(n_bytes, (u64) 32), t0,
-                                 reinterpret_cast<kc_ull *>(cells + 2), reinterpret_cast<u32 *>(cells + 3), nullptr, sp);
+                                 reinterpret_cast<kc_ull *>(cells + 2), status, nullptr, sp);
         ++ex.launches;
     }
+    kc_sig_om_counts_kernel<<<(unsigned) kc_div_up((u64) n_om + 1, 256), 256, 0, ex.stream>>>(cursor, pl.n_buckets, nbr, (u32) sp.n, sp.sub_cap, off_om);
+    ++ex.launches;
+    KC_CUDA(cudaGetLastError());
+    ex.exclusive_scan_nosync(off_om, off_om, (u64) n_om + 1);
+    const u64 dense_cap = (u64) (slice_bytes / KC_SIG_WINDOWS_PER_RECORD * 1.3) + (u64) sp.n * 8192 + 65536;
+    u64 *dense = ex.alloc<u64>(dense_cap);
     {
-        CudaExec::Scope sc(ex, KP_SORT_MISC, (u64) (n_bytes / (u32) sp.n * 16 / KC_SIG_WINDOWS_PER_RECORD));
-        kc_sig_ship_kernel<<<(unsigned) kc_div_up((u64) pl.n_buckets, 8), 256, 0, ex.stream>>>(cursor, staged, pl.n_buckets, sp);
-        ++ex.launches;
+        const u64 rec_bytes = (u64) (slice_bytes * 8 / KC_SIG_WINDOWS_PER_RECORD);
+        CudaExec::Scope sc(ex, KP_SORT_MISC, 4 * rec_bytes);  // compact: read + write; ship: read + write
+        kc_sig_compact_kernel<<<(unsigned) kc_div_up((u64) n_om, 8), 256, 0, ex.stream>>>(cursor, staged, off_om, pl.n_buckets, nbr, (u32) sp.n, sp.sub_cap, dense, dense_cap,
+                                                                                             status);
+        kc_sig_ship_kernel<<<dim3(128, (unsigned) sp.n), 256, 0, ex.stream>>>(dense, off_om, nbr, region_cap, status, sp);
+        ex.launches += 2;
         KC_CUDA(cudaGetLastError());
     }
 }
 
-// Owner side: the buckets of this rank (receive array + fill counts in its own heap, code words of the whole sequence) -> losers
-// cleared in every rank's flags.  cells: {kept (+=), -, -, status (low word)}.
+// Owner side: the buckets of this rank (the senders' streams + offset tables in its own heap, code words of the whole sequence) ->
+// losers cleared in every rank's flags.  cells: {kept (+=), -, -, status (low word)}.
 template <int L>
-void kc_sig_group_resolve(CudaExec &ex, const u64 *packed, int k, bool complements, u32 n_owned, const u32 *sub_cnt, const u64 *recv, int n_ranks, u32 sub_cap,
-                          const KsfFlagPeers &all_flags, u64 *cells, u64 n_bytes) {
+void kc_sig_group_resolve(CudaExec &ex, const u64 *packed, int k, bool complements, u32 n_owned, const u32 *offsets, u32 off_stride, const u64 *recv, int n_ranks,
+                          u32 region_cap, const KsfFlagPeers &all_flags, u64 *cells, u64 n_bytes) {
     typedef SigCfg<L> Cfg;
     typedef SigKernels<L> KK;
     if (n_owned == 0) return;
@@ -636,9 +697,9 @@ void kc_sig_group_resolve(CudaExec &ex, const u64 *packed, int k, bool complemen
     const u32 fit = (u32) (dv.n_sm * (dv.occ > 0 ? dv.occ : 1));
     const u32 grid = n_owned < fit ? n_owned : fit;
     CudaExec::Scope sc(ex, KP_KS_RESOLVE, (u64) (n_bytes / n_ranks * (8 + 8 * Cfg::NW) / KC_SIG_WINDOWS_PER_RECORD));
-    kc_sig_resolve_kernel<L, true><<<grid, Cfg::THREADS, Cfg::smem(), ex.stream>>>(packed, k, complements ? 1 : 0, sub_cnt, recv, n_owned, all_flags,
+    kc_sig_resolve_kernel<L, true><<<grid, Cfg::THREADS, Cfg::smem(), ex.stream>>>(packed, k, complements ? 1 : 0, offsets, recv, n_owned, all_flags,
                                                                                  reinterpret_cast<kc_ull *>(cells), reinterpret_cast<u32 *>(cells + 3), (u32) n_ranks,
-                                                                                 sub_cap);
+                                                                                 region_cap, off_stride);
     ++ex.launches;
     KC_CUDA(cudaGetLastError());
 }
