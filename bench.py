@@ -176,13 +176,17 @@ def workload_config(world):
     return {"workload": "BASELINE configs[1]: synthetic 50 Mbp random multi-FASTA (50 x 1 Mbp, default_rng(12345)), "
                         "k=31 canonical, min-one mask, u64 word path" + (f"; x{world}: one genome of {world} x 50 Mbp" if world > 1 else ""),
             "k": K, "bases_per_gpu": N_RECORDS * RECORD_LEN, "records_per_gpu": N_RECORDS,
-            "sharding": ("k-mer set construction sharded by hash range: the level-0 scatter kernel stores (k-mer, position) items "
-                         "straight into fixed sub-slots of the owner GPU's heap over NVLink (CUDA IPC peer pointers), ranks synchronise "
-                         "through device-side signal words (no collective and no host round trip on the data path), duplicates clear "
-                         "their first-occurrence bit on every rank; every rank repeats the greedy merge and emits its own slice of the "
-                         "superstring") if world > 1 else "single GPU",
-            "l2": "no explicit flush: each step streams ~2.4 GB of intermediates (600 MB written by level 0, read and rewritten by "
-                  "level 1, read by the resolve: >> 126 MB L2), so the 50 MB input and every kernel's operands are cold when read"}
+            "sharding": ("k-mer set construction sharded by hash range of the k-mer SIGNATURE (kmerset_sig.cuh): every rank scans its slice, "
+                         "stages super-k-mer records (8 bytes per ~5 windows) per bucket and ships them to the bucket's owner (bucket % N) "
+                         "as one dense stream per owner over NVLink (CUDA IPC peer pointers); 2-bit code words and valid-window words of "
+                         "the slice go to every rank; ranks synchronise through device-side signal words (no collective and no host round "
+                         "trip on the data path), duplicates clear their first-occurrence bit on every rank; every rank repeats the greedy "
+                         "merge and emits its own slice of the superstring") if world > 1 else "single GPU",
+            "l2": ("inputs larger than L2: the timed steps rotate over 4 device copies of the 50 MB sequence (200 MB) and every step streams "
+                   "another ~200 MB of intermediates and output (record rows 141 MB, code words, flags, 50 MB superstring), so a step's input "
+                   "was last touched > 500 MB of traffic ago (L2 = 126 MB); no explicit flush") if world == 1 else
+                  (f"inputs larger than L2: the job's sequence is {world} x 50 MB on every GPU, and every step streams the staged / shipped / "
+                   "gathered records (~3 x 78 MB per GPU), code words, flags and its superstring slice on top; no explicit flush")}
 
 
 def run_sharded_arm(args, rank, local_rank, world, ctx, part):
@@ -307,9 +311,16 @@ def run_sharded_arm(args, rank, local_rank, world, ctx, part):
     kernels = {n: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                    "gbs": (v["bytes"] / (v["ms"] / 1000.0) / 1e9) if v["ms"] > 0 and v["bytes"] else None}
                for n, v in prof.items() if v["launches"]}
-    item_bytes = 12
-    sent = r.n_occurrences / world * (world - 1) / world            # items a rank stores into OTHER ranks' heaps per job
-    s0 = kernels.get("ks_scatter0", {}).get("ms_per_step")
+    sig_runs, sig_fb = ctx.stat("sig_runs"), ctx.stat("sig_fallbacks")
+    sig_path = sig_runs > 0 and sig_fb == 0
+    # what a rank stores into OTHER ranks' heaps per job: signature path = its records (8 bytes per ~5.16 windows) to the owners, plus the
+    # 2-bit code words (1/4 byte per base) and flag words (1/8) of its slice to every other rank; fixed-slot path = 12-byte items
+    part_windows = r.n_occurrences / world
+    if sig_path:
+        sent_bytes = part_windows / 5.16 * 8 * (world - 1) / world + part_windows * (0.25 + 0.125) * (world - 1)
+    else:
+        sent_bytes = part_windows * (world - 1) / world * 12
+    s0 = (kernels.get("ks_scatter0", {}).get("ms_per_step") or 0) + ((kernels.get("sort_misc", {}).get("ms_per_step") or 0) if sig_path else 0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -324,10 +335,12 @@ def run_sharded_arm(args, rank, local_rank, world, ctx, part):
         "roofline": {"bound": "hbm", "kernel": dname + " (rank 0)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": None, "peak_source": peak_src, "share_of_step": d["ms"] / dev_ms},
         "cpu_baseline": None, "kernel_classes_rank0": kernels,
-        "exchange": {"items_stored_to_peers_per_rank_per_step": int(sent), "nvlink_store_bytes_per_rank_per_step": int(sent * item_bytes),
-                     "nvlink_gbs_during_level0_rank0": (sent * item_bytes / (s0 / 1000.0) / 1e9) if s0 else None,
+        "exchange": {"construction": "signature buckets: records + code words + flag words" if sig_path else "fixed slots: (k-mer, position) items",
+                     "nvlink_store_bytes_per_rank_per_step": int(sent_bytes),
+                     "nvlink_gbs_during_scan_and_ship_rank0": (sent_bytes / (s0 / 1000.0) / 1e9) if s0 else None,
                      "nvlink_peak_gbs_per_direction": 900.0,
-                     "collectives_on_the_data_path": 0, "fast_runs_rank0": fast_runs, "fast_fallbacks_rank0": fallbacks},
+                     "collectives_on_the_data_path": 0, "sig_runs_rank0": sig_runs, "sig_fallbacks_rank0": sig_fb,
+                     "fast_runs_rank0": fast_runs, "fast_fallbacks_rank0": fallbacks},
         "result": {"distinct_kmers": int(n_kmers), "superstring_length": int(r.length), "nodes": int(r.n_nodes)},
     }
     _REAL_STDOUT.write(json.dumps(line) + "\n")
@@ -396,8 +409,9 @@ def main():
 
     # ---- device-timed arm (input resident in HBM) ---------------------------------------------------------------
     res = None
-    for _ in range(max(args.warmup, 3)):
-        res = ctx.compute_device(d_seq.data_ptr(), d_seq.numel(), k=K)
+    d_seqs = [d_seq] + [d_seq.clone() for _ in range(3)]   # rotated, so that a step never finds its input in L2 (see config.l2)
+    for i in range(max(args.warmup, 3)):
+        res = ctx.compute_device(d_seqs[i % 4].data_ptr(), d_seq.numel(), k=K)
     ctx.profile_enable(True)
     ctx.profile_reset()
     sampler = ClockSampler(local_rank)
@@ -406,8 +420,9 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     launches = 0
-    for _ in range(args.steps):
-        res = ctx.compute_device(d_seq.data_ptr(), d_seq.numel(), k=K)
+    sig_runs0 = ctx.stat("sig_runs")
+    for i in range(args.steps):
+        res = ctx.compute_device(d_seqs[i % 4].data_ptr(), d_seq.numel(), k=K)
         launches += res.n_launches
     e1.record(stream)
     barrier()
@@ -415,6 +430,8 @@ def main():
     prof = ctx.profile()
     stage_ms = res.times_ms
     ctx.profile_enable(False)
+    sig_path = ctx.stat("sig_runs") - sig_runs0 == args.steps   # every timed step took the signature-bucket construction
+    del d_seqs
 
     # ---- end-to-end arm (pinned host buffers in, host superstring out) ----------------------------------------
     for _ in range(2):
@@ -449,24 +466,46 @@ def main():
         # dominant kernel class = largest share of device time in the timed region
         dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
         dname, d = dom
-        ach = (d["bytes"] / max(d["launches"], 1)) / (d["ms"] / max(d["launches"], 1) / 1000.0) / 1e9 if d["ms"] > 0 else 0.0
-        traffic = None
+        B, M, U, W = float(seq.size), float(res.n_occurrences), float(n_kmers), 8.0
+        # ALGORITHMIC bytes per launch = SURVEY.md 8(d)'s per-unit figure x the units one launch processes.  The two kernels of the
+        # signature-bucket construction do the work of SURVEY's pack + emit_canonical (scan) and sort / dedup / count (resolve):
+        #   scan:    F + B/4 + B/8  +  B/4 + B/8 + M W        resolve:  M W + U (W + 1)   (all radix passes charged as ONE read + ONE write)
+        # Other kernel classes keep the bytes the library declares at launch (inputs read once + outputs written once).
+        alg_8d = {"ks_scatter0": (B + B / 4 + B / 8) + (B / 4 + B / 8 + M * W), "ks_resolve": M * W + U * (W + 1)} if sig_path else {}
+        def alg_bytes(name, v):
+            return alg_8d.get(name, v["bytes"] / max(v["launches"], 1))
+        ach = alg_bytes(dname, d) / (d["ms"] / max(d["launches"], 1) / 1000.0) / 1e9 if d["ms"] > 0 else 0.0
+        traffic, tj = None, {}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(dname)
+                tj = json.load(open(tpath))
+                tj = tj.get("signature_buckets", {}) if sig_path else tj
+                traffic = tj.get(dname)
             except Exception:
-                traffic = None
-        roofline = {"bound": "hbm", "kernel": dname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                traffic, tj = None, {}
+        roofline = {"bound": "hbm", "kernel": dname + (" = kc_sig_resolve_kernel" if sig_path and dname == "ks_resolve" else
+                                                        " = kc_sig_scan_kernel" if sig_path and dname == "ks_scatter0" else ""),
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "peak_source": peak_src,
                     "launches_per_step": d["launches"] / args.steps, "ms_per_launch": d["ms"] / max(d["launches"], 1),
-                    "algorithmic_bytes_per_launch": d["bytes"] / max(d["launches"], 1),
-                    "share_of_step": d["ms"] / dev_ms}
+                    "algorithmic_bytes_per_launch": alg_bytes(dname, d),
+                    "algorithmic_bytes_are": "SURVEY 8(d): sort/dedup/count = M W + U (W + 1) per launch" if sig_path and dname == "ks_resolve" else
+                                             "SURVEY 8(d): pack + emit_canonical = F + B/2 + B/4 + M W per launch" if sig_path and dname == "ks_scatter0" else
+                                             "inputs read once + outputs written once, declared by the library at launch",
+                    "share_of_step": d["ms"] / dev_ms,
+                    "limiter": ("instruction issue, not HBM: the kernel re-creates the k-mers from 2-bit code words instead of moving them "
+                                "(ncu profiles/r02_sig_ncu.md: DRAM 5-9 % of peak, issue slots 50-61 % busy); `traffic` = measured DRAM bytes per launch")
+                               if sig_path else None}
+        if sig_path:
+            roofline["per_kernel_8d"] = {c: {"algorithmic_bytes": alg_8d[c], "ms": prof[c]["ms"] / max(prof[c]["launches"], 1),
+                                             "frac": alg_8d[c] / (prof[c]["ms"] / max(prof[c]["launches"], 1) / 1000.0) / 1e9 / peak,
+                                             "dram_bytes_ncu": tj.get(c)}
+                                         for c in ("ks_scatter0", "ks_resolve") if c in prof and prof[c]["ms"] > 0}
         # SURVEY.md §8(d) accounting next to the per-pass one: the k-mer set stage (pack + emit_canonical + sort / dedup / count) is charged
         # F + B/4 + B/8  +  B/4 + B/8 + M W  +  M W + U (W + 1) bytes — every radix pass together as ONE read + ONE write — over the time of
         # the three kernels that do that work here (level-0 partition, level-1 partition, leaf resolve); and the whole step is charged
         # SURVEY's ~60 B per distinct k-mer.  The per-kernel fractions by measured DRAM bytes come from the ncu capture (profiles/traffic.json).
-        B, M, U, W = float(seq.size), float(res.n_occurrences), float(n_kmers), 8.0
         set_ms = sum(prof[c]["ms"] for c in ("ks_scatter0", "sort_scatter", "ks_resolve") if c in prof) / args.steps
         bytes_8d = (B + B / 4 + B / 8) + (B / 4 + B / 8 + M * W) + (M * W + U * (W + 1))
         roofline["stage_8d"] = {"stage": "k-mer set (pack + emit_canonical + sort/dedup/count of SURVEY 8d = ks_scatter0 + sort_scatter + ks_resolve here)",
@@ -474,7 +513,6 @@ def main():
                                 "frac": bytes_8d / (set_ms / 1000.0) / 1e9 / peak if set_ms else None}
         roofline["step_8d"] = {"algorithmic_bytes": 60.0 * U, "ms": dev_ms / args.steps, "frac": 60.0 * U / (dev_ms / args.steps / 1000.0) / 1e9 / peak}
         try:
-            tj = json.load(open(tpath))
             roofline["frac_by_dram_bytes"] = {c: (tj[c] / (prof[c]["ms"] / max(prof[c]["launches"], 1) / 1000.0) / 1e9 / peak)
                                               for c in ("ks_scatter0", "sort_scatter", "ks_resolve") if c in tj and c in prof and prof[c]["ms"] > 0}
         except Exception:
@@ -496,7 +534,9 @@ def main():
                     "ms_per_step": e2e_ms / args.steps, "timer": "host perf_counter around kc_compute (stream-synchronous), max over ranks"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "stage_ms_last_step": stage_ms, "kernel_classes": kernels,
-            "result": {"distinct_kmers_per_gpu": int(n_kmers), "superstring_length": int(res.length), "nodes": int(res.n_nodes)},
+            "result": {"distinct_kmers_per_gpu": int(n_kmers), "superstring_length": int(res.length), "nodes": int(res.n_nodes),
+                       "kmer_set_construction": "signature buckets (kmerset_sig.cuh)" if sig_path else "fixed slots / exact (kmerset_fast.cuh, kmerset.cuh)",
+                       "sig_fallbacks": int(ctx.stat("sig_fallbacks"))},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
