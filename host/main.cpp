@@ -370,6 +370,12 @@ static int camel_compute(int argc, char **argv, bool lower_bound) {
     std::snprintf(times, sizeof(times), "GPU stages [ms]: extract %.3f, count %.3f, path %.3f, emit %.3f, total %.3f; %llu kernels",
                   out.t.extract_ms, out.t.count_ms, out.t.path_ms, out.t.emit_ms, out.t.total_ms, (unsigned long long) out.n_launches);
     write_log(times);
+    {   // which k-mer set construction ran (kmerset_sig.cuh: signature buckets; kmerset_fast.cuh / kmerset.cuh otherwise)
+        uint64_t sig_runs = 0, sig_fb = 0;
+        kc_ctx *c0 = multi ? kc_group_ctx(group, 0) : ctx;
+        if (c0 && kc_get_stat(c0, "sig_runs", &sig_runs) == KC_OK && kc_get_stat(c0, "sig_fallbacks", &sig_fb) == KC_OK && !assume_simplitigs)
+            write_log(std::string("k-mer set construction: ") + (sig_runs ? "signature buckets (super-k-mer records)" : (sig_fb ? "signature buckets overflowed, fixed slots / exact" : "fixed slots / exact")) + ".");
+    }
     if (multi) write_log("k-mer set construction sharded by hash range over " + std::to_string(devices.size()) + " GPUs.");
     bool verified_ok = true;
     if (verify) {  // what the reference's verify.py checks: the superstring represents exactly the k-mer set of the input

@@ -317,7 +317,7 @@ template <int L>
 u64 *kc_grp_sig_flags(KcGroup &G, CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool complements, const SigTuning &tune) {
     const SigPlan pl = kc_sig_plan(n_bytes, k, tune);
     if (!pl.ok || G.n < 1 || pl.n_buckets >= (1u << 28)) return nullptr;
-    const u32 sub_cap = kc_sig_sub_cap(tune, G.n);
+    const u32 sub_cap = kc_sig_sub_cap(pl, G.n);
     const u32 nbr = kc_sig_owned_buckets(pl.n_buckets, G.n, 0);
     const u32 region_cap = kc_sig_region_cap(n_bytes, G.n);
     if ((u64) G.n * region_cap * 8 > G.lay.recv_items * 8 * (u64) G.lay.limbs) return nullptr;

@@ -1527,7 +1527,7 @@ int kc_set_option(kc_ctx *ctx, const char *name, int value) {
         return KC_OK;
     }
     if (std::strcmp(name, "sig_load_pct") == 0 && value >= 0 && value <= 400) {  // > 100 forces overflows (tests)
-        ctx->sig.load_pct = value ? (u32) value : SigTuning().load_pct;  // 0 = the default
+        ctx->sig.load_pct = (u32) value;  // 0 = planned from the input size
         return KC_OK;
     }
     if (std::strcmp(name, "sig_min_items") == 0 && value >= 0) {

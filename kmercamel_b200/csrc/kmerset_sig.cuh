@@ -41,8 +41,7 @@
 
 struct SigTuning {
     bool enabled = true;
-    uint32_t load_pct = 55;            // mean records per bucket, in percent of the bucket capacity: 141 of 256.  Records arrive in
-                                       // clumps (sigma ~ 1.5 sqrt(mean) ~ 18), the first buckets get ~6 % more: mean + 6 sigma = 256
+    uint32_t load_pct = 0;             // mean records per bucket in percent of the bucket capacity; 0 = planned from the input size (kc_sig_plan)
     uint64_t min_items = 1u << 16;     // smaller inputs: nothing to gain
 };
 
@@ -57,6 +56,8 @@ struct SigPlan {
     int m = 0;          // M-mer length
     int a = 0;          // the central range of a window ending at e: M-mers ending at e - a - (W - 1) .. e - a
     u32 n_buckets = 0;
+    double mean_records = 0;  // per bucket
+    double clump = 1.5;       // sigma of a bucket's record count = clump * sqrt(mean)
 };
 
 inline SigPlan kc_sig_plan(u64 n_bytes, int k, const SigTuning &t) {
@@ -71,7 +72,22 @@ inline SigPlan kc_sig_plan(u64 n_bytes, int k, const SigTuning &t) {
         }
     }
     if (!p.m) return p;
-    const double mean_windows = KC_SIG_REC_CAP * (t.load_pct / 100.0) * KC_SIG_WINDOWS_PER_RECORD;
+    // How full may a bucket be on average?  Its record count spreads like a clumped Poisson variable: runs of windows are cut into
+    // several records (factor ~1.5 on sigma, measured), and every further occurrence of a signature M-mer in the input drops its
+    // records into the same bucket — chance repeats alone are 2 n / 4^M per M-mer (1.4 at 3.1 Gbp with M = 16: the first north-star run
+    // overflowed with the fixed 55 % load that fits 50-500 Mbp).  The fullest of nb buckets sits ~sqrt(2 ln nb) sigma above the mean, the
+    // first buckets get ~6 % more than the mean: solve 1.06 m + z * clump * sqrt(m) = 256 for m.
+    const double mu = 2.0 * (double) n_bytes / std::pow(4.0, (double) p.m);
+    p.clump = 1.5 * std::sqrt(1.0 + mu);
+    const double z = std::sqrt(2.0 * std::log((double) n_bytes / 500.0 + 16.0)) + 2.0;  // + 2: repeats of real sequence on top of the chance ones
+    const double zc = z * p.clump;
+    const double x = (-zc + std::sqrt(zc * zc + 4.0 * 1.06 * KC_SIG_REC_CAP)) / (2.0 * 1.06);
+    p.mean_records = t.load_pct ? KC_SIG_REC_CAP * (t.load_pct / 100.0) : x * x;
+    if (p.mean_records < 32.0) {  // far too clumpy for buckets of 256 records (short M-mers on a large input)
+        p.m = 0;
+        return p;
+    }
+    const double mean_windows = p.mean_records * KC_SIG_WINDOWS_PER_RECORD;
     const u64 nb = (u64) ((double) n_bytes / (mean_windows > 1.0 ? mean_windows : 1.0)) + 1;
     if (nb >= (1u << 27)) return p;
     p.n_buckets = (u32) (nb < 64 ? 64 : nb);
@@ -652,9 +668,9 @@ bool kc_kmerset_build_sig(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool 
 
 // ---- multi-GPU (group.cuh) -----------------------------------------------------------------------------------------------------
 // Records a (bucket, sender) sub-slot must hold: the bucket's mean share + 6 sigma (records arrive in clumps: sigma ~ 1.5 sqrt(mean)).
-inline u32 kc_sig_sub_cap(const SigTuning &t, int n_ranks) {
-    const double mean = KC_SIG_REC_CAP * (t.load_pct / 100.0) / n_ranks;
-    u32 cap = (u32) (mean * 1.06 + 6.0 * 1.5 * std::sqrt(mean) + 8.0);
+inline u32 kc_sig_sub_cap(const SigPlan &pl, int n_ranks) {
+    const double mean = pl.mean_records / n_ranks;
+    u32 cap = (u32) (mean * 1.06 + 7.0 * pl.clump * std::sqrt(mean) + 8.0);
     cap = (cap + 31) / 32 * 32;
     return cap < KC_SIG_REC_CAP ? cap : KC_SIG_REC_CAP;
 }
