@@ -218,14 +218,18 @@ uint64_t kc_total_launches(const kc_ctx *ctx);
 
 /* Tuning / test knobs.  "sparse_switch" (default 1): hand the individual k-mers to the greedy when 5 * simplitigs >= k-mers.
  * "small_engine" (default 1): run the tail of the overlap levels in the single-CTA kernel.
- * "fast_set" (default 1): try the histogram-free k-mer set construction first (from-FASTA compute without -M);
+ * "sig_set" (default 1): try the signature-bucket k-mer set construction first (kmerset_sig.cuh: from-FASTA compute
+ * with k >= 26, without -z and -M); "sig_load_pct" (0 = planned from the input size) and "sig_min_items": its plan
+ * parameters, exposed so that tests reach the overflow fallback and small inputs.
+ * "fast_set" (default 1): then try the histogram-free fixed-slot construction (from-FASTA compute without -M);
  * "fast_leaf_target", "fast_sigmas", "fast_min_items": its plan parameters, exposed so that tests reach the
  * multi-level plan and the overflow fallback with small inputs; "fast_heuristics" (default 1): skip the attempt when
  * duplicates are expected (-z > 1, or the previous call on an input of similar size overflowed).
  * "fast_max_ctas": upper bound of the level >= 1 scatter grid.
  * Results never depend on these options. */
 int kc_set_option(kc_ctx *ctx, const char *name, int value);
-/* Counters since kc_init: "fast_runs", "fast_fallbacks", "total_launches"; current value of the option "fast_max_ctas". */
+/* Counters since kc_init: "sig_runs", "sig_fallbacks", "fast_runs", "fast_fallbacks", "total_launches"; current value of the
+ * option "fast_max_ctas". */
 int kc_get_stat(const kc_ctx *ctx, const char *name, uint64_t *value);
 
 int kc_limbs_for_k(int k);
