@@ -416,17 +416,31 @@ template <class Exec, int L> struct Engine {
             a.strict = strict;
             a.out = ex.template alloc<u32>(8 + 128 + 8);
             ex.fill_bytes(a.out, 0, (8 + 128 + 8) * 4);
+            u32 *lvl_mask = ex.template alloc<u32>(4);
+            ex.fill_bytes(lvl_mask, 0, 16);
+            a.lvl_mask_in = lvl_mask;
+            const int mask_smem = (int) (SmallCfg<L>::T * sizeof(KWord<L + 1>));
             static KcDevOnce once;  // function attributes are per device
             once.run([&](int) {
                 KC_CUDA(cudaFuncSetAttribute(kc_small_engine_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int) SmallCfg<L>::SMEM));
+                KC_CUDA(cudaFuncSetAttribute(kc_small_level_mask_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, mask_smem));
             });
+            {   // which levels can accept an edge at all: one CTA per two levels (the engine kernel used to do this alone)
+                typename Exec::Scope sc(ex, KP_SMALL_ENGINE, 0);
+                const u32 per_cta = kc_small_mask_levels_per_cta<L>((u32) n_s, (u32) n_p);
+                kc_small_level_mask_kernel<L><<<(unsigned) kc_div_up((u64) d + 1, per_cta), 256, mask_smem, ex.stream>>>(nv, live_s, live_p, (u32) n_s, (u32) n_p, d,
+                                                                                                                      lvl_mask);
+                ++ex.launches;
+            }
             {
                 typename Exec::Scope sc(ex, KP_SMALL_ENGINE, 0);
                 // (measured: one warp instead of 256 threads makes the kernel 1.7x slower on configs[1] — the levels are
                 // bound by the work per phase, not by the block barriers)
-                // 512 threads once the tuple phases (level mask, bitonic sort) have more than two items per thread to share out
-                const unsigned small_threads = small_threads_opt ? (unsigned) small_threads_opt : (n_s + n_p > 512 ? 512u : 256u);
+                // 512 threads once the sort has work for them: two threads per tuple in the rank sort (129..256 tuples), more than two
+                // items per thread in the bitonic network (> 512 tuples)
+                const u64 nt0 = n_s + n_p;
+                const unsigned small_threads = small_threads_opt ? (unsigned) small_threads_opt : ((nt0 > 128 && nt0 <= 256) || nt0 > 512 ? 512u : 256u);
                 kc_small_engine_kernel<L><<<1, small_threads, SmallCfg<L>::SMEM, ex.stream>>>(a);
             }
             ++ex.launches;

@@ -33,7 +33,94 @@ template <int L> struct SmallEngineArgs {
     int d_start;
     bool strict;
     u32 *out;  // [0] error, [1] levels run, [2] groups, [3] edges, [4] ban rounds, [5] bans, [8 + d] clocks spent in level d (KC_TRACE)
+    const u32 *lvl_mask_in;  // [4] bit d: some (suffix, prefix) pair of the initial free ends agrees on d bases (kc_small_level_mask_kernel)
 };
+
+// Levels of one CTA of kc_small_level_mask_kernel (host and device must agree): as many hash tables as fit next to the parked k-mers,
+// at most KC_SMALL_MASK_LEVELS.  Few levels per CTA = many CTAs: the join of one level is independent of every other level.
+static const u32 KC_SMALL_MASK_LEVELS = 2;
+template <int L> KC_HD u32 kc_small_mask_table_slots(u32 n_p) {
+    u32 H2 = 64;
+    while (H2 < 2 * n_p) H2 <<= 1;
+    return H2;
+}
+template <int L> KC_HD u32 kc_small_mask_levels_per_cta(u32 n_s, u32 n_p) {
+    const u32 avail = (u32) ((SmallCfg<L>::T * sizeof(KWord<L + 1>) - (size_t) (n_s + n_p) * sizeof(KWord<L>)) / 4);
+    u32 G = avail / kc_small_mask_table_slots<L>(n_p);
+    if (G > KC_SMALL_MASK_LEVELS) G = KC_SMALL_MASK_LEVELS;
+    return G < 1 ? 1 : G;
+}
+
+// Find out ONCE at which levels any free suffix can meet any free prefix.  The live sets only shrink, so a level whose bit is clear
+// can never accept an edge and the engine skips it.  An EXACT hash join per level: the prefix keys of level d go into an
+// open-addressing table of end indices (keys are compared through the parked k-mers, so there are no false positives — a bit filter
+// lit up at every level once ~800 x 800 ends were alive, and all 31 levels of a 400-record genome ran at ~40 us each although only 11
+// could accept an edge); the suffix keys probe it.  This used to be the first phase of the single-CTA engine kernel: 17 % of its
+// clocks at 100 ends, 32 % at 800 (all (level, end) pairs through one CTA).  The levels are independent, so they now spread over
+// (d_start + 1) / levels-per-CTA CTAs that run at the same time.
+template <int L>
+__global__ void __launch_bounds__(256) kc_small_level_mask_kernel(NodeView<L> v, const u32 *__restrict__ ls, const u32 *__restrict__ lp, u32 n_s, u32 n_p,
+                                                                  int d_start, u32 *mask_out /* [4], zeroed */) {
+    extern __shared__ __align__(16) unsigned char kc_smem_raw[];
+    __shared__ u32 s_hits;
+    const u32 tid = threadIdx.x, NT = blockDim.x;
+    KWord<L> *pk = reinterpret_cast<KWord<L> *>(kc_smem_raw), *sk = pk + n_p;
+    u32 *tab = reinterpret_cast<u32 *>(sk + n_s);
+    const u32 H2 = kc_small_mask_table_slots<L>(n_p);
+    const u32 G = kc_small_mask_levels_per_cta<L>(n_s, n_p);
+    const int d_hi = d_start - (int) (blockIdx.x * G);
+    if (d_hi < 0) return;
+    const u32 g = (u32) (d_hi + 1) < G ? (u32) (d_hi + 1) : G;  // levels d_hi, d_hi - 1, ..., d_hi - g + 1
+    for (u32 i = tid; i < n_p; i += NT) pk[i] = v.first_kmer(lp[i]);
+    for (u32 i = tid; i < n_s; i += NT) sk[i] = v.last_kmer(ls[i]);
+    for (u32 i = tid; i < g * H2; i += NT) tab[i] = KC_NONE;
+    if (tid == 0) s_hits = 0;
+    __syncthreads();
+    for (u32 item = tid; item < g * n_p; item += NT) {  // (level, prefix end) pairs spread over the whole block
+        const u32 lev = item / n_p, i = item - lev * n_p;
+        const int d = d_hi - (int) lev;
+        u32 *tb = tab + lev * H2;
+        const KWord<L> key = kmer_prefix(pk[i], v.k, d);
+        u64 h = 0;
+#pragma unroll
+        for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
+        u32 sl = (u32) (h >> 40) & (H2 - 1);
+        while (true) {
+            const u32 old = atomicCAS(&tb[sl], KC_NONE, i);
+            if (old == KC_NONE || kmer_prefix(pk[old], v.k, d) == key) break;
+            sl = (sl + 1) & (H2 - 1);
+        }
+    }
+    __syncthreads();
+    u32 hits = 0;
+    for (u32 item = tid; item < g * n_s; item += NT) {
+        const u32 lev = item / n_s, i = item - lev * n_s;
+        if ((hits >> lev) & 1u) continue;
+        const int d = d_hi - (int) lev;
+        const u32 *tb = tab + lev * H2;
+        const KWord<L> key = kmer_suffix(sk[i], d);
+        u64 h = 0;
+#pragma unroll
+        for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
+        u32 sl = (u32) (h >> 40) & (H2 - 1);
+        while (true) {
+            const u32 o = tb[sl];
+            if (o == KC_NONE) break;
+            if (kmer_prefix(pk[o], v.k, d) == key) {
+                hits |= 1u << lev;
+                break;
+            }
+            sl = (sl + 1) & (H2 - 1);
+        }
+    }
+    if (hits) atomicOr(&s_hits, hits);
+    __syncthreads();
+    if (tid == 0) {
+        const u32 hm = s_hits;
+        for (u32 lev = 0; lev < g; ++lev)
+            if ((hm >> lev) & 1u) atomicOr(&mask_out[(d_hi - (int) lev) >> 5], 1u << ((d_hi - (int) lev) & 31));
+    }
+}
 
 template <int L> __global__ void __launch_bounds__(512) kc_small_engine_kernel(SmallEngineArgs<L> a) {
     typedef KWord<L + 1> TW;
@@ -104,85 +191,11 @@ template <int L> __global__ void __launch_bounds__(512) kc_small_engine_kernel(S
     long long ph_t = clock64();
 #define KC_PH(i) do { const long long kc_now = clock64(); ph[i] += kc_now - ph_t; ph_t = kc_now; } while (0)
 
-    // Find out ONCE at which levels any free suffix can meet any free prefix.  The live sets only shrink, so a level whose
-    // bit is clear can never accept an edge and is skipped.  Full k-mers of the ends are parked in the still unused tuple
-    // buffer.
-    {
-        KWord<L> *pk = reinterpret_cast<KWord<L> *>(T0), *sk = pk + n_p;
-        if (tid < 4) lvl_mask[tid] = 0;
-        for (u32 i = tid; i < n_p; i += NT) pk[i] = v.first_kmer(lp[i]);
-        for (u32 i = tid; i < n_s; i += NT) sk[i] = v.last_kmer(ls[i]);
-        __syncthreads();
-        {
-            // An EXACT hash join per level: the prefix keys of level d go into an open-addressing table of end indices (keys
-            // are compared through the parked k-mers, so there are no false positives — a bit filter lit up at every level
-            // once ~800 x 800 ends were alive, and all 31 levels of a 400-record genome ran at ~40 us each although only 11
-            // could accept an edge); the suffix keys probe it.  ~1.5 k clocks per level; all pairs x all levels cost 140 k
-            // clocks even for the 100 x 100 ends of configs[1].
-            // Several levels share one pass: each level has its own table, so only three barriers separate clear / insert /
-            // probe for a whole group of levels (all 31 at once for the 100 x 100 ends of configs[1]).
-            u32 *tab = reinterpret_cast<u32 *>(sk + n_s);
-            u32 H2 = 64;
-            while (H2 < 2 * n_p) H2 <<= 1;  // <= 8192 slots; k-mers + one table fit the tuple buffer for every L (see SmallCfg)
-            const u32 avail = (u32) ((SmallCfg<L>::T * sizeof(TW) - (size_t) (n_s + n_p) * sizeof(KWord<L>)) / 4);
-            u32 G = avail / H2;
-            if (G > 32) G = 32;
-            if (G < 1) G = 1;
-            for (int d_hi = a.d_start; d_hi >= 0; d_hi -= (int) G) {
-                const u32 g = (u32) (d_hi + 1) < G ? (u32) (d_hi + 1) : G;  // levels d_hi, d_hi - 1, ..., d_hi - g + 1
-                for (u32 i = tid; i < g * H2; i += NT) tab[i] = KC_NONE;
-                if (tid == 0) s_groups = 0;  // reused as the hit mask of the group
-                __syncthreads();
-                for (u32 item = tid; item < g * n_p; item += NT) {  // (level, prefix end) pairs spread over the whole block
-                    const u32 lev = item / n_p, i = item - lev * n_p;
-                    const int d = d_hi - (int) lev;
-                    u32 *tb = tab + lev * H2;
-                    const KWord<L> key = kmer_prefix(pk[i], v.k, d);
-                    u64 h = 0;
-#pragma unroll
-                    for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
-                    u32 sl = (u32) (h >> 40) & (H2 - 1);
-                    while (true) {
-                        const u32 old = atomicCAS(&tb[sl], KC_NONE, i);
-                        if (old == KC_NONE || kmer_prefix(pk[old], v.k, d) == key) break;
-                        sl = (sl + 1) & (H2 - 1);
-                    }
-                }
-                __syncthreads();
-                u32 hits = 0;
-                for (u32 item = tid; item < g * n_s; item += NT) {
-                    const u32 lev = item / n_s, i = item - lev * n_s;
-                    if ((hits >> lev) & 1u) continue;
-                    const int d = d_hi - (int) lev;
-                    const u32 *tb = tab + lev * H2;
-                    const KWord<L> key = kmer_suffix(sk[i], d);
-                    u64 h = 0;
-#pragma unroll
-                    for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
-                    u32 sl = (u32) (h >> 40) & (H2 - 1);
-                    while (true) {
-                        const u32 o = tb[sl];
-                        if (o == KC_NONE) break;
-                        if (kmer_prefix(pk[o], v.k, d) == key) {
-                            hits |= 1u << lev;
-                            break;
-                        }
-                        sl = (sl + 1) & (H2 - 1);
-                    }
-                }
-                if (hits) atomicOr(&s_groups, hits);
-                __syncthreads();
-                if (tid == 0) {
-                    const u32 hm = s_groups;
-                    for (u32 lev = 0; lev < g; ++lev)
-                        if ((hm >> lev) & 1u) lvl_mask[(d_hi - (int) lev) >> 5] |= 1u << ((d_hi - (int) lev) & 31);
-                }
-                __syncthreads();
-            }
-        }
-    }
+    // the levels at which any free suffix can meet any free prefix (kc_small_level_mask_kernel)
+    if (tid < 4) lvl_mask[tid] = a.lvl_mask_in[tid];
+    __syncthreads();
 
-    KC_PH(0);  // state staging + level mask
+    KC_PH(0);  // state staging
     for (int d = a.d_start; d >= 0; --d) {
         if (n_s <= done || n_p == 0) break;
         const long long lvl_t0 = clock64();
@@ -204,6 +217,8 @@ template <int L> __global__ void __launch_bounds__(512) kc_small_engine_kernel(S
                 tail_w[x] = s.chain_tail[x];
             }
         }
+        if (nt <= SmallCfg<L>::RANK_SORT)
+            for (u32 i = tid; i < nt; i += NT) group_pstart[i] = 0;  // partial ranks of the rank sort
         if (tid == 0) {
             s_groups = 0;
             s_bans = 0;
@@ -215,12 +230,30 @@ template <int L> __global__ void __launch_bounds__(512) kc_small_engine_kernel(S
         // 36+ of a bitonic network over 256 slots.
         if (nt <= SmallCfg<L>::RANK_SORT) {
             TW *dst = T0 + HCAP;
-            for (u32 i = tid; i < nt; i += NT) {
-                const TW mine = T0[i];
-                u32 r = 0;
+            const u32 P = NT / nt;  // threads per tuple
+            if (P >= 2) {
+                // each of a tuple's P threads counts the smaller tuples in its share of the buffer (consecutive threads hold consecutive
+                // tuples and walk the same share: the loads broadcast); the partial ranks meet in rk[] (zeroed in the tuple phase)
+                u32 *rk = group_pstart;
+                if (tid < nt * P) {
+                    const u32 part = tid / nt, i = tid - part * nt;
+                    const u32 j0 = part * nt / P, j1 = (part + 1) * nt / P;
+                    const TW mine = T0[i];
+                    u32 r = 0;
 #pragma unroll 8
-                for (u32 j = 0; j < nt; ++j) r += T0[j] < mine ? 1u : 0u;
-                dst[r] = mine;
+                    for (u32 j = j0; j < j1; ++j) r += T0[j] < mine ? 1u : 0u;
+                    atomicAdd(&rk[i], r);
+                }
+                __syncthreads();
+                for (u32 i = tid; i < nt; i += NT) dst[rk[i]] = T0[i];
+            } else {
+                for (u32 i = tid; i < nt; i += NT) {
+                    const TW mine = T0[i];
+                    u32 r = 0;
+#pragma unroll 8
+                    for (u32 j = 0; j < nt; ++j) r += T0[j] < mine ? 1u : 0u;
+                    dst[r] = mine;
+                }
             }
             T = dst;
             __syncthreads();

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+export KC_GROUP_TIMEOUT_MS=20000
+timeout 1200 python -m pytest tests/test_gpu.py tests/test_gpu_sparse.py tests/test_sharded.py tests/test_cli.py -m gpu -x -q > gpurun_out/pytest_engine.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_engine.log | cut -c1-300
+KC_TRACE=1 timeout 300 python profiles/small_engine_trace.py 2> gpurun_out/small_trace.log | tee gpurun_out/small_trace.txt
+grep "small engine" gpurun_out/small_trace.log | awk 'NR%3==0' | sed 's/.*phases:/phases:/' | head -12
+timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_e.json 2> gpurun_out/bench_e.err; echo "bench rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/bench_e.json')); print(d['ms_per_step'], d['ms_per_step_with_kernel_timers'], d['e2e']['ms_per_step'], d['kernel_classes']['small_engine'])"
