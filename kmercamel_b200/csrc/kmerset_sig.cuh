@@ -375,8 +375,8 @@ __global__ void __launch_bounds__(256) kc_sig_gather_kernel(const u32 *__restric
 template <int L> struct SigCfg {
     static constexpr int THREADS = (int) KC_SIG_REC_CAP;
     static constexpr int NW = L + 1;                                     // 32-base code words a window can reach into
-    static constexpr u32 T1N = 2 * KC_SIG_SLOTS, T2N = KC_SIG_SLOTS / 2;  // T2 takes the ~16 % of the items that meet another key in T1
-    static constexpr int T1_BITS = 12;
+    static constexpr u32 T1N = 4 * KC_SIG_SLOTS, T2N = KC_SIG_SLOTS / 4;  // T2 takes the items that lose their T1 slot to another key (~4 %)
+    static constexpr int T1_BITS = 13;
     static constexpr int MIN_CTAS = L == 1 ? 5 : (L == 2 ? 3 : 2);      // resident CTAs per SM the shared memory allows
     static int smem() { return (int) (KC_SIG_SLOTS * (sizeof(KWord<L>) + 4) + T1N * 2 + T2N * 4); }
 };
@@ -386,6 +386,20 @@ template <int L> struct SigCfg {
 KC_D u64 kc_reverse_symbols64_brev(u64 w) {
     const u64 b = __brevll(w);  // symbols reversed, the two bits of every symbol swapped
     return ((b >> 1) & 0x5555555555555555ULL) | ((b & 0x5555555555555555ULL) << 1);
+}
+
+// Hash of a canonical k-mer for the tables of the resolve: a sum of 32-bit products (one multiply-add per half limb instead of a
+// 64-bit product per limb); T1 takes the top bits, T2 a second mix of all of them.
+template <int L> KC_D u32 kc_sig_hash(const KWord<L> &c) {
+    constexpr u32 C[8] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
+    u32 h = 0;
+#pragma unroll
+    for (int q = 0; q < L; ++q) h += (u32) c.w[q] * C[2 * q] + (u32) (c.w[q] >> 32) * C[2 * q + 1];
+    return h;
+}
+KC_D u32 kc_sig_hash2(u32 h) {
+    h ^= h >> 15;
+    return (h * 0x2C1B3C6Du) >> 16;
 }
 
 // The code words a record's windows can reach into: word NW - 1 = the strip of the record, the others to its left.
@@ -400,8 +414,14 @@ template <int NW> KC_D void kc_sig_load_words(const u64 *__restrict__ packed, u6
 // word left by one base, reverse complement right by one base (src/parser.h:39-40; L = 1 keeps the reverse complement
 // left-aligned, so that every shift of the roll is static).  The record of bucket n + 2 and the code words of bucket n + 1 are
 // in flight (registers) while bucket n is resolved: no thread waits for HBM between the barriers.
-template <int L, bool MULTI>
-__global__ void __launch_bounds__(SigCfg<L>::THREADS, SigCfg<L>::MIN_CTAS) kc_sig_resolve_kernel(const u64 *__restrict__ packed, int k, int complements,
+//
+// All eight windows of a record are computed whatever its length and only the stores are predicated: in a warp of 32 records
+// some record has 8 windows practically always, so branches around every window saved nothing and cost the reconvergence
+// points (16 BSSY / BSYNC pairs per bucket) and the overlap of the eight independent hash / store chains (0.315 -> 0.289 ms on
+// configs[1]).  Fewer threads per CTA (160 / 192 with a second round for the records beyond, 6 CTAs per SM) were measured and change
+// nothing: 0.287 - 0.293 ms.
+template <int L, bool MULTI, bool UNI>
+__global__ void __launch_bounds__(SigCfg<L>::THREADS, SigCfg<L>::MIN_CTAS) kc_sig_resolve_kernel(const u64 *__restrict__ packed, int k,
                                                                                                 const u32 *__restrict__ cursor, const u64 *__restrict__ recs,
                                                                                                 u32 n_buckets, KsfFlagPeers fl, kc_ull *n_unique, u32 *status,
                                                                                                 u32 n_senders, u32 sub_cap, u32 off_stride) {
@@ -419,7 +439,6 @@ __global__ void __launch_bounds__(SigCfg<L>::THREADS, SigCfg<L>::MIN_CTAS) kc_si
     const int top = 2 * (k - 1);
     const int top_limb = top >> 6, top_off = top & 63;
     const int lsh = 64 * L - 2 * k;  // left-aligned <-> right-aligned
-    const bool uni = complements == 0;
     u32 kept = 0;
     const u32 stride = gridDim.x;
     u32 b = blockIdx.x;
@@ -429,6 +448,105 @@ __global__ void __launch_bounds__(SigCfg<L>::THREADS, SigCfg<L>::MIN_CTAS) kc_si
         if (bb >= n_buckets) return;
         nr = cursor[bb];
         rec = recs[(u64) bb * RC + threadIdx.x];
+    };
+    // record r (its code words in w) -> the canonical k-mers of its windows into slots t * RC + r, their T1 slots into h1
+    auto spread = [&](const u64 rec, const u64 (&w)[NW], const u32 r, u32 (&h1)[P]) -> u32 {
+        const u32 pos = (u32) rec, len = ((u32) (rec >> 32) & 7u) + 1u;
+        const int sh = 2 * (31 - (int) (pos & 31u));
+        const u64 mine = w[NW - 1];
+        const u64 ms = sh ? mine << (64 - sh) : 0ULL;  // the bases behind the first window, left-aligned
+        if constexpr (L == 1) {
+            u64 f = (sh ? (mine >> sh) | (w[0] << (64 - sh)) : mine) & kmask.w[0];
+            const u64 tmask = kmask.w[0] << lsh;
+            u64 ral = UNI ? 0ULL : ~kc_reverse_symbols64_brev(f) & tmask;  // reverse complement, left-aligned
+#pragma unroll
+            for (int t = 0; t < P; ++t) {
+                if (t) {
+                    const u64 c = (ms >> (64 - 2 * t)) & 3ULL;
+                    f = ((f << 2) | c) & kmask.w[0];
+                    if (!UNI) ral = ((ral >> 2) | ((3ULL ^ c) << 62)) & tmask;
+                }
+                KWord<1> canon;
+                canon.w[0] = f;
+                if (!UNI) {
+                    const u64 rr = ral >> lsh;
+                    canon.w[0] = f < rr ? f : rr;
+                }
+                const u32 slot = (u32) t * RC + r;
+                h1[t] = kc_sig_hash<1>(canon) >> (32 - Cfg::T1_BITS);
+                if ((u32) t < len) {
+                    sk[slot] = canon;
+                    sp[slot] = pos + (u32) t;
+                    T1[h1[t]] = (u16) slot;
+                }
+            }
+        } else {
+            KWord<L> f;
+#pragma unroll
+            for (int l = 0; l < L; ++l) f.w[l] = sh ? (w[NW - 1 - l] >> sh) | (w[NW - 2 - l] << (64 - sh)) : w[NW - 1 - l];
+            f = f & kmask;
+            KWord<L> rv;
+#pragma unroll
+            for (int i = 0; i < L; ++i) rv.w[i] = ~kc_reverse_symbols64_brev(f.w[L - 1 - i]);
+            rv = rv.shr(lsh);
+#pragma unroll
+            for (int t = 0; t < P; ++t) {
+                if ((u32) t < len) {
+                    if (t) {  // roll both strands by one base
+                        const u64 c = (ms >> (64 - 2 * t)) & 3ULL;
+                        f = f.shl(2);
+                        f.w[0] |= c;
+                        f = f & kmask;
+                        rv = rv.shr(2);
+#pragma unroll
+                        for (int i = 0; i < L; ++i)
+                            if (i == top_limb) rv.w[i] |= (3ULL ^ c) << top_off;
+                    }
+                    const KWord<L> canon = (UNI || f < rv) ? f : rv;
+                    const u32 slot = (u32) t * RC + r;
+                    sk[slot] = canon;
+                    sp[slot] = pos + (u32) t;
+                    h1[t] = kc_sig_hash<L>(canon) >> (32 - Cfg::T1_BITS);
+                    T1[h1[t]] = (u16) slot;
+                } else {
+                    h1[t] = 0;
+                }
+            }
+        }
+        return len;
+    };
+    // an item that did not win its T1 slot: equal key = duplicate (fold the positions, clear the larger one's bit); different key ->
+    // T2 with CAS + linear probing
+    auto settle = [&](const u32 slot) {
+        const KWord<L> key = sk[slot];
+        const u32 h = kc_sig_hash<L>(key);
+        const u32 o = T1[h >> (32 - Cfg::T1_BITS)];
+        if (sk[o] == key) {
+            const u32 mine_p = sp[slot];
+            const u32 was = atomicMin(&sp[o], mine_p);
+            kc_flag_clear_all<MULTI>(fl, was > mine_p ? was : mine_p);
+        } else {
+            u32 s2 = kc_sig_hash2(h) & (T2N - 1);
+#pragma unroll 1
+            for (u32 probes = 0;; ++probes) {
+                if (probes == T2N) {  // T2 is full (never seen: it would take > 512 T1 collisions in one bucket)
+                    status[0] = 1;
+                    break;
+                }
+                const u32 old = atomicCAS(&T2[s2], KC_NONE, slot);
+                if (old == KC_NONE) {
+                    ++kept;
+                    break;
+                }
+                if (sk[old] == key) {
+                    const u32 mine_p = sp[slot];
+                    const u32 was = atomicMin(&sp[old], mine_p);
+                    kc_flag_clear_all<MULTI>(fl, was > mine_p ? was : mine_p);
+                    break;
+                }
+                s2 = (s2 + 1) & (T2N - 1);
+            }
+        }
     };
     u32 nr0, nr1;
     u64 rec0, rec1;
@@ -445,125 +563,29 @@ __global__ void __launch_bounds__(SigCfg<L>::THREADS, SigCfg<L>::MIN_CTAS) kc_si
         const bool skip = n_rec == 0 || n_rec > RC;  // uniform over the CTA
         if (n_rec > RC && threadIdx.x == 0) status[0] = 1;  // the scan has set the status word already
         if (!skip) {
-            {
-                uint4 *t2v = reinterpret_cast<uint4 *>(T2) + threadIdx.x * (T2N / 4 / Cfg::THREADS);
-#pragma unroll
-                for (u32 q = 0; q < T2N / 4 / Cfg::THREADS; ++q) t2v[q] = make_uint4(KC_NONE, KC_NONE, KC_NONE, KC_NONE);
-            }
+            static_assert(T2N / 4 <= (u32) Cfg::THREADS, "one uint4 of T2 per thread");
+            if (threadIdx.x < T2N / 4) reinterpret_cast<uint4 *>(T2)[threadIdx.x] = make_uint4(KC_NONE, KC_NONE, KC_NONE, KC_NONE);
             // P1: the thread's record -> its k-mers, canonical, into the tables
             const bool have = threadIdx.x < n_rec;
-            const u32 pos = (u32) rec0, len = have ? ((u32) (rec0 >> 32) & 7u) + 1u : 0u;
+            u32 len = 0;
             u32 h1[P];
-            if (have) {
-                const int sh = 2 * (31 - (int) (pos & 31u));
-                const u64 mine = w0[NW - 1];
-                const u64 ms = sh ? mine << (64 - sh) : 0ULL;  // the bases behind the first window, left-aligned
-                if constexpr (L == 1) {
-                    u64 f = (sh ? (mine >> sh) | (w0[0] << (64 - sh)) : mine) & kmask.w[0];
-                    const u64 tmask = kmask.w[0] << lsh;
-                    u64 ral = ~kc_reverse_symbols64_brev(f) & tmask;  // reverse complement, left-aligned
-#pragma unroll
-                    for (int t = 0; t < P; ++t) {
-                        if ((u32) t < len) {
-                            if (t) {
-                                const u64 c = (ms >> (64 - 2 * t)) & 3ULL;
-                                f = ((f << 2) | c) & kmask.w[0];
-                                ral = ((ral >> 2) | ((3ULL ^ c) << 62)) & tmask;
-                            }
-                            const u64 r = ral >> lsh;
-                            const bool take_f = uni | (f < r);
-                            const u64 canon = take_f ? f : r;
-                            const u32 slot = (u32) t * RC + threadIdx.x;
-                            sk[slot].w[0] = canon;
-                            sp[slot] = pos + (u32) t;
-                            const u64 h = canon * 0xD6E8FEB86659FD93ULL;
-                            h1[t] = (u32) (h >> (64 - Cfg::T1_BITS));
-                            T1[h1[t]] = (u16) slot;
-                        }
-                    }
-                } else {
-                    KWord<L> f;
-#pragma unroll
-                    for (int l = 0; l < L; ++l) f.w[l] = sh ? (w0[NW - 1 - l] >> sh) | (w0[NW - 2 - l] << (64 - sh)) : w0[NW - 1 - l];
-                    f = f & kmask;
-                    KWord<L> r;
-#pragma unroll
-                    for (int i = 0; i < L; ++i) r.w[i] = ~kc_reverse_symbols64_brev(f.w[L - 1 - i]);
-                    r = r.shr(lsh);
-#pragma unroll
-                    for (int t = 0; t < P; ++t) {
-                        if ((u32) t < len) {
-                            if (t) {  // roll both strands by one base
-                                const u64 c = (ms >> (64 - 2 * t)) & 3ULL;
-                                f = f.shl(2);
-                                f.w[0] |= c;
-                                f = f & kmask;
-                                r = r.shr(2);
-#pragma unroll
-                                for (int i = 0; i < L; ++i)
-                                    if (i == top_limb) r.w[i] |= (3ULL ^ c) << top_off;
-                            }
-                            const KWord<L> canon = (!complements || f < r) ? f : r;
-                            const u32 slot = (u32) t * RC + threadIdx.x;
-                            sk[slot] = canon;
-                            sp[slot] = pos + (u32) t;
-                            u64 h = 0;
-#pragma unroll
-                            for (int q = 0; q < L; ++q) h = (h ^ canon.w[q]) * 0xD6E8FEB86659FD93ULL;
-                            h1[t] = (u32) (h >> (64 - Cfg::T1_BITS));
-                            T1[h1[t]] = (u16) slot;
-                        }
-                    }
-                }
-            }
+            if (have) len = spread(rec0, w0, threadIdx.x, h1);
             __syncthreads();
             // P2: the winner of a T1 slot represents its key (~92 % of the items: done).  The others are listed in a bit mask and
             //     handled in a loop of their own (a thread has ~0.4 of them; inside the unrolled pass over t every warp paid the
-            //     slow path eight times): equal key = duplicate (fold the positions, clear the larger one's bit); different key ->
-            //     T2 with CAS + linear probing
-            u32 slow = 0;
+            //     slow path eight times).  Dealing a warp's losers out one per lane through a list in shared memory — one dense
+            //     round instead of the 2-3 rounds of the unluckiest lane — was measured: 0.289 -> 0.298 ms.
+            if (have) {
+                u32 win = 0;
 #pragma unroll
-            for (int t = 0; t < P; ++t) {
-                if ((u32) t < len) {
-                    const u32 o = T1[h1[t]];
-                    if (o == (u32) t * RC + threadIdx.x) ++kept;
-                    else slow |= 1u << t;
-                }
-            }
-            while (slow) {
-                const u32 t = (u32) __ffs(slow) - 1u;
-                slow &= slow - 1u;
-                const u32 slot = t * RC + threadIdx.x;
-                const KWord<L> key = sk[slot];
-                u64 h = 0;
-#pragma unroll
-                for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0xD6E8FEB86659FD93ULL;
-                const u32 o = T1[(u32) (h >> (64 - Cfg::T1_BITS))];
-                if (sk[o] == key) {
-                    const u32 mine_p = sp[slot];
-                    const u32 was = atomicMin(&sp[o], mine_p);
-                    kc_flag_clear_all<MULTI>(fl, was > mine_p ? was : mine_p);
-                } else {
-                    u32 s2 = (u32) (h >> (64 - 2 * Cfg::T1_BITS)) & (T2N - 1);
-#pragma unroll 1
-                    for (u32 probes = 0;; ++probes) {
-                        if (probes == T2N) {  // T2 is full (never seen: it would take > 1024 T1 collisions in one bucket)
-                            status[0] = 1;
-                            break;
-                        }
-                        const u32 old = atomicCAS(&T2[s2], KC_NONE, slot);
-                        if (old == KC_NONE) {
-                            ++kept;
-                            break;
-                        }
-                        if (sk[old] == key) {
-                            const u32 mine_p = sp[slot];
-                            const u32 was = atomicMin(&sp[old], mine_p);
-                            kc_flag_clear_all<MULTI>(fl, was > mine_p ? was : mine_p);
-                            break;
-                        }
-                        s2 = (s2 + 1) & (T2N - 1);
-                    }
+                for (int t = 0; t < P; ++t) win |= (T1[h1[t]] == (u32) t * RC + threadIdx.x ? 1u : 0u) << t;
+                const u32 all = (1u << len) - 1u;
+                kept += __popc(win & all);
+                u32 slow = all & ~win;
+                while (slow) {
+                    const u32 t = (u32) __ffs(slow) - 1u;
+                    slow &= slow - 1u;
+                    settle(t * RC + threadIdx.x);
                 }
             }
             __syncthreads();  // the next bucket's P1 overwrites sk / sp / T1 / T2
@@ -589,10 +611,12 @@ template <int L> struct SigKernels {
         static KcDevOnce once;
         static Dev dev[KC_MAX_DEVICES];
         const int d = once.run([&](int dv) {
-            KC_CUDA(cudaFuncSetAttribute(kc_sig_resolve_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem()));
-            KC_CUDA(cudaFuncSetAttribute(kc_sig_resolve_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem()));
+            KC_CUDA(cudaFuncSetAttribute(kc_sig_resolve_kernel<L, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem()));
+            KC_CUDA(cudaFuncSetAttribute(kc_sig_resolve_kernel<L, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem()));
+            KC_CUDA(cudaFuncSetAttribute(kc_sig_resolve_kernel<L, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem()));
+            KC_CUDA(cudaFuncSetAttribute(kc_sig_resolve_kernel<L, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem()));
             dev[dv].n_sm = kc_sm_count(dv);
-            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev[dv].occ, kc_sig_resolve_kernel<L, false>, Cfg::THREADS, Cfg::smem()));
+            KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&dev[dv].occ, kc_sig_resolve_kernel<L, false, false>, Cfg::THREADS, Cfg::smem()));
         });
         return dev[d];
     }
@@ -657,8 +681,12 @@ bool kc_kmerset_build_sig(CudaExec &ex, const u8 *seq, u64 n_bytes, int k, bool 
         const u32 grid = pl.n_buckets < fit ? pl.n_buckets : fit;
         // records read, two code words per record
         CudaExec::Scope sc(ex, KP_KS_RESOLVE, (u64) (n_bytes * (8 + 8 * Cfg::NW) / KC_SIG_WINDOWS_PER_RECORD));
-        kc_sig_resolve_kernel<L, false><<<grid, Cfg::THREADS, Cfg::smem(), st>>>(packed, k, complements ? 1 : 0, cursor, recs, pl.n_buckets, kc_ksf_own_flags(flags),
-                                                                               reinterpret_cast<kc_ull *>(cells), status, 1u, KC_SIG_REC_CAP, 0u);
+        if (complements)
+            kc_sig_resolve_kernel<L, false, false><<<grid, Cfg::THREADS, Cfg::smem(), st>>>(packed, k, cursor, recs, pl.n_buckets, kc_ksf_own_flags(flags),
+                                                                                          reinterpret_cast<kc_ull *>(cells), status, 1u, KC_SIG_REC_CAP, 0u);
+        else
+            kc_sig_resolve_kernel<L, false, true><<<grid, Cfg::THREADS, Cfg::smem(), st>>>(packed, k, cursor, recs, pl.n_buckets, kc_ksf_own_flags(flags),
+                                                                                         reinterpret_cast<kc_ull *>(cells), status, 1u, KC_SIG_REC_CAP, 0u);
         ++ex.launches;
         KC_CUDA(cudaGetLastError());
     }
@@ -739,9 +767,12 @@ void kc_sig_group_resolve(CudaExec &ex, const u64 *packed, int k, bool complemen
         KC_CUDA(cudaGetLastError());
     }
     CudaExec::Scope sc(ex, KP_KS_RESOLVE, (u64) (n_bytes / n_ranks * (8 + 8 * Cfg::NW) / KC_SIG_WINDOWS_PER_RECORD));
-    kc_sig_resolve_kernel<L, true><<<grid, Cfg::THREADS, Cfg::smem(), ex.stream>>>(packed, k, complements ? 1 : 0, cnt_bm, recs_bm, n_owned, all_flags,
-                                                                                 reinterpret_cast<kc_ull *>(cells), reinterpret_cast<u32 *>(cells + 3), (u32) n_ranks,
-                                                                                 KC_SIG_REC_CAP, 0u);
+    if (complements)
+        kc_sig_resolve_kernel<L, true, false><<<grid, Cfg::THREADS, Cfg::smem(), ex.stream>>>(packed, k, cnt_bm, recs_bm, n_owned, all_flags, reinterpret_cast<kc_ull *>(cells),
+                                                                                            reinterpret_cast<u32 *>(cells + 3), (u32) n_ranks, KC_SIG_REC_CAP, 0u);
+    else
+        kc_sig_resolve_kernel<L, true, true><<<grid, Cfg::THREADS, Cfg::smem(), ex.stream>>>(packed, k, cnt_bm, recs_bm, n_owned, all_flags, reinterpret_cast<kc_ull *>(cells),
+                                                                                           reinterpret_cast<u32 *>(cells + 3), (u32) n_ranks, KC_SIG_REC_CAP, 0u);
     ++ex.launches;
     KC_CUDA(cudaGetLastError());
 }
