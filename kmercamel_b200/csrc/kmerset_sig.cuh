@@ -165,8 +165,7 @@ __global__ void __launch_bounds__(256) kc_sig_scan_kernel(const u8 *__restrict__
     constexpr int NH = 32 + KC_SIG_W - 1;  // M-mer hashes a strip needs
     __shared__ u64 pk[KC_EX_HALO + T];
     __shared__ u32 vm[KC_EX_HALO + T];
-    __shared__ u32 ssig[KC_EX_STRIP * T];  // signature of the window ending at strip base j of thread t at [j * T + t]; later of its piece c
-    __shared__ u8 plist[KC_EX_STRIP * T];  // piece c of thread t at [c * T + t]: first window << 3 | windows - 1
+    __shared__ u32 ssig[KC_EX_STRIP * T];  // signature of the window ending at strip base j of thread t at [j * T + t]
     const i64 block_pos0 = (i64) (tile0 + blockIdx.x) * (T * KC_EX_STRIP);
     kc_tile_load<T>(seq, n_bytes, block_pos0, pk, vm);
     __syncthreads();
@@ -228,44 +227,47 @@ __global__ void __launch_bounds__(256) kc_sig_scan_kernel(const u8 *__restrict__
         if (j) neq |= (H[j] != H[j - 1] ? 1u : 0u) << j;
     }
     const u32 emr = __brev(em);                          // bit j = window ending at strip base j
-    u32 run_starts = emr & (neq | ~(emr << 1));          // a run: valid windows of one signature
-    const u32 stops = run_starts | ~emr;
-    // the pieces (<= 8 windows) of the runs, listed first ...
-    u32 n_pieces = 0;
-    while (run_starts) {
-        u32 j = (u32) __ffs(run_starts) - 1u;
-        run_starts &= run_starts - 1u;
-        const u32 rest = j < 31 ? stops & (0xFFFFFFFFu << (j + 1)) : 0u;
-        u32 len = (rest ? (u32) __ffs(rest) - 1u : 32u) - j;
-        const u32 sig = ssig[j * T + threadIdx.x];
-        while (len) {
-            const u32 l = len < (u32) KC_SIG_PIECE ? len : (u32) KC_SIG_PIECE;
-            plist[n_pieces * T + threadIdx.x] = (u8) ((j << 3) | (l - 1u));
-            if (n_pieces != j) ssig[n_pieces * T + threadIdx.x] = sig;  // piece c <= its first window j: entries below c are never read again
-            ++n_pieces;
-            j += l;
-            len -= l;
-        }
+    const u32 run_starts = emr & (neq | ~(emr << 1));    // a run: valid windows of one signature
+    // The pieces (<= 8 windows) of the runs, bit-parallel: a run is cut every 8 windows from its start, i.e. window p starts a piece
+    // iff it starts a run, or window p - 8 starts a piece and windows p - 7 .. p all continue its run.  (A loop over the runs that
+    // listed the pieces in shared memory first was 19 % of the kernel's instructions.)
+    const u32 cont = emr & ~run_starts;
+    u32 c8 = cont & (cont << 1);
+    c8 &= c8 << 2;
+    c8 &= c8 << 4;                                       // bit p: windows p - 7 .. p continue the run of window p - 8
+    u32 ps = run_starts;
+    {
+        u32 q = (run_starts << 8) & c8;
+        ps |= q;
+        q = (q << 8) & c8;
+        ps |= q;
+        q = (q << 8) & c8;
+        ps |= q;
     }
-    // ... so that the atomics of eight pieces are in flight together (one at a time, the thread waited ~0.7 us for each slot:
-    // 51 % of the kernel's stall samples)
+    const u32 bound = ps | ~emr;                         // a piece ends before the next piece or the next window that is not valid
+    // eight pieces per round, so that their atomics are in flight together (one at a time, the thread waited ~0.7 us for each
+    // slot: 51 % of the kernel's stall samples)
     const u32 pos0 = (u32) block_pos0 + threadIdx.x * KC_EX_STRIP;
     bool over = false;
-    for (u32 c0 = 0; c0 < n_pieces; c0 += 8) {
+    while (ps) {
         u32 bk[8], slot[8], e[8];
+        bool on[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            if (c0 + u < n_pieces) {
-                e[u] = plist[(c0 + u) * T + threadIdx.x];
-                bk[u] = kc_sig_bucket(ssig[(c0 + u) * T + threadIdx.x], n_buckets);
-            }
+            on[u] = ps != 0;
+            const u32 j = ((u32) __ffs(ps) - 1u) & 31u;
+            ps &= ps - 1u;
+            const u32 rest = bound & (0xFFFFFFFEu << j);
+            const u32 len = (rest ? (u32) __ffs(rest) - 1u : 32u) - j;
+            e[u] = (j << 3) | (len - 1u);
+            bk[u] = kc_sig_bucket(ssig[j * T + threadIdx.x], n_buckets);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-            if (c0 + u < n_pieces) slot[u] = atomicAdd(&cursor[bk[u]], 1u);
+            if (on[u]) slot[u] = atomicAdd(&cursor[bk[u]], 1u);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            if (c0 + u < n_pieces) {
+            if (on[u]) {
                 const u64 rec = kc_sig_record(pos0 + (e[u] >> 3), (e[u] & 7u) + 1u);
                 if (P2P) {  // into the rank's own staging array; kc_sig_ship_kernel sends whole sub-slots
                     if (slot[u] < sp.sub_cap) recs[(u64) bk[u] * sp.sub_cap + slot[u]] = rec;
