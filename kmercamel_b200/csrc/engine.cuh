@@ -416,9 +416,14 @@ template <class Exec, int L> struct Engine {
             a.strict = strict;
             a.out = ex.template alloc<u32>(8 + 128 + 8);
             ex.fill_bytes(a.out, 0, (8 + 128 + 8) * 4);
-            u32 *lvl_mask = ex.template alloc<u32>(4);
-            ex.fill_bytes(lvl_mask, 0, 16);
+            // level masks: [4] for the whole problem, then four words per end (two copies each: they travel with the live lists)
+            u32 *lvl_mask = ex.template alloc<u32>(4 + 8 * (n_s + n_p));
+            ex.fill_bytes(lvl_mask, 0, (4 + 4 * (n_s + n_p)) * 4);
             a.lvl_mask_in = lvl_mask;
+            a.end_mask_s_a = lvl_mask + 4;
+            a.end_mask_p_a = a.end_mask_s_a + 4 * n_s;
+            a.end_mask_s_b = a.end_mask_p_a + 4 * n_p;
+            a.end_mask_p_b = a.end_mask_s_b + 4 * n_s;
             const int mask_smem = (int) (SmallCfg<L>::T * sizeof(KWord<L + 1>));
             static KcDevOnce once;  // function attributes are per device
             once.run([&](int) {
@@ -430,7 +435,7 @@ template <class Exec, int L> struct Engine {
                 typename Exec::Scope sc(ex, KP_SMALL_ENGINE, 0);
                 const u32 per_cta = kc_small_mask_levels_per_cta<L>((u32) n_s, (u32) n_p);
                 kc_small_level_mask_kernel<L><<<(unsigned) kc_div_up((u64) d + 1, per_cta), 256, mask_smem, ex.stream>>>(nv, live_s, live_p, (u32) n_s, (u32) n_p, d,
-                                                                                                                      lvl_mask);
+                                                                                                                      lvl_mask, a.end_mask_s_a, a.end_mask_p_a);
                 ++ex.launches;
             }
             {

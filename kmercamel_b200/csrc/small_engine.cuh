@@ -34,6 +34,9 @@ template <int L> struct SmallEngineArgs {
     bool strict;
     u32 *out;  // [0] error, [1] levels run, [2] groups, [3] edges, [4] ban rounds, [5] bans, [8 + d] clocks spent in level d (KC_TRACE)
     const u32 *lvl_mask_in;  // [4] bit d: some (suffix, prefix) pair of the initial free ends agrees on d bases (kc_small_level_mask_kernel)
+    // [4 * n_s], [4 * n_p]: the same per END (bit d of the four words of initial list position i: end i has a partner at level d);
+    // ping-pong copies travel with the live lists
+    u32 *end_mask_s_a, *end_mask_p_a, *end_mask_s_b, *end_mask_p_b;
 };
 
 // Levels of one CTA of kc_small_level_mask_kernel (host and device must agree): as many hash tables as fit next to the parked k-mers,
@@ -58,9 +61,13 @@ template <int L> KC_HD u32 kc_small_mask_levels_per_cta(u32 n_s, u32 n_p) {
 // could accept an edge); the suffix keys probe it.  This used to be the first phase of the single-CTA engine kernel: 17 % of its
 // clocks at 100 ends, 32 % at 800 (all (level, end) pairs through one CTA).  The levels are independent, so they now spread over
 // (d_start + 1) / levels-per-CTA CTAs that run at the same time.
+// The join also says WHICH ends have a partner at a level (end_mask_s / end_mask_p, bit d of the end's four words): an end without one
+// can never be in an active group of that level, and the engine leaves it out of the level's tuples — at the high levels of a genome
+// a handful of the ~200 free ends take part, and the tuple sort was 30 % of the engine's clocks.
 template <int L>
 __global__ void __launch_bounds__(256) kc_small_level_mask_kernel(NodeView<L> v, const u32 *__restrict__ ls, const u32 *__restrict__ lp, u32 n_s, u32 n_p,
-                                                                  int d_start, u32 *mask_out /* [4], zeroed */) {
+                                                                  int d_start, u32 *mask_out /* [4], zeroed */, u32 *end_mask_s /* [4 n_s], zeroed */,
+                                                                  u32 *end_mask_p /* [4 n_p], zeroed */) {
     extern __shared__ __align__(16) unsigned char kc_smem_raw[];
     __shared__ u32 s_hits;
     const u32 tid = threadIdx.x, NT = blockDim.x;
@@ -92,12 +99,12 @@ __global__ void __launch_bounds__(256) kc_small_level_mask_kernel(NodeView<L> v,
         }
     }
     __syncthreads();
+    constexpr u32 PROBED = 0x80000000u;  // table entry: a suffix key has met this prefix key
     u32 hits = 0;
     for (u32 item = tid; item < g * n_s; item += NT) {
         const u32 lev = item / n_s, i = item - lev * n_s;
-        if ((hits >> lev) & 1u) continue;
         const int d = d_hi - (int) lev;
-        const u32 *tb = tab + lev * H2;
+        u32 *tb = tab + lev * H2;
         const KWord<L> key = kmer_suffix(sk[i], d);
         u64 h = 0;
 #pragma unroll
@@ -106,8 +113,10 @@ __global__ void __launch_bounds__(256) kc_small_level_mask_kernel(NodeView<L> v,
         while (true) {
             const u32 o = tb[sl];
             if (o == KC_NONE) break;
-            if (kmer_prefix(pk[o], v.k, d) == key) {
+            if (kmer_prefix(pk[o & ~PROBED], v.k, d) == key) {
                 hits |= 1u << lev;
+                if (!(o & PROBED)) tb[sl] = o | PROBED;  // (several writers, one value)
+                atomicOr(&end_mask_s[4 * i + ((u32) d >> 5)], 1u << (d & 31));
                 break;
             }
             sl = (sl + 1) & (H2 - 1);
@@ -119,6 +128,26 @@ __global__ void __launch_bounds__(256) kc_small_level_mask_kernel(NodeView<L> v,
         const u32 hm = s_hits;
         for (u32 lev = 0; lev < g; ++lev)
             if ((hm >> lev) & 1u) atomicOr(&mask_out[(d_hi - (int) lev) >> 5], 1u << ((d_hi - (int) lev) & 31));
+    }
+    const u32 hm = s_hits;
+    for (u32 item = tid; item < g * n_p; item += NT) {  // the prefix ends whose key was met
+        const u32 lev = item / n_p, i = item - lev * n_p;
+        if (!((hm >> lev) & 1u)) continue;
+        const int d = d_hi - (int) lev;
+        const u32 *tb = tab + lev * H2;
+        const KWord<L> key = kmer_prefix(pk[i], v.k, d);
+        u64 h = 0;
+#pragma unroll
+        for (int q = 0; q < L; ++q) h = (h ^ key.w[q]) * 0x9E3779B97F4A7C15ULL;
+        u32 sl = (u32) (h >> 40) & (H2 - 1);
+        while (true) {  // the key is in the table
+            const u32 o = tb[sl];
+            if (kmer_prefix(pk[o & ~PROBED], v.k, d) == key) {
+                if (o & PROBED) atomicOr(&end_mask_p[4 * i + ((u32) d >> 5)], 1u << (d & 31));
+                break;
+            }
+            sl = (sl + 1) & (H2 - 1);
+        }
     }
 }
 
@@ -184,6 +213,8 @@ template <int L> __global__ void __launch_bounds__(512) kc_small_engine_kernel(S
     }
     u32 n_s = a.n_s, n_p = a.n_p;
     u32 *ls = a.live_s_a, *lp = a.live_p_a, *ls2 = a.live_s_b, *lp2 = a.live_p_b;
+    u32 *ms = a.end_mask_s_a, *mp = a.end_mask_p_a, *ms2 = a.end_mask_s_b, *mp2 = a.end_mask_p_b;
+    __shared__ u32 s_nt;
     const u32 batch = a.strict ? v.N / 16 + 1 : v.N + 1;  // see Engine::run_level
     const u32 done = v.complements ? 2u : 1u;
     u32 st_levels = 0, st_groups = 0, st_edges = 0, st_rounds = 0, st_bans = 0;
@@ -202,35 +233,40 @@ template <int L> __global__ void __launch_bounds__(512) kc_small_engine_kernel(S
         // A level whose bit is clear cannot accept an edge (the live sets only shrink): skipped without touching memory.
         if (!((lvl_mask[d >> 5] >> (d & 31)) & 1u)) continue;  // uniform: no barrier needed
         ++st_levels;
-        const u32 nt = n_s + n_p;
+        const u32 n_live = n_s + n_p;
         T = T0;
-        // 1. tuples + working copies of the chain ends
-        for (u32 i = tid; i < nt; i += NT) {
-            if (i < n_s) {
-                u32 x = ls[i];
-                T[i] = tuple_make(kmer_suffix(v.last_kmer(x), d), (u64) x);
-                head_w[x] = s.chain_head[x];
-            } else {
-                u32 x = lp[i - n_s];
-                u64 meta = KC_ROLE_P | ((u64) (x / batch) << 32) | (u64) (u32) ~x;
-                T[i] = tuple_make(kmer_prefix(v.first_kmer(x), v.k, d), meta);
-                tail_w[x] = s.chain_tail[x];
-            }
-        }
-        if (nt <= SmallCfg<L>::RANK_SORT)
-            for (u32 i = tid; i < nt; i += NT) group_pstart[i] = 0;  // partial ranks of the rank sort
         if (tid == 0) {
+            s_nt = 0;
             s_groups = 0;
             s_bans = 0;
         }
         __syncthreads();
+        // 1. working copies of the chain ends; tuples of the ends that had a partner at this level when the kernel started (the others
+        //    cannot be in an active group; the order of the tuples is irrelevant, the sort follows)
+        for (u32 i = tid; i < n_live; i += NT) {
+            if (i < n_s) {
+                u32 x = ls[i];
+                head_w[x] = s.chain_head[x];
+                if ((ms[4 * i + ((u32) d >> 5)] >> (d & 31)) & 1u) T[atomicAdd(&s_nt, 1u)] = tuple_make(kmer_suffix(v.last_kmer(x), d), (u64) x);
+            } else {
+                u32 x = lp[i - n_s];
+                tail_w[x] = s.chain_tail[x];
+                if ((mp[4 * (i - n_s) + ((u32) d >> 5)] >> (d & 31)) & 1u) {
+                    u64 meta = KC_ROLE_P | ((u64) (x / batch) << 32) | (u64) (u32) ~x;
+                    T[atomicAdd(&s_nt, 1u)] = tuple_make(kmer_prefix(v.first_kmer(x), v.k, d), meta);
+                }
+            }
+        }
+        for (u32 i = tid; i < n_live && i <= SmallCfg<L>::RANK_SORT; i += NT) group_pstart[i] = 0;  // partial ranks of the rank sort
+        __syncthreads();
+        const u32 nt = s_nt;
         KC_PH(1);  // tuples
         // 2. sort.  Tiny levels: every thread ranks its tuple against all others (tuples are distinct: they carry role
         // and node id) and drops it at its rank in the upper half of the tuple buffer — two barriers instead of the
         // 36+ of a bitonic network over 256 slots.
         if (nt <= SmallCfg<L>::RANK_SORT) {
             TW *dst = T0 + HCAP;
-            const u32 P = NT / nt;  // threads per tuple
+            const u32 P = nt ? (NT / nt < 8u ? NT / nt : 8u) : 0u;  // threads per tuple
             if (P >= 2) {
                 // each of a tuple's P threads counts the smaller tuples in its share of the buffer (consecutive threads hold consecutive
                 // tuples and walk the same share: the loads broadcast); the partial ranks meet in rk[] (zeroed in the tuple phase)
@@ -396,7 +432,7 @@ template <int L> __global__ void __launch_bounds__(512) kc_small_engine_kernel(S
                     if (tid == 0) a.out[0] = 1;
                     return;
                 }
-                for (u32 i = tid; i < nt; i += NT) {
+                for (u32 i = tid; i < n_live; i += NT) {
                     if (i < n_s) {
                         u32 x = ls[i];
                         u32 y = s.edge_from[x];
@@ -425,17 +461,27 @@ template <int L> __global__ void __launch_bounds__(512) kc_small_engine_kernel(S
         __syncthreads();
         for (u32 i = tid; i < n_s; i += NT) {
             u32 x = ls[i];
-            if (s.edge_from[x] == KC_NONE) ls2[atomicAdd(&s_live_s, 1u)] = x;
+            if (s.edge_from[x] == KC_NONE) {
+                const u32 to = atomicAdd(&s_live_s, 1u);
+                ls2[to] = x;
+                *reinterpret_cast<uint4 *>(ms2 + 4 * to) = *reinterpret_cast<const uint4 *>(ms + 4 * i);
+            }
         }
         for (u32 i = tid; i < n_p; i += NT) {
             u32 x = lp[i];
-            if (s.edge_to[x] == KC_NONE) lp2[atomicAdd(&s_live_p, 1u)] = x;
+            if (s.edge_to[x] == KC_NONE) {
+                const u32 to = atomicAdd(&s_live_p, 1u);
+                lp2[to] = x;
+                *reinterpret_cast<uint4 *>(mp2 + 4 * to) = *reinterpret_cast<const uint4 *>(mp + 4 * i);
+            }
         }
         __syncthreads();
         n_s = s_live_s;
         n_p = s_live_p;
         u32 *t32 = ls; ls = ls2; ls2 = t32;
         t32 = lp; lp = lp2; lp2 = t32;
+        t32 = ms; ms = ms2; ms2 = t32;
+        t32 = mp; mp = mp2; mp2 = t32;
         __syncthreads();
         KC_PH(6);  // live lists
         if (tid == 0) a.out[8 + d] = (u32) (clock64() - lvl_t0) | 0x80000000u;  // top bit: the level was run, not skipped

@@ -31,9 +31,13 @@ static const int KC_EX_HALO = 4;  // halo words: 4 * 32 >= 127 - 1 preceding bas
 KC_D void kc_pack4(u32 w, u32 &codes, u32 &valid) {
     u32 c = ((w >> 1) ^ (w >> 2)) & 0x03030303u;  // A,a->0 C,c->1 G,g->2 T,t->3
     codes = (c * 0x40100401u) >> 24;
-    u32 u = w & 0xDFDFDFDFu;
-    u32 m = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u);
-    valid = (((m & 0x01010101u) * 0x08040201u) >> 24) & 0xFu;
+    // valid = the case-folded byte IS the letter its code stands for: A = 0x41, C = A + 2, G = A + 6, T = A + 19, rebuilt for the four bytes
+    // at once (three multiply-adds; four emulated __vcmpeq4 cost twice the instructions), then the zero bytes of the difference
+    const u32 c0 = c & 0x01010101u, c1 = (c >> 1) & 0x01010101u;
+    const u32 expect = 0x41414141u + c0 * 2u + c1 * 6u + (c0 & c1) * 11u;
+    const u32 d = (w & 0xDFDFDFDFu) ^ expect;
+    const u32 z = ~(((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;  // bit 7 of every byte that is zero
+    valid = (((z >> 7) * 0x08040201u) >> 24) & 0xFu;
 }
 
 // WITH_POS = false: out[] receives the canonical k-mers (KWord<L>).

@@ -5,4 +5,4 @@ timeout 1200 python -m pytest tests/test_gpu.py tests/test_gpu_sparse.py tests/t
 KC_TRACE=1 timeout 300 python profiles/small_engine_trace.py 2> gpurun_out/small_trace.log | tee gpurun_out/small_trace.txt
 grep "small engine" gpurun_out/small_trace.log | awk 'NR%3==0' | sed 's/.*phases:/phases:/' | head -12
 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_e.json 2> gpurun_out/bench_e.err; echo "bench rc=$?"; python -c "
-import json; d=json.load(open('gpurun_out/bench_e.json')); print(d['ms_per_step'], d['ms_per_step_with_kernel_timers'], d['e2e']['ms_per_step'], d['kernel_classes']['small_engine'])"
+import json; d=json.load(open('gpurun_out/bench_e.json')); kc=d['kernel_classes']; print(round(d['ms_per_step'],4), round(d['ms_per_step_with_kernel_timers'],4), 'e2e', round(d['e2e']['ms_per_step'],3), {k: round(v['ms_per_step'],4) for k,v in kc.items()})"
