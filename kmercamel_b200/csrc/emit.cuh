@@ -73,7 +73,8 @@ template <int L> KC_HD bool kmer_set_contains(const KWord<L> *keys, u64 n, const
 }
 
 static const u32 KC_EMIT_SHORT = 128;   // contributions up to this many characters: one thread
-static const u32 KC_EMIT_CHUNK = 4096;   // longer ones: chunks of this many characters, 256 work items each
+static const u32 KC_EMIT_CHUNK = 16384;  // longer ones: chunks of this many characters, 256 work items each (KC_EMIT_SUB x 16 bytes per item:
+static const u32 KC_EMIT_SUB = 4;        // the search for the chunk's node and its metadata loads are paid once for 64 bytes of output)
 
 #ifdef __CUDACC__
 template <int L> KmerIndex<L> kc_kmer_index_build(CudaExec &ex, const KWord<L> *keys, u64 n, int k) {
@@ -334,12 +335,15 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
             // output bytes [a0, a0 + 16) of this item, clipped to the node's [off, off + cnt)
             const u64 n0 = off & ~(u64) 15;                                             // first chunk of the node that meets the slice
             const u64 skip = n0 < s_begin ? (s_begin - n0) / KC_EMIT_CHUNK : 0;
-            u64 a0 = n0 + ((u64) (chunk - chunks[v]) + skip) * KC_EMIT_CHUNK + (u64) lane * 16;
+            const u64 c0 = n0 + ((u64) (chunk - chunks[v]) + skip) * KC_EMIT_CHUNK + (u64) lane * 16;
+            static_assert(KC_EMIT_CHUNK == KC_EMIT_SUB * 256 * 16, "a chunk is 256 work items x KC_EMIT_SUB x 16 bytes");
+            for (u32 sub = 0; sub < KC_EMIT_SUB; ++sub) {
+            u64 a0 = c0 + (u64) sub * (256 * 16);
             u64 b0 = a0 < off ? off : a0;
             u64 b1 = a0 + 16 < off + cnt ? a0 + 16 : off + cnt;
             if (b0 < s_begin) b0 = s_begin;  // slice boundaries are multiples of 16: an item is inside or outside as a whole
             if (b1 > s_end) b1 = s_end;
-            if (b0 >= b1) return;
+            if (b0 >= b1) continue;
             const u64 j0 = b0 - off;
 #ifdef __CUDA_ARCH__
             const bool one_case = j0 + 16 <= n_upper || j0 >= n_upper;
@@ -390,6 +394,7 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
                 *reinterpret_cast<uint4 *>(ms + b0) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
             } else {
                 for (u64 a = b0; a < b1; ++a) ms[a] = kc_letter(q.symbol(v, a - off), a - off < n_upper);
+            }
             }
         }, KP_EMIT, 2 * total);
     }

@@ -130,6 +130,32 @@ __global__ void __launch_bounds__(KC_FE_THREADS) kc_scan_tile_kernel(const u32 *
     if (threadIdx.x == 0 && tile_sums) tile_sums[blockIdx.x] = total;
 }
 
+// One block walks up to a few tiles with a running carry: one launch instead of tile scan + scan of the tile sums + add
+// (the block counts of a 50 Mbp input are 6104 values: 4 launches, ~11 us, for microseconds of work).
+__global__ void __launch_bounds__(KC_FE_THREADS) kc_scan_walk_kernel(const u32 *in, u32 *out, u64 n, u32 *sum) {
+    __shared__ u32 sw[8];
+    u32 carry = 0;
+    for (u64 t0 = 0; t0 < n; t0 += 1024) {
+        const u64 base = t0 + (u64) threadIdx.x * 4;
+        u32 v[4], c = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = base + j < n ? in[base + j] : 0;
+            c += v[j];
+        }
+        u32 total;
+        u32 p = kc_block_exclusive_scan_256(c, &total, sw) + carry;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (base + j < n) out[base + j] = p;
+            p += v[j];
+        }
+        carry += total;
+        __syncthreads();  // sw is reused by the next tile
+    }
+    if (threadIdx.x == 0 && sum) *sum = carry;
+}
+
 __global__ void __launch_bounds__(KC_FE_THREADS) kc_scan_add_kernel(u32 *out, u64 n, const u32 *tile_offsets) {
     u64 base = (u64) blockIdx.x * 1024 + (u64) threadIdx.x * 4;
     u32 o = tile_offsets[blockIdx.x];
@@ -283,9 +309,9 @@ struct CudaExec {
   private:
     u32 scan_rec(const u32 *in, u32 *out, u64 n, bool want_total) {
         u64 tiles = kc_div_up(n, 1024);
-        if (tiles == 1) {
+        if (tiles <= 8) {
             u32 *sum = arena->alloc<u32>(1);
-            kc_scan_tile_kernel<<<1, KC_FE_THREADS, 0, stream>>>(in, out, n, sum);
+            kc_scan_walk_kernel<<<1, KC_FE_THREADS, 0, stream>>>(in, out, n, sum);
             ++launches;
             KC_CUDA(cudaGetLastError());
             return want_total ? read(sum) : 0;

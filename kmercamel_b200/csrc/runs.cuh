@@ -11,26 +11,31 @@
 
 #ifdef __CUDACC__
 
-static const int KC_RUN_PER_THREAD = 32;  // one word of the bit array
+static const int KC_RUN_WORDS = 4;                          // consecutive words of the bit array per thread
+static const int KC_RUN_PER_THREAD = 32 * KC_RUN_WORDS;
 static const int KC_RUN_TILE = 256 * KC_RUN_PER_THREAD;
 
-// The thread's 32 flags (bit i = position base + i) and the flags just before and after them.  The bit array has
-// one zero word of padding at the end.
-KC_D void kc_runs_load(const u32 *flags, u64 word, u32 &f, u32 &prev, u32 &next) {
-    f = flags[word];
-    prev = word ? flags[word - 1] >> 31 : 0u;
-    next = flags[word + 1] & 1u;
+// The thread's KC_RUN_WORDS x 32 flags (bit i of f[j] = position 32 (word + j) + i) and the flags just before and after them.  The
+// bit array has one zero word of padding at the end.
+KC_D void kc_runs_load(const u32 *flags, u64 word, u64 n_words, u32 (&f)[KC_RUN_WORDS], u32 &prev, u32 &next) {
+#pragma unroll
+    for (int j = 0; j < KC_RUN_WORDS; ++j) f[j] = word + j < n_words ? flags[word + j] : 0u;
+    prev = word && word <= n_words ? flags[word - 1] >> 31 : 0u;
+    next = word + KC_RUN_WORDS <= n_words ? flags[word + KC_RUN_WORDS] & 1u : 0u;
 }
+
+// starts / ends of runs inside word j, given the last flag before it and the first one after it
+KC_D u32 kc_runs_starts(u32 f, u32 prev) { return f & ~((f << 1) | prev); }
+KC_D u32 kc_runs_ends(u32 f, u32 next) { return f & ~((f >> 1) | (next << 31)); }
 
 __global__ void __launch_bounds__(256) kc_runs_count_kernel(const u32 *flags, u64 n_words, u32 *block_counts, kc_ull *total_runs) {
     __shared__ u32 sw[8];
-    const u64 word = (u64) blockIdx.x * 256 + threadIdx.x;
+    const u64 word = ((u64) blockIdx.x * 256 + threadIdx.x) * KC_RUN_WORDS;
+    u32 f[KC_RUN_WORDS], prev, next;
+    kc_runs_load(flags, word, n_words, f, prev, next);
     u32 c = 0;
-    if (word < n_words) {
-        u32 f, prev, next;
-        kc_runs_load(flags, word, f, prev, next);
-        c = __popc(f & ~((f << 1) | prev));
-    }
+#pragma unroll
+    for (int j = 0; j < KC_RUN_WORDS; ++j) c += __popc(kc_runs_starts(f[j], j ? f[j - 1] >> 31 : prev));
     u32 total;
     kc_block_exclusive_scan<256>(c, &total, sw);
     if (threadIdx.x == 0) {
@@ -42,26 +47,35 @@ __global__ void __launch_bounds__(256) kc_runs_count_kernel(const u32 *flags, u6
 // rec_off[r] = END position of the first window of run r, rec_len[r] = END position of its last window.
 __global__ void __launch_bounds__(256) kc_runs_emit_kernel(const u32 *flags, u64 n_words, const u32 *block_offsets, u64 *rec_off, u64 *rec_len) {
     __shared__ u32 sw[8];
-    const u64 word = (u64) blockIdx.x * 256 + threadIdx.x;
-    const u64 base = word * 32;
-    u32 f = 0, prev = 0, next = 0;
-    if (word < n_words) kc_runs_load(flags, word, f, prev, next);
-    const u32 starts = f & ~((f << 1) | prev);
-    const u32 ends = f & ~((f >> 1) | (next << 31));
+    const u64 word = ((u64) blockIdx.x * 256 + threadIdx.x) * KC_RUN_WORDS;
+    u32 f[KC_RUN_WORDS], prev, next;
+    kc_runs_load(flags, word, n_words, f, prev, next);
+    u32 c = 0;
+#pragma unroll
+    for (int j = 0; j < KC_RUN_WORDS; ++j) c += __popc(kc_runs_starts(f[j], j ? f[j - 1] >> 31 : prev));
     u32 total;
-    const u32 before = kc_block_exclusive_scan<256>(__popc(starts), &total, sw) + block_offsets[blockIdx.x];
-    u32 s = starts;
-    u32 r = before;
-    while (s) {
-        const int i = __ffs(s) - 1;
-        s &= s - 1;
-        rec_off[r++] = base + i;
-    }
-    u32 e = ends;
-    while (e) {
-        const int i = __ffs(e) - 1;
-        e &= e - 1;
-        rec_len[before + __popc(starts & (0xFFFFFFFFu >> (31 - i))) - 1] = base + i;
+    u32 before = kc_block_exclusive_scan<256>(c, &total, sw) + block_offsets[blockIdx.x];
+    if (c == 0 && (f[0] | f[1] | f[2] | f[3]) == 0) return;
+    static_assert(KC_RUN_WORDS == 4, "the early exit above spells the words out");
+#pragma unroll
+    for (int j = 0; j < KC_RUN_WORDS; ++j) {
+        const u64 base = (word + j) * 32;
+        const u32 starts = kc_runs_starts(f[j], j ? f[j - 1] >> 31 : prev);
+        const u32 ends = kc_runs_ends(f[j], j + 1 < KC_RUN_WORDS ? f[j + 1] & 1u : next);
+        u32 s = starts;
+        u32 r = before;
+        while (s) {
+            const int i = __ffs(s) - 1;
+            s &= s - 1;
+            rec_off[r++] = base + i;
+        }
+        u32 e = ends;
+        while (e) {  // the run of an end at bit i: (starts at positions <= its position) - 1
+            const int i = __ffs(e) - 1;
+            e &= e - 1;
+            rec_len[before + __popc(starts & (0xFFFFFFFFu >> (31 - i))) - 1] = base + i;
+        }
+        before += __popc(starts);
     }
 }
 
