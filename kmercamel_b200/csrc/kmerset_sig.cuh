@@ -458,22 +458,37 @@ __global__ void __launch_bounds__(SigCfg<L>::THREADS, SigCfg<L>::MIN_CTAS) kc_si
         const u64 mine = w[NW - 1];
         const u64 ms = sh ? mine << (64 - sh) : 0ULL;  // the bases behind the first window, left-aligned
         if constexpr (L == 1) {
-            u64 f = (sh ? (mine >> sh) | (w[0] << (64 - sh)) : mine) & kmask.w[0];
-            const u64 tmask = kmask.w[0] << lsh;
-            u64 ral = UNI ? 0ULL : ~kc_reverse_symbols64_brev(f) & tmask;  // reverse complement, left-aligned
+            // The record's k + 7 bases (first window + the 7 bases behind it) as one 96-bit value F2 : F1 : F0, right-aligned, and
+            // their reverse complement R2 : R1 : R0: window t is bits [14 - 2 t, 14 - 2 t + 2 k) of F and its reverse complement bits
+            // [2 t, 2 t + 2 k) of R — two funnel shifts by constants and one mask per strand and window, where rolling both strands
+            // (extract the next base, shift, or, mask; shift back into place to compare) cost twice that.  k >= 26 here (kc_sig_plan):
+            // the low word of a k-mer needs no mask.
+            const u64 f0 = (sh ? (mine >> sh) | (w[0] << (64 - sh)) : mine) & kmask.w[0];
+            const u64 lo64 = (f0 << 14) | (ms >> 50);
+            const u32 F0 = (u32) lo64, F1 = (u32) (lo64 >> 32), F2 = (u32) (f0 >> 50);
+            const u32 mh = (u32) (kmask.w[0] >> 32);
+            u32 R0 = 0, R1 = 0, R2 = 0;
+            if (!UNI) {
+                const u32 V0 = kc_revcomp16(F2), V1 = kc_revcomp16(F1), V2 = kc_revcomp16(F0);  // the 48 symbols reversed and complemented
+                const int q = 96 - 2 * (k + 7);                                               // ... and right-aligned again
+                R0 = __funnelshift_r(V0, V1, q);
+                R1 = __funnelshift_r(V1, V2, q);
+                R2 = V2 >> q;
+            }
 #pragma unroll
             for (int t = 0; t < P; ++t) {
-                if (t) {
-                    const u64 c = (ms >> (64 - 2 * t)) & 3ULL;
-                    f = ((f << 2) | c) & kmask.w[0];
-                    if (!UNI) ral = ((ral >> 2) | ((3ULL ^ c) << 62)) & tmask;
+                const int sf = 14 - 2 * t, sr = 2 * t;
+                u32 cl = sf ? __funnelshift_r(F0, F1, sf) : F0;
+                u32 ch = (sf ? __funnelshift_r(F1, F2, sf) : F1) & mh;
+                if (!UNI) {
+                    const u32 rl = sr ? __funnelshift_r(R0, R1, sr) : R0;
+                    const u32 rh = (sr ? __funnelshift_r(R1, R2, sr) : R1) & mh;
+                    const bool take_r = (((u64) rh << 32) | rl) < (((u64) ch << 32) | cl);
+                    cl = take_r ? rl : cl;
+                    ch = take_r ? rh : ch;
                 }
                 KWord<1> canon;
-                canon.w[0] = f;
-                if (!UNI) {
-                    const u64 rr = ral >> lsh;
-                    canon.w[0] = f < rr ? f : rr;
-                }
+                canon.w[0] = ((u64) ch << 32) | cl;
                 const u32 slot = (u32) t * RC + r;
                 h1[t] = kc_sig_hash<1>(canon) >> (32 - Cfg::T1_BITS);
                 if ((u32) t < len) {
