@@ -438,9 +438,6 @@ __global__ void __launch_bounds__(SigCfg<L>::THREADS, SigCfg<L>::MIN_CTAS) kc_si
     u32 *T2 = sp + KC_SIG_SLOTS;                                // [T2N]
     u16 *T1 = reinterpret_cast<u16 *>(T2 + T2N);                // [T1N]
     const KWord<L> kmask = KWord<L>::low_mask(2 * k);
-    const int top = 2 * (k - 1);
-    const int top_limb = top >> 6, top_off = top & 63;
-    const int lsh = 64 * L - 2 * k;  // left-aligned <-> right-aligned
     u32 kept = 0;
     const u32 stride = gridDim.x;
     u32 b = blockIdx.x;
@@ -498,35 +495,41 @@ __global__ void __launch_bounds__(SigCfg<L>::THREADS, SigCfg<L>::MIN_CTAS) kc_si
                 }
             }
         } else {
+            // the same with L + 1 limbs: F = the k + 7 bases right-aligned, R = their reverse complement
             KWord<L> f;
 #pragma unroll
             for (int l = 0; l < L; ++l) f.w[l] = sh ? (w[NW - 1 - l] >> sh) | (w[NW - 2 - l] << (64 - sh)) : w[NW - 1 - l];
             f = f & kmask;
-            KWord<L> rv;
+            KWord<L + 1> F, R;
+            F.w[0] = (f.w[0] << 14) | (ms >> 50);
 #pragma unroll
-            for (int i = 0; i < L; ++i) rv.w[i] = ~kc_reverse_symbols64_brev(f.w[L - 1 - i]);
-            rv = rv.shr(lsh);
+            for (int i = 1; i < L; ++i) F.w[i] = (f.w[i] << 14) | (f.w[i - 1] >> 50);
+            F.w[L] = f.w[L - 1] >> 50;
+            if (!UNI) {
+#pragma unroll
+                for (int i = 0; i <= L; ++i) R.w[i] = ~kc_reverse_symbols64_brev(F.w[L - i]);
+                R = R.shr(64 * (L + 1) - 2 * (k + 7));
+            }
 #pragma unroll
             for (int t = 0; t < P; ++t) {
-                if ((u32) t < len) {
-                    if (t) {  // roll both strands by one base
-                        const u64 c = (ms >> (64 - 2 * t)) & 3ULL;
-                        f = f.shl(2);
-                        f.w[0] |= c;
-                        f = f & kmask;
-                        rv = rv.shr(2);
+                const int sf = 14 - 2 * t, sr = 2 * t;
+                KWord<L> canon;
 #pragma unroll
-                        for (int i = 0; i < L; ++i)
-                            if (i == top_limb) rv.w[i] |= (3ULL ^ c) << top_off;
-                    }
-                    const KWord<L> canon = (UNI || f < rv) ? f : rv;
-                    const u32 slot = (u32) t * RC + r;
+                for (int j = 0; j < L; ++j) canon.w[j] = sf ? (F.w[j] >> sf) | (F.w[j + 1] << (64 - sf)) : F.w[j];
+                canon = canon & kmask;
+                if (!UNI) {
+                    KWord<L> rt;
+#pragma unroll
+                    for (int j = 0; j < L; ++j) rt.w[j] = sr ? (R.w[j] >> sr) | (R.w[j + 1] << (64 - sr)) : R.w[j];
+                    rt = rt & kmask;
+                    if (rt < canon) canon = rt;
+                }
+                const u32 slot = (u32) t * RC + r;
+                h1[t] = kc_sig_hash<L>(canon) >> (32 - Cfg::T1_BITS);
+                if ((u32) t < len) {
                     sk[slot] = canon;
                     sp[slot] = pos + (u32) t;
-                    h1[t] = kc_sig_hash<L>(canon) >> (32 - Cfg::T1_BITS);
                     T1[h1[t]] = (u16) slot;
-                } else {
-                    h1[t] = 0;
                 }
             }
         }
