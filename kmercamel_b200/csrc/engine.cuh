@@ -569,6 +569,9 @@ template <class Exec, int L> struct Engine {
         if (lower_bound && n_edges) commit_lower_bound();
         stats.edges += n_edges;
         stats.bans += n_bans;
+        if (std::getenv("KC_TRACE"))
+            std::fprintf(stderr, "[kc_trace] level d=%d: free ends %llu + %llu, groups %llu, edges %llu, bans %u\n", d, (unsigned long long) ns, (unsigned long long) np,
+                         (unsigned long long) n_groups, (unsigned long long) n_edges, n_bans);
         // clear ban flags for the next level
         if (n_bans) {
             u8 *bf = ban_flag;
