@@ -516,7 +516,7 @@ def main():
                                              "inputs read once + outputs written once, declared by the library at launch",
                     "share_of_step": d["ms"] / prof_ms,
                     "limiter": ("instruction issue, not HBM: the kernel re-creates the k-mers from 2-bit code words instead of moving them "
-                                "(ncu profiles/r02m_full_ncu.md: DRAM 5-9 % of peak, issue slots 50-61 % busy); `traffic` = measured DRAM bytes per launch")
+                                "(ncu profiles/r02z_final_ncu.md: DRAM 5-9 % of peak, SM throughput 53-54 %); `traffic` = measured DRAM bytes per launch")
                                if sig_path else None}
         if sig_path:
             roofline["per_kernel_8d"] = {c: {"algorithmic_bytes": alg_8d[c], "ms": prof[c]["ms"] / max(prof[c]["launches"], 1),
