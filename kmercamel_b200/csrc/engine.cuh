@@ -236,8 +236,9 @@ template <int L> struct SimulatePairFn {
 #ifdef __CUDACC__
 #include <cooperative_groups.h>
 __global__ void __launch_bounds__(256) kc_doubling_kernel(u32 *jump_a, u32 *jump_b, u32 *fin_a, u32 *fin_b, u64 *max_a, u64 *max_b, u32 ne, int rounds,
-                                                          u32 *active /*[3], zeroed*/) {
+                                                          u32 *active /*[3], zeroed*/, const u32 *ne_dev /* non-null: the slot count lives on the device, ne is its upper bound */) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    if (ne_dev) ne = *ne_dev;
     u32 *ja = jump_a, *jb = jump_b, *fa = fin_a, *fb = fin_b;
     u64 *ma = max_a, *mb = max_b;
     const u32 stride = gridDim.x * blockDim.x;
@@ -297,6 +298,7 @@ template <class Exec, int L> struct Engine {
     bool strict;
     bool lower_bound;
     bool use_small = true;      // hand the tail of the level loop to the single-CTA kernel (small_engine.cuh)
+    bool fast_levels = true;    // queue a whole level without host round trips and read its counts back once (run_level)
     int small_threads_opt = 0;  // 0 = by size; 256 / 512 (option "small_threads")
     EngineStats stats;
 
@@ -329,16 +331,20 @@ template <class Exec, int L> struct Engine {
         ban_i = ex.template alloc<u32>(BAN_CAP);
         ban_j = ex.template alloc<u32>(BAN_CAP);
         ban_ctr = ex.template alloc<u32>(4);
-        ex.fill_bytes(st.edge_from, 0xFF, N * 4);
-        ex.fill_bytes(st.edge_to, 0xFF, N * 4);
-        ex.fill_bytes(st.ovl, 0xFF, N);
-        ex.fill_bytes(ban_flag, 0, N);
-        ex.fill_bytes(ban_ctr, 0, 16);
+        // one kernel instead of five fills and a kernel: on a genome the stage is a dozen tiny operations, each ~2 us of stream time
         PathState s = st;
+        u8 *bf = ban_flag;
+        u32 *bc = ban_ctr;
         ex.for_each(N, [=] KC_HD_LAMBDA(u64 v) {
+            s.edge_from[v] = KC_NONE;
+            s.edge_to[v] = KC_NONE;
+            s.ovl[v] = 255;
+            bf[v] = 0;
             s.chain_head[v] = (u32) v;
             s.chain_tail[v] = (u32) v;
+            if (v < 4) bc[v] = 0;
         });
+        if (N < 4) ex.fill_bytes(ban_ctr, 0, 16);
         n_s = n_p = N;
     }
 
@@ -414,11 +420,11 @@ template <class Exec, int L> struct Engine {
             a.ban_cap = BAN_CAP;
             a.d_start = d;
             a.strict = strict;
-            a.out = ex.template alloc<u32>(8 + 128 + 8);
-            ex.fill_bytes(a.out, 0, (8 + 128 + 8) * 4);
-            // level masks: [4] for the whole problem, then four words per end (two copies each: they travel with the live lists)
-            u32 *lvl_mask = ex.template alloc<u32>(4 + 8 * (n_s + n_p));
-            ex.fill_bytes(lvl_mask, 0, (4 + 4 * (n_s + n_p)) * 4);
+            // status words, then the level masks: [4] for the whole problem, then four words per end (two copies each: they travel with
+            // the live lists); one allocation, one fill
+            a.out = ex.template alloc<u32>(8 + 128 + 8 + 4 + 8 * (n_s + n_p));
+            u32 *lvl_mask = a.out + (8 + 128 + 8);
+            ex.fill_bytes(a.out, 0, (8 + 128 + 8 + 4 + 4 * (n_s + n_p)) * 4);
             a.lvl_mask_in = lvl_mask;
             a.end_mask_s_a = lvl_mask + 4;
             a.end_mask_p_a = a.end_mask_s_a + 4 * n_s;
@@ -467,6 +473,9 @@ template <class Exec, int L> struct Engine {
         if (n_s == 0 || n_p == 0) return;
         ++stats.levels_run;
         stats.tuples_sorted += nt;
+        if (!list_buf[0]) {  // two generations of each live list, allocated once (the lists only shrink): the next generation goes where the one before last was
+            for (int i = 0; i < 4; ++i) list_buf[i] = ex.template alloc<u32>(i < 2 ? n_s : n_p);
+        }
         size_t mark = ex.arena->mark();
         TW *T = ex.template alloc<TW>(nt);
         TW *T2 = ex.template alloc<TW>(nt);
@@ -497,19 +506,12 @@ template <class Exec, int L> struct Engine {
         // 3. active groups = positions where a prefix run starts right after a suffix run of the same key
         u32 *group_pstart = ex.template alloc<u32>(np);
         const TW *Tc = T;
-        u64 n_groups = ex.compact_if(
-            nt,
-            [=] KC_HD_LAMBDA(u64 i) {
-                if (i == 0) return false;
-                TW a = Tc[i - 1], b = Tc[i];
-                return tuple_is_prefix(b) && !tuple_is_prefix(a) && tuple_key(a) == tuple_key(b);
-            },
-            [=] KC_HD_LAMBDA(u64 i, u32 r) { group_pstart[r] = (u32) i; });
-        stats.groups += n_groups;
-        if (n_groups == 0) {
-            ex.arena->release(mark);
-            return;
-        }
+        auto is_group = [=] KC_HD_LAMBDA(u64 i) {
+            if (i == 0) return false;
+            TW a = Tc[i - 1], b = Tc[i];
+            return tuple_is_prefix(b) && !tuple_is_prefix(a) && tuple_key(a) == tuple_key(b);
+        };
+        auto put_group = [=] KC_HD_LAMBDA(u64 i, u32 r) { group_pstart[r] = (u32) i; };
         LevelCtx<L> c;
         c.nv = nv;
         c.st = st;
@@ -526,26 +528,160 @@ template <class Exec, int L> struct Engine {
         c.ban_j = ban_j;
         c.n_bans = 0;
         c.check_cycles = !lower_bound;
-
         u32 *new_tail = ex.template alloc<u32>(ns);
-        u64 n_edges = 0;
+        u32 *so = slot_of;
+        auto has_edge = [=] KC_HD_LAMBDA(u64 i) { return s.edge_from[ls ? ls[i] : (u32) i] != KC_NONE; };
+        auto put_edge = [=] KC_HD_LAMBDA(u64 i, u32 r) {
+            u32 x = ls ? ls[i] : (u32) i;
+            new_tail[r] = x;
+            so[x] = r;
+        };
+        u64 n_groups = 0, n_edges = 0;
         u32 n_bans = 0;
-        while (true) {
-            // 4. replay every pair of groups
-            c.n_bans = n_bans;
-            SimulatePairFn<L> sim{c, group_pstart};
-            ex.for_each(n_groups, sim, KP_SIMULATE);
-            // 5. edges of this level, one slot per edge
-            u32 *so = slot_of;
-            n_edges = ex.compact_if(
-                ns, [=] KC_HD_LAMBDA(u64 i) { return s.edge_from[ls ? ls[i] : (u32) i] != KC_NONE; },
-                [=] KC_HD_LAMBDA(u64 i, u32 r) {
-                    u32 x = ls ? ls[i] : (u32) i;
-                    new_tail[r] = x;
-                    so[x] = r;
-                });
-            if (n_edges == 0 || lower_bound) break;
-            if (validate_and_commit(c, new_tail, n_edges, n_bans)) break;
+        bool settled = false, lists_done = false, cycles_pending = false;
+#ifdef __CUDACC__
+        if constexpr (Exec::is_device) if (fast_levels && (lower_bound || doubling_blocks() > 0)) {
+            // The whole level queued WITHOUT a host round trip, as if it had no cycle (nearly every level): groups, replay, this level's
+            // edges, pointer doubling, commit (skipped on the device if a cycle turns up), the next live lists — every count stays on
+            // the device, kernels are launched for its upper bound and check it — then ONE read-back of {groups, edges, cycle slots, new
+            // list sizes}.  Five synchronising read-backs per level used to separate these steps: on a 126 k-node genome the stage was
+            // bound by them, not by work (profiles/r02k_path_stage_310M.json).  A cycle (rare) falls into the step-by-step loop below.
+            u64 *cells = ex.template alloc<u64>(6);  // groups, edges, new n_s, new n_p, cycle slots, min over the cycles of the max stamp
+            ex.fill_bytes(cells, 0, 40);
+            ex.fill_bytes(cells + 5, 0xFF, 8);
+            u32 *c_groups = reinterpret_cast<u32 *>(cells), *c_edges = reinterpret_cast<u32 *>(cells + 1);
+            u32 *c_ns = reinterpret_cast<u32 *>(cells + 2), *c_np = reinterpret_cast<u32 *>(cells + 3);
+            ex.compact_if_nosync(nt, is_group, put_group, c_groups);
+            {
+                SimulatePairFn<L> sim{c, group_pstart};
+                ex.for_each(ns < np ? ns : np, [=] __device__(u64 g) {
+                    if (g < *c_groups) sim(g);
+                }, KP_SIMULATE);
+            }
+            ex.compact_if_nosync(ns, has_edge, put_edge, c_edges);
+            bool queued = true;
+            u32 *jump_a = nullptr, *fin_a = nullptr;
+            u64 *max_a = nullptr;
+            if (!lower_bound) {
+                const u32 ub = (u32) ns;
+                jump_a = ex.template alloc<u32>(ub);
+                u32 *jump_b = ex.template alloc<u32>(ub);
+                fin_a = ex.template alloc<u32>(ub);
+                u32 *fin_b = ex.template alloc<u32>(ub);
+                max_a = ex.template alloc<u64>(ub);
+                u64 *max_b = ex.template alloc<u64>(ub);
+                const u64 *stp = stamp;
+                u32 *ja = jump_a, *fa = fin_a;
+                u64 *ma = max_a;
+                ex.for_each(ub, [=] __device__(u64 r) {
+                    if (r >= *c_edges) return;
+                    u32 x = new_tail[r];
+                    u32 t = s.chain_tail[s.edge_from[x]];
+                    bool cont = s.edge_from[t] != KC_NONE;
+                    ja[r] = cont ? so[t] : KC_NONE;
+                    fa[r] = t;
+                    ma[r] = stp[x];
+                }, KP_DOUBLING, (u64) ub * 36);
+                queued = doubling_fused(jump_a, jump_b, fin_a, fin_b, max_a, max_b, ub, kc_ceil_log2(ub) + 1, c_edges);
+                if (queued) {
+                    ex.for_each(ub, [=] __device__(u64 r) {
+                        if (r < *c_edges && ja[r] != KC_NONE) {
+                            atomicAdd((kc_ull *) &cells[4], (kc_ull) 1);
+                            atomicMin((kc_ull *) &cells[5], (kc_ull) ma[r]);
+                        }
+                    });
+                    ex.for_each(ub, [=] __device__(u64 r) {  // 7. commit the chain ends, unless a cycle was found
+                        if (r >= *c_edges || cells[4] != 0) return;
+                        u32 x = new_tail[r];
+                        u32 h = s.chain_head[x];
+                        if (s.edge_to[h] == KC_NONE) {
+                            u32 t = fa[r];
+                            s.chain_tail[h] = t;
+                            s.chain_head[t] = h;
+                        }
+                    }, KP_COMMIT, (u64) ub * 16);
+                }
+            }
+            if (queued) {
+                const u32 *src_s = live_s, *src_p = live_p;
+                u32 *dst_s = list_buf[list_gen], *dst_p = list_buf[2 + list_gen];
+                ex.compact_if_nosync(ns, [=] __device__(u64 i) { return s.edge_from[src_s ? src_s[i] : (u32) i] == KC_NONE; },
+                                     [=] __device__(u64 i, u32 r) { dst_s[r] = src_s ? src_s[i] : (u32) i; }, c_ns);
+                ex.compact_if_nosync(np, [=] __device__(u64 i) { return s.edge_to[src_p ? src_p[i] : (u32) i] == KC_NONE; },
+                                     [=] __device__(u64 i, u32 r) { dst_p[r] = src_p ? src_p[i] : (u32) i; }, c_np);
+                u64 h[5];
+                ex.read_n(cells, h, 5);
+                n_groups = h[0];
+                n_edges = h[1];
+                stats.groups += n_groups;
+                if (h[4] == 0) {  // no cycle: the level stands
+                    settled = true;
+                    if (n_edges) {
+                        live_s = dst_s;
+                        live_p = dst_p;
+                        list_gen ^= 1;
+                        n_s = h[2];
+                        n_p = h[3];
+                    }
+                    lists_done = true;
+                } else {  // ban the cycle closers (validate_and_commit's last step) and replay step by step
+                    const u64 *stp = stamp;
+                    const u32 *ja = jump_a;
+                    const u64 *ma = max_a;
+                    const bool only_first = strict;
+                    const NodeView<L> v = nv;
+                    const u8 *pr = prim;
+                    u32 *bi = ban_i, *bj = ban_j, *bc = ban_ctr;
+                    u8 *bf = ban_flag;
+                    const u32 cap = BAN_CAP;
+                    ex.for_each(n_edges, [=] __device__(u64 r) {
+                        if (ja[r] == KC_NONE) return;
+                        u32 x = new_tail[r];
+                        if (stp[x] != ma[r]) return;
+                        if (only_first && ma[r] != cells[5]) return;
+                        u32 y = s.edge_from[x];
+                        u32 pi = x, pj = y;
+                        if (!pr[x]) {
+                            pi = v.mirror(y);
+                            pj = v.mirror(x);
+                        }
+                        u32 slot = atomicAdd(bc, v.complements ? 2u : 1u);
+                        if (slot + 2 <= cap) {
+                            bi[slot] = pi;
+                            bj[slot] = pj;
+                            bf[pi] = 1;
+                            if (v.complements) {
+                                bi[slot + 1] = v.mirror(pj);
+                                bj[slot + 1] = v.mirror(pi);
+                                bf[v.mirror(pj)] = 1;
+                            }
+                        }
+                    });
+                    cycles_pending = true;
+                }
+            }
+        }
+#endif
+        if (!settled && !cycles_pending) {
+            n_groups = ex.compact_if(nt, is_group, put_group);
+            stats.groups += n_groups;
+        }
+        if (n_groups == 0) {
+            ex.arena->release(mark);
+            return;
+        }
+        while (!settled) {
+            if (!cycles_pending) {
+                // 4. replay every pair of groups
+                c.n_bans = n_bans;
+                SimulatePairFn<L> sim{c, group_pstart};
+                ex.for_each(n_groups, sim, KP_SIMULATE);
+                // 5. edges of this level, one slot per edge
+                n_edges = ex.compact_if(ns, has_edge, put_edge);
+                if (n_edges == 0 || lower_bound) break;
+                if (validate_and_commit(c, new_tail, n_edges, n_bans)) break;
+            }
+            cycles_pending = false;
             // 6. cycles found: bans were appended; undo this level's edges and replay
             ++stats.ban_rounds;
             n_bans = ex.read(ban_ctr);
@@ -582,11 +718,8 @@ template <class Exec, int L> struct Engine {
         ex.arena->release(mark);
         // 8. shrink the live lists.  Only a level that accepted edges changes them; the lists only ever shrink, so the new ones are
         //    compacted straight into buffers of the old size (one compaction per list instead of count + allocate + compact)
-        if (n_edges) {
+        if (n_edges && !lists_done) {
             const u32 *src_s = live_s, *src_p = live_p;
-            if (!list_buf[0]) {  // two generations of each list, allocated once: the next generation goes where the one before last was
-                for (int i = 0; i < 4; ++i) list_buf[i] = ex.template alloc<u32>(i < 2 ? ns : np);
-            }
             u32 *dst_s = list_buf[list_gen], *dst_p = list_buf[2 + list_gen];
             list_gen ^= 1;
             n_s = ex.compact_if(
@@ -602,7 +735,8 @@ template <class Exec, int L> struct Engine {
 
 #ifdef __CUDACC__
     // All rounds of the doubling in one cooperative launch (kc_doubling_kernel); false = not available, the caller loops over launches.
-    bool doubling_fused(u32 *jump_a, u32 *jump_b, u32 *fin_a, u32 *fin_b, u64 *max_a, u64 *max_b, u32 ne, int rounds) {
+    // co-resident blocks of kc_doubling_kernel on this device; 0 = no cooperative launch
+    static int doubling_blocks() {
         static KcDevOnce once;
         static int max_blocks[KC_MAX_DEVICES];
         const int dev = once.run([&](int dv) {
@@ -611,12 +745,16 @@ template <class Exec, int L> struct Engine {
             KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kc_doubling_kernel, 256, 0));
             max_blocks[dv] = coop ? per_sm * kc_sm_count(dv) : 0;
         });
-        if (max_blocks[dev] <= 0) return false;
+        return max_blocks[dev];
+    }
+    bool doubling_fused(u32 *jump_a, u32 *jump_b, u32 *fin_a, u32 *fin_b, u64 *max_a, u64 *max_b, u32 ne, int rounds, const u32 *ne_dev = nullptr) {
+        const int max_blocks_dev = doubling_blocks();
+        if (max_blocks_dev <= 0) return false;
         u32 *active = ex.template alloc<u32>(4);
         ex.fill_bytes(active, 0, 16);
         u32 blocks = (u32) kc_div_up((u64) ne, 256);
-        if (blocks > (u32) max_blocks[dev]) blocks = (u32) max_blocks[dev];
-        void *args[] = {&jump_a, &jump_b, &fin_a, &fin_b, &max_a, &max_b, &ne, &rounds, &active};
+        if (blocks > (u32) max_blocks_dev) blocks = (u32) max_blocks_dev;
+        void *args[] = {&jump_a, &jump_b, &fin_a, &fin_b, &max_a, &max_b, &ne, &rounds, &active, &ne_dev};
         typename Exec::Scope sc(ex, KP_DOUBLING, (u64) ne * 32 * 4);
         KC_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kc_doubling_kernel), dim3(blocks), dim3(256), args, 0, ex.stream));
         ++ex.launches;

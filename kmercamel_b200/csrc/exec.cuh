@@ -80,7 +80,8 @@ KC_D u32 kc_block_exclusive_scan_256(u32 v, u32 *total, u32 *smem_warp /*[8]*/) 
 static const int KC_CP_ITEMS = 4;                         // consecutive items per thread
 static const int KC_CP_TILE = KC_FE_THREADS * KC_CP_ITEMS;  // items per block
 
-template <typename Pred> __global__ void __launch_bounds__(KC_FE_THREADS) kc_compact_count_kernel(u64 n, Pred pred, u32 *block_counts) {
+template <typename Pred>
+__global__ void __launch_bounds__(KC_FE_THREADS) kc_compact_count_kernel(u64 n, Pred pred, u32 *block_counts, u32 *grand_total = nullptr) {
     __shared__ u32 sw[8];
     u64 base = (u64) blockIdx.x * KC_CP_TILE + (u64) threadIdx.x * KC_CP_ITEMS;
     u32 c = 0;
@@ -89,7 +90,10 @@ template <typename Pred> __global__ void __launch_bounds__(KC_FE_THREADS) kc_com
         if (base + j < n && pred(base + j)) ++c;
     u32 total;
     kc_block_exclusive_scan_256(c, &total, sw);
-    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+    if (threadIdx.x == 0) {
+        block_counts[blockIdx.x] = total;
+        if (grand_total && total) atomicAdd(grand_total, total);
+    }
 }
 
 template <typename Pred, typename Emit>
@@ -304,6 +308,24 @@ struct CudaExec {
         KC_CUDA(cudaGetLastError());
         arena->release(m);
         return total;
+    }
+
+    // The same without the synchronising read-back: the number of kept items is ADDED to *total_dev (device memory, zero on entry).
+    template <typename Pred, typename Emit> void compact_if_nosync(u64 n, Pred pred, Emit emit, u32 *total_dev, u64 bytes = 0) {
+        if (n == 0) return;
+        if (n >= 0xFFFFFFFFULL) KC_THROW(KC_ERR_TOO_LARGE, "compact_if over more than 2^32-1 items");
+        Scope sc(*this, KP_COMPACT, bytes);
+        size_t m = arena->mark();
+        u64 blocks = kc_div_up(n, KC_CP_TILE);
+        u32 *counts = arena->alloc<u32>(blocks);
+        kc_compact_count_kernel<<<(unsigned) blocks, KC_FE_THREADS, 0, stream>>>(n, pred, counts, total_dev);
+        ++launches;
+        KC_CUDA(cudaGetLastError());
+        scan_rec(counts, counts, blocks, false);
+        kc_compact_emit_kernel<<<(unsigned) blocks, KC_FE_THREADS, 0, stream>>>(n, pred, emit, counts);
+        ++launches;
+        KC_CUDA(cudaGetLastError());
+        arena->release(m);
     }
 
   private:

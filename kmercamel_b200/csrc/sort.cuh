@@ -44,6 +44,8 @@ KC_D u32 kc_upper_bound_u32(const u32 *a, u32 n, u32 v) {  // first index with a
     return lo;
 }
 
+__global__ void kc_sort_root_kernel(SortBucket *dst, SortBucket root) { *dst = root; }
+
 __global__ void kc_sort_prep_kernel(SortBucket *big, u32 nb, u32 cap, u32 tile, u32 *tile_count) {
     u32 b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
@@ -447,27 +449,34 @@ void kc_sort_impl(CudaExec &ex, KWord<L> *buf0, KWord<L> *buf1, u64 n, int key_b
     root.parity = 0;
     root.bits = 0;
     u32 nb = 0, n_small = 0, n_uniform = 0;
+    // the root bucket travels as a kernel argument (a copy from the stack + a stream synchronisation used to put it there)
     if (n <= cap) {
-        KC_CUDA(cudaMemcpyAsync(small, &root, sizeof(root), cudaMemcpyHostToDevice, st));
-        KC_CUDA(cudaStreamSynchronize(st));
+        kc_sort_root_kernel<<<1, 1, 0, st>>>(small, root);
         n_small = 1;
     } else if (root.rem == 0) {
-        KC_CUDA(cudaMemcpyAsync(uniform, &root, sizeof(root), cudaMemcpyHostToDevice, st));
-        KC_CUDA(cudaStreamSynchronize(st));
+        kc_sort_root_kernel<<<1, 1, 0, st>>>(uniform, root);
         n_uniform = 1;
     } else {
-        KC_CUDA(cudaMemcpyAsync(big_a, &root, sizeof(root), cudaMemcpyHostToDevice, st));
-        KC_CUDA(cudaStreamSynchronize(st));
+        kc_sort_root_kernel<<<1, 1, 0, st>>>(big_a, root);
         nb = 1;
     }
+    ++ex.launches;
     SortBucket *cur = big_a, *nxt = big_b;
     const u32 max_ctas = 148 * 8;
+    bool first_level = true;
     while (nb > 0) {
         kc_sort_prep_kernel<<<(unsigned) kc_div_up(nb, 256), 256, 0, st>>>(cur, nb, cap, Cfg::TILE, tile_count);
         ++ex.launches;
         ex.fill_bytes(tile_count + nb, 0, 4);
         u32 *tile_prefix = tile_count;  // scanned in place; entry nb becomes the total
-        u32 n_tiles = ex.exclusive_scan(tile_count, tile_prefix, nb + 1);
+        u32 n_tiles;
+        if (first_level) {  // one bucket: the host knows its tile count (kc_sort_prep_kernel's formula), no read-back
+            ex.exclusive_scan_nosync(tile_count, tile_prefix, nb + 1);
+            n_tiles = (u32) kc_div_up(n, (u64) Cfg::TILE);
+            first_level = false;
+        } else {
+            n_tiles = ex.exclusive_scan(tile_count, tile_prefix, nb + 1);
+        }
         ex.fill_bytes(hist, 0, (size_t) nb * 256 * 4);
         u32 tiles_per_cta = (u32) kc_div_up(n_tiles, max_ctas);
         u32 ctas = (u32) kc_div_up(n_tiles, tiles_per_cta);
