@@ -1,12 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
 export KC_GROUP_TIMEOUT_MS=60000
-for N in 8; do
+for N in ${KC_NS:-8}; do
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2952$N bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; echo "bench$N rc=$?"
 done
 python - <<'PY'
 import json
-for n in (8,):
+for n in (int(__import__("os").environ.get("KC_NS", "8")),):
     f=f"gpurun_out/bench_{n}gpu.json"
     try:
         lines=[l for l in open(f).read().strip().splitlines() if l.startswith("{")]
