@@ -164,7 +164,11 @@ struct EmitResult {
 // set_keys: sorted distinct (canonical when complements) k-mers, needed only for want_maxone.
 template <class Exec, int L>
 EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L> &nv, const PathState &st,
-                               const KWord<L> *set_keys, u64 n_set, bool want_maxone, u32 slice_index = 0, u32 n_slices = 1) {
+                               const KWord<L> *set_keys, u64 n_set, bool want_maxone, u32 slice_index = 0, u32 n_slices = 1, u64 total_ub = 0) {
+    // total_ub: an upper bound of the superstring length known to the caller (0 = none).  With it, a small problem (one-CTA list
+    // ranking, record nodes, whole superstring) is emitted WITHOUT reading the length back first: the kernels take the length and the
+    // printed strand from the device cell, the buffer and the launches are sized by the bound, and the one read-back comes after the
+    // last kernel is queued — the GPU does not idle through a host round trip in the middle of a 0.7 ms job.
     EmitResult res;
     const u64 N = nv.N;
     const int k = nv.k;
@@ -234,13 +238,21 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
             });
         }
     }
-    u64 info[4];
-    ex.read_n(cell, info, 4);
-    const u64 start = info[0];
-    if (start >= N) KC_THROW(KC_ERR_INTERNAL, "no start node: the path cover contains only cycles");
-    if (info[1] == 0) KC_THROW(KC_ERR_INTERNAL, "cycle in the final path cover");
-    const u64 total = info[2];
-    const u32 fin_start = (u32) info[3];
+    bool deferred = false;
+#ifdef __CUDACC__
+    if constexpr (Exec::is_device) deferred = ranked && total_ub && !ns.kmers && !want_maxone && n_slices == 1;
+#endif
+    const u64 *cellp = deferred ? cell : nullptr;  // deferred: the kernels below read the length and the printed strand from here
+    u64 info[4] = {0, 1, total_ub, 0};
+    if (!deferred) {
+        ex.read_n(cell, info, 4);
+        const u64 start = info[0];
+        if (start >= N) KC_THROW(KC_ERR_INTERNAL, "no start node: the path cover contains only cycles");
+        if (info[1] == 0) KC_THROW(KC_ERR_INTERNAL, "cycle in the final path cover");
+    }
+    const u64 total_h = info[2];  // deferred: the bound (sizes the buffer and the launches)
+    const u32 fin_start_h = (u32) info[3];
+    const u64 total = total_h;
     // results live below the scratch: release the scratch first, then allocate outputs, then re-reserve scratch
     // is not possible with a bump arena, so outputs are allocated after the scratch and the scratch is leaked
     // until the caller releases its own mark.
@@ -248,7 +260,9 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
     // multiples of 16, so the 16-byte stores below stay aligned); `ms` is biased so that ms[a] is superstring position a.
     if (n_slices > 1 && (ns.kmers || want_maxone)) KC_THROW(KC_ERR_ARG, "sliced emission is for record nodes without -M");
     const u64 s_begin = n_slices > 1 ? ((total / n_slices) * slice_index) & ~(u64) 15 : 0;
-    const u64 s_end = n_slices > 1 && slice_index + 1 < n_slices ? ((total / n_slices) * (slice_index + 1)) & ~(u64) 15 : total;
+    const u64 s_end_h = n_slices > 1 && slice_index + 1 < n_slices ? ((total / n_slices) * (slice_index + 1)) & ~(u64) 15 : total;
+    const u64 s_end = s_end_h;
+    const u32 fin_start = fin_start_h;
     u8 *ms_base = ex.template alloc<u8>(s_end - s_begin + 1);
     u8 *ms = ms_base - s_begin;
     res.ms = ms_base;
@@ -276,6 +290,9 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
         // on 50 MB; byte stores, not DRAM, were the bound).
         u32 *chunks = ex.template alloc<u32>(N + 1);
         ex.for_each(N + 1, [=] KC_HD_LAMBDA(u64 vv) {
+            const u64 total = cellp ? cellp[2] : total_h;
+            const u32 fin_start = cellp ? (u32) cellp[3] : fin_start_h;
+            const u64 s_end = cellp ? total : s_end_h;
             u32 c = 0;
             if (vv < N && fa[vv] == fin_start) {
                 u32 v = (u32) vv;
@@ -306,6 +323,9 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
 #endif
         if (!bounded) n_chunks = ex.exclusive_scan(chunks, chunks, N + 1);
         ex.for_each(N, [=] KC_HD_LAMBDA(u64 vv) {
+            const u64 total = cellp ? cellp[2] : total_h;
+            const u32 fin_start = cellp ? (u32) cellp[3] : fin_start_h;
+            const u64 s_end = cellp ? total : s_end_h;
             u32 v = (u32) vv;
             if (fa[v] != fin_start) return;
             u64 len = q.length(v);
@@ -318,6 +338,8 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
                 if (off + j >= s_begin && off + j < s_end) ms[off + j] = kc_letter(q.symbol(v, j), j < n_upper);
         }, KP_EMIT, N * 12);
         ex.for_each((u64) n_chunks * 256, [=] KC_HD_LAMBDA(u64 w) {
+            const u64 total = cellp ? cellp[2] : total_h;
+            const u64 s_end = cellp ? total : s_end_h;
             u32 chunk = (u32) (w >> 8), lane = (u32) (w & 255);
             if (chunk >= chunks[N]) return;  // chunks[N] = the exact number of chunks
             // node owning this chunk: last v with chunks[v] <= chunk (chunks[] is the exclusive prefix, N+1 entries)
@@ -421,6 +443,14 @@ EmitResult kc_emit_superstring(Exec &ex, const NodeSeq<L> &ns, const NodeView<L>
             const bool present = kmer_set_contains(set_keys, n_set, ix, x);
             mo[p] = present ? (u8) (c - ('a' - 'A')) : c;
         }, KP_MAXONE, 2 * total);
+    }
+    if (deferred) {  // the one read-back of the stage, after its last kernel was queued
+        ex.read_n(cell, info, 4);
+        if (info[0] >= N) KC_THROW(KC_ERR_INTERNAL, "no start node: the path cover contains only cycles");
+        if (info[1] == 0) KC_THROW(KC_ERR_INTERNAL, "cycle in the final path cover");
+        if (info[2] > total_ub) KC_THROW(KC_ERR_INTERNAL, "superstring longer than its bound");
+        res.length = info[2];
+        res.slice_len = info[2];
     }
     res.n_printed = nv.n;  // one strand: every node or its mirror
     (void) mark;

@@ -405,7 +405,8 @@ void run_pipeline(kc_ctx *ctx, CudaExec &ex, const DevInput &in, const kc_params
     }
     EmitResult er;
     try {
-        er = kc_emit_superstring<CudaExec, L>(ex, ns, nv, eng.st, uniq, U, p.want_maxone != 0, slice_index, n_slices);
+        // every character of the superstring is a character of some node: nodes are pieces of the input that overlap by < k
+        er = kc_emit_superstring<CudaExec, L>(ex, ns, nv, eng.st, uniq, U, p.want_maxone != 0, slice_index, n_slices, in.n_bytes + n_nodes * (u64) p.k + 16);
     } catch (const KcError &) {
         eng.check_small();  // a failed small-engine run is the cause, report that one
         throw;
