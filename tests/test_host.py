@@ -76,6 +76,52 @@ def test_frame_fasta_big_and_empty(spneumoniae_bytes):
     assert len(off) == 0
 
 
+def _fuzz_fasta(rng, n_rec, max_lines, widths, final_nl):
+    out = []
+    alphabet = np.frombuffer(b"ACGTacgtN>@+ ", dtype=np.uint8)
+    for r in range(n_rec):
+        hdr = b">" + (b"r%d" % r if rng.random() < 0.8 else b"") + (b" some comment" if rng.random() < 0.3 else b"") + (b"\tx" if rng.random() < 0.1 else b"")
+        out.append(hdr + b"\n")
+        for _ in range(int(rng.integers(0, max_lines + 1))):
+            line = bytes(rng.choice(alphabet, size=int(rng.choice(widths))))
+            if line[:1] in (b">", b"@", b"+"):
+                line = b"A" + line[1:]
+            out.append(line + b"\n")
+            if rng.random() < 0.1:
+                out.append(b"\n")
+    data = b"".join(out)
+    return data if final_nl or not data.endswith(b"\n") else data[:-1]
+
+
+def test_frame_fasta_parallel_path(golden, monkeypatch):
+    """Plain FASTA is framed by several threads (framing.cpp frame_plain_fasta_parallel; default for inputs >= 8 MB): same records
+    as the oracle's restatement of kseq_read whatever the thread count; FASTQ / '\\r' / stray-marker inputs are declined and take
+    the serial reader."""
+    rng = np.random.default_rng(5)
+    for it in range(150):
+        data = _fuzz_fasta(rng, int(rng.integers(1, 40)), int(rng.integers(0, 6)), [0, 1, 2, 5, 60, 80], bool(rng.random() < 0.7))
+        want = orc.frame_fasta(data)
+        for threads in ("2", "3", "8", "32"):
+            monkeypatch.setenv("KC_FRAME_THREADS", threads)
+            seq, off, ln = kb.frame_fasta(data)
+            assert [bytes(seq[int(o):int(o) + int(l)]) for o, l in zip(off, ln)] == want, (it, threads)
+            assert all(seq[int(o) + int(l)] == 10 for o, l in zip(off, ln)) and len(seq) == int(off[-1]) + int(ln[-1]) + 1
+    for name, g in golden["parser_cases"].items():
+        data = g["text"].encode()
+        for threads in ("2", "8"):
+            monkeypatch.setenv("KC_FRAME_THREADS", threads)
+            seq, off, ln = kb.frame_fasta(data)
+            assert [bytes(seq[int(o):int(o) + int(l)]) for o, l in zip(off, ln)] == orc.frame_fasta(data), name
+    # above the size threshold the parallel path is the default: identical bytes to the serial reader
+    big = _fuzz_fasta(rng, 60, 400, [80], True) * 10
+    assert len(big) > (8 << 20)
+    monkeypatch.setenv("KC_FRAME_THREADS", "1")
+    a = kb.frame_fasta(big)
+    monkeypatch.delenv("KC_FRAME_THREADS")
+    b = kb.frame_fasta(big)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and len(a[1]) == 600
+
+
 def test_synth_fasta_roundtrip():
     from kmercamel_b200 import synth
     recs = synth.random_genome_records(3, 205, 7)
